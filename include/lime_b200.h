@@ -1,0 +1,191 @@
+/*
+ * lime_b200.h — C ABI of liblime_b200.so: the B200 (sm_100a) implementation of LIME's scoring hot
+ * path (reference: seongeunryu/lime-cikm25).
+ *
+ * The reference is pure Python/PyTorch: its "FFI" for this path is the set of nn.Module forward
+ * calls on the path.  Each entry point below names the reference interface it replaces
+ * (file:line in the reference tree).  INTEGRATION.md shows the ctypes stub a maintainer would add
+ * to the reference's newsEncoders.py / userEncoders.py / util.py to bind them.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless its name starts with h_.  The caller owns all
+ *     memory (in this repo: torch tensors); the library never allocates or frees device memory.
+ *   - `stream` is a cudaStream_t passed as void*.  Calls enqueue work on it and return without
+ *     synchronising.
+ *   - Return value: 0 on success, non-zero on error; lime_last_error() describes the last error
+ *     raised on the calling thread.  There is no CPU fallback: without a CUDA device every compute
+ *     entry point fails.
+ *   - fp32 everywhere (the reference never enables TF32/autocast, config.py:218-219); ids int32 as
+ *     the reference's corpus arrays (corpus.py:361-368); masks one byte per element (torch.bool).
+ *   - Matrices are row-major with an explicit leading dimension (elements, not bytes).
+ */
+#ifndef LIME_B200_H_
+#define LIME_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIME_B200_ABI_VERSION 1
+
+/* Compile-time model geometry of the LIME-CROWN-CROWN configuration (config.py:54-91 defaults). */
+#define LIME_D        400   /* lime_output_dim == news_embedding_dim == attention_dim          */
+#define LIME_TOPIC    50    /* category_embedding_dim (topic representation width)             */
+#define LIME_TOPIC_LD 52    /* topic width padded to a multiple of 4 floats                    */
+#define LIME_CA_HEADS 10    /* CandidateAware_ClickedNewsAttention.num_heads, layers.py:22     */
+
+/* Row layout of the per-news vector cache (floats).  See DESIGN.md "HBM layout".               */
+#define LIME_HIST_LD   852  /* [ vc 0..399 | gw 400..799 | topic 800..851 ]                    */
+#define LIME_HIST_VC   0
+#define LIME_HIST_GW   400
+#define LIME_HIST_T    800
+#define LIME_CAND_LD   1720 /* [ w1 | w2 | w3 | scal(8) | tq 50x10 | qb 10 | pad 2 ]           */
+#define LIME_CAND_W    0
+#define LIME_CAND_SCAL 1200
+#define LIME_CAND_TQ   1208
+#define LIME_CAND_QB   1708
+#define LIME_CAND_NFOLD 1207 /* columns produced by the folded GEMM: w1,w2,w3 + 7 scalars       */
+#define LIME_HTAB_LD   800  /* per (freshness bucket, lifetime bucket): [ T | gwT ]            */
+#define LIME_CTAB_LD   1208 /* per bucket pair: [ w1T | w2T | w3T | scalT(8) ]                 */
+
+int         lime_abi_version(void);
+const char *lime_last_error(void);
+/* Number of CUDA devices visible; <= 0 means the product path cannot run. */
+int         lime_device_count(void);
+/* Kernels launched by this library on the calling thread since the last reset (bench.py's
+ * gpu_launches).  */
+int64_t     lime_launch_count(void);
+void        lime_launch_count_reset(void);
+
+/* ---- FreshnessEncoder.bucketize, newsEncoders.py:53-58 (bit-exact) --------------------------- */
+int lime_bucketize(const float *seconds, int64_t n, int num_buckets, int32_t *buckets, void *stream);
+
+/* ---- dense building blocks (torch.nn.Linear / F.linear on the path) --------------------------
+ * C[m, n] = act( A[m, :k] . W[n, :k]^T + bias[n] ) + residual[m, n]
+ * act: 0 none, 1 relu, 2 tanh.  bias / residual may be NULL.  k, lda, ldw must be multiples of 4
+ * and A, W 16-byte aligned (pad with zeros).                                                     */
+int lime_linear(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias,
+                const float *residual, int64_t ldr, float *C, int64_t ldc,
+                int64_t m, int n, int k, int act, void *stream);
+/* Same contract, operands rounded to bf16 and multiplied on the tcgen05 tensor cores with fp32
+ * accumulation in TMEM ("bf16 mode" of the north star; metrics-level parity).                    */
+int lime_linear_bf16(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias,
+                     const float *residual, int64_t ldr, float *C, int64_t ldc,
+                     int64_t m, int n, int k, int act, void *stream);
+/* Small general GEMM with arbitrary strides (weight folding, done once per checkpoint):
+ * C[i*ldc + j] = alpha * sum_k A[i*sam + k*sak] * B[k*sbk + j*sbn]                                */
+int lime_gemm_strided(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbk,
+                      int64_t sbn, float *C, int64_t ldc, int m, int n, int k, float alpha,
+                      void *stream);
+
+/* ---- newsEncoders.CROWN.forward pieces, newsEncoders.py:302-373 ------------------------------ */
+/* word_embedding(ids) + PositionalEncoding (:311-315, :806-828): out[r, :] = E[ids[r], :] + pe[r % T, :] */
+int lime_embed_pe(const float *E, int64_t vocab, const int32_t *ids, int64_t rows, int T, int d,
+                  const float *pe, float *out, void *stream);
+/* nn.MultiheadAttention core of the TransformerEncoderLayer (:244-247), no mask:
+ * qkv [n_news*T, 3*d] (q | k | v) -> ctx [n_news*T, d], softmax(q k^T / sqrt(d/nhead)) v per head.
+ * Supported: T in {32, 128}, d/nhead <= 32.                                                      */
+int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, void *stream);
+/* nn.LayerNorm over the last dim (eps as given). */
+int lime_layernorm(const float *x, int64_t ldx, const float *gamma, const float *beta, float *y,
+                   int64_t ldy, int64_t rows, int d, float eps, void *stream);
+/* LayerNorm of every token followed by the unmasked mean over the T tokens of a news (:317,:321):
+ * x [n_news*T, d] -> out[n, :d] (row stride ldo). */
+int lime_layernorm_meanpool(const float *x, const float *gamma, const float *beta, float *out,
+                            int64_t ldo, int64_t n_news, int T, int d, float eps, void *stream);
+/* category_affine(category_embedding(c) || subCategory_embedding(s)) (:340-342 and
+ * userEncoders.py:103-105,115-117): out[n, :50] (row stride ldo; columns 50..width-1 zeroed). */
+int lime_topic_rep(const float *cat_emb, const float *sub_emb, const float *W, const float *b,
+                   const int32_t *cat, const int32_t *sub, int64_t n, float *out, int64_t ldo,
+                   int width, void *stream);
+/* layers.Attention over the k intents (layers.py:285-300): pre = affine1(e) (before tanh),
+ * e [n, k, D] -> out [n, D] (row stride ldo) = sum_k softmax_k(w2 . tanh(pre_k)) e_k.             */
+int lime_intent_pool(const float *pre, const float *e, const float *w2, float *out, int64_t ldo,
+                     int64_t n, int k, int D, void *stream);
+/* similarity_compute + concat + feature_fusion (:297-300,:367-371):
+ * content[n] = [ title | (cos(title, body)+1)/2 * body | cat_emb[c] | sub_emb[s] ]  (row stride ldo) */
+int lime_content_fuse(const float *title, const float *body, const float *cat_emb,
+                      const float *sub_emb, const int32_t *cat, const int32_t *sub, int64_t n, int D,
+                      int cat_dim, int sub_dim, float *content, int64_t ldo, void *stream);
+/* FreshnessEncoder embedding concat for every (freshness bucket, lifetime bucket) pair (:78-81):
+ * out[bf*nb + bl] = [ Ef[bf] | El[bl] ]                                                           */
+int lime_bucket_pairs(const float *Ef, const float *El, int num_buckets, int dim, float *out,
+                      void *stream);
+
+/* small helpers used while folding weights */
+int lime_scale_rows(float *M, int64_t ld, const float *row_scale, float alpha, int rows, int cols,
+                    void *stream);                         /* M[i,:] *= alpha * row_scale[i] (NULL -> 1) */
+int lime_prefix_rows(float *M, int64_t ld, int rows, int cols, void *stream); /* inclusive prefix sum over rows */
+
+/* ---- userEncoders.CROWN.forward + RemainingLifetimeWeighting (eval, one candidate per sample) --
+ * Replaces, for a whole impression set at once, what compute_scores (util.py:88-112) obtains by
+ * calling Model.forward (model.py:151-187) on batches of (user, candidate) pairs:
+ *   CandidateAware_ClickedNewsAttention (layers.py:52-93) -> GraphSAGE mean aggregation
+ *   (userEncoders.py:121,151-157) -> candidate-query pooling (:158-171) -> lifetime-weighted dot
+ *   (util.py:23-49), on cached news vectors (the reference re-encodes 50 history news per pair).
+ * The reference's result depends on the runtime mini-batch size through GraphSAGE
+ * (SURVEY.md §8a row 10): a pair with global index g uses prefix length
+ *   P = (g >= tail_start) ? prefix_tail : prefix_main,    g = pair_index_base + local pair index.
+ */
+typedef struct {
+    /* per-news cache built by the Python host from the entry points above */
+    const float *hist_rows;     /* [news_num, LIME_HIST_LD]                                      */
+    const float *cand_rows;     /* [news_num, LIME_CAND_LD]                                      */
+    const float *hist_tab;      /* [nb*nb, LIME_HTAB_LD]                                         */
+    const float *cand_tab;      /* [nb*nb, LIME_CTAB_LD]                                         */
+    const float *gate_bias;     /* [LIME_D]  -log2(e) * gate_proj.bias                           */
+    const float *un_prefix;     /* [config.batch_size, LIME_D] prefix sums of lin_l(user_node_embedding) */
+    int32_t news_num;
+    int32_t num_buckets;
+    int32_t user_nodes;         /* config.batch_size (rows of user_node_embedding)               */
+    float   sigmoid_alpha;      /* config.sigmoid_scaling_alpha                                  */
+    float   penalty_beta;       /* config.penalty_scaling_beta                                   */
+    int32_t use_lifetime_weighting; /* config.use_remaining_lifetime_weighting                   */
+    int32_t use_expired_penalty;    /* config.use_expired_penalty                                */
+} LimeNewsCache;
+
+typedef struct {
+    /* impression-major inputs (dataset.py:192-227 layout, candidates flattened) */
+    const int32_t *hist_news;   /* [I, H] row index into the cache, padding = 0                  */
+    const uint8_t *hist_mask;   /* [I, H]                                                        */
+    const float   *hist_fresh;  /* [I, H] seconds                                                */
+    const float   *hist_life;   /* [I, H] seconds                                                */
+    const int32_t *cand_news;   /* [P]                                                           */
+    const float   *cand_fresh;  /* [P]                                                           */
+    const float   *cand_life;   /* [P]                                                           */
+    const float   *cand_remaining; /* [P] remaining lifetime handed to RemainingLifetimeWeighting, or
+                                      NULL: cand_life - cand_fresh (lifetime_type='user_topic',
+                                      util.py:103-104)                                             */
+    /* work units: consecutive candidates of one impression, at most tile_c each */
+    const int32_t *unit_imp;    /* [U] impression of the unit                                    */
+    const int32_t *unit_pair0;  /* [U] first (local) pair index                                  */
+    const int32_t *unit_count;  /* [U] number of candidates, 1..tile_c                           */
+    int32_t num_units;
+    int32_t max_history;        /* H                                                             */
+    int32_t tile_c;             /* capacity the unit list was built for                          */
+} LimeImpressions;
+
+int lime_score_impressions(const LimeNewsCache *cache, const LimeImpressions *imp,
+                           int64_t pair_index_base, int32_t prefix_main, int64_t tail_start,
+                           int32_t prefix_tail, float *scores, int32_t *work_counter,
+                           void *stream);
+/* Dynamic shared memory the scoring kernel needs for (H, tile_c); > 232448 means unsupported. */
+int64_t lime_score_smem_bytes(int32_t max_history, int32_t tile_c);
+
+/* ---- compute_scores' ranking (util.py:113-123) + evaluate.scoring (evaluate.py:32-89) ---------
+ * Per impression i with candidates cand_off[i]..cand_off[i+1]: stable descending rank (ties keep
+ * candidate order, -0.0 == 0.0), then AUC / MRR / nDCG@5 / nDCG@10 with y_score = 1/rank in fp64.
+ * ranks [P] int32 (may be NULL), metrics [I, 4] fp64.  Impressions without candidates get NaNs
+ * and are skipped by lime_metrics_reduce (evaluate.py:44-45).                                     */
+int lime_rank_metrics(const float *scores, const uint8_t *labels, const int64_t *cand_off,
+                      int64_t num_impressions, int32_t *ranks, double *metrics, void *stream);
+/* sums[0..3] = sum over valid impressions of the 4 metrics, sums[4] = number of valid impressions
+ * (deterministic fixed-order reduction; the caller divides, or all-reduces across ranks first).  */
+int lime_metrics_reduce(const double *metrics, int64_t num_impressions, double *sums, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIME_B200_H_ */

@@ -1,0 +1,77 @@
+// Shared device/host helpers for liblime_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "lime_b200.h"
+
+namespace lime {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+void count_launch();
+
+#define LIME_CHECK_ARG(cond, ...)                                                            \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            ::lime::set_error(__VA_ARGS__);                                                    \
+            return 1;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+// call after every kernel launch: picks up launch-configuration errors without synchronising
+#define LIME_LAUNCH_CHECK(name)                                                              \
+    do {                                                                                       \
+        ::lime::count_launch();                                                                \
+        cudaError_t e__ = cudaGetLastError();                                                  \
+        if (e__ != cudaSuccess) {                                                              \
+            ::lime::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));         \
+            return 2;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+#define LIME_CUDA(call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            ::lime::set_error("%s failed: %s", #call, cudaGetErrorString(e__));                \
+            return 3;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int num_sms();
+
+// ---- warp helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// FreshnessEncoder.bucketize (newsEncoders.py:53-58), bit-exact with the reference's fp32 op
+// sequence: clamp(min=1) -> log -> divide by fp32 log(86400) -> multiply by fp32(num_buckets/7)
+// -> truncate -> clamp(max=num_buckets-1).  The divisor is the CPU 0-dim tensor
+// torch.log(torch.tensor(86400.)) = 0x4135de2e; `scale` is (float)(num_buckets / 7.0) computed on
+// the host in double then rounded, as torch does for tensor * python-float.  No fast-math here.
+__device__ __forceinline__ int bucketize_seconds(float x, float scale, int num_buckets) {
+    x = fmaxf(x, 1.0f);
+    if (x != x) x = 1.0f;  // torch.clamp propagates NaN; a NaN age has no bucket -> treat as 1 s
+    const float log_day = __uint_as_float(0x4135de2eu);
+    float scaled = __fdiv_rn(logf(x), log_day);
+    float prod = __fmul_rn(scaled, scale);
+    long long b = (long long)prod;  // truncation toward zero, like Tensor.long()
+    if (b > num_buckets - 1) b = num_buckets - 1;
+    if (b < 0) b = 0;
+    return (int)b;
+}
+
+}  // namespace lime

@@ -1,0 +1,428 @@
+// Stage A glue kernels of the LIME/CROWN news encoder (sm_100a): everything in
+// newsEncoders.CROWN.forward (newsEncoders.py:302-373) and FreshnessEncoder (:53-83) that is not a
+// dense layer.  The dense layers are lime_linear / lime_linear_bf16.
+#include "common.cuh"
+
+namespace lime {
+
+// ---- FreshnessEncoder.bucketize ---------------------------------------------------------------
+__global__ void bucketize_kernel(const float *__restrict__ x, int64_t n, float scale, int nb,
+                                 int32_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = bucketize_seconds(x[i], scale, nb);
+}
+
+// ---- word embedding gather + positional encoding (newsEncoders.py:311-315, 822-828) ------------
+// one thread per 128-bit piece of an output row; the embedding row (d*4 bytes, 16-byte multiple for
+// d = 300) is read with one LDG.128 per thread, coalesced across the row.
+__global__ void __launch_bounds__(256)
+embed_pe_kernel(const float *__restrict__ E, int64_t vocab, const int32_t *__restrict__ ids,
+                int64_t rows, int T, int d4, const float *__restrict__ pe, float *__restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * d4) return;
+    const int64_t r = idx / d4;
+    const int q = (int)(idx - r * d4);
+    int64_t id = ids[r];
+    id = (id < 0 || id >= vocab) ? 0 : id;
+    const float4 e = reinterpret_cast<const float4 *>(E)[id * d4 + q];
+    const float4 p = reinterpret_cast<const float4 *>(pe)[(r % T) * d4 + q];
+    reinterpret_cast<float4 *>(out)[idx] = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+}
+
+// ---- multi-head self-attention core, no mask (nn.MultiheadAttention inside the encoder layer) ---
+// 128 threads: one query row per thread, G = 128/T heads of one news per block.  K and V of the
+// block's heads sit in shared memory (rows padded to 32 floats); every thread walks the same key j
+// at the same time, so all K/V reads are warp broadcasts.  Online softmax in chunks of 8 keys.
+template <int T>
+__global__ void __launch_bounds__(128)
+mha_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int nhead, int hd, float scale) {
+    constexpr int G = 128 / T;
+    constexpr int HP = 32;
+    __shared__ __align__(16) float Ks[G][T][HP];
+    __shared__ __align__(16) float Vs[G][T][HP];
+    const int64_t news = blockIdx.y;
+    const int head0 = blockIdx.x * G;
+    const int tid = threadIdx.x;
+    const int64_t ld = 3 * (int64_t)d;
+    const float *base = qkv + news * T * ld;
+
+    for (int idx = tid; idx < G * T * HP; idx += 128) {
+        const int e = idx % HP;
+        const int j = (idx / HP) % T;
+        const int g = idx / (HP * T);
+        const int head = head0 + g;
+        float kv = 0.f, vv = 0.f;
+        if (head < nhead && e < hd) {
+            kv = base[j * ld + d + head * hd + e];
+            vv = base[j * ld + 2 * d + head * hd + e];
+        }
+        Ks[g][j][e] = kv;
+        Vs[g][j][e] = vv;
+    }
+    __syncthreads();
+
+    const int g = tid / T;
+    const int i = tid - g * T;
+    const int head = head0 + g;
+    if (head >= nhead) return;
+    float q[HP], acc[HP];
+#pragma unroll
+    for (int e = 0; e < HP; ++e) {
+        q[e] = (e < hd) ? base[i * ld + head * hd + e] * scale : 0.0f;
+        acc[e] = 0.0f;
+    }
+    float m = -INFINITY, l = 0.0f;
+    for (int j0 = 0; j0 < T; j0 += 8) {
+        float s[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const float4 *kr = reinterpret_cast<const float4 *>(&Ks[g][j0 + jj][0]);
+            float a = 0.0f;
+#pragma unroll
+            for (int e4 = 0; e4 < HP / 4; ++e4) {
+                const float4 kk = kr[e4];
+                a = fmaf(q[4 * e4 + 0], kk.x, a);
+                a = fmaf(q[4 * e4 + 1], kk.y, a);
+                a = fmaf(q[4 * e4 + 2], kk.z, a);
+                a = fmaf(q[4 * e4 + 3], kk.w, a);
+            }
+            s[jj] = a;
+        }
+        float cm = s[0];
+#pragma unroll
+        for (int jj = 1; jj < 8; ++jj) cm = fmaxf(cm, s[jj]);
+        const float mn = fmaxf(m, cm);
+        const float corr = __expf(m - mn);
+        l *= corr;
+#pragma unroll
+        for (int e = 0; e < HP; ++e) acc[e] *= corr;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const float p = __expf(s[jj] - mn);
+            l += p;
+            const float4 *vr = reinterpret_cast<const float4 *>(&Vs[g][j0 + jj][0]);
+#pragma unroll
+            for (int e4 = 0; e4 < HP / 4; ++e4) {
+                const float4 vv = vr[e4];
+                acc[4 * e4 + 0] = fmaf(p, vv.x, acc[4 * e4 + 0]);
+                acc[4 * e4 + 1] = fmaf(p, vv.y, acc[4 * e4 + 1]);
+                acc[4 * e4 + 2] = fmaf(p, vv.z, acc[4 * e4 + 2]);
+                acc[4 * e4 + 3] = fmaf(p, vv.w, acc[4 * e4 + 3]);
+            }
+        }
+        m = mn;
+    }
+    const float inv = 1.0f / l;
+    float *o = ctx + (news * T + i) * (int64_t)d + head * hd;
+#pragma unroll
+    for (int e = 0; e < HP; ++e)
+        if (e < hd) o[e] = acc[e] * inv;
+}
+
+// ---- LayerNorm (two-pass, like ATen) ------------------------------------------------------------
+constexpr int kLnMaxPerLane = 16;   // d <= 512
+
+__device__ __forceinline__ void ln_row(const float *__restrict__ x, int d, int lane, float eps,
+                                       const float *__restrict__ gamma, const float *__restrict__ beta,
+                                       float (&y)[kLnMaxPerLane]) {
+    float v[kLnMaxPerLane];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = (c < d) ? x[c] : 0.0f;
+        s += v[i];
+    }
+    const float mu = warp_sum(s) / (float)d;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        const float t = (c < d) ? (v[i] - mu) : 0.0f;
+        q = fmaf(t, t, q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        y[i] = (c < d) ? fmaf((v[i] - mu) * rstd, gamma[c], beta[c]) : 0.0f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float *__restrict__ x, int64_t ldx, const float *__restrict__ gamma,
+                 const float *__restrict__ beta, float *__restrict__ y, int64_t ldy, int64_t rows,
+                 int d, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    float o[kLnMaxPerLane];
+    ln_row(x + r * ldx, d, lane, eps, gamma, beta, o);
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        if (c < d) y[r * ldy + c] = o[i];
+    }
+}
+
+// LayerNorm of every token + unmasked mean over the T tokens (newsEncoders.py:317,321)
+__global__ void __launch_bounds__(256)
+layernorm_meanpool_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
+                          const float *__restrict__ beta, float *__restrict__ out, int64_t ldo, int T,
+                          int d, float eps) {
+    __shared__ float part[8][kLnMaxPerLane * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t news = blockIdx.x;
+    float acc[kLnMaxPerLane];
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) acc[i] = 0.0f;
+    for (int t = warp; t < T; t += 8) {
+        float o[kLnMaxPerLane];
+        ln_row(x + (news * T + t) * (int64_t)d, d, lane, eps, gamma, beta, o);
+#pragma unroll
+        for (int i = 0; i < kLnMaxPerLane; ++i) acc[i] += o[i];
+    }
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) part[warp][lane + 32 * i] = acc[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += 256) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += part[w][c];
+        out[news * ldo + c] = s / (float)T;
+    }
+}
+
+// ---- topic representation: category_affine(cat_emb[c] || sub_emb[s]) --------------------------
+__global__ void __launch_bounds__(64)
+topic_rep_kernel(const float *__restrict__ cat_emb, const float *__restrict__ sub_emb,
+                 const float *__restrict__ W, const float *__restrict__ b,
+                 const int32_t *__restrict__ cat, const int32_t *__restrict__ sub, int64_t n,
+                 float *__restrict__ out, int64_t ldo, int width) {
+    __shared__ float in[2 * LIME_TOPIC];
+    const int64_t i = blockIdx.x;
+    const int t = threadIdx.x;
+    if (t < LIME_TOPIC) {
+        in[t] = cat_emb[(int64_t)cat[i] * LIME_TOPIC + t];
+        in[LIME_TOPIC + t] = sub_emb[(int64_t)sub[i] * LIME_TOPIC + t];
+    }
+    __syncthreads();
+    if (t < LIME_TOPIC) {
+        float a = b[t];
+        const float *w = W + t * 2 * LIME_TOPIC;
+#pragma unroll 10
+        for (int k = 0; k < 2 * LIME_TOPIC; ++k) a = fmaf(w[k], in[k], a);
+        out[i * ldo + t] = a;
+    } else if (t < width) {
+        out[i * ldo + t] = 0.0f;
+    }
+}
+
+// ---- layers.Attention over the k intents (layers.py:285-300) -----------------------------------
+__global__ void __launch_bounds__(128)
+intent_pool_kernel(const float *__restrict__ pre, const float *__restrict__ e,
+                   const float *__restrict__ w2, float *__restrict__ out, int64_t ldo, int64_t n, int k,
+                   int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    float sc[8];
+    float m = -INFINITY;
+    for (int kk = 0; kk < k; ++kk) {
+        const float *p = pre + (i * k + kk) * (int64_t)D;
+        float a = 0.0f;
+        for (int c = lane; c < D; c += 32) a = fmaf(w2[c], tanhf(p[c]), a);
+        sc[kk] = warp_sum(a);
+        m = fmaxf(m, sc[kk]);
+    }
+    float l = 0.0f;
+    for (int kk = 0; kk < k; ++kk) {
+        sc[kk] = expf(sc[kk] - m);
+        l += sc[kk];
+    }
+    for (int c = lane; c < D; c += 32) {
+        float a = 0.0f;
+        for (int kk = 0; kk < k; ++kk) a = fmaf(sc[kk] / l, e[(i * k + kk) * (int64_t)D + c], a);
+        out[i * ldo + c] = a;
+    }
+}
+
+// ---- cosine gate + concat + feature fusion (newsEncoders.py:297-300, 367-371, 221-225) ----------
+__global__ void __launch_bounds__(128)
+content_fuse_kernel(const float *__restrict__ title, const float *__restrict__ body,
+                    const float *__restrict__ cat_emb, const float *__restrict__ sub_emb,
+                    const int32_t *__restrict__ cat, const int32_t *__restrict__ sub, int64_t n, int D,
+                    int cat_dim, int sub_dim, float *__restrict__ content, int64_t ldo) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float *t = title + i * (int64_t)D;
+    const float *b = body + i * (int64_t)D;
+    float tb = 0.f, tt = 0.f, bb = 0.f;
+    for (int c = lane; c < D; c += 32) {
+        const float x = t[c], y = b[c];
+        tb = fmaf(x, y, tb);
+        tt = fmaf(x, x, tt);
+        bb = fmaf(y, y, bb);
+    }
+    tb = warp_sum(tb);
+    tt = warp_sum(tt);
+    bb = warp_sum(bb);
+    const float eps = 1e-8f;   // F.cosine_similarity default
+    const float cosv = tb / (fmaxf(sqrtf(tt), eps) * fmaxf(sqrtf(bb), eps));
+    const float sim = (cosv + 1.0f) / 2.0f;
+    float *o = content + i * ldo;
+    for (int c = lane; c < D; c += 32) {
+        o[c] = t[c];
+        o[D + c] = sim * b[c];
+    }
+    const float *ce = cat_emb + (int64_t)cat[i] * cat_dim;
+    const float *se = sub_emb + (int64_t)sub[i] * sub_dim;
+    for (int c = lane; c < cat_dim; c += 32) o[2 * D + c] = ce[c];
+    for (int c = lane; c < sub_dim; c += 32) o[2 * D + cat_dim + c] = se[c];
+}
+
+__global__ void bucket_pairs_kernel(const float *__restrict__ Ef, const float *__restrict__ El, int nb,
+                                    int dim, float *__restrict__ out) {
+    const int pair = blockIdx.x;
+    const int bf = pair / nb, bl = pair - bf * nb;
+    for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+        out[(int64_t)pair * 2 * dim + c] = Ef[(int64_t)bf * dim + c];
+        out[(int64_t)pair * 2 * dim + dim + c] = El[(int64_t)bl * dim + c];
+    }
+}
+
+__global__ void scale_rows_kernel(float *M, int64_t ld, const float *__restrict__ rs, float alpha, int rows,
+                                  int cols) {
+    const int r = blockIdx.x;
+    const float s = alpha * (rs ? rs[r] : 1.0f);
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) M[(int64_t)r * ld + c] *= s;
+}
+
+__global__ void prefix_rows_kernel(float *M, int64_t ld, int rows, int cols) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float run = 0.0f;
+    for (int r = 0; r < rows; ++r) {
+        run += M[(int64_t)r * ld + c];
+        M[(int64_t)r * ld + c] = run;
+    }
+}
+
+}  // namespace lime
+
+using namespace lime;
+
+extern "C" int lime_bucketize(const float *seconds, int64_t n, int num_buckets, int32_t *buckets,
+                              void *stream) {
+    LIME_CHECK_ARG(seconds && buckets && num_buckets >= 1, "lime_bucketize: bad argument");
+    if (n <= 0) return 0;
+    const float scale = (float)((double)num_buckets / 7.0);
+    bucketize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(seconds, n, scale, num_buckets, buckets);
+    LIME_LAUNCH_CHECK("bucketize_kernel");
+    return 0;
+}
+
+extern "C" int lime_embed_pe(const float *E, int64_t vocab, const int32_t *ids, int64_t rows, int T,
+                             int d, const float *pe, float *out, void *stream) {
+    LIME_CHECK_ARG(E && ids && pe && out, "lime_embed_pe: null argument");
+    LIME_CHECK_ARG((d & 3) == 0 && T > 0 && vocab > 0, "lime_embed_pe: d=%d must be a multiple of 4", d);
+    if (rows <= 0) return 0;
+    const int64_t total = rows * (d / 4);
+    embed_pe_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(E, vocab, ids, rows, T, d / 4, pe, out);
+    LIME_LAUNCH_CHECK("embed_pe_kernel");
+    return 0;
+}
+
+extern "C" int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, void *stream) {
+    LIME_CHECK_ARG(qkv && ctx, "lime_mha: null argument");
+    LIME_CHECK_ARG(nhead > 0 && d % nhead == 0 && d / nhead <= 32, "lime_mha: head dim %d unsupported (<= 32)", nhead ? d / nhead : -1);
+    LIME_CHECK_ARG(T == 32 || T == 128, "lime_mha: T=%d unsupported (32 or 128)", T);
+    LIME_CHECK_ARG(n_news <= 65535, "lime_mha: at most 65535 news per call (got %lld)", (long long)n_news);
+    if (n_news <= 0) return 0;
+    const int hd = d / nhead;
+    const float scale = 1.0f / sqrtf((float)hd);
+    if (T == 32) {
+        dim3 grid((nhead + 3) / 4, (unsigned)n_news);
+        mha_kernel<32><<<grid, 128, 0, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale);
+    } else {
+        dim3 grid(nhead, (unsigned)n_news);
+        mha_kernel<128><<<grid, 128, 0, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale);
+    }
+    LIME_LAUNCH_CHECK("mha_kernel");
+    return 0;
+}
+
+extern "C" int lime_layernorm(const float *x, int64_t ldx, const float *gamma, const float *beta, float *y,
+                              int64_t ldy, int64_t rows, int d, float eps, void *stream) {
+    LIME_CHECK_ARG(x && gamma && beta && y, "lime_layernorm: null argument");
+    LIME_CHECK_ARG(d > 0 && d <= 32 * kLnMaxPerLane, "lime_layernorm: d=%d unsupported (<= 512)", d);
+    if (rows <= 0) return 0;
+    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(x, ldx, gamma, beta, y, ldy, rows, d, eps);
+    LIME_LAUNCH_CHECK("layernorm_kernel");
+    return 0;
+}
+
+extern "C" int lime_layernorm_meanpool(const float *x, const float *gamma, const float *beta, float *out,
+                                       int64_t ldo, int64_t n_news, int T, int d, float eps, void *stream) {
+    LIME_CHECK_ARG(x && gamma && beta && out, "lime_layernorm_meanpool: null argument");
+    LIME_CHECK_ARG(d > 0 && d <= 32 * kLnMaxPerLane && T > 0, "lime_layernorm_meanpool: d=%d unsupported", d);
+    if (n_news <= 0) return 0;
+    layernorm_meanpool_kernel<<<(unsigned)n_news, 256, 0, as_stream(stream)>>>(x, gamma, beta, out, ldo, T, d, eps);
+    LIME_LAUNCH_CHECK("layernorm_meanpool_kernel");
+    return 0;
+}
+
+extern "C" int lime_topic_rep(const float *cat_emb, const float *sub_emb, const float *W, const float *b,
+                              const int32_t *cat, const int32_t *sub, int64_t n, float *out, int64_t ldo,
+                              int width, void *stream) {
+    LIME_CHECK_ARG(cat_emb && sub_emb && W && b && cat && sub && out, "lime_topic_rep: null argument");
+    LIME_CHECK_ARG(width >= LIME_TOPIC && width <= 64, "lime_topic_rep: width %d not in [50,64]", width);
+    if (n <= 0) return 0;
+    topic_rep_kernel<<<(unsigned)n, 64, 0, as_stream(stream)>>>(cat_emb, sub_emb, W, b, cat, sub, n, out, ldo, width);
+    LIME_LAUNCH_CHECK("topic_rep_kernel");
+    return 0;
+}
+
+extern "C" int lime_intent_pool(const float *pre, const float *e, const float *w2, float *out, int64_t ldo,
+                                int64_t n, int k, int D, void *stream) {
+    LIME_CHECK_ARG(pre && e && w2 && out, "lime_intent_pool: null argument");
+    LIME_CHECK_ARG(k >= 1 && k <= 8, "lime_intent_pool: k=%d unsupported (1..8)", k);
+    if (n <= 0) return 0;
+    intent_pool_kernel<<<(unsigned)((n + 3) / 4), 128, 0, as_stream(stream)>>>(pre, e, w2, out, ldo, n, k, D);
+    LIME_LAUNCH_CHECK("intent_pool_kernel");
+    return 0;
+}
+
+extern "C" int lime_content_fuse(const float *title, const float *body, const float *cat_emb,
+                                 const float *sub_emb, const int32_t *cat, const int32_t *sub, int64_t n,
+                                 int D, int cat_dim, int sub_dim, float *content, int64_t ldo, void *stream) {
+    LIME_CHECK_ARG(title && body && cat_emb && sub_emb && cat && sub && content, "lime_content_fuse: null argument");
+    if (n <= 0) return 0;
+    content_fuse_kernel<<<(unsigned)((n + 3) / 4), 128, 0, as_stream(stream)>>>(title, body, cat_emb, sub_emb, cat, sub, n, D, cat_dim, sub_dim, content, ldo);
+    LIME_LAUNCH_CHECK("content_fuse_kernel");
+    return 0;
+}
+
+extern "C" int lime_bucket_pairs(const float *Ef, const float *El, int num_buckets, int dim, float *out,
+                                 void *stream) {
+    LIME_CHECK_ARG(Ef && El && out && num_buckets >= 1 && dim >= 1, "lime_bucket_pairs: bad argument");
+    bucket_pairs_kernel<<<num_buckets * num_buckets, 256, 0, as_stream(stream)>>>(Ef, El, num_buckets, dim, out);
+    LIME_LAUNCH_CHECK("bucket_pairs_kernel");
+    return 0;
+}
+
+extern "C" int lime_scale_rows(float *M, int64_t ld, const float *row_scale, float alpha, int rows, int cols,
+                               void *stream) {
+    LIME_CHECK_ARG(M && rows > 0 && cols > 0, "lime_scale_rows: bad argument");
+    scale_rows_kernel<<<rows, 128, 0, as_stream(stream)>>>(M, ld, row_scale, alpha, rows, cols);
+    LIME_LAUNCH_CHECK("scale_rows_kernel");
+    return 0;
+}
+
+extern "C" int lime_prefix_rows(float *M, int64_t ld, int rows, int cols, void *stream) {
+    LIME_CHECK_ARG(M && rows > 0 && cols > 0, "lime_prefix_rows: bad argument");
+    prefix_rows_kernel<<<(cols + 127) / 128, 128, 0, as_stream(stream)>>>(M, ld, rows, cols);
+    LIME_LAUNCH_CHECK("prefix_rows_kernel");
+    return 0;
+}

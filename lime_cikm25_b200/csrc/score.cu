@@ -1,0 +1,477 @@
+// Stage B: impression scoring on cached news vectors (sm_100a).
+//
+// One kernel replaces, per (user, candidate) pair, the reference's
+//   CandidateAware_ClickedNewsAttention.forward   layers.py:52-93
+//   userEncoders.CROWN.forward tail               userEncoders.py:121,151-171
+//   RemainingLifetimeWeighting.forward            util.py:23-49
+// for the eval layout (one candidate per sample, model.py:158-169).
+//
+// Algebra (DESIGN.md §"Scoring kernel"): with v_h the cached LIME vector of history slot h,
+//   a      = softmax_h( sum_heads softmax_h( Q_head . K_{h,head} / 20, masked ) )      [phase 1]
+//   o_h    = v_h * (e + a_h) / (e + 1),  e = exp(-(a_h * (W_g v_h) + b_g))            [phase 2]
+//            (== gate*a_h*v_h + (1-gate)*v_h with gate = sigmoid(W_g (a_h v_h) + b_g))
+//   x_h    = LayerNorm(o_h)
+//   g_h    = W_l m + b_l + W_r x_h,   m = mean of the first P rows of [x ; user_node_embedding]
+//   alpha  = softmax_h( (W_K g_h) . (W_Q c + b_Q) / 20 ) = softmax_h( x_h . p / 20 ),  p = (W_K W_r)^T (W_Q c + b_Q)
+//   score  = ( m . (W_l^T c) + b_l . c + sum_h alpha_h x_h . (W_r^T c) ) * w(remaining lifetime)
+// so a pair needs, per history row, five reductions over the 400 dims
+//   S0 = sum o, S1 = sum o^2, D1 = sum o*(gamma*p/20), D2 = sum o*(gamma*W_r^T c), D3 = sum o*(gamma*W_l^T c)
+// (the LayerNorm is folded into the dots).  Everything linear in c is cached per news / per
+// lifetime-bucket pair at cache-build time (cand_rows / cand_tab).
+//
+// Thread mapping (phase 2, the hot loop): 13 warps; a warp owns 4 history rows, 8 lanes per row,
+// a lane holds dims d = l8 + 8*j (j < 50) of v_h and W_g v_h in REGISTERS for the whole unit, so the
+// per-candidate loop touches only shared memory: one LDS.128 per element fetches
+// (gate bias, w1, w2, w3)[d], identical across the 4 row groups of a warp (broadcast, 1 wavefront).
+// A work unit is <= tile_c consecutive candidates of one impression; CTAs are persistent (one per
+// SM) and pull units from a global counter.
+#include "common.cuh"
+
+namespace lime {
+
+constexpr int kD = LIME_D;
+constexpr int kEPL = kD / 8;        // elements per lane (50)
+constexpr int kWarps = 13;
+constexpr int kThreads = kWarps * 32;
+constexpr int kRowsPerChunk = kWarps * 4;   // 52 history rows resident in registers at a time
+constexpr int kTStride = LIME_TOPIC + 1;    // 51: conflict-free column reads of the topic tile
+constexpr int kTqStride = 12;               // heads padded 10 -> 12 (3 x LDS.128)
+constexpr int kTqWarp = LIME_TOPIC * kTqStride + kTqStride;   // 612 floats per warp
+constexpr int kNW = 3 * kD;                 // 1200 candidate-vector floats staged per candidate
+
+struct ScoreArgs {
+    LimeNewsCache cache;
+    LimeImpressions imp;
+    long long pair_index_base;
+    long long tail_start;
+    int prefix_main;
+    int prefix_tail;
+    float bucket_scale;
+    float ln_eps;
+    float *scores;
+    int *work_counter;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct SmemLayout {
+    float4 *wbuf;      // [2][kD]   (gate bias', w1, w2, w3) per dim, double buffered
+    float *t_s;        // [H][kTStride]  topic representation of the history slots
+    float *a_s;        // [tile_c][H]    candidate-aware attention weights
+    float *lg_s;       // [tile_c][H]    x_h . p / 20
+    float *y_s;        // [tile_c][H]    x_h . W_r^T c
+    float *z_s;        // [tile_c][H]    x_h . W_l^T c
+    float *tq_s;       // [kWarps][kTqWarp]
+    float *cscal;      // [tile_c][8]    W1s W2s W3s B1 B2 B3 cb  (news part + table part)
+    float *cw;         // [tile_c]       lifetime weight
+    int *cnews;        // [tile_c]
+    int *ctab;         // [tile_c]
+    int *cP;           // [tile_c]
+    int *hnews;        // [H]
+    int *htab;         // [H]
+    int *hmask;        // [H]
+    int *unit_bcast;   // [4]
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+__host__ __device__ inline size_t smem_carve(SmemLayout *L, unsigned char *base, int H, int TC) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align16(off + bytes);
+        return o;
+    };
+    size_t o_wbuf = take(sizeof(float4) * 2 * kD);
+    size_t o_t = take(sizeof(float) * H * kTStride);
+    size_t o_a = take(sizeof(float) * TC * H);
+    size_t o_lg = take(sizeof(float) * TC * H);
+    size_t o_y = take(sizeof(float) * TC * H);
+    size_t o_z = take(sizeof(float) * TC * H);
+    size_t o_tq = take(sizeof(float) * kWarps * kTqWarp);
+    size_t o_cs = take(sizeof(float) * TC * 8);
+    size_t o_cw = take(sizeof(float) * TC);
+    size_t o_cn = take(sizeof(int) * TC);
+    size_t o_ct = take(sizeof(int) * TC);
+    size_t o_cp = take(sizeof(int) * TC);
+    size_t o_hn = take(sizeof(int) * H);
+    size_t o_ht = take(sizeof(int) * H);
+    size_t o_hm = take(sizeof(int) * H);
+    size_t o_ub = take(sizeof(int) * 4);
+    if (L) {
+        L->wbuf = reinterpret_cast<float4 *>(base + o_wbuf);
+        L->t_s = reinterpret_cast<float *>(base + o_t);
+        L->a_s = reinterpret_cast<float *>(base + o_a);
+        L->lg_s = reinterpret_cast<float *>(base + o_lg);
+        L->y_s = reinterpret_cast<float *>(base + o_y);
+        L->z_s = reinterpret_cast<float *>(base + o_z);
+        L->tq_s = reinterpret_cast<float *>(base + o_tq);
+        L->cscal = reinterpret_cast<float *>(base + o_cs);
+        L->cw = reinterpret_cast<float *>(base + o_cw);
+        L->cnews = reinterpret_cast<int *>(base + o_cn);
+        L->ctab = reinterpret_cast<int *>(base + o_ct);
+        L->cP = reinterpret_cast<int *>(base + o_cp);
+        L->hnews = reinterpret_cast<int *>(base + o_hn);
+        L->htab = reinterpret_cast<int *>(base + o_ht);
+        L->hmask = reinterpret_cast<int *>(base + o_hm);
+        L->unit_bcast = reinterpret_cast<int *>(base + o_ub);
+    }
+    return off;
+}
+
+// RemainingLifetimeWeighting weight (util.py:39-46), IEEE fp32 like torch's CUDA sigmoid.
+__device__ __forceinline__ float lifetime_weight(float r, const LimeNewsCache &c) {
+    if (!c.use_lifetime_weighting) return 1.0f;
+    if (c.use_expired_penalty) {
+        float s = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__fmul_rn(c.sigmoid_alpha, r))));
+        float pos = (r >= 0.0f) ? 1.0f : 0.0f;
+        float neg = (r < 0.0f) ? 1.0f : 0.0f;
+        return __fadd_rn(__fmul_rn(pos, s), __fmul_rn(__fmul_rn(neg, c.penalty_beta), s));
+    }
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__fmul_rn(c.sigmoid_alpha, fabsf(r)))));
+}
+
+template <int MAXP>
+__global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const LimeNewsCache &C = args.cache;
+    const LimeImpressions &I = args.imp;
+    const int H = I.max_history;
+    const int TC = I.tile_c;
+    SmemLayout S;
+    smem_carve(&S, smem_raw, H, TC);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int l8 = lane & 7;
+    const int rg = lane >> 3;
+    const int nb = C.num_buckets;
+    const int passes = (H + 31) >> 5;
+    const int chunks = (H + kRowsPerChunk - 1) / kRowsPerChunk;
+
+    // gate bias' = -log2(e) * b_g lives in .x of both staging buffers for the kernel's lifetime
+    for (int d = tid; d < 2 * kD; d += kThreads) S.wbuf[d].x = C.gate_bias[d % kD];
+
+    for (;;) {
+        __syncthreads();   // previous unit fully consumed (also orders the .x init above)
+        if (tid == 0) S.unit_bcast[0] = atomicAdd(args.work_counter, 1);
+        __syncthreads();
+        const int unit = S.unit_bcast[0];
+        if (unit >= I.num_units) break;
+        const int imp = I.unit_imp[unit];
+        const int pair0 = I.unit_pair0[unit];
+        const int cnt = I.unit_count[unit];
+
+        // ---------------- phase 0: unit metadata + topic tile -----------------------------------
+        for (int h = tid; h < H; h += kThreads) {
+            const long long o = (long long)imp * H + h;
+            int n = I.hist_news[o];
+            n = (n < 0 || n >= C.news_num) ? 0 : n;
+            S.hnews[h] = n;
+            S.hmask[h] = I.hist_mask[o];
+            const int bf = bucketize_seconds(I.hist_fresh[o], args.bucket_scale, nb);
+            const int bl = bucketize_seconds(I.hist_life[o], args.bucket_scale, nb);
+            S.htab[h] = bf * nb + bl;
+        }
+        for (int c = tid; c < cnt; c += kThreads) {
+            const long long p = (long long)pair0 + c;
+            int n = I.cand_news[p];
+            n = (n < 0 || n >= C.news_num) ? 0 : n;
+            S.cnews[c] = n;
+            const float fr = I.cand_fresh[p], lf = I.cand_life[p];
+            S.ctab[c] = bucketize_seconds(fr, args.bucket_scale, nb) * nb +
+                        bucketize_seconds(lf, args.bucket_scale, nb);
+            S.cw[c] = lifetime_weight(I.cand_remaining ? I.cand_remaining[p] : __fsub_rn(lf, fr), C);
+            S.cP[c] = (args.pair_index_base + p >= args.tail_start) ? args.prefix_tail : args.prefix_main;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < H * LIME_TOPIC; idx += kThreads) {
+            const int h = idx / LIME_TOPIC, k = idx - h * LIME_TOPIC;
+            S.t_s[h * kTStride + k] = C.hist_rows[(size_t)S.hnews[h] * LIME_HIST_LD + LIME_HIST_T + k];
+        }
+        __syncthreads();
+
+        // ---------------- phase 1: candidate-aware attention weights a[c][h] ---------------------
+        // layers.py:66-81 with N = 1 (query weight softmax over a single candidate == 1).
+        for (int c = warp; c < cnt; c += kWarps) {
+            float *tq = S.tq_s + warp * kTqWarp;
+            const float *crow = C.cand_rows + (size_t)S.cnews[c] * LIME_CAND_LD;
+            for (int idx = lane; idx < LIME_TOPIC * LIME_CA_HEADS; idx += 32) {
+                const int k = idx / LIME_CA_HEADS, hd = idx - k * LIME_CA_HEADS;
+                tq[k * kTqStride + hd] = crow[LIME_CAND_TQ + idx];
+            }
+            if (lane < LIME_CA_HEADS) tq[LIME_TOPIC * kTqStride + lane] = crow[LIME_CAND_QB + lane];
+            if (lane < 8) {
+                const float tabv = C.cand_tab[(size_t)S.ctab[c] * LIME_CTAB_LD + LIME_CAND_SCAL + lane];
+                S.cscal[c * 8 + lane] = crow[LIME_CAND_SCAL + lane] + tabv;
+            }
+            __syncwarp();
+
+            float sc[MAXP][LIME_CA_HEADS];
+#pragma unroll
+            for (int p = 0; p < MAXP; ++p) {
+                if (p < passes) {
+                    const int hh = lane + 32 * p;
+                    const bool valid = hh < H;
+                    const float *trow = S.t_s + (valid ? hh : 0) * kTStride;
+                    float acc[LIME_CA_HEADS];
+#pragma unroll
+                    for (int hd = 0; hd < LIME_CA_HEADS; ++hd) acc[hd] = tq[LIME_TOPIC * kTqStride + hd];
+#pragma unroll 5
+                    for (int k = 0; k < LIME_TOPIC; ++k) {
+                        const float tv = trow[k];
+                        const float4 q0 = *reinterpret_cast<const float4 *>(tq + k * kTqStride);
+                        const float4 q1 = *reinterpret_cast<const float4 *>(tq + k * kTqStride + 4);
+                        const float2 q2 = *reinterpret_cast<const float2 *>(tq + k * kTqStride + 8);
+                        acc[0] = fmaf(q0.x, tv, acc[0]);
+                        acc[1] = fmaf(q0.y, tv, acc[1]);
+                        acc[2] = fmaf(q0.z, tv, acc[2]);
+                        acc[3] = fmaf(q0.w, tv, acc[3]);
+                        acc[4] = fmaf(q1.x, tv, acc[4]);
+                        acc[5] = fmaf(q1.y, tv, acc[5]);
+                        acc[6] = fmaf(q1.z, tv, acc[6]);
+                        acc[7] = fmaf(q1.w, tv, acc[7]);
+                        acc[8] = fmaf(q2.x, tv, acc[8]);
+                        acc[9] = fmaf(q2.y, tv, acc[9]);
+                    }
+                    const bool keep = valid && (S.hmask[valid ? hh : 0] != 0);
+#pragma unroll
+                    for (int hd = 0; hd < LIME_CA_HEADS; ++hd)
+                        sc[p][hd] = valid ? (keep ? acc[hd] : -1e9f) : -INFINITY;   // masked_fill(mask==0,-1e9)
+                } else {
+#pragma unroll
+                    for (int hd = 0; hd < LIME_CA_HEADS; ++hd) sc[p][hd] = -INFINITY;
+                }
+            }
+            float agg[MAXP];
+#pragma unroll
+            for (int p = 0; p < MAXP; ++p) agg[p] = 0.0f;
+#pragma unroll
+            for (int hd = 0; hd < LIME_CA_HEADS; ++hd) {
+                float m = -INFINITY;
+#pragma unroll
+                for (int p = 0; p < MAXP; ++p) m = fmaxf(m, sc[p][hd]);
+                m = warp_max(m);
+                float e[MAXP];
+                float l = 0.0f;
+#pragma unroll
+                for (int p = 0; p < MAXP; ++p) {
+                    e[p] = __expf(sc[p][hd] - m);   // -inf rows (h >= H) give 0
+                    l += e[p];
+                }
+                l = warp_sum(l);
+                const float inv = __fdividef(1.0f, l);
+#pragma unroll
+                for (int p = 0; p < MAXP; ++p) agg[p] = fmaf(e[p], inv, agg[p]);
+            }
+            // second, unmasked softmax over the history (layers.py:81)
+            float m2 = -INFINITY;
+#pragma unroll
+            for (int p = 0; p < MAXP; ++p) {
+                const bool valid = (p < passes) && (lane + 32 * p < H);
+                m2 = fmaxf(m2, valid ? agg[p] : -INFINITY);
+            }
+            m2 = warp_max(m2);
+            float l2 = 0.0f;
+#pragma unroll
+            for (int p = 0; p < MAXP; ++p) {
+                const bool valid = (p < passes) && (lane + 32 * p < H);
+                agg[p] = valid ? __expf(agg[p] - m2) : 0.0f;
+                l2 += agg[p];
+            }
+            l2 = warp_sum(l2);
+            const float inv2 = __fdividef(1.0f, l2);
+#pragma unroll
+            for (int p = 0; p < MAXP; ++p) {
+                const int hh = lane + 32 * p;
+                if (p < passes && hh < H) S.a_s[c * H + hh] = agg[p] * inv2;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // ---------------- phase 2: gated residual + LayerNorm statistics + 3 dots per row --------
+        for (int chunk = 0; chunk < chunks; ++chunk) {
+            const int h = chunk * kRowsPerChunk + warp * 4 + rg;
+            const bool row_ok = h < H;
+            float v[kEPL], gw[kEPL];
+            {
+                const int hn = row_ok ? S.hnews[h] : 0;
+                const int ht = row_ok ? S.htab[h] : 0;
+                const float *hr = C.hist_rows + (size_t)hn * LIME_HIST_LD + l8;
+                const float *tr = C.hist_tab + (size_t)ht * LIME_HTAB_LD + l8;
+#pragma unroll
+                for (int j = 0; j < kEPL; ++j) {
+                    v[j] = row_ok ? (hr[LIME_HIST_VC + 8 * j] + tr[8 * j]) : 0.0f;
+                    gw[j] = row_ok ? (hr[LIME_HIST_GW + 8 * j] + tr[kD + 8 * j]) : 0.0f;
+                }
+            }
+            // stage candidate 0
+            for (int idx = tid; idx < kNW; idx += kThreads) {
+                const int which = idx / kD, d = idx - which * kD;
+                const float val = C.cand_rows[(size_t)S.cnews[0] * LIME_CAND_LD + idx] +
+                                  C.cand_tab[(size_t)S.ctab[0] * LIME_CTAB_LD + idx];
+                reinterpret_cast<float *>(S.wbuf + d)[1 + which] = val;
+            }
+            __syncthreads();
+            for (int c = 0; c < cnt; ++c) {
+                const int buf = c & 1;
+                float nv[3];
+                const bool has_next = (c + 1 < cnt);
+                if (has_next) {
+                    const float *cr = C.cand_rows + (size_t)S.cnews[c + 1] * LIME_CAND_LD;
+                    const float *ct = C.cand_tab + (size_t)S.ctab[c + 1] * LIME_CTAB_LD;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const int idx = tid + q * kThreads;
+                        nv[q] = (idx < kNW) ? (cr[idx] + ct[idx]) : 0.0f;
+                    }
+                }
+                const float a = row_ok ? S.a_s[c * H + h] : 0.0f;
+                const float4 *wb = S.wbuf + buf * kD + l8;
+                float s0 = 0.f, s1 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                for (int j = 0; j < kEPL; ++j) {
+                    const float4 q = wb[8 * j];
+                    const float zz = fminf(fmaf(a, gw[j], q.x), 80.0f);
+                    const float e = ex2_approx(zz);
+                    const float o = v[j] * ((e + a) * rcp_approx(e + 1.0f));
+                    s0 += o;
+                    s1 = fmaf(o, o, s1);
+                    d1 = fmaf(o, q.y, d1);
+                    d2 = fmaf(o, q.z, d2);
+                    d3 = fmaf(o, q.w, d3);
+                }
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+                    d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+                    d3 += __shfl_xor_sync(0xffffffffu, d3, o);
+                }
+                if (l8 == 0 && row_ok) {
+                    const float *cs = S.cscal + c * 8;
+                    const float mu = s0 * (1.0f / kD);
+                    const float var = fmaxf(fmaf(-mu, mu, s1 * (1.0f / kD)), 0.0f);
+                    const float rstd = rsqrtf(var + args.ln_eps);
+                    S.lg_s[c * H + h] = fmaf(rstd, fmaf(-mu, cs[0], d1), cs[3]);
+                    S.y_s[c * H + h] = fmaf(rstd, fmaf(-mu, cs[1], d2), cs[4]);
+                    S.z_s[c * H + h] = fmaf(rstd, fmaf(-mu, cs[2], d3), cs[5]);
+                }
+                if (has_next) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const int idx = tid + q * kThreads;
+                        if (idx < kNW) {
+                            const int which = idx / kD, d = idx - which * kD;
+                            reinterpret_cast<float *>(S.wbuf + (buf ^ 1) * kD + d)[1 + which] = nv[q];
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---------------- phase 3: candidate-query pooling + lifetime-weighted dot ---------------
+        for (int c = warp; c < cnt; c += kWarps) {
+            const int P = S.cP[c];
+            const int pz = P < H ? P : H;
+            float m = -INFINITY;
+            for (int hh = lane; hh < H; hh += 32) m = fmaxf(m, S.lg_s[c * H + hh]);
+            m = warp_max(m);
+            float l = 0.f, acc = 0.f, ms = 0.f;
+            for (int hh = lane; hh < H; hh += 32) {
+                const float e = __expf(S.lg_s[c * H + hh] - m);
+                l += e;
+                acc = fmaf(e, S.y_s[c * H + hh], acc);
+                if (hh < pz) ms += S.z_s[c * H + hh];
+            }
+            l = warp_sum(l);
+            acc = warp_sum(acc);
+            ms = warp_sum(ms);
+            float un = 0.f;
+            if (P > H) {   // user-node rows take part in the GraphSAGE mean (userEncoders.py:121,153)
+                int j = P - H - 1;
+                j = j < C.user_nodes ? j : C.user_nodes - 1;
+                const float *u = C.un_prefix + (size_t)j * kD;
+                const float *hr = C.hist_rows + (size_t)S.cnews[c] * LIME_HIST_LD + LIME_HIST_VC;
+                const float *tr = C.hist_tab + (size_t)S.ctab[c] * LIME_HTAB_LD;
+                for (int d = lane; d < kD; d += 32) un = fmaf(hr[d] + tr[d], u[d], un);
+                un = warp_sum(un);
+            }
+            if (lane == 0) {
+                const float base = (ms + un) / (float)P + S.cscal[c * 8 + 6] + acc / l;
+                args.scores[(long long)pair0 + c] = base * S.cw[c];
+            }
+        }
+    }
+}
+
+}  // namespace lime
+
+using namespace lime;
+
+extern "C" int64_t lime_score_smem_bytes(int32_t max_history, int32_t tile_c) {
+    return (int64_t)smem_carve(nullptr, nullptr, max_history, tile_c);
+}
+
+extern "C" int lime_score_impressions(const LimeNewsCache *cache, const LimeImpressions *imp,
+                                      int64_t pair_index_base, int32_t prefix_main,
+                                      int64_t tail_start, int32_t prefix_tail, float *scores,
+                                      int32_t *work_counter, void *stream) {
+    LIME_CHECK_ARG(cache && imp && scores && work_counter, "lime_score_impressions: null argument");
+    const int H = imp->max_history, TC = imp->tile_c;
+    LIME_CHECK_ARG(H >= 1 && H <= 224, "lime_score_impressions: max_history %d not in [1,224]", H);
+    LIME_CHECK_ARG(TC >= 1, "lime_score_impressions: tile_c %d < 1", TC);
+    LIME_CHECK_ARG(cache->num_buckets >= 1 && cache->news_num >= 1, "lime_score_impressions: empty cache");
+    // runtime batch larger than max_history + config.batch_size is an out-of-range gather in the
+    // reference (userEncoders.py:94,153); reject it instead of reading past user_node_embedding
+    LIME_CHECK_ARG(prefix_main >= 1 && prefix_main <= H + cache->user_nodes,
+                   "lime_score_impressions: prefix_main %d not in [1, %d]", prefix_main, H + cache->user_nodes);
+    LIME_CHECK_ARG(prefix_tail >= 1 && prefix_tail <= H + cache->user_nodes,
+                   "lime_score_impressions: prefix_tail %d not in [1, %d]", prefix_tail, H + cache->user_nodes);
+    if (imp->num_units <= 0) return 0;
+    const size_t smem = smem_carve(nullptr, nullptr, H, TC);
+    LIME_CHECK_ARG(smem <= 232448, "lime_score_impressions: (H=%d, tile_c=%d) needs %zu B of shared memory", H, TC, smem);
+
+    ScoreArgs a;
+    a.cache = *cache;
+    a.imp = *imp;
+    a.pair_index_base = pair_index_base;
+    a.tail_start = tail_start;
+    a.prefix_main = prefix_main;
+    a.prefix_tail = prefix_tail;
+    a.bucket_scale = (float)((double)cache->num_buckets / 7.0);
+    a.ln_eps = 1e-5f;
+    a.scores = scores;
+    a.work_counter = work_counter;
+
+    cudaStream_t st = as_stream(stream);
+    LIME_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(int32_t), st));
+    int grid = num_sms();
+    if (grid > imp->num_units) grid = imp->num_units;
+    const int passes = (H + 31) / 32;
+    if (passes <= 2) {
+        LIME_CUDA(cudaFuncSetAttribute(score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        score_kernel<2><<<grid, kThreads, smem, st>>>(a);
+    } else if (passes <= 4) {
+        LIME_CUDA(cudaFuncSetAttribute(score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        score_kernel<4><<<grid, kThreads, smem, st>>>(a);
+    } else {
+        LIME_CUDA(cudaFuncSetAttribute(score_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        score_kernel<7><<<grid, kThreads, smem, st>>>(a);
+    }
+    LIME_LAUNCH_CHECK("score_kernel");
+    return 0;
+}

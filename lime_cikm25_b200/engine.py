@@ -1,0 +1,429 @@
+"""Host-side driver of the B200 path: weight preparation, news-vector cache build (Stage A) and
+impression scoring (Stage B).  All arithmetic is done by liblime_b200.so through ``ops``; torch
+supplies device buffers, views/copies and the current stream.
+
+Layout of the per-news cache in HBM (fp32; DESIGN.md "HBM layout"):
+
+  hist_rows [news, 852]   vc = W_c content            (0..399)   LIME projection, content half, no bias
+                          gw = -log2(e) W_g vc          (400..799) gate pre-activation of the history role
+                          t  = topic representation     (800..851) LIME's frozen tables, padded 50->52
+  cand_rows [news, 1720]  w1 = gamma*P vc/20 | w2 = gamma*W_r^T vc | w3 = gamma*W_l^T vc   (0..1199)
+                          7 scalars (1200..1206), tq 50x10 (1208..1707), qb 10 (1708..1717)
+  hist_tab  [nb*nb, 800]  the same two history vectors for T[bf,bl] = W_f tanh(dense(E_f|E_l)) + b
+  cand_tab  [nb*nb, 1208] the same candidate block for T[bf,bl] (+ the constants coming from Q.bias)
+
+A LIME news vector is v(news, bf, bl) = vc[news] + T[bf, bl]; everything the scoring kernel needs is
+linear in v, so it is cached as a per-news part plus a per-bucket-pair part.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import LimeImpressions, LimeNewsCache, check
+
+D = 400
+HIST_LD, CAND_LD, HTAB_LD, CTAB_LD = 852, 1720, 800, 1208
+HIST_GW, HIST_T = 400, 800
+CAND_SCAL, CAND_TQ, CAND_NFOLD = 1200, 1208, 1207
+TOPIC, TOPIC_LD, HEADS = 50, 52, 10
+LOG2E = 1.4426950408889634
+
+
+def _fingerprint(params):
+    return tuple((p.data_ptr(), p._version) for p in params)
+
+
+def _check_geometry(cfg):
+    """The kernels are specialised for the LIME-CROWN-CROWN geometry of config.py's defaults."""
+    want = dict(word_embedding_dim=300, head_num=10, feedforward_dim=512, intent_embedding_dim=400,
+                intent_num=3, attention_dim=400, category_embedding_dim=50, subCategory_embedding_dim=50,
+                lime_output_dim=400, fusion_method="concat", num_layers=1,
+                use_candidate_ware_clicked_news_attention=True, use_residual_connection=True,
+                click_predictor="dot_product")
+    for k, v in want.items():
+        if getattr(cfg, k) != v:
+            raise NotImplementedError("lime_cikm25_b200 supports %s=%r only (got %r)" % (k, v, getattr(cfg, k)))
+    if cfg.max_title_length != 32 or cfg.max_abstract_length != 128:
+        raise NotImplementedError("title/body lengths must be 32/128 (config.py:144-163 forces them)")
+
+
+class NewsEncoderEngine:
+    """Stage A: LIME(CROWN) news encoder, eval mode (newsEncoders.py:140-161, 302-373)."""
+
+    def __init__(self, lime_module, cfg):
+        _check_geometry(cfg)
+        self.m = lime_module
+        self.cfg = cfg
+        self._prep = None
+        self._fp = None
+        self.bf16 = False        # "bf16 mode": the 4 transformer GEMMs on tcgen05 (lime_linear_bf16)
+
+    # -- weights -----------------------------------------------------------------------------------
+    def _params(self):
+        return [p for p in self.m.parameters()] + [b for b in self.m.buffers()]
+
+    def prepare(self):
+        fp = _fingerprint(self._params())
+        if self._prep is not None and fp == self._fp:
+            return self._prep
+        m, base = self.m, self.m.base_news_encoder
+        dev = base.word_embedding.weight.device
+        if dev.type != "cuda":
+            raise _lib.LimeError("model parameters must live on a CUDA device (no CPU fallback)")
+        f32 = dict(dtype=torch.float32, device=dev)
+        P = {}
+        # intent layers: one [k*400, 352] weight (K padded 350 -> 352) so the 3 FCs are a single GEMM
+        k = len(base.intent_layers)
+        W = torch.zeros(k * 400, 352, **f32)
+        b = torch.empty(k * 400, **f32)
+        for i, lin in enumerate(base.intent_layers):
+            W[i * 400:(i + 1) * 400, :350].copy_(lin.weight.detach())
+            b[i * 400:(i + 1) * 400].copy_(lin.bias.detach())
+        P["intent_w"], P["intent_b"] = W, b
+
+        def tr(t):
+            l = t.layers[0]
+            return dict(in_w=l.self_attn.in_proj_weight.detach(), in_b=l.self_attn.in_proj_bias.detach(),
+                        out_w=l.self_attn.out_proj.weight.detach(), out_b=l.self_attn.out_proj.bias.detach(),
+                        l1_w=l.linear1.weight.detach(), l1_b=l.linear1.bias.detach(),
+                        l2_w=l.linear2.weight.detach(), l2_b=l.linear2.bias.detach(),
+                        n1_w=l.norm1.weight.detach(), n1_b=l.norm1.bias.detach(),
+                        n2_w=l.norm2.weight.detach(), n2_b=l.norm2.bias.detach(),
+                        eps1=l.norm1.eps, eps2=l.norm2.eps)
+        P["title"], P["body"] = tr(base.title_transformer), tr(base.body_transformer)
+        P["title_pe"] = base.title_pos_encoder.pe.detach().reshape(-1, 300).contiguous()
+        P["body_pe"] = base.body_pos_encoder.pe.detach().reshape(-1, 300).contiguous()
+        pw = m.project.weight.detach()                    # [400, 1800] = [W_c | W_f]
+        P["Wc"], P["Wf"], P["proj_b"] = pw[:, :900], pw[:, 900:], m.project.bias.detach()
+        self._prep, self._fp = P, fp
+        return P
+
+    # -- one transformer branch (title or body) ----------------------------------------------------
+    def _branch(self, ids, T, W, pe, feat):
+        base = self.m.base_news_encoder
+        n = ids.shape[0]
+        rows = n * T
+        dev = ids.device
+        E = base.word_embedding.weight.detach()
+        x0 = torch.empty(rows, 300, dtype=torch.float32, device=dev)
+        ops.embed_pe(E, ids, T, pe, x0)
+        qkv = ops.linear(x0, W["in_w"], W["in_b"], bf16=self.bf16)
+        ctx = torch.empty(rows, 300, dtype=torch.float32, device=dev)
+        ops.mha(qkv, ctx, n, T, 300, self.cfg.head_num)
+        del qkv
+        y = ops.linear(ctx, W["out_w"], W["out_b"], residual=x0, bf16=self.bf16)
+        x1 = ops.layernorm(y, W["n1_w"], W["n1_b"], out=ctx, eps=W["eps1"])       # reuse ctx
+        hf = ops.linear(x1, W["l1_w"], W["l1_b"], act=ops.ACT_RELU, bf16=self.bf16)
+        y2 = ops.linear(hf, W["l2_w"], W["l2_b"], residual=x1, out=y, bf16=self.bf16)
+        ops.layernorm_meanpool(y2, W["n2_w"], W["n2_b"], feat, n, T, eps=W["eps2"])
+
+    def encode_content(self, title_text, body_text, category, subCategory):
+        """newsEncoders.CROWN.forward, flat over news: int32 [n,32], [n,128], [n], [n] -> fp32 [n,900]."""
+        P = self.prepare()
+        base = self.m.base_news_encoder
+        n = title_text.shape[0]
+        dev = title_text.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        feat_t = torch.empty(n, 352, **f32)
+        feat_b = torch.empty(n, 352, **f32)
+        self._branch(title_text, 32, P["title"], P["title_pe"], feat_t)
+        self._branch(body_text, 128, P["body"], P["body_pe"], feat_b)
+        # category-aware intent disentanglement (:340-356): topic from CROWN's own tables
+        for feat in (feat_t, feat_b):
+            ops.topic_rep(base.category_embedding.weight.detach(), base.subCategory_embedding.weight.detach(),
+                          base.category_affine.weight.detach(), base.category_affine.bias.detach(),
+                          category, subCategory, feat[:, 300:], TOPIC_LD)
+        k = len(base.intent_layers)
+        pooled = []
+        for feat, att in ((feat_t, base.title_intent_attention), (feat_b, base.body_intent_attention)):
+            e = ops.linear(feat, P["intent_w"], P["intent_b"], act=ops.ACT_RELU)          # [n, k*400]
+            pre = ops.linear(e.view(n * k, 400), att.affine1.weight.detach(), att.affine1.bias.detach())
+            out = torch.empty(n, 400, **f32)
+            ops.intent_pool(pre, e, att.affine2.weight.detach().reshape(-1), out, n, k, 400)
+            pooled.append(out)
+        content = torch.empty(n, 900, **f32)
+        ops.content_fuse(pooled[0], pooled[1], base.category_embedding.weight.detach(),
+                         base.subCategory_embedding.weight.detach(), category, subCategory, content)
+        return content
+
+    def freshness_table(self):
+        """T[bf*nb+bl] = W_f tanh(dense(E_f[bf] | E_l[bl])) + project.bias  -> [nb*nb, 400]
+        (FreshnessEncoder.forward :60-83 followed by the freshness half of LIME.project :151-153)."""
+        P = self.prepare()
+        fe = self.m.freshness_encoder
+        nb = fe.num_buckets
+        dev = P["Wc"].device
+        pairs = torch.empty(nb * nb, 2 * fe.freshness_embedding.weight.shape[1], dtype=torch.float32, device=dev)
+        ops.bucket_pairs(fe.freshness_embedding.weight.detach(), fe.lifetime_embedding.weight.detach(), pairs)
+        hid = ops.linear(pairs, fe.dense.weight.detach(), fe.dense.bias.detach(), act=ops.ACT_TANH)
+        return ops.linear(hid, P["Wf"], P["proj_b"])
+
+
+class ScoringEngine:
+    """Stage B: folded user-encoder weights, cache rows, fused scoring launch."""
+
+    def __init__(self, model):
+        self.model = model
+        self.cfg = model.config
+        self.news = model.news_encoder.engine
+        self._fold = None
+        self._fp = None
+
+    def _params(self):
+        return [p for p in self.model.parameters()] + [b for b in self.model.buffers()]
+
+    # -- fold the user-encoder weights (once per checkpoint) ---------------------------------------
+    def fold(self):
+        fp = _fingerprint(self._params())
+        if self._fold is not None and fp == self._fp:
+            return self._fold
+        ue = self.model.user_encoder
+        ca = ue.candidate_aware_attn
+        sage = ue.graph_sage.convs[0]
+        dev = ue.K.weight.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        WK, WQ, bQ = ue.K.weight.detach(), ue.Q.weight.detach(), ue.Q.bias.detach()
+        Wl, bl, Wr = sage.lin_l.weight.detach(), sage.lin_l.bias.detach(), sage.lin_r.weight.detach()
+        gamma, beta = ca.layernorm.weight.detach(), ca.layernorm.bias.detach()
+        inv_s = 1.0 / math.sqrt(float(self.cfg.attention_dim))           # userEncoders.py:71,163
+        F = {}
+        # P = (W_K W_r)^T W_Q = W_r^T (W_K^T W_Q)
+        X = ops.gemm_strided(WK.t(), WQ)
+        Pm = ops.gemm_strided(Wr.t(), X)
+        G = torch.zeros(CAND_NFOLD + 1, D, **f32)                       # [1208, 400], last row unused
+        G[0:400].copy_(Pm)
+        ops.scale_rows(G[0:400], gamma, inv_s)
+        G[400:800].copy_(Wr.t())
+        ops.scale_rows(G[400:800], gamma, 1.0)
+        G[800:1200].copy_(Wl.t())
+        ops.scale_rows(G[800:1200], gamma, 1.0)
+        ones = torch.ones(1, D, **f32)
+        ops.gemm_strided(ones, G[0:400], out=G[1200:1201])               # W1s = gamma . p / 20
+        ops.gemm_strided(ones, G[400:800], out=G[1201:1202])             # W2s
+        ops.gemm_strided(ones, G[800:1200], out=G[1202:1203])            # W3s
+        ops.gemm_strided(beta.view(1, D), Pm, alpha=inv_s, out=G[1203:1204])   # B1 = beta . p / 20
+        ops.gemm_strided(beta.view(1, D), Wr.t(), out=G[1204:1205])      # B2
+        ops.gemm_strided(beta.view(1, D), Wl.t(), out=G[1205:1206])      # B3
+        G[1206].copy_(bl)                                                # cb = b_l . c
+        F["G"] = G
+        # constants from Q.bias: p0 = W_r^T W_K^T b_Q
+        x0 = ops.gemm_strided(bQ.view(1, D), WK)
+        p0 = ops.gemm_strided(x0, Wr)                                    # [1, 400]
+        cconst = torch.zeros(CAND_NFOLD + 1, **f32)
+        cconst[0:400].copy_(p0.view(-1))
+        ops.scale_rows(cconst[0:400].view(D, 1), gamma, inv_s)           # gamma * p0 / 20
+        ops.gemm_strided(ones, cconst[0:400].view(D, 1), out=cconst[1200:1201].view(1, 1))
+        ops.gemm_strided(beta.view(1, D), p0.view(D, 1), alpha=inv_s, out=cconst[1203:1204].view(1, 1))
+        F["cconst"] = cconst
+        # gate: z' = -log2(e) (a W_g v + b_g)
+        Gg = ca.gate_proj.weight.detach().clone()
+        ops.scale_rows(Gg, None, -LOG2E)
+        gb = ca.gate_proj.bias.detach().clone().view(1, D)
+        ops.scale_rows(gb, None, -LOG2E)
+        F["Gg"], F["gate_bias"] = Gg, gb.view(-1)
+        # topic attention: S[head,h] = (W_k,head^T Q_head) . t_h + Q_head . b_k,head, all / sqrt(D),
+        # with Q = W_q t_c + b_q   (layers.py:66-70)  ->  affine map of t_c into [50*10 + 10]
+        Wq, bq = ca.query_proj.weight.detach(), ca.query_proj.bias.detach()
+        Wk, bk = ca.key_proj.weight.detach(), ca.key_proj.bias.detach()
+        hd = D // HEADS
+        inv_sc = 1.0 / float(ca.scale)
+        A = torch.zeros(TOPIC * HEADS + HEADS, TOPIC_LD, **f32)
+        a0 = torch.zeros(TOPIC * HEADS + HEADS, **f32)
+        Av = A[:TOPIC * HEADS].view(TOPIC, HEADS, TOPIC_LD)
+        a0v = a0[:TOPIC * HEADS].view(TOPIC, HEADS)
+        for h in range(HEADS):
+            sl = slice(h * hd, (h + 1) * hd)
+            ops.gemm_strided(Wk[sl].t(), Wq[sl], alpha=inv_sc, out=Av[:, h, :TOPIC])
+            ops.gemm_strided(Wk[sl].t(), bq[sl].view(hd, 1), alpha=inv_sc, out=a0v[:, h:h + 1])
+            r = TOPIC * HEADS + h
+            ops.gemm_strided(bk[sl].view(1, hd), Wq[sl], alpha=inv_sc, out=A[r:r + 1, :TOPIC])
+            ops.gemm_strided(bk[sl].view(1, hd), bq[sl].view(hd, 1), alpha=inv_sc, out=a0[r:r + 1].view(1, 1))
+        F["Atq"], F["atq0"] = A, a0
+        # user-node rows of the GraphSAGE mean: prefix sums of lin_l(user_node_embedding) (no bias)
+        un = ops.linear(ue.user_node_embedding.detach(), Wl)
+        ops.prefix_rows(un)
+        F["un_prefix"] = un
+        # bucket-pair tables
+        T = self.news.freshness_table()                                  # [nb*nb, 400]
+        nb2 = T.shape[0]
+        htab = torch.empty(nb2, HTAB_LD, **f32)
+        htab[:, :D].copy_(T)
+        ops.linear(htab[:, :D], Gg, out=htab[:, D:])
+        ctab = torch.zeros(nb2, CTAB_LD, **f32)
+        ops.linear(htab[:, :D], G, bias=cconst, out=ctab[:, :CAND_NFOLD], n=CAND_NFOLD)
+        F["hist_tab"], F["cand_tab"] = htab, ctab
+        self._fold, self._fp = F, fp
+        return F
+
+    # -- per-news cache ----------------------------------------------------------------------------
+    def build_rows(self, title_text, body_text, category, subCategory, chunk=2048):
+        """Encode news and derive both cache roles.  int32 device tensors [n,32], [n,128], [n], [n]
+        -> (hist_rows [n,852], cand_rows [n,1720])."""
+        F = self.fold()
+        lime = self.model.news_encoder
+        n = title_text.shape[0]
+        dev = title_text.device
+        hist = torch.zeros(n, HIST_LD, dtype=torch.float32, device=dev)
+        cand = torch.zeros(n, CAND_LD, dtype=torch.float32, device=dev)
+        Wc = self.news.prepare()["Wc"]
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            tt, bt = title_text[lo:hi].contiguous(), body_text[lo:hi].contiguous()
+            ct, sb = category[lo:hi].contiguous(), subCategory[lo:hi].contiguous()
+            content = self.news.encode_content(tt, bt, ct, sb)
+            h, c = hist[lo:hi], cand[lo:hi]
+            ops.linear(content, Wc, out=h[:, :D])                                   # vc
+            ops.linear(h[:, :D], F["Gg"], out=h[:, HIST_GW:HIST_GW + D])            # gw
+            ops.topic_rep(lime.category_embedding.weight.detach(), lime.subCategory_embedding.weight.detach(),
+                          lime.category_affine.weight.detach(), lime.category_affine.bias.detach(),
+                          ct, sb, h[:, HIST_T:], TOPIC_LD)
+            ops.linear(h[:, :D], F["G"], out=c[:, :CAND_NFOLD], n=CAND_NFOLD)       # w1 w2 w3 + scalars
+            ops.linear(h[:, HIST_T:HIST_T + TOPIC_LD], F["Atq"], F["atq0"],
+                       out=c[:, CAND_TQ:CAND_TQ + TOPIC * HEADS + HEADS])           # tq, qb
+        return hist, cand
+
+    def cache_struct(self, hist_rows, cand_rows):
+        F = self.fold()
+        cfg = self.cfg
+        return LimeNewsCache(
+            hist_rows=hist_rows.data_ptr(), cand_rows=cand_rows.data_ptr(),
+            hist_tab=F["hist_tab"].data_ptr(), cand_tab=F["cand_tab"].data_ptr(),
+            gate_bias=F["gate_bias"].data_ptr(), un_prefix=F["un_prefix"].data_ptr(),
+            news_num=hist_rows.shape[0], num_buckets=cfg.num_buckets,
+            user_nodes=F["un_prefix"].shape[0], sigmoid_alpha=float(cfg.sigmoid_scaling_alpha),
+            penalty_beta=float(cfg.penalty_scaling_beta),
+            use_lifetime_weighting=int(bool(cfg.use_remaining_lifetime_weighting)),
+            use_expired_penalty=int(bool(cfg.use_expired_penalty)))
+
+    def lime_vectors(self, hist_rows, freshness, lifetime):
+        """v = vc + T[bucket(freshness), bucket(lifetime)]  (LIME.forward output, [n,400])."""
+        F = self.fold()
+        nb = self.cfg.num_buckets
+        idx = ops.bucketize(freshness, nb).long() * nb + ops.bucketize(lifetime, nb).long()
+        # pure gather + add of two cached rows: plumbing for the module-level API, not on the scoring path
+        return hist_rows[:, :D] + F["hist_tab"][:, :D].index_select(0, idx.reshape(-1))
+
+    def score(self, hist_rows, cand_rows, dimp, prefix_main, tail_start=None, prefix_tail=None,
+              pair_index_base=0, out=None):
+        """Launch the fused scoring kernel over a DeviceImpressions set -> fp32 scores [P]."""
+        lib = _lib.require_device()
+        cache = self.cache_struct(hist_rows, cand_rows)
+        st = dimp.struct()
+        if out is None:
+            out = torch.empty(dimp.num_pairs, dtype=torch.float32, device=hist_rows.device)
+        if tail_start is None:
+            tail_start, prefix_tail = 1 << 62, prefix_main
+        check(lib.lime_score_impressions(cache, st, int(pair_index_base), int(prefix_main), int(tail_start),
+                                         int(prefix_tail), out.data_ptr(), dimp.work_counter.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream), "lime_score_impressions")
+        return out
+
+
+def choose_tile_c(max_history):
+    """Largest multiple of 13 (warps per CTA) up to 52 whose shared-memory footprint fits."""
+    lib = _lib.load()
+    for tc in (52, 39, 26, 13):
+        if lib.lime_score_smem_bytes(int(max_history), tc) <= 232448:
+            return tc
+    raise _lib.LimeError("max_history=%d does not fit the scoring kernel's shared memory" % max_history)
+
+
+def build_units(cand_off, tile_c):
+    """Work units of the scoring kernel: every impression's candidate list is cut into runs of at
+    most ``tile_c`` consecutive candidates.  Returns (unit_imp, unit_pair0, unit_count) as int64."""
+    cand_off = np.asarray(cand_off, np.int64)
+    counts = np.diff(cand_off)
+    nun = (counts + tile_c - 1) // tile_c
+    unit_imp = np.repeat(np.arange(counts.shape[0], dtype=np.int64), nun)
+    first = np.cumsum(nun) - nun
+    kk = np.arange(unit_imp.shape[0], dtype=np.int64) - first[unit_imp]
+    unit_pair0 = cand_off[:-1][unit_imp] + kk * tile_c
+    unit_count = np.minimum(tile_c, counts[unit_imp] - kk * tile_c)
+    return unit_imp, unit_pair0, unit_count
+
+
+class DeviceImpressions:
+    """Impression set resident in HBM + the work-unit list of the scoring kernel."""
+
+    @classmethod
+    def from_pairs(cls, hist_mask, hist_fresh, hist_life, cand_fresh, cand_life, cand_remaining, n_cand):
+        """Per-pair layout of Model.forward (one impression per sample, ``n_cand`` candidates each):
+        the freshly encoded batch is its own news cache with history rows first
+        (row b*H+h) and candidate rows after them (row B*H + b*n_cand + j).  Device tensors only."""
+        self = cls.__new__(cls)
+        dev = hist_mask.device
+        B, H = hist_mask.shape
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.tile_c = choose_tile_c(H)
+        if n_cand > self.tile_c:
+            raise _lib.LimeError("at most %d candidates per sample in Model.forward" % self.tile_c)
+        self.max_history, self.num_pairs, self.num_impressions, self.num_units = H, B * n_cand, B, B
+        self.device = dev
+        self.dev = dict(
+            hist_news=torch.arange(B * H, **i32).view(B, H),
+            hist_mask=hist_mask.to(torch.uint8).contiguous(),
+            hist_fresh=hist_fresh.float().contiguous(), hist_life=hist_life.float().contiguous(),
+            cand_news=torch.arange(B * H, B * H + B * n_cand, **i32),
+            cand_fresh=cand_fresh.float().reshape(-1).contiguous(),
+            cand_life=cand_life.float().reshape(-1).contiguous(),
+            unit_imp=torch.arange(B, **i32), unit_pair0=torch.arange(0, B * n_cand, n_cand, **i32),
+            unit_count=torch.full((B,), n_cand, **i32))
+        if cand_remaining is not None:
+            self.dev["cand_remaining"] = cand_remaining.float().reshape(-1).contiguous()
+        self.work_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        return self
+
+    def __init__(self, imp, device, tile_c=None, cand_remaining=None):
+        H = imp.hist_news.shape[1]
+        self.tile_c = int(tile_c or choose_tile_c(H))
+        self.max_history = H
+        self.num_pairs = int(imp.cand_news.shape[0])
+        self.num_impressions = int(imp.hist_news.shape[0])
+        unit_imp, unit_pair0, unit_count = build_units(imp.cand_off, self.tile_c)
+        self.num_units = int(unit_imp.shape[0])
+        self.host = dict(
+            hist_news=np.ascontiguousarray(imp.hist_news, np.int32),
+            hist_mask=np.ascontiguousarray(imp.hist_mask).astype(np.uint8),
+            hist_fresh=np.ascontiguousarray(imp.hist_fresh, np.float32),
+            hist_life=np.ascontiguousarray(imp.hist_life, np.float32),
+            cand_news=np.ascontiguousarray(imp.cand_news, np.int32),
+            cand_fresh=np.ascontiguousarray(imp.cand_fresh, np.float32),
+            cand_life=np.ascontiguousarray(imp.cand_life, np.float32),
+            unit_imp=unit_imp.astype(np.int32), unit_pair0=unit_pair0.astype(np.int32),
+            unit_count=unit_count.astype(np.int32),
+            cand_off=np.ascontiguousarray(imp.cand_off, np.int64),
+            labels=np.ascontiguousarray(imp.labels, np.uint8),
+        )
+        if cand_remaining is not None:      # lifetime_type 'fixed' / 'topic_wise' (util.py:98-102)
+            self.host["cand_remaining"] = np.ascontiguousarray(cand_remaining, np.float32)
+        self.pinned = {k: torch.from_numpy(v).pin_memory() for k, v in self.host.items()}
+        self.dev = {}
+        self.device = device
+        self.work_counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.upload()
+
+    def h2d_bytes(self):
+        return int(sum(v.numel() * v.element_size() for v in self.pinned.values()))
+
+    def upload(self):
+        """Host (pinned) -> HBM copy of every input array, on the current stream."""
+        for k, v in self.pinned.items():
+            if k not in self.dev:
+                self.dev[k] = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+            self.dev[k].copy_(v, non_blocking=True)
+
+    def struct(self):
+        d = self.dev
+        return LimeImpressions(
+            hist_news=d["hist_news"].data_ptr(), hist_mask=d["hist_mask"].data_ptr(),
+            hist_fresh=d["hist_fresh"].data_ptr(), hist_life=d["hist_life"].data_ptr(),
+            cand_news=d["cand_news"].data_ptr(), cand_fresh=d["cand_fresh"].data_ptr(),
+            cand_life=d["cand_life"].data_ptr(),
+            cand_remaining=d["cand_remaining"].data_ptr() if "cand_remaining" in d else None,
+            unit_imp=d["unit_imp"].data_ptr(),
+            unit_pair0=d["unit_pair0"].data_ptr(), unit_count=d["unit_count"].data_ptr(),
+            num_units=self.num_units, max_history=self.max_history, tile_c=self.tile_c)

@@ -1,0 +1,188 @@
+"""Tensor-level wrappers over the C ABI (include/lime_b200.h).
+
+torch is used for device memory and the current stream only; every computation below is a call
+into liblime_b200.so.  Inputs must be CUDA tensors of the stated dtype; nothing is copied or cast
+silently except where the docstring says so.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t, dtype, name):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.LimeError("%s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.data_ptr()
+
+
+def _rowmajor(t, name):
+    """(pointer-checked tensor, leading dimension) of a 2-D view whose last dim is contiguous."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError("%s must be 2-D with a contiguous last dimension" % name)
+    return t.stride(0)
+
+
+def bucketize(seconds, num_buckets):
+    """FreshnessEncoder.bucketize (newsEncoders.py:53-58): fp32 seconds -> int32 bucket ids."""
+    lib = _lib.require_device()
+    x = seconds.contiguous()
+    out = torch.empty(x.shape, dtype=torch.int32, device=x.device)
+    check(lib.lime_bucketize(_ptr(x, torch.float32, "seconds"), x.numel(), int(num_buckets),
+                             out.data_ptr(), _stream()), "lime_bucketize")
+    return out
+
+
+def linear(a, w, bias=None, residual=None, act=ACT_NONE, out=None, n=None, k=None, bf16=False):
+    """out[m, :n] = act(a[m, :k] @ w[:n, :k].T + bias) + residual.  a, w, residual, out are 2-D views
+    with contiguous last dim (arbitrary row stride); k, row strides of a and w multiples of 4."""
+    lib = _lib.require_device()
+    m = a.shape[0]
+    n = w.shape[0] if n is None else n
+    k = a.shape[1] if k is None else k
+    lda, ldw = _rowmajor(a, "a"), _rowmajor(w, "w")
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    ldc = _rowmajor(out, "out")
+    ldr = _rowmajor(residual, "residual") if residual is not None else 0
+    fn = lib.lime_linear_bf16 if bf16 else lib.lime_linear
+    check(fn(_ptr(a, torch.float32, "a"), lda, _ptr(w, torch.float32, "w"), ldw,
+             _ptr(bias, torch.float32, "bias"), _ptr(residual, torch.float32, "residual"), ldr,
+             _ptr(out, torch.float32, "out"), ldc, m, n, k, act, _stream()),
+          "lime_linear_bf16" if bf16 else "lime_linear")
+    return out
+
+
+def gemm_strided(a, b, alpha=1.0, out=None):
+    """out = alpha * a @ b for arbitrary-stride 2-D views (weight folding only)."""
+    lib = _lib.require_device()
+    m, k = a.shape
+    k2, n = b.shape
+    assert k == k2
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    check(lib.lime_gemm_strided(_ptr(a, torch.float32, "a"), a.stride(0), a.stride(1),
+                                _ptr(b, torch.float32, "b"), b.stride(0), b.stride(1),
+                                _ptr(out, torch.float32, "out"), _rowmajor(out, "out"),
+                                m, n, k, float(alpha), _stream()), "lime_gemm_strided")
+    return out
+
+
+def embed_pe(E, ids, T, pe, out):
+    lib = _lib.require_device()
+    rows = ids.numel()
+    check(lib.lime_embed_pe(_ptr(E, torch.float32, "E"), E.shape[0], _ptr(ids, torch.int32, "ids"),
+                            rows, T, E.shape[1], _ptr(pe, torch.float32, "pe"),
+                            _ptr(out, torch.float32, "out"), _stream()), "lime_embed_pe")
+    return out
+
+
+def mha(qkv, ctx, n_news, T, d, nhead):
+    lib = _lib.require_device()
+    check(lib.lime_mha(_ptr(qkv, torch.float32, "qkv"), _ptr(ctx, torch.float32, "ctx"), n_news, T, d,
+                       nhead, _stream()), "lime_mha")
+    return ctx
+
+
+def layernorm(x, gamma, beta, out, eps=1e-5):
+    lib = _lib.require_device()
+    check(lib.lime_layernorm(_ptr(x, torch.float32, "x"), _rowmajor(x, "x"),
+                             _ptr(gamma, torch.float32, "gamma"), _ptr(beta, torch.float32, "beta"),
+                             _ptr(out, torch.float32, "out"), _rowmajor(out, "out"), x.shape[0],
+                             x.shape[1], eps, _stream()), "lime_layernorm")
+    return out
+
+
+def layernorm_meanpool(x, gamma, beta, out, n_news, T, eps=1e-5):
+    """x [n_news*T, d] contiguous -> out[:, :d] (2-D view, any row stride)."""
+    lib = _lib.require_device()
+    check(lib.lime_layernorm_meanpool(_ptr(x, torch.float32, "x"), _ptr(gamma, torch.float32, "gamma"),
+                                      _ptr(beta, torch.float32, "beta"), _ptr(out, torch.float32, "out"),
+                                      _rowmajor(out, "out"), n_news, T, x.shape[1], eps, _stream()),
+          "lime_layernorm_meanpool")
+    return out
+
+
+def topic_rep(cat_emb, sub_emb, W, b, cat, sub, out, width):
+    lib = _lib.require_device()
+    check(lib.lime_topic_rep(_ptr(cat_emb, torch.float32, "cat_emb"), _ptr(sub_emb, torch.float32, "sub_emb"),
+                             _ptr(W, torch.float32, "W"), _ptr(b, torch.float32, "b"),
+                             _ptr(cat, torch.int32, "cat"), _ptr(sub, torch.int32, "sub"), cat.numel(),
+                             _ptr(out, torch.float32, "out"), _rowmajor(out, "out"), width, _stream()),
+          "lime_topic_rep")
+    return out
+
+
+def intent_pool(pre, e, w2, out, n, k, D):
+    lib = _lib.require_device()
+    check(lib.lime_intent_pool(_ptr(pre, torch.float32, "pre"), _ptr(e, torch.float32, "e"),
+                               _ptr(w2, torch.float32, "w2"), _ptr(out, torch.float32, "out"),
+                               _rowmajor(out, "out"), n, k, D, _stream()), "lime_intent_pool")
+    return out
+
+
+def content_fuse(title, body, cat_emb, sub_emb, cat, sub, out):
+    lib = _lib.require_device()
+    n, D = title.shape
+    check(lib.lime_content_fuse(_ptr(title, torch.float32, "title"), _ptr(body, torch.float32, "body"),
+                                _ptr(cat_emb, torch.float32, "cat_emb"), _ptr(sub_emb, torch.float32, "sub_emb"),
+                                _ptr(cat, torch.int32, "cat"), _ptr(sub, torch.int32, "sub"), n, D,
+                                cat_emb.shape[1], sub_emb.shape[1], _ptr(out, torch.float32, "out"),
+                                _rowmajor(out, "out"), _stream()), "lime_content_fuse")
+    return out
+
+
+def bucket_pairs(Ef, El, out):
+    lib = _lib.require_device()
+    check(lib.lime_bucket_pairs(_ptr(Ef, torch.float32, "Ef"), _ptr(El, torch.float32, "El"), Ef.shape[0],
+                                Ef.shape[1], _ptr(out, torch.float32, "out"), _stream()), "lime_bucket_pairs")
+    return out
+
+
+def scale_rows(M, row_scale=None, alpha=1.0):
+    lib = _lib.require_device()
+    check(lib.lime_scale_rows(_ptr(M, torch.float32, "M"), _rowmajor(M, "M"),
+                              _ptr(row_scale, torch.float32, "row_scale"), float(alpha), M.shape[0],
+                              M.shape[1], _stream()), "lime_scale_rows")
+    return M
+
+
+def prefix_rows(M):
+    lib = _lib.require_device()
+    check(lib.lime_prefix_rows(_ptr(M, torch.float32, "M"), _rowmajor(M, "M"), M.shape[0], M.shape[1],
+                               _stream()), "lime_prefix_rows")
+    return M
+
+
+def rank_metrics(scores, labels, cand_off, want_ranks=True):
+    """Per-impression stable ranks (int32 [P]) and [I,4] fp64 (auc, mrr, ndcg5, ndcg10)."""
+    lib = _lib.require_device()
+    I = cand_off.numel() - 1
+    ranks = torch.empty(scores.shape, dtype=torch.int32, device=scores.device) if want_ranks else None
+    metrics = torch.empty((I, 4), dtype=torch.float64, device=scores.device)
+    check(lib.lime_rank_metrics(_ptr(scores, torch.float32, "scores"), _ptr(labels, torch.uint8, "labels"),
+                                _ptr(cand_off, torch.int64, "cand_off"), I,
+                                ranks.data_ptr() if want_ranks else None, metrics.data_ptr(), _stream()),
+          "lime_rank_metrics")
+    return ranks, metrics
+
+
+def metrics_reduce(metrics):
+    """[I,4] fp64 -> fp64 [5] = (sum auc, sum mrr, sum ndcg5, sum ndcg10, valid impressions)."""
+    lib = _lib.require_device()
+    sums = torch.empty(5, dtype=torch.float64, device=metrics.device)
+    check(lib.lime_metrics_reduce(_ptr(metrics, torch.float64, "metrics"), metrics.shape[0],
+                                  sums.data_ptr(), _stream()), "lime_metrics_reduce")
+    return sums
