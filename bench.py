@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the LIME scoring hot path (BASELINE.json configs[1]).
+
+A *step* = one full evaluation pass over one impression set: fused scoring of every
+(impression, candidate) pair on the cached news vectors, per-impression stable ranking and
+AUC / MRR / nDCG@5 / nDCG@10, and (N > 1) the NCCL all-reduce of the five metric partial sums.
+Metric: impressions/s (whole job).  See DESIGN.md "Measurement" for every definition used here.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, sm_100a)
+  python bench.py --impl reference ...                      the reference's algorithm on host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "eval_impressions_per_sec"
+UNIT = "impressions/s"
+D, H = 400, 50
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--news", type=int, default=65238, help="news in the vector cache (MIND: 65,238)")
+    ap.add_argument("--vocab", type=int, default=40000)
+    ap.add_argument("--impressions", type=int, default=73152, help="impressions per step per GPU (MIND-small dev size)")
+    ap.add_argument("--batch-size", type=int, default=32, help="reference mini-batch size (GraphSAGE prefix)")
+    ap.add_argument("--cpu-pairs", type=int, default=192, help="pairs in the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bf16-encoder", action="store_true", help="run the 4 transformer GEMMs on tcgen05 (bf16 mode)")
+    return ap.parse_args()
+
+
+def algorithmic_bytes(imp):
+    """per impression (H + C)(D*4 + 4 + 4 + 4 + 8) + H + 4C bytes (fp32)."""
+    C = np.diff(imp.cand_off).astype(np.float64)
+    return float(np.sum((H + C) * (D * 4 + 20) + H + 4 * C))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_setup(args, rank, need_news_text=True):
+    from lime_cikm25_b200 import synth
+    from lime_cikm25_b200.config import default_config as make_config
+    cfg = make_config(vocabulary_size=args.vocab, batch_size=args.batch_size, word_embedding_init="skip")
+    news = synth.make_news_table(args.news, vocabulary_size=args.vocab, seed=1)
+    imp = synth.make_impressions(args.impressions, news.news_num, seed=100 + rank)
+    return cfg, news, imp
+
+
+def cpu_baseline(args, cfg, news, imp, model_sd, steps=None, warmup=0):
+    """The reference's algorithm (oracle port: per-pair batches, 51 news encodes per pair,
+    util.py:88-112) on the host cores, on a bounded sample of the same workload."""
+    from oracle import lime_oracle as O
+    from lime_cikm25_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    bs = args.batch_size
+    batches = []
+    for b in synth.impressions_to_pair_batches(news, imp.slice(0, min(imp.num_impressions, 64)), bs):
+        if len(b[0]) == bs:
+            batches.append(b)
+        if len(batches) * bs >= (args.cpu_pairs if steps is None else bs * (steps + warmup)):
+            break
+    cbar = float(np.mean(np.diff(imp.cand_off)))
+    times = []
+    with torch.no_grad():
+        for i, b in enumerate(batches):
+            t0 = time.perf_counter()
+            O.model_forward(model_sd, b, cfg)
+            times.append(time.perf_counter() - t0)
+    timed = times[warmup:] if len(times) > warmup else times
+    pairs_s = bs * len(timed) / sum(timed)
+    return {"value": pairs_s / cbar, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d mini-batches of %d (user,candidate) pairs, each pair re-encoding %d news as "
+                      "util.py:88-112 does; %.1f pairs/s; converted with mean %.1f candidates/impression"
+                      % (len(timed), bs, H + 1, pairs_s, cbar),
+            "pairs_per_sec": pairs_s, "ms_per_step": 1e3 * sum(timed) / len(timed)}
+
+
+def run_reference(args):
+    """--impl reference: rank 0 times the oracle port of the reference's CPU path."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import lime_cikm25_b200 as L
+    from lime_cikm25_b200 import synth
+    cfg, news, imp = make_setup(args, 0)
+    model = L.Model(cfg)
+    model.initialize()
+    synth.synthetic_parameters(model, seed=0)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    steps = max(1, min(args.steps, 12))
+    warm = max(1, min(args.warmup, 2))
+    cb = cpu_baseline(args, cfg, news, imp, sd, steps=steps, warmup=warm)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, imp),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, imp):
+    C = np.diff(imp.cand_off)
+    return {"workload": "MIND-large-shaped eval (BASELINE.json configs[1]): %d-news fp32 vector cache, "
+                        "impression scoring + AUC/MRR/nDCG@5/10" % args.news,
+            "news": args.news, "impressions_per_step_per_gpu": imp.num_impressions,
+            "pairs_per_step_per_gpu": int(imp.num_pairs), "history": H, "mean_candidates": float(C.mean()),
+            "max_candidates": int(C.max()), "reference_batch_size": args.batch_size, "num_buckets": 10,
+            "l2": "inputs exceed L2: the news-vector cache alone is %.0f MB vs 126 MB" % (args.news * 2572 * 4 / 1e6)}
+
+
+def run_b200(args):
+    import lime_cikm25_b200 as L
+    from lime_cikm25_b200 import _lib, engine, parallel, synth, util
+    import torch.distributed as dist
+
+    rank, world, local = parallel.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.require_device()
+    cfg, news, imp = make_setup(args, rank)
+    model = L.Model(cfg)
+    model.initialize()
+    synth.synthetic_parameters(model, seed=0)
+    sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()} if rank == 0 else None
+    model = model.to(dev).eval()
+    model.news_encoder.engine.bf16 = bool(args.bf16_encoder)
+
+    # ---- news-vector cache (Stage A), built once per checkpoint; timed and reported separately ----
+    with torch.no_grad():
+        model.scoring.fold()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cache = util.build_news_cache(model, news, dev)
+        torch.cuda.synchronize()
+        cache_s = time.perf_counter() - t0
+    dimp = engine.DeviceImpressions(imp, dev)
+    torch.cuda.synchronize()
+    scores = torch.empty(dimp.num_pairs, dtype=torch.float32, device=dev)
+    bs = args.batch_size
+
+    def step():
+        return util.evaluate_device(model, cache, dimp, bs, scores_out=scores, want_ranks=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(3, args.warmup)):
+            step()
+        barrier()
+        # ---- timed region: exactly K steps, CUDA events on the launching stream, max over ranks ----
+        sampler = ClockSampler(local) if rank == 0 else None
+        lib.lime_launch_count_reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            _, _, _, sums = step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = int(lib.lime_launch_count())
+        result = sums.tolist()
+        # ---- the dominant kernel alone (roofline numerator) ----
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(args.steps):
+            util.score_impressions(model, cache, dimp, bs, out=scores)
+        k1.record()
+        torch.cuda.synchronize()
+        kernel_ms = k0.elapsed_time(k1) / args.steps
+        # ---- end to end: host (pinned) inputs -> H2D -> score -> metrics -> D2H of the 5 sums ----
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            dimp.upload()
+            s = step()[3].tolist()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    tot = torch.tensor([dimp.num_impressions, dimp.num_pairs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms, e2e_ms = t.tolist()
+    total_imp, total_pairs = tot.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg = algorithmic_bytes(imp)
+    achieved = alg / (kernel_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": total_imp * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, imp),
+        "pairs_per_sec": total_pairs * args.steps / (ms * 1e-3),
+        "e2e": {"value": total_imp * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": dimp.h2d_bytes(), "d2h_bytes_per_step": 40},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "lime::score_kernel<2>", "kernel_ms": kernel_ms,
+                     "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                     "note": "exact fp32 per-pair semantics make this kernel MUFU/issue-bound, not HBM-bound: "
+                             "DESIGN.md 'Scoring kernel roofline'"},
+        "clocks": clocks,
+        "cache_build": {"seconds": cache_s, "news_per_sec": news.news_num / cache_s,
+                        "tflops": news.news_num * 241.3e6 / cache_s / 1e12,
+                        "encoder": "bf16 tcgen05" if args.bf16_encoder else "fp32"},
+        "metrics": {"auc": result[0] / result[4], "mrr": result[1] / result[4],
+                    "ndcg5": result[2] / result[4], "ndcg10": result[3] / result[4]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(args, cfg, news, imp, sd_cpu)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

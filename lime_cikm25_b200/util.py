@@ -80,16 +80,25 @@ def score_impressions(model, cache: NewsVectorCache, dimp: DeviceImpressions, ba
                                pair_index_base=pair_index_base, out=out)
 
 
+def evaluate_device(model, cache, dimp, batch_size, pair_index_base=0, total_pairs=None, group=None,
+                    scores_out=None, want_ranks=True):
+    """The device-side part of evaluate_impressions, fully asynchronous: 3 kernel launches (score,
+    rank+metrics, reduce) and, in a process group, one all-reduce.  Returns device tensors."""
+    scores = score_impressions(model, cache, dimp, batch_size, pair_index_base, total_pairs, out=scores_out)
+    ranks, per_imp = ops.rank_metrics(scores, dimp.dev["labels"], dimp.dev["cand_off"], want_ranks=want_ranks)
+    sums = ops.metrics_reduce(per_imp)
+    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        torch.distributed.all_reduce(sums, group=group)
+    return scores, ranks, per_imp, sums
+
+
 def evaluate_impressions(model, cache, dimp, batch_size, pair_index_base=0, total_pairs=None,
                          group=None, return_details=False):
     """Scores -> per-impression stable ranks -> (auc, mrr, ndcg5, ndcg10) averaged over impressions,
     all on the device.  With a ``torch.distributed`` process group the five partial sums are
     all-reduced (NCCL), so every rank returns the global means."""
-    scores = score_impressions(model, cache, dimp, batch_size, pair_index_base, total_pairs)
-    ranks, per_imp = ops.rank_metrics(scores, dimp.dev["labels"], dimp.dev["cand_off"])
-    sums = ops.metrics_reduce(per_imp)
-    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-        torch.distributed.all_reduce(sums, group=group)
+    scores, ranks, per_imp, sums = evaluate_device(model, cache, dimp, batch_size, pair_index_base,
+                                                   total_pairs, group)
     s = sums.tolist()                                # device -> host read of the step's result
     result = tuple(x / s[4] for x in s[:4])
     if return_details:

@@ -1,0 +1,180 @@
+"""Unit parity of every C-ABI kernel against a plain torch reference of the same op (fp64 where
+rounding matters).  All calls go through ctypes into liblime_b200.so."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from lime_cikm25_b200 import ops  # noqa: E402
+from oracle import lime_oracle as O  # noqa: E402
+
+DEV = "cuda"
+
+
+def gen(seed):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+def randn(*shape, seed=0, scale=1.0):
+    return (torch.randn(*shape, generator=gen(seed)) * scale).to(DEV)
+
+
+def close(got, want, tol=1e-5):
+    want = want.double()
+    err = (got.double() - want).abs().max().item()
+    scale = want.pow(2).mean().sqrt().item() + 1e-30
+    assert err <= tol * scale, "max err %.3e vs rms %.3e" % (err, scale)
+
+
+def test_bucketize_bit_exact(lib, golden_dir):
+    g = np.load(os.path.join(golden_dir, "buckets.npz"))
+    for nb in (10, 20, 50):
+        x = torch.from_numpy(g["x_%d" % nb]).to(DEV)
+        got = ops.bucketize(x, nb)
+        # (1) the reference's own op sequence evaluated by torch on this GPU
+        xc = torch.clamp(x.float(), min=1)
+        want = torch.clamp((torch.log(xc) / torch.log(torch.tensor(60 * 60 * 24.0)) * (nb / 7)).long(), max=nb - 1)
+        assert torch.equal(got.long(), want)
+        # (2) the golden ids produced by the reference on CPU
+        assert np.array_equal(got.cpu().numpy(), g["b_%d" % nb])
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 7, 52), (37, 300, 300), (129, 900, 300), (256, 512, 300), (300, 300, 512),
+                                   (77, 1207, 400), (100, 510, 52), (64, 400, 900), (100, 900, 1000), (5, 1200, 352)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_linear(lib, m, n, k, act):
+    a, w, b = randn(m, k, seed=1), randn(n, k, seed=2, scale=k ** -0.5), randn(n, seed=3)
+    r = randn(m, n, seed=4)
+    got = ops.linear(a, w, b, residual=r, act=act)
+    z = a.double() @ w.double().t() + b.double()
+    z = [z, torch.relu(z), torch.tanh(z)][act] + r.double()
+    close(got, z, 2e-6)
+    close(ops.linear(a, w, act=act), [lambda t: t, torch.relu, torch.tanh][act](a.double() @ w.double().t()), 2e-6)
+
+
+def test_linear_strided_views(lib):
+    big_a = randn(50, 852, seed=5)
+    big_w = randn(400, 1800, seed=6, scale=0.03)
+    out = torch.zeros(50, 1720, device=DEV)
+    ops.linear(big_a[:, 400:800], big_w[:, 900:1300], out=out[:, 1208:1608])
+    close(out[:, 1208:1608], big_a[:, 400:800].double() @ big_w[:, 900:1300].double().t(), 2e-6)
+    assert float(out[:, :1208].abs().sum()) == 0 and float(out[:, 1608:].abs().sum()) == 0
+
+
+def test_gemm_strided(lib):
+    a, b = randn(400, 40, seed=7), randn(40, 50, seed=8)
+    close(ops.gemm_strided(a, b, alpha=0.5), 0.5 * a.double() @ b.double())
+    close(ops.gemm_strided(a.t(), a), a.double().t() @ a.double())           # transposed view
+    out = torch.zeros(50, 10, 52, device=DEV)
+    ops.gemm_strided(b.t(), b, out=out[:, 3, :50])
+    close(out[:, 3, :50], b.double().t() @ b.double())
+
+
+@pytest.mark.parametrize("T", [32, 128])
+def test_embed_pe_and_mha(lib, T):
+    n, d, heads, V = 9, 300, 10, 100
+    E = randn(V, d, seed=9, scale=0.1)
+    ids = torch.randint(0, V, (n * T,), generator=gen(10)).to(torch.int32).to(DEV)
+    pe = O.positional_encoding(T, d, torch.float32).to(DEV)
+    x = torch.empty(n * T, d, device=DEV)
+    ops.embed_pe(E, ids, T, pe, x)
+    assert torch.equal(x.view(n, T, d), E[ids.long()].view(n, T, d) + pe)
+    qkv = randn(n * T, 3 * d, seed=11)
+    ctx = torch.empty(n * T, d, device=DEV)
+    ops.mha(qkv, ctx, n, T, d, heads)
+    q, k, v = qkv.double().view(n, T, 3, heads, d // heads).permute(2, 0, 3, 1, 4)
+    att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d // heads), dim=-1)
+    close(ctx.view(n, T, d), (att @ v).transpose(1, 2).reshape(n, T, d), 2e-6)
+
+
+def test_layernorm_and_meanpool(lib):
+    rows, d, T = 7 * 32, 300, 32
+    x, g, b = randn(rows, d, seed=12) + 0.3, randn(d, seed=13) * 0.1 + 1, randn(d, seed=14) * 0.1
+    y = torch.empty_like(x)
+    ops.layernorm(x, g, b, y)
+    want = torch.nn.functional.layer_norm(x.double(), (d,), g.double(), b.double(), 1e-5)
+    close(y, want, 2e-6)
+    out = torch.zeros(7, 352, device=DEV)
+    ops.layernorm_meanpool(x, g, b, out, 7, T)
+    close(out[:, :300], want.view(7, T, d).mean(1), 2e-6)
+    assert float(out[:, 300:].abs().sum()) == 0
+    y400 = torch.empty(5, 400, device=DEV)
+    x400 = randn(5, 400, seed=15)
+    ops.layernorm(x400, randn(400, seed=16), randn(400, seed=17), y400)
+    close(y400, torch.nn.functional.layer_norm(x400.double(), (400,), randn(400, seed=16).double(), randn(400, seed=17).double()), 2e-6)
+
+
+def test_topic_intent_content(lib):
+    n = 33
+    ce, se = randn(18, 50, seed=18, scale=0.1), randn(270, 50, seed=19, scale=0.1)
+    W, b = randn(50, 100, seed=20, scale=0.1), randn(50, seed=21, scale=0.1)
+    cat = torch.randint(0, 18, (n,), generator=gen(22)).to(torch.int32).to(DEV)
+    sub = torch.randint(0, 270, (n,), generator=gen(23)).to(torch.int32).to(DEV)
+    out = torch.full((n, 352), 7.0, device=DEV)
+    ops.topic_rep(ce, se, W, b, cat, sub, out[:, 300:], 52)
+    want = torch.cat([ce[cat.long()], se[sub.long()]], 1).double() @ W.double().t() + b.double()
+    close(out[:, 300:350], want, 2e-6)
+    assert float(out[:, 350:].abs().sum()) == 0 and float((out[:, :300] - 7).abs().sum()) == 0
+    # intent attention pooling
+    e, pre, w2 = randn(n, 3, 400, seed=24).relu(), randn(n, 3, 400, seed=25), randn(400, seed=26, scale=0.07)
+    pooled = torch.empty(n, 400, device=DEV)
+    ops.intent_pool(pre.view(n * 3, 400), e.view(n, 1200), w2, pooled, n, 3, 400)
+    alpha = torch.softmax(torch.tanh(pre.double()) @ w2.double(), dim=1)
+    close(pooled, (alpha.unsqueeze(-1) * e.double()).sum(1), 2e-6)
+    # cosine gate + concat
+    t, bd = randn(n, 400, seed=27).relu(), randn(n, 400, seed=28).relu()
+    content = torch.empty(n, 900, device=DEV)
+    ops.content_fuse(t, bd, ce, se, cat, sub, content)
+    sim = (torch.nn.functional.cosine_similarity(t.double(), bd.double(), dim=1) + 1) / 2
+    close(content, torch.cat([t.double(), sim.unsqueeze(1) * bd.double(), ce[cat.long()].double(), se[sub.long()].double()], 1), 2e-6)
+
+
+def test_small_helpers(lib):
+    Ef, El = randn(10, 500, seed=29), randn(10, 500, seed=30)
+    out = torch.empty(100, 1000, device=DEV)
+    ops.bucket_pairs(Ef, El, out)
+    assert torch.equal(out.view(10, 10, 1000)[3, 7], torch.cat([Ef[3], El[7]]))
+    M = randn(6, 40, seed=31)
+    want = M.double() * (randn(6, seed=32).double() * 0.25).unsqueeze(1)
+    ops.scale_rows(M, randn(6, seed=32), 0.25)
+    close(M, want, 1e-6)
+    Pm = randn(9, 33, seed=33)
+    wantp = Pm.double().cumsum(0)
+    ops.prefix_rows(Pm)
+    close(Pm, wantp, 1e-6)
+
+
+def test_rank_metrics_match_reference_golden(lib, golden_dir):
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    scores = torch.from_numpy(g["scores"]).to(DEV)
+    labels = torch.from_numpy(g["labels"]).to(DEV)
+    off = torch.from_numpy(g["cand_off"]).to(DEV)
+    ranks, per = ops.rank_metrics(scores, labels, off)
+    assert np.array_equal(ranks.cpu().numpy(), g["ranks"])          # stable ties, -0.0 == 0.0
+    sums = ops.metrics_reduce(per).cpu().numpy()
+    assert sums[4] == len(g["cand_off"]) - 1
+    assert np.allclose(sums[:4] / sums[4], g["metrics"], rtol=0, atol=1e-12)
+    # per-impression values against the oracle's restatement of evaluate.py
+    per = per.cpu().numpy()
+    o = g["cand_off"]
+    for i in (0, 10, 57, 199):
+        rk = O.rank_impression(g["scores"][o[i]:o[i + 1]])
+        assert np.allclose(per[i], O.impression_metrics(rk, g["labels"][o[i]:o[i + 1]]), atol=1e-12)
+
+
+def test_rank_metrics_edge_cases(lib):
+    # empty impression is skipped (evaluate.py:44-45); a 1-candidate impression has no AUC
+    scores = torch.tensor([0.5, 0.5, 0.5, -1.0, 2.0], device=DEV)
+    labels = torch.tensor([0, 1, 0, 1, 0], dtype=torch.uint8, device=DEV)
+    off = torch.tensor([0, 3, 3, 5], device=DEV)
+    ranks, per = ops.rank_metrics(scores, labels, off)
+    assert ranks.tolist() == [1, 2, 3, 2, 1]
+    per = per.cpu().numpy()
+    assert np.isnan(per[1]).all()
+    assert per[0, 0] == 0.5 and per[0, 1] == 0.5 and per[2, 0] == 0.0
+    sums = ops.metrics_reduce(torch.from_numpy(per).to(DEV)).cpu().numpy()
+    assert sums[4] == 2

@@ -1,0 +1,260 @@
+"""End-to-end parity of the CUDA path with (a) the golden vectors produced by the unmodified
+reference and (b) the CPU oracle, through the drop-in module API and the C ABI.
+
+Logit tolerance: 1e-4 relative (north star), measured as max|a-b| / max(|b|, 0.1*rms(b)) — see
+tests/test_oracle_golden.py::rel for why a floor is needed; integer work (buckets, ranks) is exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import lime_cikm25_b200 as L  # noqa: E402
+from lime_cikm25_b200 import engine, ops, parallel, synth, util  # noqa: E402
+from oracle import lime_oracle as O  # noqa: E402
+from oracle.make_golden import CASES, case_inputs  # noqa: E402
+from oracle.ref_import import make_config  # noqa: E402
+
+DEV = "cuda"
+TOL = 1e-4
+
+
+def rel(a, b, floor=None):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    if floor is None:
+        floor = 0.1 * float(np.sqrt(np.mean(b * b))) + 1e-30
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def load_case(case, golden_dir, **cfg_over):
+    spec, cfg, news, imp = case_inputs(case)
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    cfg.word_embedding_init = "skip"
+    for k, v in cfg_over.items():
+        setattr(cfg, k, v)
+    model = L.Model(cfg)
+    model.initialize()
+    checksum = synth.synthetic_parameters(model, spec["weights_seed"])
+    assert checksum == float(g["weights_checksum"]), "synthetic weights were not regenerated identically"
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    return cfg, news, imp, g, sd, model.to(DEV).eval()
+
+
+@pytest.mark.parametrize("case", ["small_bs8", "buckets20"])
+def test_news_encoder_stage_vectors(lib, case, golden_dir):
+    """CROWN.forward -> 900-d content and LIME.forward -> 400-d vectors vs the reference's outputs."""
+    cfg, news, imp, g, sd, model = load_case(case, golden_dir)
+    n0 = g["content"].shape[0]
+    t = lambda a: torch.as_tensor(a[:n0]).unsqueeze(0).to(DEV)
+    fresh, life = torch.as_tensor(g["stage_fresh"]).to(DEV), torch.as_tensor(g["stage_life"]).to(DEV)
+    args = (t(news.title_text), t(news.title_mask), t(news.title_text) * 0, t(news.body_text), t(news.body_mask),
+            t(news.body_text) * 0, t(news.category), t(news.subCategory), None)
+    with torch.no_grad():
+        content = model.news_encoder.base_news_encoder(*args, None, None)[0]
+        vec = model.news_encoder(*args, fresh.unsqueeze(0), life.unsqueeze(0))[0]
+    assert content.shape == (n0, 900) and vec.shape == (n0, 400)
+    assert rel(content.cpu().numpy(), g["content"]) < TOL
+    assert rel(vec.cpu().numpy(), g["lime_vec"]) < TOL
+    # the cache's two-part representation reproduces the same vector
+    hist, cand = model.scoring.build_rows(*(x[0].contiguous() for x in (args[0], args[3], args[6], args[7])))
+    assert rel(model.scoring.lime_vectors(hist, fresh, life).cpu().numpy(), g["lime_vec"]) < TOL
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_model_forward_matches_reference(lib, case, golden_dir):
+    """Model.forward on the reference's own eval mini-batches (26 tensors, one pair per sample)."""
+    cfg, news, imp, g, sd, model = load_case(case, golden_dir)
+    out = []
+    with torch.no_grad():
+        for batch in synth.impressions_to_pair_batches(news, imp, cfg.batch_size):
+            tb = [torch.as_tensor(x).to(DEV) for x in batch]
+            logits = model(*tb, tb[24] - tb[23])
+            assert logits.shape == (len(batch[0]), 1)
+            out.append(logits.squeeze(1).cpu())
+    scores = torch.cat(out).numpy()
+    assert np.array_equal(scores == 0, g["scores"] == 0)           # saturated weights give exact zeros
+    assert rel(scores, g["scores"]) < TOL
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_cached_impression_eval_matches_reference(lib, case, golden_dir):
+    """News-vector cache + impression-major scoring + device ranking/metrics == compute_scores."""
+    cfg, news, imp, g, sd, model = load_case(case, golden_dir)
+    with torch.no_grad():
+        cache = util.build_news_cache(model, news)
+        dimp = engine.DeviceImpressions(imp, DEV)
+        metrics, det = util.evaluate_impressions(model, cache, dimp, cfg.batch_size, return_details=True)
+    scores = det["scores"].cpu().numpy()
+    assert np.array_equal(scores == 0, g["scores"] == 0)
+    assert rel(scores, g["scores"]) < TOL
+    assert np.allclose(metrics, g["metrics"], atol=1e-3)
+    # ranks: exact unless two non-tied reference scores are closer than the fp32 tolerance
+    ranks = det["ranks"].cpu().numpy()
+    want = np.concatenate(O.evaluate_impressions(
+        [scores[imp.cand_off[i]:imp.cand_off[i + 1]] for i in range(imp.num_impressions)],
+        [imp.labels[imp.cand_off[i]:imp.cand_off[i + 1]] for i in range(imp.num_impressions)])[1])
+    assert np.array_equal(ranks, want)
+    assert (ranks != g["ranks"]).mean() < 0.1
+    # base score (no lifetime weighting) exposes every pair un-saturated
+    model.config.use_remaining_lifetime_weighting = False
+    with torch.no_grad():
+        base = util.score_impressions(model, cache, dimp, cfg.batch_size).cpu().numpy()
+    assert rel(base, g["base_scores"]) < TOL
+
+
+def _stage_b_oracle(model, sd, cfg, cache, news, imp, prefix):
+    """CPU oracle of the user encoder + click score on the GPU-built LIME vectors (isolates Stage B)."""
+    se = model.scoring
+    out = np.zeros(imp.num_pairs, np.float32)
+    H = imp.hist_news.shape[1]
+    for i in range(imp.num_impressions):
+        hn = torch.as_tensor(imp.hist_news[i]).long()
+        hv = se.lime_vectors(cache.hist_rows[hn.to(DEV)], torch.as_tensor(imp.hist_fresh[i]).to(DEV),
+                             torch.as_tensor(imp.hist_life[i]).to(DEV)).cpu()
+        for p in range(imp.cand_off[i], imp.cand_off[i + 1]):
+            cn = int(imp.cand_news[p])
+            cv = se.lime_vectors(cache.hist_rows[cn:cn + 1], torch.as_tensor(imp.cand_fresh[p:p + 1]).to(DEV),
+                                 torch.as_tensor(imp.cand_life[p:p + 1]).to(DEV)).cpu()
+            u = O.crown_user(sd, hv.view(1, H, -1), torch.as_tensor(news.category[hn]).view(1, H),
+                             torch.as_tensor(news.subCategory[hn]).view(1, H),
+                             torch.as_tensor(news.category[cn:cn + 1]).view(1, 1),
+                             torch.as_tensor(news.subCategory[cn:cn + 1]).view(1, 1),
+                             torch.as_tensor(imp.hist_mask[i]).view(1, H), cv.view(1, 1, -1), cfg,
+                             prefix_len=prefix)
+            r = torch.tensor(imp.cand_life[p] - imp.cand_fresh[p])
+            out[p] = float((u * cv.view(1, 1, -1)).sum() * O.lifetime_weight(r, cfg))
+    return out
+
+
+@pytest.mark.parametrize("H,cand,prefix", [(200, 70, 32), (100, 5, 120), (20, 300, 7), (50, 1, 64)])
+def test_scoring_kernel_sweep_shapes(lib, H, cand, prefix):
+    """Sweep shapes of BASELINE.json configs[4]: history up to 200 (multi-chunk register tiling),
+    300 candidates (multi-unit impressions), GraphSAGE prefix below / above H."""
+    cfg = make_config(vocabulary_size=400, batch_size=128, max_history_num=H, word_embedding_init="skip")
+    model = L.Model(cfg)
+    model.initialize()
+    synth.synthetic_parameters(model, 5)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).eval()
+    news = synth.make_news_table(90, vocabulary_size=400, seed=H)
+    imp = synth.make_impressions(2, news.news_num, max_history=H, cand_fixed=cand, near_zero_frac=0.9, seed=cand)
+    imp.hist_mask[1, H // 2:] = False
+    with torch.no_grad():
+        cache = util.build_news_cache(model, news)
+        dimp = engine.DeviceImpressions(imp, DEV)
+        got = model.scoring.score(cache.hist_rows, cache.cand_rows, dimp, prefix_main=prefix).cpu().numpy()
+        want = _stage_b_oracle(model, sd, cfg, cache, news, imp, prefix)
+    assert rel(got, want) < TOL
+
+
+def test_bucket_sweep_and_flags(lib):
+    """B = 50 buckets (2,500-entry tables) and the weighting flags of util.py:34-46."""
+    for over in (dict(num_buckets=50), dict(use_expired_penalty=False), dict(use_remaining_lifetime_weighting=False)):
+        cfg = make_config(vocabulary_size=300, batch_size=8, word_embedding_init="skip", **over)
+        model = L.Model(cfg)
+        model.initialize()
+        synth.synthetic_parameters(model, 6)
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        model = model.to(DEV).eval()
+        news = synth.make_news_table(40, vocabulary_size=300, seed=1)
+        imp = synth.make_impressions(3, news.news_num, cand_fixed=4, near_zero_frac=0.8, seed=2)
+        with torch.no_grad():
+            cache = util.build_news_cache(model, news)
+            got = util.score_impressions(model, cache, engine.DeviceImpressions(imp, DEV), 8).cpu().numpy()
+            want = O.score_pairs_reference_style(sd, news, imp, cfg, 8).numpy()
+        assert rel(got, want) < TOL, over
+
+
+def test_properties_at_scale(lib):
+    """Size-independent properties on a MIND-shaped run too large for the CPU oracle: determinism,
+    invariance to the unit tiling and to rank sharding, rank permutations, metric ranges."""
+    cfg = make_config(vocabulary_size=5000, batch_size=32, word_embedding_init="skip")
+    model = L.Model(cfg)
+    model.initialize()
+    synth.synthetic_parameters(model, 7)
+    model = model.to(DEV).eval()
+    news = synth.make_news_table(3000, vocabulary_size=5000, seed=11)
+    imp = synth.make_impressions(4000, news.news_num, seed=12)
+    with torch.no_grad():
+        cache = util.build_news_cache(model, news)
+        cache2 = util.build_news_cache(model, news, chunk=700)
+        assert torch.equal(cache.hist_rows, cache2.hist_rows) and torch.equal(cache.cand_rows, cache2.cand_rows)
+        d52 = engine.DeviceImpressions(imp, DEV)
+        d13 = engine.DeviceImpressions(imp, DEV, tile_c=13)
+        m1, det1 = util.evaluate_impressions(model, cache, d52, 32, return_details=True)
+        m2, det2 = util.evaluate_impressions(model, cache, d52, 32, return_details=True)
+        s13 = util.score_impressions(model, cache, d13, 32)
+    assert torch.equal(det1["scores"], det2["scores"]) and m1 == m2                 # deterministic
+    assert torch.equal(det1["scores"], s13)                                          # tiling-invariant
+    assert all(0.0 <= x <= 1.0 for x in m1)
+    ranks = det1["ranks"].cpu().numpy()
+    for i in range(0, imp.num_impressions, 97):
+        r = np.sort(ranks[imp.cand_off[i]:imp.cand_off[i + 1]])
+        assert np.array_equal(r, np.arange(1, len(r) + 1))                           # a permutation of 1..C
+    # 4-way impression sharding (what 4 ranks would do) reproduces scores bit-for-bit and the means
+    sums = torch.zeros(5, dtype=torch.float64, device=DEV)
+    parts = []
+    with torch.no_grad():
+        for r in range(4):
+            sub, base, total = parallel.shard_impressions(imp, r, 4)
+            d = engine.DeviceImpressions(sub, DEV)
+            _, det = util.evaluate_impressions(model, cache, d, 32, pair_index_base=base, total_pairs=total,
+                                               return_details=True)
+            parts.append(det["scores"])
+            sums += det["sums"]
+    assert torch.equal(torch.cat(parts), det1["scores"])
+    assert np.allclose((sums[:4] / sums[4]).cpu().numpy(), m1, atol=1e-12)
+    # scores do not depend on the order of the candidates inside an impression
+    perm = imp.slice(0, 50)
+    order = np.concatenate([np.arange(perm.cand_off[i], perm.cand_off[i + 1])[::-1] for i in range(50)])
+    flipped = synth.Impressions(perm.hist_news, perm.hist_mask, perm.hist_fresh, perm.hist_life, perm.cand_off,
+                                perm.cand_news[order], perm.cand_fresh[order], perm.cand_life[order],
+                                perm.labels[order], perm.user_id)
+    with torch.no_grad():
+        a = model.scoring.score(cache.hist_rows, cache.cand_rows, engine.DeviceImpressions(perm, DEV), 32)
+        b = model.scoring.score(cache.hist_rows, cache.cand_rows, engine.DeviceImpressions(flipped, DEV), 32)
+    assert torch.equal(a[torch.as_tensor(order).to(DEV)], b)
+
+
+def test_compute_scores_drop_in(lib, tmp_path, monkeypatch):
+    """util.compute_scores with the reference's signature: rank file + truth file round trip."""
+    import types
+    cfg = make_config(vocabulary_size=300, batch_size=8, word_embedding_init="skip", category_lifetime_map=None)
+    model = L.Model(cfg)
+    model.initialize()
+    synth.synthetic_parameters(model, 8)
+    model = model.to(DEV)
+    news = synth.make_news_table(40, vocabulary_size=300, seed=3)
+    imp = synth.make_impressions(9, news.news_num, cand_mean=5, near_zero_frac=0.5, seed=4)
+    beh, idx = [], []
+    for i in range(imp.num_impressions):
+        n = int(imp.hist_mask[i].sum())
+        for p in range(imp.cand_off[i], imp.cand_off[i + 1]):
+            beh.append([int(imp.user_id[i]), imp.hist_news[i].tolist(), imp.hist_mask[i].copy(), int(imp.cand_news[p]),
+                        i, float(imp.cand_fresh[p]), float(imp.cand_life[p]), imp.hist_fresh[i, :n].tolist(),
+                        imp.hist_life[i, :n].tolist()])
+            idx.append(i)
+    corpus = types.SimpleNamespace(
+        dev_behaviors=beh, dev_indices=idx, max_history_num=50,
+        config=types.SimpleNamespace(vocabulary_size=300, category_num=18, subCategory_num=270),
+        news_title_text=news.title_text, news_title_mask=news.title_mask, news_abstract_text=news.body_text,
+        news_abstract_mask=news.body_mask, news_category=news.category, news_subCategory=news.subCategory)
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("dev/ref")
+    with open("dev/ref/truth-small.txt", "w") as f:
+        for i in range(imp.num_impressions):
+            lab = imp.labels[imp.cand_off[i]:imp.cand_off[i + 1]].tolist()
+            f.write(("" if i == 0 else "\n") + str(i + 1) + " " + str(lab).replace(" ", ""))
+    res = str(tmp_path / "res.txt")
+    metrics = util.compute_scores(model, corpus, 8, "dev", res, "small")
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    want_scores = O.score_pairs_reference_style(sd, news, imp, cfg, 8).numpy()
+    want, ranks = O.evaluate_impressions(
+        [want_scores[imp.cand_off[i]:imp.cand_off[i + 1]] for i in range(imp.num_impressions)],
+        [imp.labels[imp.cand_off[i]:imp.cand_off[i + 1]] for i in range(imp.num_impressions)])
+    assert np.allclose(metrics, want, atol=1e-3)
+    lines = open(res).read().split("\n")
+    assert len(lines) == imp.num_impressions and lines[0].startswith("1 [")
