@@ -58,15 +58,19 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // FreshnessEncoder.bucketize (newsEncoders.py:53-58), bit-exact with the reference's fp32 op
-// sequence: clamp(min=1) -> log -> divide by fp32 log(86400) -> multiply by fp32(num_buckets/7)
-// -> truncate -> clamp(max=num_buckets-1).  The divisor is the CPU 0-dim tensor
-// torch.log(torch.tensor(86400.)) = 0x4135de2e; `scale` is (float)(num_buckets / 7.0) computed on
-// the host in double then rounded, as torch does for tensor * python-float.  No fast-math here.
+// sequence AS ATen EXECUTES IT ON CUDA (the reference asserts a GPU, config.py:212):
+// clamp(min=1) -> log -> "divide" by the CPU 0-dim tensor torch.log(torch.tensor(86400.)) =
+// 0x4135de2e, which ATen's CUDA div kernel turns into a multiplication by the fp32 reciprocal
+// (BinaryDivTrueKernel.cu: iter.is_cpu_scalar(2) -> a * (1/b)) -> multiply by fp32(num_buckets/7)
+// (python double rounded to fp32, as tensor * python-float does) -> truncate -> clamp(max).
+// The CPU path of the same reference performs a true division and differs on 57 of 20,654
+// knife-edge inputs at B = 50 (none at B = 10, 20): tests/test_gpu_kernels.py.  No fast-math here.
 __device__ __forceinline__ int bucketize_seconds(float x, float scale, int num_buckets) {
     x = fmaxf(x, 1.0f);
     if (x != x) x = 1.0f;  // torch.clamp propagates NaN; a NaN age has no bucket -> treat as 1 s
     const float log_day = __uint_as_float(0x4135de2eu);
-    float scaled = __fdiv_rn(logf(x), log_day);
+    const float inv_log_day = __fdiv_rn(1.0f, log_day);
+    float scaled = __fmul_rn(logf(x), inv_log_day);
     float prod = __fmul_rn(scaled, scale);
     long long b = (long long)prod;  // truncation toward zero, like Tensor.long()
     if (b > num_buckets - 1) b = num_buckets - 1;

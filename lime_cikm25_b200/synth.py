@@ -149,9 +149,9 @@ def make_impressions(num_impressions, news_num, *, max_history=50, cand_mean=37.
     labels = (rng.random(P) < 0.1).astype(np.uint8)
     first = cand_off[:-1]
     pos_slot = first + rng.integers(0, C)
-    neg_slot = first + (pos_slot - first + 1 + rng.integers(0, C - 1)) % C
-    labels[pos_slot] = 1
+    neg_slot = first + (pos_slot - first + 1 + rng.integers(0, np.maximum(C - 1, 1))) % C
     labels[neg_slot] = 0
+    labels[pos_slot] = 1           # a single-candidate impression (C == 1) keeps its positive only
     user_id = rng.integers(0, num_users, size=I).astype(np.int64)
     return Impressions(hist_news, hist_mask, hist_fresh, hist_life, cand_off, cand_news,
                        cand_fresh, cand_life, labels, user_id)
