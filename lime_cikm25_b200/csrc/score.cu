@@ -19,10 +19,11 @@
 // (the LayerNorm is folded into the dots).  Everything linear in c is cached per news / per
 // lifetime-bucket pair at cache-build time (cand_rows / cand_tab).
 //
-// Thread mapping (phase 2, the hot loop): 13 warps; a warp owns 4 history rows, 8 lanes per row,
-// a lane holds dims d = l8 + 8*j (j < 50) of v_h and W_g v_h in REGISTERS for the whole unit, so the
-// per-candidate loop touches only shared memory: one LDS.128 per element fetches
-// (gate bias, w1, w2, w3)[d], identical across the 4 row groups of a warp (broadcast, 1 wavefront).
+// Thread mapping (phase 2, the hot loop): 13 warps; a warp owns 4 history rows; a lane holds dims
+// d = lane + 32*j (j < 13) of v_h and W_g v_h of those 4 rows in REGISTERS for the whole unit, so the
+// per-candidate loop touches only shared memory: one conflict-free LDS.128 fetches
+// (gate bias, w1, w2, w3)[d] and is reused by the 4 rows (0.25 LDS per element).  The 4x5 partial
+// sums of a warp are reduced with a split butterfly (30 shuffles instead of 100).
 // A work unit is <= tile_c consecutive candidates of one impression; CTAs are persistent (one per
 // SM) and pull units from a global counter.
 #include "common.cuh"
@@ -33,7 +34,9 @@ constexpr int kD = LIME_D;
 constexpr int kEPL = kD / 8;        // elements per lane (50)
 constexpr int kWarps = 13;
 constexpr int kThreads = kWarps * 32;
-constexpr int kRowsPerChunk = kWarps * 4;   // 52 history rows resident in registers at a time
+constexpr int kRowsPerWarp = 4;
+constexpr int kRowsPerChunk = kWarps * kRowsPerWarp;   // 52 history rows resident in registers at a time
+constexpr int kSlots = (kD + 31) / 32;      // 13 register slots per lane and row (d = lane + 32 j)
 constexpr int kTStride = LIME_TOPIC + 1;    // 51: conflict-free column reads of the topic tile
 constexpr int kTqStride = 12;               // heads padded 10 -> 12 (3 x LDS.128)
 constexpr int kTqWarp = LIME_TOPIC * kTqStride + kTqStride;   // 612 floats per warp
@@ -141,7 +144,7 @@ __device__ __forceinline__ float lifetime_weight(float r, const LimeNewsCache &c
 }
 
 template <int MAXP>
-__global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args) {
+__global__ void __maxnreg__(152) score_kernel(const ScoreArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const LimeNewsCache &C = args.cache;
     const LimeImpressions &I = args.imp;
@@ -153,8 +156,6 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int l8 = lane & 7;
-    const int rg = lane >> 3;
     const int nb = C.num_buckets;
     const int passes = (H + 31) >> 5;
     const int chunks = (H + kRowsPerChunk - 1) / kRowsPerChunk;
@@ -302,18 +303,21 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
 
         // ---------------- phase 2: gated residual + LayerNorm statistics + 3 dots per row --------
         for (int chunk = 0; chunk < chunks; ++chunk) {
-            const int h = chunk * kRowsPerChunk + warp * 4 + rg;
-            const bool row_ok = h < H;
-            float v[kEPL], gw[kEPL];
-            {
-                const int hn = row_ok ? S.hnews[h] : 0;
-                const int ht = row_ok ? S.htab[h] : 0;
-                const float *hr = C.hist_rows + (size_t)hn * LIME_HIST_LD + l8;
-                const float *tr = C.hist_tab + (size_t)ht * LIME_HTAB_LD + l8;
+            // this warp's 4 history rows; lane holds dims d = lane + 32*j (j < 13; j = 12 only for lane < 16)
+            const int h0 = chunk * kRowsPerChunk + warp * kRowsPerWarp;
+            float v[kRowsPerWarp][kSlots], gw[kRowsPerWarp][kSlots];
 #pragma unroll
-                for (int j = 0; j < kEPL; ++j) {
-                    v[j] = row_ok ? (hr[LIME_HIST_VC + 8 * j] + tr[8 * j]) : 0.0f;
-                    gw[j] = row_ok ? (hr[LIME_HIST_GW + 8 * j] + tr[kD + 8 * j]) : 0.0f;
+            for (int r = 0; r < kRowsPerWarp; ++r) {
+                const bool row_ok = (h0 + r) < H;
+                const int hn = row_ok ? S.hnews[h0 + r] : 0;
+                const int ht = row_ok ? S.htab[h0 + r] : 0;
+                const float *hr = C.hist_rows + (size_t)hn * LIME_HIST_LD + lane;
+                const float *tr = C.hist_tab + (size_t)ht * LIME_HTAB_LD + lane;
+#pragma unroll
+                for (int j = 0; j < kSlots; ++j) {
+                    const bool ok = row_ok && (lane + 32 * j < kD);
+                    v[r][j] = ok ? (hr[LIME_HIST_VC + 32 * j] + tr[32 * j]) : 0.0f;
+                    gw[r][j] = ok ? (hr[LIME_HIST_GW + 32 * j] + tr[kD + 32 * j]) : 0.0f;
                 }
             }
             // stage candidate 0
@@ -337,37 +341,65 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
                         nv[q] = (idx < kNW) ? (cr[idx] + ct[idx]) : 0.0f;
                     }
                 }
-                const float a = row_ok ? S.a_s[c * H + h] : 0.0f;
-                const float4 *wb = S.wbuf + buf * kD + l8;
-                float s0 = 0.f, s1 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+                float a[kRowsPerWarp], oma[kRowsPerWarp];
+                float acc[kRowsPerWarp][5];
 #pragma unroll
-                for (int j = 0; j < kEPL; ++j) {
-                    const float4 q = wb[8 * j];
-                    const float zz = fminf(fmaf(a, gw[j], q.x), 80.0f);
-                    const float e = ex2_approx(zz);
-                    const float o = v[j] * ((e + a) * rcp_approx(e + 1.0f));
-                    s0 += o;
-                    s1 = fmaf(o, o, s1);
-                    d1 = fmaf(o, q.y, d1);
-                    d2 = fmaf(o, q.z, d2);
-                    d3 = fmaf(o, q.w, d3);
+                for (int r = 0; r < kRowsPerWarp; ++r) {
+                    a[r] = (h0 + r < H) ? S.a_s[c * H + h0 + r] : 0.0f;
+                    oma[r] = 1.0f - a[r];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) acc[r][q] = 0.0f;
+                }
+                const float4 *wb = S.wbuf + buf * kD + lane;
+#pragma unroll
+                for (int j = 0; j < kSlots; ++j) {
+                    // (gate bias', w1, w2, w3)[d]: one LDS.128 feeds the 4 rows of the warp.  The last
+                    // slot (d = 384 + lane) only exists for lane < 16; v = gw = 0 there so o = 0, and the
+                    // address is clamped to stay inside the buffer.
+                    const float4 q = wb[(j < kSlots - 1 || lane < 16) ? 32 * j : 0];
+#pragma unroll
+                    for (int r = 0; r < kRowsPerWarp; ++r) {
+                        // o = v (1 - (1 - a) sigmoid(a W_g v + b_g)),  sigmoid = 1 / (1 + 2^(z'))
+                        const float e = ex2_approx(fmaf(a[r], gw[r][j], q.x));   // +inf -> gate 0, no NaN
+                        const float g = rcp_approx(e + 1.0f);
+                        const float o = fmaf(-(v[r][j] * oma[r]), g, v[r][j]);
+                        acc[r][0] += o;
+                        acc[r][1] = fmaf(o, o, acc[r][1]);
+                        acc[r][2] = fmaf(o, q.y, acc[r][2]);
+                        acc[r][3] = fmaf(o, q.z, acc[r][3]);
+                        acc[r][4] = fmaf(o, q.w, acc[r][4]);
+                    }
+                }
+                // split butterfly: 20 partial sums -> lane group (lane>>3) ends up owning row (lane>>3)
+                float k2[2][5], k1[5];
+                const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        const float send = hi16 ? acc[rr][q] : acc[rr + 2][q];
+                        const float keep = hi16 ? acc[rr + 2][q] : acc[rr][q];
+                        k2[rr][q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const float send = hi8 ? k2[0][q] : k2[1][q];
+                    const float keep = hi8 ? k2[1][q] : k2[0][q];
+                    k1[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
                 }
 #pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
-                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-                    d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-                    d3 += __shfl_xor_sync(0xffffffffu, d3, o);
-                }
-                if (l8 == 0 && row_ok) {
+                for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) k1[q] += __shfl_xor_sync(0xffffffffu, k1[q], o);
+                const int h = h0 + (lane >> 3);
+                if ((lane & 7) == 0 && h < H) {
                     const float *cs = S.cscal + c * 8;
-                    const float mu = s0 * (1.0f / kD);
-                    const float var = fmaxf(fmaf(-mu, mu, s1 * (1.0f / kD)), 0.0f);
+                    const float mu = k1[0] * (1.0f / kD);
+                    const float var = fmaxf(fmaf(-mu, mu, k1[1] * (1.0f / kD)), 0.0f);
                     const float rstd = rsqrtf(var + args.ln_eps);
-                    S.lg_s[c * H + h] = fmaf(rstd, fmaf(-mu, cs[0], d1), cs[3]);
-                    S.y_s[c * H + h] = fmaf(rstd, fmaf(-mu, cs[1], d2), cs[4]);
-                    S.z_s[c * H + h] = fmaf(rstd, fmaf(-mu, cs[2], d3), cs[5]);
+                    S.lg_s[c * H + h] = fmaf(rstd, fmaf(-mu, cs[0], k1[2]), cs[3]);
+                    S.y_s[c * H + h] = fmaf(rstd, fmaf(-mu, cs[1], k1[3]), cs[4]);
+                    S.z_s[c * H + h] = fmaf(rstd, fmaf(-mu, cs[2], k1[4]), cs[5]);
                 }
                 if (has_next) {
 #pragma unroll
