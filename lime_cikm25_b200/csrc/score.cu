@@ -68,6 +68,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 
 struct SmemLayout {
     float4 *wbuf;      // [2][kD]   (gate bias', w1, w2, w3) per dim, double buffered
+    float *v_s;        // [kRowsPerChunk][kD] LIME vectors of the chunk's history rows (warp-private rows)
     float *t_s;        // [H][kTStride]  topic representation of the history slots
     float *a_s;        // [tile_c][H]    candidate-aware attention weights
     float *lg_s;       // [tile_c][H]    x_h . p / 20
@@ -95,6 +96,7 @@ __host__ __device__ inline size_t smem_carve(SmemLayout *L, unsigned char *base,
         return o;
     };
     size_t o_wbuf = take(sizeof(float4) * 2 * kD);
+    size_t o_v = take(sizeof(float) * kRowsPerChunk * kD);
     size_t o_t = take(sizeof(float) * H * kTStride);
     size_t o_a = take(sizeof(float) * TC * H);
     size_t o_lg = take(sizeof(float) * TC * H);
@@ -112,6 +114,7 @@ __host__ __device__ inline size_t smem_carve(SmemLayout *L, unsigned char *base,
     size_t o_ub = take(sizeof(int) * 4);
     if (L) {
         L->wbuf = reinterpret_cast<float4 *>(base + o_wbuf);
+        L->v_s = reinterpret_cast<float *>(base + o_v);
         L->t_s = reinterpret_cast<float *>(base + o_t);
         L->a_s = reinterpret_cast<float *>(base + o_a);
         L->lg_s = reinterpret_cast<float *>(base + o_lg);
@@ -144,7 +147,7 @@ __device__ __forceinline__ float lifetime_weight(float r, const LimeNewsCache &c
 }
 
 template <int MAXP>
-__global__ void __maxnreg__(152) score_kernel(const ScoreArgs args) {
+__global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const LimeNewsCache &C = args.cache;
     const LimeImpressions &I = args.imp;
@@ -305,7 +308,10 @@ __global__ void __maxnreg__(152) score_kernel(const ScoreArgs args) {
         for (int chunk = 0; chunk < chunks; ++chunk) {
             // this warp's 4 history rows; lane holds dims d = lane + 32*j (j < 13; j = 12 only for lane < 16)
             const int h0 = chunk * kRowsPerChunk + warp * kRowsPerWarp;
-            float v[kRowsPerWarp][kSlots], gw[kRowsPerWarp][kSlots];
+            // W_g v lives in registers, v itself in this warp's private rows of the shared v tile: a
+            // 13-warp CTA puts 4 warps on one SM sub-partition, which caps a thread at 128 registers
+            float gw[kRowsPerWarp][kSlots];
+            float *vrow = S.v_s + (size_t)warp * kRowsPerWarp * kD + lane;
 #pragma unroll
             for (int r = 0; r < kRowsPerWarp; ++r) {
                 const bool row_ok = (h0 + r) < H;
@@ -315,11 +321,13 @@ __global__ void __maxnreg__(152) score_kernel(const ScoreArgs args) {
                 const float *tr = C.hist_tab + (size_t)ht * LIME_HTAB_LD + lane;
 #pragma unroll
                 for (int j = 0; j < kSlots; ++j) {
-                    const bool ok = row_ok && (lane + 32 * j < kD);
-                    v[r][j] = ok ? (hr[LIME_HIST_VC + 32 * j] + tr[32 * j]) : 0.0f;
+                    const bool in = lane + 32 * j < kD;
+                    const bool ok = row_ok && in;
+                    if (in) vrow[r * kD + 32 * j] = ok ? (hr[LIME_HIST_VC + 32 * j] + tr[32 * j]) : 0.0f;
                     gw[r][j] = ok ? (hr[LIME_HIST_GW + 32 * j] + tr[kD + 32 * j]) : 0.0f;
                 }
             }
+            __syncwarp();
             // stage candidate 0
             for (int idx = tid; idx < kNW; idx += kThreads) {
                 const int which = idx / kD, d = idx - which * kD;
@@ -356,13 +364,15 @@ __global__ void __maxnreg__(152) score_kernel(const ScoreArgs args) {
                     // (gate bias', w1, w2, w3)[d]: one LDS.128 feeds the 4 rows of the warp.  The last
                     // slot (d = 384 + lane) only exists for lane < 16; v = gw = 0 there so o = 0, and the
                     // address is clamped to stay inside the buffer.
-                    const float4 q = wb[(j < kSlots - 1 || lane < 16) ? 32 * j : 0];
+                    const bool in = (j < kSlots - 1) || (lane < 16);
+                    const float4 q = wb[in ? 32 * j : 0];
 #pragma unroll
                     for (int r = 0; r < kRowsPerWarp; ++r) {
                         // o = v (1 - (1 - a) sigmoid(a W_g v + b_g)),  sigmoid = 1 / (1 + 2^(z'))
+                        const float vv = in ? vrow[r * kD + 32 * j] : 0.0f;
                         const float e = ex2_approx(fmaf(a[r], gw[r][j], q.x));   // +inf -> gate 0, no NaN
                         const float g = rcp_approx(e + 1.0f);
-                        const float o = fmaf(-(v[r][j] * oma[r]), g, v[r][j]);
+                        const float o = fmaf(-(vv * oma[r]), g, vv);
                         acc[r][0] += o;
                         acc[r][1] = fmaf(o, o, acc[r][1]);
                         acc[r][2] = fmaf(o, q.y, acc[r][2]);
