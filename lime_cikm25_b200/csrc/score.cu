@@ -19,8 +19,8 @@
 // (the LayerNorm is folded into the dots).  Everything linear in c is cached per news / per
 // lifetime-bucket pair at cache-build time (cand_rows / cand_tab).
 //
-// Thread mapping (phase 2, the hot loop): 13 warps; a warp owns 4 history rows; a lane holds dims
-// d = lane + 32*j (j < 13) of v_h and W_g v_h of those 4 rows in REGISTERS for the whole unit, so the
+// Thread mapping (phase 2, the hot loop): 16 warps; a warp owns 3-4 history rows; a lane holds dims
+// d = lane + 32*j (j < 13) of W_g v_h in REGISTERS (v_h in warp-private shared rows), so the
 // per-candidate loop touches only shared memory: one conflict-free LDS.128 fetches
 // (gate bias, w1, w2, w3)[d] and is reused by the 4 rows (0.25 LDS per element).  The 4x5 partial
 // sums of a warp are reduced with a split butterfly (30 shuffles instead of 100).
@@ -32,10 +32,10 @@ namespace lime {
 
 constexpr int kD = LIME_D;
 constexpr int kEPL = kD / 8;        // elements per lane (50)
-constexpr int kWarps = 13;
+constexpr int kWarps = 16;                  // 4 per SM sub-partition: balanced issue, 128 registers/thread
 constexpr int kThreads = kWarps * 32;
 constexpr int kRowsPerWarp = 4;
-constexpr int kRowsPerChunk = kWarps * kRowsPerWarp;   // 52 history rows resident in registers at a time
+constexpr int kRowsPerChunk = kWarps * kRowsPerWarp;   // up to 64 history rows resident per pass
 constexpr int kSlots = (kD + 31) / 32;      // 13 register slots per lane and row (d = lane + 32 j)
 constexpr int kTStride = LIME_TOPIC + 1;    // 51: conflict-free column reads of the topic tile
 constexpr int kTqStride = 12;               // heads padded 10 -> 12 (3 x LDS.128)
@@ -307,14 +307,19 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
         // ---------------- phase 2: gated residual + LayerNorm statistics + 3 dots per row --------
         for (int chunk = 0; chunk < chunks; ++chunk) {
             // this warp's 4 history rows; lane holds dims d = lane + 32*j (j < 13; j = 12 only for lane < 16)
-            const int h0 = chunk * kRowsPerChunk + warp * kRowsPerWarp;
+            // balanced split of the chunk's rows over the 16 warps (H = 50: two warps take 4 rows, the
+            // others 3), so every SM sub-partition issues the same amount of work between barriers
+            const int R = min(kRowsPerChunk, H - chunk * kRowsPerChunk);
+            const int rbase = R / kWarps, rrem = R % kWarps;
+            const int nrows = rbase + (warp < rrem ? 1 : 0);
+            const int h0 = chunk * kRowsPerChunk + warp * rbase + min(warp, rrem);
             // W_g v lives in registers, v itself in this warp's private rows of the shared v tile: a
             // 13-warp CTA puts 4 warps on one SM sub-partition, which caps a thread at 128 registers
             float gw[kRowsPerWarp][kSlots];
             float *vrow = S.v_s + (size_t)warp * kRowsPerWarp * kD + lane;
 #pragma unroll
             for (int r = 0; r < kRowsPerWarp; ++r) {
-                const bool row_ok = (h0 + r) < H;
+                const bool row_ok = r < nrows;
                 const int hn = row_ok ? S.hnews[h0 + r] : 0;
                 const int ht = row_ok ? S.htab[h0 + r] : 0;
                 const float *hr = C.hist_rows + (size_t)hn * LIME_HIST_LD + lane;
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
                 float acc[kRowsPerWarp][5];
 #pragma unroll
                 for (int r = 0; r < kRowsPerWarp; ++r) {
-                    a[r] = (h0 + r < H) ? S.a_s[c * H + h0 + r] : 0.0f;
+                    a[r] = (r < nrows) ? S.a_s[c * H + h0 + r] : 0.0f;
                     oma[r] = 1.0f - a[r];
 #pragma unroll
                     for (int q = 0; q < 5; ++q) acc[r][q] = 0.0f;
@@ -368,6 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
                     const float4 q = wb[in ? 32 * j : 0];
 #pragma unroll
                     for (int r = 0; r < kRowsPerWarp; ++r) {
+                        if (r >= nrows) continue;   // warp-uniform
                         // o = v (1 - (1 - a) sigmoid(a W_g v + b_g)),  sigmoid = 1 / (1 + 2^(z'))
                         const float vv = in ? vrow[r * kD + 32 * j] : 0.0f;
                         const float e = ex2_approx(fmaf(a[r], gw[r][j], q.x));   // +inf -> gate 0, no NaN
@@ -402,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
 #pragma unroll
                     for (int q = 0; q < 5; ++q) k1[q] += __shfl_xor_sync(0xffffffffu, k1[q], o);
                 const int h = h0 + (lane >> 3);
-                if ((lane & 7) == 0 && h < H) {
+                if ((lane & 7) == 0 && (lane >> 3) < nrows) {
                     const float *cs = S.cscal + c * 8;
                     const float mu = k1[0] * (1.0f / kD);
                     const float var = fmaxf(fmaf(-mu, mu, k1[1] * (1.0f / kD)), 0.0f);

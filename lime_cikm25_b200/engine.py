@@ -324,9 +324,9 @@ class ScoringEngine:
 
 
 def choose_tile_c(max_history):
-    """Largest multiple of 13 (warps per CTA) up to 52 whose shared-memory footprint fits."""
+    """Largest multiple of 16 (warps per CTA) up to 48 whose shared-memory footprint fits."""
     lib = _lib.load()
-    for tc in (52, 39, 26, 13):
+    for tc in (48, 32, 16, 8):
         if lib.lime_score_smem_bytes(int(max_history), tc) <= 232448:
             return tc
     raise _lib.LimeError("max_history=%d does not fit the scoring kernel's shared memory" % max_history)

@@ -37,9 +37,9 @@ def test_struct_sizes_match_header(lib):
 
 def test_smem_budget_query(lib):
     from lime_cikm25_b200.engine import choose_tile_c
-    assert lib.lime_score_smem_bytes(50, 52) < 232448
-    assert choose_tile_c(50) == 52
-    assert choose_tile_c(200) in (13, 26, 39, 52)
+    assert lib.lime_score_smem_bytes(50, 48) < 232448
+    assert choose_tile_c(50) == 48
+    assert choose_tile_c(200) in (8, 16, 32, 48)
     assert lib.lime_score_smem_bytes(200, choose_tile_c(200)) <= 232448
 
 

@@ -182,8 +182,8 @@ def test_properties_at_scale(lib):
         cache = util.build_news_cache(model, news)
         cache2 = util.build_news_cache(model, news, chunk=700)
         assert torch.equal(cache.hist_rows, cache2.hist_rows) and torch.equal(cache.cand_rows, cache2.cand_rows)
-        d52 = engine.DeviceImpressions(imp, DEV)
-        d13 = engine.DeviceImpressions(imp, DEV, tile_c=13)
+        d52 = engine.DeviceImpressions(imp, DEV)    # default tile
+        d13 = engine.DeviceImpressions(imp, DEV, tile_c=16)
         m1, det1 = util.evaluate_impressions(model, cache, d52, 32, return_details=True)
         m2, det2 = util.evaluate_impressions(model, cache, d52, 32, return_details=True)
         s13 = util.score_impressions(model, cache, d13, 32)
