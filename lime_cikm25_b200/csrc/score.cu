@@ -26,6 +26,8 @@
 // sums of a warp are reduced with a split butterfly (30 shuffles instead of 100).
 // A work unit is <= tile_c consecutive candidates of one impression; CTAs are persistent (one per
 // SM) and pull units from a global counter.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace lime {
@@ -343,7 +345,9 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
             __syncthreads();
             for (int c = 0; c < cnt; ++c) {
                 const int buf = c & 1;
-                float nv[3];
+                // prefetch the next candidate's folded vectors (news part, bucket-table part); the add
+                // and the shared-memory store happen after this candidate's math so the loads overlap it
+                float nvr[3], nvt[3];
                 const bool has_next = (c + 1 < cnt);
                 if (has_next) {
                     const float *cr = C.cand_rows + (size_t)S.cnews[c + 1] * LIME_CAND_LD;
@@ -351,62 +355,75 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
                         const int idx = tid + q * kThreads;
-                        nv[q] = (idx < kNW) ? (cr[idx] + ct[idx]) : 0.0f;
+                        nvr[q] = (idx < kNW) ? cr[idx] : 0.0f;
+                        nvt[q] = (idx < kNW) ? ct[idx] : 0.0f;
                     }
-                }
-                float a[kRowsPerWarp], oma[kRowsPerWarp];
-                float acc[kRowsPerWarp][5];
-#pragma unroll
-                for (int r = 0; r < kRowsPerWarp; ++r) {
-                    a[r] = (r < nrows) ? S.a_s[c * H + h0 + r] : 0.0f;
-                    oma[r] = 1.0f - a[r];
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) acc[r][q] = 0.0f;
                 }
                 const float4 *wb = S.wbuf + buf * kD + lane;
+                const float *ac = S.a_s + c * H + h0;
+                float k1[5];
+                // compile-time row count: one warp-uniform branch per candidate instead of one per element
+                auto rows = [&](auto nr_tag) {
+                    constexpr int NR = decltype(nr_tag)::value;
+                    float a[NR], oma[NR], acc[kRowsPerWarp][5];
 #pragma unroll
-                for (int j = 0; j < kSlots; ++j) {
-                    // (gate bias', w1, w2, w3)[d]: one LDS.128 feeds the 4 rows of the warp.  The last
-                    // slot (d = 384 + lane) only exists for lane < 16; v = gw = 0 there so o = 0, and the
-                    // address is clamped to stay inside the buffer.
-                    const bool in = (j < kSlots - 1) || (lane < 16);
-                    const float4 q = wb[in ? 32 * j : 0];
+                    for (int r = 0; r < kRowsPerWarp; ++r)
 #pragma unroll
-                    for (int r = 0; r < kRowsPerWarp; ++r) {
-                        if (r >= nrows) continue;   // warp-uniform
-                        // o = v (1 - (1 - a) sigmoid(a W_g v + b_g)),  sigmoid = 1 / (1 + 2^(z'))
-                        const float vv = in ? vrow[r * kD + 32 * j] : 0.0f;
-                        const float e = ex2_approx(fmaf(a[r], gw[r][j], q.x));   // +inf -> gate 0, no NaN
-                        const float g = rcp_approx(e + 1.0f);
-                        const float o = fmaf(-(vv * oma[r]), g, vv);
-                        acc[r][0] += o;
-                        acc[r][1] = fmaf(o, o, acc[r][1]);
-                        acc[r][2] = fmaf(o, q.y, acc[r][2]);
-                        acc[r][3] = fmaf(o, q.z, acc[r][3]);
-                        acc[r][4] = fmaf(o, q.w, acc[r][4]);
+                        for (int q = 0; q < 5; ++q) acc[r][q] = 0.0f;
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) {
+                        a[r] = ac[r];
+                        oma[r] = 1.0f - a[r];
                     }
-                }
-                // split butterfly: 20 partial sums -> lane group (lane>>3) ends up owning row (lane>>3)
-                float k2[2][5], k1[5];
-                const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr)
+                    for (int j = 0; j < kSlots; ++j) {
+                        // (gate bias', w1, w2, w3)[d]: one LDS.128 feeds all rows of the warp.  The last slot
+                        // (d = 384 + lane) only exists for lane < 16: v = gw = 0 there (o = 0), address clamped.
+                        const bool in = (j < kSlots - 1) || (lane < 16);
+                        const float4 q = wb[in ? 32 * j : 0];
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) {
+                            // o = v (1 - (1 - a) sigmoid(a W_g v + b_g)),  sigmoid = 1 / (1 + 2^(z'))
+                            const float vv = in ? vrow[r * kD + 32 * j] : 0.0f;
+                            const float e = ex2_approx(fmaf(a[r], gw[r][j], q.x));   // +inf -> gate 0, no NaN
+                            const float g = rcp_approx(e + 1.0f);
+                            const float o = fmaf(-(vv * oma[r]), g, vv);
+                            acc[r][0] += o;
+                            acc[r][1] = fmaf(o, o, acc[r][1]);
+                            acc[r][2] = fmaf(o, q.y, acc[r][2]);
+                            acc[r][3] = fmaf(o, q.z, acc[r][3]);
+                            acc[r][4] = fmaf(o, q.w, acc[r][4]);
+                        }
+                    }
+                    // split butterfly: 4x5 partial sums -> lane group (lane>>3) ends up owning row (lane>>3)
+                    float k2[2][5];
+                    const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            const float send = hi16 ? acc[rr][q] : acc[rr + 2][q];
+                            const float keep = hi16 ? acc[rr + 2][q] : acc[rr][q];
+                            k2[rr][q] = (NR > 2 ? __shfl_xor_sync(0xffffffffu, send, 16) : 0.0f) + keep;
+                        }
 #pragma unroll
                     for (int q = 0; q < 5; ++q) {
-                        const float send = hi16 ? acc[rr][q] : acc[rr + 2][q];
-                        const float keep = hi16 ? acc[rr + 2][q] : acc[rr][q];
-                        k2[rr][q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        const float send = hi8 ? k2[0][q] : k2[1][q];
+                        const float keep = hi8 ? k2[1][q] : k2[0][q];
+                        k1[q] = (NR > 1 ? __shfl_xor_sync(0xffffffffu, send, 8) : 0.0f) + keep;
                     }
 #pragma unroll
-                for (int q = 0; q < 5; ++q) {
-                    const float send = hi8 ? k2[0][q] : k2[1][q];
-                    const float keep = hi8 ? k2[1][q] : k2[0][q];
-                    k1[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) k1[q] += __shfl_xor_sync(0xffffffffu, k1[q], o);
+                };
+                switch (nrows) {
+                    case 4: rows(std::integral_constant<int, 4>{}); break;
+                    case 3: rows(std::integral_constant<int, 3>{}); break;
+                    case 2: rows(std::integral_constant<int, 2>{}); break;
+                    case 1: rows(std::integral_constant<int, 1>{}); break;
+                    default: break;
                 }
-#pragma unroll
-                for (int o = 4; o > 0; o >>= 1)
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) k1[q] += __shfl_xor_sync(0xffffffffu, k1[q], o);
                 const int h = h0 + (lane >> 3);
                 if ((lane & 7) == 0 && (lane >> 3) < nrows) {
                     const float *cs = S.cscal + c * 8;
@@ -423,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
                         const int idx = tid + q * kThreads;
                         if (idx < kNW) {
                             const int which = idx / kD, d = idx - which * kD;
-                            reinterpret_cast<float *>(S.wbuf + (buf ^ 1) * kD + d)[1 + which] = nv[q];
+                            reinterpret_cast<float *>(S.wbuf + (buf ^ 1) * kD + d)[1 + which] = nvr[q] + nvt[q];
                         }
                     }
                 }
