@@ -68,6 +68,21 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
+// Phase-2 dim mapping: lane owns dims 128*jp + 4*lane + e (jp < 3, e < 4; register slot 4*jp + e) and,
+// for lane < 16, dim 384 + lane (slot 12).  v rows keep the natural order (one LDS.128 per jp); the
+// candidate float4s are stored at wpos(d) so that slot s of all lanes is one contiguous 512-byte row.
+__device__ __forceinline__ int wpos(int d) {
+    return d < 384 ? ((((d >> 7) << 2) + (d & 3)) << 5) + ((d & 127) >> 2) : d;
+}
+
+__device__ __forceinline__ void accum5(float (&acc)[5], float o, const float4 &q) {
+    acc[0] += o;
+    acc[1] = fmaf(o, o, acc[1]);
+    acc[2] = fmaf(o, q.y, acc[2]);
+    acc[3] = fmaf(o, q.z, acc[3]);
+    acc[4] = fmaf(o, q.w, acc[4]);
+}
+
 struct SmemLayout {
     float4 *wbuf;      // [2][kD]   (gate bias', w1, w2, w3) per dim, double buffered
     float *v_s;        // [kRowsPerChunk][kD] LIME vectors of the chunk's history rows (warp-private rows)
@@ -166,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
     const int chunks = (H + kRowsPerChunk - 1) / kRowsPerChunk;
 
     // gate bias' = -log2(e) * b_g lives in .x of both staging buffers for the kernel's lifetime
-    for (int d = tid; d < 2 * kD; d += kThreads) S.wbuf[d].x = C.gate_bias[d % kD];
+    for (int d = tid; d < 2 * kD; d += kThreads) S.wbuf[(d / kD) * kD + wpos(d % kD)].x = C.gate_bias[d % kD];
 
     for (;;) {
         __syncthreads();   // previous unit fully consumed (also orders the .x init above)
@@ -308,31 +323,42 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
 
         // ---------------- phase 2: gated residual + LayerNorm statistics + 3 dots per row --------
         for (int chunk = 0; chunk < chunks; ++chunk) {
-            // this warp's 4 history rows; lane holds dims d = lane + 32*j (j < 13; j = 12 only for lane < 16)
             // balanced split of the chunk's rows over the 16 warps (H = 50: two warps take 4 rows, the
-            // others 3), so every SM sub-partition issues the same amount of work between barriers
+            // others 3); the extra rows go to the highest warp ids, which the issue arbiter favours
             const int R = min(kRowsPerChunk, H - chunk * kRowsPerChunk);
             const int rbase = R / kWarps, rrem = R % kWarps;
-            const int nrows = rbase + (warp < rrem ? 1 : 0);
-            const int h0 = chunk * kRowsPerChunk + warp * rbase + min(warp, rrem);
-            // W_g v lives in registers, v itself in this warp's private rows of the shared v tile: a
-            // 13-warp CTA puts 4 warps on one SM sub-partition, which caps a thread at 128 registers
+            const int wfirst = kWarps - rrem;                 // warps >= wfirst own rbase + 1 rows
+            const int nrows = rbase + (warp >= wfirst ? 1 : 0);
+            const int h0 = chunk * kRowsPerChunk + warp * rbase + max(warp - wfirst, 0);
+            // W_g v lives in registers, v itself in this warp's private rows of the shared v tile (16
+            // warps = 4 per SM sub-partition caps a thread at 128 registers)
             float gw[kRowsPerWarp][kSlots];
-            float *vrow = S.v_s + (size_t)warp * kRowsPerWarp * kD + lane;
+            float *vrow = S.v_s + (size_t)warp * kRowsPerWarp * kD;
 #pragma unroll
             for (int r = 0; r < kRowsPerWarp; ++r) {
                 const bool row_ok = r < nrows;
                 const int hn = row_ok ? S.hnews[h0 + r] : 0;
                 const int ht = row_ok ? S.htab[h0 + r] : 0;
-                const float *hr = C.hist_rows + (size_t)hn * LIME_HIST_LD + lane;
-                const float *tr = C.hist_tab + (size_t)ht * LIME_HTAB_LD + lane;
+                const float *hr = C.hist_rows + (size_t)hn * LIME_HIST_LD;
+                const float *tr = C.hist_tab + (size_t)ht * LIME_HTAB_LD;
 #pragma unroll
-                for (int j = 0; j < kSlots; ++j) {
-                    const bool in = lane + 32 * j < kD;
-                    const bool ok = row_ok && in;
-                    if (in) vrow[r * kD + 32 * j] = ok ? (hr[LIME_HIST_VC + 32 * j] + tr[32 * j]) : 0.0f;
-                    gw[r][j] = ok ? (hr[LIME_HIST_GW + 32 * j] + tr[kD + 32 * j]) : 0.0f;
+                for (int jp = 0; jp < 3; ++jp) {
+                    const int d = 128 * jp + 4 * lane;
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 v1 = row_ok ? *reinterpret_cast<const float4 *>(hr + LIME_HIST_VC + d) : z4;
+                    const float4 v2 = row_ok ? *reinterpret_cast<const float4 *>(tr + d) : z4;
+                    const float4 g1 = row_ok ? *reinterpret_cast<const float4 *>(hr + LIME_HIST_GW + d) : z4;
+                    const float4 g2 = row_ok ? *reinterpret_cast<const float4 *>(tr + kD + d) : z4;
+                    *reinterpret_cast<float4 *>(vrow + r * kD + d) =
+                        make_float4(v1.x + v2.x, v1.y + v2.y, v1.z + v2.z, v1.w + v2.w);
+                    gw[r][4 * jp + 0] = g1.x + g2.x;
+                    gw[r][4 * jp + 1] = g1.y + g2.y;
+                    gw[r][4 * jp + 2] = g1.z + g2.z;
+                    gw[r][4 * jp + 3] = g1.w + g2.w;
                 }
+                const bool tail = row_ok && lane < 16;
+                if (lane < 16) vrow[r * kD + 384 + lane] = tail ? (hr[LIME_HIST_VC + 384 + lane] + tr[384 + lane]) : 0.0f;
+                gw[r][12] = tail ? (hr[LIME_HIST_GW + 384 + lane] + tr[kD + 384 + lane]) : 0.0f;
             }
             __syncwarp();
             // stage candidate 0
@@ -340,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
                 const int which = idx / kD, d = idx - which * kD;
                 const float val = C.cand_rows[(size_t)S.cnews[0] * LIME_CAND_LD + idx] +
                                   C.cand_tab[(size_t)S.ctab[0] * LIME_CTAB_LD + idx];
-                reinterpret_cast<float *>(S.wbuf + d)[1 + which] = val;
+                reinterpret_cast<float *>(S.wbuf + wpos(d))[1 + which] = val;
             }
             __syncthreads();
             for (int c = 0; c < cnt; ++c) {
@@ -375,24 +401,39 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
                         a[r] = ac[r];
                         oma[r] = 1.0f - a[r];
                     }
+                    // o = v (1 - (1 - a) sigmoid(a W_g v + b_g)), sigmoid(z) = 1 / (1 + 2^z'), z' = -log2(e) z.
+                    // Two elements share one MUFU.RCP: 1/x = y / (x y).  z' is clamped to 60 so the product of
+                    // two denominators stays finite (gate <= 2^-60 there, i.e. 0 in fp32 arithmetic).
 #pragma unroll
-                    for (int j = 0; j < kSlots; ++j) {
-                        // (gate bias', w1, w2, w3)[d]: one LDS.128 feeds all rows of the warp.  The last slot
-                        // (d = 384 + lane) only exists for lane < 16: v = gw = 0 there (o = 0), address clamped.
-                        const bool in = (j < kSlots - 1) || (lane < 16);
-                        const float4 q = wb[in ? 32 * j : 0];
+                    for (int jp = 0; jp < 3; ++jp) {
+                        float4 v4[NR];
+#pragma unroll
+                        for (int r = 0; r < NR; ++r)
+                            v4[r] = *reinterpret_cast<const float4 *>(vrow + r * kD + 128 * jp + 4 * lane);
+#pragma unroll
+                        for (int eh = 0; eh < 2; ++eh) {
+                            const float4 qa = wb[(4 * jp + 2 * eh) * 32];
+                            const float4 qb = wb[(4 * jp + 2 * eh + 1) * 32];
+#pragma unroll
+                            for (int r = 0; r < NR; ++r) {
+                                const float va = eh ? v4[r].z : v4[r].x;
+                                const float vb = eh ? v4[r].w : v4[r].y;
+                                const float da = ex2_approx(fminf(fmaf(a[r], gw[r][4 * jp + 2 * eh], qa.x), 60.0f)) + 1.0f;
+                                const float db = ex2_approx(fminf(fmaf(a[r], gw[r][4 * jp + 2 * eh + 1], qb.x), 60.0f)) + 1.0f;
+                                const float ri = rcp_approx(da * db);
+                                accum5(acc[r], fmaf(-(va * oma[r]), ri * db, va), qa);
+                                accum5(acc[r], fmaf(-(vb * oma[r]), ri * da, vb), qb);
+                            }
+                        }
+                    }
+                    {   // tail slot: dims 384 + lane, lanes 0..15 (v = gw = 0 elsewhere, address clamped)
+                        const bool in = lane < 16;
+                        const float4 q = wb[in ? 384 : 0];
 #pragma unroll
                         for (int r = 0; r < NR; ++r) {
-                            // o = v (1 - (1 - a) sigmoid(a W_g v + b_g)),  sigmoid = 1 / (1 + 2^(z'))
-                            const float vv = in ? vrow[r * kD + 32 * j] : 0.0f;
-                            const float e = ex2_approx(fmaf(a[r], gw[r][j], q.x));   // +inf -> gate 0, no NaN
-                            const float g = rcp_approx(e + 1.0f);
-                            const float o = fmaf(-(vv * oma[r]), g, vv);
-                            acc[r][0] += o;
-                            acc[r][1] = fmaf(o, o, acc[r][1]);
-                            acc[r][2] = fmaf(o, q.y, acc[r][2]);
-                            acc[r][3] = fmaf(o, q.z, acc[r][3]);
-                            acc[r][4] = fmaf(o, q.w, acc[r][4]);
+                            const float vv = in ? vrow[r * kD + 384 + lane] : 0.0f;
+                            const float e = ex2_approx(fminf(fmaf(a[r], gw[r][12], q.x), 60.0f));
+                            accum5(acc[r], fmaf(-(vv * oma[r]), rcp_approx(e + 1.0f), vv), q);
                         }
                     }
                     // split butterfly: 4x5 partial sums -> lane group (lane>>3) ends up owning row (lane>>3)
@@ -404,13 +445,13 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
                         for (int q = 0; q < 5; ++q) {
                             const float send = hi16 ? acc[rr][q] : acc[rr + 2][q];
                             const float keep = hi16 ? acc[rr + 2][q] : acc[rr][q];
-                            k2[rr][q] = (NR > 2 ? __shfl_xor_sync(0xffffffffu, send, 16) : 0.0f) + keep;
+                            k2[rr][q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
                         }
 #pragma unroll
                     for (int q = 0; q < 5; ++q) {
                         const float send = hi8 ? k2[0][q] : k2[1][q];
                         const float keep = hi8 ? k2[1][q] : k2[0][q];
-                        k1[q] = (NR > 1 ? __shfl_xor_sync(0xffffffffu, send, 8) : 0.0f) + keep;
+                        k1[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
                     }
 #pragma unroll
                     for (int o = 4; o > 0; o >>= 1)
@@ -440,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
                         const int idx = tid + q * kThreads;
                         if (idx < kNW) {
                             const int which = idx / kD, d = idx - which * kD;
-                            reinterpret_cast<float *>(S.wbuf + (buf ^ 1) * kD + d)[1 + which] = nvr[q] + nvt[q];
+                            reinterpret_cast<float *>(S.wbuf + (buf ^ 1) * kD + wpos(d))[1 + which] = nvr[q] + nvt[q];
                         }
                     }
                 }
