@@ -1,0 +1,69 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU eval plumbing: impressions sharded by rank with the
+global pair index preserved, per-rank metric partial sums (here produced by the CPU oracle — the
+GPU box produces them with lime_rank_metrics / lime_metrics_reduce), one SUM all-reduce, global means
+equal to the single-process result."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from lime_cikm25_b200 import parallel, synth
+from oracle import lime_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _per_impression(imp, scores):
+    rows = []
+    for i in range(imp.num_impressions):
+        s, y = scores[imp.cand_off[i]:imp.cand_off[i + 1]], imp.labels[imp.cand_off[i]:imp.cand_off[i + 1]]
+        rows.append(O.impression_metrics(O.rank_impression(s), y))
+    return np.asarray(rows, np.float64)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w, _ = parallel.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    imp = synth.make_impressions(64, 300, seed=9)
+    scores = np.random.default_rng(3).standard_normal(imp.num_pairs).astype(np.float32)
+    scores[::7] = 0.0                                              # ties
+    mine, base, total = parallel.shard_impressions(imp, rank, world)
+    assert total == imp.num_pairs
+    per = _per_impression(mine, scores[base:base + mine.num_pairs])
+    sums = torch.tensor(list(per.sum(0)) + [float(per.shape[0])], dtype=torch.float64)
+    means = parallel.all_reduce_sums(sums)
+    # the reference's mini-batch tail rule must not depend on the shard: global pair index is kept
+    q.put((rank, means, base, mine.num_pairs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_metric_reduction_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    imp = synth.make_impressions(64, 300, seed=9)
+    scores = np.random.default_rng(3).standard_normal(imp.num_pairs).astype(np.float32)
+    scores[::7] = 0.0
+    want = _per_impression(imp, scores).mean(0)
+    for rank, means, base, n in out:
+        assert np.allclose(means, want, rtol=0, atol=1e-12)
+    assert out[0][2] == 0 and out[1][2] == out[0][3] and out[0][3] + out[1][3] == imp.num_pairs
