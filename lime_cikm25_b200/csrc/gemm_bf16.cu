@@ -1,8 +1,184 @@
-// placeholder, replaced by the tcgen05 implementation
+// "bf16 mode" dense layer on the 5th-generation tensor cores (sm_100a):
+//   C = act(bf16(A) . bf16(W)^T + bias) + residual,  fp32 accumulation in TMEM, fp32 in / fp32 out.
+// Same contract as lime_linear (gemm.cu); used for the four transformer GEMMs of the news encoder
+// (newsEncoders.py:244-247) when NewsEncoderEngine.bf16 is set.  Parity bar: metrics within 1e-3.
+//
+// One CTA = one 128 x bn output tile (bn <= 256, multiple of 16).  Warp roles:
+//   warps 0-3  producers: fp32 global -> bf16 -> shared memory in the canonical K-major SWIZZLE_128B
+//              layout (tc05.cuh), 64-wide K chunks, 2-stage ring guarded by full/empty mbarriers;
+//              afterwards the same four warps are the epilogue (warp w owns TMEM lanes 32w..32w+31).
+//   warp 4     allocates TMEM; lane 0 issues tcgen05.mma (M=128, N=bn, K=16) and commits to mbarriers.
+// Two CTAs fit on an SM (96 KB + 256 TMEM columns each), so one CTA's epilogue overlaps the other's
+// main loop.
 #include "common.cuh"
+#include "tc05.cuh"
+
+namespace lime {
+
+constexpr int GB_M = 128, GB_K = 64, GB_STAGES = 2, GB_NMAX = 256;
+constexpr int GB_A_BYTES = GB_M * 128, GB_W_BYTES = GB_NMAX * 128;
+constexpr int GB_STAGE_BYTES = GB_A_BYTES + GB_W_BYTES;
+constexpr int GB_SMEM = GB_STAGES * GB_STAGE_BYTES + 1024 /* alignment slack */ + 64 /* barriers */;
+constexpr int GB_THREADS = 160;
+
+__device__ __forceinline__ float act_apply(int act, float x) {
+    if (act == 1) return fmaxf(x, 0.0f);
+    if (act == 2) return tanhf(x);
+    return x;
+}
+
+// rows x 64 fp32 (row stride ld, valid rows < rows_valid, valid k < k_total) -> bf16 swizzled tile
+__device__ __forceinline__ void stage_tile(unsigned char *tile, const float *__restrict__ src, int64_t ld,
+                                           int64_t row0, int64_t rows_valid, int rows, int k0, int k_total, int tid) {
+    for (int t = tid; t < rows * 8; t += 128) {
+        const int row = t >> 3, chunk = t & 7;
+        const int kk = k0 + chunk * 8;
+        const int64_t r = row0 + row;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (r < rows_valid) {
+            const float *p = src + r * ld + kk;
+            if (kk + 4 <= k_total) a = *reinterpret_cast<const float4 *>(p);
+            if (kk + 8 <= k_total) b = *reinterpret_cast<const float4 *>(p + 4);
+        }
+        uint4 o;
+        o.x = tc::pack_bf16(a.x, a.y);
+        o.y = tc::pack_bf16(a.z, a.w);
+        o.z = tc::pack_bf16(b.x, b.y);
+        o.w = tc::pack_bf16(b.z, b.w);
+        *reinterpret_cast<uint4 *>(tile + tc::sw128_offset(row, chunk)) = o;
+    }
+}
+
+__global__ void __launch_bounds__(GB_THREADS, 2)
+linear_bf16_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ W, int64_t ldw,
+                   const float *__restrict__ bias, const float *__restrict__ residual, int64_t ldr,
+                   float *__restrict__ C, int64_t ldc, int64_t m, int n, int k, int bn, int act, uint32_t idesc) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *base = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + GB_STAGES * GB_STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + GB_STAGES, *accum = bars + 2 * GB_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * GB_STAGES + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = (n + bn - 1) / bn;      // N tiles of one M tile are adjacent CTAs: the A tile is an L2 hit
+    const int64_t row0 = (int64_t)(blockIdx.x / ntiles) * GB_M;
+    const int col0 = (int)(blockIdx.x % ntiles) * bn;
+    const int kchunks = (k + GB_K - 1) / GB_K;
+
+    if (tid == 0) {
+        for (int s = 0; s < GB_STAGES; ++s) {
+            tc::mbar_init(full + s, 128);
+            tc::mbar_init(empty + s, 1);
+        }
+        tc::mbar_init(accum, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 4) tc::tmem_alloc(tmem_slot, 256);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        // ---------------- producers ----------------
+        for (int kc = 0; kc < kchunks; ++kc) {
+            const int s = kc % GB_STAGES;
+            const uint32_t ph = (uint32_t)(kc / GB_STAGES) & 1u;
+            tc::mbar_wait(empty + s, ph ^ 1u);
+            unsigned char *st = base + s * GB_STAGE_BYTES;
+            stage_tile(st, A, lda, row0, m, GB_M, kc * GB_K, k, tid);
+            stage_tile(st + GB_A_BYTES, W, ldw, col0, n, bn, kc * GB_K, k, tid);
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(full + s);
+        }
+        // ---------------- epilogue ----------------
+        tc::mbar_wait(accum, 0);
+        tc::fence_after_sync();
+        const int64_t r = row0 + warp * 32 + lane;
+        const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+        const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+                         (residual == nullptr || (((ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(residual) & 15) == 0)));
+        for (int c0 = 0; c0 < bn; c0 += 16) {
+            float v[16];
+            tc::tmem_ld16(tlane + (uint32_t)c0, v);
+            const int c = col0 + c0;
+            if (r >= m || c >= n) continue;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                float x = v[e];
+                if (bias != nullptr && c + e < n) x += bias[c + e];
+                v[e] = act_apply(act, x);
+            }
+            if (vec && c + 16 <= n) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    if (residual != nullptr) {
+                        const float4 rr = *reinterpret_cast<const float4 *>(residual + r * ldr + c + 4 * q);
+                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                    }
+                    *reinterpret_cast<float4 *>(C + r * ldc + c + 4 * q) = o;
+                }
+            } else {
+                for (int e = 0; e < 16 && c + e < n; ++e) {
+                    float x = v[e];
+                    if (residual != nullptr) x += residual[r * ldr + c + e];
+                    C[r * ldc + c + e] = x;
+                }
+            }
+        }
+    } else {
+        // ---------------- MMA issuer ----------------
+        for (int kc = 0; kc < kchunks; ++kc) {
+            const int s = kc % GB_STAGES;
+            const uint32_t ph = (uint32_t)(kc / GB_STAGES) & 1u;
+            tc::mbar_wait(full + s, ph);
+            tc::fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_addr = tc::smem_u32(base + s * GB_STAGE_BYTES);
+                const uint64_t da = tc::smem_desc_sw128(a_addr), db = tc::smem_desc_sw128(a_addr + GB_A_BYTES);
+                const int rem = k - kc * GB_K;
+                const int ksteps = rem >= GB_K ? GB_K / 16 : (rem + 15) / 16;
+                for (int ks = 0; ks < ksteps; ++ks)
+                    tc::mma_bf16(tmem, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (kc | ks) != 0);
+                tc::mma_commit(empty + s);
+                if (kc == kchunks - 1) tc::mma_commit(accum);
+            }
+            __syncwarp();
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace lime
+
+using namespace lime;
+
 extern "C" int lime_linear_bf16(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias,
                                 const float *residual, int64_t ldr, float *C, int64_t ldc, int64_t m,
                                 int n, int k, int act, void *stream) {
-    lime::set_error("lime_linear_bf16: not implemented yet");
-    return 9;
+    LIME_CHECK_ARG(A && W && C, "lime_linear_bf16: null pointer");
+    LIME_CHECK_ARG(m >= 0 && n > 0 && k > 0, "lime_linear_bf16: bad shape m=%lld n=%d k=%d", (long long)m, n, k);
+    LIME_CHECK_ARG((k & 3) == 0 && (lda & 3) == 0 && (ldw & 3) == 0, "lime_linear_bf16: k, lda, ldw must be multiples of 4");
+    LIME_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "lime_linear_bf16: A and W must be 16-byte aligned");
+    LIME_CHECK_ARG(act >= 0 && act <= 2, "lime_linear_bf16: act %d", act);
+    if (m == 0) return 0;
+    // balanced N tiles: fewest tiles of at most 256 columns, each a multiple of 16
+    const int ntiles = (n + GB_NMAX - 1) / GB_NMAX;
+    const int bn = (((n + ntiles - 1) / ntiles) + 15) & ~15;
+    const int64_t mtiles = (m + GB_M - 1) / GB_M;
+    const int nt = (n + bn - 1) / bn;
+    LIME_CHECK_ARG(mtiles * nt < (int64_t)1 << 31, "lime_linear_bf16: m too large for one launch (%lld rows)", (long long)m);
+    static bool attr_set = false;
+    if (!attr_set) {
+        LIME_CUDA(cudaFuncSetAttribute(linear_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM));
+        attr_set = true;
+    }
+    linear_bf16_kernel<<<(unsigned)(mtiles * nt), GB_THREADS, GB_SMEM, as_stream(stream)>>>(
+        A, lda, W, ldw, bias, residual, ldr, C, ldc, m, n, k, bn, act, tc::idesc_bf16_f32(GB_M, bn));
+    LIME_LAUNCH_CHECK("linear_bf16_kernel");
+    return 0;
 }
