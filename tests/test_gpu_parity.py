@@ -258,3 +258,34 @@ def test_compute_scores_drop_in(lib, tmp_path, monkeypatch):
     assert np.allclose(metrics, want, atol=1e-3)
     lines = open(res).read().split("\n")
     assert len(lines) == imp.num_impressions and lines[0].startswith("1 [")
+
+
+def test_bf16_mode_metrics(lib, golden_dir):
+    """bf16 mode (north star): the four transformer GEMMs of the news encoder on tcgen05 with bf16
+    operands; AUC/MRR/nDCG@5/10 within 1e-3 absolute of the fp32 path, stage vectors bf16-accurate."""
+    cfg, news, imp, g, sd, model = load_case("small_bs8", golden_dir)
+    n0 = g["content"].shape[0]
+    t = lambda a: torch.as_tensor(a[:n0]).to(DEV).contiguous()
+    model.news_encoder.engine.bf16 = True
+    with torch.no_grad():
+        content = model.news_encoder.engine.encode_content(t(news.title_text), t(news.body_text), t(news.category),
+                                                           t(news.subCategory))
+    c = content.cpu().numpy().astype(np.float64)
+    rms = float(np.sqrt(np.mean((c - g["content"]) ** 2)) / np.sqrt(np.mean(g["content"].astype(np.float64) ** 2)))
+    assert 1e-6 < rms < 1e-2, rms        # bf16-accurate, and the tensor-core path really ran (not bit-equal to fp32)
+
+    cfg = make_config(vocabulary_size=5000, batch_size=32, word_embedding_init="skip")
+    model = L.Model(cfg)
+    model.initialize()
+    synth.synthetic_parameters(model, 7)
+    model = model.to(DEV).eval()
+    news = synth.make_news_table(2500, vocabulary_size=5000, seed=21)
+    imp = synth.make_impressions(3000, news.news_num, seed=22)
+    res = {}
+    with torch.no_grad():
+        dimp = engine.DeviceImpressions(imp, DEV)
+        for mode in (False, True):
+            model.news_encoder.engine.bf16 = mode
+            cache = util.build_news_cache(model, news)
+            res[mode] = util.evaluate_impressions(model, cache, dimp, 32)
+    assert np.allclose(res[True], res[False], atol=1e-3), (res[True], res[False])
