@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LIME_B200_ABI_VERSION 1
+#define LIME_B200_ABI_VERSION 2
 
 /* Compile-time model geometry of the LIME-CROWN-CROWN configuration (config.py:54-91 defaults). */
 #define LIME_D        400   /* lime_output_dim == news_embedding_dim == attention_dim          */
@@ -49,6 +49,9 @@ extern "C" {
 #define LIME_CAND_NFOLD 1207 /* columns produced by the folded GEMM: w1,w2,w3 + 7 scalars       */
 #define LIME_HTAB_LD   800  /* per (freshness bucket, lifetime bucket): [ T | gwT ]            */
 #define LIME_CTAB_LD   1208 /* per bucket pair: [ w1T | w2T | w3T | scalT(8) ]                 */
+/* Tensor-core scoring path (score_tc.cu): history rows per impression, candidates per work unit. */
+#define LIME_TC_MAX_HISTORY 64
+#define LIME_TC_TILE_C      42
 
 int         lime_abi_version(void);
 const char *lime_last_error(void);
@@ -167,11 +170,29 @@ typedef struct {
     int32_t tile_c;             /* capacity the unit list was built for                          */
 } LimeImpressions;
 
+/* scratch: caller-owned int32 device buffer of lime_score_scratch_ints(num_units) elements
+ * (work counters + the list of units the fast path hands to the exact kernel); contents are
+ * overwritten by every call.
+ *
+ * Two kernels implement the same arithmetic:
+ *   - exact   (score.cu): every (candidate, history row) gate evaluated element by element; any H <= 224.
+ *   - tensor  (score_tc.cu, H <= LIME_TC_MAX_HISTORY): per history row the gated vector is evaluated at
+ *     4 Chebyshev nodes of the attention weight a over the unit's candidates, the 3 dots with every
+ *     candidate are tcgen05 MMAs on error-compensated bf16 pairs (fp32 accumulation in TMEM), and each
+ *     pair interpolates in a.  A unit whose a-spread makes the interpolation bound exceed the
+ *     tolerance is re-scored by the exact kernel in the same call.
+ * lime_score_configure(mode, tolerance): mode 0 = tensor path with exact fallback (default,
+ * tolerance 1e-6 on the gate), 1 = exact only, 2 = tensor path with every unit forced through the
+ * fallback (tests).  Process-wide. */
 int lime_score_impressions(const LimeNewsCache *cache, const LimeImpressions *imp,
                            int64_t pair_index_base, int32_t prefix_main, int64_t tail_start,
-                           int32_t prefix_tail, float *scores, int32_t *work_counter,
+                           int32_t prefix_tail, float *scores, int32_t *scratch,
                            void *stream);
-/* Dynamic shared memory the scoring kernel needs for (H, tile_c); > 232448 means unsupported. */
+int     lime_score_configure(int32_t mode, float tolerance);
+int64_t lime_score_scratch_ints(int32_t num_units);
+/* Work-unit capacity (candidates per unit) to build the unit list with for a given H; 0 = unsupported. */
+int32_t lime_score_tile_c(int32_t max_history);
+/* Dynamic shared memory the exact scoring kernel needs for (H, tile_c); > 232448 means unsupported. */
 int64_t lime_score_smem_bytes(int32_t max_history, int32_t tile_c);
 
 /* ---- compute_scores' ranking (util.py:113-123) + evaluate.scoring (evaluate.py:32-89) ---------

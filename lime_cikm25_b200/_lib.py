@@ -61,11 +61,14 @@ PROTOTYPES = {
     "lime_score_impressions": (C.c_int, [C.POINTER(LimeNewsCache), C.POINTER(LimeImpressions), I64, I32,
                                          I64, I32, P, P, P]),
     "lime_score_smem_bytes": (I64, [I32, I32]),
+    "lime_score_configure": (C.c_int, [I32, F32]),
+    "lime_score_scratch_ints": (I64, [I32]),
+    "lime_score_tile_c": (I32, [I32]),
     "lime_rank_metrics": (C.c_int, [P, P, P, I64, P, P, P]),
     "lime_metrics_reduce": (C.c_int, [P, I64, P, P]),
 }
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _lib = None
 
 

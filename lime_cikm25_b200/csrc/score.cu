@@ -29,6 +29,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "score_common.cuh"
 
 namespace lime {
 
@@ -43,30 +44,6 @@ constexpr int kTStride = LIME_TOPIC + 1;    // 51: conflict-free column reads of
 constexpr int kTqStride = 12;               // heads padded 10 -> 12 (3 x LDS.128)
 constexpr int kTqWarp = LIME_TOPIC * kTqStride + kTqStride;   // 612 floats per warp
 constexpr int kNW = 3 * kD;                 // 1200 candidate-vector floats staged per candidate
-
-struct ScoreArgs {
-    LimeNewsCache cache;
-    LimeImpressions imp;
-    long long pair_index_base;
-    long long tail_start;
-    int prefix_main;
-    int prefix_tail;
-    float bucket_scale;
-    float ln_eps;
-    float *scores;
-    int *work_counter;
-};
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 // Phase-2 dim mapping: lane owns dims 128*jp + 4*lane + e (jp < 3, e < 4; register slot 4*jp + e) and,
 // for lane < 16, dim 384 + lane (slot 12).  v rows keep the natural order (one LDS.128 per jp); the
@@ -151,18 +128,6 @@ __host__ __device__ inline size_t smem_carve(SmemLayout *L, unsigned char *base,
     return off;
 }
 
-// RemainingLifetimeWeighting weight (util.py:39-46), IEEE fp32 like torch's CUDA sigmoid.
-__device__ __forceinline__ float lifetime_weight(float r, const LimeNewsCache &c) {
-    if (!c.use_lifetime_weighting) return 1.0f;
-    if (c.use_expired_penalty) {
-        float s = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__fmul_rn(c.sigmoid_alpha, r))));
-        float pos = (r >= 0.0f) ? 1.0f : 0.0f;
-        float neg = (r < 0.0f) ? 1.0f : 0.0f;
-        return __fadd_rn(__fmul_rn(pos, s), __fmul_rn(__fmul_rn(neg, c.penalty_beta), s));
-    }
-    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__fmul_rn(c.sigmoid_alpha, fabsf(r)))));
-}
-
 template <int MAXP>
 __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -187,8 +152,13 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
         __syncthreads();   // previous unit fully consumed (also orders the .x init above)
         if (tid == 0) S.unit_bcast[0] = atomicAdd(args.work_counter, 1);
         __syncthreads();
-        const int unit = S.unit_bcast[0];
-        if (unit >= I.num_units) break;
+        int unit = S.unit_bcast[0];
+        if (args.unit_list != nullptr) {
+            if (unit >= *args.unit_list_count) break;
+            unit = args.unit_list[unit];
+        } else if (unit >= I.num_units) {
+            break;
+        }
         const int imp = I.unit_imp[unit];
         const int pair0 = I.unit_pair0[unit];
         const int cnt = I.unit_count[unit];
@@ -526,47 +496,18 @@ __global__ void __launch_bounds__(kThreads, 1) score_kernel(const ScoreArgs args
 
 }  // namespace lime
 
-using namespace lime;
+namespace lime {
 
-extern "C" int64_t lime_score_smem_bytes(int32_t max_history, int32_t tile_c) {
-    return (int64_t)smem_carve(nullptr, nullptr, max_history, tile_c);
-}
+int64_t score_exact_smem(int H, int TC) { return (int64_t)smem_carve(nullptr, nullptr, H, TC); }
 
-extern "C" int lime_score_impressions(const LimeNewsCache *cache, const LimeImpressions *imp,
-                                      int64_t pair_index_base, int32_t prefix_main,
-                                      int64_t tail_start, int32_t prefix_tail, float *scores,
-                                      int32_t *work_counter, void *stream) {
-    LIME_CHECK_ARG(cache && imp && scores && work_counter, "lime_score_impressions: null argument");
-    const int H = imp->max_history, TC = imp->tile_c;
-    LIME_CHECK_ARG(H >= 1 && H <= 224, "lime_score_impressions: max_history %d not in [1,224]", H);
-    LIME_CHECK_ARG(TC >= 1, "lime_score_impressions: tile_c %d < 1", TC);
-    LIME_CHECK_ARG(cache->num_buckets >= 1 && cache->news_num >= 1, "lime_score_impressions: empty cache");
-    // runtime batch larger than max_history + config.batch_size is an out-of-range gather in the
-    // reference (userEncoders.py:94,153); reject it instead of reading past user_node_embedding
-    LIME_CHECK_ARG(prefix_main >= 1 && prefix_main <= H + cache->user_nodes,
-                   "lime_score_impressions: prefix_main %d not in [1, %d]", prefix_main, H + cache->user_nodes);
-    LIME_CHECK_ARG(prefix_tail >= 1 && prefix_tail <= H + cache->user_nodes,
-                   "lime_score_impressions: prefix_tail %d not in [1, %d]", prefix_tail, H + cache->user_nodes);
-    if (imp->num_units <= 0) return 0;
+// exact kernel over all units (unit_list == NULL) or over the device-side fallback list
+int launch_score_exact(const ScoreArgs &a, int grid_limit, cudaStream_t st) {
+    const int H = a.imp.max_history, TC = a.imp.tile_c;
     const size_t smem = smem_carve(nullptr, nullptr, H, TC);
     LIME_CHECK_ARG(smem <= 232448, "lime_score_impressions: (H=%d, tile_c=%d) needs %zu B of shared memory", H, TC, smem);
-
-    ScoreArgs a;
-    a.cache = *cache;
-    a.imp = *imp;
-    a.pair_index_base = pair_index_base;
-    a.tail_start = tail_start;
-    a.prefix_main = prefix_main;
-    a.prefix_tail = prefix_tail;
-    a.bucket_scale = (float)((double)cache->num_buckets / 7.0);
-    a.ln_eps = 1e-5f;
-    a.scores = scores;
-    a.work_counter = work_counter;
-
-    cudaStream_t st = as_stream(stream);
-    LIME_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(int32_t), st));
+    LIME_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int32_t), st));
     int grid = num_sms();
-    if (grid > imp->num_units) grid = imp->num_units;
+    if (grid > grid_limit) grid = grid_limit;
     const int passes = (H + 31) / 32;
     if (passes <= 2) {
         LIME_CUDA(cudaFuncSetAttribute(score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -580,4 +521,80 @@ extern "C" int lime_score_impressions(const LimeNewsCache *cache, const LimeImpr
     }
     LIME_LAUNCH_CHECK("score_kernel");
     return 0;
+}
+
+// process-wide scoring mode (lime_score_configure)
+static int g_score_mode = 0;
+static float g_score_tol = 1e-6f;
+
+}  // namespace lime
+
+using namespace lime;
+
+extern "C" int64_t lime_score_smem_bytes(int32_t max_history, int32_t tile_c) {
+    return (int64_t)smem_carve(nullptr, nullptr, max_history, tile_c);
+}
+
+extern "C" int64_t lime_score_scratch_ints(int32_t num_units) { return 4 + (int64_t)(num_units > 0 ? num_units : 0); }
+
+extern "C" int32_t lime_score_tile_c(int32_t max_history) {
+    if (max_history <= LIME_TC_MAX_HISTORY) return LIME_TC_TILE_C;
+    for (int tc = 48; tc >= 8; tc -= 8)
+        if (smem_carve(nullptr, nullptr, max_history, tc) <= 232448) return tc;
+    return 0;
+}
+
+extern "C" int lime_score_configure(int32_t mode, float tolerance) {
+    LIME_CHECK_ARG(mode >= 0 && mode <= 2, "lime_score_configure: mode %d not in {0,1,2}", mode);
+    g_score_mode = mode;
+    g_score_tol = tolerance;
+    return 0;
+}
+
+extern "C" int lime_score_impressions(const LimeNewsCache *cache, const LimeImpressions *imp,
+                                      int64_t pair_index_base, int32_t prefix_main,
+                                      int64_t tail_start, int32_t prefix_tail, float *scores,
+                                      int32_t *scratch, void *stream) {
+    LIME_CHECK_ARG(cache && imp && scores && scratch, "lime_score_impressions: null argument");
+    const int H = imp->max_history, TC = imp->tile_c;
+    LIME_CHECK_ARG(H >= 1 && H <= 224, "lime_score_impressions: max_history %d not in [1,224]", H);
+    LIME_CHECK_ARG(TC >= 1, "lime_score_impressions: tile_c %d < 1", TC);
+    LIME_CHECK_ARG(cache->num_buckets >= 1 && cache->news_num >= 1, "lime_score_impressions: empty cache");
+    // runtime batch larger than max_history + config.batch_size is an out-of-range gather in the
+    // reference (userEncoders.py:94,153); reject it instead of reading past user_node_embedding
+    LIME_CHECK_ARG(prefix_main >= 1 && prefix_main <= H + cache->user_nodes,
+                   "lime_score_impressions: prefix_main %d not in [1, %d]", prefix_main, H + cache->user_nodes);
+    LIME_CHECK_ARG(prefix_tail >= 1 && prefix_tail <= H + cache->user_nodes,
+                   "lime_score_impressions: prefix_tail %d not in [1, %d]", prefix_tail, H + cache->user_nodes);
+    if (imp->num_units <= 0) return 0;
+
+    ScoreArgs a;
+    a.cache = *cache;
+    a.imp = *imp;
+    a.pair_index_base = pair_index_base;
+    a.tail_start = tail_start;
+    a.prefix_main = prefix_main;
+    a.prefix_tail = prefix_tail;
+    a.bucket_scale = (float)((double)cache->num_buckets / 7.0);
+    a.ln_eps = 1e-5f;
+    a.scores = scores;
+    a.work_counter = scratch;
+    a.unit_list = nullptr;
+    a.unit_list_count = nullptr;
+    a.fallback_list = scratch + 4;
+    a.fallback_count = scratch + 1;
+    a.interp_tol = g_score_mode == 2 ? 0.0f : g_score_tol;
+    cudaStream_t st = as_stream(stream);
+
+    const bool tc_ok = g_score_mode != 1 && H <= LIME_TC_MAX_HISTORY && TC <= LIME_TC_TILE_C;
+    if (!tc_ok) return launch_score_exact(a, imp->num_units, st);
+
+    // fast path: interpolated gate + tcgen05 dots; units whose error bound exceeds the tolerance are
+    // appended to a device-side list and re-scored by the exact kernel (usually an empty launch)
+    int rc = launch_score_tc(a, st);
+    if (rc != 0) return rc;
+    a.work_counter = scratch + 2;
+    a.unit_list = scratch + 4;
+    a.unit_list_count = scratch + 1;
+    return launch_score_exact(a, imp->num_units, st);
 }

@@ -100,6 +100,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// same with fp16 operands (format code 0)
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // D[tmem] (+)= A[smem] . B[smem]^T ; one thread issues for the CTA
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          bool accumulate) {
@@ -109,6 +114,11 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
+}
+
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        bool accumulate) {
+    mma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);   // same instruction; the operand format is in idesc
 }
 
 // arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed

@@ -201,10 +201,13 @@ class ScoringEngine:
         ops.scale_rows(G[400:800], gamma, 1.0)
         G[800:1200].copy_(Wl.t())
         ops.scale_rows(G[800:1200], gamma, 1.0)
-        ones = torch.ones(1, D, **f32)
-        ops.gemm_strided(ones, G[0:400], out=G[1200:1201])               # W1s = gamma . p / 20
-        ops.gemm_strided(ones, G[400:800], out=G[1201:1202])             # W2s
-        ops.gemm_strided(ones, G[800:1200], out=G[1202:1203])            # W3s
+        # LayerNorm subtracts the row mean of o, so only the mean-free part of each folded candidate
+        # vector matters:  sum_d (o_d - mu) w_d = sum_d o_d (w_d - mean(w)).  Centring the three blocks
+        # here (w -> (I - 11^T/D) w, linear in v) removes the cancellation D - mu * sum(w) from both
+        # scoring kernels; the three "sum of w" scalars (columns 1200..1202) become exact zeros.
+        centre = torch.eye(D, **f32) - 1.0 / D
+        for blk in range(3):
+            G[blk * 400:(blk + 1) * 400].copy_(ops.gemm_strided(centre, G[blk * 400:(blk + 1) * 400].clone()))
         ops.gemm_strided(beta.view(1, D), Pm, alpha=inv_s, out=G[1203:1204])   # B1 = beta . p / 20
         ops.gemm_strided(beta.view(1, D), Wr.t(), out=G[1204:1205])      # B2
         ops.gemm_strided(beta.view(1, D), Wl.t(), out=G[1205:1206])      # B3
@@ -216,7 +219,7 @@ class ScoringEngine:
         cconst = torch.zeros(CAND_NFOLD + 1, **f32)
         cconst[0:400].copy_(p0.view(-1))
         ops.scale_rows(cconst[0:400].view(D, 1), gamma, inv_s)           # gamma * p0 / 20
-        ops.gemm_strided(ones, cconst[0:400].view(D, 1), out=cconst[1200:1201].view(1, 1))
+        cconst[0:400].copy_(ops.gemm_strided(centre, cconst[0:400].clone().view(D, 1)).view(-1))
         ops.gemm_strided(beta.view(1, D), p0.view(D, 1), alpha=inv_s, out=cconst[1203:1204].view(1, 1))
         F["cconst"] = cconst
         # gate: z' = -log2(e) (a W_g v + b_g)
@@ -324,12 +327,13 @@ class ScoringEngine:
 
 
 def choose_tile_c(max_history):
-    """Largest multiple of 16 (warps per CTA) up to 48 whose shared-memory footprint fits."""
+    """Candidates per work unit for this history length (lime_score_tile_c: 42 on the tensor-core
+    path, H <= 64; the largest shared-memory-feasible multiple of 8 up to 48 on the exact path)."""
     lib = _lib.load()
-    for tc in (48, 32, 16, 8):
-        if lib.lime_score_smem_bytes(int(max_history), tc) <= 232448:
-            return tc
-    raise _lib.LimeError("max_history=%d does not fit the scoring kernel's shared memory" % max_history)
+    tc = int(lib.lime_score_tile_c(int(max_history)))
+    if tc <= 0:
+        raise _lib.LimeError("max_history=%d does not fit the scoring kernel's shared memory" % max_history)
+    return tc
 
 
 def build_units(cand_off, tile_c):
@@ -374,7 +378,7 @@ class DeviceImpressions:
             unit_count=torch.full((B,), n_cand, **i32))
         if cand_remaining is not None:
             self.dev["cand_remaining"] = cand_remaining.float().reshape(-1).contiguous()
-        self.work_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.work_counter = torch.zeros(int(_lib.load().lime_score_scratch_ints(self.num_units)), dtype=torch.int32, device=dev)
         return self
 
     def __init__(self, imp, device, tile_c=None, cand_remaining=None):
@@ -403,7 +407,8 @@ class DeviceImpressions:
         self.pinned = {k: torch.from_numpy(v).pin_memory() for k, v in self.host.items()}
         self.dev = {}
         self.device = device
-        self.work_counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.work_counter = torch.zeros(int(_lib.load().lime_score_scratch_ints(self.num_units)), dtype=torch.int32,
+                                        device=device)
         self.upload()
 
     def h2d_bytes(self):

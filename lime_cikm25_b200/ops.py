@@ -186,3 +186,12 @@ def metrics_reduce(metrics):
     check(lib.lime_metrics_reduce(_ptr(metrics, torch.float64, "metrics"), metrics.shape[0],
                                   sums.data_ptr(), _stream()), "lime_metrics_reduce")
     return sums
+
+
+SCORE_AUTO, SCORE_EXACT, SCORE_FORCE_FALLBACK = 0, 1, 2
+
+
+def score_configure(mode=SCORE_AUTO, tolerance=1e-6):
+    """lime_score_configure: 0 = tensor-core scoring with exact fallback (default), 1 = exact kernel
+    only, 2 = tensor-core path with every unit forced through the fallback (tests)."""
+    check(_lib.load().lime_score_configure(int(mode), float(tolerance)), "lime_score_configure")
