@@ -41,17 +41,21 @@ extern "C" {
 #define LIME_HIST_VC   0
 #define LIME_HIST_GW   400
 #define LIME_HIST_T    800
+#define LIME_HIST_TOPIC_ID 850 /* int32 bit pattern: compact id of the news' (category, subCategory) pair */
 #define LIME_CAND_LD   1720 /* [ w1 | w2 | w3 | scal(8) | tq 50x10 | qb 10 | pad 2 ]           */
 #define LIME_CAND_W    0
 #define LIME_CAND_SCAL 1200
 #define LIME_CAND_TQ   1208
 #define LIME_CAND_QB   1708
+#define LIME_CAND_TOPIC_ID 1718 /* int32 bit pattern, same id as LIME_HIST_TOPIC_ID                 */
 #define LIME_CAND_NFOLD 1207 /* columns produced by the folded GEMM: w1,w2,w3 + 7 scalars       */
 #define LIME_HTAB_LD   800  /* per (freshness bucket, lifetime bucket): [ T | gwT ]            */
 #define LIME_CTAB_LD   1208 /* per bucket pair: [ w1T | w2T | w3T | scalT(8) ]                 */
 /* Tensor-core scoring path (score_tc.cu): history rows per impression, candidates per work unit. */
 #define LIME_TC_MAX_HISTORY 64
-#define LIME_TC_TILE_C      42
+#define LIME_TC_TILE_C      37
+#define LIME_TOPIC_TAB_LD   12  /* 10 head logits of a (candidate topic, history topic) pair, padded */
+#define LIME_TC_MAX_TOPICS  1024
 
 int         lime_abi_version(void);
 const char *lime_last_error(void);
@@ -140,9 +144,12 @@ typedef struct {
     const float *cand_tab;      /* [nb*nb, LIME_CTAB_LD]                                         */
     const float *gate_bias;     /* [LIME_D]  -log2(e) * gate_proj.bias                           */
     const float *un_prefix;     /* [config.batch_size, LIME_D] prefix sums of lin_l(user_node_embedding) */
+    const float *topic_table;   /* [num_topics, num_topics, LIME_TOPIC_TAB_LD] from lime_topic_pair_table,
+                                   or NULL (then only the exact kernel can run)                      */
     int32_t news_num;
     int32_t num_buckets;
     int32_t user_nodes;         /* config.batch_size (rows of user_node_embedding)               */
+    int32_t num_topics;         /* distinct (category, subCategory) pairs registered in the cache */
     float   sigmoid_alpha;      /* config.sigmoid_scaling_alpha                                  */
     float   penalty_beta;       /* config.penalty_scaling_beta                                   */
     int32_t use_lifetime_weighting; /* config.use_remaining_lifetime_weighting                   */
@@ -184,11 +191,22 @@ typedef struct {
  * lime_score_configure(mode, tolerance): mode 0 = tensor path with exact fallback (default,
  * tolerance 1e-6 on the gate), 1 = exact only, 2 = tensor path with every unit forced through the
  * fallback (tests).  Process-wide. */
+/* sizeof() of the two argument structs as this library was compiled (binding self-check). */
+int64_t lime_sizeof_news_cache(void);
+int64_t lime_sizeof_impressions(void);
+
 int lime_score_impressions(const LimeNewsCache *cache, const LimeImpressions *imp,
                            int64_t pair_index_base, int32_t prefix_main, int64_t tail_start,
                            int32_t prefix_tail, float *scores, int32_t *scratch,
                            void *stream);
 int     lime_score_configure(int32_t mode, float tolerance);
+/* Candidate-aware attention logits depend on the news only through their (category, subCategory)
+ * pair (layers.py:66-70 on the 50-d topic representations), so they are tabulated once per checkpoint:
+ *   out[(tc * T + th) * LIME_TOPIC_TAB_LD + head] = Q_head(topic tc) . K_head(topic th) / sqrt(D)
+ * topics [T, ldt]: topic representation of every distinct topic (50 used columns);
+ * tq [T, ldq]: the [50*10 | 10] candidate-role affine image of the same topics (LIME_CAND_TQ block). */
+int     lime_topic_pair_table(const float *topics, int64_t ldt, const float *tq, int64_t ldq, int32_t T,
+                              float *out, void *stream);
 int64_t lime_score_scratch_ints(int32_t num_units);
 /* Work-unit capacity (candidates per unit) to build the unit list with for a given H; 0 = unsupported. */
 int32_t lime_score_tile_c(int32_t max_history);

@@ -19,7 +19,8 @@ class LimeNewsCache(C.Structure):
     _fields_ = [
         ("hist_rows", C.c_void_p), ("cand_rows", C.c_void_p), ("hist_tab", C.c_void_p),
         ("cand_tab", C.c_void_p), ("gate_bias", C.c_void_p), ("un_prefix", C.c_void_p),
-        ("news_num", C.c_int32), ("num_buckets", C.c_int32), ("user_nodes", C.c_int32),
+        ("topic_table", C.c_void_p),
+        ("news_num", C.c_int32), ("num_buckets", C.c_int32), ("user_nodes", C.c_int32), ("num_topics", C.c_int32),
         ("sigmoid_alpha", C.c_float), ("penalty_beta", C.c_float),
         ("use_lifetime_weighting", C.c_int32), ("use_expired_penalty", C.c_int32),
     ]
@@ -64,6 +65,9 @@ PROTOTYPES = {
     "lime_score_configure": (C.c_int, [I32, F32]),
     "lime_score_scratch_ints": (I64, [I32]),
     "lime_score_tile_c": (I32, [I32]),
+    "lime_sizeof_news_cache": (I64, []),
+    "lime_sizeof_impressions": (I64, []),
+    "lime_topic_pair_table": (C.c_int, [P, I64, P, I64, I32, P, P]),
     "lime_rank_metrics": (C.c_int, [P, P, P, I64, P, P, P]),
     "lime_metrics_reduce": (C.c_int, [P, I64, P, P]),
 }
@@ -90,6 +94,9 @@ def load():
         fn = getattr(lib, name)          # AttributeError here == header/library mismatch
         fn.restype = res
         fn.argtypes = args
+    if (lib.lime_sizeof_news_cache() != C.sizeof(LimeNewsCache)
+            or lib.lime_sizeof_impressions() != C.sizeof(LimeImpressions)):
+        raise LimeError("ctypes struct layout does not match include/lime_b200.h")
     if lib.lime_abi_version() != ABI_VERSION:
         raise LimeError("liblime_b200.so ABI %d != binding ABI %d" % (lib.lime_abi_version(), ABI_VERSION))
     _lib = lib

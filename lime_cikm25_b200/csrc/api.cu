@@ -49,3 +49,7 @@ extern "C" int lime_device_count(void) {
 extern "C" int64_t lime_launch_count(void) { return lime::g_launches; }
 
 extern "C" void lime_launch_count_reset(void) { lime::g_launches = 0; }
+
+extern "C" int64_t lime_sizeof_news_cache(void) { return (int64_t)sizeof(LimeNewsCache); }
+
+extern "C" int64_t lime_sizeof_impressions(void) { return (int64_t)sizeof(LimeImpressions); }

@@ -586,7 +586,8 @@ extern "C" int lime_score_impressions(const LimeNewsCache *cache, const LimeImpr
     a.interp_tol = g_score_mode == 2 ? 0.0f : g_score_tol;
     cudaStream_t st = as_stream(stream);
 
-    const bool tc_ok = g_score_mode != 1 && H <= LIME_TC_MAX_HISTORY && TC <= LIME_TC_TILE_C;
+    const bool tc_ok = g_score_mode != 1 && H <= LIME_TC_MAX_HISTORY && TC <= LIME_TC_TILE_C &&
+                       cache->topic_table != nullptr && cache->num_topics >= 1;
     if (!tc_ok) return launch_score_exact(a, imp->num_units, st);
 
     // fast path: interpolated gate + tcgen05 dots; units whose error bound exceeds the tolerance are

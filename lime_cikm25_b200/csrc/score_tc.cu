@@ -21,12 +21,15 @@
 //   2^-17, measurably is not enough: 6e-5 on the logits).  Units holding a value beyond the fp16 range are
 //   flagged for the exact kernel as well.
 //
-// CTA = 16 compute warps + 1 MMA-issuer warp, persistent, one per SM; work units as in score.cu.
-// Per unit:  phase 0 metadata / bucketize -> phase 1 topic attention a[c][h] (CUDA cores, exact) ->
-//   nodes -> 7 K-chunks of 64 dims: compute warps write the swizzled fp16 hi/lo operand tiles of
-//   O (256 x 64) and W (<=128 x 64) into a 2-stage shared-memory ring while the issuer warp runs the
-//   previous chunk's MMAs (mbarrier full/free) -> epilogue: TMEM -> registers, Lagrange combination over
-//   the 4 lanes of a quad, LayerNorm folding -> phase 3 pooling softmax + GraphSAGE mean + lifetime weight.
+// CTA = 8 compute warps + 1 MMA-issuer warp, persistent, TWO per SM (110 KB of shared memory and 256 TMEM
+// columns each) so that one CTA's latency-bound phases overlap the other's math; work units as in score.cu.
+// Per unit:  phase 0 metadata / bucketize / L2 prefetch of the unit's cache rows -> phase 1 topic attention
+//   a[c][h]: head logits gathered from the (candidate topic, history topic) table, softmaxes in registers ->
+//   nodes -> 13 K-chunks of 32 dims: compute warps write the swizzled fp16 hi/lo operand tiles of
+//   O (256 rows) and W (<=112 rows); the two 32-dim halves of the 64-dim SWIZZLE_128B tile act as a 2-stage
+//   ring (mbarrier full/free) so the issuer warp runs chunk k's MMAs while chunk k+1 is produced ->
+//   epilogue: TMEM -> registers, Lagrange combination over the 4 lanes of a quad, LayerNorm folding ->
+//   phase 3 pooling softmax + GraphSAGE mean + lifetime weight.
 #include "score_common.cuh"
 #include <cuda_fp16.h>
 
@@ -36,56 +39,55 @@ namespace lime {
 namespace {
 
 constexpr int kD = LIME_D;
-constexpr int kWarps = 16;
-constexpr int kThreads = (kWarps + 1) * 32;
+constexpr int kWarps = 8;                       // compute warps; warp 8 issues the MMAs
+constexpr int kCompute = kWarps * 32;
+constexpr int kThreads = kCompute + 32;
 constexpr int kRows = LIME_TC_MAX_HISTORY;      // history rows per unit -> 4 * 64 = 256 operand rows
-constexpr int kTile = LIME_TC_TILE_C;           // candidates per unit -> 3 * 42 = 126 <= 128 MMA columns
-constexpr int kChunks = 7;                      // 64-wide K chunks over D = 400 (the last holds 16 dims)
-constexpr int kABytes = 256 * 128;
-constexpr int kBBytes = 128 * 128;
-constexpr int kStage = 2 * kABytes + 2 * kBBytes;
-constexpr int kTStride = LIME_TOPIC + 1;
-constexpr int kTqStride = 12;
-constexpr int kTqWarp = LIME_TOPIC * kTqStride + kTqStride;
-constexpr int kBThreads = 12 * 32;              // warps with warp % 4 != 0 stage the candidate operand
+constexpr int kTile = LIME_TC_TILE_C;           // candidates per unit -> 3 * 37 = 111 <= 112 MMA columns
+constexpr int kNMax = 112;
+constexpr int kChunks = 13;                     // 32-wide K chunks over D = 400 (the last holds 16 dims)
+constexpr int kABytes = 256 * 128;              // one 64-dim operand image of O (hi or lo)
+constexpr int kBBytes = kNMax * 128;            // one 64-dim operand image of W (hi or lo)
+constexpr int kTileBytes = 2 * kABytes + 2 * kBBytes;
+constexpr int kTabLd = LIME_TOPIC_TAB_LD;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kHalfSafe = 32768.0f;             // operands beyond this are not split into fp16 pairs
+constexpr float kHalfSafe = 32768.0f;           // operands beyond this are not split into fp16 pairs
 
 // shared-memory map (bytes from the 1024-aligned base)
-constexpr int OFF_STAGE = 0;                                  // 2 x kStage
-constexpr int OFF_T = 0;                                      //   alias (phase 1): topic tile [64][51]
-constexpr int OFF_TQ = 16384;                                 //   alias (phase 1): per-warp tq [16][612]
-constexpr int OFF_LG = 0;                                     //   alias (after the MMAs): lg / y / z [42][64]
+constexpr int OFF_AHI = 0, OFF_ALO = kABytes, OFF_BHI = 2 * kABytes, OFF_BLO = 2 * kABytes + kBBytes;
+constexpr int OFF_LG = 0;                                     // alias (after the MMAs): lg / y / z [37][64]
 constexpr int OFF_Y = OFF_LG + kTile * kRows * 4;
 constexpr int OFF_Z = OFF_Y + kTile * kRows * 4;
-constexpr int OFF_A = 2 * kStage;                             // a[c][h]  [42][64]
+constexpr int OFF_A = kTileBytes;                             // a[c][h]  [37][64]
 constexpr int OFF_BIAS = OFF_A + kTile * kRows * 4;           // gate bias' [400]
 constexpr int OFF_S01 = OFF_BIAS + kD * 4;                    // node sums [64][4][2]
 constexpr int OFF_MID = OFF_S01 + kRows * 8 * 4;
 constexpr int OFF_WINV = OFF_MID + kRows * 4;
 constexpr int OFF_WHALF = OFF_WINV + kRows * 4;
 constexpr int OFF_GMAX = OFF_WHALF + kRows * 4;
-constexpr int OFF_CSCAL = OFF_GMAX + kRows * 4;               // [42][8]
+constexpr int OFF_CSCAL = OFF_GMAX + kRows * 4;               // [37][8]
 constexpr int OFF_CW = OFF_CSCAL + kTile * 8 * 4;
-constexpr int OFF_CNEWS = OFF_CW + 176;
-constexpr int OFF_CTAB = OFF_CNEWS + 176;
-constexpr int OFF_CP = OFF_CTAB + 176;
-constexpr int OFF_HNEWS = OFF_CP + 176;
+constexpr int OFF_CNEWS = OFF_CW + 160;
+constexpr int OFF_CTAB = OFF_CNEWS + 160;
+constexpr int OFF_CP = OFF_CTAB + 160;
+constexpr int OFF_CTOPIC = OFF_CP + 160;
+constexpr int OFF_HNEWS = OFF_CTOPIC + 160;
 constexpr int OFF_HTAB = OFF_HNEWS + kRows * 4;
 constexpr int OFF_HMASK = OFF_HTAB + kRows * 4;
-constexpr int OFF_BARS = OFF_HMASK + kRows * 4;               // full[2] free[2] accum
+constexpr int OFF_HTOPIC = OFF_HMASK + kRows * 4;
+constexpr int OFF_BARS = OFF_HTOPIC + kRows * 4;              // full[2] free[2] accum
 constexpr int OFF_MISC = OFF_BARS + 64;                       // tmem slot, unit broadcast, flag
 constexpr int kSmemBytes = OFF_MISC + 64 + 1024;
-static_assert(OFF_TQ + kWarps * kTqWarp * 4 <= 2 * kStage, "phase-1 alias overflows the operand ring");
-static_assert(OFF_Z + kTile * kRows * 4 <= kStage, "epilogue alias overflows stage 0");
-static_assert(kSmemBytes <= 232448, "shared memory budget");
-static_assert(OFF_BARS % 8 == 0 && OFF_A % 16 == 0 && OFF_BIAS % 16 == 0, "alignment");
+static_assert(OFF_Z + kTile * kRows * 4 <= 2 * kABytes, "epilogue alias overflows the O operand images");
+static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
+static_assert(OFF_BARS % 8 == 0 && OFF_A % 16 == 0 && OFF_BIAS % 16 == 0 && OFF_BLO % 1024 == 0, "alignment");
 
 // 4 Chebyshev nodes on [-1, 1]
 constexpr float kX0 = -0.92387953251128674f, kX1 = -0.38268343236508977f;
 constexpr float kX2 = 0.38268343236508977f, kX3 = 0.92387953251128674f;
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // 8 fp32 -> 8 fp16 hi + 8 fp16 lo (x = hi + lo to 2^-22: 11 + 11 significant bits), as two 16-byte
 // chunks; returns max |x| so the caller can flag values outside the fp16 range
@@ -106,11 +108,9 @@ __device__ __forceinline__ float split8(const float (&x)[8], uint4 &hi, uint4 &l
     return mx;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const ScoreArgs args) {
+__global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs args) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float *t_s = reinterpret_cast<float *>(base + OFF_T);
-    float *tq_s = reinterpret_cast<float *>(base + OFF_TQ);
     float *lg_s = reinterpret_cast<float *>(base + OFF_LG);
     float *y_s = reinterpret_cast<float *>(base + OFF_Y);
     float *z_s = reinterpret_cast<float *>(base + OFF_Z);
@@ -126,9 +126,11 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const ScoreArgs a
     int *cnews = reinterpret_cast<int *>(base + OFF_CNEWS);
     int *ctab = reinterpret_cast<int *>(base + OFF_CTAB);
     int *cP = reinterpret_cast<int *>(base + OFF_CP);
+    int *ctopic = reinterpret_cast<int *>(base + OFF_CTOPIC);
     int *hnews = reinterpret_cast<int *>(base + OFF_HNEWS);
     int *htab = reinterpret_cast<int *>(base + OFF_HTAB);
     int *hmask = reinterpret_cast<int *>(base + OFF_HMASK);
+    int *htopic = reinterpret_cast<int *>(base + OFF_HTOPIC);
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(base + OFF_BARS);
     uint64_t *bar_free = bar_full + 2;
     uint64_t *bar_accum = bar_full + 4;
@@ -140,13 +142,13 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const ScoreArgs a
     const LimeImpressions &I = args.imp;
     const int H = I.max_history;
     const int nb = C.num_buckets;
+    const int T = C.num_topics;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int passes = (H + 31) >> 5;
 
     for (int d = tid; d < kD; d += kThreads) bias_s[d] = C.gate_bias[d];
     if (tid == 0) {
-        tc::mbar_init(bar_full + 0, kWarps * 32);
-        tc::mbar_init(bar_full + 1, kWarps * 32);
+        tc::mbar_init(bar_full + 0, kCompute);
+        tc::mbar_init(bar_full + 1, kCompute);
         tc::mbar_init(bar_free + 0, 1);
         tc::mbar_init(bar_free + 1, 1);
         tc::mbar_init(bar_accum, 1);
@@ -158,8 +160,8 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const ScoreArgs a
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    uint32_t g = 0;          // K chunks staged so far by this CTA: stage = g & 1, per-stage use = g >> 1
-    uint32_t unit_iter = 0;  // units processed so far (phase of bar_accum)
+    uint32_t use[2] = {0u, 0u};   // how often each 32-dim half of the operand tile has been staged so far
+    uint32_t unit_iter = 0;       // units processed so far (phase of bar_accum)
 
     for (;;) {
         __syncthreads();
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const ScoreArgs a
         const int pair0 = I.unit_pair0[unit];
         const int cnt = I.unit_count[unit];
 
-        // ---------------- phase 0: unit metadata ------------------------------------------------
+        // ---------------- phase 0: unit metadata, L2 prefetch of the rows the unit will read ------
         for (int h = tid; h < H; h += kThreads) {
             const long long o = (long long)imp * H + h;
             int n = I.hist_news[o];
@@ -181,6 +183,9 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const ScoreArgs a
             const int bf = bucketize_seconds(I.hist_fresh[o], args.bucket_scale, nb);
             const int bl = bucketize_seconds(I.hist_life[o], args.bucket_scale, nb);
             htab[h] = bf * nb + bl;
+            const float *hrow = C.hist_rows + (size_t)n * LIME_HIST_LD;
+            int tp = __float_as_int(__ldg(hrow + LIME_HIST_TOPIC_ID));
+            htopic[h] = (tp < 0 || tp >= T) ? 0 : tp;
         }
         for (int c = tid; c < cnt; c += kThreads) {
             const long long p = (long long)pair0 + c;
@@ -191,81 +196,63 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const ScoreArgs a
             ctab[c] = bucketize_seconds(fr, args.bucket_scale, nb) * nb + bucketize_seconds(lf, args.bucket_scale, nb);
             cw[c] = lifetime_weight(I.cand_remaining ? I.cand_remaining[p] : __fsub_rn(lf, fr), C);
             cP[c] = (args.pair_index_base + p >= args.tail_start) ? args.prefix_tail : args.prefix_main;
+            const float *crow = C.cand_rows + (size_t)n * LIME_CAND_LD;
+            int tp = __float_as_int(__ldg(crow + LIME_CAND_TOPIC_ID));
+            ctopic[c] = (tp < 0 || tp >= T) ? 0 : tp;
         }
         if (tid == 0) flag_s[0] = 0;
         __syncthreads();
-        for (int idx = tid; idx < H * LIME_TOPIC; idx += kThreads) {
-            const int h = idx / LIME_TOPIC, k = idx - h * LIME_TOPIC;
-            t_s[h * kTStride + k] = C.hist_rows[(size_t)hnews[h] * LIME_HIST_LD + LIME_HIST_T + k];
+        // history rows: vc | gw = 3200 B = 25 lines; candidate rows: w1 w2 w3 = 4800 B = 38 lines (+1 unaligned)
+        for (int idx = tid; idx < H * 26; idx += kThreads) {
+            const int h = idx / 26, l = idx - h * 26;
+            prefetch_l2(reinterpret_cast<const char *>(C.hist_rows + (size_t)hnews[h] * LIME_HIST_LD) + l * 128);
         }
-        __syncthreads();
+        for (int idx = tid; idx < cnt * 39; idx += kThreads) {
+            const int c = idx / 39, l = idx - c * 39;
+            prefetch_l2(reinterpret_cast<const char *>(C.cand_rows + (size_t)cnews[c] * LIME_CAND_LD) + l * 128);
+        }
 
         // ---------------- phase 1: candidate-aware attention weights a[c][h] (layers.py:66-81) ----
         if (warp < kWarps) {
+            const bool v0 = lane < H, v1 = lane + 32 < H;
+            const int t0 = htopic[v0 ? lane : 0], t1 = htopic[v1 ? lane + 32 : 0];
+            const bool k0 = v0 && hmask[v0 ? lane : 0] != 0, k1 = v1 && hmask[v1 ? lane + 32 : 0] != 0;
             for (int c = warp; c < cnt; c += kWarps) {
-                float *tq = tq_s + warp * kTqWarp;
-                const float *crow = C.cand_rows + (size_t)cnews[c] * LIME_CAND_LD;
-                for (int idx = lane; idx < LIME_TOPIC * LIME_CA_HEADS; idx += 32) {
-                    const int k = idx / LIME_CA_HEADS, hd = idx - k * LIME_CA_HEADS;
-                    tq[k * kTqStride + hd] = crow[LIME_CAND_TQ + idx];
-                }
-                if (lane < LIME_CA_HEADS) tq[LIME_TOPIC * kTqStride + lane] = crow[LIME_CAND_QB + lane];
                 if (lane < 8) {
+                    const float *crow = C.cand_rows + (size_t)cnews[c] * LIME_CAND_LD;
                     const float tabv = C.cand_tab[(size_t)ctab[c] * LIME_CTAB_LD + LIME_CAND_SCAL + lane];
                     cscal[c * 8 + lane] = crow[LIME_CAND_SCAL + lane] + tabv;
                 }
-                __syncwarp();
+                const float *trow = C.topic_table + (size_t)ctopic[c] * T * kTabLd;
                 float sc[2][LIME_CA_HEADS];
+                {
+                    const float *r0 = trow + (size_t)t0 * kTabLd, *r1 = trow + (size_t)t1 * kTabLd;
+                    const float4 a0 = ldg4(r0), a1 = ldg4(r0 + 4), a2 = ldg4(r0 + 8);
+                    const float4 b0 = ldg4(r1), b1 = ldg4(r1 + 4), b2 = ldg4(r1 + 8);
+                    const float x0[LIME_CA_HEADS] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
+                    const float x1[LIME_CA_HEADS] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
 #pragma unroll
-                for (int p = 0; p < 2; ++p) {
-                    const int hh = lane + 32 * p;
-                    const bool valid = (p < passes) && hh < H;
-                    const float *trow = t_s + (valid ? hh : 0) * kTStride;
-                    float acc[LIME_CA_HEADS];
-#pragma unroll
-                    for (int hd = 0; hd < LIME_CA_HEADS; ++hd) acc[hd] = tq[LIME_TOPIC * kTqStride + hd];
-                    if (p < passes) {
-#pragma unroll 5
-                        for (int k = 0; k < LIME_TOPIC; ++k) {
-                            const float tv = trow[k];
-                            const float4 q0 = *reinterpret_cast<const float4 *>(tq + k * kTqStride);
-                            const float4 q1 = *reinterpret_cast<const float4 *>(tq + k * kTqStride + 4);
-                            const float2 q2 = *reinterpret_cast<const float2 *>(tq + k * kTqStride + 8);
-                            acc[0] = fmaf(q0.x, tv, acc[0]);
-                            acc[1] = fmaf(q0.y, tv, acc[1]);
-                            acc[2] = fmaf(q0.z, tv, acc[2]);
-                            acc[3] = fmaf(q0.w, tv, acc[3]);
-                            acc[4] = fmaf(q1.x, tv, acc[4]);
-                            acc[5] = fmaf(q1.y, tv, acc[5]);
-                            acc[6] = fmaf(q1.z, tv, acc[6]);
-                            acc[7] = fmaf(q1.w, tv, acc[7]);
-                            acc[8] = fmaf(q2.x, tv, acc[8]);
-                            acc[9] = fmaf(q2.y, tv, acc[9]);
-                        }
+                    for (int hd = 0; hd < LIME_CA_HEADS; ++hd) {   // masked_fill(mask == 0, -1e9), layers.py:72
+                        sc[0][hd] = v0 ? (k0 ? x0[hd] : -1e9f) : -INFINITY;
+                        sc[1][hd] = v1 ? (k1 ? x1[hd] : -1e9f) : -INFINITY;
                     }
-                    const bool keep = valid && (hmask[valid ? hh : 0] != 0);
-#pragma unroll
-                    for (int hd = 0; hd < LIME_CA_HEADS; ++hd)
-                        sc[p][hd] = valid ? (keep ? acc[hd] : -1e9f) : -INFINITY;   // masked_fill(mask==0,-1e9)
                 }
                 float agg[2] = {0.0f, 0.0f};
 #pragma unroll
                 for (int hd = 0; hd < LIME_CA_HEADS; ++hd) {
-                    float m = warp_max(fmaxf(sc[0][hd], sc[1][hd]));
+                    const float m = warp_max(fmaxf(sc[0][hd], sc[1][hd]));
                     const float e0 = __expf(sc[0][hd] - m), e1 = __expf(sc[1][hd] - m);
                     const float inv = __fdividef(1.0f, warp_sum(e0 + e1));
                     agg[0] = fmaf(e0, inv, agg[0]);
                     agg[1] = fmaf(e1, inv, agg[1]);
                 }
                 // second, unmasked softmax over the history (layers.py:81)
-                const bool v0 = lane < H, v1 = lane + 32 < H;
                 const float m2 = warp_max(fmaxf(v0 ? agg[0] : -INFINITY, v1 ? agg[1] : -INFINITY));
                 agg[0] = v0 ? __expf(agg[0] - m2) : 0.0f;
                 agg[1] = v1 ? __expf(agg[1] - m2) : 0.0f;
                 const float inv2 = __fdividef(1.0f, warp_sum(agg[0] + agg[1]));
                 if (v0) a_s[c * kRows + lane] = agg[0] * inv2;
                 if (v1) a_s[c * kRows + lane + 32] = agg[1] * inv2;
-                __syncwarp();
             }
         }
         __syncthreads();
@@ -283,27 +270,27 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const ScoreArgs a
             whalf_s[tid] = wh;
             winv_s[tid] = 1.0f / wh;
         }
-        __syncthreads();   // also: every phase-1 read of the aliased t_s / tq_s is done
+        __syncthreads();
 
         const int n_cols = (3 * cnt + 15) & ~15;
         const int mtiles = (4 * H + 127) >> 7;
 
         if (warp < kWarps) {
-            // ---------------- operand production: 7 K chunks through the 2-stage ring ------------
-            const int hr = 4 * warp + (lane >> 3), q = lane & 7;
+            // ---------------- operand production: 13 K chunks of 32 dims --------------------------
+            const int hr = tid >> 2, q = tid & 3;
             const bool row_ok = hr < H;
             const float mid = row_ok ? mid_s[hr] : 0.0f, wh = row_ok ? whalf_s[hr] : 0.0f;
             const float aj[4] = {fmaf(wh, kX0, mid), fmaf(wh, kX1, mid), fmaf(wh, kX2, mid), fmaf(wh, kX3, mid)};
             const float *hrow = C.hist_rows + (size_t)(row_ok ? hnews[hr] : 0) * LIME_HIST_LD;
             const float *trow = C.hist_tab + (size_t)(row_ok ? htab[hr] : 0) * LIME_HTAB_LD;
-            const int bt = (warp & 3) ? ((warp - 1 - (warp >> 2)) * 32 + lane) : -1;
             float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             float gmx = 0.0f, xmax = 0.0f;
-            for (int kc = 0; kc < kChunks; ++kc, ++g) {
-                const uint32_t s = g & 1u, u = g >> 1;
+            for (int kc = 0; kc < kChunks; ++kc) {
+                const int s = kc & 1;
+                const uint32_t u = use[s]++;
                 if (u >= 1) tc::mbar_wait(bar_free + s, (u - 1) & 1u);
-                unsigned char *st = base + OFF_STAGE + s * kStage;
-                const int d0 = 64 * kc + 8 * q;
+                const int d0 = 32 * kc + 8 * q;
+                const int lq = 4 * s + q;                  // 16-byte chunk inside the 128-byte tile row
                 if (row_ok && d0 < kD) {
                     float v[8], gg[8];
                     {
@@ -335,39 +322,38 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const ScoreArgs a
                         }
                         uint4 hi, lo;
                         xmax = fmaxf(xmax, split8(o, hi, lo));
-                        const uint32_t off = tc::sw128_offset(4 * hr + j, q);
-                        *reinterpret_cast<uint4 *>(st + off) = hi;
-                        *reinterpret_cast<uint4 *>(st + kABytes + off) = lo;
+                        const uint32_t off = tc::sw128_offset(4 * hr + j, lq);
+                        *reinterpret_cast<uint4 *>(base + OFF_AHI + off) = hi;
+                        *reinterpret_cast<uint4 *>(base + OFF_ALO + off) = lo;
                     }
                 }
-                if (bt >= 0) {
-                    for (int task = bt; task < 3 * cnt * 8; task += kBThreads) {
-                        const int n = task >> 3, qq = task & 7;
-                        const int d1 = 64 * kc + 8 * qq;
-                        if (d1 >= kD) continue;
-                        const int c = n / 3, k = n - 3 * c;
-                        const float *cr = C.cand_rows + (size_t)cnews[c] * LIME_CAND_LD + k * kD + d1;
-                        const float *ct = C.cand_tab + (size_t)ctab[c] * LIME_CTAB_LD + k * kD + d1;
-                        const float4 a0 = ldg4(cr), a1 = ldg4(cr + 4), b0 = ldg4(ct), b1 = ldg4(ct + 4);
-                        const float x[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w,
-                                            a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
-                        uint4 hi, lo;
-                        xmax = fmaxf(xmax, split8(x, hi, lo));
-                        const uint32_t off = tc::sw128_offset(n, qq);
-                        *reinterpret_cast<uint4 *>(st + 2 * kABytes + off) = hi;
-                        *reinterpret_cast<uint4 *>(st + 2 * kABytes + kBBytes + off) = lo;
-                    }
+                for (int task = tid; task < 3 * cnt * 4; task += kCompute) {
+                    const int n = task >> 2, qq = task & 3;
+                    const int d1 = 32 * kc + 8 * qq;
+                    if (d1 >= kD) continue;
+                    const int c = n / 3, k = n - 3 * c;
+                    const float *cr = C.cand_rows + (size_t)cnews[c] * LIME_CAND_LD + k * kD + d1;
+                    const float *ct = C.cand_tab + (size_t)ctab[c] * LIME_CTAB_LD + k * kD + d1;
+                    const float4 a0 = ldg4(cr), a1 = ldg4(cr + 4), b0 = ldg4(ct), b1 = ldg4(ct + 4);
+                    const float x[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w,
+                                        a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
+                    uint4 hi, lo;
+                    xmax = fmaxf(xmax, split8(x, hi, lo));
+                    const uint32_t off = tc::sw128_offset(n, 4 * s + qq);
+                    *reinterpret_cast<uint4 *>(base + OFF_BHI + off) = hi;
+                    *reinterpret_cast<uint4 *>(base + OFF_BLO + off) = lo;
                 }
                 tc::fence_proxy_async_smem();
                 tc::mbar_arrive(bar_full + s);
             }
-            // node sums of the row: sum o, sum o^2 per node, over the 8 lanes that share the row
+            // node sums of the row: sum o, sum o^2 per node, over the 4 lanes that share the row
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
+            for (int o = 1; o < 4; o <<= 1) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) ps[i] += __shfl_xor_sync(0xffffffffu, ps[i], o);
                 gmx = fmaxf(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
             }
+            if (!(xmax <= kHalfSafe)) flag_s[0] = 1;   // outside the fp16 operand range (or NaN): exact kernel
             if (row_ok && q == 0) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) s01_s[hr * 8 + i] = ps[i];
@@ -376,21 +362,21 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const ScoreArgs a
         } else {
             // ---------------- MMA issuer ---------------------------------------------------------
             const uint32_t idesc = tc::idesc_f16_f32(128, n_cols);
-            for (int kc = 0; kc < kChunks; ++kc, ++g) {
-                const uint32_t s = g & 1u, u = g >> 1;
+            const uint32_t sb = tc::smem_u32(base);
+            for (int kc = 0; kc < kChunks; ++kc) {
+                const int s = kc & 1;
+                const uint32_t u = use[s]++;
                 tc::mbar_wait(bar_full + s, u & 1u);
                 tc::fence_after_sync();
                 if (lane == 0) {
-                    const uint32_t sb = tc::smem_u32(base + OFF_STAGE + s * kStage);
-                    const int ksteps = kc < kChunks - 1 ? 4 : (kD - 64 * (kChunks - 1)) / 16;
+                    const int ksteps = kc < kChunks - 1 ? 2 : (kD - 32 * (kChunks - 1)) / 16;
+                    const uint64_t bhi = tc::smem_desc_sw128(sb + OFF_BHI), blo = tc::smem_desc_sw128(sb + OFF_BLO);
                     for (int mt = 0; mt < mtiles; ++mt) {
-                        const uint64_t ahi = tc::smem_desc_sw128(sb + mt * 16384);
-                        const uint64_t alo = tc::smem_desc_sw128(sb + kABytes + mt * 16384);
-                        const uint64_t bhi = tc::smem_desc_sw128(sb + 2 * kABytes);
-                        const uint64_t blo = tc::smem_desc_sw128(sb + 2 * kABytes + kBBytes);
+                        const uint64_t ahi = tc::smem_desc_sw128(sb + OFF_AHI + mt * 16384);
+                        const uint64_t alo = tc::smem_desc_sw128(sb + OFF_ALO + mt * 16384);
                         const uint32_t td = tmem + (uint32_t)(mt * 128);
                         for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t k2 = (uint64_t)(2 * ks);
+                            const uint64_t k2 = (uint64_t)(2 * (2 * s + ks));   // 32 bytes per K step of 16
                             tc::mma_f16(td, ahi + k2, bhi + k2, idesc, (kc | ks) != 0);
                             tc::mma_f16(td, ahi + k2, blo + k2, idesc, true);
                             tc::mma_f16(td, alo + k2, bhi + k2, idesc, true);
@@ -415,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const ScoreArgs a
             // ---------------- epilogue: TMEM -> Lagrange combination -> LayerNorm folding ---------
             tc::mbar_wait(bar_accum, unit_iter & 1u);
             tc::fence_after_sync();
-            const int qd = warp & 3, mt = (warp >> 2) & 1, cpar = warp >> 3;
+            const int qd = warp & 3, mt = warp >> 2;
             if (mt < mtiles) {
                 const int r = 128 * mt + 32 * qd + lane;
                 const int hr = r >> 2, j = r & 3;
@@ -428,15 +414,15 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const ScoreArgs a
                 const float xa = j == 0 ? kX1 : kX0, xb = j <= 1 ? kX2 : kX1, xc = j == 3 ? kX2 : kX3;
                 const float invden = 1.0f / ((xj - xa) * (xj - xb) * (xj - xc));
                 const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(128 * mt);
-                for (int cg = cpar; 16 * cg < cnt; cg += 2) {
+                for (int cg = 0; 16 * cg < cnt; ++cg) {
                     float v[48];
                     tc::tmem_ld16(taddr + 48 * cg, *reinterpret_cast<float(*)[16]>(&v[0]));
-                    tc::tmem_ld16(taddr + 48 * cg + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
                     if (cg < 2) {
+                        tc::tmem_ld16(taddr + 48 * cg + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
                         tc::tmem_ld16(taddr + 48 * cg + 32, *reinterpret_cast<float(*)[16]>(&v[32]));
-                    } else {
+                    } else {        // candidates 32..36 live in columns 96..110 of the 112-column tile
 #pragma unroll
-                        for (int i = 32; i < 48; ++i) v[i] = 0.0f;
+                        for (int i = 16; i < 48; ++i) v[i] = 0.0f;
                     }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -515,6 +501,31 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const ScoreArgs a
     if (warp == kWarps) tc::tmem_dealloc(tmem, 256);
 }
 
+// out[(tc * T + th) * 12 + head] = sum_k tq[tc][k * 10 + head] * topics[th][k] + tq[tc][500 + head]
+// (same accumulation order as phase 1 of the exact kernel, so both kernels see identical logits)
+__global__ void topic_pair_table_kernel(const float *__restrict__ topics, int64_t ldt, const float *__restrict__ tq,
+                                        int64_t ldq, int T, float *__restrict__ out) {
+    __shared__ float q_s[LIME_TOPIC * LIME_CA_HEADS + LIME_CA_HEADS];
+    const int tcand = blockIdx.x;
+    for (int i = threadIdx.x; i < LIME_TOPIC * LIME_CA_HEADS + LIME_CA_HEADS; i += blockDim.x) q_s[i] = tq[(size_t)tcand * ldq + i];
+    __syncthreads();
+    for (int th = threadIdx.x; th < T; th += blockDim.x) {
+        float acc[LIME_CA_HEADS];
+#pragma unroll
+        for (int hd = 0; hd < LIME_CA_HEADS; ++hd) acc[hd] = q_s[LIME_TOPIC * LIME_CA_HEADS + hd];
+        for (int k = 0; k < LIME_TOPIC; ++k) {
+            const float tv = topics[(size_t)th * ldt + k];
+#pragma unroll
+            for (int hd = 0; hd < LIME_CA_HEADS; ++hd) acc[hd] = fmaf(q_s[k * LIME_CA_HEADS + hd], tv, acc[hd]);
+        }
+        float *o = out + ((size_t)tcand * T + th) * kTabLd;
+#pragma unroll
+        for (int hd = 0; hd < LIME_CA_HEADS; ++hd) o[hd] = acc[hd];
+        o[10] = 0.0f;
+        o[11] = 0.0f;
+    }
+}
+
 }  // namespace
 
 int launch_score_tc(const ScoreArgs &a, cudaStream_t st) {
@@ -524,7 +535,7 @@ int launch_score_tc(const ScoreArgs &a, cudaStream_t st) {
         attr_set = true;
     }
     LIME_CUDA(cudaMemsetAsync(a.work_counter, 0, 2 * sizeof(int32_t), st));   // work counter + fallback count
-    int grid = num_sms();
+    int grid = 2 * num_sms();
     if (grid > a.imp.num_units) grid = a.imp.num_units;
     score_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
     LIME_LAUNCH_CHECK("score_tc_kernel");
@@ -532,3 +543,12 @@ int launch_score_tc(const ScoreArgs &a, cudaStream_t st) {
 }
 
 }  // namespace lime
+
+extern "C" int lime_topic_pair_table(const float *topics, int64_t ldt, const float *tq, int64_t ldq, int32_t T,
+                                     float *out, void *stream) {
+    LIME_CHECK_ARG(topics && tq && out, "lime_topic_pair_table: null argument");
+    LIME_CHECK_ARG(T >= 1 && T <= LIME_TC_MAX_TOPICS, "lime_topic_pair_table: T=%d not in [1, %d]", T, LIME_TC_MAX_TOPICS);
+    lime::topic_pair_table_kernel<<<T, 128, 0, lime::as_stream(stream)>>>(topics, ldt, tq, ldq, T, out);
+    LIME_LAUNCH_CHECK("topic_pair_table_kernel");
+    return 0;
+}

@@ -27,8 +27,9 @@ from ._lib import LimeImpressions, LimeNewsCache, check
 
 D = 400
 HIST_LD, CAND_LD, HTAB_LD, CTAB_LD = 852, 1720, 800, 1208
-HIST_GW, HIST_T = 400, 800
-CAND_SCAL, CAND_TQ, CAND_NFOLD = 1200, 1208, 1207
+HIST_GW, HIST_T, HIST_TOPIC_ID = 400, 800, 850
+CAND_SCAL, CAND_TQ, CAND_NFOLD, CAND_TOPIC_ID = 1200, 1208, 1207, 1718
+TOPIC_TAB_LD, MAX_TOPICS = 12, 1024
 TOPIC, TOPIC_LD, HEADS = 50, 52, 10
 LOG2E = 1.4426950408889634
 
@@ -172,15 +173,59 @@ class ScoringEngine:
         self.news = model.news_encoder.engine
         self._fold = None
         self._fp = None
+        self._reset_topics()
 
     def _params(self):
         return [p for p in self.model.parameters()] + [b for b in self.model.buffers()]
+
+    # -- topic registry: compact ids of the (category, subCategory) pairs seen so far + logit table ----
+    def _reset_topics(self):
+        self._topic_ids = {}          # (category, subCategory) key -> compact id
+        self._topic_vec = []          # [52] topic representation per id (device)
+        self._topic_tq = []           # [510] candidate-role affine image per id (device)
+        self._topic_table = None      # [T, T, 12] head logits, rebuilt when the registry grows
+        self._topic_table_n = 0
+
+    def _register_topics(self, category, subCategory, hist, cand):
+        """Assign compact topic ids to the news of freshly built cache rows and stamp them into the
+        rows (index building: torch plumbing; the logit table itself comes from lime_topic_pair_table)."""
+        key = category.long() * 1000003 + subCategory.long()
+        uniq, inverse = torch.unique(key, return_inverse=True)
+        first = torch.full((uniq.numel(),), key.numel(), dtype=torch.long, device=key.device)
+        first.scatter_reduce_(0, inverse, torch.arange(key.numel(), device=key.device), reduce="amin")
+        lut = []
+        for k, r in zip(uniq.tolist(), first.tolist()):
+            if k not in self._topic_ids:
+                self._topic_ids[k] = len(self._topic_ids)
+                self._topic_vec.append(hist[r, HIST_T:HIST_T + TOPIC_LD].clone())
+                self._topic_tq.append(cand[r, CAND_TQ:CAND_TQ + TOPIC * HEADS + HEADS].clone())
+            lut.append(self._topic_ids[k])
+        ids = torch.tensor(lut, dtype=torch.int32, device=key.device)[inverse]
+        hist[:, HIST_TOPIC_ID].view(torch.int32).copy_(ids)
+        cand[:, CAND_TOPIC_ID].view(torch.int32).copy_(ids)
+
+    def topic_table(self):
+        """(table [T,T,12] or None, T).  None when more than MAX_TOPICS topics are registered: the
+        tensor-core scoring path is then unavailable and lime_score_impressions runs the exact kernel."""
+        T = len(self._topic_ids)
+        if T == 0 or T > MAX_TOPICS:
+            return None, 0
+        if self._topic_table is None or self._topic_table_n != T:
+            lib = _lib.require_device()
+            tv, tq = torch.stack(self._topic_vec).contiguous(), torch.stack(self._topic_tq).contiguous()
+            tab = torch.empty(T, T, TOPIC_TAB_LD, dtype=torch.float32, device=tv.device)
+            check(lib.lime_topic_pair_table(tv.data_ptr(), tv.stride(0), tq.data_ptr(), tq.stride(0), T,
+                                            tab.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                  "lime_topic_pair_table")
+            self._topic_table, self._topic_table_n = tab, T
+        return self._topic_table, T
 
     # -- fold the user-encoder weights (once per checkpoint) ---------------------------------------
     def fold(self):
         fp = _fingerprint(self._params())
         if self._fold is not None and fp == self._fp:
             return self._fold
+        self._reset_topics()          # cached topic vectors belong to the previous weights
         ue = self.model.user_encoder
         ca = ue.candidate_aware_attn
         sage = ue.graph_sage.convs[0]
@@ -287,15 +332,18 @@ class ScoringEngine:
             ops.linear(h[:, :D], F["G"], out=c[:, :CAND_NFOLD], n=CAND_NFOLD)       # w1 w2 w3 + scalars
             ops.linear(h[:, HIST_T:HIST_T + TOPIC_LD], F["Atq"], F["atq0"],
                        out=c[:, CAND_TQ:CAND_TQ + TOPIC * HEADS + HEADS])           # tq, qb
+        self._register_topics(category, subCategory, hist, cand)
         return hist, cand
 
     def cache_struct(self, hist_rows, cand_rows):
         F = self.fold()
         cfg = self.cfg
+        table, T = self.topic_table()
         return LimeNewsCache(
             hist_rows=hist_rows.data_ptr(), cand_rows=cand_rows.data_ptr(),
             hist_tab=F["hist_tab"].data_ptr(), cand_tab=F["cand_tab"].data_ptr(),
             gate_bias=F["gate_bias"].data_ptr(), un_prefix=F["un_prefix"].data_ptr(),
+            topic_table=table.data_ptr() if table is not None else None, num_topics=T,
             news_num=hist_rows.shape[0], num_buckets=cfg.num_buckets,
             user_nodes=F["un_prefix"].shape[0], sigmoid_alpha=float(cfg.sigmoid_scaling_alpha),
             penalty_beta=float(cfg.penalty_scaling_beta),
