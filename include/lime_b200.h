@@ -41,6 +41,7 @@ extern "C" {
 #define LIME_HIST_VC   0
 #define LIME_HIST_GW   400
 #define LIME_HIST_T    800
+#define LIME_HIST_GW_ABSMAX 851 /* max_d |gw[d]| of the row (bounds the gate interpolation error)     */
 #define LIME_HIST_TOPIC_ID 850 /* int32 bit pattern: compact id of the news' (category, subCategory) pair */
 #define LIME_CAND_LD   1720 /* [ w1 | w2 | w3 | scal(8) | tq 50x10 | qb 10 | pad 2 ]           */
 #define LIME_CAND_W    0
@@ -122,6 +123,8 @@ int lime_bucket_pairs(const float *Ef, const float *El, int num_buckets, int dim
                       void *stream);
 
 /* small helpers used while folding weights */
+/* out[i * ldo] = max_j |M[i * ld + j]|,  j < cols */
+int lime_row_absmax(const float *M, int64_t ld, int64_t rows, int cols, float *out, int64_t ldo, void *stream);
 int lime_scale_rows(float *M, int64_t ld, const float *row_scale, float alpha, int rows, int cols,
                     void *stream);                         /* M[i,:] *= alpha * row_scale[i] (NULL -> 1) */
 int lime_prefix_rows(float *M, int64_t ld, int rows, int cols, void *stream); /* inclusive prefix sum over rows */
@@ -150,6 +153,7 @@ typedef struct {
     int32_t num_buckets;
     int32_t user_nodes;         /* config.batch_size (rows of user_node_embedding)               */
     int32_t num_topics;         /* distinct (category, subCategory) pairs registered in the cache */
+    float   tab_gw_absmax;      /* max |gw| over hist_tab (same purpose as LIME_HIST_GW_ABSMAX)   */
     float   sigmoid_alpha;      /* config.sigmoid_scaling_alpha                                  */
     float   penalty_beta;       /* config.penalty_scaling_beta                                   */
     int32_t use_lifetime_weighting; /* config.use_remaining_lifetime_weighting                   */

@@ -21,7 +21,7 @@ class LimeNewsCache(C.Structure):
         ("cand_tab", C.c_void_p), ("gate_bias", C.c_void_p), ("un_prefix", C.c_void_p),
         ("topic_table", C.c_void_p),
         ("news_num", C.c_int32), ("num_buckets", C.c_int32), ("user_nodes", C.c_int32), ("num_topics", C.c_int32),
-        ("sigmoid_alpha", C.c_float), ("penalty_beta", C.c_float),
+        ("tab_gw_absmax", C.c_float), ("sigmoid_alpha", C.c_float), ("penalty_beta", C.c_float),
         ("use_lifetime_weighting", C.c_int32), ("use_expired_penalty", C.c_int32),
     ]
 
@@ -59,6 +59,7 @@ PROTOTYPES = {
     "lime_bucket_pairs": (C.c_int, [P, P, C.c_int, C.c_int, P, P]),
     "lime_scale_rows": (C.c_int, [P, I64, P, F32, C.c_int, C.c_int, P]),
     "lime_prefix_rows": (C.c_int, [P, I64, C.c_int, C.c_int, P]),
+    "lime_row_absmax": (C.c_int, [P, I64, I64, C.c_int, P, I64, P]),
     "lime_score_impressions": (C.c_int, [C.POINTER(LimeNewsCache), C.POINTER(LimeImpressions), I64, I32,
                                          I64, I32, P, P, P]),
     "lime_score_smem_bytes": (I64, [I32, I32]),

@@ -299,6 +299,17 @@ __global__ void scale_rows_kernel(float *M, int64_t ld, const float *__restrict_
     for (int c = threadIdx.x; c < cols; c += blockDim.x) M[(int64_t)r * ld + c] *= s;
 }
 
+// one warp per row: out[row] = max |M[row][:]|
+__global__ void row_absmax_kernel(const float *__restrict__ M, int64_t ld, int64_t rows, int cols, float *__restrict__ out,
+                                  int64_t ldo) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float m = 0.0f;
+    for (int j = threadIdx.x & 31; j < cols; j += 32) m = fmaxf(m, fabsf(M[row * ld + j]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) out[row * ldo] = m;
+}
+
 __global__ void prefix_rows_kernel(float *M, int64_t ld, int rows, int cols) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
@@ -424,5 +435,13 @@ extern "C" int lime_prefix_rows(float *M, int64_t ld, int rows, int cols, void *
     LIME_CHECK_ARG(M && rows > 0 && cols > 0, "lime_prefix_rows: bad argument");
     prefix_rows_kernel<<<(cols + 127) / 128, 128, 0, as_stream(stream)>>>(M, ld, rows, cols);
     LIME_LAUNCH_CHECK("prefix_rows_kernel");
+    return 0;
+}
+
+extern "C" int lime_row_absmax(const float *M, int64_t ld, int64_t rows, int cols, float *out, int64_t ldo, void *stream) {
+    LIME_CHECK_ARG(M && out && cols > 0, "lime_row_absmax: bad argument");
+    if (rows <= 0) return 0;
+    row_absmax_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, as_stream(stream)>>>(M, ld, rows, cols, out, ldo);
+    LIME_LAUNCH_CHECK("row_absmax_kernel");
     return 0;
 }

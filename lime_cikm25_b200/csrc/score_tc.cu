@@ -80,11 +80,18 @@ constexpr int OFF_MISC = OFF_BARS + 64;                       // tmem slot, unit
 constexpr int kSmemBytes = OFF_MISC + 64 + 1024;
 static_assert(OFF_Z + kTile * kRows * 4 <= 2 * kABytes, "epilogue alias overflows the O operand images");
 static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
+static_assert(3 * kTile * 4 <= 2 * kCompute, "candidate operand: at most 2 staging tasks per compute thread");
 static_assert(OFF_BARS % 8 == 0 && OFF_A % 16 == 0 && OFF_BIAS % 16 == 0 && OFF_BLO % 1024 == 0, "alignment");
 
-// 4 Chebyshev nodes on [-1, 1]
+// Chebyshev nodes on [-1, 1]: 4-node and 2-node sets
 constexpr float kX0 = -0.92387953251128674f, kX1 = -0.38268343236508977f;
 constexpr float kX2 = 0.38268343236508977f, kX3 = 0.92387953251128674f;
+constexpr float kY0 = -0.70710678118654752f, kY1 = 0.70710678118654752f;
+
+template <int NODES> __device__ __forceinline__ float node_x(int j) {
+    if (NODES == 2) return j == 0 ? kY0 : kY1;
+    return j == 0 ? kX0 : j == 1 ? kX1 : j == 2 ? kX2 : kX3;
+}
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -108,6 +115,171 @@ __device__ __forceinline__ float split8(const float (&x)[8], uint4 &hi, uint4 &l
     return mx;
 }
 
+// Operand production for one work unit: NODES rows of O per history row (fp16 hi / lo images, K chunks of
+// 32 dims through the two halves of the 64-dim tile) and the folded vectors of the candidates; also the node
+// sums (sum o, sum o^2).  Executed by the 256 compute threads; use[] are the per-half staging counters, which
+// every thread of the CTA advances identically.
+template <int NODES>
+__device__ __forceinline__ void produce_operands(unsigned char *base, const LimeNewsCache &C, int H, int cnt, int tid,
+                                                 const int *hnews, const int *htab, const int *cnews, const int *ctab,
+                                                 const float *mid_s, const float *whalf_s, const float *bias_s,
+                                                 float *s01_s, int *flag_s, uint64_t *bar_full, uint64_t *bar_free,
+                                                 uint32_t (&use)[2]) {
+    const int hr = tid >> 2, q = tid & 3;
+    const bool row_ok = hr < H;
+    const float mid = row_ok ? mid_s[hr] : 0.0f, wh = row_ok ? whalf_s[hr] : 0.0f;
+    float aj[NODES];
+#pragma unroll
+    for (int j = 0; j < NODES; ++j) aj[j] = fmaf(wh, node_x<NODES>(j), mid);
+    const float *hrow = C.hist_rows + (size_t)(row_ok ? hnews[hr] : 0) * LIME_HIST_LD;
+    const float *trow = C.hist_tab + (size_t)(row_ok ? htab[hr] : 0) * LIME_HTAB_LD;
+    float ps[2 * NODES];
+#pragma unroll
+    for (int i = 0; i < 2 * NODES; ++i) ps[i] = 0.0f;
+    float xmax = 0.0f;
+    const int btasks = 3 * cnt * 4;
+    for (int kc = 0; kc < kChunks; ++kc) {
+        const int s = kc & 1;
+        const uint32_t u = use[s]++;
+        if (u >= 1) tc::mbar_wait(bar_free + s, (u - 1) & 1u);
+        const int d0 = 32 * kc + 8 * q;
+        const int lq = 4 * s + q;                  // 16-byte chunk inside the 128-byte tile row
+        if (row_ok && d0 < kD) {
+            float v[8], gg[8];
+            {
+                const float4 a0 = ldg4(hrow + LIME_HIST_VC + d0), a1 = ldg4(hrow + LIME_HIST_VC + d0 + 4);
+                const float4 b0 = ldg4(trow + d0), b1 = ldg4(trow + d0 + 4);
+                const float4 c0 = ldg4(hrow + LIME_HIST_GW + d0), c1 = ldg4(hrow + LIME_HIST_GW + d0 + 4);
+                const float4 e0 = ldg4(trow + kD + d0), e1 = ldg4(trow + kD + d0 + 4);
+                v[0] = a0.x + b0.x; v[1] = a0.y + b0.y; v[2] = a0.z + b0.z; v[3] = a0.w + b0.w;
+                v[4] = a1.x + b1.x; v[5] = a1.y + b1.y; v[6] = a1.z + b1.z; v[7] = a1.w + b1.w;
+                gg[0] = c0.x + e0.x; gg[1] = c0.y + e0.y; gg[2] = c0.z + e0.z; gg[3] = c0.w + e0.w;
+                gg[4] = c1.x + e1.x; gg[5] = c1.y + e1.y; gg[6] = c1.z + e1.z; gg[7] = c1.w + e1.w;
+            }
+            const float4 bb0 = *reinterpret_cast<const float4 *>(bias_s + d0);
+            const float4 bb1 = *reinterpret_cast<const float4 *>(bias_s + d0 + 4);
+            const float bb[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xmax = fmaxf(xmax, fabsf(v[e]));   // |o| <= |v|: one range check per element
+#pragma unroll
+            for (int j = 0; j < NODES; ++j) {
+                // o = v (1 - (1 - a_j) sigmoid(a_j W_g v + b_g)),  sigmoid(z) = 1 / (1 + 2^z'),  z' = -log2(e) z
+                const float a = aj[j], oma = 1.0f - a;
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float den = ex2_approx(fmaf(a, gg[e], bb[e])) + 1.0f;
+                    o[e] = fmaf(-(v[e] * oma), rcp_approx(den), v[e]);
+                    ps[2 * j] += o[e];
+                    ps[2 * j + 1] = fmaf(o[e], o[e], ps[2 * j + 1]);
+                }
+                uint4 hi, lo;
+                split8(o, hi, lo);
+                const uint32_t off = tc::sw128_offset(NODES * hr + j, lq);
+                *reinterpret_cast<uint4 *>(base + OFF_AHI + off) = hi;
+                *reinterpret_cast<uint4 *>(base + OFF_ALO + off) = lo;
+            }
+        }
+        for (int task = tid; task < btasks; task += kCompute) {
+            const int n = task >> 2, qq = task & 3;
+            const int d1 = 32 * kc + 8 * qq;
+            if (d1 >= kD) continue;
+            const int c = n / 3, k = n - 3 * c;
+            const float *cr = C.cand_rows + (size_t)cnews[c] * LIME_CAND_LD + k * kD + d1;
+            const float *ct = C.cand_tab + (size_t)ctab[c] * LIME_CTAB_LD + k * kD + d1;
+            const float4 a0 = ldg4(cr), a1 = ldg4(cr + 4), b0 = ldg4(ct), b1 = ldg4(ct + 4);
+            const float x[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w,
+                                a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
+            uint4 hi, lo;
+            xmax = fmaxf(xmax, split8(x, hi, lo));
+            const uint32_t off = tc::sw128_offset(n, 4 * s + qq);
+            *reinterpret_cast<uint4 *>(base + OFF_BHI + off) = hi;
+            *reinterpret_cast<uint4 *>(base + OFF_BLO + off) = lo;
+        }
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(bar_full + s);
+    }
+    // node sums of the row: sum o, sum o^2 per node, over the 4 lanes that share the row
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 2 * NODES; ++i) ps[i] += __shfl_xor_sync(0xffffffffu, ps[i], o);
+    }
+    if (!(xmax <= kHalfSafe)) atomicOr(flag_s, 4);   // outside the fp16 operand range (or NaN): exact kernel
+    if (row_ok && q == 0) {
+#pragma unroll
+        for (int i = 0; i < 2 * NODES; ++i) s01_s[hr * 8 + i] = ps[i];
+    }
+}
+
+// Epilogue of one work unit: every compute thread owns one accumulator row (TMEM lane) = one (history row,
+// node); the NODES lanes of a row combine their dots with the Lagrange weights of each candidate, lane j = 0
+// folds the LayerNorm and writes lg / y / z.
+template <int NODES>
+__device__ __forceinline__ void epilogue(uint32_t tmem, int warp, int lane, int H, int cnt, int mtiles, float ln_eps,
+                                         const float *a_s, const float *mid_s, const float *winv_s, const float *s01_s,
+                                         const float *cscal, float *lg_s, float *y_s, float *z_s) {
+    const int qd = warp & 3, mt = warp >> 2;
+    if (mt < mtiles) {
+        const int r = 128 * mt + 32 * qd + lane;
+        const int hr = r / NODES, j = r % NODES;
+        const bool row_ok = hr < H;
+        const int hc = row_ok ? hr : 0;
+        const float mid = mid_s[hc], winv = winv_s[hc];
+        const float s0n = row_ok ? s01_s[hc * 8 + 2 * j] : 0.0f, s1n = row_ok ? s01_s[hc * 8 + 2 * j + 1] : 0.0f;
+        // L_j(t) = prod_{m != j} (t - x_m) / (x_j - x_m); with 2 nodes there is a single factor
+        float xa, xb = 0.0f, xc = 0.0f, invden;
+        if (NODES == 2) {
+            xa = j == 0 ? kY1 : kY0;
+            invden = 1.0f / ((j == 0 ? kY0 : kY1) - xa);
+        } else {
+            const float xj = j == 0 ? kX0 : j == 1 ? kX1 : j == 2 ? kX2 : kX3;
+            xa = j == 0 ? kX1 : kX0, xb = j <= 1 ? kX2 : kX1, xc = j == 3 ? kX2 : kX3;
+            invden = 1.0f / ((xj - xa) * (xj - xb) * (xj - xc));
+        }
+        const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(128 * mt);
+        for (int cg = 0; 16 * cg < cnt; ++cg) {
+            float v[48];
+            tc::tmem_ld16(taddr + 48 * cg, *reinterpret_cast<float(*)[16]>(&v[0]));
+            if (cg < 2) {
+                tc::tmem_ld16(taddr + 48 * cg + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+                tc::tmem_ld16(taddr + 48 * cg + 32, *reinterpret_cast<float(*)[16]>(&v[32]));
+            } else {        // candidates 32..36 live in columns 96..110 of the 112-column tile
+#pragma unroll
+                for (int i = 16; i < 48; ++i) v[i] = 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int c = 16 * cg + i;
+                if (c < cnt) {
+                    float t = (a_s[c * kRows + hc] - mid) * winv;
+                    t = fminf(fmaxf(t, -1.0f), 1.0f);
+                    const float L = NODES == 2 ? (t - xa) * invden : (t - xa) * (t - xb) * (t - xc) * invden;
+                    float p0 = L * v[3 * i], p1 = L * v[3 * i + 1], p2 = L * v[3 * i + 2];
+                    float p3 = L * s0n, p4 = L * s1n;
+#pragma unroll
+                    for (int o = 1; o < NODES; o <<= 1) {
+                        p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+                        p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+                        p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+                        p3 += __shfl_xor_sync(0xffffffffu, p3, o);
+                        p4 += __shfl_xor_sync(0xffffffffu, p4, o);
+                    }
+                    if (j == 0 && row_ok) {
+                        const float *cs = cscal + c * 8;
+                        const float mu = p3 * (1.0f / kD);
+                        const float var = fmaxf(fmaf(-mu, mu, p4 * (1.0f / kD)), 0.0f);
+                        const float rstd = rsqrtf(var + ln_eps);
+                        lg_s[c * kRows + hr] = fmaf(rstd, fmaf(-mu, cs[0], p0), cs[3]);
+                        y_s[c * kRows + hr] = fmaf(rstd, fmaf(-mu, cs[1], p1), cs[4]);
+                        z_s[c * kRows + hr] = fmaf(rstd, fmaf(-mu, cs[2], p2), cs[5]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs args) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -120,7 +292,6 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
     float *mid_s = reinterpret_cast<float *>(base + OFF_MID);
     float *winv_s = reinterpret_cast<float *>(base + OFF_WINV);
     float *whalf_s = reinterpret_cast<float *>(base + OFF_WHALF);
-    float *gmax_s = reinterpret_cast<float *>(base + OFF_GMAX);
     float *cscal = reinterpret_cast<float *>(base + OFF_CSCAL);
     float *cw = reinterpret_cast<float *>(base + OFF_CW);
     int *cnews = reinterpret_cast<int *>(base + OFF_CNEWS);
@@ -269,96 +440,29 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             mid_s[tid] = 0.5f * (hi + lo);
             whalf_s[tid] = wh;
             winv_s[tid] = 1.0f / wh;
+            // Interpolation error of f(a) = (1 - a) sigmoid(g a + b) on [mid - w, mid + w] with n Chebyshev nodes:
+            // max|d^n f| w^n / (n! 2^(n-1));  |d^2 f| <= 0.0962 g^2 + 0.5 |g|,  |d^4 f| <= 0.125 g^4 + 0.5 |g|^3.
+            // g is bounded by the cached max |W_g vc| of the news plus the max over the bucket-pair table.
+            const float gabs = (__ldg(C.hist_rows + (size_t)hnews[tid] * LIME_HIST_LD + LIME_HIST_GW_ABSMAX) + C.tab_gw_absmax) *
+                               (1.0f / kLog2e);
+            const float w2 = wh * wh, g2 = gabs * gabs;
+            const float err2 = w2 * (0.0962f * g2 + 0.5f * gabs) * 0.25f;
+            const float err4 = w2 * w2 * (0.125f * g2 * g2 + 0.5f * g2 * gabs) * (1.0f / 192.0f);
+            if (!(err2 <= args.interp_tol)) atomicOr(flag_s, 1);          // 2 nodes are not enough
+            if (!(err4 <= args.interp_tol)) atomicOr(flag_s, 2);          // 4 nodes are not enough: exact kernel
         }
         __syncthreads();
+        const int flags0 = flag_s[0];
+        const int nodes = (flags0 & 1) ? 4 : 2;
 
         const int n_cols = (3 * cnt + 15) & ~15;
-        const int mtiles = (4 * H + 127) >> 7;
+        const int mtiles = (nodes * H + 127) >> 7;
 
         if (warp < kWarps) {
-            // ---------------- operand production: 13 K chunks of 32 dims --------------------------
-            const int hr = tid >> 2, q = tid & 3;
-            const bool row_ok = hr < H;
-            const float mid = row_ok ? mid_s[hr] : 0.0f, wh = row_ok ? whalf_s[hr] : 0.0f;
-            const float aj[4] = {fmaf(wh, kX0, mid), fmaf(wh, kX1, mid), fmaf(wh, kX2, mid), fmaf(wh, kX3, mid)};
-            const float *hrow = C.hist_rows + (size_t)(row_ok ? hnews[hr] : 0) * LIME_HIST_LD;
-            const float *trow = C.hist_tab + (size_t)(row_ok ? htab[hr] : 0) * LIME_HTAB_LD;
-            float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            float gmx = 0.0f, xmax = 0.0f;
-            for (int kc = 0; kc < kChunks; ++kc) {
-                const int s = kc & 1;
-                const uint32_t u = use[s]++;
-                if (u >= 1) tc::mbar_wait(bar_free + s, (u - 1) & 1u);
-                const int d0 = 32 * kc + 8 * q;
-                const int lq = 4 * s + q;                  // 16-byte chunk inside the 128-byte tile row
-                if (row_ok && d0 < kD) {
-                    float v[8], gg[8];
-                    {
-                        const float4 a0 = ldg4(hrow + LIME_HIST_VC + d0), a1 = ldg4(hrow + LIME_HIST_VC + d0 + 4);
-                        const float4 b0 = ldg4(trow + d0), b1 = ldg4(trow + d0 + 4);
-                        const float4 c0 = ldg4(hrow + LIME_HIST_GW + d0), c1 = ldg4(hrow + LIME_HIST_GW + d0 + 4);
-                        const float4 e0 = ldg4(trow + kD + d0), e1 = ldg4(trow + kD + d0 + 4);
-                        v[0] = a0.x + b0.x; v[1] = a0.y + b0.y; v[2] = a0.z + b0.z; v[3] = a0.w + b0.w;
-                        v[4] = a1.x + b1.x; v[5] = a1.y + b1.y; v[6] = a1.z + b1.z; v[7] = a1.w + b1.w;
-                        gg[0] = c0.x + e0.x; gg[1] = c0.y + e0.y; gg[2] = c0.z + e0.z; gg[3] = c0.w + e0.w;
-                        gg[4] = c1.x + e1.x; gg[5] = c1.y + e1.y; gg[6] = c1.z + e1.z; gg[7] = c1.w + e1.w;
-                    }
-                    const float4 bb0 = *reinterpret_cast<const float4 *>(bias_s + d0);
-                    const float4 bb1 = *reinterpret_cast<const float4 *>(bias_s + d0 + 4);
-                    const float bb[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) gmx = fmaxf(gmx, fabsf(gg[e]));
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        // o = v (1 - (1 - a_j) sigmoid(a_j W_g v + b_g)),  sigmoid(z) = 1 / (1 + 2^z'),  z' = -log2(e) z
-                        const float a = aj[j], oma = 1.0f - a;
-                        float o[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float den = ex2_approx(fmaf(a, gg[e], bb[e])) + 1.0f;
-                            o[e] = fmaf(-(v[e] * oma), rcp_approx(den), v[e]);
-                            ps[2 * j] += o[e];
-                            ps[2 * j + 1] = fmaf(o[e], o[e], ps[2 * j + 1]);
-                        }
-                        uint4 hi, lo;
-                        xmax = fmaxf(xmax, split8(o, hi, lo));
-                        const uint32_t off = tc::sw128_offset(4 * hr + j, lq);
-                        *reinterpret_cast<uint4 *>(base + OFF_AHI + off) = hi;
-                        *reinterpret_cast<uint4 *>(base + OFF_ALO + off) = lo;
-                    }
-                }
-                for (int task = tid; task < 3 * cnt * 4; task += kCompute) {
-                    const int n = task >> 2, qq = task & 3;
-                    const int d1 = 32 * kc + 8 * qq;
-                    if (d1 >= kD) continue;
-                    const int c = n / 3, k = n - 3 * c;
-                    const float *cr = C.cand_rows + (size_t)cnews[c] * LIME_CAND_LD + k * kD + d1;
-                    const float *ct = C.cand_tab + (size_t)ctab[c] * LIME_CTAB_LD + k * kD + d1;
-                    const float4 a0 = ldg4(cr), a1 = ldg4(cr + 4), b0 = ldg4(ct), b1 = ldg4(ct + 4);
-                    const float x[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w,
-                                        a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
-                    uint4 hi, lo;
-                    xmax = fmaxf(xmax, split8(x, hi, lo));
-                    const uint32_t off = tc::sw128_offset(n, 4 * s + qq);
-                    *reinterpret_cast<uint4 *>(base + OFF_BHI + off) = hi;
-                    *reinterpret_cast<uint4 *>(base + OFF_BLO + off) = lo;
-                }
-                tc::fence_proxy_async_smem();
-                tc::mbar_arrive(bar_full + s);
-            }
-            // node sums of the row: sum o, sum o^2 per node, over the 4 lanes that share the row
-#pragma unroll
-            for (int o = 1; o < 4; o <<= 1) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) ps[i] += __shfl_xor_sync(0xffffffffu, ps[i], o);
-                gmx = fmaxf(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
-            }
-            if (!(xmax <= kHalfSafe)) flag_s[0] = 1;   // outside the fp16 operand range (or NaN): exact kernel
-            if (row_ok && q == 0) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) s01_s[hr * 8 + i] = ps[i];
-                gmax_s[hr] = gmx;
-            }
+            if (nodes == 2) produce_operands<2>(base, C, H, cnt, tid, hnews, htab, cnews, ctab, mid_s, whalf_s, bias_s, s01_s,
+                                                flag_s, bar_full, bar_free, use);
+            else            produce_operands<4>(base, C, H, cnt, tid, hnews, htab, cnews, ctab, mid_s, whalf_s, bias_s, s01_s,
+                                                flag_s, bar_full, bar_free, use);
         } else {
             // ---------------- MMA issuer ---------------------------------------------------------
             const uint32_t idesc = tc::idesc_f16_f32(128, n_cols);
@@ -391,75 +495,17 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
         __syncthreads();   // node sums visible
 
         if (warp < kWarps) {
-            // ---------------- interpolation-error bound -> exact fallback ------------------------
-            if (tid < H) {
-                const float gabs = gmax_s[tid] * (1.0f / kLog2e), w = whalf_s[tid];
-                const float w2 = w * w, g3 = gabs * gabs * gabs;
-                const float err = w2 * w2 * (0.125f * g3 * gabs + 0.5f * g3) * (1.0f / 192.0f);
-                if (!(err <= args.interp_tol)) flag_s[0] = 1;
-            }
             // ---------------- epilogue: TMEM -> Lagrange combination -> LayerNorm folding ---------
             tc::mbar_wait(bar_accum, unit_iter & 1u);
             tc::fence_after_sync();
-            const int qd = warp & 3, mt = warp >> 2;
-            if (mt < mtiles) {
-                const int r = 128 * mt + 32 * qd + lane;
-                const int hr = r >> 2, j = r & 3;
-                const bool row_ok = hr < H;
-                const int hc = row_ok ? hr : 0;
-                const float mid = mid_s[hc], winv = winv_s[hc];
-                const float s0n = row_ok ? s01_s[hc * 8 + 2 * j] : 0.0f, s1n = row_ok ? s01_s[hc * 8 + 2 * j + 1] : 0.0f;
-                // L_j(t) = (t - xa)(t - xb)(t - xc) / ((x_j - xa)(x_j - xb)(x_j - xc))
-                const float xj = j == 0 ? kX0 : j == 1 ? kX1 : j == 2 ? kX2 : kX3;
-                const float xa = j == 0 ? kX1 : kX0, xb = j <= 1 ? kX2 : kX1, xc = j == 3 ? kX2 : kX3;
-                const float invden = 1.0f / ((xj - xa) * (xj - xb) * (xj - xc));
-                const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(128 * mt);
-                for (int cg = 0; 16 * cg < cnt; ++cg) {
-                    float v[48];
-                    tc::tmem_ld16(taddr + 48 * cg, *reinterpret_cast<float(*)[16]>(&v[0]));
-                    if (cg < 2) {
-                        tc::tmem_ld16(taddr + 48 * cg + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
-                        tc::tmem_ld16(taddr + 48 * cg + 32, *reinterpret_cast<float(*)[16]>(&v[32]));
-                    } else {        // candidates 32..36 live in columns 96..110 of the 112-column tile
-#pragma unroll
-                        for (int i = 16; i < 48; ++i) v[i] = 0.0f;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int c = 16 * cg + i;
-                        if (c < cnt) {
-                            float t = (a_s[c * kRows + hc] - mid) * winv;
-                            t = fminf(fmaxf(t, -1.0f), 1.0f);
-                            const float L = (t - xa) * (t - xb) * (t - xc) * invden;
-                            float p0 = L * v[3 * i], p1 = L * v[3 * i + 1], p2 = L * v[3 * i + 2];
-                            float p3 = L * s0n, p4 = L * s1n;
-#pragma unroll
-                            for (int o = 1; o < 4; o <<= 1) {
-                                p0 += __shfl_xor_sync(0xffffffffu, p0, o);
-                                p1 += __shfl_xor_sync(0xffffffffu, p1, o);
-                                p2 += __shfl_xor_sync(0xffffffffu, p2, o);
-                                p3 += __shfl_xor_sync(0xffffffffu, p3, o);
-                                p4 += __shfl_xor_sync(0xffffffffu, p4, o);
-                            }
-                            if (j == 0 && row_ok) {
-                                const float *cs = cscal + c * 8;
-                                const float mu = p3 * (1.0f / kD);
-                                const float var = fmaxf(fmaf(-mu, mu, p4 * (1.0f / kD)), 0.0f);
-                                const float rstd = rsqrtf(var + args.ln_eps);
-                                lg_s[c * kRows + hr] = fmaf(rstd, fmaf(-mu, cs[0], p0), cs[3]);
-                                y_s[c * kRows + hr] = fmaf(rstd, fmaf(-mu, cs[1], p1), cs[4]);
-                                z_s[c * kRows + hr] = fmaf(rstd, fmaf(-mu, cs[2], p2), cs[5]);
-                            }
-                        }
-                    }
-                }
-            }
+            if (nodes == 2) epilogue<2>(tmem, warp, lane, H, cnt, mtiles, args.ln_eps, a_s, mid_s, winv_s, s01_s, cscal, lg_s, y_s, z_s);
+            else            epilogue<4>(tmem, warp, lane, H, cnt, mtiles, args.ln_eps, a_s, mid_s, winv_s, s01_s, cscal, lg_s, y_s, z_s);
         }
         tc::fence_before_sync();
         __syncthreads();
         ++unit_iter;
 
-        if (tid == 0 && flag_s[0] != 0) args.fallback_list[atomicAdd(args.fallback_count, 1)] = unit;
+        if (tid == 0 && (flag_s[0] & 6) != 0) args.fallback_list[atomicAdd(args.fallback_count, 1)] = unit;
 
         // ---------------- phase 3: candidate-query pooling + lifetime-weighted dot ---------------
         if (warp < kWarps) {

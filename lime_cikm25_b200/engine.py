@@ -27,7 +27,7 @@ from ._lib import LimeImpressions, LimeNewsCache, check
 
 D = 400
 HIST_LD, CAND_LD, HTAB_LD, CTAB_LD = 852, 1720, 800, 1208
-HIST_GW, HIST_T, HIST_TOPIC_ID = 400, 800, 850
+HIST_GW, HIST_T, HIST_TOPIC_ID, HIST_GW_ABSMAX = 400, 800, 850, 851
 CAND_SCAL, CAND_TQ, CAND_NFOLD, CAND_TOPIC_ID = 1200, 1208, 1207, 1718
 TOPIC_TAB_LD, MAX_TOPICS = 12, 1024
 TOPIC, TOPIC_LD, HEADS = 50, 52, 10
@@ -304,6 +304,9 @@ class ScoringEngine:
         ctab = torch.zeros(nb2, CTAB_LD, **f32)
         ops.linear(htab[:, :D], G, bias=cconst, out=ctab[:, :CAND_NFOLD], n=CAND_NFOLD)
         F["hist_tab"], F["cand_tab"] = htab, ctab
+        tabmax = torch.empty(nb2, **f32)
+        ops.row_absmax(htab[:, D:], tabmax)
+        F["tab_gw_absmax"] = float(tabmax.max())        # one scalar per checkpoint (host read at fold time)
         self._fold, self._fp = F, fp
         return F
 
@@ -332,6 +335,7 @@ class ScoringEngine:
             ops.linear(h[:, :D], F["G"], out=c[:, :CAND_NFOLD], n=CAND_NFOLD)       # w1 w2 w3 + scalars
             ops.linear(h[:, HIST_T:HIST_T + TOPIC_LD], F["Atq"], F["atq0"],
                        out=c[:, CAND_TQ:CAND_TQ + TOPIC * HEADS + HEADS])           # tq, qb
+        ops.row_absmax(hist[:, HIST_GW:HIST_GW + D], hist[:, HIST_GW_ABSMAX])
         self._register_topics(category, subCategory, hist, cand)
         return hist, cand
 
@@ -344,6 +348,7 @@ class ScoringEngine:
             hist_tab=F["hist_tab"].data_ptr(), cand_tab=F["cand_tab"].data_ptr(),
             gate_bias=F["gate_bias"].data_ptr(), un_prefix=F["un_prefix"].data_ptr(),
             topic_table=table.data_ptr() if table is not None else None, num_topics=T,
+            tab_gw_absmax=F["tab_gw_absmax"],
             news_num=hist_rows.shape[0], num_buckets=cfg.num_buckets,
             user_nodes=F["un_prefix"].shape[0], sigmoid_alpha=float(cfg.sigmoid_scaling_alpha),
             penalty_beta=float(cfg.penalty_scaling_beta),

@@ -188,6 +188,14 @@ def metrics_reduce(metrics):
     return sums
 
 
+def row_absmax(m, out):
+    """out[i] = max_j |m[i, j]| for a 2-D view m; out is a 1-D (possibly strided) view."""
+    lib = _lib.require_device()
+    check(lib.lime_row_absmax(_ptr(m, torch.float32, "m"), _rowmajor(m, "m"), m.shape[0], m.shape[1],
+                              _ptr(out, torch.float32, "out"), out.stride(0), _stream()), "lime_row_absmax")
+    return out
+
+
 SCORE_AUTO, SCORE_EXACT, SCORE_FORCE_FALLBACK = 0, 1, 2
 
 
