@@ -117,14 +117,14 @@ __device__ __forceinline__ float split8(const float (&x)[8], uint4 &hi, uint4 &l
 
 // Operand production for one work unit: NODES rows of O per history row (fp16 hi / lo images, K chunks of
 // 32 dims through the two halves of the 64-dim tile) and the folded vectors of the candidates; also the node
-// sums (sum o, sum o^2).  Executed by the 256 compute threads; use[] are the per-half staging counters, which
-// every thread of the CTA advances identically.
+// sums (sum o, sum o^2).  Executed by the 256 compute threads; unit_iter (units done by this CTA) gives the
+// mbarrier phases: the two half-tiles are staged 7 and 6 times per unit.
 template <int NODES>
 __device__ __forceinline__ void produce_operands(unsigned char *base, const LimeNewsCache &C, int H, int cnt, int tid,
                                                  const int *hnews, const int *htab, const int *cnews, const int *ctab,
                                                  const float *mid_s, const float *whalf_s, const float *bias_s,
                                                  float *s01_s, int *flag_s, uint64_t *bar_full, uint64_t *bar_free,
-                                                 uint32_t (&use)[2]) {
+                                                 uint32_t unit_iter) {
     const int hr = tid >> 2, q = tid & 3;
     const bool row_ok = hr < H;
     const float mid = row_ok ? mid_s[hr] : 0.0f, wh = row_ok ? whalf_s[hr] : 0.0f;
@@ -140,7 +140,7 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
     const int btasks = 3 * cnt * 4;
     for (int kc = 0; kc < kChunks; ++kc) {
         const int s = kc & 1;
-        const uint32_t u = use[s]++;
+        const uint32_t u = unit_iter * (s ? 6u : 7u) + (uint32_t)(kc >> 1);   // uses of this half so far
         if (u >= 1) tc::mbar_wait(bar_free + s, (u - 1) & 1u);
         const int d0 = 32 * kc + 8 * q;
         const int lq = 4 * s + q;                  // 16-byte chunk inside the 128-byte tile row
@@ -219,7 +219,9 @@ template <int NODES>
 __device__ __forceinline__ void epilogue(uint32_t tmem, int warp, int lane, int H, int cnt, int mtiles, float ln_eps,
                                          const float *a_s, const float *mid_s, const float *winv_s, const float *s01_s,
                                          const float *cscal, float *lg_s, float *y_s, float *z_s) {
-    const int qd = warp & 3, mt = warp >> 2;
+    const int qd = warp & 3;
+    const int mt = NODES == 2 ? 0 : warp >> 2;               // 2 nodes: one 128-row tile, warps 4-7 take the odd
+    const int cg0 = NODES == 2 ? warp >> 2 : 0, cgs = NODES == 2 ? 2 : 1;   // groups of 16 candidates
     if (mt < mtiles) {
         const int r = 128 * mt + 32 * qd + lane;
         const int hr = r / NODES, j = r % NODES;
@@ -238,7 +240,7 @@ __device__ __forceinline__ void epilogue(uint32_t tmem, int warp, int lane, int 
             invden = 1.0f / ((xj - xa) * (xj - xb) * (xj - xc));
         }
         const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(128 * mt);
-        for (int cg = 0; 16 * cg < cnt; ++cg) {
+        for (int cg = cg0; 16 * cg < cnt; cg += cgs) {
             float v[48];
             tc::tmem_ld16(taddr + 48 * cg, *reinterpret_cast<float(*)[16]>(&v[0]));
             if (cg < 2) {
@@ -331,7 +333,6 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    uint32_t use[2] = {0u, 0u};   // how often each 32-dim half of the operand tile has been staged so far
     uint32_t unit_iter = 0;       // units processed so far (phase of bar_accum)
 
     for (;;) {
@@ -460,16 +461,16 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
 
         if (warp < kWarps) {
             if (nodes == 2) produce_operands<2>(base, C, H, cnt, tid, hnews, htab, cnews, ctab, mid_s, whalf_s, bias_s, s01_s,
-                                                flag_s, bar_full, bar_free, use);
+                                                flag_s, bar_full, bar_free, unit_iter);
             else            produce_operands<4>(base, C, H, cnt, tid, hnews, htab, cnews, ctab, mid_s, whalf_s, bias_s, s01_s,
-                                                flag_s, bar_full, bar_free, use);
+                                                flag_s, bar_full, bar_free, unit_iter);
         } else {
             // ---------------- MMA issuer ---------------------------------------------------------
             const uint32_t idesc = tc::idesc_f16_f32(128, n_cols);
             const uint32_t sb = tc::smem_u32(base);
             for (int kc = 0; kc < kChunks; ++kc) {
                 const int s = kc & 1;
-                const uint32_t u = use[s]++;
+                const uint32_t u = unit_iter * (s ? 6u : 7u) + (uint32_t)(kc >> 1);
                 tc::mbar_wait(bar_full + s, u & 1u);
                 tc::fence_after_sync();
                 if (lane == 0) {
