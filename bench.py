@@ -252,6 +252,13 @@ def run_b200(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg = algorithmic_bytes(imp)
     achieved = alg / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "score_traffic.json")
+    if os.path.isfile(tpath):
+        tj = json.load(open(tpath))
+        w = tj.get("workload", {})
+        if w.get("news") == args.news and w.get("impressions") == args.impressions and w.get("history") == H:
+            traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
     line = {
         "metric": METRIC, "value": total_imp * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
@@ -262,10 +269,13 @@ def run_b200(args):
                 "h2d_bytes_per_step": dimp.h2d_bytes(), "d2h_bytes_per_step": 40},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "lime::score_kernel<2>", "kernel_ms": kernel_ms,
+                     "traffic": traffic, "kernel": "lime::score_tc_kernel", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
-                     "note": "exact fp32 per-pair semantics make this kernel MUFU/issue-bound, not HBM-bound: "
-                             "DESIGN.md 'Scoring kernel roofline'"},
+                     "note": "kernel_ms = one lime_score_impressions call (score_tc_kernel + the usually empty exact-"
+                             "fallback launch), CUDA events. traffic (ncu, one launch) exceeds the algorithmic bytes "
+                             "because a history row is cached as vc|gw (3200 B) and a candidate as w1|w2|w3 (4800 B) "
+                             "instead of one 1600 B vector; the kernel is latency/issue bound, not HBM bound: "
+                             "DESIGN.md section 3"},
         "clocks": clocks,
         "cache_build": {"seconds": cache_s, "news_per_sec": news.news_num / cache_s,
                         "tflops": news.news_num * 241.3e6 / cache_s / 1e12,
