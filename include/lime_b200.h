@@ -228,6 +228,44 @@ int lime_rank_metrics(const float *scores, const uint8_t *labels, const int64_t 
  * (deterministic fixed-order reduction; the caller divides, or all-reduces across ranks first).  */
 int lime_metrics_reduce(const double *metrics, int64_t num_impressions, double *sums, void *stream);
 
+
+/* ---- training: backward kernels of the same path (trainer.py:131-146 differentiates through them) ----
+ * Parameter gradients are ACCUMULATED into caller-zeroed buffers; activation gradients are overwritten. */
+/* C (+)= alpha * op(A) . op(B).  a_kmajor: element (i, kk) of op(A) at A[i*lda + kk], else A[kk*lda + i];
+ * b_kmajor: element (kk, j) of op(B) at B[j*ldb + kk] (an nn.Linear weight), else B[kk*ldb + j].
+ * nn.Linear backward: dX = lime_gemm(dY, 1, W, 0), dW = lime_gemm(dY, 0, X, 0) (split-K over the tokens). */
+int lime_gemm(const float *A, int64_t lda, int a_kmajor, const float *B, int64_t ldb, int b_kmajor, float *C,
+              int64_t ldc, int64_t m, int n, int64_t k, float alpha, int accumulate, void *stream);
+/* dx = dy * act'(.) evaluated from the OUTPUT y of the fused activation (1 relu, 2 tanh) */
+int lime_act_bwd(const float *dy, int64_t lddy, const float *y, int64_t ldy, float *dx, int64_t lddx,
+                 int64_t rows, int cols, int act, void *stream);
+/* out[c] += sum_r M[r, c]  (bias gradients) */
+int lime_col_sum(const float *M, int64_t ld, int64_t rows, int cols, float *out, void *stream);
+/* nn.LayerNorm backward from the layer INPUT x.  bcast_T > 0: dy holds one row per news and row r uses
+ * dy[r / bcast_T] / bcast_T (backward of the token mean, newsEncoders.py:317,321). */
+int lime_layernorm_bwd(const float *x, int64_t ldx, const float *gamma, const float *dy, int64_t lddy,
+                       int bcast_T, float *dx, int64_t lddx, float *dgamma, float *dbeta, int64_t rows, int d,
+                       float eps, void *stream);
+/* out[r, :d] = table[ids[r], :d]  /  dtable[ids[r], :d] += src[r, :d]  (embedding forward / backward) */
+int lime_gather_rows(const float *table, int64_t ldt, int64_t table_rows, const int32_t *ids, int64_t n, int d,
+                     float *out, int64_t ldo, void *stream);
+int lime_scatter_add_rows(const float *src, int64_t lds, const int32_t *ids, int64_t n, int d, float *dtable,
+                          int64_t ldt, int64_t table_rows, void *stream);
+/* backward of lime_mha: dctx [n_news*T, d] -> dqkv [n_news*T, 3d] */
+int lime_mha_bwd(const float *qkv, const float *dctx, float *dqkv, int64_t n_news, int T, int d, int nhead,
+                 void *stream);
+/* backward of lime_intent_pool: dout [n, D] -> dpre, de [n, k, D], dw2 [D] (accumulated) */
+int lime_intent_pool_bwd(const float *pre, const float *e, const float *w2, const float *dout, int64_t lddo,
+                         float *dpre, float *de, float *dw2, int64_t n, int k, int D, void *stream);
+/* backward of lime_content_fuse w.r.t. title / body (the category slices of dcontent are scattered by the
+ * caller with lime_scatter_add_rows) */
+int lime_content_fuse_bwd(const float *title, const float *body, const float *dcontent, int64_t ldc, int64_t n,
+                          int D, float *dtitle, float *dbody, void *stream);
+/* inverted dropout, stateless: y = x * keep(seed, element index) / (1 - p); the backward is the same call
+ * on the gradient with the same seed */
+int lime_dropout(const float *x, int64_t ldx, float *y, int64_t ldy, int64_t rows, int cols, float p,
+                 uint64_t seed, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

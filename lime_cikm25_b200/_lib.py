@@ -71,6 +71,16 @@ PROTOTYPES = {
     "lime_topic_pair_table": (C.c_int, [P, I64, P, I64, I32, P, P]),
     "lime_rank_metrics": (C.c_int, [P, P, P, I64, P, P, P]),
     "lime_metrics_reduce": (C.c_int, [P, I64, P, P]),
+    "lime_gemm": (C.c_int, [P, I64, C.c_int, P, I64, C.c_int, P, I64, I64, C.c_int, I64, F32, C.c_int, P]),
+    "lime_act_bwd": (C.c_int, [P, I64, P, I64, P, I64, I64, C.c_int, C.c_int, P]),
+    "lime_col_sum": (C.c_int, [P, I64, I64, C.c_int, P, P]),
+    "lime_layernorm_bwd": (C.c_int, [P, I64, P, P, I64, C.c_int, P, I64, P, P, I64, C.c_int, F32, P]),
+    "lime_gather_rows": (C.c_int, [P, I64, I64, P, I64, C.c_int, P, I64, P]),
+    "lime_scatter_add_rows": (C.c_int, [P, I64, P, I64, C.c_int, P, I64, I64, P]),
+    "lime_mha_bwd": (C.c_int, [P, P, P, I64, C.c_int, C.c_int, C.c_int, P]),
+    "lime_intent_pool_bwd": (C.c_int, [P, P, P, P, I64, P, P, P, I64, C.c_int, C.c_int, P]),
+    "lime_content_fuse_bwd": (C.c_int, [P, P, P, I64, I64, C.c_int, P, P, P]),
+    "lime_dropout": (C.c_int, [P, I64, P, I64, I64, C.c_int, F32, C.c_uint64, P]),
 }
 
 ABI_VERSION = 2

@@ -1,0 +1,223 @@
+"""torch.autograd.Function wrappers: forward AND backward of every op are calls into liblime_b200.so
+(ops.py); torch only records the graph, owns the buffers and accumulates parameter gradients.
+
+These make ``Model.forward`` differentiable in training mode, so that the reference's own training
+step (trainer.py:131-148: loss, ``backward()``, ``clip_grad_norm_``, ``Adam.step``) runs unchanged on
+top of the B200 kernels.  All tensors are fp32 CUDA, 2-D row-major views unless stated otherwise.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class Linear(torch.autograd.Function):
+    """y = act(x @ w.T + b) + residual  (lime_linear); backward with lime_gemm / lime_col_sum."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, residual):
+        if act and residual is not None:
+            raise ValueError("activation and residual cannot be combined (the activation output is needed)")
+        y = ops.linear(x, w, b, residual=residual, act=act)
+        ctx.act = act
+        ctx.save_for_backward(x, w, y if act else None)
+        ctx.has_b, ctx.has_res = b is not None, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = _c(dy)
+        dz = ops.act_bwd(dy, y, ctx.act) if ctx.act else dy
+        m, k = x.shape
+        n = w.shape[0]
+        dx = ops.gemm(dz, True, w, False, m, k, n) if ctx.needs_input_grad[0] else None
+        dw = ops.gemm(dz, False, x, False, n, k, m) if ctx.needs_input_grad[1] else None
+        db = ops.col_sum(dz) if ctx.has_b and ctx.needs_input_grad[2] else None
+        dres = dy if ctx.has_res and ctx.needs_input_grad[4] else None
+        return dx, dw, db, None, dres
+
+
+def linear(x, w, b=None, act=0, residual=None):
+    return Linear.apply(x, w, b, act, residual)
+
+
+class LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        y = torch.empty_like(x)
+        ops.layernorm(x, gamma, beta, out=y, eps=eps)
+        ctx.eps = eps
+        ctx.save_for_backward(x, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_bwd(x, gamma, _c(dy), ctx.eps)
+        return dx, dg, db, None
+
+
+class LayerNormMeanPool(torch.autograd.Function):
+    """LayerNorm of every token + unmasked mean over the T tokens of a news -> [n, d]."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, n, T, eps):
+        out = torch.empty((n, x.shape[1]), dtype=torch.float32, device=x.device)
+        ops.layernorm_meanpool(x, gamma, beta, out, n, T, eps=eps)
+        ctx.T, ctx.eps = T, eps
+        ctx.save_for_backward(x, gamma)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, gamma = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_bwd(x, gamma, _c(dout), ctx.eps, bcast_T=ctx.T)
+        return dx, dg, db, None, None, None
+
+
+class EmbedPE(torch.autograd.Function):
+    """word_embedding(ids) + positional encoding; dense [V, d] gradient like nn.Embedding."""
+
+    @staticmethod
+    def forward(ctx, E, ids, T, pe):
+        out = torch.empty((ids.numel(), E.shape[1]), dtype=torch.float32, device=E.device)
+        ops.embed_pe(E, ids, T, pe, out)
+        ctx.save_for_backward(ids)
+        ctx.shape = E.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        dE = torch.zeros(ctx.shape, dtype=torch.float32, device=dout.device)
+        ops.scatter_add_rows(_c(dout), ids.reshape(-1), dE)
+        return dE, None, None, None
+
+
+class Gather(torch.autograd.Function):
+    """table[ids] -> [n, d]  (category / bucket-table lookups)."""
+
+    @staticmethod
+    def forward(ctx, table, ids):
+        ctx.save_for_backward(ids)
+        ctx.shape = table.shape
+        return ops.gather_rows(table, ids)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        dT = torch.zeros(ctx.shape, dtype=torch.float32, device=dout.device)
+        ops.scatter_add_rows(_c(dout), ids, dT)
+        return dT, None
+
+
+class MHA(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, n, T, d, heads):
+        out = torch.empty((qkv.shape[0], d), dtype=torch.float32, device=qkv.device)
+        ops.mha(qkv, out, n, T, d, heads)
+        ctx.dims = (n, T, d, heads)
+        ctx.save_for_backward(qkv)
+        return out
+
+    @staticmethod
+    def backward(ctx, dctx):
+        (qkv,) = ctx.saved_tensors
+        n, T, d, heads = ctx.dims
+        return ops.mha_bwd(qkv, _c(dctx), n, T, d, heads), None, None, None, None
+
+
+class IntentPool(torch.autograd.Function):
+    """layers.Attention over the k intents: pre [n*k, D] (affine1 output), e [n*k, D], w2 [D] -> [n, D]."""
+
+    @staticmethod
+    def forward(ctx, pre, e, w2, n, k):
+        D = e.shape[1]
+        out = torch.empty((n, D), dtype=torch.float32, device=e.device)
+        ops.intent_pool(pre, e, w2, out, n, k, D)
+        ctx.dims = (n, k, D)
+        ctx.save_for_backward(pre, e, w2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        pre, e, w2 = ctx.saved_tensors
+        n, k, D = ctx.dims
+        dpre, de, dw2 = ops.intent_pool_bwd(pre, e, w2, _c(dout), n, k, D)
+        return dpre, de, dw2, None, None
+
+
+class ContentFuse(torch.autograd.Function):
+    """[title | sim * body | dropout(cat_emb[c]) | dropout(sub_emb[s])] -> [n, 900]."""
+
+    @staticmethod
+    def forward(ctx, title, body, cat_table, sub_table, cat, sub, p, seed):
+        n, D = title.shape
+        cd, sd = cat_table.shape[1], sub_table.shape[1]
+        out = torch.empty((n, 2 * D + cd + sd), dtype=torch.float32, device=title.device)
+        ops.content_fuse(title, body, cat_table, sub_table, cat, sub, out)
+        if p > 0:                                   # feature_fusion drops the two category embeddings (:224)
+            ops.dropout(out[:, 2 * D:2 * D + cd], p, seed, out=out[:, 2 * D:2 * D + cd])
+            ops.dropout(out[:, 2 * D + cd:], p, seed + 1, out=out[:, 2 * D + cd:])
+        ctx.meta = (D, cd, sd, p, seed, cat_table.shape)
+        ctx.save_for_backward(title, body, cat)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        title, body, cat = ctx.saved_tensors
+        D, cd, sd, p, seed, tshape = ctx.meta
+        dout = _c(dout)
+        dt, db = ops.content_fuse_bwd(title, body, dout)
+        dcat_table = None
+        if ctx.needs_input_grad[2]:
+            g = dout[:, 2 * D:2 * D + cd]
+            if p > 0:
+                g = ops.dropout(g, p, seed)
+            dcat_table = torch.zeros(tshape, dtype=torch.float32, device=dout.device)
+            ops.scatter_add_rows(g, cat, dcat_table)
+        return dt, db, dcat_table, None, None, None, None, None
+
+
+class Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        ctx.p, ctx.seed = p, seed
+        return ops.dropout(x, p, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.dropout(_c(dy), ctx.p, ctx.seed), None, None
+
+
+def dropout(x, p, seed):
+    return Dropout.apply(x, p, seed) if p > 0 else x
+
+
+class BucketPairs(torch.autograd.Function):
+    """[Ef[bf] | El[bl]] for every (bf, bl) -> [nb*nb, 2*dim]."""
+
+    @staticmethod
+    def forward(ctx, Ef, El):
+        nb, dim = Ef.shape
+        out = torch.empty((nb * nb, 2 * dim), dtype=torch.float32, device=Ef.device)
+        ops.bucket_pairs(Ef, El, out)
+        ctx.meta = (nb, dim)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        nb, dim = ctx.meta
+        dout = _c(dout)
+        idx = torch.arange(nb * nb, dtype=torch.int32, device=dout.device)
+        dEf = torch.zeros((nb, dim), dtype=torch.float32, device=dout.device)
+        dEl = torch.zeros((nb, dim), dtype=torch.float32, device=dout.device)
+        ops.scatter_add_rows(dout[:, :dim], torch.div(idx, nb, rounding_mode="floor").to(torch.int32), dEf)
+        ops.scatter_add_rows(dout[:, dim:], torch.remainder(idx, nb).to(torch.int32), dEl)
+        return dEf, dEl

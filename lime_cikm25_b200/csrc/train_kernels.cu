@@ -1,0 +1,610 @@
+// Backward (and training-only forward) kernels of the LIME scoring path (sm_100a): everything
+// trainer.py:131-146 differentiates through that is not already a forward kernel of news_kernels.cu.
+// All fp32 (the reference trains in fp32, config.py:218-219).  Gradients of parameters are ACCUMULATED
+// into caller-zeroed buffers (atomics / split-K), matching autograd's accumulate semantics.
+#include "common.cuh"
+
+namespace lime {
+
+// =================================================================================================
+// General fp32 GEMM for the backward passes of nn.Linear:  C (+)= alpha * op(A) . op(B)
+//   A_KMAJOR: element (i, kk) of op(A) at A[i * lda + kk], else at A[kk * lda + i]
+//   B_KMAJOR: element (kk, j) of op(B) at B[j * ldb + kk], else at B[kk * ldb + j]
+// 128 x 128 x 16 tiles, 8 x 8 per thread; split-K over gridDim.z with atomicAdd accumulation.
+// =================================================================================================
+constexpr int TBM = 128, TBN = 128, TBK = 16;
+
+template <bool KMAJOR>
+__device__ __forceinline__ void load_tile(float (&dst)[TBK][TBM + 4], const float *__restrict__ src, int64_t ld,
+                                          int64_t mn0, int64_t mn_lim, int k0, int k_lim, int tid) {
+    if (KMAJOR) {
+        // element (i, kk) at src[(mn0 + i) * ld + k0 + kk]: float4 along kk
+        const int lr = tid >> 2, lk = (tid & 3) * 4;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int i = lr + 64 * q;
+            const int64_t r = mn0 + i;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (r < mn_lim) {
+                const float *p = src + r * ld + k0 + lk;
+                if (k0 + lk + 3 < k_lim && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+                    const float4 t = *reinterpret_cast<const float4 *>(p);
+                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (k0 + lk + e < k_lim) v[e] = p[e];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dst[lk + e][i] = v[e];
+        }
+    } else {
+        // element (i, kk) at src[(k0 + kk) * ld + mn0 + i]: float4 along i
+        const int kk = tid >> 5, i4 = (tid & 31) * 4;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int k = kk + 8 * q;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (k0 + k < k_lim) {
+                const float *p = src + (int64_t)(k0 + k) * ld + mn0 + i4;
+                if (mn0 + i4 + 3 < mn_lim && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+                    const float4 t = *reinterpret_cast<const float4 *>(p);
+                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (mn0 + i4 + e < mn_lim) v[e] = p[e];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dst[k][i4 + e] = v[e];
+        }
+    }
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(256, 2)
+gemm_general_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ B, int64_t ldb,
+                    float *__restrict__ C, int64_t ldc, int64_t m, int n, int64_t k, int64_t k_per_split, float alpha,
+                    int accumulate) {
+    __shared__ __align__(16) float As[TBK][TBM + 4];
+    __shared__ __align__(16) float Bs[TBK][TBN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t row0 = (int64_t)blockIdx.y * TBM;
+    const int col0 = blockIdx.x * TBN;
+    const int64_t kbeg = (int64_t)blockIdx.z * k_per_split;
+    const int64_t kend = (kbeg + k_per_split < k) ? kbeg + k_per_split : k;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+    // operands are addressed relative to the split's first k so that int k indices stay small
+    const float *Ab = A_KMAJOR ? A + kbeg : A + kbeg * lda;
+    const float *Bb = B_KMAJOR ? B + kbeg : B + kbeg * ldb;
+    const int klen = (int)(kend - kbeg);
+    for (int k0 = 0; k0 < klen; k0 += TBK) {
+        load_tile<A_KMAJOR>(As, Ab, lda, row0, m, k0, klen, tid);
+        load_tile<B_KMAJOR>(Bs, Bb, ldb, col0, n, k0, klen, tid);
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < TBK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[kk][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    const bool atomic = gridDim.z > 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (r >= m) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (c >= n) continue;
+            float *o = C + r * ldc + c;
+            const float v = alpha * acc[i][j];
+            if (atomic) atomicAdd(o, v);
+            else *o = accumulate ? *o + v : v;
+        }
+    }
+}
+
+// dx = dy * act'(y) from the OUTPUT y of the fused activation (1 relu, 2 tanh); in place allowed
+__global__ void act_bwd_kernel(const float *__restrict__ dy, int64_t lddy, const float *__restrict__ y, int64_t ldy,
+                               float *__restrict__ dx, int64_t lddx, int64_t rows, int cols, int act) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols) return;
+    const int64_t r = idx / cols;
+    const int c = (int)(idx - r * cols);
+    const float g = dy[r * lddy + c], o = y[r * ldy + c];
+    dx[r * lddx + c] = act == 1 ? (o > 0.0f ? g : 0.0f) : g * (1.0f - o * o);
+}
+
+// out[c] += sum_r M[r][c]   (bias gradients)
+__global__ void __launch_bounds__(256) col_sum_kernel(const float *__restrict__ M, int64_t ld, int64_t rows, int cols,
+                                                      int64_t rows_per_block, float *__restrict__ out) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= cols) return;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float s = 0.0f;
+    for (int64_t r = r0; r < r1; ++r) s += M[r * ld + c];
+    atomicAdd(out + c, s);
+}
+
+// =================================================================================================
+// LayerNorm backward (nn.LayerNorm, biased variance).  x: the layer input.  bcast_T > 0: the upstream
+// gradient is per NEWS (row r uses dy[(r / bcast_T)] / bcast_T) - the backward of the unmasked token
+// mean that follows the second norm of the encoder layer (newsEncoders.py:317,321).
+// One warp walks rows r = w, w + W, ...; per-lane column accumulators give dgamma / dbeta with one
+// atomicAdd per (warp, column).
+// =================================================================================================
+constexpr int kLnCols = 16;   // d <= 512
+
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float *__restrict__ x, int64_t ldx, const float *__restrict__ gamma,
+                     const float *__restrict__ dy, int64_t lddy, int bcast_T, float *__restrict__ dx, int64_t lddx,
+                     float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t rows, int d, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), W = (int64_t)gridDim.x * 8;
+    float dg[kLnCols], db[kLnCols], gm[kLnCols];
+#pragma unroll
+    for (int i = 0; i < kLnCols; ++i) {
+        const int c = lane + 32 * i;
+        dg[i] = 0.0f;
+        db[i] = 0.0f;
+        gm[i] = c < d ? gamma[c] : 0.0f;
+    }
+    const float inv_d = 1.0f / (float)d;
+    const float gscale = bcast_T > 0 ? 1.0f / (float)bcast_T : 1.0f;
+    for (int64_t r = w0; r < rows; r += W) {
+        const float *xr = x + r * ldx;
+        const float *gr = dy + (bcast_T > 0 ? (r / bcast_T) : r) * lddy;
+        float v[kLnCols], g[kLnCols];
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < kLnCols; ++i) {
+            const int c = lane + 32 * i;
+            v[i] = c < d ? xr[c] : 0.0f;
+            g[i] = c < d ? gr[c] * gscale : 0.0f;
+            s += v[i];
+        }
+        const float mu = warp_sum(s) * inv_d;
+        float q = 0.0f;
+#pragma unroll
+        for (int i = 0; i < kLnCols; ++i) {
+            const int c = lane + 32 * i;
+            v[i] = c < d ? v[i] - mu : 0.0f;
+            q = fmaf(v[i], v[i], q);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+        float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < kLnCols; ++i) {
+            v[i] *= rstd;                       // xhat
+            dg[i] = fmaf(g[i], v[i], dg[i]);
+            db[i] += g[i];
+            g[i] *= gm[i];                      // dxhat
+            s1 += g[i];
+            s2 = fmaf(g[i], v[i], s2);
+        }
+        s1 = warp_sum(s1) * inv_d;
+        s2 = warp_sum(s2) * inv_d;
+#pragma unroll
+        for (int i = 0; i < kLnCols; ++i) {
+            const int c = lane + 32 * i;
+            if (c < d) dx[r * lddx + c] = rstd * (g[i] - s1 - v[i] * s2);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kLnCols; ++i) {
+        const int c = lane + 32 * i;
+        if (c < d) {
+            atomicAdd(dgamma + c, dg[i]);
+            atomicAdd(dbeta + c, db[i]);
+        }
+    }
+}
+
+// =================================================================================================
+// Embedding-style gathers / scatters: out[r, :d] = table[ids[r], :d];  dtable[ids[r], :d] += src[r, :d]
+// (word embedding + positional encoding backward: the encoding is additive, so src = dx0;
+//  category / freshness / lifetime tables likewise.)
+// =================================================================================================
+__global__ void gather_rows_kernel(const float *__restrict__ table, int64_t ldt, int64_t nrows_table,
+                                   const int32_t *__restrict__ ids, int64_t n, int d, float *__restrict__ out, int64_t ldo) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * d) return;
+    const int64_t r = idx / d;
+    const int c = (int)(idx - r * d);
+    int64_t id = ids[r];
+    id = (id < 0 || id >= nrows_table) ? 0 : id;
+    out[r * ldo + c] = table[id * ldt + c];
+}
+
+__global__ void scatter_add_rows_kernel(const float *__restrict__ src, int64_t lds, const int32_t *__restrict__ ids,
+                                        int64_t n, int d, float *__restrict__ dtable, int64_t ldt, int64_t nrows_table) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * d) return;
+    const int64_t r = idx / d;
+    const int c = (int)(idx - r * d);
+    int64_t id = ids[r];
+    id = (id < 0 || id >= nrows_table) ? 0 : id;
+    atomicAdd(dtable + id * ldt + c, src[r * lds + c]);
+}
+
+// =================================================================================================
+// Self-attention core backward (nn.MultiheadAttention without mask): one CTA per (news, head), one thread per
+// token.  P = softmax(s Q K^T) is rebuilt in shared memory; dV = P^T dO, dS = P (dP - rowsum(dP P)),
+// dQ = s dS K, dK = s dS^T Q.
+// =================================================================================================
+template <int T>
+__global__ void __launch_bounds__(T)
+mha_bwd_kernel(const float *__restrict__ qkv, const float *__restrict__ dctx, float *__restrict__ dqkv, int d, int nhead,
+               int hd, float scale) {
+    constexpr int HP = 33;                    // head dim (<= 32) padded: conflict-free row reads
+    extern __shared__ float sm[];
+    float *Qs = sm, *Ks = Qs + T * HP, *Vs = Ks + T * HP, *Os = Vs + T * HP, *P = Os + T * HP;   // P: [T][T + 1]
+    const int64_t news = blockIdx.y;
+    const int head = blockIdx.x;
+    const int i = threadIdx.x;
+    const int64_t ld = 3 * (int64_t)d;
+    const float *base = qkv + news * T * ld;
+    for (int e = 0; e < hd; ++e) {
+        Qs[i * HP + e] = base[i * ld + head * hd + e];
+        Ks[i * HP + e] = base[i * ld + d + head * hd + e];
+        Vs[i * HP + e] = base[i * ld + 2 * d + head * hd + e];
+        Os[i * HP + e] = dctx[(news * T + i) * (int64_t)d + head * hd + e];
+    }
+    __syncthreads();
+    float *Pi = P + i * (T + 1);
+    float m = -INFINITY;
+    for (int j = 0; j < T; ++j) {
+        float a = 0.0f;
+        for (int e = 0; e < hd; ++e) a = fmaf(Qs[i * HP + e], Ks[j * HP + e], a);
+        a *= scale;
+        Pi[j] = a;
+        m = fmaxf(m, a);
+    }
+    float l = 0.0f;
+    for (int j = 0; j < T; ++j) {
+        const float p = expf(Pi[j] - m);
+        Pi[j] = p;
+        l += p;
+    }
+    const float inv = 1.0f / l;
+    for (int j = 0; j < T; ++j) Pi[j] *= inv;
+    __syncthreads();
+    // dV_i = sum_r P[r][i] dO_r   (thread i = key/value token)
+    {
+        float acc[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] = 0.0f;
+        for (int r = 0; r < T; ++r) {
+            const float p = P[r * (T + 1) + i];
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+                if (e < hd) acc[e] = fmaf(p, Os[r * HP + e], acc[e]);
+        }
+        float *o = dqkv + (news * T + i) * ld + 2 * d + head * hd;
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+            if (e < hd) o[e] = acc[e];
+    }
+    __syncthreads();
+    // dS row i (in place of P row i)
+    {
+        float rowdot = 0.0f;
+        for (int j = 0; j < T; ++j) {
+            float dp = 0.0f;
+            for (int e = 0; e < hd; ++e) dp = fmaf(Os[i * HP + e], Vs[j * HP + e], dp);
+            rowdot = fmaf(dp, Pi[j], rowdot);
+        }
+        for (int j = 0; j < T; ++j) {
+            float dp = 0.0f;
+            for (int e = 0; e < hd; ++e) dp = fmaf(Os[i * HP + e], Vs[j * HP + e], dp);
+            Pi[j] = Pi[j] * (dp - rowdot) * scale;
+        }
+    }
+    __syncthreads();
+    {
+        float aq[32], ak[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            aq[e] = 0.0f;
+            ak[e] = 0.0f;
+        }
+        for (int j = 0; j < T; ++j) {
+            const float sij = Pi[j];                      // dS[i][j]
+            const float sji = P[j * (T + 1) + i];         // dS[j][i]
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+                if (e < hd) {
+                    aq[e] = fmaf(sij, Ks[j * HP + e], aq[e]);
+                    ak[e] = fmaf(sji, Qs[j * HP + e], ak[e]);
+                }
+        }
+        float *oq = dqkv + (news * T + i) * ld + head * hd;
+        float *ok = dqkv + (news * T + i) * ld + d + head * hd;
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+            if (e < hd) {
+                oq[e] = aq[e];
+                ok[e] = ak[e];
+            }
+    }
+}
+
+// =================================================================================================
+// layers.Attention over the k intents, backward (layers.py:285-300).  One warp per news.
+//   score_k = w2 . tanh(pre_k),  alpha = softmax_k(score),  out = sum_k alpha_k e_k
+// =================================================================================================
+__global__ void __launch_bounds__(128)
+intent_pool_bwd_kernel(const float *__restrict__ pre, const float *__restrict__ e, const float *__restrict__ w2,
+                       const float *__restrict__ dout, int64_t lddo, float *__restrict__ dpre, float *__restrict__ de,
+                       float *__restrict__ dw2, int64_t n, int k, int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    float sc[8], da[8];
+    float m = -INFINITY;
+    for (int kk = 0; kk < k; ++kk) {
+        const float *p = pre + (i * k + kk) * (int64_t)D;
+        const float *ee = e + (i * k + kk) * (int64_t)D;
+        float a = 0.0f, b = 0.0f;
+        for (int c = lane; c < D; c += 32) {
+            a = fmaf(w2[c], tanhf(p[c]), a);
+            b = fmaf(dout[i * lddo + c], ee[c], b);
+        }
+        sc[kk] = warp_sum(a);
+        da[kk] = warp_sum(b);
+        m = fmaxf(m, sc[kk]);
+    }
+    float l = 0.0f;
+    for (int kk = 0; kk < k; ++kk) {
+        sc[kk] = expf(sc[kk] - m);
+        l += sc[kk];
+    }
+    float dot = 0.0f;
+    for (int kk = 0; kk < k; ++kk) {
+        sc[kk] /= l;                      // alpha_k
+        dot = fmaf(sc[kk], da[kk], dot);
+    }
+    for (int kk = 0; kk < k; ++kk) {
+        const float ds = sc[kk] * (da[kk] - dot);      // d score_k
+        const float *p = pre + (i * k + kk) * (int64_t)D;
+        for (int c = lane; c < D; c += 32) {
+            const float t = tanhf(p[c]);
+            de[(i * k + kk) * (int64_t)D + c] = sc[kk] * dout[i * lddo + c];
+            dpre[(i * k + kk) * (int64_t)D + c] = ds * w2[c] * (1.0f - t * t);
+            atomicAdd(dw2 + c, ds * t);
+        }
+    }
+}
+
+// =================================================================================================
+// cosine gate + concat, backward (newsEncoders.py:297-300, 367-371): content = [t | sim b | cat | sub],
+// sim = (cos(t, b) + 1) / 2.  dcat_rows gets the gradient of the category slice (scattered by the caller).
+// =================================================================================================
+__global__ void __launch_bounds__(128)
+content_fuse_bwd_kernel(const float *__restrict__ title, const float *__restrict__ body, const float *__restrict__ dcontent,
+                        int64_t ldc, int64_t n, int D, float *__restrict__ dtitle, float *__restrict__ dbody) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float *t = title + i * (int64_t)D, *b = body + i * (int64_t)D;
+    const float *g = dcontent + i * ldc;
+    float tb = 0.f, tt = 0.f, bb = 0.f, gs = 0.f;
+    for (int c = lane; c < D; c += 32) {
+        const float x = t[c], y = b[c];
+        tb = fmaf(x, y, tb);
+        tt = fmaf(x, x, tt);
+        bb = fmaf(y, y, bb);
+        gs = fmaf(g[D + c], y, gs);            // d sim = sum_c dcontent_body[c] * body[c]
+    }
+    tb = warp_sum(tb);
+    tt = warp_sum(tt);
+    bb = warp_sum(bb);
+    gs = warp_sum(gs);
+    const float eps = 1e-8f;
+    const float nt = sqrtf(tt), nbv = sqrtf(bb);
+    const float ct = fmaxf(nt, eps), cb = fmaxf(nbv, eps);
+    const float cosv = tb / (ct * cb);
+    const float sim = (cosv + 1.0f) * 0.5f;
+    const float dcos = 0.5f * gs;
+    // d cos / d t = b / (ct cb) - cos * t / nt^2 (when nt > eps), symmetric for b
+    const float it = nt > eps ? 1.0f / (nt * nt) : 0.0f, ib = nbv > eps ? 1.0f / (nbv * nbv) : 0.0f;
+    const float inv = 1.0f / (ct * cb);
+    for (int c = lane; c < D; c += 32) {
+        const float x = t[c], y = b[c];
+        dtitle[i * (int64_t)D + c] = g[c] + dcos * (y * inv - cosv * x * it);
+        dbody[i * (int64_t)D + c] = sim * g[D + c] + dcos * (x * inv - cosv * y * ib);
+    }
+}
+
+// =================================================================================================
+// Inverted dropout with a stateless counter-based generator (forward and backward apply the same
+// mask: y = x * keep / (1 - p)).  element index -> 32 random bits via two rounds of a 64-bit mix.
+// =================================================================================================
+__device__ __forceinline__ uint32_t mix_bits(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (uint32_t)(z >> 32);
+}
+
+__global__ void dropout_kernel(const float *__restrict__ x, int64_t ldx, float *__restrict__ y, int64_t ldy, int64_t rows,
+                               int cols, float p, uint64_t seed) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols) return;
+    const int64_t r = idx / cols;
+    const int c = (int)(idx - r * cols);
+    const float u = (float)mix_bits(seed, (uint64_t)idx) * (1.0f / 4294967296.0f);
+    y[r * ldy + c] = u >= p ? x[r * ldx + c] * (1.0f / (1.0f - p)) : 0.0f;
+}
+
+}  // namespace lime
+
+using namespace lime;
+
+// C (+)= alpha * op(A) . op(B);  a_kmajor / b_kmajor as documented above;  accumulate: add to C.
+extern "C" int lime_gemm(const float *A, int64_t lda, int a_kmajor, const float *B, int64_t ldb, int b_kmajor, float *C,
+                         int64_t ldc, int64_t m, int n, int64_t k, float alpha, int accumulate, void *stream) {
+    LIME_CHECK_ARG(A && B && C && m > 0 && n > 0 && k > 0, "lime_gemm: bad argument");
+    cudaStream_t st = as_stream(stream);
+    const int64_t gy = (m + TBM - 1) / TBM;
+    const int gx = (n + TBN - 1) / TBN;
+    LIME_CHECK_ARG(gy <= 65535, "lime_gemm: m too large (%lld rows)", (long long)m);
+    // split K when the output grid cannot fill the GPU (weight gradients: k = all tokens)
+    int64_t splits = 1;
+    const int64_t ctas = gy * gx, target = 2LL * num_sms();
+    if (ctas < target && k >= 4096) {
+        splits = (target + ctas - 1) / ctas;
+        const int64_t max_splits = k / 1024;
+        if (splits > max_splits) splits = max_splits;
+        if (splits > 65535) splits = 65535;
+        if (splits < 1) splits = 1;
+    }
+    int64_t kps = (k + splits - 1) / splits;
+    kps = (kps + TBK - 1) / TBK * TBK;
+    splits = (k + kps - 1) / kps;
+    if (splits > 1 && !accumulate) {
+        if (ldc == n) {
+            LIME_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)m * n, st));
+        } else {
+            LIME_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * n, (size_t)m, st));
+        }
+    }
+    dim3 grid(gx, (unsigned)gy, (unsigned)splits);
+    if (a_kmajor && b_kmajor) gemm_general_kernel<true, true><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, m, n, k, kps, alpha, accumulate);
+    else if (a_kmajor) gemm_general_kernel<true, false><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, m, n, k, kps, alpha, accumulate);
+    else if (b_kmajor) gemm_general_kernel<false, true><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, m, n, k, kps, alpha, accumulate);
+    else gemm_general_kernel<false, false><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, m, n, k, kps, alpha, accumulate);
+    LIME_LAUNCH_CHECK("gemm_general_kernel");
+    return 0;
+}
+
+extern "C" int lime_act_bwd(const float *dy, int64_t lddy, const float *y, int64_t ldy, float *dx, int64_t lddx,
+                            int64_t rows, int cols, int act, void *stream) {
+    LIME_CHECK_ARG(dy && y && dx && (act == 1 || act == 2), "lime_act_bwd: bad argument");
+    if (rows <= 0 || cols <= 0) return 0;
+    const int64_t total = rows * cols;
+    act_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(dy, lddy, y, ldy, dx, lddx, rows, cols, act);
+    LIME_LAUNCH_CHECK("act_bwd_kernel");
+    return 0;
+}
+
+extern "C" int lime_col_sum(const float *M, int64_t ld, int64_t rows, int cols, float *out, void *stream) {
+    LIME_CHECK_ARG(M && out && cols > 0, "lime_col_sum: bad argument");
+    if (rows <= 0) return 0;
+    const int64_t rpb = 512;
+    dim3 grid((cols + 255) / 256, (unsigned)((rows + rpb - 1) / rpb));
+    LIME_CHECK_ARG(grid.y <= 65535, "lime_col_sum: too many rows");
+    col_sum_kernel<<<grid, 256, 0, as_stream(stream)>>>(M, ld, rows, cols, rpb, out);
+    LIME_LAUNCH_CHECK("col_sum_kernel");
+    return 0;
+}
+
+extern "C" int lime_layernorm_bwd(const float *x, int64_t ldx, const float *gamma, const float *dy, int64_t lddy,
+                                  int bcast_T, float *dx, int64_t lddx, float *dgamma, float *dbeta, int64_t rows, int d,
+                                  float eps, void *stream) {
+    LIME_CHECK_ARG(x && gamma && dy && dx && dgamma && dbeta, "lime_layernorm_bwd: null argument");
+    LIME_CHECK_ARG(d >= 1 && d <= 32 * kLnCols, "lime_layernorm_bwd: d=%d unsupported", d);
+    if (rows <= 0) return 0;
+    int64_t blocks = (rows + 7) / 8;
+    const int64_t cap = 8LL * num_sms();
+    if (blocks > cap) blocks = cap;
+    layernorm_bwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, ldx, gamma, dy, lddy, bcast_T, dx, lddx, dgamma,
+                                                                          dbeta, rows, d, eps);
+    LIME_LAUNCH_CHECK("layernorm_bwd_kernel");
+    return 0;
+}
+
+extern "C" int lime_gather_rows(const float *table, int64_t ldt, int64_t table_rows, const int32_t *ids, int64_t n, int d,
+                                float *out, int64_t ldo, void *stream) {
+    LIME_CHECK_ARG(table && ids && out && d > 0 && table_rows > 0, "lime_gather_rows: bad argument");
+    if (n <= 0) return 0;
+    const int64_t total = n * d;
+    gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(table, ldt, table_rows, ids, n, d, out, ldo);
+    LIME_LAUNCH_CHECK("gather_rows_kernel");
+    return 0;
+}
+
+extern "C" int lime_scatter_add_rows(const float *src, int64_t lds, const int32_t *ids, int64_t n, int d, float *dtable,
+                                     int64_t ldt, int64_t table_rows, void *stream) {
+    LIME_CHECK_ARG(src && ids && dtable && d > 0 && table_rows > 0, "lime_scatter_add_rows: bad argument");
+    if (n <= 0) return 0;
+    const int64_t total = n * d;
+    LIME_CHECK_ARG((total + 255) / 256 < (1LL << 31), "lime_scatter_add_rows: too large");
+    scatter_add_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(src, lds, ids, n, d, dtable, ldt,
+                                                                                         table_rows);
+    LIME_LAUNCH_CHECK("scatter_add_rows_kernel");
+    return 0;
+}
+
+extern "C" int lime_mha_bwd(const float *qkv, const float *dctx, float *dqkv, int64_t n_news, int T, int d, int nhead,
+                            void *stream) {
+    LIME_CHECK_ARG(qkv && dctx && dqkv, "lime_mha_bwd: null argument");
+    LIME_CHECK_ARG((T == 32 || T == 128) && d % nhead == 0 && d / nhead <= 32, "lime_mha_bwd: unsupported shape T=%d d=%d heads=%d", T, d, nhead);
+    if (n_news <= 0) return 0;
+    LIME_CHECK_ARG(n_news <= 65535, "lime_mha_bwd: at most 65535 news per call");
+    const int hd = d / nhead;
+    const float scale = 1.0f / sqrtf((float)hd);
+    dim3 grid(nhead, (unsigned)n_news);
+    const size_t smem = sizeof(float) * (4 * (size_t)T * 33 + (size_t)T * (T + 1));
+    if (T == 32) {
+        mha_bwd_kernel<32><<<grid, 32, smem, as_stream(stream)>>>(qkv, dctx, dqkv, d, nhead, hd, scale);
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            LIME_CUDA(cudaFuncSetAttribute(mha_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = true;
+        }
+        mha_bwd_kernel<128><<<grid, 128, smem, as_stream(stream)>>>(qkv, dctx, dqkv, d, nhead, hd, scale);
+    }
+    LIME_LAUNCH_CHECK("mha_bwd_kernel");
+    return 0;
+}
+
+extern "C" int lime_intent_pool_bwd(const float *pre, const float *e, const float *w2, const float *dout, int64_t lddo,
+                                    float *dpre, float *de, float *dw2, int64_t n, int k, int D, void *stream) {
+    LIME_CHECK_ARG(pre && e && w2 && dout && dpre && de && dw2, "lime_intent_pool_bwd: null argument");
+    LIME_CHECK_ARG(k >= 1 && k <= 8, "lime_intent_pool_bwd: k=%d unsupported (1..8)", k);
+    if (n <= 0) return 0;
+    intent_pool_bwd_kernel<<<(unsigned)((n + 3) / 4), 128, 0, as_stream(stream)>>>(pre, e, w2, dout, lddo, dpre, de, dw2, n, k, D);
+    LIME_LAUNCH_CHECK("intent_pool_bwd_kernel");
+    return 0;
+}
+
+extern "C" int lime_content_fuse_bwd(const float *title, const float *body, const float *dcontent, int64_t ldc, int64_t n,
+                                     int D, float *dtitle, float *dbody, void *stream) {
+    LIME_CHECK_ARG(title && body && dcontent && dtitle && dbody, "lime_content_fuse_bwd: null argument");
+    if (n <= 0) return 0;
+    content_fuse_bwd_kernel<<<(unsigned)((n + 3) / 4), 128, 0, as_stream(stream)>>>(title, body, dcontent, ldc, n, D, dtitle, dbody);
+    LIME_LAUNCH_CHECK("content_fuse_bwd_kernel");
+    return 0;
+}
+
+extern "C" int lime_dropout(const float *x, int64_t ldx, float *y, int64_t ldy, int64_t rows, int cols, float p,
+                            uint64_t seed, void *stream) {
+    LIME_CHECK_ARG(x && y && p >= 0.0f && p < 1.0f, "lime_dropout: bad argument");
+    if (rows <= 0 || cols <= 0) return 0;
+    const int64_t total = rows * cols;
+    dropout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, ldx, y, ldy, rows, cols, p, seed);
+    LIME_LAUNCH_CHECK("dropout_kernel");
+    return 0;
+}

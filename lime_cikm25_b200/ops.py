@@ -203,3 +203,109 @@ def score_configure(mode=SCORE_AUTO, tolerance=1e-6):
     """lime_score_configure: 0 = tensor-core scoring with exact fallback (default), 1 = exact kernel
     only, 2 = tensor-core path with every unit forced through the fallback (tests)."""
     check(_lib.load().lime_score_configure(int(mode), float(tolerance)), "lime_score_configure")
+
+
+# ---- training kernels (csrc/train_kernels.cu) -------------------------------------------------------
+def gemm(a, a_kmajor, b, b_kmajor, m, n, k, out=None, alpha=1.0, accumulate=False):
+    """out[m, n] (+)= alpha * op(a) @ op(b) (lime_gemm; see include/lime_b200.h for the layouts)."""
+    lib = _lib.require_device()
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    check(lib.lime_gemm(_ptr(a, torch.float32, "a"), _rowmajor(a, "a"), int(bool(a_kmajor)),
+                        _ptr(b, torch.float32, "b"), _rowmajor(b, "b"), int(bool(b_kmajor)),
+                        _ptr(out, torch.float32, "out"), _rowmajor(out, "out"), m, n, k, float(alpha),
+                        int(bool(accumulate)), _stream()), "lime_gemm")
+    return out
+
+
+def act_bwd(dy, y, act, out=None):
+    lib = _lib.require_device()
+    if out is None:
+        out = torch.empty_like(dy)
+    check(lib.lime_act_bwd(_ptr(dy, torch.float32, "dy"), _rowmajor(dy, "dy"), _ptr(y, torch.float32, "y"),
+                           _rowmajor(y, "y"), _ptr(out, torch.float32, "out"), _rowmajor(out, "out"),
+                           dy.shape[0], dy.shape[1], int(act), _stream()), "lime_act_bwd")
+    return out
+
+
+def col_sum(m, out=None):
+    lib = _lib.require_device()
+    if out is None:
+        out = torch.zeros(m.shape[1], dtype=torch.float32, device=m.device)
+    check(lib.lime_col_sum(_ptr(m, torch.float32, "m"), _rowmajor(m, "m"), m.shape[0], m.shape[1],
+                           _ptr(out, torch.float32, "out"), _stream()), "lime_col_sum")
+    return out
+
+
+def layernorm_bwd(x, gamma, dy, eps=1e-5, bcast_T=0):
+    """-> (dx, dgamma, dbeta).  bcast_T > 0: dy has one row per news (mean-pool backward)."""
+    lib = _lib.require_device()
+    rows, d = x.shape
+    dx = torch.empty((rows, d), dtype=torch.float32, device=x.device)
+    dg = torch.zeros(d, dtype=torch.float32, device=x.device)
+    db = torch.zeros(d, dtype=torch.float32, device=x.device)
+    check(lib.lime_layernorm_bwd(_ptr(x, torch.float32, "x"), _rowmajor(x, "x"), _ptr(gamma, torch.float32, "gamma"),
+                                 _ptr(dy, torch.float32, "dy"), _rowmajor(dy, "dy"), int(bcast_T), dx.data_ptr(), d,
+                                 dg.data_ptr(), db.data_ptr(), rows, d, float(eps), _stream()), "lime_layernorm_bwd")
+    return dx, dg, db
+
+
+def gather_rows(table, ids, out=None):
+    lib = _lib.require_device()
+    n, d = ids.numel(), table.shape[1]
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=table.device)
+    check(lib.lime_gather_rows(_ptr(table, torch.float32, "table"), _rowmajor(table, "table"), table.shape[0],
+                               _ptr(ids, torch.int32, "ids"), n, d, _ptr(out, torch.float32, "out"),
+                               _rowmajor(out, "out"), _stream()), "lime_gather_rows")
+    return out
+
+
+def scatter_add_rows(src, ids, dtable):
+    lib = _lib.require_device()
+    check(lib.lime_scatter_add_rows(_ptr(src, torch.float32, "src"), _rowmajor(src, "src"),
+                                    _ptr(ids, torch.int32, "ids"), ids.numel(), src.shape[1],
+                                    _ptr(dtable, torch.float32, "dtable"), _rowmajor(dtable, "dtable"),
+                                    dtable.shape[0], _stream()), "lime_scatter_add_rows")
+    return dtable
+
+
+def mha_bwd(qkv, dctx, n_news, T, d, nhead):
+    lib = _lib.require_device()
+    dqkv = torch.empty_like(qkv)
+    for lo in range(0, n_news, 65535):
+        hi = min(n_news, lo + 65535)
+        check(lib.lime_mha_bwd(qkv[lo * T:].data_ptr(), dctx[lo * T:].data_ptr(), dqkv[lo * T:].data_ptr(), hi - lo, T, d,
+                               nhead, _stream()), "lime_mha_bwd")
+    return dqkv
+
+
+def intent_pool_bwd(pre, e, w2, dout, n, k, D):
+    lib = _lib.require_device()
+    dpre, de = torch.empty_like(pre), torch.empty_like(e)
+    dw2 = torch.zeros(D, dtype=torch.float32, device=pre.device)
+    check(lib.lime_intent_pool_bwd(_ptr(pre, torch.float32, "pre"), _ptr(e, torch.float32, "e"), _ptr(w2, torch.float32, "w2"),
+                                   _ptr(dout, torch.float32, "dout"), _rowmajor(dout, "dout"), dpre.data_ptr(), de.data_ptr(),
+                                   dw2.data_ptr(), n, k, D, _stream()), "lime_intent_pool_bwd")
+    return dpre, de, dw2
+
+
+def content_fuse_bwd(title, body, dcontent):
+    lib = _lib.require_device()
+    n, D = title.shape
+    dt, db = torch.empty_like(title), torch.empty_like(body)
+    check(lib.lime_content_fuse_bwd(_ptr(title, torch.float32, "title"), _ptr(body, torch.float32, "body"),
+                                    _ptr(dcontent, torch.float32, "dcontent"), _rowmajor(dcontent, "dcontent"), n, D,
+                                    dt.data_ptr(), db.data_ptr(), _stream()), "lime_content_fuse_bwd")
+    return dt, db
+
+
+def dropout(x, p, seed, out=None):
+    """y = x * keep / (1 - p) with a stateless mask (same call on the gradient = backward)."""
+    lib = _lib.require_device()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.lime_dropout(_ptr(x, torch.float32, "x"), _rowmajor(x, "x"), _ptr(out, torch.float32, "out"),
+                           _rowmajor(out, "out"), x.shape[0], x.shape[1], float(p), int(seed) & (2 ** 64 - 1), _stream()),
+          "lime_dropout")
+    return out

@@ -1,0 +1,126 @@
+"""Gradient parity of the training path (forward + backward kernels) against torch autograd run on the
+CPU oracle in fp64 (every dropout p = 0, model.training = True: SURVEY.md section 7)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import lime_cikm25_b200 as L  # noqa: E402
+from lime_cikm25_b200 import ops, synth, training  # noqa: E402
+from oracle import lime_oracle as O  # noqa: E402
+from oracle.ref_import import make_config  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    floor = 0.1 * float(np.sqrt(np.mean(b * b))) + 1e-30
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def gen(seed):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+def randn(*shape, seed=0, scale=1.0):
+    return (torch.randn(*shape, generator=gen(seed)) * scale).to(DEV)
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 900, 300), (70, 52, 100), (5000, 300, 512), (33, 400, 352)])
+def test_linear_backward(lib, m, n, k):
+    from lime_cikm25_b200 import autograd as A
+    x, w, b = randn(m, k, seed=1).requires_grad_(), randn(n, k, seed=2, scale=k ** -0.5).requires_grad_(), randn(n, seed=3).requires_grad_()
+    r = randn(m, n, seed=4).requires_grad_()
+    g = randn(m, n, seed=5)
+    for act in (0, 1, 2):
+        for t in (x, w, b, r):
+            t.grad = None
+        y = A.linear(x, w, b, act=act, residual=None if act else r)
+        y.backward(g)
+        x64, w64, b64, r64 = (t.detach().double().cpu().requires_grad_() for t in (x, w, b, r))
+        z = x64 @ w64.t() + b64
+        z = [z + r64, torch.relu(z), torch.tanh(z)][act]
+        z.backward(g.double().cpu())
+        assert rel(y.detach().cpu(), z.detach()) < 5e-5
+        assert rel(x.grad.cpu(), x64.grad) < 5e-5 and rel(w.grad.cpu(), w64.grad) < 5e-5 and rel(b.grad.cpu(), b64.grad) < 5e-5
+        if not act:
+            assert rel(r.grad.cpu(), r64.grad) < 1e-6
+
+
+def test_layernorm_and_mha_backward(lib):
+    from lime_cikm25_b200 import autograd as A
+    n, T, d, heads = 5, 32, 300, 10
+    x = randn(n * T, d, seed=1).requires_grad_()
+    gm, bt = (1 + 0.1 * randn(d, seed=2)).requires_grad_(), randn(d, seed=3, scale=0.1).requires_grad_()
+    g = randn(n, d, seed=4)
+    out = A.LayerNormMeanPool.apply(x, gm, bt, n, T, 1e-5)
+    out.backward(g)
+    x64, g64, b64 = (t.detach().double().cpu().requires_grad_() for t in (x, gm, bt))
+    ref = torch.nn.functional.layer_norm(x64, (d,), g64, b64, 1e-5).view(n, T, d).mean(1)
+    ref.backward(g.double().cpu())
+    assert rel(out.detach().cpu(), ref.detach()) < 5e-5
+    assert rel(x.grad.cpu(), x64.grad) < 5e-5 and rel(gm.grad.cpu(), g64.grad) < 5e-5 and rel(bt.grad.cpu(), b64.grad) < 5e-5
+    for T in (32, 128):
+        qkv = randn(n * T, 3 * d, seed=6, scale=0.7).requires_grad_()
+        go = randn(n * T, d, seed=7)
+        ctx = A.MHA.apply(qkv, n, T, d, heads)
+        ctx.backward(go)
+        q64 = qkv.detach().double().cpu().requires_grad_()
+        q, k, v = (q64[:, i * d:(i + 1) * d].view(n, T, heads, d // heads).transpose(1, 2) for i in range(3))
+        att = torch.softmax(q @ k.transpose(-1, -2) / (d // heads) ** 0.5, dim=-1) @ v
+        ref = att.transpose(1, 2).reshape(n * T, d)
+        ref.backward(go.double().cpu())
+        assert rel(ctx.detach().cpu(), ref.detach()) < 5e-5
+        assert rel(qkv.grad.cpu(), q64.grad) < 5e-5
+
+
+def _make(case_seed, **over):
+    cfg = make_config(vocabulary_size=500, batch_size=4, word_embedding_init="skip", dropout_rate=0.0, **over)
+    model = L.Model(cfg)
+    model.initialize()
+    synth.synthetic_parameters(model, case_seed)
+    sd = {k: v.detach().clone().double().requires_grad_(v.dtype.is_floating_point) for k, v in model.state_dict().items()}
+    return cfg, model.to(DEV).train(), sd
+
+
+def test_news_encoder_gradients(lib):
+    """LIME(CROWN) encode of 10 news: output and every parameter gradient vs fp64 autograd on the oracle."""
+    cfg, model, sd = _make(21)
+    news = synth.make_news_table(9, vocabulary_size=cfg.vocabulary_size, seed=3)
+    n = news.news_num
+    rng = np.random.default_rng(5)
+    fresh = np.exp(rng.uniform(0, 16, n)).astype(np.float32)
+    life = np.exp(rng.uniform(6, 13, n)).astype(np.float32)
+    R = torch.randn(n, 400, generator=gen(9))
+    t32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.int32)).to(DEV)
+    v = training.encode_news(model.news_encoder, t32(news.title_text), t32(news.body_text), t32(news.category),
+                             t32(news.subCategory), torch.as_tensor(fresh).to(DEV), torch.as_tensor(life).to(DEV))
+    (v * R.to(DEV)).sum().backward()
+    tl = lambda a: torch.as_tensor(np.asarray(a)).long()
+    v64 = O.lime_news(sd, tl(news.title_text), tl(news.body_text), tl(news.category), tl(news.subCategory),
+                      torch.as_tensor(fresh), torch.as_tensor(life), cfg, torch.float64)
+    (v64 * R.double()).sum().backward()
+    assert rel(v.detach().cpu(), v64.detach()) < 1e-4
+    # the same computation by torch's own fp32 CPU kernels: the yardstick for fp32 rounding through the
+    # transformer layer (a gradient is accepted within 1e-3 of fp64 AND within 4x of what torch-fp32 achieves)
+    sd32 = {k: t.detach().float().requires_grad_(t.dtype.is_floating_point) for k, t in sd.items()}
+    v32 = O.lime_news(sd32, tl(news.title_text), tl(news.body_text), tl(news.category), tl(news.subCategory),
+                      torch.as_tensor(fresh), torch.as_tensor(life), cfg, torch.float32)
+    (v32 * R).sum().backward()
+    checked, worst = 0, 0.0
+    for name, p in model.named_parameters():
+        if not name.startswith("news_encoder.") or not p.requires_grad:      # frozen tables (newsEncoders.py:91-94,177-178)
+            continue
+        g64 = sd[name].grad
+        if g64 is None or float(g64.abs().max()) == 0.0:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        assert p.grad is not None, name
+        err, err32 = rel(p.grad.cpu(), g64), rel(sd32[name].grad, g64)
+        assert err < 1e-3 and err < 4 * err32 + 1e-4, (name, err, err32)
+        worst = max(worst, err)
+        checked += 1
+    assert checked >= 40
+    print("news-encoder gradients: %d parameters, worst relative error %.2e" % (checked, worst))
