@@ -266,6 +266,43 @@ int lime_content_fuse_bwd(const float *title, const float *body, const float *dc
 int lime_dropout(const float *x, int64_t ldx, float *y, int64_t ldy, int64_t rows, int cols, float p,
                  uint64_t seed, void *stream);
 
+/* ---- training: CROWN user encoder + click score, N candidates per sample (userEncoders.py:101-175,
+ * layers.py:52-93, util.py:23-49).  Dense layers are lime_linear / lime_gemm; these are the pieces between. */
+/* a[b, h] of CandidateAware_ClickedNewsAttention from Qp = query_proj(t_c) [B,N,400], Kp = key_proj(t_h)
+ * [B,H,400], mask [B,H] (layers.py:66-81; attention dropout not applied) and its backward. */
+int lime_ca_attention_fwd(const float *Qp, const float *Kp, const uint8_t *mask, int32_t B, int32_t N, int32_t H,
+                          float *a, void *stream);
+int lime_ca_attention_bwd(const float *Qp, const float *Kp, const uint8_t *mask, int32_t B, int32_t N, int32_t H,
+                          const float *da, float *dQp, float *dKp, void *stream);
+/* wc = a * v per row (layers.py:84) */
+int lime_row_scale_fwd(const float *v, const float *a, int64_t rows, int d, float *out, void *stream);
+int lime_row_scale_bwd(const float *v, const float *a, const float *dwc, int64_t rows, int d, float *dv, float *da,
+                       void *stream);
+/* o = sigmoid(z) * wc + (1 - sigmoid(z)) * v (layers.py:87-88), elementwise over `total` values */
+int lime_gate_mix_fwd(const float *z, const float *wc, const float *v, int64_t total, float *o, void *stream);
+int lime_gate_mix_bwd(const float *z, const float *wc, const float *v, const float *dout, int64_t total, float *dz,
+                      float *dwc, float *dv, void *stream);
+/* GraphSAGE mean over node indices 0..P-1 of [x_b (H rows) ; user_node rows] (userEncoders.py:91-98,121,153) */
+int lime_sage_mean_fwd(const float *x, const float *un, int32_t B, int32_t H, int32_t P, int32_t un_rows, float *m,
+                       void *stream);
+int lime_sage_mean_bwd(const float *dm, int32_t B, int32_t H, int32_t P, int32_t un_rows, float *dx, float *dun,
+                       void *stream);
+/* g[b,h] = r[b,h] + l[b]  /  dl[b] = sum_h dg[b,h] */
+int lime_add_row_bcast(const float *r, const float *l, int64_t rows, int32_t H, int d, float *g, void *stream);
+int lime_sum_over_h(const float *dg, int32_t B, int32_t H, int d, float *dl, void *stream);
+/* candidate-query pooling (userEncoders.py:158-171): Kg = K(g) [B,H,400], q = Q(c) [B,N,400], g [B,H,400]
+ * -> u [B,N,400], alpha [B,N,H] (saved for the backward) */
+int lime_pool_fwd(const float *Kg, const float *q, const float *g, int32_t B, int32_t N, int32_t H, float *u,
+                  float *alpha, void *stream);
+int lime_pool_bwd(const float *Kg, const float *q, const float *g, const float *alpha, const float *du, int32_t B,
+                  int32_t N, int32_t H, float *dKg, float *dq, float *dg, void *stream);
+/* scores[r] = (u[r] . c[r]) * w(remaining[r]) (util.py:23-49); w is returned for the backward */
+int lime_click_score_fwd(const float *u, const float *c, const float *remaining, int64_t rows, float alpha,
+                         float beta, int32_t use_weighting, int32_t use_expired_penalty, float *scores, float *w,
+                         void *stream);
+int lime_click_score_bwd(const float *u, const float *c, const float *w, const float *dscores, int64_t rows,
+                         float *du, float *dc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,20 @@ PROTOTYPES = {
     "lime_intent_pool_bwd": (C.c_int, [P, P, P, P, I64, P, P, P, I64, C.c_int, C.c_int, P]),
     "lime_content_fuse_bwd": (C.c_int, [P, P, P, I64, I64, C.c_int, P, P, P]),
     "lime_dropout": (C.c_int, [P, I64, P, I64, I64, C.c_int, F32, C.c_uint64, P]),
+    "lime_ca_attention_fwd": (C.c_int, [P, P, P, I32, I32, I32, P, P]),
+    "lime_ca_attention_bwd": (C.c_int, [P, P, P, I32, I32, I32, P, P, P, P]),
+    "lime_row_scale_fwd": (C.c_int, [P, P, I64, C.c_int, P, P]),
+    "lime_row_scale_bwd": (C.c_int, [P, P, P, I64, C.c_int, P, P, P]),
+    "lime_gate_mix_fwd": (C.c_int, [P, P, P, I64, P, P]),
+    "lime_gate_mix_bwd": (C.c_int, [P, P, P, P, I64, P, P, P, P]),
+    "lime_sage_mean_fwd": (C.c_int, [P, P, I32, I32, I32, I32, P, P]),
+    "lime_sage_mean_bwd": (C.c_int, [P, I32, I32, I32, I32, P, P, P]),
+    "lime_add_row_bcast": (C.c_int, [P, P, I64, I32, C.c_int, P, P]),
+    "lime_sum_over_h": (C.c_int, [P, I32, I32, C.c_int, P, P]),
+    "lime_pool_fwd": (C.c_int, [P, P, P, I32, I32, I32, P, P, P]),
+    "lime_pool_bwd": (C.c_int, [P, P, P, P, P, I32, I32, I32, P, P, P, P]),
+    "lime_click_score_fwd": (C.c_int, [P, P, P, I64, F32, F32, I32, I32, P, P, P]),
+    "lime_click_score_bwd": (C.c_int, [P, P, P, P, I64, P, P, P]),
 }
 
 ABI_VERSION = 2

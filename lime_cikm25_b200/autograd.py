@@ -221,3 +221,101 @@ class BucketPairs(torch.autograd.Function):
         ops.scatter_add_rows(dout[:, :dim], torch.div(idx, nb, rounding_mode="floor").to(torch.int32), dEf)
         ops.scatter_add_rows(dout[:, dim:], torch.remainder(idx, nb).to(torch.int32), dEl)
         return dEf, dEl
+
+
+# ---- user encoder + click score (csrc/train_user.cu) -------------------------------------------------
+class CAAttention(torch.autograd.Function):
+    """(Qp [B*N,400], Kp [B*H,400], mask uint8 [B,H]) -> a [B*H] (layers.py:66-81)."""
+
+    @staticmethod
+    def forward(ctx, Qp, Kp, mask, B, N, H):
+        ctx.dims = (B, N, H)
+        ctx.save_for_backward(Qp, Kp, mask)
+        return ops.ca_attention_fwd(Qp, Kp, mask, B, N, H)
+
+    @staticmethod
+    def backward(ctx, da):
+        Qp, Kp, mask = ctx.saved_tensors
+        B, N, H = ctx.dims
+        dQ, dK = ops.ca_attention_bwd(Qp, Kp, mask, B, N, H, _c(da))
+        return dQ, dK, None, None, None, None
+
+
+class RowScale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, a):
+        ctx.save_for_backward(v, a)
+        return ops.row_scale_fwd(v, a)
+
+    @staticmethod
+    def backward(ctx, dwc):
+        v, a = ctx.saved_tensors
+        return ops.row_scale_bwd(v, a, _c(dwc))
+
+
+class GateMix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, wc, v):
+        ctx.save_for_backward(z, wc, v)
+        return ops.gate_mix_fwd(z, wc, v)
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, wc, v = ctx.saved_tensors
+        return ops.gate_mix_bwd(z, wc, v, _c(dout))
+
+
+class SageMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, un, B, H, P):
+        ctx.dims = (B, H, P, un.shape[0])
+        return ops.sage_mean_fwd(x, un, B, H, P)
+
+    @staticmethod
+    def backward(ctx, dm):
+        B, H, P, un_rows = ctx.dims
+        dx, dun = ops.sage_mean_bwd(_c(dm), B, H, P, un_rows)
+        return dx, dun, None, None, None
+
+
+class AddRowBroadcast(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, r, l, H):
+        ctx.dims = (l.shape[0], H)
+        return ops.add_row_bcast(r, l, H)
+
+    @staticmethod
+    def backward(ctx, dg):
+        B, H = ctx.dims
+        dg = _c(dg)
+        return dg, ops.sum_over_h(dg, B, H), None
+
+
+class Pool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Kg, q, g, B, N, H):
+        u, alpha = ops.pool_fwd(Kg, q, g, B, N, H)
+        ctx.dims = (B, N, H)
+        ctx.save_for_backward(Kg, q, g, alpha)
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        Kg, q, g, alpha = ctx.saved_tensors
+        B, N, H = ctx.dims
+        dKg, dq, dg = ops.pool_bwd(Kg, q, g, alpha, _c(du), B, N, H)
+        return dKg, dq, dg, None, None, None
+
+
+class ClickScore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, c, remaining, alpha, beta, use_weighting, use_penalty):
+        s, w = ops.click_score_fwd(u, c, remaining, alpha, beta, use_weighting, use_penalty)
+        ctx.save_for_backward(u, c, w)
+        return s
+
+    @staticmethod
+    def backward(ctx, ds):
+        u, c, w = ctx.saved_tensors
+        du, dc = ops.click_score_bwd(u, c, w, _c(ds))
+        return du, dc, None, None, None, None, None

@@ -62,15 +62,26 @@ class Model(nn.Module):
                 news_subCategory, news_title_text, news_title_mask, news_title_entity,
                 news_content_text, news_content_mask, news_content_entity, news_freshness,
                 news_user_topic_lifetime, remaining_lifetime):
-        """Eval layout (model.py:158-169): candidate tensors carry no news dim; returns [B, 1].
+        """Training mode: differentiable path (training.py), candidates [B, N, ...] -> logits [B, N].
+        Eval layout (model.py:158-169): candidate tensors carry no news dim; returns [B, 1].
 
         The B*(H+1) news of the batch are encoded once (Stage A kernels) into a batch-local vector
         cache, then one fused kernel (Stage B) scores the B pairs.  The GraphSAGE prefix is the
         runtime batch size B, exactly as in the reference (userEncoders.py:91-98,153)."""
         if self.training:
-            raise NotImplementedError(
-                "Model.forward: the training forward/backward is not built on the B200 path yet; "
-                "call model.eval() (there is no PyTorch fallback)")
+            # training layout (model.py:171-181): N = 1 + M candidates per sample, differentiable path
+            if news_category.dim() != 2:
+                raise _lib.LimeError("training-mode Model.forward expects candidate tensors [B, N, ...] (dataset.py:105-141)")
+            from . import training
+            self._train_calls = getattr(self, "_train_calls", 0) + 1
+            logits = training.model_forward(
+                self, user_category, user_subCategory, user_title_text, user_content_text, user_freshness,
+                user_user_topic_lifetime, user_history_mask, news_category, news_subCategory, news_title_text,
+                news_content_text, news_freshness, news_user_topic_lifetime, remaining_lifetime,
+                seed=int(getattr(self.config, "seed", 0)) * 1000003 + self._train_calls * 101)
+            self.news_encoder.auxiliary_loss = torch.zeros((), device=logits.device)   # category loss * alpha (= 0)
+            self.news_encoder.base_news_encoder.auxiliary_loss = self.news_encoder.auxiliary_loss
+            return logits
         if news_category.dim() != 1:
             raise _lib.LimeError("eval-mode Model.forward expects one candidate per sample (model.py:158-169)")
         B, H = user_category.shape

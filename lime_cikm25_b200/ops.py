@@ -309,3 +309,120 @@ def dropout(x, p, seed, out=None):
                            _rowmajor(out, "out"), x.shape[0], x.shape[1], float(p), int(seed) & (2 ** 64 - 1), _stream()),
           "lime_dropout")
     return out
+
+
+# ---- training kernels of the user encoder (csrc/train_user.cu) -------------------------------------
+def _f32(t, name):
+    return _ptr(t, torch.float32, name)
+
+
+def ca_attention_fwd(Qp, Kp, mask, B, N, H):
+    lib = _lib.require_device()
+    a = torch.empty((B * H,), dtype=torch.float32, device=Qp.device)
+    check(lib.lime_ca_attention_fwd(_f32(Qp, "Qp"), _f32(Kp, "Kp"), _ptr(mask, torch.uint8, "mask"), B, N, H, a.data_ptr(),
+                                    _stream()), "lime_ca_attention_fwd")
+    return a
+
+
+def ca_attention_bwd(Qp, Kp, mask, B, N, H, da):
+    lib = _lib.require_device()
+    dQ, dK = torch.empty_like(Qp), torch.empty_like(Kp)
+    check(lib.lime_ca_attention_bwd(_f32(Qp, "Qp"), _f32(Kp, "Kp"), _ptr(mask, torch.uint8, "mask"), B, N, H, _f32(da, "da"),
+                                    dQ.data_ptr(), dK.data_ptr(), _stream()), "lime_ca_attention_bwd")
+    return dQ, dK
+
+
+def row_scale_fwd(v, a):
+    lib = _lib.require_device()
+    out = torch.empty_like(v)
+    check(lib.lime_row_scale_fwd(_f32(v, "v"), _f32(a, "a"), v.shape[0], v.shape[1], out.data_ptr(), _stream()), "lime_row_scale_fwd")
+    return out
+
+
+def row_scale_bwd(v, a, dwc):
+    lib = _lib.require_device()
+    dv, da = torch.empty_like(v), torch.empty_like(a)
+    check(lib.lime_row_scale_bwd(_f32(v, "v"), _f32(a, "a"), _f32(dwc, "dwc"), v.shape[0], v.shape[1], dv.data_ptr(),
+                                 da.data_ptr(), _stream()), "lime_row_scale_bwd")
+    return dv, da
+
+
+def gate_mix_fwd(z, wc, v):
+    lib = _lib.require_device()
+    o = torch.empty_like(v)
+    check(lib.lime_gate_mix_fwd(_f32(z, "z"), _f32(wc, "wc"), _f32(v, "v"), v.numel(), o.data_ptr(), _stream()), "lime_gate_mix_fwd")
+    return o
+
+
+def gate_mix_bwd(z, wc, v, dout):
+    lib = _lib.require_device()
+    dz, dwc, dv = torch.empty_like(v), torch.empty_like(v), torch.empty_like(v)
+    check(lib.lime_gate_mix_bwd(_f32(z, "z"), _f32(wc, "wc"), _f32(v, "v"), _f32(dout, "dout"), v.numel(), dz.data_ptr(),
+                                dwc.data_ptr(), dv.data_ptr(), _stream()), "lime_gate_mix_bwd")
+    return dz, dwc, dv
+
+
+def sage_mean_fwd(x, un, B, H, P):
+    lib = _lib.require_device()
+    m = torch.empty((B, x.shape[1]), dtype=torch.float32, device=x.device)
+    check(lib.lime_sage_mean_fwd(_f32(x, "x"), _f32(un, "un"), B, H, P, un.shape[0], m.data_ptr(), _stream()), "lime_sage_mean_fwd")
+    return m
+
+
+def sage_mean_bwd(dm, B, H, P, un_rows):
+    lib = _lib.require_device()
+    d = dm.shape[1]
+    dx = torch.empty((B * H, d), dtype=torch.float32, device=dm.device)
+    dun = torch.empty((un_rows, d), dtype=torch.float32, device=dm.device)
+    check(lib.lime_sage_mean_bwd(_f32(dm, "dm"), B, H, P, un_rows, dx.data_ptr(), dun.data_ptr(), _stream()), "lime_sage_mean_bwd")
+    return dx, dun
+
+
+def add_row_bcast(r, l, H):
+    lib = _lib.require_device()
+    g = torch.empty_like(r)
+    check(lib.lime_add_row_bcast(_f32(r, "r"), _f32(l, "l"), r.shape[0], H, r.shape[1], g.data_ptr(), _stream()), "lime_add_row_bcast")
+    return g
+
+
+def sum_over_h(dg, B, H):
+    lib = _lib.require_device()
+    dl = torch.empty((B, dg.shape[1]), dtype=torch.float32, device=dg.device)
+    check(lib.lime_sum_over_h(_f32(dg, "dg"), B, H, dg.shape[1], dl.data_ptr(), _stream()), "lime_sum_over_h")
+    return dl
+
+
+def pool_fwd(Kg, q, g, B, N, H):
+    lib = _lib.require_device()
+    u = torch.empty((B * N, Kg.shape[1]), dtype=torch.float32, device=Kg.device)
+    alpha = torch.empty((B * N, H), dtype=torch.float32, device=Kg.device)
+    check(lib.lime_pool_fwd(_f32(Kg, "Kg"), _f32(q, "q"), _f32(g, "g"), B, N, H, u.data_ptr(), alpha.data_ptr(), _stream()),
+          "lime_pool_fwd")
+    return u, alpha
+
+
+def pool_bwd(Kg, q, g, alpha, du, B, N, H):
+    lib = _lib.require_device()
+    dKg, dq, dg = torch.empty_like(Kg), torch.empty_like(q), torch.empty_like(g)
+    check(lib.lime_pool_bwd(_f32(Kg, "Kg"), _f32(q, "q"), _f32(g, "g"), _f32(alpha, "alpha"), _f32(du, "du"), B, N, H,
+                            dKg.data_ptr(), dq.data_ptr(), dg.data_ptr(), _stream()), "lime_pool_bwd")
+    return dKg, dq, dg
+
+
+def click_score_fwd(u, c, remaining, alpha, beta, use_weighting, use_penalty):
+    lib = _lib.require_device()
+    rows = u.shape[0]
+    s = torch.empty((rows,), dtype=torch.float32, device=u.device)
+    w = torch.empty((rows,), dtype=torch.float32, device=u.device)
+    check(lib.lime_click_score_fwd(_f32(u, "u"), _f32(c, "c"), _f32(remaining, "remaining"), rows, float(alpha), float(beta),
+                                   int(bool(use_weighting)), int(bool(use_penalty)), s.data_ptr(), w.data_ptr(), _stream()),
+          "lime_click_score_fwd")
+    return s, w
+
+
+def click_score_bwd(u, c, w, ds):
+    lib = _lib.require_device()
+    du, dc = torch.empty_like(u), torch.empty_like(c)
+    check(lib.lime_click_score_bwd(_f32(u, "u"), _f32(c, "c"), _f32(w, "w"), _f32(ds, "ds"), u.shape[0], du.data_ptr(),
+                                   dc.data_ptr(), _stream()), "lime_click_score_bwd")
+    return du, dc

@@ -76,3 +76,57 @@ def encode_news(lime, title_text, body_text, category, subCategory, freshness, l
     cd = content.shape[1]
     pw = lime.project.weight
     return A.linear(fresh, pw[:, cd:], None, residual=A.linear(content, pw[:, :cd], lime.project.bias))
+
+
+def user_scores(model, hist_vec, cand_vec, hist_cat, hist_sub, cand_cat, cand_sub, hist_mask, remaining, B, H, N, seed=0):
+    """CROWN user encoder + lifetime-weighted click score, training layout.
+    hist_vec [B*H,400], cand_vec [B*N,400] (LIME vectors), int32 category ids flat, mask uint8 [B,H],
+    remaining [B*N] fp32 seconds -> logits [B, N] (userEncoders.py:101-175, util.py:23-49)."""
+    ue, lime, cfg = model.user_encoder, model.news_encoder, model.config
+    ca = ue.candidate_aware_attn
+    sage = ue.graph_sage.convs[0]
+    p = float(cfg.dropout_rate) if model.training else 0.0
+    # topic representations from LIME's frozen tables + category_affine (userEncoders.py:103-105,115-117)
+    pad_h = torch.zeros(B * H, 2, dtype=torch.float32, device=hist_vec.device)
+    pad_c = torch.zeros(B * N, 2, dtype=torch.float32, device=hist_vec.device)
+    th = torch.cat([topic_representation(lime, hist_cat, hist_sub), pad_h], dim=1)            # [B*H, 52]
+    tc = torch.cat([topic_representation(lime, cand_cat, cand_sub), pad_c], dim=1)            # [B*N, 52]
+    Qp = A.linear(tc, F.pad(ca.query_proj.weight, (0, 2)), ca.query_proj.bias)                # layers.py:66
+    Kp = A.linear(th, F.pad(ca.key_proj.weight, (0, 2)), ca.key_proj.bias)                    # layers.py:67
+    a = A.CAAttention.apply(Qp, Kp, hist_mask, B, N, H)                                        # [B*H]
+    wc = A.RowScale.apply(hist_vec, a)                                                         # layers.py:84
+    z = A.linear(wc, ca.gate_proj.weight, ca.gate_proj.bias)
+    o = A.GateMix.apply(z, wc, hist_vec)                                                       # layers.py:87-88
+    x = A.LayerNorm.apply(o, ca.layernorm.weight, ca.layernorm.bias, ca.layernorm.eps)
+    # GraphSAGE over [x ; dropout(user_node_embedding)], sources = runtime batch (userEncoders.py:91-98,121,151-157)
+    un = A.dropout(ue.user_node_embedding, p, seed + 51)
+    m = A.SageMean.apply(x, un, B, H, B)
+    g = A.AddRowBroadcast.apply(A.linear(x, sage.lin_r.weight, None), A.linear(m, sage.lin_l.weight, sage.lin_l.bias), H)
+    # candidate-query pooling (userEncoders.py:158-171)
+    Kg = A.linear(g, ue.K.weight, None)
+    q = A.linear(cand_vec, ue.Q.weight, ue.Q.bias)
+    u = A.Pool.apply(Kg, q, g, B, N, H)
+    rw = model.remaining_lifetime_weighting
+    s = A.ClickScore.apply(u, cand_vec, remaining.reshape(-1).float().contiguous(), rw.alpha, rw.beta,
+                           rw.use_remaining_lifetime_weighting, rw.use_expired_penalty)
+    return s.view(B, N)
+
+
+def model_forward(model, user_category, user_subCategory, user_title_text, user_content_text, user_freshness,
+                  user_lifetime, user_history_mask, news_category, news_subCategory, news_title_text,
+                  news_content_text, news_freshness, news_lifetime, remaining_lifetime, seed=0):
+    """Training-mode Model.forward (model.py:151-187): candidate tensors carry the news dim N."""
+    B, H = user_category.shape
+    N = news_category.shape[1]
+    i32 = torch.int32
+    flat = lambda t, w: t.reshape(-1, w).to(i32).contiguous()
+    title = torch.cat([flat(user_title_text, user_title_text.shape[-1]), flat(news_title_text, news_title_text.shape[-1])])
+    body = torch.cat([flat(user_content_text, user_content_text.shape[-1]), flat(news_content_text, news_content_text.shape[-1])])
+    cat = torch.cat([user_category.reshape(-1), news_category.reshape(-1)]).to(i32).contiguous()
+    sub = torch.cat([user_subCategory.reshape(-1), news_subCategory.reshape(-1)]).to(i32).contiguous()
+    fresh = torch.cat([user_freshness.reshape(-1), news_freshness.reshape(-1)]).float().contiguous()
+    life = torch.cat([user_lifetime.reshape(-1), news_lifetime.reshape(-1)]).float().contiguous()
+    vec = encode_news(model.news_encoder, title, body, cat, sub, fresh, life, seed)            # [B*H + B*N, 400]
+    hist_vec, cand_vec = vec[:B * H], vec[B * H:]
+    return user_scores(model, hist_vec, cand_vec, cat[:B * H], sub[:B * H], cat[B * H:], sub[B * H:],
+                       user_history_mask.to(torch.uint8).contiguous(), remaining_lifetime, B, H, N, seed)

@@ -55,11 +55,18 @@ def test_frozen_and_dead_parameters():
     assert float(m.user_encoder.user_node_embedding.abs().sum()) == 0.0          # zero-init (userEncoders.py:81)
 
 
-def test_training_forward_fails_loudly():
-    _, m = small_model()
+def test_training_forward_needs_a_gpu():
+    """Training-mode Model.forward is the differentiable B200 path (training.py); on a box without a
+    CUDA device it must fail loudly instead of falling back to PyTorch."""
+    from lime_cikm25_b200 import _lib
+    cfg, m = small_model()
     m.train()
-    with pytest.raises(NotImplementedError):
-        m(*([None] * 26))
+    news = synth.make_news_table(30, vocabulary_size=cfg.vocabulary_size, seed=1)
+    tb = [torch.as_tensor(x) for x in synth.make_train_batch(news, 2, seed=2)]
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    with pytest.raises(_lib.LimeError):
+        m(*tb, tb[24] - tb[23])
 
 
 def test_build_units():
