@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--cpu-pairs", type=int, default=192, help="pairs in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bf16-encoder", action="store_true", help="run the 4 transformer GEMMs on tcgen05 (bf16 mode)")
+    ap.add_argument("--train-steps", type=int, default=4, help="timed training steps of the secondary train_step report (0 = skip)")
+    ap.add_argument("--train-batch", type=int, default=32, help="samples per rank per training step (BASELINE.json configs[2])")
     return ap.parse_args()
 
 
@@ -159,6 +161,50 @@ def workload_config(args, imp):
             "l2": "inputs exceed L2: the news-vector cache alone is %.0f MB vs 126 MB" % (args.news * 2572 * 4 / 1e6)}
 
 
+def train_report(args, cfg, news, dev, rank, world):
+    """Secondary measurement (BASELINE.json configs[2]): one optimisation step as trainer.py:89-148 does it —
+    forward (B x (50 history + 5 candidates) news encodes), loss, backward, [NCCL gradient all-reduce], clip, Adam —
+    on the differentiable B200 path, fp32, batch resident in HBM.  Returns a dict for the JSON line."""
+    import lime_cikm25_b200 as L
+    from lime_cikm25_b200 import _lib, synth
+    from lime_cikm25_b200.trainer import Trainer
+    import torch.distributed as dist
+    lib = _lib.require_device()
+    torch.manual_seed(0)
+    model = L.Model(cfg)
+    model.initialize()
+    synth.synthetic_parameters(model, seed=0)
+    model = model.to(dev).train()
+    tr = Trainer(model, cfg)
+    B = args.train_batch
+    batch = [torch.as_tensor(x).to(dev) for x in synth.make_train_batch(news, B, seed=500 + rank)]
+    for _ in range(2):
+        tr.step(batch)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    lib.lime_launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.train_steps):
+        loss = tr.step(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.train_steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    news_per_step = B * (H + 5)
+    return {"metric": "train_samples_per_sec", "value": B * world / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+            "batch_per_gpu": B, "history": H, "candidates": 5, "dtype": "f32", "dropout_rate": float(cfg.dropout_rate),
+            "news_encodes_per_step_per_gpu": news_per_step, "loss": float(loss),
+            "tflops": 3 * 241.3e6 * news_per_step / (ms * 1e-3) / 1e12,
+            "gpu_launches_per_step": int(lib.lime_launch_count()) // max(1, args.train_steps),
+            "allreduce_bytes_per_step": int(getattr(tr, "allreduce_bytes", 0)),
+            "optimizer": "torch.optim.Adam + clip_grad_norm_(4.0), as trainer.py:33,147"}
+
+
 def run_b200(args):
     import lime_cikm25_b200 as L
     from lime_cikm25_b200 import _lib, engine, parallel, synth, util
@@ -233,6 +279,12 @@ def run_b200(args):
         e2e_s = time.perf_counter() - t0
         clocks = sampler.stop() if sampler else None
 
+    train = None
+    if args.train_steps > 0:
+        del cache, scores
+        torch.cuda.empty_cache()
+        train = train_report(args, cfg, news, dev, rank, world)
+
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     tot = torch.tensor([dimp.num_impressions, dimp.num_pairs], dtype=torch.float64, device=dev)
     if world > 1:
@@ -283,6 +335,8 @@ def run_b200(args):
         "metrics": {"auc": result[0] / result[4], "mrr": result[1] / result[4],
                     "ndcg5": result[2] / result[4], "ndcg10": result[3] / result[4]},
     }
+    if train is not None:
+        line["train_step"] = train
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(args, cfg, news, imp, sd_cpu)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -62,7 +62,7 @@ int         lime_abi_version(void);
 const char *lime_last_error(void);
 /* Number of CUDA devices visible; <= 0 means the product path cannot run. */
 int         lime_device_count(void);
-/* Kernels launched by this library on the calling thread since the last reset (bench.py's
+/* Kernels launched by this library (any thread of the process) since the last reset (bench.py's
  * gpu_launches).  */
 int64_t     lime_launch_count(void);
 void        lime_launch_count_reset(void);

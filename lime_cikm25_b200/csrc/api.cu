@@ -1,5 +1,7 @@
 // Library-level plumbing of liblime_b200.so: error string, launch counter, device queries.
 #include <stdarg.h>
+
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -7,7 +9,7 @@
 namespace lime {
 
 static thread_local char g_error[512] = "";
-static thread_local int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};   // process-wide: autograd runs the backward kernels on its own thread
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -16,7 +18,7 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-void count_launch() { ++g_launches; }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int num_sms() {
     static int cached = 0;
@@ -46,9 +48,9 @@ extern "C" int lime_device_count(void) {
     return n;
 }
 
-extern "C" int64_t lime_launch_count(void) { return lime::g_launches; }
+extern "C" int64_t lime_launch_count(void) { return lime::g_launches.load(std::memory_order_relaxed); }
 
-extern "C" void lime_launch_count_reset(void) { lime::g_launches = 0; }
+extern "C" void lime_launch_count_reset(void) { lime::g_launches.store(0, std::memory_order_relaxed); }
 
 extern "C" int64_t lime_sizeof_news_cache(void) { return (int64_t)sizeof(LimeNewsCache); }
 

@@ -9,7 +9,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 timeout 600 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref exit $?"; cat gpurun_out/bench_ref.json
 if [ "${1:-}" = "ncu" ]; then
-  SMALL="--steps 2 --warmup 3 --news 8000 --impressions 8000 --no-cpu-baseline"
+  SMALL="--steps 2 --warmup 3 --news 8000 --impressions 8000 --no-cpu-baseline --train-steps 0"
   timeout 600 python bench.py $SMALL > gpurun_out/plain.log 2>&1 && \
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py $SMALL > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches exit $?"

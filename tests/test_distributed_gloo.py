@@ -49,6 +49,44 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    parallel.init_from_env(backend="gloo")
+    from lime_cikm25_b200 import trainer
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(7, 5)), torch.nn.Parameter(torch.randn(11)),
+              torch.nn.Parameter(torch.randn(3, 3)), torch.nn.Parameter(torch.randn(2), requires_grad=False)]
+    params[0].grad = torch.full((7, 5), float(rank + 1))
+    params[1].grad = torch.arange(11.0) * (rank + 1)
+    if rank == 0:
+        params[2].grad = torch.ones(3, 3)            # a parameter that got no gradient on rank 1
+    nbytes = trainer.allreduce_gradients(params)
+    q.put((rank, params[0].grad.clone(), params[1].grad.clone(),
+           None if params[2].grad is None else params[2].grad.clone(), nbytes))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_gloo_world2():
+    """The data-parallel gradient exchange of the training path: mean over ranks, same flat layout on every
+    rank even when a parameter has no gradient somewhere."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted((q.get(timeout=120) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, g0, g1, g2, nbytes in out:
+        assert torch.allclose(g0, torch.full((7, 5), 1.5)) and torch.allclose(g1, torch.arange(11.0) * 1.5)
+        assert nbytes == (35 + 11 + 9) * 4
+    assert torch.allclose(out[0][3], torch.full((3, 3), 0.5)) and out[1][3] is None
+
+
 def test_sharded_metric_reduction_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
