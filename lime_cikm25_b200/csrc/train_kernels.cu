@@ -248,8 +248,10 @@ __global__ void scatter_add_rows_kernel(const float *__restrict__ src, int64_t l
 
 // =================================================================================================
 // Self-attention core backward (nn.MultiheadAttention without mask): one CTA per (news, head), one thread per
-// token.  P = softmax(s Q K^T) is rebuilt in shared memory; dV = P^T dO, dS = P (dP - rowsum(dP P)),
-// dQ = s dS K, dK = s dS^T Q.
+// token.  Nothing of size T x T is stored: thread i first derives the softmax statistics of query row i
+// (max, 1/sum, rowdot_i = sum_j P_ij dP_ij) and dQ_i; then, as key/value token j, it walks all query rows and
+// rebuilds P_ij and dS_ij = P_ij (dP_ij - rowdot_i) from those statistics to accumulate dK_j and dV_j.
+// Shared memory is only Q, K, V, dO (4 x T x 33 floats = 67 KB at T = 128), so three CTAs share an SM.
 // =================================================================================================
 template <int T>
 __global__ void __launch_bounds__(T)
@@ -257,95 +259,105 @@ mha_bwd_kernel(const float *__restrict__ qkv, const float *__restrict__ dctx, fl
                int hd, float scale) {
     constexpr int HP = 33;                    // head dim (<= 32) padded: conflict-free row reads
     extern __shared__ float sm[];
-    float *Qs = sm, *Ks = Qs + T * HP, *Vs = Ks + T * HP, *Os = Vs + T * HP, *P = Os + T * HP;   // P: [T][T + 1]
+    float *Qs = sm, *Ks = Qs + T * HP, *Vs = Ks + T * HP, *Os = Vs + T * HP, *st = Os + T * HP;   // st: [3][T]
     const int64_t news = blockIdx.y;
     const int head = blockIdx.x;
     const int i = threadIdx.x;
     const int64_t ld = 3 * (int64_t)d;
     const float *base = qkv + news * T * ld;
-    for (int e = 0; e < hd; ++e) {
-        Qs[i * HP + e] = base[i * ld + head * hd + e];
-        Ks[i * HP + e] = base[i * ld + d + head * hd + e];
-        Vs[i * HP + e] = base[i * ld + 2 * d + head * hd + e];
-        Os[i * HP + e] = dctx[(news * T + i) * (int64_t)d + head * hd + e];
+    for (int idx = i; idx < T * 32; idx += T) {
+        const int r = idx >> 5, e = idx & 31;
+        const bool ok = e < hd;
+        Qs[r * HP + e] = ok ? base[r * ld + head * hd + e] : 0.0f;
+        Ks[r * HP + e] = ok ? base[r * ld + d + head * hd + e] : 0.0f;
+        Vs[r * HP + e] = ok ? base[r * ld + 2 * d + head * hd + e] : 0.0f;
+        Os[r * HP + e] = ok ? dctx[(news * T + r) * (int64_t)d + head * hd + e] : 0.0f;
     }
     __syncthreads();
-    float *Pi = P + i * (T + 1);
+    float q[32], o[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        q[e] = Qs[i * HP + e] * scale;
+        o[e] = Os[i * HP + e];
+    }
+    // pass 1: row maximum
     float m = -INFINITY;
     for (int j = 0; j < T; ++j) {
         float a = 0.0f;
-        for (int e = 0; e < hd; ++e) a = fmaf(Qs[i * HP + e], Ks[j * HP + e], a);
-        a *= scale;
-        Pi[j] = a;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) a = fmaf(q[e], Ks[j * HP + e], a);
         m = fmaxf(m, a);
     }
-    float l = 0.0f;
+    // pass 2: sum, rowdot and the un-normalised dQ pieces:  dQ_i = s * sum_j P_ij (dP_ij - rowdot) K_j
+    float l = 0.0f, pd = 0.0f;
+    float a1[32], a2[32];                     // sum_j p~ dP K_j   and   sum_j p~ K_j   (p~ = exp(s - m))
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        a1[e] = 0.0f;
+        a2[e] = 0.0f;
+    }
     for (int j = 0; j < T; ++j) {
-        const float p = expf(Pi[j] - m);
-        Pi[j] = p;
-        l += p;
-    }
-    const float inv = 1.0f / l;
-    for (int j = 0; j < T; ++j) Pi[j] *= inv;
-    __syncthreads();
-    // dV_i = sum_r P[r][i] dO_r   (thread i = key/value token)
-    {
-        float acc[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) acc[e] = 0.0f;
-        for (int r = 0; r < T; ++r) {
-            const float p = P[r * (T + 1) + i];
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-                if (e < hd) acc[e] = fmaf(p, Os[r * HP + e], acc[e]);
-        }
-        float *o = dqkv + (news * T + i) * ld + 2 * d + head * hd;
-#pragma unroll
-        for (int e = 0; e < 32; ++e)
-            if (e < hd) o[e] = acc[e];
-    }
-    __syncthreads();
-    // dS row i (in place of P row i)
-    {
-        float rowdot = 0.0f;
-        for (int j = 0; j < T; ++j) {
-            float dp = 0.0f;
-            for (int e = 0; e < hd; ++e) dp = fmaf(Os[i * HP + e], Vs[j * HP + e], dp);
-            rowdot = fmaf(dp, Pi[j], rowdot);
-        }
-        for (int j = 0; j < T; ++j) {
-            float dp = 0.0f;
-            for (int e = 0; e < hd; ++e) dp = fmaf(Os[i * HP + e], Vs[j * HP + e], dp);
-            Pi[j] = Pi[j] * (dp - rowdot) * scale;
-        }
-    }
-    __syncthreads();
-    {
-        float aq[32], ak[32];
+        float a = 0.0f, dp = 0.0f;
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-            aq[e] = 0.0f;
-            ak[e] = 0.0f;
+            a = fmaf(q[e], Ks[j * HP + e], a);
+            dp = fmaf(o[e], Vs[j * HP + e], dp);
         }
-        for (int j = 0; j < T; ++j) {
-            const float sij = Pi[j];                      // dS[i][j]
-            const float sji = P[j * (T + 1) + i];         // dS[j][i]
+        const float p = expf(a - m);
+        l += p;
+        pd = fmaf(p, dp, pd);
+        const float pdp = p * dp;
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-                if (e < hd) {
-                    aq[e] = fmaf(sij, Ks[j * HP + e], aq[e]);
-                    ak[e] = fmaf(sji, Qs[j * HP + e], ak[e]);
-                }
+        for (int e = 0; e < 32; ++e) {
+            const float k = Ks[j * HP + e];
+            a1[e] = fmaf(pdp, k, a1[e]);
+            a2[e] = fmaf(p, k, a2[e]);
         }
+    }
+    const float inv = 1.0f / l;
+    const float rowdot = pd * inv;
+    st[i] = m;
+    st[T + i] = inv;
+    st[2 * T + i] = rowdot;
+    {
         float *oq = dqkv + (news * T + i) * ld + head * hd;
-        float *ok = dqkv + (news * T + i) * ld + d + head * hd;
 #pragma unroll
         for (int e = 0; e < 32; ++e)
-            if (e < hd) {
-                oq[e] = aq[e];
-                ok[e] = ak[e];
-            }
+            if (e < hd) oq[e] = scale * inv * (a1[e] - rowdot * a2[e]);
     }
+    __syncthreads();
+    // pass 3: this thread as key/value token j = i
+    float kj[32], vj[32], dk[32], dv[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        kj[e] = Ks[i * HP + e] * scale;
+        vj[e] = Vs[i * HP + e];
+        dk[e] = 0.0f;
+        dv[e] = 0.0f;
+    }
+    for (int r = 0; r < T; ++r) {
+        float a = 0.0f, dp = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            a = fmaf(Qs[r * HP + e], kj[e], a);
+            dp = fmaf(Os[r * HP + e], vj[e], dp);
+        }
+        const float p = expf(a - st[r]) * st[T + r];
+        const float ds = p * (dp - st[2 * T + r]) * scale;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            dv[e] = fmaf(p, Os[r * HP + e], dv[e]);
+            dk[e] = fmaf(ds, Qs[r * HP + e], dk[e]);
+        }
+    }
+    float *ok = dqkv + (news * T + i) * ld + d + head * hd;
+    float *ov = dqkv + (news * T + i) * ld + 2 * d + head * hd;
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+        if (e < hd) {
+            ok[e] = dk[e];
+            ov[e] = dv[e];
+        }
 }
 
 // =================================================================================================
@@ -565,7 +577,7 @@ extern "C" int lime_mha_bwd(const float *qkv, const float *dctx, float *dqkv, in
     const int hd = d / nhead;
     const float scale = 1.0f / sqrtf((float)hd);
     dim3 grid(nhead, (unsigned)n_news);
-    const size_t smem = sizeof(float) * (4 * (size_t)T * 33 + (size_t)T * (T + 1));
+    const size_t smem = sizeof(float) * (4 * (size_t)T * 33 + 3 * (size_t)T);
     if (T == 32) {
         mha_bwd_kernel<32><<<grid, 32, smem, as_stream(stream)>>>(qkv, dctx, dqkv, d, nhead, hd, scale);
     } else {
