@@ -161,15 +161,16 @@ def workload_config(args, imp):
             "l2": "inputs exceed L2: the news-vector cache alone is %.0f MB vs 126 MB" % (args.news * 2572 * 4 / 1e6)}
 
 
-def train_report(args, cfg, news, dev, rank, world):
+def train_report(args, cfg, news, dev, rank, world, bf16=False):
     """Secondary measurement (BASELINE.json configs[2]): one optimisation step as trainer.py:89-148 does it —
     forward (B x (50 history + 5 candidates) news encodes), loss, backward, [NCCL gradient all-reduce], clip, Adam —
     on the differentiable B200 path, fp32, batch resident in HBM.  Returns a dict for the JSON line."""
     import lime_cikm25_b200 as L
-    from lime_cikm25_b200 import _lib, synth
+    from lime_cikm25_b200 import _lib, autograd, synth
     from lime_cikm25_b200.trainer import Trainer
     import torch.distributed as dist
     lib = _lib.require_device()
+    autograd.set_bf16(bf16)
     torch.manual_seed(0)
     model = L.Model(cfg)
     model.initialize()
@@ -196,8 +197,9 @@ def train_report(args, cfg, news, dev, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     news_per_step = B * (H + 5)
-    return {"metric": "train_samples_per_sec", "value": B * world / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
-            "batch_per_gpu": B, "history": H, "candidates": 5, "dtype": "f32", "dropout_rate": float(cfg.dropout_rate),
+    autograd.set_bf16(False)
+    return {"metric": "train_samples_per_sec", "gemm_mode": "bf16 tcgen05 (fp32 accumulate, fp32 master weights)" if bf16 else "fp32 FFMA", "value": B * world / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+            "batch_per_gpu": B, "history": H, "candidates": 5, "dtype": "bf16" if bf16 else "f32", "dropout_rate": float(cfg.dropout_rate),
             "news_encodes_per_step_per_gpu": news_per_step, "loss": float(loss),
             "tflops": 3 * 241.3e6 * news_per_step / (ms * 1e-3) / 1e12,
             "gpu_launches_per_step": int(lib.lime_launch_count()) // max(1, args.train_steps),
@@ -232,6 +234,15 @@ def run_b200(args):
         cache = util.build_news_cache(model, news, dev)
         torch.cuda.synchronize()
         cache_s = time.perf_counter() - t0
+        # the other encoder mode, timed only (the scored cache stays the one selected by --bf16-encoder)
+        model.news_encoder.engine.bf16 = not bool(args.bf16_encoder)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        other = util.build_news_cache(model, news, dev)
+        torch.cuda.synchronize()
+        cache_other_s = time.perf_counter() - t0
+        del other
+        model.news_encoder.engine.bf16 = bool(args.bf16_encoder)
     dimp = engine.DeviceImpressions(imp, dev)
     torch.cuda.synchronize()
     scores = torch.empty(dimp.num_pairs, dtype=torch.float32, device=dev)
@@ -283,7 +294,9 @@ def run_b200(args):
     if args.train_steps > 0:
         del cache, scores
         torch.cuda.empty_cache()
-        train = train_report(args, cfg, news, dev, rank, world)
+        train = train_report(args, cfg, news, dev, rank, world, bf16=True)
+        train["fp32"] = {k: v for k, v in train_report(args, cfg, news, dev, rank, world, bf16=False).items()
+                         if k in ("value", "ms_per_step", "tflops", "loss", "gemm_mode")}
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     tot = torch.tensor([dimp.num_impressions, dimp.num_pairs], dtype=torch.float64, device=dev)
@@ -331,7 +344,10 @@ def run_b200(args):
         "clocks": clocks,
         "cache_build": {"seconds": cache_s, "news_per_sec": news.news_num / cache_s,
                         "tflops": news.news_num * 241.3e6 / cache_s / 1e12,
-                        "encoder": "bf16 tcgen05" if args.bf16_encoder else "fp32"},
+                        "encoder": "bf16 tcgen05" if args.bf16_encoder else "fp32",
+                        "other_mode": {"encoder": "fp32" if args.bf16_encoder else "bf16 tcgen05", "seconds": cache_other_s,
+                                       "news_per_sec": news.news_num / cache_other_s,
+                                       "tflops": news.news_num * 241.3e6 / cache_other_s / 1e12}},
         "metrics": {"auc": result[0] / result[4], "mrr": result[1] / result[4],
                     "ndcg5": result[2] / result[4], "ndcg10": result[3] / result[4]},
     }

@@ -236,6 +236,9 @@ int lime_metrics_reduce(const double *metrics, int64_t num_impressions, double *
  * nn.Linear backward: dX = lime_gemm(dY, 1, W, 0), dW = lime_gemm(dY, 0, X, 0) (split-K over the tokens). */
 int lime_gemm(const float *A, int64_t lda, int a_kmajor, const float *B, int64_t ldb, int b_kmajor, float *C,
               int64_t ldc, int64_t m, int n, int64_t k, float alpha, int accumulate, void *stream);
+/* bf16 mode of lime_gemm: operands rounded to bf16, tcgen05 tensor cores, fp32 accumulation in TMEM. */
+int lime_gemm_bf16(const float *A, int64_t lda, int a_kmajor, const float *B, int64_t ldb, int b_kmajor, float *C,
+                   int64_t ldc, int64_t m, int n, int64_t k, float alpha, int accumulate, void *stream);
 /* dx = dy * act'(.) evaluated from the OUTPUT y of the fused activation (1 relu, 2 tanh) */
 int lime_act_bwd(const float *dy, int64_t lddy, const float *y, int64_t ldy, float *dx, int64_t lddx,
                  int64_t rows, int cols, int act, void *stream);

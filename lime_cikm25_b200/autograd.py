@@ -12,6 +12,17 @@ import torch
 from . import ops
 
 
+# "bf16 mode" of the training path (BASELINE.json configs[2]): every nn.Linear forward and backward GEMM runs
+# on the tcgen05 tensor cores with bf16 operands and fp32 accumulation (lime_linear_bf16 / lime_gemm_bf16);
+# parameters, activations, gradients and the optimizer stay fp32.  Off by default: fp32 is the parity mode.
+BF16 = False
+
+
+def set_bf16(enabled):
+    global BF16
+    BF16 = bool(enabled)
+
+
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
@@ -23,8 +34,9 @@ class Linear(torch.autograd.Function):
     def forward(ctx, x, w, b, act, residual):
         if act and residual is not None:
             raise ValueError("activation and residual cannot be combined (the activation output is needed)")
-        y = ops.linear(x, w, b, residual=residual, act=act)
+        y = ops.linear(x, w, b, residual=residual, act=act, bf16=BF16)
         ctx.act = act
+        ctx.bf16 = BF16
         ctx.save_for_backward(x, w, y if act else None)
         ctx.has_b, ctx.has_res = b is not None, residual is not None
         return y
@@ -36,8 +48,8 @@ class Linear(torch.autograd.Function):
         dz = ops.act_bwd(dy, y, ctx.act) if ctx.act else dy
         m, k = x.shape
         n = w.shape[0]
-        dx = ops.gemm(dz, True, w, False, m, k, n) if ctx.needs_input_grad[0] else None
-        dw = ops.gemm(dz, False, x, False, n, k, m) if ctx.needs_input_grad[1] else None
+        dx = ops.gemm(dz, True, w, False, m, k, n, bf16=ctx.bf16) if ctx.needs_input_grad[0] else None
+        dw = ops.gemm(dz, False, x, False, n, k, m, bf16=ctx.bf16) if ctx.needs_input_grad[1] else None
         db = ops.col_sum(dz) if ctx.has_b and ctx.needs_input_grad[2] else None
         dres = dy if ctx.has_res and ctx.needs_input_grad[4] else None
         return dx, dw, db, None, dres

@@ -206,12 +206,12 @@ def score_configure(mode=SCORE_AUTO, tolerance=1e-6):
 
 
 # ---- training kernels (csrc/train_kernels.cu) -------------------------------------------------------
-def gemm(a, a_kmajor, b, b_kmajor, m, n, k, out=None, alpha=1.0, accumulate=False):
-    """out[m, n] (+)= alpha * op(a) @ op(b) (lime_gemm; see include/lime_b200.h for the layouts)."""
+def gemm(a, a_kmajor, b, b_kmajor, m, n, k, out=None, alpha=1.0, accumulate=False, bf16=False):
+    """out[m, n] (+)= alpha * op(a) @ op(b) (lime_gemm / lime_gemm_bf16; see include/lime_b200.h for the layouts)."""
     lib = _lib.require_device()
     if out is None:
         out = torch.empty((m, n), dtype=torch.float32, device=a.device)
-    check(lib.lime_gemm(_ptr(a, torch.float32, "a"), _rowmajor(a, "a"), int(bool(a_kmajor)),
+    check((lib.lime_gemm_bf16 if bf16 else lib.lime_gemm)(_ptr(a, torch.float32, "a"), _rowmajor(a, "a"), int(bool(a_kmajor)),
                         _ptr(b, torch.float32, "b"), _rowmajor(b, "b"), int(bool(b_kmajor)),
                         _ptr(out, torch.float32, "out"), _rowmajor(out, "out"), m, n, k, float(alpha),
                         int(bool(accumulate)), _stream()), "lime_gemm")

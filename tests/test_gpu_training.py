@@ -170,3 +170,55 @@ def test_training_step_gradients(lib, bs, B):
         checked += 1
     assert checked >= 55
     print("training step: %d parameters, worst gradient error %.2e" % (checked, worst))
+
+
+@pytest.mark.parametrize("ak,bk", [(True, True), (True, False), (False, True), (False, False)])
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (900, 300, 5000), (5000, 300, 900), (130, 512, 300), (400, 52, 1760)])
+def test_gemm_bf16_all_layouts(lib, ak, bk, m, n, k):
+    """bf16-mode GEMM of the backward passes (tcgen05, K-major and MN-major operands, split-K): equals an fp64
+    product of the bf16-rounded operands up to fp32 accumulation; the fp32 FFMA lime_gemm likewise."""
+    a = randn(m, k, seed=1) if ak else randn(k, m, seed=1)
+    b = randn(n, k, seed=2, scale=k ** -0.5) if bk else randn(k, n, seed=2, scale=k ** -0.5)
+    opa = (a if ak else a.t()).double()
+    opb = (b.t() if bk else b).double()
+    for bf16 in (False, True):
+        got = ops.gemm(a, ak, b, bk, m, n, k, alpha=0.5, bf16=bf16)
+        want = 0.5 * ((a.bfloat16().double() if ak else a.bfloat16().double().t()) @ (b.bfloat16().double().t() if bk else b.bfloat16().double())) \
+            if bf16 else 0.5 * (opa @ opb)
+        assert rel(got.cpu(), want.cpu()) < 5e-5, (bf16, ak, bk)
+    acc = torch.ones(m, n, device=DEV)
+    ops.gemm(a, ak, b, bk, m, n, k, out=acc, accumulate=True, bf16=True)
+    want = 1 + (a.bfloat16().double() if ak else a.bfloat16().double().t()) @ (b.bfloat16().double().t() if bk else b.bfloat16().double())
+    assert rel(acc.cpu(), want.cpu()) < 5e-5
+
+
+def test_training_step_bf16_mode(lib):
+    """bf16 mode of the training step: logits and the loss stay close to the fp32 path, gradients agree in
+    direction (cosine > 0.99 for every sizeable parameter gradient)."""
+    from lime_cikm25_b200 import autograd as A
+    cfg, model, sd = _make(33)
+    news = synth.make_news_table(40, vocabulary_size=cfg.vocabulary_size, seed=4)
+    tb = [torch.as_tensor(x).to(DEV) for x in synth.make_train_batch(news, 4, seed=8)]
+    out = {}
+    try:
+        for mode in (False, True):
+            A.set_bf16(mode)
+            model.zero_grad(set_to_none=True)
+            logits = model(*tb, tb[24] - tb[23])
+            loss = (-torch.log_softmax(logits, dim=1)[:, 0]).mean()
+            loss.backward()
+            out[mode] = (logits.detach().clone(), float(loss), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None})
+    finally:
+        A.set_bf16(False)
+    assert float((out[True][0] - out[False][0]).abs().max()) < 0.05 * float(out[False][0].abs().max()) + 1e-3
+    assert abs(out[True][1] - out[False][1]) < 0.05 * abs(out[False][1]) + 1e-3
+    assert float((out[True][0] - out[False][0]).abs().max()) > 0              # the tensor-core path really ran
+    n_checked = 0
+    for name, g32 in out[False][2].items():
+        if float(g32.norm()) < 1e-6:
+            continue
+        gb = out[True][2][name]
+        cos = float((gb * g32).sum() / (gb.norm() * g32.norm() + 1e-30))
+        assert cos > 0.95, (name, cos)      # the word table is the deepest, worst-conditioned gradient (0.98)
+        n_checked += 1
+    assert n_checked >= 50
