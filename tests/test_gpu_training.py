@@ -194,11 +194,13 @@ def test_gemm_bf16_all_layouts(lib, ak, bk, m, n, k):
 
 def test_training_step_bf16_mode(lib):
     """bf16 mode of the training step: logits and the loss stay close to the fp32 path, gradients agree in
-    direction (cosine > 0.99 for every sizeable parameter gradient)."""
+    direction.  16 samples and no lifetime weighting, so that every pair carries gradient (with 4 samples and
+    saturated weights the loss hangs on a handful of pairs and single parameter gradients get as noisy as
+    cosine 0.67 under bf16 rounding; with all 80 pairs active every cosine is above 0.99)."""
     from lime_cikm25_b200 import autograd as A
-    cfg, model, sd = _make(33)
+    cfg, model, sd = _make(33, batch_size=16, use_remaining_lifetime_weighting=False)
     news = synth.make_news_table(40, vocabulary_size=cfg.vocabulary_size, seed=4)
-    tb = [torch.as_tensor(x).to(DEV) for x in synth.make_train_batch(news, 4, seed=8)]
+    tb = [torch.as_tensor(x).to(DEV) for x in synth.make_train_batch(news, 16, seed=8)]
     out = {}
     try:
         for mode in (False, True):
@@ -213,12 +215,16 @@ def test_training_step_bf16_mode(lib):
     assert float((out[True][0] - out[False][0]).abs().max()) < 0.05 * float(out[False][0].abs().max()) + 1e-3
     assert abs(out[True][1] - out[False][1]) < 0.05 * abs(out[False][1]) + 1e-3
     assert float((out[True][0] - out[False][0]).abs().max()) > 0              # the tensor-core path really ran
-    n_checked = 0
+    n_checked, dot, n32, nb16 = 0, 0.0, 0.0, 0.0
     for name, g32 in out[False][2].items():
+        gb = out[True][2][name]
+        dot += float((gb.double() * g32.double()).sum())
+        n32 += float(g32.double().pow(2).sum())
+        nb16 += float(gb.double().pow(2).sum())
         if float(g32.norm()) < 1e-6:
             continue
-        gb = out[True][2][name]
         cos = float((gb * g32).sum() / (gb.norm() * g32.norm() + 1e-30))
-        assert cos > 0.95, (name, cos)      # the word table is the deepest, worst-conditioned gradient (0.98)
+        assert cos > 0.98, (name, cos)
         n_checked += 1
     assert n_checked >= 50
+    assert dot / (n32 ** 0.5 * nb16 ** 0.5) > 0.995    # the full gradient vector keeps its direction
