@@ -303,3 +303,61 @@ def test_bf16_mode_metrics(lib, golden_dir):
             cache = util.build_news_cache(model, news)
             res[mode] = util.evaluate_impressions(model, cache, dimp, 32)
     assert np.allclose(res[True], res[False], atol=1e-3), (res[True], res[False])
+
+
+def test_tensor_core_scoring_paths(lib):
+    """Every branch of lime_score_impressions on one impression set: 2-node units (default), 4-node units (tolerance
+    between the two interpolation bounds), all units through the exact-fallback list (tolerance 0), exact kernel
+    only; edge impressions: empty history (uniform attention), one candidate (zero-width node interval), 300
+    candidates (9 units), and operands beyond the fp16 range (flagged for the exact kernel)."""
+    cfg = make_config(vocabulary_size=600, batch_size=32, word_embedding_init="skip")
+    model = L.Model(cfg)
+    model.initialize()
+    synth.synthetic_parameters(model, 9)
+    model = model.to(DEV).eval()
+    news = synth.make_news_table(400, vocabulary_size=600, seed=31)
+    imp = synth.make_impressions(60, news.news_num, seed=32)
+    imp.hist_mask[0, :] = False                                     # empty history
+    imp.hist_news[0, :] = 0
+    imp.hist_mask[1, 1:] = False                                    # a single clicked news
+    edge = [synth.make_impressions(1, news.news_num, cand_fixed=c, seed=40 + c) for c in (1, 2, 300)]
+    def cat(a, b):
+        off = np.concatenate([a.cand_off, b.cand_off[1:] + a.cand_off[-1]])
+        return synth.Impressions(np.concatenate([a.hist_news, b.hist_news]), np.concatenate([a.hist_mask, b.hist_mask]),
+                                 np.concatenate([a.hist_fresh, b.hist_fresh]), np.concatenate([a.hist_life, b.hist_life]), off,
+                                 np.concatenate([a.cand_news, b.cand_news]), np.concatenate([a.cand_fresh, b.cand_fresh]),
+                                 np.concatenate([a.cand_life, b.cand_life]), np.concatenate([a.labels, b.labels]),
+                                 np.concatenate([a.user_id, b.user_id]))
+    for e in edge:
+        imp = cat(imp, e)
+    model.config.use_remaining_lifetime_weighting = False           # every pair un-saturated
+    out, fallback = {}, {}
+    try:
+        with torch.no_grad():
+            cache = util.build_news_cache(model, news)
+            dimp = engine.DeviceImpressions(imp, DEV)
+            for name, (mode, tol) in dict(two=(ops.SCORE_AUTO, 1e-6), four=(ops.SCORE_AUTO, 1e-13), forced=(ops.SCORE_FORCE_FALLBACK, 1e-6),
+                                          exact=(ops.SCORE_EXACT, 1e-6)).items():
+                ops.score_configure(mode, tol)
+                out[name] = util.score_impressions(model, cache, dimp, 32).clone()
+                fallback[name] = int(dimp.work_counter[1])
+            # operands outside the fp16 range: scale one history news' cached vectors beyond 32768
+            big = cache.hist_rows.clone()
+            big[int(imp.hist_news[2, 0]), :400] *= 1e6
+            ops.score_configure(ops.SCORE_AUTO, 1e-6)
+            s_big = model.scoring.score(big, cache.cand_rows, dimp, prefix_main=32).clone()
+            fb_big = int(dimp.work_counter[1])
+            ops.score_configure(ops.SCORE_EXACT, 1e-6)
+            s_big_exact = model.scoring.score(big, cache.cand_rows, dimp, prefix_main=32).clone()
+    finally:
+        ops.score_configure(ops.SCORE_AUTO, 1e-6)
+    ex = out["exact"].cpu().numpy()
+    assert fallback["two"] == 0 and fallback["four"] == 0 and fallback["forced"] == dimp.num_units
+    assert torch.equal(out["forced"], out["exact"])
+    assert rel(out["two"].cpu().numpy(), ex) < 5e-5 and rel(out["four"].cpu().numpy(), ex) < 5e-5
+    assert float((out["two"] - out["four"]).abs().max()) > 0        # the two node counts are different code paths
+    assert fb_big >= 1                                              # flagged, re-scored exactly
+    users = [i for i in range(imp.num_impressions) if int(imp.hist_news[2, 0]) in imp.hist_news[i]]
+    sel = np.concatenate([np.arange(imp.cand_off[i], imp.cand_off[i + 1]) for i in users])
+    assert torch.equal(s_big[sel], s_big_exact[sel])
+    assert np.isfinite(s_big.cpu().numpy()).all()
