@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LIME_B200_ABI_VERSION 2
+#define LIME_B200_ABI_VERSION 3
 
 /* Compile-time model geometry of the LIME-CROWN-CROWN configuration (config.py:54-91 defaults). */
 #define LIME_D        400   /* lime_output_dim == news_embedding_dim == attention_dim          */
@@ -50,11 +50,13 @@ extern "C" {
 #define LIME_CAND_QB   1708
 #define LIME_CAND_TOPIC_ID 1718 /* int32 bit pattern, same id as LIME_HIST_TOPIC_ID                 */
 #define LIME_CAND_NFOLD 1207 /* columns produced by the folded GEMM: w1,w2,w3 + 7 scalars       */
+#define LIME_CAND_ABSMAX 1207 /* max |w1 w2 w3| of the row, written by lime_split_f16_pairs (fp16 operand range check) */
+#define LIME_CAND16_LD 2400 /* fp16 elements per row of cand16 / ctab16: per folded vector k the 400 hi halves, then the 400 lo halves */
 #define LIME_HTAB_LD   800  /* per (freshness bucket, lifetime bucket): [ T | gwT ]            */
 #define LIME_CTAB_LD   1208 /* per bucket pair: [ w1T | w2T | w3T | scalT(8) ]                 */
 /* Tensor-core scoring path (score_tc.cu): history rows per impression, candidates per work unit. */
-#define LIME_TC_MAX_HISTORY 64
-#define LIME_TC_TILE_C      37
+#define LIME_TC_MAX_HISTORY 56
+#define LIME_TC_TILE_C      42
 #define LIME_TOPIC_TAB_LD   12  /* 10 head logits of a (candidate topic, history topic) pair, padded */
 #define LIME_TC_MAX_TOPICS  1024
 
@@ -149,6 +151,9 @@ typedef struct {
     const float *un_prefix;     /* [config.batch_size, LIME_D] prefix sums of lin_l(user_node_embedding) */
     const float *topic_table;   /* [num_topics, num_topics, LIME_TOPIC_TAB_LD] from lime_topic_pair_table,
                                    or NULL (then only the exact kernel can run)                      */
+    const void  *cand16;        /* [news_num, LIME_CAND16_LD] fp16: w1 w2 w3 of cand_rows as hi/lo pairs
+                                   (lime_split_f16_pairs), or NULL (exact kernel only)               */
+    const void  *ctab16;        /* [nb*nb, LIME_CAND16_LD] fp16: the same for cand_tab               */
     int32_t news_num;
     int32_t num_buckets;
     int32_t user_nodes;         /* config.batch_size (rows of user_node_embedding)               */
@@ -158,6 +163,9 @@ typedef struct {
     float   penalty_beta;       /* config.penalty_scaling_beta                                   */
     int32_t use_lifetime_weighting; /* config.use_remaining_lifetime_weighting                   */
     int32_t use_expired_penalty;    /* config.use_expired_penalty                                */
+    float   topic_logit_absmax; /* max |entry| of topic_table (entries are log2(e)-scaled logits): the tensor-core
+                                   path runs its softmax without a max pass and requires this <= 64   */
+    int32_t tc_tables_ok;       /* nonzero: ctab16 holds no value beyond the fp16 operand range      */
 } LimeNewsCache;
 
 typedef struct {
@@ -206,11 +214,19 @@ int lime_score_impressions(const LimeNewsCache *cache, const LimeImpressions *im
 int     lime_score_configure(int32_t mode, float tolerance);
 /* Candidate-aware attention logits depend on the news only through their (category, subCategory)
  * pair (layers.py:66-70 on the 50-d topic representations), so they are tabulated once per checkpoint:
- *   out[(tc * T + th) * LIME_TOPIC_TAB_LD + head] = Q_head(topic tc) . K_head(topic th) / sqrt(D)
+ *   out[(tc * T + th) * LIME_TOPIC_TAB_LD + head] = log2(e) * Q_head(topic tc) . K_head(topic th) / sqrt(D)
  * topics [T, ldt]: topic representation of every distinct topic (50 used columns);
  * tq [T, ldq]: the [50*10 | 10] candidate-role affine image of the same topics (LIME_CAND_TQ block). */
 int     lime_topic_pair_table(const float *topics, int64_t ldt, const float *tq, int64_t ldq, int32_t T,
                               float *out, void *stream);
+/* fp32 -> fp16 hi/lo pairs for the tensor-core scoring path: src [rows, lds] holds `blocks` blocks of
+ * LIME_D columns; dst [rows, blocks * 2 * LIME_D] fp16 receives per block the hi halves then the lo halves
+ * (x = hi + lo to 2^-22).  absmax (may be NULL): absmax[row * ldo] = max |x| of the row (inf for NaN). */
+int     lime_split_f16_pairs(const float *src, int64_t lds, int64_t rows, int32_t blocks, void *dst,
+                             float *absmax, int64_t ldo, void *stream);
+/* Diagnostic: per-phase clock64() totals of the tensor-core scoring kernel since the last call (thread 0 of every CTA;
+ * slots listed in score_tc.cu), host buffer of 16 uint64.  Synchronises the device. */
+int     lime_score_phase_clocks(uint64_t *out16);
 int64_t lime_score_scratch_ints(int32_t num_units);
 /* Work-unit capacity (candidates per unit) to build the unit list with for a given H; 0 = unsupported. */
 int32_t lime_score_tile_c(int32_t max_history);

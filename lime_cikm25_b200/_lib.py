@@ -19,10 +19,11 @@ class LimeNewsCache(C.Structure):
     _fields_ = [
         ("hist_rows", C.c_void_p), ("cand_rows", C.c_void_p), ("hist_tab", C.c_void_p),
         ("cand_tab", C.c_void_p), ("gate_bias", C.c_void_p), ("un_prefix", C.c_void_p),
-        ("topic_table", C.c_void_p),
+        ("topic_table", C.c_void_p), ("cand16", C.c_void_p), ("ctab16", C.c_void_p),
         ("news_num", C.c_int32), ("num_buckets", C.c_int32), ("user_nodes", C.c_int32), ("num_topics", C.c_int32),
         ("tab_gw_absmax", C.c_float), ("sigmoid_alpha", C.c_float), ("penalty_beta", C.c_float),
         ("use_lifetime_weighting", C.c_int32), ("use_expired_penalty", C.c_int32),
+        ("topic_logit_absmax", C.c_float), ("tc_tables_ok", C.c_int32),
     ]
 
 
@@ -62,6 +63,8 @@ PROTOTYPES = {
     "lime_row_absmax": (C.c_int, [P, I64, I64, C.c_int, P, I64, P]),
     "lime_score_impressions": (C.c_int, [C.POINTER(LimeNewsCache), C.POINTER(LimeImpressions), I64, I32,
                                          I64, I32, P, P, P]),
+    "lime_split_f16_pairs": (C.c_int, [P, I64, I64, I32, P, P, I64, P]),
+    "lime_score_phase_clocks": (C.c_int, [P]),
     "lime_score_smem_bytes": (I64, [I32, I32]),
     "lime_score_configure": (C.c_int, [I32, F32]),
     "lime_score_scratch_ints": (I64, [I32]),
@@ -98,7 +101,7 @@ PROTOTYPES = {
     "lime_click_score_bwd": (C.c_int, [P, P, P, P, I64, P, P, P]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 

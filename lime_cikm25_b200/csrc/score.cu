@@ -587,7 +587,8 @@ extern "C" int lime_score_impressions(const LimeNewsCache *cache, const LimeImpr
     cudaStream_t st = as_stream(stream);
 
     const bool tc_ok = g_score_mode != 1 && H <= LIME_TC_MAX_HISTORY && TC <= LIME_TC_TILE_C &&
-                       cache->topic_table != nullptr && cache->num_topics >= 1;
+                       cache->topic_table != nullptr && cache->num_topics >= 1 && cache->cand16 != nullptr &&
+                       cache->ctab16 != nullptr && cache->tc_tables_ok != 0 && cache->topic_logit_absmax <= 64.0f;
     if (!tc_ok) return launch_score_exact(a, imp->num_units, st);
 
     // fast path: interpolated gate + tcgen05 dots; units whose error bound exceeds the tolerance are

@@ -1,4 +1,4 @@
-// Stage B on the tensor cores: impression scoring for H <= 64 history rows (sm_100a, tcgen05 + TMEM).
+// Stage B on the tensor cores: impression scoring for H <= 56 history rows (sm_100a, tcgen05 + TMEM).
 //
 // Same arithmetic as score.cu (see its header for the algebra and the reference lines), restructured so
 // that the 400-wide gate sigmoid is no longer evaluated per (candidate, history row):
@@ -6,30 +6,36 @@
 //   o_h(a) = v_h * (1 - (1 - a) * sigmoid(a * W_g v_h + b_g))       depends on the candidate only through
 //                                                                     the scalar attention weight a = a[c][h].
 //   Over the <= 42 candidates of a work unit, a[.][h] spans an interval [mid_h - w_h, mid_h + w_h].  o_h is
-//   analytic in a, so it is evaluated EXACTLY at the 4 Chebyshev nodes a_j of that interval and every
+//   analytic in a, so it is evaluated EXACTLY at 2 (or 4) Chebyshev nodes a_j of that interval and every
 //   candidate interpolates:  o_h(a[c][h]) = sum_j L_j(t) o_h(a_j),  t = (a[c][h] - mid_h) / w_h.
 //   The reductions a pair needs are linear in o (dots with the candidate's 3 folded vectors, sum o) or are
 //   scalar functions of a (sum o^2), so they interpolate the same way:
-//       D_k[c][h] = sum_j L_j(t) * ( O[4h+j][:] . w_k[c][:] ),    O = [o_h(a_j)]  (4H x 400),  k = 1..3
-//   and O . W^T  (4H x 400) x (400 x 3C) is ONE GEMM per work unit -> tcgen05.mma.
-//   Interpolation error of the gate for 4 Chebyshev nodes:  <= w^4 (0.125 g^4 + 0.5 |g|^3) / 192  with
-//   g = max_d |W_g v_h|  (4th derivative of (1-a) sigmoid(g a + b)); a unit where this exceeds the tolerance
-//   (default 1e-6, i.e. below the 2^-22 of the ex2.approx the exact kernel uses) is appended to a
-//   device-side list and re-scored by the exact kernel.  fp32 fidelity of the dots: both GEMM operands are
-//   split x = hi + lo into two fp16 (11 + 11 significant bits) and D += Ahi Bhi + Ahi Blo + Alo Bhi with fp32
-//   accumulation in TMEM (relative error ~2^-21 per product, the level of an fp32 FMA chain; a bf16 pair,
-//   2^-17, measurably is not enough: 6e-5 on the logits).  Units holding a value beyond the fp16 range are
-//   flagged for the exact kernel as well.
+//       D_k[c][h] = sum_j L_j(t) * ( w_k[c][:] . O[nodes*h + j][:] ),   O = [o_h(a_j)],  k = 1..3
+//   and  W . O^T  (3C x 400) x (400 x nodes*H)  is ONE GEMM per work unit -> tcgen05.mma.
+//   Interpolation error of the gate:  2 nodes  w^2 (0.0962 g^2 + 0.5 |g|) / 4,   4 nodes
+//   w^4 (0.125 g^4 + 0.5 |g|^3) / 192,  g = max_d |W_g v_h|; a unit where even 4 nodes exceed the tolerance
+//   (default 1e-6, below the 2^-22 of the ex2.approx the exact kernel uses) is appended to a device-side
+//   list and re-scored by the exact kernel.  fp32 fidelity of the dots: both GEMM operands are fp16 hi + lo
+//   pairs (11 + 11 significant bits), D += Whi Ohi + Whi Olo + Wlo Ohi with fp32 accumulation in TMEM.
 //
-// CTA = 8 compute warps + 1 MMA-issuer warp, persistent, TWO per SM (110 KB of shared memory and 256 TMEM
-// columns each) so that one CTA's latency-bound phases overlap the other's math; work units as in score.cu.
-// Per unit:  phase 0 metadata / bucketize / L2 prefetch of the unit's cache rows -> phase 1 topic attention
-//   a[c][h]: head logits gathered from the (candidate topic, history topic) table, softmaxes in registers ->
-//   nodes -> 13 K-chunks of 32 dims: compute warps write the swizzled fp16 hi/lo operand tiles of
-//   O (256 rows) and W (<=112 rows); the two 32-dim halves of the 64-dim SWIZZLE_128B tile act as a 2-stage
-//   ring (mbarrier full/free) so the issuer warp runs chunk k's MMAs while chunk k+1 is produced ->
-//   epilogue: TMEM -> registers, Lagrange combination over the 4 lanes of a quad, LayerNorm folding ->
-//   phase 3 pooling softmax + GraphSAGE mean + lifetime weight.
+// What changed against the first tensor-core version (round 1c, 19.2 ms per bench step):
+//   * history rows are DEDUPLICATED per unit: slots with the same (news, bucket pair, mask) -- in practice
+//     the padding of a short history, dataset.py:123-128 -- are one operand row with a multiplicity that
+//     enters the two softmaxes, the pooling and the GraphSAGE mean.  H = 50 slots -> ~26 rows on average.
+//   * the candidate side is the M operand (TMEM lanes) and is NOT produced by compute threads any more: the
+//     cache holds every folded candidate vector already split into fp16 hi / lo (cand16, ctab16), a loader
+//     warp streams the rows with cp.async straight into the swizzled operand tile; the bucket-pair part
+//     is a second K range (K = 400 news + 400 table) instead of a register add + split.
+//   * the history side is the N operand: N = nodes * rows <= 112, so the MMA work follows the deduplicated
+//     row count; the epilogue thread owns a (candidate, k) lane and walks the columns -- the Lagrange
+//     combination is in-thread (no shuffles), lg / y / z lanes are warp-uniform.
+//   * candidate-aware attention: 8 lanes per candidate, head logits pre-scaled by log2(e), no max pass
+//     (the table's |logit| bound is checked by the host), multiplicity-weighted sums.
+//
+// CTA = 8 compute warps + 1 MMA-issuer warp + 1 loader warp, persistent, TWO per SM (113 KB of shared
+// memory and 128 TMEM columns each).  Per unit: metadata + dedup -> attention a[c][u] -> nodes ->
+// 13 K-stages of 32 dims (the two 32-dim halves of the 64-dim SWIZZLE_128B tile are a 2-stage ring with
+// full/free mbarriers) -> epilogue TMEM -> lg / y / z -> pooling softmax + GraphSAGE mean + lifetime weight.
 #include "score_common.cuh"
 #include <cuda_fp16.h>
 
@@ -39,54 +45,87 @@ namespace lime {
 namespace {
 
 constexpr int kD = LIME_D;
-constexpr int kWarps = 8;                       // compute warps; warp 8 issues the MMAs
-constexpr int kCompute = kWarps * 32;
+constexpr int kCWarps = 7;                      // compute warps (8 warps per CTA -> 4 per SM sub-partition at two CTAs per SM: 128 registers, no spills)
+constexpr int kCompute = kCWarps * 32;
+constexpr int kMmaWarp = kCWarps;               // warp 7 issues the MMAs
+constexpr int kRPT = kCompute / 8;              // operand rows produced per pass by one task slot (8 threads per row): 28
 constexpr int kThreads = kCompute + 32;
-constexpr int kRows = LIME_TC_MAX_HISTORY;      // history rows per unit -> 4 * 64 = 256 operand rows
-constexpr int kTile = LIME_TC_TILE_C;           // candidates per unit -> 3 * 37 = 111 <= 112 MMA columns
-constexpr int kNMax = 112;
-constexpr int kChunks = 13;                     // 32-wide K chunks over D = 400 (the last holds 16 dims)
-constexpr int kABytes = 256 * 128;              // one 64-dim operand image of O (hi or lo)
-constexpr int kBBytes = kNMax * 128;            // one 64-dim operand image of W (hi or lo)
-constexpr int kTileBytes = 2 * kABytes + 2 * kBBytes;
+constexpr int kH = LIME_TC_MAX_HISTORY;         // 56 history slots at most
+constexpr int kTile = LIME_TC_TILE_C;           // 42 candidates per unit -> 126 of the 128 M rows
+constexpr int kQ3 = kTile - 32;                 // candidates living in TMEM quadrant 3
+constexpr int kBRows = 112;                     // N rows of the O operand: nodes * unique rows of a pass
+constexpr int kStages = 13;                     // 32-wide K stages over D = 400 (the last holds 16 dims)
+constexpr int kAImg = 128 * 128;                // one 64-dim image of the candidate operand (hi or lo)
+constexpr int kBImg = kBRows * 128;
 constexpr int kTabLd = LIME_TOPIC_TAB_LD;
+constexpr int kAS = kTile;                      // row stride of a_s / lg / y / z  ([u][c])
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kHalfSafe = 32768.0f;           // operands beyond this are not split into fp16 pairs
+constexpr float kS1Max = 1073741824.0f;         // sum o^2 <= 2^30  =>  every |o| <= 32768 (fp16 operand range)
+constexpr int kC16 = LIME_CAND16_LD;            // fp16 elements per cand16 / ctab16 row: [k][hi | lo][400]
 
 // shared-memory map (bytes from the 1024-aligned base)
-constexpr int OFF_AHI = 0, OFF_ALO = kABytes, OFF_BHI = 2 * kABytes, OFF_BLO = 2 * kABytes + kBBytes;
-constexpr int OFF_LG = 0;                                     // alias (after the MMAs): lg / y / z [37][64]
-constexpr int OFF_Y = OFF_LG + kTile * kRows * 4;
-constexpr int OFF_Z = OFF_Y + kTile * kRows * 4;
-constexpr int OFF_A = kTileBytes;                             // a[c][h]  [37][64]
-constexpr int OFF_BIAS = OFF_A + kTile * kRows * 4;           // gate bias' [400]
-constexpr int OFF_S01 = OFF_BIAS + kD * 4;                    // node sums [64][4][2]
-constexpr int OFF_MID = OFF_S01 + kRows * 8 * 4;
-constexpr int OFF_WINV = OFF_MID + kRows * 4;
-constexpr int OFF_WHALF = OFF_WINV + kRows * 4;
-constexpr int OFF_GMAX = OFF_WHALF + kRows * 4;
-constexpr int OFF_CSCAL = OFF_GMAX + kRows * 4;               // [37][8]
-constexpr int OFF_CW = OFF_CSCAL + kTile * 8 * 4;
-constexpr int OFF_CNEWS = OFF_CW + 160;
-constexpr int OFF_CTAB = OFF_CNEWS + 160;
-constexpr int OFF_CP = OFF_CTAB + 160;
-constexpr int OFF_CTOPIC = OFF_CP + 160;
-constexpr int OFF_HNEWS = OFF_CTOPIC + 160;
-constexpr int OFF_HTAB = OFF_HNEWS + kRows * 4;
-constexpr int OFF_HMASK = OFF_HTAB + kRows * 4;
-constexpr int OFF_HTOPIC = OFF_HMASK + kRows * 4;
-constexpr int OFF_BARS = OFF_HTOPIC + kRows * 4;              // full[2] free[2] accum
-constexpr int OFF_MISC = OFF_BARS + 64;                       // tmem slot, unit broadcast, flag
-constexpr int kSmemBytes = OFF_MISC + 64 + 1024;
-static_assert(OFF_Z + kTile * kRows * 4 <= 2 * kABytes, "epilogue alias overflows the O operand images");
+constexpr int OFF_A = 0;                                      // 4 images: news hi, news lo, table hi, table lo
+constexpr int OFF_BHI = 4 * kAImg, OFF_BLO = OFF_BHI + kBImg;
+constexpr int OFF_OUT = OFF_BHI;                              // alias (after the MMAs): lg / y / z [56][42]
+constexpr int OFF_AS = OFF_BLO + kBImg;                       // a[u][c]
+constexpr int OFF_BIAS = OFF_AS + kH * kAS * 4;               // gate bias' [400]
+constexpr int OFF_S01 = OFF_BIAS + kD * 4;                    // node sums [56][8]; phase-0 scratch aliases it
+constexpr int OFF_MID = OFF_S01 + kH * 8 * 4;
+constexpr int OFF_WINV = OFF_MID + kH * 4;
+constexpr int OFF_WHALF = OFF_WINV + kH * 4;
+constexpr int OFF_CSCAL = OFF_WHALF + kH * 4;                 // [42][4]  B1 B2 B3 cb
+constexpr int OFF_POOL = OFF_CSCAL + kTile * 16;              // [42][4]  running m, l, acc, ms
+constexpr int kCArr = 48 * 4;
+constexpr int OFF_CW = OFF_POOL + kTile * 16;
+constexpr int OFF_CNEWS = OFF_CW + kCArr;
+constexpr int OFF_CTAB = OFF_CNEWS + kCArr;
+constexpr int OFF_CP = OFF_CTAB + kCArr;
+constexpr int OFF_CTOPIC = OFF_CP + kCArr;
+constexpr int kUArr = kH * 4;
+constexpr int OFF_UNEWS = OFF_CTOPIC + kCArr;
+constexpr int OFF_UTAB = OFF_UNEWS + kUArr;
+constexpr int OFF_UMASK = OFF_UTAB + kUArr;
+constexpr int OFF_UTOPIC = OFF_UMASK + kUArr;
+constexpr int OFF_UMULT = OFF_UTOPIC + kUArr;                 // float multiplicity
+constexpr int OFF_UMP0 = OFF_UMULT + kUArr;                   // float multiplicity inside the GraphSAGE prefix (main)
+constexpr int OFF_UMP1 = OFF_UMP0 + kUArr;                    // ... (tail batch)
+constexpr int OFF_UGABS = OFF_UMP1 + kUArr;
+constexpr int OFF_UFIRST = OFF_UGABS + kUArr;                 // history slot of the unique row
+constexpr int OFF_BARS = OFF_UFIRST + kUArr;                  // fullA[2] fullB[2] free[2] accum
+constexpr int OFF_MISC = OFF_BARS + 64;                       // tmem slot, unit ids, flags, U, ...
+constexpr int OFF_PROF = OFF_MISC + 64;                       // phase clocks of thread 0 (diagnostic)
+constexpr int OFF_ROWOFF = OFF_PROF + 128;                    // loader: element offsets of the 128 M rows (news, table)
+constexpr int kSmemBytes = OFF_ROWOFF + 1024 + 1024;
+// phase-0 scratch inside the node-sum area
+constexpr int OFF_HKN = OFF_S01, OFF_HKT = OFF_HKN + kH * 4, OFF_HKM = OFF_HKT + kH * 4, OFF_HFIRST = OFF_HKM + kH * 4;
+static_assert(OFF_HFIRST + kH * 4 <= OFF_MID, "phase-0 scratch overflows the node-sum area");
+static_assert(3 * kH * kAS * 4 <= 2 * kBImg, "epilogue alias overflows the O operand images");
 static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
-static_assert(3 * kTile * 4 <= 2 * kCompute, "candidate operand: at most 2 staging tasks per compute thread");
-static_assert(OFF_BARS % 8 == 0 && OFF_A % 16 == 0 && OFF_BIAS % 16 == 0 && OFF_BLO % 1024 == 0, "alignment");
+static_assert(3 * kTile <= 128 && kTile <= 48 && kTile >= 32, "candidate rows: 32 per k in TMEM quadrants 0-2, the rest in quadrant 3");
+static_assert(3 * kQ3 <= 32, "quadrant 3 holds (tile - 32) candidates x 3");
+static_assert(OFF_BARS % 8 == 0 && OFF_AS % 16 == 0 && OFF_BIAS % 16 == 0 && OFF_S01 % 16 == 0 && OFF_BHI % 1024 == 0 && OFF_BLO % 1024 == 0, "alignment");
+static_assert(2 * kH <= kBRows && kBRows % 16 == 0 && kBRows <= 128 && kH % 8 == 0 && kH <= 64, "N operand");
+
+// misc ints
+enum { M_TMEM = 0, M_UNIT = 2, M_NEXT = 3, M_FLAGS = 4, M_U = 5, M_NUN = 6, M_NODES = 7, M_NPASS = 8, M_WC0 = 9, M_WC1 = 10, M_NPAD = 11 };
 
 // Chebyshev nodes on [-1, 1]: 4-node and 2-node sets
 constexpr float kX0 = -0.92387953251128674f, kX1 = -0.38268343236508977f;
 constexpr float kX2 = 0.38268343236508977f, kX3 = 0.92387953251128674f;
 constexpr float kY0 = -0.70710678118654752f, kY1 = 0.70710678118654752f;
+
+// Phase timing (diagnostic): thread 0 of every CTA accumulates clock64() deltas per phase; lime_score_phase_clocks reads
+// and clears the totals.  Slots: 0 metadata, 1 dedup, 2 attention, 3 nodes, 4 operand production (incl. ring waits),
+// 5 wait for the last MMA, 6 epilogue, 7 pooling, 8 final score, 9 units, 10 barrier at the end of production.
+__device__ unsigned long long g_phase_clocks[16];
+#define LIME_TICK(slot)                                                  \
+    do {                                                                 \
+        if (tid == 0) {                                                  \
+            const long long now__ = clock64();                           \
+            prof[slot] += (unsigned long long)(now__ - t_last);          \
+            t_last = now__;                                              \
+        }                                                                \
+    } while (0)
 
 template <int NODES> __device__ __forceinline__ float node_x(int j) {
     if (NODES == 2) return j == 0 ? kY0 : kY1;
@@ -94,222 +133,383 @@ template <int NODES> __device__ __forceinline__ float node_x(int j) {
 }
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// arrive on the mbarrier once every cp.async issued so far by this thread has completed (counts as one arrival)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(kCompute) : "memory"); }
 
-// 8 fp32 -> 8 fp16 hi + 8 fp16 lo (x = hi + lo to 2^-22: 11 + 11 significant bits), as two 16-byte
-// chunks; returns max |x| so the caller can flag values outside the fp16 range
-__device__ __forceinline__ float split8(const float (&x)[8], uint4 &hi, uint4 &lo) {
-    uint32_t h[4], l[4];
-    float mx = 0.0f;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const __half2 hh = __floats2half2_rn(x[2 * p], x[2 * p + 1]);
-        const float2 hf = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(x[2 * p] - hf.x, x[2 * p + 1] - hf.y);
-        h[p] = *reinterpret_cast<const uint32_t *>(&hh);
-        l[p] = *reinterpret_cast<const uint32_t *>(&ll);
-        mx = fmaxf(mx, fmaxf(fabsf(x[2 * p]), fabsf(x[2 * p + 1])));
+// (candidate, folded vector k) of M row 32 * quadrant + lane (= TMEM lane): k = 0..2 fill quadrants 0..2 for
+// c < 32, the remaining candidates share quadrant 3; c = kTile marks an unused row
+__device__ __forceinline__ void m_row_owner(int quadrant, int lane, int &c, int &k) {
+    if (quadrant < 3) {
+        c = lane;
+        k = quadrant;
+    } else {
+        k = lane / kQ3;
+        c = 32 + lane - k * kQ3;
+        if (k > 2) {
+            k = 2;
+            c = kTile;
+        }
     }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-    return mx;
 }
 
-// Operand production for one work unit: NODES rows of O per history row (fp16 hi / lo images, K chunks of
-// 32 dims through the two halves of the 64-dim tile) and the folded vectors of the candidates; also the node
-// sums (sum o, sum o^2).  Executed by the 256 compute threads; unit_iter (units done by this CTA) gives the
-// mbarrier phases: the two half-tiles are staged 7 and 6 times per unit.
-template <int NODES>
-__device__ __forceinline__ void produce_operands(unsigned char *base, const LimeNewsCache &C, int H, int cnt, int tid,
-                                                 const int *hnews, const int *htab, const int *cnews, const int *ctab,
-                                                 const float *mid_s, const float *whalf_s, const float *bias_s,
-                                                 float *s01_s, int *flag_s, uint64_t *bar_full, uint64_t *bar_free,
-                                                 uint32_t unit_iter) {
-    const int hr = tid >> 2, q = tid & 3;
-    const bool row_ok = hr < H;
-    const float mid = row_ok ? mid_s[hr] : 0.0f, wh = row_ok ? whalf_s[hr] : 0.0f;
-    float aj[NODES];
+// 4 fp32 -> 4 fp16 hi + 4 fp16 lo (x = hi + lo to 2^-22: 11 + 11 significant bits)
+__device__ __forceinline__ void split4(const float (&x)[4], uint2 &hi, uint2 &lo) {
+    const __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(x[0] - f0.x, x[1] - f0.y), l1 = __floats2half2_rn(x[2] - f1.x, x[3] - f1.y);
+    hi = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+    lo = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+}
+
+// Operand production of one pass: NODES rows of O per unique history row u0 <= u < u0 + nrows (fp16 hi / lo
+// images, K stages of 32 dims through the two halves of the 64-dim tile) and the node sums (sum o, sum o^2).
+// Executed by the 256 compute threads; a thread owns 4 dims of a row per stage (8 threads per row) and, when
+// the pass holds more than 28 rows, the same dims of row + 28.  use0/use1 count the uses of the two ring
+// halves over the kernel's lifetime (mbarrier phases).
+template <int NODES, int TPT>
+__device__ __forceinline__ void produce_operands(unsigned char *base, const LimeNewsCache &C, int u0, int nrows, int tid,
+                                                 const int *unews, const int *utab, const float *mid_s,
+                                                 const float *whalf_s, const float *bias_s, float *s01_s, int *flag_s,
+                                                 const uint32_t *rowoff_s, const __half *cand16, const __half *ctab16,
+                                                 uint64_t *bar_full, uint64_t *bar_free, uint32_t &use0, uint32_t &use1) {
+    const int sub = tid & 7;
+    // candidate operand (M side): warp w streams the row groups 2w and 2w + 1 of every stage with cp.async -- lane =
+    // (row in group, 16-byte chunk), so one instruction moves the 64 contiguous bytes of a stage for 8 operand rows
+    const int a_rsub = (tid >> 2) & 7, a_ch = tid & 3, a_g0 = tid >> 5;      // row groups a_g0 + 7 i (i < 3) of 8 rows each
+    uint32_t a_on[3], a_ot[3];
 #pragma unroll
-    for (int j = 0; j < NODES; ++j) aj[j] = fmaf(wh, node_x<NODES>(j), mid);
-    const float *hrow = C.hist_rows + (size_t)(row_ok ? hnews[hr] : 0) * LIME_HIST_LD;
-    const float *trow = C.hist_tab + (size_t)(row_ok ? htab[hr] : 0) * LIME_HTAB_LD;
-    float ps[2 * NODES];
+    for (int i = 0; i < 3; ++i) {
+        const int g = a_g0 + kCWarps * i;
+        a_on[i] = g < 16 ? rowoff_s[8 * g + a_rsub] : 0xffffffffu;
+        a_ot[i] = g < 16 ? rowoff_s[128 + 8 * g + a_rsub] : 0u;
+    }
+    const uint32_t a_dst = tc::smem_u32(base) + OFF_A + (uint32_t)a_g0 * 1024u + (uint32_t)a_rsub * 128u;
+    bool ok[TPT];
+    const float *hrow[TPT], *trow[TPT];
+    float aj[TPT][NODES], ps[TPT][2 * NODES];
 #pragma unroll
-    for (int i = 0; i < 2 * NODES; ++i) ps[i] = 0.0f;
-    float xmax = 0.0f;
-    const int btasks = 3 * cnt * 4;
-    for (int kc = 0; kc < kChunks; ++kc) {
+    for (int t = 0; t < TPT; ++t) {
+        const int ul = (tid >> 3) + kRPT * t;
+        ok[t] = ul < nrows;
+        const int u = u0 + (ok[t] ? ul : 0);
+        const float mid = mid_s[u], wh = whalf_s[u];
+#pragma unroll
+        for (int j = 0; j < NODES; ++j) aj[t][j] = fmaf(wh, node_x<NODES>(j), mid);
+        hrow[t] = C.hist_rows + (size_t)unews[u] * LIME_HIST_LD;
+        trow[t] = C.hist_tab + (size_t)utab[u] * LIME_HTAB_LD;
+#pragma unroll
+        for (int i = 0; i < 2 * NODES; ++i) ps[t][i] = 0.0f;
+    }
+    // one row per thread: stage kc + 1's global loads are in flight while stage kc is evaluated (two rows per
+    // thread: no register room for that, the two rows overlap each other's latency instead)
+    constexpr bool kPipe = true;
+    float4 nx[TPT][4];
+#pragma unroll
+    for (int t = 0; t < TPT; ++t) {
+        if (!kPipe) break;
+        const int d0 = 4 * sub;
+        nx[t][0] = ldg4(hrow[t] + LIME_HIST_VC + d0);
+        nx[t][1] = ldg4(trow[t] + d0);
+        nx[t][2] = ldg4(hrow[t] + LIME_HIST_GW + d0);
+        nx[t][3] = ldg4(trow[t] + kD + d0);
+    }
+    for (int kc = 0; kc < kStages; ++kc) {
         const int s = kc & 1;
-        const uint32_t u = unit_iter * (s ? 6u : 7u) + (uint32_t)(kc >> 1);   // uses of this half so far
-        if (u >= 1) tc::mbar_wait(bar_free + s, (u - 1) & 1u);
-        const int d0 = 32 * kc + 8 * q;
-        const int lq = 4 * s + q;                  // 16-byte chunk inside the 128-byte tile row
-        if (row_ok && d0 < kD) {
-            float v[8], gg[8];
-            {
-                const float4 a0 = ldg4(hrow + LIME_HIST_VC + d0), a1 = ldg4(hrow + LIME_HIST_VC + d0 + 4);
-                const float4 b0 = ldg4(trow + d0), b1 = ldg4(trow + d0 + 4);
-                const float4 c0 = ldg4(hrow + LIME_HIST_GW + d0), c1 = ldg4(hrow + LIME_HIST_GW + d0 + 4);
-                const float4 e0 = ldg4(trow + kD + d0), e1 = ldg4(trow + kD + d0 + 4);
-                v[0] = a0.x + b0.x; v[1] = a0.y + b0.y; v[2] = a0.z + b0.z; v[3] = a0.w + b0.w;
-                v[4] = a1.x + b1.x; v[5] = a1.y + b1.y; v[6] = a1.z + b1.z; v[7] = a1.w + b1.w;
-                gg[0] = c0.x + e0.x; gg[1] = c0.y + e0.y; gg[2] = c0.z + e0.z; gg[3] = c0.w + e0.w;
-                gg[4] = c1.x + e1.x; gg[5] = c1.y + e1.y; gg[6] = c1.z + e1.z; gg[7] = c1.w + e1.w;
-            }
-            const float4 bb0 = *reinterpret_cast<const float4 *>(bias_s + d0);
-            const float4 bb1 = *reinterpret_cast<const float4 *>(bias_s + d0 + 4);
-            const float bb[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
+        const int d0 = 32 * kc + 4 * sub;
+        float v[TPT][4], gg[TPT][4];
+        if (!kPipe && d0 < kD) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) xmax = fmaxf(xmax, fabsf(v[e]));   // |o| <= |v|: one range check per element
-#pragma unroll
-            for (int j = 0; j < NODES; ++j) {
-                // o = v (1 - (1 - a_j) sigmoid(a_j W_g v + b_g)),  sigmoid(z) = 1 / (1 + 2^z'),  z' = -log2(e) z
-                const float a = aj[j], oma = 1.0f - a;
-                float o[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float den = ex2_approx(fmaf(a, gg[e], bb[e])) + 1.0f;
-                    o[e] = fmaf(-(v[e] * oma), rcp_approx(den), v[e]);
-                    ps[2 * j] += o[e];
-                    ps[2 * j + 1] = fmaf(o[e], o[e], ps[2 * j + 1]);
-                }
-                uint4 hi, lo;
-                split8(o, hi, lo);
-                const uint32_t off = tc::sw128_offset(NODES * hr + j, lq);
-                *reinterpret_cast<uint4 *>(base + OFF_AHI + off) = hi;
-                *reinterpret_cast<uint4 *>(base + OFF_ALO + off) = lo;
+            for (int t = 0; t < TPT; ++t) {
+                nx[t][0] = ldg4(hrow[t] + LIME_HIST_VC + d0);
+                nx[t][1] = ldg4(trow[t] + d0);
+                nx[t][2] = ldg4(hrow[t] + LIME_HIST_GW + d0);
+                nx[t][3] = ldg4(trow[t] + kD + d0);
             }
         }
-        for (int task = tid; task < btasks; task += kCompute) {
-            const int n = task >> 2, qq = task & 3;
-            const int d1 = 32 * kc + 8 * qq;
-            if (d1 >= kD) continue;
-            const int c = n / 3, k = n - 3 * c;
-            const float *cr = C.cand_rows + (size_t)cnews[c] * LIME_CAND_LD + k * kD + d1;
-            const float *ct = C.cand_tab + (size_t)ctab[c] * LIME_CTAB_LD + k * kD + d1;
-            const float4 a0 = ldg4(cr), a1 = ldg4(cr + 4), b0 = ldg4(ct), b1 = ldg4(ct + 4);
-            const float x[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w,
-                                a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
-            uint4 hi, lo;
-            xmax = fmaxf(xmax, split8(x, hi, lo));
-            const uint32_t off = tc::sw128_offset(n, 4 * s + qq);
-            *reinterpret_cast<uint4 *>(base + OFF_BHI + off) = hi;
-            *reinterpret_cast<uint4 *>(base + OFF_BLO + off) = lo;
+#pragma unroll
+        for (int t = 0; t < TPT; ++t) {
+            v[t][0] = nx[t][0].x + nx[t][1].x; v[t][1] = nx[t][0].y + nx[t][1].y;
+            v[t][2] = nx[t][0].z + nx[t][1].z; v[t][3] = nx[t][0].w + nx[t][1].w;
+            gg[t][0] = nx[t][2].x + nx[t][3].x; gg[t][1] = nx[t][2].y + nx[t][3].y;
+            gg[t][2] = nx[t][2].z + nx[t][3].z; gg[t][3] = nx[t][2].w + nx[t][3].w;
+        }
+        if (kPipe && d0 + 32 < kD) {
+#pragma unroll
+            for (int t = 0; t < TPT; ++t) {
+                nx[t][0] = ldg4(hrow[t] + LIME_HIST_VC + d0 + 32);
+                nx[t][1] = ldg4(trow[t] + d0 + 32);
+                nx[t][2] = ldg4(hrow[t] + LIME_HIST_GW + d0 + 32);
+                nx[t][3] = ldg4(trow[t] + kD + d0 + 32);
+            }
+        }
+        const uint32_t uses = s ? use1 : use0;
+        if (uses >= 1) tc::mbar_wait(bar_free + s, (uses - 1) & 1u);
+        if (kc < kStages - 1 || a_ch < (kD - 32 * (kStages - 1)) / 8) {
+            const uint32_t dst = a_dst + (uint32_t)(((4 * s + a_ch) ^ a_rsub) << 4);
+            const int eo = 32 * kc + 8 * a_ch;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                if (a_on[i] != 0xffffffffu) {
+                    const uint32_t di = dst + (uint32_t)(kCWarps * i) * 1024u;
+                    cp_async16(di, cand16 + a_on[i] + eo);
+                    cp_async16(di + kAImg, cand16 + a_on[i] + kD + eo);
+                    cp_async16(di + 2 * kAImg, ctab16 + a_ot[i] + eo);
+                    cp_async16(di + 3 * kAImg, ctab16 + a_ot[i] + kD + eo);
+                }
+            }
+        }
+        cp_async_mbar_arrive_noinc(bar_full + s);      // arrives when this thread's copies have landed
+        if (d0 < kD) {
+            const float4 bb4 = *reinterpret_cast<const float4 *>(bias_s + d0);
+            const float bb[4] = {bb4.x, bb4.y, bb4.z, bb4.w};
+#pragma unroll
+            for (int t = 0; t < TPT; ++t) {
+                if (ok[t]) {
+                    const int nrow0 = NODES * ((tid >> 3) + kRPT * t);
+#pragma unroll
+                    for (int j = 0; j < NODES; ++j) {
+                        // o = v (1 - (1 - a_j) sigmoid(a_j W_g v + b_g)),  sigmoid(z) = 1 / (1 + 2^z'),  z' = -log2(e) z
+                        const float a = aj[t][j], oma = 1.0f - a;
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float den = ex2_approx(fmaf(a, gg[t][e], bb[e])) + 1.0f;
+                            o[e] = fmaf(-(v[t][e] * oma), rcp_approx(den), v[t][e]);
+                            ps[t][2 * j] += o[e];
+                            ps[t][2 * j + 1] = fmaf(o[e], o[e], ps[t][2 * j + 1]);
+                        }
+                        uint2 hi, lo;
+                        split4(o, hi, lo);
+                        const uint32_t off = tc::sw128_offset(nrow0 + j, 4 * s + (sub >> 1)) + 8u * (sub & 1);
+                        *reinterpret_cast<uint2 *>(base + OFF_BHI + off) = hi;
+                        *reinterpret_cast<uint2 *>(base + OFF_BLO + off) = lo;
+                    }
+                }
+            }
         }
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(bar_full + s);
+        if (s) ++use1; else ++use0;
     }
-    // node sums of the row: sum o, sum o^2 per node, over the 4 lanes that share the row
+    // node sums of the row: sum o, sum o^2 per node, over the 8 lanes that share the row
 #pragma unroll
-    for (int o = 1; o < 4; o <<= 1) {
+    for (int t = 0; t < TPT; ++t) {
 #pragma unroll
-        for (int i = 0; i < 2 * NODES; ++i) ps[i] += __shfl_xor_sync(0xffffffffu, ps[i], o);
-    }
-    if (!(xmax <= kHalfSafe)) atomicOr(flag_s, 4);   // outside the fp16 operand range (or NaN): exact kernel
-    if (row_ok && q == 0) {
+        for (int o = 1; o < 8; o <<= 1) {
 #pragma unroll
-        for (int i = 0; i < 2 * NODES; ++i) s01_s[hr * 8 + i] = ps[i];
+            for (int i = 0; i < 2 * NODES; ++i) ps[t][i] += __shfl_xor_sync(0xffffffffu, ps[t][i], o);
+        }
+        if (ok[t] && sub == 0) {
+            const int u = u0 + (tid >> 3) + kRPT * t;
+            bool in_range = true;
+#pragma unroll
+            for (int j = 0; j < NODES; ++j) {
+                s01_s[u * 8 + 2 * j] = ps[t][2 * j];
+                s01_s[u * 8 + 2 * j + 1] = ps[t][2 * j + 1];
+                in_range = in_range && (ps[t][2 * j + 1] <= kS1Max);
+            }
+            if (!in_range) atomicOr(flag_s, 4);   // outside the fp16 operand range (or NaN): exact kernel
+        }
     }
 }
 
-// Epilogue of one work unit: every compute thread owns one accumulator row (TMEM lane) = one (history row,
-// node); the NODES lanes of a row combine their dots with the Lagrange weights of each candidate, lane j = 0
-// folds the LayerNorm and writes lg / y / z.
+// Epilogue of one pass: a compute thread owns one accumulator row (TMEM lane) = one (candidate, k) and walks
+// the columns (unique history row, node) of the pass; warps w and w + 4 share a TMEM quadrant and alternate
+// over the 16-column blocks (quadrant 3, the candidates beyond 32, has warp 3 alone).  Writes out[k][u][c]  (k = 0: pooling logit, 1: pooled value, 2: GraphSAGE term).
 template <int NODES>
-__device__ __forceinline__ void epilogue(uint32_t tmem, int warp, int lane, int H, int cnt, int mtiles, float ln_eps,
+__device__ __forceinline__ void epilogue(uint32_t tmem, int warp, int lane, int u0, int nrows, int cnt, float ln_eps,
                                          const float *a_s, const float *mid_s, const float *winv_s, const float *s01_s,
-                                         const float *cscal, float *lg_s, float *y_s, float *z_s) {
+                                         const float *cscal, float *out_s) {
+    constexpr int UPB = 16 / NODES;               // unique rows per 16-column block
     const int qd = warp & 3;
-    const int mt = NODES == 2 ? 0 : warp >> 2;               // 2 nodes: one 128-row tile, warps 4-7 take the odd
-    const int cg0 = NODES == 2 ? warp >> 2 : 0, cgs = NODES == 2 ? 2 : 1;   // groups of 16 candidates
-    if (mt < mtiles) {
-        const int r = 128 * mt + 32 * qd + lane;
-        const int hr = r / NODES, j = r % NODES;
-        const bool row_ok = hr < H;
-        const int hc = row_ok ? hr : 0;
-        const float mid = mid_s[hc], winv = winv_s[hc];
-        const float s0n = row_ok ? s01_s[hc * 8 + 2 * j] : 0.0f, s1n = row_ok ? s01_s[hc * 8 + 2 * j + 1] : 0.0f;
-        // L_j(t) = prod_{m != j} (t - x_m) / (x_j - x_m); with 2 nodes there is a single factor
-        float xa, xb = 0.0f, xc = 0.0f, invden;
-        if (NODES == 2) {
-            xa = j == 0 ? kY1 : kY0;
-            invden = 1.0f / ((j == 0 ? kY0 : kY1) - xa);
-        } else {
-            const float xj = j == 0 ? kX0 : j == 1 ? kX1 : j == 2 ? kX2 : kX3;
-            xa = j == 0 ? kX1 : kX0, xb = j <= 1 ? kX2 : kX1, xc = j == 3 ? kX2 : kX3;
-            invden = 1.0f / ((xj - xa) * (xj - xb) * (xj - xc));
-        }
-        const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16) + (uint32_t)(128 * mt);
-        for (int cg = cg0; 16 * cg < cnt; cg += cgs) {
-            float v[48];
-            tc::tmem_ld16(taddr + 48 * cg, *reinterpret_cast<float(*)[16]>(&v[0]));
-            if (cg < 2) {
-                tc::tmem_ld16(taddr + 48 * cg + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
-                tc::tmem_ld16(taddr + 48 * cg + 32, *reinterpret_cast<float(*)[16]>(&v[32]));
-            } else {        // candidates 32..36 live in columns 96..110 of the 112-column tile
+    int c, k;
+    m_row_owner(qd, lane, c, k);
+    const bool valid = c < cnt;
+    const int cc = valid ? c : 0;
+    const float bk = cscal[cc * 4 + k];
+    float *outk = out_s + k * (kH * kAS);
+    const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16);
+    const int nblocks = (NODES * nrows + 15) >> 4;
+    const int bstep = qd + 4 < kCWarps ? 2 : 1;      // quadrants whose partner warp w + 4 is the MMA issuer are walked by one warp
+    for (int b = bstep == 2 ? warp >> 2 : 0; b < nblocks; b += bstep) {
+        float v[16];
+        tc::tmem_ld16(taddr + 16 * b, v);
 #pragma unroll
-                for (int i = 16; i < 48; ++i) v[i] = 0.0f;
+        for (int i = 0; i < UPB; ++i) {
+            const int ul = UPB * b + i;
+            if (ul < nrows) {
+                const int u = u0 + ul;
+                float t = (a_s[u * kAS + cc] - mid_s[u]) * winv_s[u];
+                t = fminf(fmaxf(t, -1.0f), 1.0f);
+                float p, s0, s1;
+                if (NODES == 2) {
+                    const float4 ss = *reinterpret_cast<const float4 *>(s01_s + u * 8);
+                    const float l1 = fmaf(t, 0.5f / kY1, 0.5f), l0 = 1.0f - l1;      // (t - y0) / (y1 - y0)
+                    p = fmaf(l1, v[2 * i + 1], l0 * v[2 * i]);
+                    s0 = fmaf(l1, ss.z, l0 * ss.x);
+                    s1 = fmaf(l1, ss.w, l0 * ss.y);
+                } else {
+                    const float4 sa = *reinterpret_cast<const float4 *>(s01_s + u * 8);
+                    const float4 sb = *reinterpret_cast<const float4 *>(s01_s + u * 8 + 4);
+                    const float t0 = t - kX0, t1 = t - kX1, t2 = t - kX2, t3 = t - kX3;
+                    const float l0 = t1 * t2 * t3 * (1.0f / ((kX0 - kX1) * (kX0 - kX2) * (kX0 - kX3)));
+                    const float l1 = t0 * t2 * t3 * (1.0f / ((kX1 - kX0) * (kX1 - kX2) * (kX1 - kX3)));
+                    const float l2 = t0 * t1 * t3 * (1.0f / ((kX2 - kX0) * (kX2 - kX1) * (kX2 - kX3)));
+                    const float l3 = t0 * t1 * t2 * (1.0f / ((kX3 - kX0) * (kX3 - kX1) * (kX3 - kX2)));
+                    p = l0 * v[4 * i] + l1 * v[4 * i + 1] + l2 * v[4 * i + 2] + l3 * v[4 * i + 3];
+                    s0 = l0 * sa.x + l1 * sa.z + l2 * sb.x + l3 * sb.z;
+                    s1 = l0 * sa.y + l1 * sa.w + l2 * sb.y + l3 * sb.w;
+                }
+                // LayerNorm folded into the dot: the candidate vectors are mean-centred, so x.w = rstd * (o.w)
+                const float mu = s0 * (1.0f / kD);
+                const float var = fmaxf(fmaf(-mu, mu, s1 * (1.0f / kD)), 0.0f);
+                const float rstd = rsqrtf(var + ln_eps);
+                if (valid) outk[u * kAS + c] = fmaf(rstd, p, bk);
             }
+        }
+    }
+}
+
+// Candidate-aware attention weights a[u][c] (layers.py:66-81) of one work unit.  LPC lanes share a candidate, a lane owns
+// the unique rows u = l + LPC * i (i < 4): all 12 table loads of a lane are issued before the first exponential, the 40
+// exponentials stay in registers for both softmaxes.  Head logits come pre-scaled by log2(e) from the topic-pair table
+// (no max pass: the host checks the table's |logit| bound); masked slots (mask == 0 -> -1e9, layers.py:72) contribute
+// exactly 0 unless every slot is masked, in which case both softmaxes are uniform over the H slots.
+template <int LPC>
+__device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, int cnt, int nun, int warp, int lane,
+                                          const int *ctopic, const int *utopic, const int *umask, const float *umult,
+                                          float *a_s, unsigned long long *prof) {
+    const int tid = threadIdx.x;
+    long long t_last = clock64();
+    constexpr int CPW = 32 / LPC;                 // candidates per warp and round
+    const int l = lane & (LPC - 1), g = lane / LPC;
+    float w[4], mu[4];
+    int tp[4];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int c = 16 * cg + i;
-                if (c < cnt) {
-                    float t = (a_s[c * kRows + hc] - mid) * winv;
-                    t = fminf(fmaxf(t, -1.0f), 1.0f);
-                    const float L = NODES == 2 ? (t - xa) * invden : (t - xa) * (t - xb) * (t - xc) * invden;
-                    float p0 = L * v[3 * i], p1 = L * v[3 * i + 1], p2 = L * v[3 * i + 2];
-                    float p3 = L * s0n, p4 = L * s1n;
+    for (int i = 0; i < 4; ++i) {
+        const int u = l + LPC * i;
+        const bool in = u < U;
+        mu[i] = in ? umult[u] : 0.0f;
+        w[i] = (in && umask[u] != 0) ? mu[i] : 0.0f;
+        tp[i] = in ? utopic[u] : 0;
+    }
+    LIME_TICK(11);
+    for (int c0 = CPW * warp; c0 < cnt; c0 += CPW * kCWarps) {
+        const int c = c0 + g;
+        const bool cvalid = c < cnt;
+        const int cc = cvalid ? c : cnt - 1;
+        float e2[4];
+        float s2 = 0.0f;
+        if (nun > 0) {
+            const float *trow = C.topic_table + (size_t)ctopic[cc] * T * kTabLd;
+            float4 x[4][3];
 #pragma unroll
-                    for (int o = 1; o < NODES; o <<= 1) {
-                        p0 += __shfl_xor_sync(0xffffffffu, p0, o);
-                        p1 += __shfl_xor_sync(0xffffffffu, p1, o);
-                        p2 += __shfl_xor_sync(0xffffffffu, p2, o);
-                        p3 += __shfl_xor_sync(0xffffffffu, p3, o);
-                        p4 += __shfl_xor_sync(0xffffffffu, p4, o);
-                    }
-                    if (j == 0 && row_ok) {
-                        const float *cs = cscal + c * 8;
-                        const float mu = p3 * (1.0f / kD);
-                        const float var = fmaxf(fmaf(-mu, mu, p4 * (1.0f / kD)), 0.0f);
-                        const float rstd = rsqrtf(var + ln_eps);
-                        lg_s[c * kRows + hr] = fmaf(rstd, fmaf(-mu, cs[0], p0), cs[3]);
-                        y_s[c * kRows + hr] = fmaf(rstd, fmaf(-mu, cs[1], p1), cs[4]);
-                        z_s[c * kRows + hr] = fmaf(rstd, fmaf(-mu, cs[2], p2), cs[5]);
-                    }
+            for (int i = 0; i < 4; ++i) {
+                const float *r0 = trow + (size_t)tp[i] * kTabLd;
+                x[i][0] = ldg4(r0);
+                x[i][1] = ldg4(r0 + 4);
+                x[i][2] = ldg4(r0 + 8);
+            }
+            if (__float_as_int(x[0][0].x) == 0x7fc12345 || __float_as_int(x[3][2].y) == 0x7fc12345) a_s[0] = 0.f;   // wait for the loads
+            LIME_TICK(12);
+            float e[4][LIME_CA_HEADS], sum[LIME_CA_HEADS];
+#pragma unroll
+            for (int hd = 0; hd < LIME_CA_HEADS; ++hd) sum[hd] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float xs[LIME_CA_HEADS] = {x[i][0].x, x[i][0].y, x[i][0].z, x[i][0].w, x[i][1].x,
+                                                 x[i][1].y, x[i][1].z, x[i][1].w, x[i][2].x, x[i][2].y};
+#pragma unroll
+                for (int hd = 0; hd < LIME_CA_HEADS; ++hd) {
+                    e[i][hd] = ex2_approx(xs[hd]);
+                    sum[hd] = fmaf(w[i], e[i][hd], sum[hd]);
                 }
             }
+#pragma unroll
+            for (int o = 1; o < LPC; o <<= 1) {
+#pragma unroll
+                for (int hd = 0; hd < LIME_CA_HEADS; ++hd) sum[hd] += __shfl_xor_sync(0xffffffffu, sum[hd], o);
+            }
+            LIME_TICK(13);
+#pragma unroll
+            for (int hd = 0; hd < LIME_CA_HEADS; ++hd) sum[hd] = __fdividef(1.0f, sum[hd]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float agg = 0.0f;
+#pragma unroll
+                for (int hd = 0; hd < LIME_CA_HEADS; ++hd) agg = fmaf(e[i][hd], sum[hd], agg);
+                agg = w[i] > 0.0f ? agg : 0.0f;
+                // second, unmasked softmax over the history (layers.py:81); agg in [0, 10]: no max needed
+                e2[i] = ex2_approx(agg * kLog2e);
+                s2 = fmaf(mu[i], e2[i], s2);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                e2[i] = 1.0f;
+                s2 += mu[i];
+            }
         }
+#pragma unroll
+        for (int o = 1; o < LPC; o <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        const float inv2 = __fdividef(1.0f, s2);
+        if (cvalid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int u = l + LPC * i;
+                if (u < U) a_s[u * kAS + c] = e2[i] * inv2;
+            }
+        }
+        LIME_TICK(14);
     }
 }
 
 __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs args) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float *lg_s = reinterpret_cast<float *>(base + OFF_LG);
-    float *y_s = reinterpret_cast<float *>(base + OFF_Y);
-    float *z_s = reinterpret_cast<float *>(base + OFF_Z);
-    float *a_s = reinterpret_cast<float *>(base + OFF_A);
+    float *out_s = reinterpret_cast<float *>(base + OFF_OUT);
+    float *a_s = reinterpret_cast<float *>(base + OFF_AS);
     float *bias_s = reinterpret_cast<float *>(base + OFF_BIAS);
     float *s01_s = reinterpret_cast<float *>(base + OFF_S01);
     float *mid_s = reinterpret_cast<float *>(base + OFF_MID);
     float *winv_s = reinterpret_cast<float *>(base + OFF_WINV);
     float *whalf_s = reinterpret_cast<float *>(base + OFF_WHALF);
     float *cscal = reinterpret_cast<float *>(base + OFF_CSCAL);
+    float *pool_s = reinterpret_cast<float *>(base + OFF_POOL);
     float *cw = reinterpret_cast<float *>(base + OFF_CW);
     int *cnews = reinterpret_cast<int *>(base + OFF_CNEWS);
     int *ctab = reinterpret_cast<int *>(base + OFF_CTAB);
     int *cP = reinterpret_cast<int *>(base + OFF_CP);
     int *ctopic = reinterpret_cast<int *>(base + OFF_CTOPIC);
-    int *hnews = reinterpret_cast<int *>(base + OFF_HNEWS);
-    int *htab = reinterpret_cast<int *>(base + OFF_HTAB);
-    int *hmask = reinterpret_cast<int *>(base + OFF_HMASK);
-    int *htopic = reinterpret_cast<int *>(base + OFF_HTOPIC);
+    int *unews = reinterpret_cast<int *>(base + OFF_UNEWS);
+    int *utab = reinterpret_cast<int *>(base + OFF_UTAB);
+    int *umask = reinterpret_cast<int *>(base + OFF_UMASK);
+    int *utopic = reinterpret_cast<int *>(base + OFF_UTOPIC);
+    float *umult = reinterpret_cast<float *>(base + OFF_UMULT);
+    float *ump0 = reinterpret_cast<float *>(base + OFF_UMP0);
+    float *ump1 = reinterpret_cast<float *>(base + OFF_UMP1);
+    float *ugabs = reinterpret_cast<float *>(base + OFF_UGABS);
+    int *ufirst = reinterpret_cast<int *>(base + OFF_UFIRST);
+    int *hkn = reinterpret_cast<int *>(base + OFF_HKN);
+    int *hkt = reinterpret_cast<int *>(base + OFF_HKT);
+    int *hkm = reinterpret_cast<int *>(base + OFF_HKM);
+    int *hfirst = reinterpret_cast<int *>(base + OFF_HFIRST);
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(base + OFF_BARS);
     uint64_t *bar_free = bar_full + 2;
     uint64_t *bar_accum = bar_full + 4;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(base + OFF_MISC);
-    int *unit_bcast = reinterpret_cast<int *>(base + OFF_MISC + 8);
-    int *flag_s = reinterpret_cast<int *>(base + OFF_MISC + 16);
+    volatile int *misc = reinterpret_cast<volatile int *>(base + OFF_MISC);
+    int *flag_s = reinterpret_cast<int *>(base + OFF_MISC) + M_FLAGS;
+    uint32_t *rowoff_s = reinterpret_cast<uint32_t *>(base + OFF_ROWOFF);
 
     const LimeNewsCache &C = args.cache;
     const LimeImpressions &I = args.imp;
@@ -317,47 +517,60 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
     const int nb = C.num_buckets;
     const int T = C.num_topics;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const __half *cand16 = reinterpret_cast<const __half *>(C.cand16);
+    const __half *ctab16 = reinterpret_cast<const __half *>(C.ctab16);
 
     for (int d = tid; d < kD; d += kThreads) bias_s[d] = C.gate_bias[d];
     if (tid == 0) {
-        tc::mbar_init(bar_full + 0, kCompute);
-        tc::mbar_init(bar_full + 1, kCompute);
+        tc::mbar_init(bar_full + 0, 2 * kCompute);    // per compute thread: its cp.async copies + its O rows
+        tc::mbar_init(bar_full + 1, 2 * kCompute);
         tc::mbar_init(bar_free + 0, 1);
         tc::mbar_init(bar_free + 1, 1);
         tc::mbar_init(bar_accum, 1);
         tc::mbar_fence_init();
+        misc[M_NEXT] = atomicAdd(args.work_counter, 1);
     }
-    if (warp == kWarps) tc::tmem_alloc(tmem_slot, 256);
+    if (warp == kMmaWarp) tc::tmem_alloc(reinterpret_cast<uint32_t *>(base + OFF_MISC) + M_TMEM, 128);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = *(reinterpret_cast<volatile uint32_t *>(base + OFF_MISC) + M_TMEM);
 
-    uint32_t unit_iter = 0;       // units processed so far (phase of bar_accum)
+    unsigned long long *prof = reinterpret_cast<unsigned long long *>(base + OFF_PROF);
+    if (tid == 0) {
+        for (int i = 0; i < 16; ++i) prof[i] = 0;
+    }
+    long long t_last = clock64();
+    uint32_t use0 = 0, use1 = 0;     // uses of the two ring halves so far (every role counts the same sequence)
+    uint32_t pass_iter = 0;          // passes processed so far (phase of bar_accum)
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) unit_bcast[0] = atomicAdd(args.work_counter, 1);
+        if (tid == 0) {
+            misc[M_UNIT] = misc[M_NEXT];
+            misc[M_NEXT] = atomicAdd(args.work_counter, 1);
+            misc[M_FLAGS] = 0;
+        }
         __syncthreads();
-        const int unit = unit_bcast[0];
+        const int unit = misc[M_UNIT];
         if (unit >= I.num_units) break;
+        if (tid == 0) { t_last = clock64(); ++prof[9]; }
         const int imp = I.unit_imp[unit];
         const int pair0 = I.unit_pair0[unit];
         const int cnt = I.unit_count[unit];
+        const int pz0 = args.prefix_main < H ? args.prefix_main : H;
+        const int pz1 = args.prefix_tail < H ? args.prefix_tail : H;
 
-        // ---------------- phase 0: unit metadata, L2 prefetch of the rows the unit will read ------
+        // ---------------- phase 0: unit metadata; L2 prefetch of the NEXT unit's cache rows --------
         for (int h = tid; h < H; h += kThreads) {
             const long long o = (long long)imp * H + h;
             int n = I.hist_news[o];
             n = (n < 0 || n >= C.news_num) ? 0 : n;
-            hnews[h] = n;
-            hmask[h] = I.hist_mask[o];
+            hkn[h] = n;
+            hkm[h] = I.hist_mask[o] != 0 ? 1 : 0;
             const int bf = bucketize_seconds(I.hist_fresh[o], args.bucket_scale, nb);
             const int bl = bucketize_seconds(I.hist_life[o], args.bucket_scale, nb);
-            htab[h] = bf * nb + bl;
-            const float *hrow = C.hist_rows + (size_t)n * LIME_HIST_LD;
-            int tp = __float_as_int(__ldg(hrow + LIME_HIST_TOPIC_ID));
-            htopic[h] = (tp < 0 || tp >= T) ? 0 : tp;
+            hkt[h] = bf * nb + bl;
         }
         for (int c = tid; c < cnt; c += kThreads) {
             const long long p = (long long)pair0 + c;
@@ -365,167 +578,285 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             n = (n < 0 || n >= C.news_num) ? 0 : n;
             cnews[c] = n;
             const float fr = I.cand_fresh[p], lf = I.cand_life[p];
-            ctab[c] = bucketize_seconds(fr, args.bucket_scale, nb) * nb + bucketize_seconds(lf, args.bucket_scale, nb);
+            const int tb = bucketize_seconds(fr, args.bucket_scale, nb) * nb + bucketize_seconds(lf, args.bucket_scale, nb);
+            ctab[c] = tb;
             cw[c] = lifetime_weight(I.cand_remaining ? I.cand_remaining[p] : __fsub_rn(lf, fr), C);
             cP[c] = (args.pair_index_base + p >= args.tail_start) ? args.prefix_tail : args.prefix_main;
+            prefetch_l2_bulk(cand16 + (size_t)n * kC16, kC16 * 2);      // the operand rows this unit streams in phase 2
             const float *crow = C.cand_rows + (size_t)n * LIME_CAND_LD;
+            const float *ctr = C.cand_tab + (size_t)tb * LIME_CTAB_LD;
             int tp = __float_as_int(__ldg(crow + LIME_CAND_TOPIC_ID));
             ctopic[c] = (tp < 0 || tp >= T) ? 0 : tp;
-        }
-        if (tid == 0) flag_s[0] = 0;
-        __syncthreads();
-        // history rows: vc | gw = 3200 B = 25 lines; candidate rows: w1 w2 w3 = 4800 B = 38 lines (+1 unaligned)
-        for (int idx = tid; idx < H * 26; idx += kThreads) {
-            const int h = idx / 26, l = idx - h * 26;
-            prefetch_l2(reinterpret_cast<const char *>(C.hist_rows + (size_t)hnews[h] * LIME_HIST_LD) + l * 128);
-        }
-        for (int idx = tid; idx < cnt * 39; idx += kThreads) {
-            const int c = idx / 39, l = idx - c * 39;
-            prefetch_l2(reinterpret_cast<const char *>(C.cand_rows + (size_t)cnews[c] * LIME_CAND_LD) + l * 128);
-        }
-
-        // ---------------- phase 1: candidate-aware attention weights a[c][h] (layers.py:66-81) ----
-        if (warp < kWarps) {
-            const bool v0 = lane < H, v1 = lane + 32 < H;
-            const int t0 = htopic[v0 ? lane : 0], t1 = htopic[v1 ? lane + 32 : 0];
-            const bool k0 = v0 && hmask[v0 ? lane : 0] != 0, k1 = v1 && hmask[v1 ? lane + 32 : 0] != 0;
-            for (int c = warp; c < cnt; c += kWarps) {
-                if (lane < 8) {
-                    const float *crow = C.cand_rows + (size_t)cnews[c] * LIME_CAND_LD;
-                    const float tabv = C.cand_tab[(size_t)ctab[c] * LIME_CTAB_LD + LIME_CAND_SCAL + lane];
-                    cscal[c * 8 + lane] = crow[LIME_CAND_SCAL + lane] + tabv;
-                }
-                const float *trow = C.topic_table + (size_t)ctopic[c] * T * kTabLd;
-                float sc[2][LIME_CA_HEADS];
-                {
-                    const float *r0 = trow + (size_t)t0 * kTabLd, *r1 = trow + (size_t)t1 * kTabLd;
-                    const float4 a0 = ldg4(r0), a1 = ldg4(r0 + 4), a2 = ldg4(r0 + 8);
-                    const float4 b0 = ldg4(r1), b1 = ldg4(r1 + 4), b2 = ldg4(r1 + 8);
-                    const float x0[LIME_CA_HEADS] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
-                    const float x1[LIME_CA_HEADS] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
 #pragma unroll
-                    for (int hd = 0; hd < LIME_CA_HEADS; ++hd) {   // masked_fill(mask == 0, -1e9), layers.py:72
-                        sc[0][hd] = v0 ? (k0 ? x0[hd] : -1e9f) : -INFINITY;
-                        sc[1][hd] = v1 ? (k1 ? x1[hd] : -1e9f) : -INFINITY;
-                    }
-                }
-                float agg[2] = {0.0f, 0.0f};
-#pragma unroll
-                for (int hd = 0; hd < LIME_CA_HEADS; ++hd) {
-                    const float m = warp_max(fmaxf(sc[0][hd], sc[1][hd]));
-                    const float e0 = __expf(sc[0][hd] - m), e1 = __expf(sc[1][hd] - m);
-                    const float inv = __fdividef(1.0f, warp_sum(e0 + e1));
-                    agg[0] = fmaf(e0, inv, agg[0]);
-                    agg[1] = fmaf(e1, inv, agg[1]);
-                }
-                // second, unmasked softmax over the history (layers.py:81)
-                const float m2 = warp_max(fmaxf(v0 ? agg[0] : -INFINITY, v1 ? agg[1] : -INFINITY));
-                agg[0] = v0 ? __expf(agg[0] - m2) : 0.0f;
-                agg[1] = v1 ? __expf(agg[1] - m2) : 0.0f;
-                const float inv2 = __fdividef(1.0f, warp_sum(agg[0] + agg[1]));
-                if (v0) a_s[c * kRows + lane] = agg[0] * inv2;
-                if (v1) a_s[c * kRows + lane + 32] = agg[1] * inv2;
-            }
+            for (int k = 0; k < 4; ++k) cscal[c * 4 + k] = __ldg(crow + LIME_CAND_SCAL + 3 + k) + __ldg(ctr + LIME_CAND_SCAL + 3 + k);
+            if (!(__ldg(crow + LIME_CAND_ABSMAX) <= 32768.0f)) atomicOr(flag_s, 4);   // fp16 operand range
+            pool_s[c * 4 + 0] = -INFINITY;
+            pool_s[c * 4 + 1] = 0.0f;
+            pool_s[c * 4 + 2] = 0.0f;
+            pool_s[c * 4 + 3] = 0.0f;
         }
         __syncthreads();
+        LIME_TICK(0);
 
-        // ---------------- interpolation nodes per history row ------------------------------------
+        // element offsets of the 128 M operand rows inside cand16 / ctab16 (0xffffffff: unused row)
+        if (tid >= kCompute - 128 && tid < kCompute) {
+            const int r = tid - (kCompute - 128);
+            int c, k;
+            m_row_owner(r >> 5, r & 31, c, k);
+            const bool ok = c < cnt;
+            const int cc = ok ? c : 0;
+            rowoff_s[r] = ok ? (uint32_t)cnews[cc] * (uint32_t)kC16 + (uint32_t)(k * 2 * kD) : 0xffffffffu;
+            rowoff_s[128 + r] = (uint32_t)ctab[cc] * (uint32_t)kC16 + (uint32_t)(k * 2 * kD);
+        }
+        // ---------------- dedup of the history slots: (news, bucket pair, mask) -> unique rows -----
         if (tid < H) {
-            float lo = a_s[tid], hi = lo;
-            for (int c = 1; c < cnt; ++c) {
-                const float a = a_s[c * kRows + tid];
-                lo = fminf(lo, a);
-                hi = fmaxf(hi, a);
+            const int n = hkn[tid], t = hkt[tid], m = hkm[tid];
+            int f = tid;
+            for (int j = 0; j < tid; ++j) {
+                if (hkn[j] == n && hkt[j] == t && hkm[j] == m) {
+                    f = j;
+                    break;
+                }
             }
-            const float wh = fmaxf(0.5f * (hi - lo), 1e-7f);
-            mid_s[tid] = 0.5f * (hi + lo);
-            whalf_s[tid] = wh;
-            winv_s[tid] = 1.0f / wh;
-            // Interpolation error of f(a) = (1 - a) sigmoid(g a + b) on [mid - w, mid + w] with n Chebyshev nodes:
-            // max|d^n f| w^n / (n! 2^(n-1));  |d^2 f| <= 0.0962 g^2 + 0.5 |g|,  |d^4 f| <= 0.125 g^4 + 0.5 |g|^3.
-            // g is bounded by the cached max |W_g vc| of the news plus the max over the bucket-pair table.
-            const float gabs = (__ldg(C.hist_rows + (size_t)hnews[tid] * LIME_HIST_LD + LIME_HIST_GW_ABSMAX) + C.tab_gw_absmax) *
-                               (1.0f / kLog2e);
-            const float w2 = wh * wh, g2 = gabs * gabs;
-            const float err2 = w2 * (0.0962f * g2 + 0.5f * gabs) * 0.25f;
-            const float err4 = w2 * w2 * (0.125f * g2 * g2 + 0.5f * g2 * gabs) * (1.0f / 192.0f);
-            if (!(err2 <= args.interp_tol)) atomicOr(flag_s, 1);          // 2 nodes are not enough
-            if (!(err4 <= args.interp_tol)) atomicOr(flag_s, 2);          // 4 nodes are not enough: exact kernel
+            hfirst[tid] = f;
         }
         __syncthreads();
-        const int flags0 = flag_s[0];
-        const int nodes = (flags0 & 1) ? 4 : 2;
+        if (warp < 2) {
+            const bool isf = tid < H && hfirst[tid < H ? tid : 0] == tid;
+            const unsigned bal = __ballot_sync(0xffffffffu, isf);
+            if (lane == 0) misc[M_WC0 + warp] = __popc(bal);
+            if (isf) hkm[tid] |= (__popc(bal & ((1u << lane) - 1u)) << 8) | 0x10000;   // rank inside the warp, "is first" bit
+        }
+        __syncthreads();
+        if (tid < H) {
+            const int km = hkm[tid];
+            if (km & 0x10000) {
+                const int u = ((km >> 8) & 0xff) + (warp == 1 ? misc[M_WC0] : 0);
+                unews[u] = hkn[tid];
+                utab[u] = hkt[tid];
+                umask[u] = km & 1;
+                ufirst[u] = tid;
+            }
+        }
+        const int U = misc[M_WC0] + misc[M_WC1];
+        __syncthreads();
+        if (tid < U) {
+            const int f = ufirst[tid];
+            int m = 0, m0 = 0, m1 = 0;
+            for (int h = 0; h < H; ++h) {
+                const int eq = hfirst[h] == f ? 1 : 0;
+                m += eq;
+                m0 += (h < pz0) ? eq : 0;
+                m1 += (h < pz1) ? eq : 0;
+            }
+            umult[tid] = (float)m;
+            ump0[tid] = (float)m0;
+            ump1[tid] = (float)m1;
+            const float *hrow = C.hist_rows + (size_t)unews[tid] * LIME_HIST_LD;
+            prefetch_l2_bulk(hrow, 2 * kD * 4);                          // vc | gw, read in phase 2
+            int tp = __float_as_int(__ldg(hrow + LIME_HIST_TOPIC_ID));
+            utopic[tid] = (tp < 0 || tp >= T) ? 0 : tp;
+            ugabs[tid] = __ldg(hrow + LIME_HIST_GW_ABSMAX);
+        }
+        if (warp == 2) {   // number of unmasked history slots
+            int nun = 0;
+            for (int h = lane; h < H; h += 32) nun += hkm[h] & 1;
+            nun = __reduce_add_sync(0xffffffffu, nun);
+            if (lane == 0) misc[M_NUN] = nun;
+        }
+        __syncthreads();
+        LIME_TICK(1);
 
-        const int n_cols = (3 * cnt + 15) & ~15;
-        const int mtiles = (nodes * H + 127) >> 7;
+        // ================= roles ======================================================================
+        if (warp < kCWarps) {
+            // ---------------- phase 1: candidate-aware attention weights a[u][c] (layers.py:66-81) ------
+            if (U <= 32) attention<8>(C, T, U, cnt, misc[M_NUN], warp, lane, ctopic, utopic, umask, umult, a_s, prof);
+            else         attention<16>(C, T, U, cnt, misc[M_NUN], warp, lane, ctopic, utopic, umask, umult, a_s, prof);
+            if (tid == 0) t_last = clock64();
+            bar_compute();
+            LIME_TICK(15);
+            if (tid == 0) t_last = clock64();
 
-        if (warp < kWarps) {
-            if (nodes == 2) produce_operands<2>(base, C, H, cnt, tid, hnews, htab, cnews, ctab, mid_s, whalf_s, bias_s, s01_s,
-                                                flag_s, bar_full, bar_free, unit_iter);
-            else            produce_operands<4>(base, C, H, cnt, tid, hnews, htab, cnews, ctab, mid_s, whalf_s, bias_s, s01_s,
-                                                flag_s, bar_full, bar_free, unit_iter);
-        } else {
-            // ---------------- MMA issuer ---------------------------------------------------------
-            const uint32_t idesc = tc::idesc_f16_f32(128, n_cols);
-            const uint32_t sb = tc::smem_u32(base);
-            for (int kc = 0; kc < kChunks; ++kc) {
-                const int s = kc & 1;
-                const uint32_t u = unit_iter * (s ? 6u : 7u) + (uint32_t)(kc >> 1);
-                tc::mbar_wait(bar_full + s, u & 1u);
-                tc::fence_after_sync();
-                if (lane == 0) {
-                    const int ksteps = kc < kChunks - 1 ? 2 : (kD - 32 * (kChunks - 1)) / 16;
-                    const uint64_t bhi = tc::smem_desc_sw128(sb + OFF_BHI), blo = tc::smem_desc_sw128(sb + OFF_BLO);
-                    for (int mt = 0; mt < mtiles; ++mt) {
-                        const uint64_t ahi = tc::smem_desc_sw128(sb + OFF_AHI + mt * 16384);
-                        const uint64_t alo = tc::smem_desc_sw128(sb + OFF_ALO + mt * 16384);
-                        const uint32_t td = tmem + (uint32_t)(mt * 128);
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t k2 = (uint64_t)(2 * (2 * s + ks));   // 32 bytes per K step of 16
-                            tc::mma_f16(td, ahi + k2, bhi + k2, idesc, (kc | ks) != 0);
-                            tc::mma_f16(td, ahi + k2, blo + k2, idesc, true);
-                            tc::mma_f16(td, alo + k2, bhi + k2, idesc, true);
+            // ---------------- interpolation nodes per unique row (4 lanes per row) --------------------
+            {
+                const int u = tid >> 2, l4 = tid & 3;
+                const int uc = u < U ? u : U - 1;
+                float lo = INFINITY, hi = -INFINITY;
+                for (int c = l4; c < cnt; c += 4) {
+                    const float a = a_s[uc * kAS + c];
+                    lo = fminf(lo, a);
+                    hi = fmaxf(hi, a);
+                }
+#pragma unroll
+                for (int o = 1; o < 4; o <<= 1) {
+                    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+                }
+                if (u < U && l4 == 0) {
+                    const float wh = fmaxf(0.5f * (hi - lo), 1e-7f);
+                    mid_s[u] = 0.5f * (hi + lo);
+                    whalf_s[u] = wh;
+                    winv_s[u] = 1.0f / wh;
+                    // Interpolation error of f(a) = (1 - a) sigmoid(g a + b) on [mid - w, mid + w] with n Chebyshev
+                    // nodes: max|d^n f| w^n / (n! 2^(n-1));  |d^2 f| <= 0.0962 g^2 + 0.5 |g|,
+                    // |d^4 f| <= 0.125 g^4 + 0.5 |g|^3.  g is bounded by the cached max |W_g vc| of the news plus
+                    // the max over the bucket-pair table.
+                    const float gabs = (ugabs[u] + C.tab_gw_absmax) * (1.0f / kLog2e);
+                    const float w2 = wh * wh, g2 = gabs * gabs;
+                    const float err2 = w2 * (0.0962f * g2 + 0.5f * gabs) * 0.25f;
+                    const float err4 = w2 * w2 * (0.125f * g2 * g2 + 0.5f * g2 * gabs) * (1.0f / 192.0f);
+                    if (!(err2 <= args.interp_tol)) atomicOr(flag_s, 1);          // 2 nodes are not enough
+                    if (!(err4 <= args.interp_tol)) atomicOr(flag_s, 2);          // 4 nodes are not enough: exact kernel
+                }
+            }
+            bar_compute();
+            if (tid == 0) {
+                const int nd = (flag_s[0] & 1) ? 4 : 2;
+                misc[M_NODES] = nd;
+                misc[M_NPASS] = (nd * U + kBRows - 1) / kBRows;
+            }
+            bar_compute();
+            LIME_TICK(3);
+        }
+        // the number of passes is known to the other roles at the first CTA barrier below; pass 0 always exists
+        int npass = 1;
+        for (int pass = 0; pass < npass; ++pass) {
+            if (warp < kCWarps) {
+                const int nodes = misc[M_NODES];
+                const int G = kBRows / nodes;
+                const int u0 = pass * G;
+                const int nrows = min(G, U - u0);
+                if (tid == 0) misc[M_NPAD] = (nodes * nrows + 15) & ~15;      // published by the first full-barrier arrive
+                if (nodes == 2) {
+                    if (nrows > kRPT) produce_operands<2, 2>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, bias_s, s01_s, flag_s, rowoff_s, cand16, ctab16, bar_full, bar_free, use0, use1);
+                    else            produce_operands<2, 1>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, bias_s, s01_s, flag_s, rowoff_s, cand16, ctab16, bar_full, bar_free, use0, use1);
+                } else {
+                    produce_operands<4, 1>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, bias_s, s01_s, flag_s, rowoff_s, cand16, ctab16, bar_full, bar_free, use0, use1);
+                }
+            } else if (warp == kMmaWarp) {
+                // ---------------- MMA issuer -------------------------------------------------------------
+                // first (the compute warps are still in phase 1): pull the NEXT unit's impression arrays into L2 (the cache
+                // rows are prefetched by their own unit: a whole unit of look-ahead for 296 CTAs overflows the L2)
+                if (pass == 0) {
+                    const int nxt = misc[M_NEXT];
+                    if (nxt < I.num_units) {
+                        const int nimp = I.unit_imp[nxt], np0 = I.unit_pair0[nxt], ncnt = I.unit_count[nxt];
+                        const long long ho = (long long)nimp * H;
+                        for (int j = lane; 32 * j < H; j += 32) prefetch_l2(I.hist_news + ho + 32 * j);
+                        for (int j = lane; 32 * j < ncnt; j += 32) prefetch_l2(I.cand_news + np0 + 32 * j);
+                        // the impression arrays themselves (phase 0 of the next unit reads them)
+                        if (lane < 2) prefetch_l2(I.hist_mask + ho + 32 * lane);
+                        if (lane < 3) {
+                            prefetch_l2(I.hist_fresh + ho + 32 * lane);
+                            prefetch_l2(I.hist_life + ho + 32 * lane);
+                            prefetch_l2(I.cand_fresh + np0 + 32 * lane);
+                            prefetch_l2(I.cand_life + np0 + 32 * lane);
+                            if (I.cand_remaining) prefetch_l2(I.cand_remaining + np0 + 32 * lane);
                         }
                     }
-                    tc::mma_commit(bar_free + s);
-                    if (kc == kChunks - 1) tc::mma_commit(bar_accum);
                 }
-                __syncwarp();
+                const uint32_t sb = tc::smem_u32(base);
+                uint32_t idesc = 0;
+                for (int kc = 0; kc < kStages; ++kc) {
+                    const int s = kc & 1;
+                    const uint32_t uses = s ? use1 : use0;
+                    tc::mbar_wait(bar_full + s, uses & 1u);
+                    tc::fence_after_sync();
+                    if (kc == 0) idesc = tc::idesc_f16_f32(128, misc[M_NPAD]);
+                    if (lane == 0) {
+                        const int ksteps = kc < kStages - 1 ? 2 : (kD - 32 * (kStages - 1)) / 16;
+                        const uint64_t bhi = tc::smem_desc_sw128(sb + OFF_BHI), blo = tc::smem_desc_sw128(sb + OFF_BLO);
+                        const uint64_t a_nh = tc::smem_desc_sw128(sb + OFF_A), a_nl = tc::smem_desc_sw128(sb + OFF_A + kAImg);
+                        const uint64_t a_th = tc::smem_desc_sw128(sb + OFF_A + 2 * kAImg), a_tl = tc::smem_desc_sw128(sb + OFF_A + 3 * kAImg);
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t k2 = (uint64_t)(2 * (2 * s + ks));   // 32 bytes per K step of 16
+                            tc::mma_f16(tmem, a_nh + k2, bhi + k2, idesc, (kc | ks) != 0);
+                            tc::mma_f16(tmem, a_nh + k2, blo + k2, idesc, true);
+                            tc::mma_f16(tmem, a_nl + k2, bhi + k2, idesc, true);
+                            tc::mma_f16(tmem, a_th + k2, bhi + k2, idesc, true);
+                            tc::mma_f16(tmem, a_th + k2, blo + k2, idesc, true);
+                            tc::mma_f16(tmem, a_tl + k2, bhi + k2, idesc, true);
+                        }
+                        tc::mma_commit(bar_free + s);
+                        if (kc == kStages - 1) tc::mma_commit(bar_accum);
+                    }
+                    __syncwarp();
+                    if (s) ++use1; else ++use0;
+                }
             }
-        }
-        __syncthreads();   // node sums visible
+            LIME_TICK(4);
+            __syncthreads();   // node sums, flags and the pass count are visible to every role
+            LIME_TICK(10);
+            npass = misc[M_NPASS];
 
-        if (warp < kWarps) {
-            // ---------------- epilogue: TMEM -> Lagrange combination -> LayerNorm folding ---------
-            tc::mbar_wait(bar_accum, unit_iter & 1u);
-            tc::fence_after_sync();
-            if (nodes == 2) epilogue<2>(tmem, warp, lane, H, cnt, mtiles, args.ln_eps, a_s, mid_s, winv_s, s01_s, cscal, lg_s, y_s, z_s);
-            else            epilogue<4>(tmem, warp, lane, H, cnt, mtiles, args.ln_eps, a_s, mid_s, winv_s, s01_s, cscal, lg_s, y_s, z_s);
-        }
-        tc::fence_before_sync();
-        __syncthreads();
-        ++unit_iter;
+            if (warp < kCWarps) {
+                // ---------------- epilogue: TMEM -> Lagrange combination -> LayerNorm folding ---------
+                const int nodes = misc[M_NODES];
+                const int G = kBRows / nodes;
+                const int u0 = pass * G;
+                const int nrows = min(G, U - u0);
+                tc::mbar_wait(bar_accum, pass_iter & 1u);
+                tc::fence_after_sync();
+                LIME_TICK(5);
+                if (nodes == 2) epilogue<2>(tmem, warp, lane, u0, nrows, cnt, args.ln_eps, a_s, mid_s, winv_s, s01_s, cscal, out_s);
+                else            epilogue<4>(tmem, warp, lane, u0, nrows, cnt, args.ln_eps, a_s, mid_s, winv_s, s01_s, cscal, out_s);
+                tc::fence_before_sync();
+                bar_compute();
+                LIME_TICK(6);
 
-        if (tid == 0 && (flag_s[0] & 6) != 0) args.fallback_list[atomicAdd(args.fallback_count, 1)] = unit;
-
-        // ---------------- phase 3: candidate-query pooling + lifetime-weighted dot ---------------
-        if (warp < kWarps) {
-            for (int c = warp; c < cnt; c += kWarps) {
-                const int P = cP[c];
-                const int pz = P < H ? P : H;
-                float m = -INFINITY;
-                for (int hh = lane; hh < H; hh += 32) m = fmaxf(m, lg_s[c * kRows + hh]);
-                m = warp_max(m);
-                float l = 0.f, acc = 0.f, ms = 0.f;
-                for (int hh = lane; hh < H; hh += 32) {
-                    const float e = __expf(lg_s[c * kRows + hh] - m);
-                    l += e;
-                    acc = fmaf(e, y_s[c * kRows + hh], acc);
-                    if (hh < pz) ms += z_s[c * kRows + hh];
+                // ---------------- candidate-query pooling over the rows of this pass (online softmax) -----
+                // 8 lanes per candidate; multiplicities weight the softmax sum, the pooled value and the mean
+                const float *lg_s = out_s, *y_s = out_s + kH * kAS, *z_s = out_s + 2 * kH * kAS;
+                const int l8 = lane & 7, g = lane >> 3;
+                for (int c0 = 4 * warp; c0 < cnt; c0 += 4 * kCWarps) {
+                    const int c = c0 + g;
+                    const bool cvalid = c < cnt;
+                    const int cc = cvalid ? c : cnt - 1;
+                    const float *mp = cP[cc] == args.prefix_main ? ump0 : ump1;
+                    float m = -INFINITY;
+                    for (int ul = l8; ul < nrows; ul += 8) m = fmaxf(m, lg_s[(u0 + ul) * kAS + cc]);
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    float l = 0.f, acc = 0.f, ms = 0.f;
+                    for (int ul = l8; ul < nrows; ul += 8) {
+                        const int u = u0 + ul;
+                        const float e = umult[u] * ex2_approx((lg_s[u * kAS + cc] - m) * kLog2e);
+                        l += e;
+                        acc = fmaf(e, y_s[u * kAS + cc], acc);
+                        ms = fmaf(mp[u], z_s[u * kAS + cc], ms);
+                    }
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        l += __shfl_xor_sync(0xffffffffu, l, o);
+                        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                        ms += __shfl_xor_sync(0xffffffffu, ms, o);
+                    }
+                    if (cvalid && l8 == 0) {
+                        const float m_old = pool_s[c * 4 + 0];
+                        const float m_new = fmaxf(m_old, m);
+                        const float f_old = ex2_approx((m_old - m_new) * kLog2e);    // 0 on the first pass (m_old = -inf)
+                        const float f_new = ex2_approx((m - m_new) * kLog2e);
+                        pool_s[c * 4 + 0] = m_new;
+                        pool_s[c * 4 + 1] = fmaf(pool_s[c * 4 + 1], f_old, l * f_new);
+                        pool_s[c * 4 + 2] = fmaf(pool_s[c * 4 + 2], f_old, acc * f_new);
+                        pool_s[c * 4 + 3] += ms;
+                    }
                 }
-                l = warp_sum(l);
-                acc = warp_sum(acc);
-                ms = warp_sum(ms);
+            }
+            ++pass_iter;
+            __syncthreads();   // out_s (aliasing the O operand) is free again; TMEM may be overwritten
+            LIME_TICK(7);
+        }
+
+        if (tid == 0) {
+            if ((flag_s[0] & 6) != 0) args.fallback_list[atomicAdd(args.fallback_count, 1)] = unit;
+            if (flag_s[0] & 1) atomicAdd(args.fallback_count + 2, 1);   // statistics: 4-node units
+        }
+
+        // ---------------- lifetime-weighted click score (util.py:23-49) --------------------------------
+        if (warp < kCWarps) {
+            for (int c = warp; c < cnt; c += kCWarps) {
+                const int P = cP[c];
                 float un = 0.f;
                 if (P > H) {   // user-node rows take part in the GraphSAGE mean (userEncoders.py:121,153)
                     int jn = P - H - 1;
@@ -537,19 +868,24 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
                     un = warp_sum(un);
                 }
                 if (lane == 0) {
-                    const float bs = (ms + un) / (float)P + cscal[c * 8 + 6] + acc / l;
+                    const float bs = (pool_s[c * 4 + 3] + un) / (float)P + cscal[c * 4 + 3] + pool_s[c * 4 + 2] / pool_s[c * 4 + 1];
                     args.scores[(long long)pair0 + c] = bs * cw[c];
                 }
             }
         }
+        LIME_TICK(8);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 0; i < 16; ++i) atomicAdd(&g_phase_clocks[i], prof[i]);
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == kWarps) tc::tmem_dealloc(tmem, 256);
+    if (warp == kMmaWarp) tc::tmem_dealloc(tmem, 128);
 }
 
-// out[(tc * T + th) * 12 + head] = sum_k tq[tc][k * 10 + head] * topics[th][k] + tq[tc][500 + head]
-// (same accumulation order as phase 1 of the exact kernel, so both kernels see identical logits)
+// out[(tc * T + th) * 12 + head] = log2(e) * ( sum_k tq[tc][k * 10 + head] * topics[th][k] + tq[tc][500 + head] )
+// (pre-scaled so that the scoring kernel's softmax is a bare ex2)
 __global__ void topic_pair_table_kernel(const float *__restrict__ topics, int64_t ldt, const float *__restrict__ tq,
                                         int64_t ldq, int T, float *__restrict__ out) {
     __shared__ float q_s[LIME_TOPIC * LIME_CA_HEADS + LIME_CA_HEADS];
@@ -567,10 +903,35 @@ __global__ void topic_pair_table_kernel(const float *__restrict__ topics, int64_
         }
         float *o = out + ((size_t)tcand * T + th) * kTabLd;
 #pragma unroll
-        for (int hd = 0; hd < LIME_CA_HEADS; ++hd) o[hd] = acc[hd];
+        for (int hd = 0; hd < LIME_CA_HEADS; ++hd) o[hd] = acc[hd] * kLog2e;
         o[10] = 0.0f;
         o[11] = 0.0f;
     }
+}
+
+// src [rows, lds] fp32, `blocks` blocks of 400 columns -> dst [rows, blocks * 800] fp16: per block the 400 hi
+// halves followed by the 400 lo halves (x = hi + lo to 2^-22); absmax[row * ldo] = max |x| of the row
+__global__ void split_f16_pairs_kernel(const float *__restrict__ src, int64_t lds, int blocks, __half *__restrict__ dst,
+                                       float *__restrict__ absmax, int64_t ldo) {
+    __shared__ float red[4];
+    const int64_t row = blockIdx.x;
+    const float *s = src + row * lds;
+    __half *d = dst + row * (int64_t)blocks * 2 * kD;
+    float mx = 0.0f;
+    for (int e = threadIdx.x; e < blocks * kD; e += blockDim.x) {
+        const int k = e / kD, dd = e - k * kD;
+        const float x = s[e];
+        const __half h = __float2half_rn(x);
+        const __half l = __float2half_rn(x - __half2float(h));
+        d[k * 2 * kD + dd] = h;
+        d[k * 2 * kD + kD + dd] = l;
+        mx = fmaxf(mx, fabsf(x));
+        if (x != x) mx = INFINITY;
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0 && absmax != nullptr) absmax[row * ldo] = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
 }
 
 }  // namespace
@@ -581,7 +942,7 @@ int launch_score_tc(const ScoreArgs &a, cudaStream_t st) {
         LIME_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_set = true;
     }
-    LIME_CUDA(cudaMemsetAsync(a.work_counter, 0, 2 * sizeof(int32_t), st));   // work counter + fallback count
+    LIME_CUDA(cudaMemsetAsync(a.work_counter, 0, 4 * sizeof(int32_t), st));   // work counter, fallback count, exact counter, stats
     int grid = 2 * num_sms();
     if (grid > a.imp.num_units) grid = a.imp.num_units;
     score_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
@@ -597,5 +958,24 @@ extern "C" int lime_topic_pair_table(const float *topics, int64_t ldt, const flo
     LIME_CHECK_ARG(T >= 1 && T <= LIME_TC_MAX_TOPICS, "lime_topic_pair_table: T=%d not in [1, %d]", T, LIME_TC_MAX_TOPICS);
     lime::topic_pair_table_kernel<<<T, 128, 0, lime::as_stream(stream)>>>(topics, ldt, tq, ldq, T, out);
     LIME_LAUNCH_CHECK("topic_pair_table_kernel");
+    return 0;
+}
+
+extern "C" int lime_score_phase_clocks(uint64_t *out16) {
+    LIME_CHECK_ARG(out16, "lime_score_phase_clocks: null argument");
+    unsigned long long zero[16] = {0};
+    LIME_CUDA(cudaDeviceSynchronize());
+    LIME_CUDA(cudaMemcpyFromSymbol(out16, lime::g_phase_clocks, sizeof(zero)));
+    LIME_CUDA(cudaMemcpyToSymbol(lime::g_phase_clocks, zero, sizeof(zero)));
+    return 0;
+}
+
+extern "C" int lime_split_f16_pairs(const float *src, int64_t lds, int64_t rows, int32_t blocks, void *dst,
+                                    float *absmax, int64_t ldo, void *stream) {
+    LIME_CHECK_ARG(src && dst, "lime_split_f16_pairs: null argument");
+    LIME_CHECK_ARG(blocks >= 1 && lds >= (int64_t)blocks * LIME_D, "lime_split_f16_pairs: blocks=%d lds=%lld", blocks, (long long)lds);
+    if (rows <= 0) return 0;
+    lime::split_f16_pairs_kernel<<<(unsigned)rows, 128, 0, lime::as_stream(stream)>>>(src, lds, blocks, reinterpret_cast<__half *>(dst), absmax, ldo);
+    LIME_LAUNCH_CHECK("split_f16_pairs_kernel");
     return 0;
 }

@@ -11,6 +11,9 @@ Layout of the per-news cache in HBM (fp32; DESIGN.md "HBM layout"):
                           7 scalars (1200..1206), tq 50x10 (1208..1707), qb 10 (1708..1717)
   hist_tab  [nb*nb, 800]  the same two history vectors for T[bf,bl] = W_f tanh(dense(E_f|E_l)) + b
   cand_tab  [nb*nb, 1208] the same candidate block for T[bf,bl] (+ the constants coming from Q.bias)
+  cand16    [news, 2400]  fp16: w1 w2 w3 of cand_rows as hi/lo pairs (x = hi + lo to 2^-22), the M operand
+                          of the tensor-core scoring kernel, streamed by cp.async without touching registers
+  ctab16    [nb*nb, 2400] fp16: the same for cand_tab
 
 A LIME news vector is v(news, bf, bl) = vc[news] + T[bf, bl]; everything the scoring kernel needs is
 linear in v, so it is cached as a per-news part plus a per-bucket-pair part.
@@ -28,8 +31,9 @@ from ._lib import LimeImpressions, LimeNewsCache, check
 D = 400
 HIST_LD, CAND_LD, HTAB_LD, CTAB_LD = 852, 1720, 800, 1208
 HIST_GW, HIST_T, HIST_TOPIC_ID, HIST_GW_ABSMAX = 400, 800, 850, 851
-CAND_SCAL, CAND_TQ, CAND_NFOLD, CAND_TOPIC_ID = 1200, 1208, 1207, 1718
-TOPIC_TAB_LD, MAX_TOPICS = 12, 1024
+CAND_SCAL, CAND_TQ, CAND_NFOLD, CAND_TOPIC_ID, CAND_ABSMAX = 1200, 1208, 1207, 1718, 1207
+F16_SAFE = 32768.0
+TOPIC_TAB_LD, MAX_TOPICS, TC_MAX_HISTORY = 12, 1024, 56
 TOPIC, TOPIC_LD, HEADS = 50, 52, 10
 LOG2E = 1.4426950408889634
 
@@ -183,8 +187,9 @@ class ScoringEngine:
         self._topic_ids = {}          # (category, subCategory) key -> compact id
         self._topic_vec = []          # [52] topic representation per id (device)
         self._topic_tq = []           # [510] candidate-role affine image per id (device)
-        self._topic_table = None      # [T, T, 12] head logits, rebuilt when the registry grows
+        self._topic_table = None      # [T, T, 12] log2(e)-scaled head logits, rebuilt when the registry grows
         self._topic_table_n = 0
+        self._topic_absmax = 0.0
 
     def _register_topics(self, category, subCategory, hist, cand):
         """Assign compact topic ids to the news of freshly built cache rows and stamp them into the
@@ -218,6 +223,7 @@ class ScoringEngine:
                                             tab.data_ptr(), torch.cuda.current_stream().cuda_stream),
                   "lime_topic_pair_table")
             self._topic_table, self._topic_table_n = tab, T
+            self._topic_absmax = float(tab.abs().max())      # one scalar per registry change (host read)
         return self._topic_table, T
 
     # -- fold the user-encoder weights (once per checkpoint) ---------------------------------------
@@ -304,9 +310,12 @@ class ScoringEngine:
         ctab = torch.zeros(nb2, CTAB_LD, **f32)
         ops.linear(htab[:, :D], G, bias=cconst, out=ctab[:, :CAND_NFOLD], n=CAND_NFOLD)
         F["hist_tab"], F["cand_tab"] = htab, ctab
-        tabmax = torch.empty(nb2, **f32)
-        ops.row_absmax(htab[:, D:], tabmax)
-        F["tab_gw_absmax"] = float(tabmax.max())        # one scalar per checkpoint (host read at fold time)
+        tabmax = torch.empty(2, nb2, **f32)
+        ops.row_absmax(htab[:, D:], tabmax[0])
+        F["ctab16"] = ops.split_f16_pairs(ctab, 3, absmax=tabmax[1])
+        tm = tabmax.max(dim=1).values.tolist()          # two scalars per checkpoint (host read at fold time)
+        F["tab_gw_absmax"] = tm[0]
+        F["tc_tables_ok"] = int(tm[1] <= F16_SAFE)
         self._fold, self._fp = F, fp
         return F
 
@@ -339,7 +348,12 @@ class ScoringEngine:
         self._register_topics(category, subCategory, hist, cand)
         return hist, cand
 
-    def cache_struct(self, hist_rows, cand_rows):
+    def split_candidates(self, cand_rows):
+        """cand16 [n, 2400] fp16: the folded candidate vectors as hi/lo pairs; stamps max |w| of every row
+        into cand_rows[:, 1207] (the scoring kernel sends rows beyond the fp16 range to the exact kernel)."""
+        return ops.split_f16_pairs(cand_rows, 3, absmax=cand_rows[:, CAND_ABSMAX])
+
+    def cache_struct(self, hist_rows, cand_rows, cand16=None):
         F = self.fold()
         cfg = self.cfg
         table, T = self.topic_table()
@@ -348,6 +362,8 @@ class ScoringEngine:
             hist_tab=F["hist_tab"].data_ptr(), cand_tab=F["cand_tab"].data_ptr(),
             gate_bias=F["gate_bias"].data_ptr(), un_prefix=F["un_prefix"].data_ptr(),
             topic_table=table.data_ptr() if table is not None else None, num_topics=T,
+            cand16=cand16.data_ptr() if cand16 is not None else None, ctab16=F["ctab16"].data_ptr(),
+            topic_logit_absmax=self._topic_absmax, tc_tables_ok=F["tc_tables_ok"],
             tab_gw_absmax=F["tab_gw_absmax"],
             news_num=hist_rows.shape[0], num_buckets=cfg.num_buckets,
             user_nodes=F["un_prefix"].shape[0], sigmoid_alpha=float(cfg.sigmoid_scaling_alpha),
@@ -364,10 +380,15 @@ class ScoringEngine:
         return hist_rows[:, :D] + F["hist_tab"][:, :D].index_select(0, idx.reshape(-1))
 
     def score(self, hist_rows, cand_rows, dimp, prefix_main, tail_start=None, prefix_tail=None,
-              pair_index_base=0, out=None):
-        """Launch the fused scoring kernel over a DeviceImpressions set -> fp32 scores [P]."""
+              pair_index_base=0, out=None, cand16=None):
+        """Launch the fused scoring kernel over a DeviceImpressions set -> fp32 scores [P].
+        ``cand16``: split_candidates(cand_rows) if the caller keeps it (NewsVectorCache does); derived
+        here otherwise."""
         lib = _lib.require_device()
-        cache = self.cache_struct(hist_rows, cand_rows)
+        if cand16 is None and dimp.max_history <= TC_MAX_HISTORY:
+            cand16 = self.split_candidates(cand_rows)
+        cache = self.cache_struct(hist_rows, cand_rows, cand16)
+        self._keepalive = cand16
         st = dimp.struct()
         if out is None:
             out = torch.empty(dimp.num_pairs, dtype=torch.float32, device=hist_rows.device)

@@ -31,14 +31,16 @@ def test_abi_version(lib):
 
 def test_struct_sizes_match_header(lib):
     # the ctypes mirrors against sizeof() as compiled from include/lime_b200.h
-    assert ctypes.sizeof(_lib.LimeNewsCache) == lib.lime_sizeof_news_cache() == 7 * 8 + 10 * 4
+    assert ctypes.sizeof(_lib.LimeNewsCache) == lib.lime_sizeof_news_cache() == 9 * 8 + 12 * 4
     assert ctypes.sizeof(_lib.LimeImpressions) == lib.lime_sizeof_impressions() == 11 * 8 + 3 * 4 + 4
 
 
 def test_smem_budget_query(lib):
     from lime_cikm25_b200.engine import choose_tile_c
     assert lib.lime_score_smem_bytes(50, 48) < 232448
-    assert choose_tile_c(50) == 37 and choose_tile_c(64) == 37          # tensor-core path: 3 * 37 <= 112 MMA columns
+    assert choose_tile_c(50) == 42 and choose_tile_c(56) == 42          # tensor-core path: 3 * 42 <= 128 M rows (TMEM lanes)
+    assert choose_tile_c(64) in (8, 16, 24, 32, 40, 48)                 # beyond 56 slots: exact kernel
+    assert lib.lime_score_smem_bytes(56, 42) <= 232448                  # the exact kernel doubles as the fallback
     assert choose_tile_c(200) in (8, 16, 24, 32, 40, 48)
     assert lib.lime_score_scratch_ints(10) == 14
     assert lib.lime_score_smem_bytes(200, choose_tile_c(200)) <= 232448
