@@ -51,6 +51,7 @@ extern "C" {
 #define LIME_CAND_TOPIC_ID 1718 /* int32 bit pattern, same id as LIME_HIST_TOPIC_ID                 */
 #define LIME_CAND_NFOLD 1207 /* columns produced by the folded GEMM: w1,w2,w3 + 7 scalars       */
 #define LIME_CAND_ABSMAX 1207 /* max |w1 w2 w3| of the row, written by lime_split_f16_pairs (fp16 operand range check) */
+#define LIME_CAND16_SCALE 1024.0f /* cand16 / ctab16 hold scale * w (keeps the lo halves out of the fp16 subnormals) */
 #define LIME_CAND16_LD 2400 /* fp16 elements per row of cand16 / ctab16: per folded vector k the 400 hi halves, then the 400 lo halves */
 #define LIME_HTAB_LD   800  /* per (freshness bucket, lifetime bucket): [ T | gwT ]            */
 #define LIME_CTAB_LD   1208 /* per bucket pair: [ w1T | w2T | w3T | scalT(8) ]                 */
@@ -221,8 +222,8 @@ int     lime_topic_pair_table(const float *topics, int64_t ldt, const float *tq,
                               float *out, void *stream);
 /* fp32 -> fp16 hi/lo pairs for the tensor-core scoring path: src [rows, lds] holds `blocks` blocks of
  * LIME_D columns; dst [rows, blocks * 2 * LIME_D] fp16 receives per block the hi halves then the lo halves
- * (x = hi + lo to 2^-22).  absmax (may be NULL): absmax[row * ldo] = max |x| of the row (inf for NaN). */
-int     lime_split_f16_pairs(const float *src, int64_t lds, int64_t rows, int32_t blocks, void *dst,
+ * (scale * x = hi + lo to 2^-22; the scoring kernel expects scale = LIME_CAND16_SCALE).  absmax (may be NULL): absmax[row * ldo] = max |x| of the row (inf for NaN). */
+int     lime_split_f16_pairs(const float *src, int64_t lds, int64_t rows, int32_t blocks, float scale, void *dst,
                              float *absmax, int64_t ldo, void *stream);
 /* Diagnostic: per-phase clock64() totals of the tensor-core scoring kernel since the last call (thread 0 of every CTA;
  * slots listed in score_tc.cu), host buffer of 16 uint64.  Synchronises the device. */

@@ -63,7 +63,7 @@ PROTOTYPES = {
     "lime_row_absmax": (C.c_int, [P, I64, I64, C.c_int, P, I64, P]),
     "lime_score_impressions": (C.c_int, [C.POINTER(LimeNewsCache), C.POINTER(LimeImpressions), I64, I32,
                                          I64, I32, P, P, P]),
-    "lime_split_f16_pairs": (C.c_int, [P, I64, I64, I32, P, P, I64, P]),
+    "lime_split_f16_pairs": (C.c_int, [P, I64, I64, I32, F32, P, P, I64, P]),
     "lime_score_phase_clocks": (C.c_int, [P]),
     "lime_score_smem_bytes": (I64, [I32, I32]),
     "lime_score_configure": (C.c_int, [I32, F32]),

@@ -33,7 +33,7 @@
 //     (the table's |logit| bound is checked by the host), multiplicity-weighted sums.
 //
 // CTA = 8 compute warps + 1 MMA-issuer warp + 1 loader warp, persistent, TWO per SM (113 KB of shared
-// memory and 128 TMEM columns each).  Per unit: metadata + dedup -> attention a[c][u] -> nodes ->
+// memory and 256 TMEM columns each).  Per unit: metadata + dedup -> attention a[c][u] -> nodes ->
 // 13 K-stages of 32 dims (the two 32-dim halves of the 64-dim SWIZZLE_128B tile are a 2-stage ring with
 // full/free mbarriers) -> epilogue TMEM -> lg / y / z -> pooling softmax + GraphSAGE mean + lifetime weight.
 #include "score_common.cuh"
@@ -60,7 +60,14 @@ constexpr int kBImg = kBRows * 128;
 constexpr int kTabLd = LIME_TOPIC_TAB_LD;
 constexpr int kAS = kTile;                      // row stride of a_s / lg / y / z  ([u][c])
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kS1Max = 1073741824.0f;         // sum o^2 <= 2^30  =>  every |o| <= 32768 (fp16 operand range)
+// Both operands are scaled by a power of two before the fp16 hi / lo split, so that the lo halves of typical values
+// (|w| ~ 1e-2, |o| ~ 1e-1) stay in the normal fp16 range (>= 6.1e-5) instead of losing bits as subnormals; the
+// accumulators are un-scaled in the epilogue (exact: powers of two).
+constexpr float kWScale = LIME_CAND16_SCALE;    // cand16 / ctab16 hold w * 1024
+constexpr float kOScale = 256.0f;               // O operand holds o * 256
+constexpr float kUnscale = 1.0f / (kWScale * kOScale);
+constexpr float kS1Max = 1073741824.0f;         // sum (256 o)^2 <= 2^30  =>  every |256 o| <= 32768 (fp16 operand range)
+constexpr float kWAbsMax = 32768.0f / kWScale;  // |w| beyond this leaves the fp16 operand range -> exact kernel
 constexpr int kC16 = LIME_CAND16_LD;            // fp16 elements per cand16 / ctab16 row: [k][hi | lo][400]
 
 // shared-memory map (bytes from the 1024-aligned base)
@@ -97,8 +104,9 @@ constexpr int OFF_PROF = OFF_MISC + 64;                       // phase clocks of
 constexpr int OFF_ROWOFF = OFF_PROF + 128;                    // loader: element offsets of the 128 M rows (news, table)
 constexpr int kSmemBytes = OFF_ROWOFF + 1024 + 1024;
 // phase-0 scratch inside the node-sum area
-constexpr int OFF_HKN = OFF_S01, OFF_HKT = OFF_HKN + kH * 4, OFF_HKM = OFF_HKT + kH * 4, OFF_HFIRST = OFF_HKM + kH * 4;
-static_assert(OFF_HFIRST + kH * 4 <= OFF_MID, "phase-0 scratch overflows the node-sum area");
+constexpr int OFF_HKN = OFF_S01, OFF_HKT = OFF_HKN + kH * 4, OFF_HTP = OFF_HKT + kH * 4, OFF_HGA = OFF_HTP + kH * 4;
+constexpr int OFF_HFIRST = OFF_HGA + kH * 4, OFF_HMULT = OFF_HFIRST + kH * 4;
+static_assert(OFF_HMULT + kH * 4 <= OFF_MID, "phase-0 scratch overflows the node-sum area");
 static_assert(3 * kH * kAS * 4 <= 2 * kBImg, "epilogue alias overflows the O operand images");
 static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
 static_assert(3 * kTile <= 128 && kTile <= 48 && kTile >= 32, "candidate rows: 32 per k in TMEM quadrants 0-2, the rest in quadrant 3");
@@ -117,7 +125,9 @@ constexpr float kY0 = -0.70710678118654752f, kY1 = 0.70710678118654752f;
 // Phase timing (diagnostic): thread 0 of every CTA accumulates clock64() deltas per phase; lime_score_phase_clocks reads
 // and clears the totals.  Slots: 0 metadata, 1 dedup, 2 attention, 3 nodes, 4 operand production (incl. ring waits),
 // 5 wait for the last MMA, 6 epilogue, 7 pooling, 8 final score, 9 units, 10 barrier at the end of production.
+// Compiled in only with -DLIME_TC_PHASE_CLOCKS (make PHASE_CLOCKS=1): the extra live registers cost spills.
 __device__ unsigned long long g_phase_clocks[16];
+#ifdef LIME_TC_PHASE_CLOCKS
 #define LIME_TICK(slot)                                                  \
     do {                                                                 \
         if (tid == 0) {                                                  \
@@ -126,6 +136,9 @@ __device__ unsigned long long g_phase_clocks[16];
             t_last = now__;                                              \
         }                                                                \
     } while (0)
+#else
+#define LIME_TICK(slot) do { } while (0)
+#endif
 
 template <int NODES> __device__ __forceinline__ float node_x(int j) {
     if (NODES == 2) return j == 0 ? kY0 : kY1;
@@ -183,9 +196,11 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
                                                  const uint32_t *rowoff_s, const __half *cand16, const __half *ctab16,
                                                  uint64_t *bar_full, uint64_t *bar_free, uint32_t &use0, uint32_t &use1) {
     const int sub = tid & 7;
-    // candidate operand (M side): warp w streams the row groups 2w and 2w + 1 of every stage with cp.async -- lane =
-    // (row in group, 16-byte chunk), so one instruction moves the 64 contiguous bytes of a stage for 8 operand rows
-    const int a_rsub = (tid >> 2) & 7, a_ch = tid & 3, a_g0 = tid >> 5;      // row groups a_g0 + 7 i (i < 3) of 8 rows each
+    // candidate operand (M side): warp w streams the row groups w, w + 7, w + 14 of every stage with cp.async -- lane =
+    // (row in group, 16-byte chunk), one instruction moves the 64 contiguous bytes of a stage for 8 operand rows.  The
+    // copies of stage k + 1 are issued right after the O rows of stage k, so they fly while stage k + 1 is evaluated;
+    // cp.async.mbarrier.arrive.noinc publishes them when they land (no thread waits for the data).
+    const int a_rsub = (tid >> 2) & 7, a_ch = tid & 3, a_g0 = tid >> 5;
     uint32_t a_on[3], a_ot[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -194,6 +209,28 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
         a_ot[i] = g < 16 ? rowoff_s[128 + 8 * g + a_rsub] : 0u;
     }
     const uint32_t a_dst = tc::smem_u32(base) + OFF_A + (uint32_t)a_g0 * 1024u + (uint32_t)a_rsub * 128u;
+    auto issue_copies = [&](int kc) {       // stage kc -> ring slot kc & 1 (waits until the MMAs of stage kc - 2 have drained it)
+        const int s = kc & 1;
+        const uint32_t uses = s ? use1 : use0;
+        if (uses >= 1) tc::mbar_wait(bar_free + s, (uses - 1) & 1u);
+        if (kc < kStages - 1 || a_ch < (kD - 32 * (kStages - 1)) / 8) {
+            const uint32_t dst = a_dst + (uint32_t)(((4 * s + a_ch) ^ a_rsub) << 4);
+            const int eo = 32 * kc + 8 * a_ch;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                if (a_on[i] != 0xffffffffu) {
+                    const uint32_t di = dst + (uint32_t)(kCWarps * i) * 1024u;
+                    cp_async16(di, cand16 + a_on[i] + eo);
+                    cp_async16(di + kAImg, cand16 + a_on[i] + kD + eo);
+                    cp_async16(di + 2 * kAImg, ctab16 + a_ot[i] + eo);
+                    cp_async16(di + 3 * kAImg, ctab16 + a_ot[i] + kD + eo);
+                }
+            }
+        }
+        cp_async_mbar_arrive_noinc(bar_full + s);
+        if (s) ++use1; else ++use0;
+    };
+    issue_copies(0);
     bool ok[TPT];
     const float *hrow[TPT], *trow[TPT];
     float aj[TPT][NODES], ps[TPT][2 * NODES];
@@ -212,7 +249,7 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
     }
     // one row per thread: stage kc + 1's global loads are in flight while stage kc is evaluated (two rows per
     // thread: no register room for that, the two rows overlap each other's latency instead)
-    constexpr bool kPipe = true;
+    constexpr bool kPipe = TPT == 1;
     float4 nx[TPT][4];
 #pragma unroll
     for (int t = 0; t < TPT; ++t) {
@@ -238,8 +275,8 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
         }
 #pragma unroll
         for (int t = 0; t < TPT; ++t) {
-            v[t][0] = nx[t][0].x + nx[t][1].x; v[t][1] = nx[t][0].y + nx[t][1].y;
-            v[t][2] = nx[t][0].z + nx[t][1].z; v[t][3] = nx[t][0].w + nx[t][1].w;
+            v[t][0] = (nx[t][0].x + nx[t][1].x) * kOScale; v[t][1] = (nx[t][0].y + nx[t][1].y) * kOScale;
+            v[t][2] = (nx[t][0].z + nx[t][1].z) * kOScale; v[t][3] = (nx[t][0].w + nx[t][1].w) * kOScale;
             gg[t][0] = nx[t][2].x + nx[t][3].x; gg[t][1] = nx[t][2].y + nx[t][3].y;
             gg[t][2] = nx[t][2].z + nx[t][3].z; gg[t][3] = nx[t][2].w + nx[t][3].w;
         }
@@ -252,24 +289,7 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
                 nx[t][3] = ldg4(trow[t] + kD + d0 + 32);
             }
         }
-        const uint32_t uses = s ? use1 : use0;
-        if (uses >= 1) tc::mbar_wait(bar_free + s, (uses - 1) & 1u);
-        if (kc < kStages - 1 || a_ch < (kD - 32 * (kStages - 1)) / 8) {
-            const uint32_t dst = a_dst + (uint32_t)(((4 * s + a_ch) ^ a_rsub) << 4);
-            const int eo = 32 * kc + 8 * a_ch;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                if (a_on[i] != 0xffffffffu) {
-                    const uint32_t di = dst + (uint32_t)(kCWarps * i) * 1024u;
-                    cp_async16(di, cand16 + a_on[i] + eo);
-                    cp_async16(di + kAImg, cand16 + a_on[i] + kD + eo);
-                    cp_async16(di + 2 * kAImg, ctab16 + a_ot[i] + eo);
-                    cp_async16(di + 3 * kAImg, ctab16 + a_ot[i] + kD + eo);
-                }
-            }
-        }
-        cp_async_mbar_arrive_noinc(bar_full + s);      // arrives when this thread's copies have landed
-        if (d0 < kD) {
+        if (d0 < kD) {      // the slot is free: this thread waited for it when it issued the stage's copies
             const float4 bb4 = *reinterpret_cast<const float4 *>(bias_s + d0);
             const float bb[4] = {bb4.x, bb4.y, bb4.z, bb4.w};
 #pragma unroll
@@ -299,7 +319,7 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
         }
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(bar_full + s);
-        if (s) ++use1; else ++use0;
+        if (kc + 1 < kStages) issue_copies(kc + 1);
     }
     // node sums of the row: sum o, sum o^2 per node, over the 8 lanes that share the row
 #pragma unroll
@@ -314,8 +334,8 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
             bool in_range = true;
 #pragma unroll
             for (int j = 0; j < NODES; ++j) {
-                s01_s[u * 8 + 2 * j] = ps[t][2 * j];
-                s01_s[u * 8 + 2 * j + 1] = ps[t][2 * j + 1];
+                s01_s[u * 8 + 2 * j] = ps[t][2 * j] * (1.0f / kOScale);
+                s01_s[u * 8 + 2 * j + 1] = ps[t][2 * j + 1] * (1.0f / (kOScale * kOScale));
                 in_range = in_range && (ps[t][2 * j + 1] <= kS1Max);
             }
             if (!in_range) atomicOr(flag_s, 4);   // outside the fp16 operand range (or NaN): exact kernel
@@ -342,8 +362,15 @@ __device__ __forceinline__ void epilogue(uint32_t tmem, int warp, int lane, int 
     const int nblocks = (NODES * nrows + 15) >> 4;
     const int bstep = qd + 4 < kCWarps ? 2 : 1;      // quadrants whose partner warp w + 4 is the MMA issuer are walked by one warp
     for (int b = bstep == 2 ? warp >> 2 : 0; b < nblocks; b += bstep) {
+      {
+        // the two accumulators of the block (news part, table part): both loads are issued before the single wait
+        uint32_t rn[16], rt[16];
+        tc::tmem_ld16_nowait(taddr + 16 * b, rn);
+        tc::tmem_ld16_nowait(taddr + 128 + 16 * b, rt);
+        tc::tmem_ld_wait();
         float v[16];
-        tc::tmem_ld16(taddr + 16 * b, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rn[i]) + __uint_as_float(rt[i]);
 #pragma unroll
         for (int i = 0; i < UPB; ++i) {
             const int ul = UPB * b + i;
@@ -373,10 +400,11 @@ __device__ __forceinline__ void epilogue(uint32_t tmem, int warp, int lane, int 
                 // LayerNorm folded into the dot: the candidate vectors are mean-centred, so x.w = rstd * (o.w)
                 const float mu = s0 * (1.0f / kD);
                 const float var = fmaxf(fmaf(-mu, mu, s1 * (1.0f / kD)), 0.0f);
-                const float rstd = rsqrtf(var + ln_eps);
+                const float rstd = rsqrtf(var + ln_eps) * kUnscale;
                 if (valid) outk[u * kAS + c] = fmaf(rstd, p, bk);
             }
         }
+      }
     }
 }
 
@@ -388,9 +416,7 @@ __device__ __forceinline__ void epilogue(uint32_t tmem, int warp, int lane, int 
 template <int LPC>
 __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, int cnt, int nun, int warp, int lane,
                                           const int *ctopic, const int *utopic, const int *umask, const float *umult,
-                                          float *a_s, unsigned long long *prof) {
-    const int tid = threadIdx.x;
-    long long t_last = clock64();
+                                          float *a_s) {
     constexpr int CPW = 32 / LPC;                 // candidates per warp and round
     const int l = lane & (LPC - 1), g = lane / LPC;
     float w[4], mu[4];
@@ -403,7 +429,6 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
         w[i] = (in && umask[u] != 0) ? mu[i] : 0.0f;
         tp[i] = in ? utopic[u] : 0;
     }
-    LIME_TICK(11);
     for (int c0 = CPW * warp; c0 < cnt; c0 += CPW * kCWarps) {
         const int c = c0 + g;
         const bool cvalid = c < cnt;
@@ -420,8 +445,6 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
                 x[i][1] = ldg4(r0 + 4);
                 x[i][2] = ldg4(r0 + 8);
             }
-            if (__float_as_int(x[0][0].x) == 0x7fc12345 || __float_as_int(x[3][2].y) == 0x7fc12345) a_s[0] = 0.f;   // wait for the loads
-            LIME_TICK(12);
             float e[4][LIME_CA_HEADS], sum[LIME_CA_HEADS];
 #pragma unroll
             for (int hd = 0; hd < LIME_CA_HEADS; ++hd) sum[hd] = 0.0f;
@@ -440,7 +463,6 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
 #pragma unroll
                 for (int hd = 0; hd < LIME_CA_HEADS; ++hd) sum[hd] += __shfl_xor_sync(0xffffffffu, sum[hd], o);
             }
-            LIME_TICK(13);
 #pragma unroll
             for (int hd = 0; hd < LIME_CA_HEADS; ++hd) sum[hd] = __fdividef(1.0f, sum[hd]);
 #pragma unroll
@@ -470,7 +492,6 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
                 if (u < U) a_s[u * kAS + c] = e2[i] * inv2;
             }
         }
-        LIME_TICK(14);
     }
 }
 
@@ -502,8 +523,10 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
     int *ufirst = reinterpret_cast<int *>(base + OFF_UFIRST);
     int *hkn = reinterpret_cast<int *>(base + OFF_HKN);
     int *hkt = reinterpret_cast<int *>(base + OFF_HKT);
-    int *hkm = reinterpret_cast<int *>(base + OFF_HKM);
+    int *htp = reinterpret_cast<int *>(base + OFF_HTP);
+    float *hga = reinterpret_cast<float *>(base + OFF_HGA);
     int *hfirst = reinterpret_cast<int *>(base + OFF_HFIRST);
+    int *hmult = reinterpret_cast<int *>(base + OFF_HMULT);
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(base + OFF_BARS);
     uint64_t *bar_free = bar_full + 2;
     uint64_t *bar_accum = bar_full + 4;
@@ -530,17 +553,19 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
         tc::mbar_fence_init();
         misc[M_NEXT] = atomicAdd(args.work_counter, 1);
     }
-    if (warp == kMmaWarp) tc::tmem_alloc(reinterpret_cast<uint32_t *>(base + OFF_MISC) + M_TMEM, 128);
+    if (warp == kMmaWarp) tc::tmem_alloc(reinterpret_cast<uint32_t *>(base + OFF_MISC) + M_TMEM, 256);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *(reinterpret_cast<volatile uint32_t *>(base + OFF_MISC) + M_TMEM);
 
+#ifdef LIME_TC_PHASE_CLOCKS
     unsigned long long *prof = reinterpret_cast<unsigned long long *>(base + OFF_PROF);
     if (tid == 0) {
         for (int i = 0; i < 16; ++i) prof[i] = 0;
     }
     long long t_last = clock64();
+#endif
     uint32_t use0 = 0, use1 = 0;     // uses of the two ring halves so far (every role counts the same sequence)
     uint32_t pass_iter = 0;          // passes processed so far (phase of bar_accum)
 
@@ -554,7 +579,9 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
         __syncthreads();
         const int unit = misc[M_UNIT];
         if (unit >= I.num_units) break;
+#ifdef LIME_TC_PHASE_CLOCKS
         if (tid == 0) { t_last = clock64(); ++prof[9]; }
+#endif
         const int imp = I.unit_imp[unit];
         const int pair0 = I.unit_pair0[unit];
         const int cnt = I.unit_count[unit];
@@ -567,10 +594,15 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             int n = I.hist_news[o];
             n = (n < 0 || n >= C.news_num) ? 0 : n;
             hkn[h] = n;
-            hkm[h] = I.hist_mask[o] != 0 ? 1 : 0;
+            const float *hrow = C.hist_rows + (size_t)n * LIME_HIST_LD;
+            const int tp = __float_as_int(__ldg(hrow + LIME_HIST_TOPIC_ID));
+            const float ga = __ldg(hrow + LIME_HIST_GW_ABSMAX);
+            const int mk = I.hist_mask[o] != 0 ? 1 : 0;
             const int bf = bucketize_seconds(I.hist_fresh[o], args.bucket_scale, nb);
             const int bl = bucketize_seconds(I.hist_life[o], args.bucket_scale, nb);
-            hkt[h] = bf * nb + bl;
+            hkt[h] = 2 * (bf * nb + bl) + mk;          // second key word: bucket pair and mask
+            htp[h] = (tp < 0 || tp >= T) ? 0 : tp;
+            hga[h] = ga;
         }
         for (int c = tid; c < cnt; c += kThreads) {
             const long long p = (long long)pair0 + c;
@@ -589,7 +621,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             ctopic[c] = (tp < 0 || tp >= T) ? 0 : tp;
 #pragma unroll
             for (int k = 0; k < 4; ++k) cscal[c * 4 + k] = __ldg(crow + LIME_CAND_SCAL + 3 + k) + __ldg(ctr + LIME_CAND_SCAL + 3 + k);
-            if (!(__ldg(crow + LIME_CAND_ABSMAX) <= 32768.0f)) atomicOr(flag_s, 4);   // fp16 operand range
+            if (!(__ldg(crow + LIME_CAND_ABSMAX) <= kWAbsMax)) atomicOr(flag_s, 4);   // fp16 operand range
             pool_s[c * 4 + 0] = -INFINITY;
             pool_s[c * 4 + 1] = 0.0f;
             pool_s[c * 4 + 2] = 0.0f;
@@ -609,73 +641,66 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             rowoff_s[128 + r] = (uint32_t)ctab[cc] * (uint32_t)kC16 + (uint32_t)(k * 2 * kD);
         }
         // ---------------- dedup of the history slots: (news, bucket pair, mask) -> unique rows -----
-        if (tid < H) {
-            const int n = hkn[tid], t = hkt[tid], m = hkm[tid];
-            int f = tid;
-            for (int j = 0; j < tid; ++j) {
-                if (hkn[j] == n && hkt[j] == t && hkm[j] == m) {
-                    f = j;
-                    break;
+        // warp w takes the reference slots w, w + 7, ...; a lane holds the keys of slots lane and lane + 32, two ballots
+        // give the set of equal slots: its lowest member is the unique row, its size the multiplicity
+        if (warp < kCWarps) {
+            const int ha = lane, hb = lane + 32;
+            const int k1a = ha < H ? hkn[ha] : -1 - ha, k2a = ha < H ? hkt[ha] : -1;
+            const int k1b = hb < H ? hkn[hb] : -1 - hb, k2b = hb < H ? hkt[hb] : -1;
+            const unsigned p0lo = pz0 >= 32 ? 0xffffffffu : (1u << pz0) - 1u, p0hi = pz0 > 32 ? (1u << (pz0 - 32)) - 1u : 0u;
+            const unsigned p1lo = pz1 >= 32 ? 0xffffffffu : (1u << pz1) - 1u, p1hi = pz1 > 32 ? (1u << (pz1 - 32)) - 1u : 0u;
+            for (int r = warp; r < H; r += kCWarps) {
+                const int r1 = hkn[r], r2 = hkt[r];
+                const unsigned m0 = __ballot_sync(0xffffffffu, k1a == r1 && k2a == r2);
+                const unsigned m1 = __ballot_sync(0xffffffffu, k1b == r1 && k2b == r2);
+                if (lane == 0) {
+                    hfirst[r] = m0 ? __ffs(m0) - 1 : 31 + __ffs(m1);
+                    hmult[r] = (__popc(m0) + __popc(m1)) | ((__popc(m0 & p0lo) + __popc(m1 & p0hi)) << 8) |
+                               ((__popc(m0 & p1lo) + __popc(m1 & p1hi)) << 16);
                 }
             }
-            hfirst[tid] = f;
         }
         __syncthreads();
-        if (warp < 2) {
-            const bool isf = tid < H && hfirst[tid < H ? tid : 0] == tid;
-            const unsigned bal = __ballot_sync(0xffffffffu, isf);
-            if (lane == 0) misc[M_WC0 + warp] = __popc(bal);
-            if (isf) hkm[tid] |= (__popc(bal & ((1u << lane) - 1u)) << 8) | 0x10000;   // rank inside the warp, "is first" bit
-        }
-        __syncthreads();
-        if (tid < H) {
-            const int km = hkm[tid];
-            if (km & 0x10000) {
-                const int u = ((km >> 8) & 0xff) + (warp == 1 ? misc[M_WC0] : 0);
-                unews[u] = hkn[tid];
-                utab[u] = hkt[tid];
-                umask[u] = km & 1;
-                ufirst[u] = tid;
+        if (warp == 0) {      // compaction: unique rows in slot order
+            const int ha = lane, hb = lane + 32;
+            const bool isfa = ha < H && hfirst[ha < H ? ha : 0] == ha, isfb = hb < H && hfirst[hb < H ? hb : 0] == hb;
+            const unsigned b0 = __ballot_sync(0xffffffffu, isfa), b1 = __ballot_sync(0xffffffffu, isfb);
+            const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int h = half ? hb : ha;
+                if (half ? isfb : isfa) {
+                    const int u = half ? __popc(b0) + __popc(b1 & lt) : __popc(b0 & lt);
+                    const int k2 = hkt[h], pk = hmult[h];
+                    unews[u] = hkn[h];
+                    utab[u] = k2 >> 1;
+                    umask[u] = k2 & 1;
+                    utopic[u] = htp[h];
+                    ugabs[u] = hga[h];
+                    umult[u] = (float)(pk & 0xff);
+                    ump0[u] = (float)((pk >> 8) & 0xff);
+                    ump1[u] = (float)((pk >> 16) & 0xff);
+                    prefetch_l2_bulk(C.hist_rows + (size_t)hkn[h] * LIME_HIST_LD, 2 * kD * 4);      // vc | gw, read in phase 2
+                }
             }
-        }
-        const int U = misc[M_WC0] + misc[M_WC1];
-        __syncthreads();
-        if (tid < U) {
-            const int f = ufirst[tid];
-            int m = 0, m0 = 0, m1 = 0;
-            for (int h = 0; h < H; ++h) {
-                const int eq = hfirst[h] == f ? 1 : 0;
-                m += eq;
-                m0 += (h < pz0) ? eq : 0;
-                m1 += (h < pz1) ? eq : 0;
-            }
-            umult[tid] = (float)m;
-            ump0[tid] = (float)m0;
-            ump1[tid] = (float)m1;
-            const float *hrow = C.hist_rows + (size_t)unews[tid] * LIME_HIST_LD;
-            prefetch_l2_bulk(hrow, 2 * kD * 4);                          // vc | gw, read in phase 2
-            int tp = __float_as_int(__ldg(hrow + LIME_HIST_TOPIC_ID));
-            utopic[tid] = (tp < 0 || tp >= T) ? 0 : tp;
-            ugabs[tid] = __ldg(hrow + LIME_HIST_GW_ABSMAX);
-        }
-        if (warp == 2) {   // number of unmasked history slots
-            int nun = 0;
-            for (int h = lane; h < H; h += 32) nun += hkm[h] & 1;
+            int nun = (ha < H ? hkt[ha] & 1 : 0) + (hb < H ? hkt[hb] & 1 : 0);      // unmasked history slots
             nun = __reduce_add_sync(0xffffffffu, nun);
-            if (lane == 0) misc[M_NUN] = nun;
+            if (lane == 0) {
+                misc[M_U] = __popc(b0) + __popc(b1);
+                misc[M_NUN] = nun;
+            }
         }
         __syncthreads();
+        const int U = misc[M_U];
         LIME_TICK(1);
 
         // ================= roles ======================================================================
         if (warp < kCWarps) {
             // ---------------- phase 1: candidate-aware attention weights a[u][c] (layers.py:66-81) ------
-            if (U <= 32) attention<8>(C, T, U, cnt, misc[M_NUN], warp, lane, ctopic, utopic, umask, umult, a_s, prof);
-            else         attention<16>(C, T, U, cnt, misc[M_NUN], warp, lane, ctopic, utopic, umask, umult, a_s, prof);
-            if (tid == 0) t_last = clock64();
+            if (U <= 32) attention<8>(C, T, U, cnt, misc[M_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
+            else         attention<16>(C, T, U, cnt, misc[M_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
             bar_compute();
-            LIME_TICK(15);
-            if (tid == 0) t_last = clock64();
+            LIME_TICK(2);
 
             // ---------------- interpolation nodes per unique row (4 lanes per row) --------------------
             {
@@ -770,12 +795,14 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
                         const uint64_t a_th = tc::smem_desc_sw128(sb + OFF_A + 2 * kAImg), a_tl = tc::smem_desc_sw128(sb + OFF_A + 3 * kAImg);
                         for (int ks = 0; ks < ksteps; ++ks) {
                             const uint64_t k2 = (uint64_t)(2 * (2 * s + ks));   // 32 bytes per K step of 16
-                            tc::mma_f16(tmem, a_nh + k2, bhi + k2, idesc, (kc | ks) != 0);
+                            // two accumulators (news part: columns 0.., table part: columns 128..): half as many
+                            // accumulation steps each; the epilogue adds them in fp32
+                            tc::mma_f16(tmem, a_nl + k2, bhi + k2, idesc, (kc | ks) != 0);
                             tc::mma_f16(tmem, a_nh + k2, blo + k2, idesc, true);
-                            tc::mma_f16(tmem, a_nl + k2, bhi + k2, idesc, true);
-                            tc::mma_f16(tmem, a_th + k2, bhi + k2, idesc, true);
-                            tc::mma_f16(tmem, a_th + k2, blo + k2, idesc, true);
-                            tc::mma_f16(tmem, a_tl + k2, bhi + k2, idesc, true);
+                            tc::mma_f16(tmem, a_nh + k2, bhi + k2, idesc, true);
+                            tc::mma_f16(tmem + 128, a_tl + k2, bhi + k2, idesc, (kc | ks) != 0);
+                            tc::mma_f16(tmem + 128, a_th + k2, blo + k2, idesc, true);
+                            tc::mma_f16(tmem + 128, a_th + k2, bhi + k2, idesc, true);
                         }
                         tc::mma_commit(bar_free + s);
                         if (kc == kStages - 1) tc::mma_commit(bar_accum);
@@ -836,10 +863,18 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
                         const float m_new = fmaxf(m_old, m);
                         const float f_old = ex2_approx((m_old - m_new) * kLog2e);    // 0 on the first pass (m_old = -inf)
                         const float f_new = ex2_approx((m - m_new) * kLog2e);
+                        const float l_new = fmaf(pool_s[c * 4 + 1], f_old, l * f_new);
+                        const float acc_new = fmaf(pool_s[c * 4 + 2], f_old, acc * f_new);
+                        const float ms_new = pool_s[c * 4 + 3] + ms;
                         pool_s[c * 4 + 0] = m_new;
-                        pool_s[c * 4 + 1] = fmaf(pool_s[c * 4 + 1], f_old, l * f_new);
-                        pool_s[c * 4 + 2] = fmaf(pool_s[c * 4 + 2], f_old, acc * f_new);
-                        pool_s[c * 4 + 3] += ms;
+                        pool_s[c * 4 + 1] = l_new;
+                        pool_s[c * 4 + 2] = acc_new;
+                        pool_s[c * 4 + 3] = ms_new;
+                        // lifetime-weighted click score (util.py:23-49) once the last pass is in; the rare P > H case
+                        // (user-node rows in the GraphSAGE mean) is finished after the pass loop
+                        const int P = cP[c];
+                        if (pass == npass - 1 && P <= H)
+                            args.scores[(long long)pair0 + c] = (ms_new / (float)P + cscal[c * 4 + 3] + acc_new / l_new) * cw[c];
                     }
                 }
             }
@@ -853,35 +888,37 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             if (flag_s[0] & 1) atomicAdd(args.fallback_count + 2, 1);   // statistics: 4-node units
         }
 
-        // ---------------- lifetime-weighted click score (util.py:23-49) --------------------------------
-        if (warp < kCWarps) {
+        // ---------------- P > H: user-node rows take part in the GraphSAGE mean (userEncoders.py:121,153) -------
+        if ((args.prefix_main > H || args.prefix_tail > H) && warp < kCWarps) {
             for (int c = warp; c < cnt; c += kCWarps) {
                 const int P = cP[c];
-                float un = 0.f;
-                if (P > H) {   // user-node rows take part in the GraphSAGE mean (userEncoders.py:121,153)
+                if (P > H) {
                     int jn = P - H - 1;
                     jn = jn < C.user_nodes ? jn : C.user_nodes - 1;
                     const float *uu = C.un_prefix + (size_t)jn * kD;
                     const float *hr2 = C.hist_rows + (size_t)cnews[c] * LIME_HIST_LD + LIME_HIST_VC;
                     const float *tr2 = C.hist_tab + (size_t)ctab[c] * LIME_HTAB_LD;
+                    float un = 0.f;
                     for (int d = lane; d < kD; d += 32) un = fmaf(hr2[d] + tr2[d], uu[d], un);
                     un = warp_sum(un);
-                }
-                if (lane == 0) {
-                    const float bs = (pool_s[c * 4 + 3] + un) / (float)P + cscal[c * 4 + 3] + pool_s[c * 4 + 2] / pool_s[c * 4 + 1];
-                    args.scores[(long long)pair0 + c] = bs * cw[c];
+                    if (lane == 0) {
+                        const float bs = (pool_s[c * 4 + 3] + un) / (float)P + cscal[c * 4 + 3] + pool_s[c * 4 + 2] / pool_s[c * 4 + 1];
+                        args.scores[(long long)pair0 + c] = bs * cw[c];
+                    }
                 }
             }
         }
         LIME_TICK(8);
     }
+#ifdef LIME_TC_PHASE_CLOCKS
     __syncthreads();
     if (tid == 0) {
         for (int i = 0; i < 16; ++i) atomicAdd(&g_phase_clocks[i], prof[i]);
     }
+#endif
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == kMmaWarp) tc::tmem_dealloc(tmem, 128);
+    if (warp == kMmaWarp) tc::tmem_dealloc(tmem, 256);
 }
 
 // out[(tc * T + th) * 12 + head] = log2(e) * ( sum_k tq[tc][k * 10 + head] * topics[th][k] + tq[tc][500 + head] )
@@ -910,9 +947,9 @@ __global__ void topic_pair_table_kernel(const float *__restrict__ topics, int64_
 }
 
 // src [rows, lds] fp32, `blocks` blocks of 400 columns -> dst [rows, blocks * 800] fp16: per block the 400 hi
-// halves followed by the 400 lo halves (x = hi + lo to 2^-22); absmax[row * ldo] = max |x| of the row
-__global__ void split_f16_pairs_kernel(const float *__restrict__ src, int64_t lds, int blocks, __half *__restrict__ dst,
-                                       float *__restrict__ absmax, int64_t ldo) {
+// halves followed by the 400 lo halves (scale * x = hi + lo to 2^-22); absmax[row * ldo] = max |x| of the row
+__global__ void split_f16_pairs_kernel(const float *__restrict__ src, int64_t lds, int blocks, float scale,
+                                       __half *__restrict__ dst, float *__restrict__ absmax, int64_t ldo) {
     __shared__ float red[4];
     const int64_t row = blockIdx.x;
     const float *s = src + row * lds;
@@ -921,8 +958,9 @@ __global__ void split_f16_pairs_kernel(const float *__restrict__ src, int64_t ld
     for (int e = threadIdx.x; e < blocks * kD; e += blockDim.x) {
         const int k = e / kD, dd = e - k * kD;
         const float x = s[e];
-        const __half h = __float2half_rn(x);
-        const __half l = __float2half_rn(x - __half2float(h));
+        const float xs = x * scale;
+        const __half h = __float2half_rn(xs);
+        const __half l = __float2half_rn(xs - __half2float(h));
         d[k * 2 * kD + dd] = h;
         d[k * 2 * kD + kD + dd] = l;
         mx = fmaxf(mx, fabsf(x));
@@ -970,12 +1008,12 @@ extern "C" int lime_score_phase_clocks(uint64_t *out16) {
     return 0;
 }
 
-extern "C" int lime_split_f16_pairs(const float *src, int64_t lds, int64_t rows, int32_t blocks, void *dst,
+extern "C" int lime_split_f16_pairs(const float *src, int64_t lds, int64_t rows, int32_t blocks, float scale, void *dst,
                                     float *absmax, int64_t ldo, void *stream) {
     LIME_CHECK_ARG(src && dst, "lime_split_f16_pairs: null argument");
     LIME_CHECK_ARG(blocks >= 1 && lds >= (int64_t)blocks * LIME_D, "lime_split_f16_pairs: blocks=%d lds=%lld", blocks, (long long)lds);
     if (rows <= 0) return 0;
-    lime::split_f16_pairs_kernel<<<(unsigned)rows, 128, 0, lime::as_stream(stream)>>>(src, lds, blocks, reinterpret_cast<__half *>(dst), absmax, ldo);
+    lime::split_f16_pairs_kernel<<<(unsigned)rows, 128, 0, lime::as_stream(stream)>>>(src, lds, blocks, scale, reinterpret_cast<__half *>(dst), absmax, ldo);
     LIME_LAUNCH_CHECK("split_f16_pairs_kernel");
     return 0;
 }

@@ -196,14 +196,17 @@ def row_absmax(m, out):
     return out
 
 
-def split_f16_pairs(src, blocks=3, absmax=None):
+CAND16_SCALE = 1024.0      # LIME_CAND16_SCALE
+
+
+def split_f16_pairs(src, blocks=3, absmax=None, scale=CAND16_SCALE):
     """lime_split_f16_pairs: fp32 [rows, >= blocks*400] (row-major view) -> fp16 [rows, blocks*800] with, per
     block of 400 columns, the hi halves then the lo halves (operand format of the tensor-core scoring
     kernel).  ``absmax``: optional 1-D (strided) fp32 view receiving max |x| per row."""
     lib = _lib.require_device()
     rows = src.shape[0]
     dst = torch.empty(rows, blocks * 800, dtype=torch.float16, device=src.device)
-    check(lib.lime_split_f16_pairs(_ptr(src, torch.float32, "src"), _rowmajor(src, "src"), rows, blocks, dst.data_ptr(),
+    check(lib.lime_split_f16_pairs(_ptr(src, torch.float32, "src"), _rowmajor(src, "src"), rows, blocks, float(scale), dst.data_ptr(),
                                    _ptr(absmax, torch.float32, "absmax") if absmax is not None else None,
                                    absmax.stride(0) if absmax is not None else 0, _stream()), "lime_split_f16_pairs")
     return dst
