@@ -51,6 +51,7 @@ extern "C" {
 #define LIME_CAND_TOPIC_ID 1718 /* int32 bit pattern, same id as LIME_HIST_TOPIC_ID                 */
 #define LIME_CAND_NFOLD 1207 /* columns produced by the folded GEMM: w1,w2,w3 + 7 scalars       */
 #define LIME_CAND_ABSMAX 1207 /* max |w1 w2 w3| of the row, written by lime_split_f16_pairs (fp16 operand range check) */
+#define LIME_META_LD 8      /* news_meta row: topic id | gw absmax | w absmax | B1 | B2 | B3 | cb | pad */
 #define LIME_CAND16_SCALE 1024.0f /* cand16 / ctab16 hold scale * w (keeps the lo halves out of the fp16 subnormals) */
 #define LIME_CAND16_LD 2400 /* fp16 elements per row of cand16 / ctab16: per folded vector k the 400 hi halves, then the 400 lo halves */
 #define LIME_HTAB_LD   800  /* per (freshness bucket, lifetime bucket): [ T | gwT ]            */
@@ -155,6 +156,9 @@ typedef struct {
     const void  *cand16;        /* [news_num, LIME_CAND16_LD] fp16: w1 w2 w3 of cand_rows as hi/lo pairs
                                    (lime_split_f16_pairs), or NULL (exact kernel only)               */
     const void  *ctab16;        /* [nb*nb, LIME_CAND16_LD] fp16: the same for cand_tab               */
+    const float *news_meta;     /* [news_num, LIME_META_LD]: the scalars phase 0 of the tensor-core kernel needs, packed
+                                   into one 32-byte sector per news (2 MB for 65k news: L2 resident) -- topic id (int32
+                                   bits), gw absmax, w absmax, B1, B2, B3, cb, 0; or NULL (exact kernel only)   */
     int32_t news_num;
     int32_t num_buckets;
     int32_t user_nodes;         /* config.batch_size (rows of user_node_embedding)               */

@@ -594,9 +594,9 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             int n = I.hist_news[o];
             n = (n < 0 || n >= C.news_num) ? 0 : n;
             hkn[h] = n;
-            const float *hrow = C.hist_rows + (size_t)n * LIME_HIST_LD;
-            const int tp = __float_as_int(__ldg(hrow + LIME_HIST_TOPIC_ID));
-            const float ga = __ldg(hrow + LIME_HIST_GW_ABSMAX);
+            const float2 mt = __ldg(reinterpret_cast<const float2 *>(C.news_meta + (size_t)n * LIME_META_LD));
+            const int tp = __float_as_int(mt.x);
+            const float ga = mt.y;
             const int mk = I.hist_mask[o] != 0 ? 1 : 0;
             const int bf = bucketize_seconds(I.hist_fresh[o], args.bucket_scale, nb);
             const int bl = bucketize_seconds(I.hist_life[o], args.bucket_scale, nb);
@@ -615,13 +615,15 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             cw[c] = lifetime_weight(I.cand_remaining ? I.cand_remaining[p] : __fsub_rn(lf, fr), C);
             cP[c] = (args.pair_index_base + p >= args.tail_start) ? args.prefix_tail : args.prefix_main;
             prefetch_l2_bulk(cand16 + (size_t)n * kC16, kC16 * 2);      // the operand rows this unit streams in phase 2
-            const float *crow = C.cand_rows + (size_t)n * LIME_CAND_LD;
+            const float4 m0 = ldg4(C.news_meta + (size_t)n * LIME_META_LD), m1 = ldg4(C.news_meta + (size_t)n * LIME_META_LD + 4);
             const float *ctr = C.cand_tab + (size_t)tb * LIME_CTAB_LD;
-            int tp = __float_as_int(__ldg(crow + LIME_CAND_TOPIC_ID));
+            const int tp = __float_as_int(m0.x);
             ctopic[c] = (tp < 0 || tp >= T) ? 0 : tp;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) cscal[c * 4 + k] = __ldg(crow + LIME_CAND_SCAL + 3 + k) + __ldg(ctr + LIME_CAND_SCAL + 3 + k);
-            if (!(__ldg(crow + LIME_CAND_ABSMAX) <= kWAbsMax)) atomicOr(flag_s, 4);   // fp16 operand range
+            cscal[c * 4 + 0] = m0.w + __ldg(ctr + LIME_CAND_SCAL + 3);
+            cscal[c * 4 + 1] = m1.x + __ldg(ctr + LIME_CAND_SCAL + 4);
+            cscal[c * 4 + 2] = m1.y + __ldg(ctr + LIME_CAND_SCAL + 5);
+            cscal[c * 4 + 3] = m1.z + __ldg(ctr + LIME_CAND_SCAL + 6);
+            if (!(m0.z <= kWAbsMax)) atomicOr(flag_s, 4);   // fp16 operand range
             pool_s[c * 4 + 0] = -INFINITY;
             pool_s[c * 4 + 1] = 0.0f;
             pool_s[c * 4 + 2] = 0.0f;

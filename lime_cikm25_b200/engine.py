@@ -353,7 +353,18 @@ class ScoringEngine:
         into cand_rows[:, 1207] (the scoring kernel sends rows beyond the fp16 range to the exact kernel)."""
         return ops.split_f16_pairs(cand_rows, 3, absmax=cand_rows[:, CAND_ABSMAX])
 
-    def cache_struct(self, hist_rows, cand_rows, cand16=None):
+    @staticmethod
+    def news_meta(hist_rows, cand_rows):
+        """[n, 8] fp32, one 32-byte sector per news: topic id (int32 bits) | gw absmax | w absmax | B1 B2 B3 cb | 0 --
+        the scalars phase 0 of the tensor-core kernel reads (column gather of existing cache values: plumbing).
+        Call after split_candidates (which stamps the w absmax column)."""
+        meta = torch.zeros(hist_rows.shape[0], 8, dtype=torch.float32, device=hist_rows.device)
+        meta[:, 0:2].copy_(hist_rows[:, HIST_TOPIC_ID:HIST_GW_ABSMAX + 1])
+        meta[:, 2].copy_(cand_rows[:, CAND_ABSMAX])
+        meta[:, 3:7].copy_(cand_rows[:, CAND_SCAL + 3:CAND_SCAL + 7])
+        return meta
+
+    def cache_struct(self, hist_rows, cand_rows, cand16=None, meta=None):
         F = self.fold()
         cfg = self.cfg
         table, T = self.topic_table()
@@ -363,6 +374,7 @@ class ScoringEngine:
             gate_bias=F["gate_bias"].data_ptr(), un_prefix=F["un_prefix"].data_ptr(),
             topic_table=table.data_ptr() if table is not None else None, num_topics=T,
             cand16=cand16.data_ptr() if cand16 is not None else None, ctab16=F["ctab16"].data_ptr(),
+            news_meta=meta.data_ptr() if meta is not None else None,
             topic_logit_absmax=self._topic_absmax, tc_tables_ok=F["tc_tables_ok"],
             tab_gw_absmax=F["tab_gw_absmax"],
             news_num=hist_rows.shape[0], num_buckets=cfg.num_buckets,
@@ -380,15 +392,16 @@ class ScoringEngine:
         return hist_rows[:, :D] + F["hist_tab"][:, :D].index_select(0, idx.reshape(-1))
 
     def score(self, hist_rows, cand_rows, dimp, prefix_main, tail_start=None, prefix_tail=None,
-              pair_index_base=0, out=None, cand16=None):
+              pair_index_base=0, out=None, cand16=None, meta=None):
         """Launch the fused scoring kernel over a DeviceImpressions set -> fp32 scores [P].
-        ``cand16``: split_candidates(cand_rows) if the caller keeps it (NewsVectorCache does); derived
-        here otherwise."""
+        ``cand16`` / ``meta``: split_candidates(cand_rows) and news_meta(hist_rows, cand_rows) if the caller keeps
+        them (NewsVectorCache does); derived here otherwise."""
         lib = _lib.require_device()
-        if cand16 is None and dimp.max_history <= TC_MAX_HISTORY:
+        if (cand16 is None or meta is None) and dimp.max_history <= TC_MAX_HISTORY:
             cand16 = self.split_candidates(cand_rows)
-        cache = self.cache_struct(hist_rows, cand_rows, cand16)
-        self._keepalive = cand16
+            meta = self.news_meta(hist_rows, cand_rows)
+        cache = self.cache_struct(hist_rows, cand_rows, cand16, meta)
+        self._keepalive = (cand16, meta)
         st = dimp.struct()
         if out is None:
             out = torch.empty(dimp.num_pairs, dtype=torch.float32, device=hist_rows.device)

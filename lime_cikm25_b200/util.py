@@ -43,13 +43,14 @@ class NewsVectorCache:
     hist_rows: torch.Tensor     # [news_num, 852] fp32
     cand_rows: torch.Tensor     # [news_num, 1720] fp32
     cand16: torch.Tensor = None  # [news_num, 2400] fp16 hi/lo pairs of cand_rows[:, :1200] (tensor-core scoring operand)
+    meta: torch.Tensor = None    # [news_num, 8] fp32 per-news scalars of the tensor-core kernel's phase 0
 
     @property
     def news_num(self):
         return int(self.hist_rows.shape[0])
 
     def nbytes(self):
-        return self.hist_rows.numel() * 4 + self.cand_rows.numel() * 4 + (self.cand16.numel() * 2 if self.cand16 is not None else 0)
+        return self.hist_rows.numel() * 4 + self.cand_rows.numel() * 4 + (self.cand16.numel() * 2 if self.cand16 is not None else 0) + (self.meta.numel() * 4 if self.meta is not None else 0)
 
 
 def build_news_cache(model, news: NewsTable, device=None, chunk=2048) -> NewsVectorCache:
@@ -61,7 +62,8 @@ def build_news_cache(model, news: NewsTable, device=None, chunk=2048) -> NewsVec
         hist, cand = model.scoring.build_rows(t(news.title_text), t(news.body_text), t(news.category),
                                               t(news.subCategory), chunk=chunk)
         cand16 = model.scoring.split_candidates(cand)
-    return NewsVectorCache(hist, cand, cand16)
+        meta = model.scoring.news_meta(hist, cand)
+    return NewsVectorCache(hist, cand, cand16, meta)
 
 
 def _tail(total_pairs, batch_size):
@@ -79,7 +81,7 @@ def score_impressions(model, cache: NewsVectorCache, dimp: DeviceImpressions, ba
     tail_start, prefix_tail = _tail(total, batch_size)
     return model.scoring.score(cache.hist_rows, cache.cand_rows, dimp, prefix_main=batch_size,
                                tail_start=tail_start, prefix_tail=prefix_tail,
-                               pair_index_base=pair_index_base, out=out, cand16=cache.cand16)
+                               pair_index_base=pair_index_base, out=out, cand16=cache.cand16, meta=cache.meta)
 
 
 def evaluate_device(model, cache, dimp, batch_size, pair_index_base=0, total_pairs=None, group=None,
