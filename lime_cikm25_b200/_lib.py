@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblime_b200.so")
+LIB_PATH = os.environ.get("LIME_B200_LIB") or os.path.join(_HERE, "liblime_b200.so")   # the override selects an experiment build
 
 c_float_p = C.c_void_p      # device pointers travel as integers (tensor.data_ptr())
 c_int_p = C.c_void_p

@@ -115,7 +115,8 @@ static_assert(OFF_BARS % 8 == 0 && OFF_AS % 16 == 0 && OFF_BIAS % 16 == 0 && OFF
 static_assert(2 * kH <= kBRows && kBRows % 16 == 0 && kBRows <= 128 && kH % 8 == 0 && kH <= 64, "N operand");
 
 // misc ints
-enum { M_TMEM = 0, M_UNIT = 2, M_NEXT = 3, M_FLAGS = 4, M_U = 5, M_NUN = 6, M_NODES = 7, M_NPASS = 8, M_WC0 = 9, M_WC1 = 10, M_NPAD = 11 };
+enum { M_TMEM = 0, M_UNIT = 2, M_NEXT = 3, M_FLAGS = 4, M_U = 5, M_NUN = 6, M_NODES = 7, M_NPASS = 8, M_WC0 = 9, M_WC1 = 10, M_NPAD = 11,
+       M_NEXT2 = 12, M_NIMP = 13, M_NP0 = 14, M_NCNT = 15 };   // the unit after next; (impression, first pair, count) of the next unit
 
 // Chebyshev nodes on [-1, 1]: 4-node and 2-node sets
 constexpr float kX0 = -0.92387953251128674f, kX1 = -0.38268343236508977f;
@@ -147,7 +148,13 @@ template <int NODES> __device__ __forceinline__ float node_x(int j) {
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+#if defined(LIME_TC_NO_ROW_PREFETCH)
+    (void)p; (void)bytes;
+#elif defined(LIME_TC_LINE_PREFETCH)
+    for (uint32_t o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p) + o));
+#else
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -551,7 +558,13 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
         tc::mbar_init(bar_free + 1, 1);
         tc::mbar_init(bar_accum, 1);
         tc::mbar_fence_init();
-        misc[M_NEXT] = atomicAdd(args.work_counter, 1);
+        const int u0 = atomicAdd(args.work_counter, 1);
+        misc[M_NEXT] = u0;
+        misc[M_NEXT2] = atomicAdd(args.work_counter, 1);
+        const bool in0 = u0 < args.imp.num_units;
+        misc[M_NIMP] = in0 ? args.imp.unit_imp[u0] : 0;
+        misc[M_NP0] = in0 ? args.imp.unit_pair0[u0] : 0;
+        misc[M_NCNT] = in0 ? args.imp.unit_count[u0] : 0;
     }
     if (warp == kMmaWarp) tc::tmem_alloc(reinterpret_cast<uint32_t *>(base + OFF_MISC) + M_TMEM, 256);
     tc::fence_before_sync();
@@ -573,7 +586,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
         __syncthreads();
         if (tid == 0) {
             misc[M_UNIT] = misc[M_NEXT];
-            misc[M_NEXT] = atomicAdd(args.work_counter, 1);
+            misc[M_NEXT] = misc[M_NEXT2];
             misc[M_FLAGS] = 0;
         }
         __syncthreads();
@@ -582,9 +595,8 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
 #ifdef LIME_TC_PHASE_CLOCKS
         if (tid == 0) { t_last = clock64(); ++prof[9]; }
 #endif
-        const int imp = I.unit_imp[unit];
-        const int pair0 = I.unit_pair0[unit];
-        const int cnt = I.unit_count[unit];
+        // staged one unit ahead by the MMA warp, which rewrites them only after the barriers of phase 0
+        const int imp = misc[M_NIMP], pair0 = misc[M_NP0], cnt = misc[M_NCNT];
         const int pz0 = args.prefix_main < H ? args.prefix_main : H;
         const int pz1 = args.prefix_tail < H ? args.prefix_tail : H;
 
@@ -766,8 +778,14 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
                 // rows are prefetched by their own unit: a whole unit of look-ahead for 296 CTAs overflows the L2)
                 if (pass == 0) {
                     const int nxt = misc[M_NEXT];
+                    if (lane == 0) misc[M_NEXT2] = atomicAdd(args.work_counter, 1);
                     if (nxt < I.num_units) {
                         const int nimp = I.unit_imp[nxt], np0 = I.unit_pair0[nxt], ncnt = I.unit_count[nxt];
+                        if (lane == 0) {
+                            misc[M_NIMP] = nimp;
+                            misc[M_NP0] = np0;
+                            misc[M_NCNT] = ncnt;
+                        }
                         const long long ho = (long long)nimp * H;
                         for (int j = lane; 32 * j < H; j += 32) prefetch_l2(I.hist_news + ho + 32 * j);
                         for (int j = lane; 32 * j < ncnt; j += 32) prefetch_l2(I.cand_news + np0 + 32 * j);
