@@ -616,7 +616,8 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             htp[h] = (tp < 0 || tp >= T) ? 0 : tp;
             hga[h] = ga;
         }
-        for (int c = tid; c < cnt; c += kThreads) {
+        // (candidates on warps 4.., history slots on warps 0..: the two dependent load chains run side by side)
+        for (int c = (tid + kThreads - 128) % kThreads; c < cnt; c += kThreads) {
             const long long p = (long long)pair0 + c;
             int n = I.cand_news[p];
             n = (n < 0 || n >= C.news_num) ? 0 : n;
