@@ -200,11 +200,12 @@ typedef struct {
  *
  * Two kernels implement the same arithmetic:
  *   - exact   (score.cu): every (candidate, history row) gate evaluated element by element; any H <= 224.
- *   - tensor  (score_tc.cu, H <= LIME_TC_MAX_HISTORY): per history row the gated vector is evaluated at
- *     4 Chebyshev nodes of the attention weight a over the unit's candidates, the 3 dots with every
- *     candidate are tcgen05 MMAs on error-compensated bf16 pairs (fp32 accumulation in TMEM), and each
- *     pair interpolates in a.  A unit whose a-spread makes the interpolation bound exceed the
- *     tolerance is re-scored by the exact kernel in the same call.
+ *   - tensor  (score_tc.cu, H <= LIME_TC_MAX_HISTORY): history slots with the same (news, bucket pair, mask) are
+ *     deduplicated; per unique row the gated vector is evaluated at 2 (or 4) Chebyshev nodes of the attention
+ *     weight a over the unit's candidates, the 3 dots with every candidate are tcgen05 MMAs on fp16 hi/lo pairs
+ *     (candidate side pre-split in cand16 / ctab16, fp32 accumulation in TMEM), and each pair interpolates in a.
+ *     A unit whose a-spread makes the interpolation bound exceed the tolerance, or that holds an operand beyond
+ *     the fp16 range, is re-scored by the exact kernel in the same call.
  * lime_score_configure(mode, tolerance): mode 0 = tensor path with exact fallback (default,
  * tolerance 1e-6 on the gate), 1 = exact only, 2 = tensor path with every unit forced through the
  * fallback (tests).  Process-wide. */
