@@ -57,7 +57,7 @@ extern "C" {
 #define LIME_HTAB_LD   800  /* per (freshness bucket, lifetime bucket): [ T | gwT ]            */
 #define LIME_CTAB_LD   1208 /* per bucket pair: [ w1T | w2T | w3T | scalT(8) ]                 */
 /* Tensor-core scoring path (score_tc.cu): history rows per impression, candidates per work unit. */
-#define LIME_TC_MAX_HISTORY 56
+#define LIME_TC_MAX_HISTORY 52
 #define LIME_TC_TILE_C      42
 #define LIME_TOPIC_TAB_LD   12  /* 10 head logits of a (candidate topic, history topic) pair, padded */
 #define LIME_TC_MAX_TOPICS  1024

@@ -73,50 +73,52 @@ constexpr int kC16 = LIME_CAND16_LD;            // fp16 elements per cand16 / ct
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr int OFF_A = 0;                                      // 4 images: news hi, news lo, table hi, table lo
 constexpr int OFF_BHI = 4 * kAImg, OFF_BLO = OFF_BHI + kBImg;
-constexpr int OFF_OUT = OFF_BHI;                              // alias (after the MMAs): lg / y / z [56][42]
+constexpr int OFF_OUT = OFF_BHI;                              // alias (after the MMAs): lg / y / z [52][42]
 constexpr int OFF_AS = OFF_BLO + kBImg;                       // a[u][c]
-constexpr int OFF_BIAS = OFF_AS + kH * kAS * 4;               // gate bias' [400]
-constexpr int OFF_S01 = OFF_BIAS + kD * 4;                    // node sums [56][8]; phase-0 scratch aliases it
+constexpr int OFF_S01 = OFF_AS + kH * kAS * 4;                // node sums [52][8]
 constexpr int OFF_MID = OFF_S01 + kH * 8 * 4;
 constexpr int OFF_WINV = OFF_MID + kH * 4;
 constexpr int OFF_WHALF = OFF_WINV + kH * 4;
-constexpr int OFF_CSCAL = OFF_WHALF + kH * 4;                 // [42][4]  B1 B2 B3 cb
-constexpr int OFF_POOL = OFF_CSCAL + kTile * 16;              // [42][4]  running m, l, acc, ms
-constexpr int kCArr = 48 * 4;
-constexpr int OFF_CW = OFF_POOL + kTile * 16;
-constexpr int OFF_CNEWS = OFF_CW + kCArr;
-constexpr int OFF_CTAB = OFF_CNEWS + kCArr;
-constexpr int OFF_CP = OFF_CTAB + kCArr;
-constexpr int OFF_CTOPIC = OFF_CP + kCArr;
-constexpr int kUArr = kH * 4;
-constexpr int OFF_UNEWS = OFF_CTOPIC + kCArr;
-constexpr int OFF_UTAB = OFF_UNEWS + kUArr;
-constexpr int OFF_UMASK = OFF_UTAB + kUArr;
-constexpr int OFF_UTOPIC = OFF_UMASK + kUArr;
-constexpr int OFF_UMULT = OFF_UTOPIC + kUArr;                 // float multiplicity
-constexpr int OFF_UMP0 = OFF_UMULT + kUArr;                   // float multiplicity inside the GraphSAGE prefix (main)
-constexpr int OFF_UMP1 = OFF_UMP0 + kUArr;                    // ... (tail batch)
-constexpr int OFF_UGABS = OFF_UMP1 + kUArr;
-constexpr int OFF_UFIRST = OFF_UGABS + kUArr;                 // history slot of the unique row
-constexpr int OFF_BARS = OFF_UFIRST + kUArr;                  // fullA[2] fullB[2] free[2] accum
-constexpr int OFF_MISC = OFF_BARS + 64;                       // tmem slot, unit ids, flags, U, ...
+constexpr int OFF_POOL = OFF_WHALF + kH * 4;                  // [42][4]  running m, l, acc, ms
+// Per-unit arrays written by the front end (unit metadata + dedup): DOUBLE BUFFERED, the MMA-issuer warp prepares unit
+// i + 1 while the compute warps are in the epilogue / pooling of unit i
+constexpr int kCArr = 48 * 4, kUArr = kH * 4;
+constexpr int UB_CSCAL = 0;                                   // [42][4]  B1 B2 B3 cb
+constexpr int UB_CW = UB_CSCAL + kTile * 16;
+constexpr int UB_CNEWS = UB_CW + kCArr;
+constexpr int UB_CTAB = UB_CNEWS + kCArr;
+constexpr int UB_CP = UB_CTAB + kCArr;
+constexpr int UB_CTOPIC = UB_CP + kCArr;
+constexpr int UB_UNEWS = UB_CTOPIC + kCArr;
+constexpr int UB_UTAB = UB_UNEWS + kUArr;
+constexpr int UB_UMASK = UB_UTAB + kUArr;
+constexpr int UB_UTOPIC = UB_UMASK + kUArr;
+constexpr int UB_UMULT = UB_UTOPIC + kUArr;                   // float multiplicity
+constexpr int UB_UMP0 = UB_UMULT + kUArr;                     // float multiplicity inside the GraphSAGE prefix (main)
+constexpr int UB_UMP1 = UB_UMP0 + kUArr;                      // ... (tail batch)
+constexpr int UB_UGABS = UB_UMP1 + kUArr;
+constexpr int UB_INFO = UB_UGABS + kUArr;                     // ints: unit, impression, first pair, count, U, unmasked slots, flags
+constexpr int kUnitBuf = UB_INFO + 32;
+constexpr int OFF_UB = OFF_POOL + kTile * 16;
+// front-end scratch (one warp): keys, topic ids, gate bounds of the H history slots
+constexpr int OFF_HKN = OFF_UB + 2 * kUnitBuf, OFF_HKT = OFF_HKN + kUArr, OFF_HTP = OFF_HKT + kUArr, OFF_HGA = OFF_HTP + kUArr;
+constexpr int OFF_BARS = OFF_HGA + kUArr;                     // full[2] free[2] accum
+constexpr int OFF_MISC = OFF_BARS + 64;                       // tmem slot, nodes, passes, N
 constexpr int OFF_PROF = OFF_MISC + 64;                       // phase clocks of thread 0 (diagnostic)
-constexpr int OFF_ROWOFF = OFF_PROF + 128;                    // loader: element offsets of the 128 M rows (news, table)
-constexpr int kSmemBytes = OFF_ROWOFF + 1024 + 1024;
-// phase-0 scratch inside the node-sum area
-constexpr int OFF_HKN = OFF_S01, OFF_HKT = OFF_HKN + kH * 4, OFF_HTP = OFF_HKT + kH * 4, OFF_HGA = OFF_HTP + kH * 4;
-constexpr int OFF_HFIRST = OFF_HGA + kH * 4, OFF_HMULT = OFF_HFIRST + kH * 4;
-static_assert(OFF_HMULT + kH * 4 <= OFF_MID, "phase-0 scratch overflows the node-sum area");
+constexpr int kSmemBytes = OFF_PROF + 128 + 1024;
 static_assert(3 * kH * kAS * 4 <= 2 * kBImg, "epilogue alias overflows the O operand images");
 static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
 static_assert(3 * kTile <= 128 && kTile <= 48 && kTile >= 32, "candidate rows: 32 per k in TMEM quadrants 0-2, the rest in quadrant 3");
 static_assert(3 * kQ3 <= 32, "quadrant 3 holds (tile - 32) candidates x 3");
-static_assert(OFF_BARS % 8 == 0 && OFF_AS % 16 == 0 && OFF_BIAS % 16 == 0 && OFF_S01 % 16 == 0 && OFF_BHI % 1024 == 0 && OFF_BLO % 1024 == 0, "alignment");
-static_assert(2 * kH <= kBRows && kBRows % 16 == 0 && kBRows <= 128 && kH % 8 == 0 && kH <= 64, "N operand");
+static_assert(OFF_BARS % 8 == 0 && OFF_AS % 16 == 0 && OFF_S01 % 16 == 0 && OFF_UB % 16 == 0 && kUnitBuf % 16 == 0 &&
+              OFF_BHI % 1024 == 0 && OFF_BLO % 1024 == 0, "alignment");
+static_assert(2 * kH <= kBRows && kBRows % 16 == 0 && kBRows <= 128 && kH % 4 == 0 && kH <= 64 && 4 * kH <= 2 * kBRows, "N operand");
+static_assert(kH <= 2 * kRPT && kH <= kCompute / 4 && kBRows / 4 <= kRPT, "row mappings of the compute threads");
 
 // misc ints
-enum { M_TMEM = 0, M_UNIT = 2, M_NEXT = 3, M_FLAGS = 4, M_U = 5, M_NUN = 6, M_NODES = 7, M_NPASS = 8, M_WC0 = 9, M_WC1 = 10, M_NPAD = 11,
-       M_NEXT2 = 12, M_NIMP = 13, M_NP0 = 14, M_NCNT = 15 };   // the unit after next; (impression, first pair, count) of the next unit
+enum { M_TMEM = 0, M_NODES = 2, M_NPASS = 3, M_NPAD = 4 };
+// unit info ints
+enum { UI_UNIT = 0, UI_IMP = 1, UI_PAIR0 = 2, UI_CNT = 3, UI_U = 4, UI_NUN = 5, UI_FLAGS = 6 };
 
 // Chebyshev nodes on [-1, 1]: 4-node and 2-node sets
 constexpr float kX0 = -0.92387953251128674f, kX1 = -0.38268343236508977f;
@@ -199,8 +201,8 @@ __device__ __forceinline__ void split4(const float (&x)[4], uint2 &hi, uint2 &lo
 template <int NODES, int TPT>
 __device__ __forceinline__ void produce_operands(unsigned char *base, const LimeNewsCache &C, int u0, int nrows, int tid,
                                                  const int *unews, const int *utab, const float *mid_s,
-                                                 const float *whalf_s, const float *bias_s, float *s01_s, int *flag_s,
-                                                 const uint32_t *rowoff_s, const __half *cand16, const __half *ctab16,
+                                                 const float *whalf_s, float *s01_s, int *flag_s, const int *cnews,
+                                                 const int *ctab, int cnt, const __half *cand16, const __half *ctab16,
                                                  uint64_t *bar_full, uint64_t *bar_free, uint32_t &use0, uint32_t &use1) {
     const int sub = tid & 7;
     // candidate operand (M side): warp w streams the row groups w, w + 7, w + 14 of every stage with cp.async -- lane =
@@ -211,9 +213,13 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
     uint32_t a_on[3], a_ot[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const int g = a_g0 + kCWarps * i;
-        a_on[i] = g < 16 ? rowoff_s[8 * g + a_rsub] : 0xffffffffu;
-        a_ot[i] = g < 16 ? rowoff_s[128 + 8 * g + a_rsub] : 0u;
+        const int g = a_g0 + kCWarps * i;          // element offsets of operand row 8 g + a_rsub inside cand16 / ctab16
+        int c = kTile, k = 0;
+        if (g < 16) m_row_owner(g >> 2, 8 * (g & 3) + a_rsub, c, k);
+        const bool rok = c < cnt;
+        const int cc = rok ? c : 0;
+        a_on[i] = rok ? (uint32_t)cnews[cc] * (uint32_t)kC16 + (uint32_t)(k * 2 * kD) : 0xffffffffu;
+        a_ot[i] = (uint32_t)ctab[cc] * (uint32_t)kC16 + (uint32_t)(k * 2 * kD);
     }
     const uint32_t a_dst = tc::smem_u32(base) + OFF_A + (uint32_t)a_g0 * 1024u + (uint32_t)a_rsub * 128u;
     auto issue_copies = [&](int kc) {       // stage kc -> ring slot kc & 1 (waits until the MMAs of stage kc - 2 have drained it)
@@ -297,7 +303,7 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
             }
         }
         if (d0 < kD) {      // the slot is free: this thread waited for it when it issued the stage's copies
-            const float4 bb4 = *reinterpret_cast<const float4 *>(bias_s + d0);
+            const float4 bb4 = ldg4(C.gate_bias + d0);
             const float bb[4] = {bb4.x, bb4.y, bb4.z, bb4.w};
 #pragma unroll
             for (int t = 0; t < TPT; ++t) {
@@ -502,55 +508,154 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
     }
 }
 
+// Front end of one work unit, executed by ONE warp (the MMA issuer) in two parts while the compute warps work on the
+// previous unit.  Part 1, during its attention phase: unit metadata (history keys, bucket pairs, topic ids; candidate
+// rows, lifetime weights, folded scalars).  Writes the unit buffer `ub` and the front-end scratch.
+__device__ __forceinline__ void front_meta(const ScoreArgs &args, unsigned char *ub, int unit, int lane, int *hkn, int *hkt,
+                                           int *htp, float *hga) {
+    const LimeNewsCache &C = args.cache;
+    const LimeImpressions &I = args.imp;
+    const int H = I.max_history, nb = C.num_buckets, T = C.num_topics;
+    int *info = reinterpret_cast<int *>(ub + UB_INFO);
+    float *cscal = reinterpret_cast<float *>(ub + UB_CSCAL);
+    float *cw = reinterpret_cast<float *>(ub + UB_CW);
+    int *cnews = reinterpret_cast<int *>(ub + UB_CNEWS);
+    int *ctab = reinterpret_cast<int *>(ub + UB_CTAB);
+    int *cP = reinterpret_cast<int *>(ub + UB_CP);
+    int *ctopic = reinterpret_cast<int *>(ub + UB_CTOPIC);
+    if (unit >= I.num_units) {
+        if (lane == 0) info[UI_UNIT] = unit;
+        __syncwarp();
+        return;
+    }
+    const int imp = I.unit_imp[unit], pair0 = I.unit_pair0[unit], cnt = I.unit_count[unit];
+    int flags = 0;
+    for (int h = lane; h < H; h += 32) {
+        const long long o = (long long)imp * H + h;
+        int n = I.hist_news[o];
+        n = (n < 0 || n >= C.news_num) ? 0 : n;
+        const float2 mt = __ldg(reinterpret_cast<const float2 *>(C.news_meta + (size_t)n * LIME_META_LD));
+        const int tp = __float_as_int(mt.x);
+        const int mk = I.hist_mask[o] != 0 ? 1 : 0;
+        const int bf = bucketize_seconds(I.hist_fresh[o], args.bucket_scale, nb);
+        const int bl = bucketize_seconds(I.hist_life[o], args.bucket_scale, nb);
+        hkn[h] = n;
+        hkt[h] = 2 * (bf * nb + bl) + mk;          // second key word: bucket pair and mask
+        htp[h] = (tp < 0 || tp >= T) ? 0 : tp;
+        hga[h] = mt.y;
+    }
+    for (int c = lane; c < cnt; c += 32) {
+        const long long p = (long long)pair0 + c;
+        int n = I.cand_news[p];
+        n = (n < 0 || n >= C.news_num) ? 0 : n;
+        const float fr = I.cand_fresh[p], lf = I.cand_life[p];
+        const float4 m0 = ldg4(C.news_meta + (size_t)n * LIME_META_LD), m1 = ldg4(C.news_meta + (size_t)n * LIME_META_LD + 4);
+        const int tb = bucketize_seconds(fr, args.bucket_scale, nb) * nb + bucketize_seconds(lf, args.bucket_scale, nb);
+        const float *ctr = C.cand_tab + (size_t)tb * LIME_CTAB_LD;
+        const int tp = __float_as_int(m0.x);
+        cnews[c] = n;
+        ctab[c] = tb;
+        cw[c] = lifetime_weight(I.cand_remaining ? I.cand_remaining[p] : __fsub_rn(lf, fr), C);
+        cP[c] = (args.pair_index_base + p >= args.tail_start) ? args.prefix_tail : args.prefix_main;
+        ctopic[c] = (tp < 0 || tp >= T) ? 0 : tp;
+        cscal[c * 4 + 0] = m0.w + __ldg(ctr + LIME_CAND_SCAL + 3);
+        cscal[c * 4 + 1] = m1.x + __ldg(ctr + LIME_CAND_SCAL + 4);
+        cscal[c * 4 + 2] = m1.y + __ldg(ctr + LIME_CAND_SCAL + 5);
+        cscal[c * 4 + 3] = m1.z + __ldg(ctr + LIME_CAND_SCAL + 6);
+        if (!(m0.z <= kWAbsMax)) flags = 4;        // beyond the fp16 operand range: exact kernel
+    }
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0) {
+        info[UI_UNIT] = unit;
+        info[UI_IMP] = imp;
+        info[UI_PAIR0] = pair0;
+        info[UI_CNT] = cnt;
+        info[UI_FLAGS] = flags;
+    }
+    __syncwarp();
+}
+
+// Part 2, during the previous unit's epilogue: deduplication of the history slots into unique operand rows.
+__device__ __forceinline__ void front_dedup(const ScoreArgs &args, unsigned char *ub, int lane, const int *hkn, const int *hkt,
+                                            const int *htp, const float *hga) {
+    const LimeImpressions &I = args.imp;
+    const int H = I.max_history;
+    int *info = reinterpret_cast<int *>(ub + UB_INFO);
+    if (info[UI_UNIT] >= I.num_units) return;
+    int *unews = reinterpret_cast<int *>(ub + UB_UNEWS);
+    int *utab = reinterpret_cast<int *>(ub + UB_UTAB);
+    int *umask = reinterpret_cast<int *>(ub + UB_UMASK);
+    int *utopic = reinterpret_cast<int *>(ub + UB_UTOPIC);
+    float *umult = reinterpret_cast<float *>(ub + UB_UMULT);
+    float *ump0 = reinterpret_cast<float *>(ub + UB_UMP0);
+    float *ump1 = reinterpret_cast<float *>(ub + UB_UMP1);
+    float *ugabs = reinterpret_cast<float *>(ub + UB_UGABS);
+    // ---- dedup: slots with equal (news, bucket pair, mask) are one operand row.  A lane holds the keys of slots lane and
+    // lane + 32; two ballots per reference slot give the set of equal slots (lowest member = the unique row, size = the
+    // multiplicity); slots already absorbed by an earlier reference are skipped (the zero padding is one iteration).
+    const int pz0 = args.prefix_main < H ? args.prefix_main : H, pz1 = args.prefix_tail < H ? args.prefix_tail : H;
+    const int ha = lane, hb = lane + 32;
+    const int k1a = ha < H ? hkn[ha] : -1 - ha, k2a = ha < H ? hkt[ha] : -1;
+    const int k1b = hb < H ? hkn[hb] : -1 - hb, k2b = hb < H ? hkt[hb] : -1;
+    const unsigned p0lo = pz0 >= 32 ? 0xffffffffu : (1u << pz0) - 1u, p0hi = pz0 > 32 ? (1u << (pz0 - 32)) - 1u : 0u;
+    const unsigned p1lo = pz1 >= 32 ? 0xffffffffu : (1u << pz1) - 1u, p1hi = pz1 > 32 ? (1u << (pz1 - 32)) - 1u : 0u;
+    unsigned seen0 = 0, seen1 = 0;     // slots already assigned to a unique row (warp-uniform)
+    int U = 0;
+    for (int r = 0; r < H; ++r) {
+        if ((r < 32 ? seen0 >> r : seen1 >> (r - 32)) & 1u) continue;
+        const int r1 = hkn[r], r2 = hkt[r];
+        const unsigned m0 = __ballot_sync(0xffffffffu, k1a == r1 && k2a == r2);
+        const unsigned m1 = __ballot_sync(0xffffffffu, k1b == r1 && k2b == r2);
+        seen0 |= m0;
+        seen1 |= m1;
+        if (lane == 0) {
+            unews[U] = r1;
+            utab[U] = r2 >> 1;
+            umask[U] = r2 & 1;
+            utopic[U] = htp[r];
+            ugabs[U] = hga[r];
+            umult[U] = (float)(__popc(m0) + __popc(m1));
+            ump0[U] = (float)(__popc(m0 & p0lo) + __popc(m1 & p0hi));
+            ump1[U] = (float)(__popc(m0 & p1lo) + __popc(m1 & p1hi));
+        }
+        ++U;
+    }
+    int nun = (ha < H ? k2a & 1 : 0) + (hb < H ? k2b & 1 : 0);      // unmasked history slots
+    nun = __reduce_add_sync(0xffffffffu, nun);
+    if (lane == 0) {
+        info[UI_U] = U;
+        info[UI_NUN] = nun;
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs args) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float *out_s = reinterpret_cast<float *>(base + OFF_OUT);
     float *a_s = reinterpret_cast<float *>(base + OFF_AS);
-    float *bias_s = reinterpret_cast<float *>(base + OFF_BIAS);
     float *s01_s = reinterpret_cast<float *>(base + OFF_S01);
     float *mid_s = reinterpret_cast<float *>(base + OFF_MID);
     float *winv_s = reinterpret_cast<float *>(base + OFF_WINV);
     float *whalf_s = reinterpret_cast<float *>(base + OFF_WHALF);
-    float *cscal = reinterpret_cast<float *>(base + OFF_CSCAL);
     float *pool_s = reinterpret_cast<float *>(base + OFF_POOL);
-    float *cw = reinterpret_cast<float *>(base + OFF_CW);
-    int *cnews = reinterpret_cast<int *>(base + OFF_CNEWS);
-    int *ctab = reinterpret_cast<int *>(base + OFF_CTAB);
-    int *cP = reinterpret_cast<int *>(base + OFF_CP);
-    int *ctopic = reinterpret_cast<int *>(base + OFF_CTOPIC);
-    int *unews = reinterpret_cast<int *>(base + OFF_UNEWS);
-    int *utab = reinterpret_cast<int *>(base + OFF_UTAB);
-    int *umask = reinterpret_cast<int *>(base + OFF_UMASK);
-    int *utopic = reinterpret_cast<int *>(base + OFF_UTOPIC);
-    float *umult = reinterpret_cast<float *>(base + OFF_UMULT);
-    float *ump0 = reinterpret_cast<float *>(base + OFF_UMP0);
-    float *ump1 = reinterpret_cast<float *>(base + OFF_UMP1);
-    float *ugabs = reinterpret_cast<float *>(base + OFF_UGABS);
-    int *ufirst = reinterpret_cast<int *>(base + OFF_UFIRST);
     int *hkn = reinterpret_cast<int *>(base + OFF_HKN);
     int *hkt = reinterpret_cast<int *>(base + OFF_HKT);
     int *htp = reinterpret_cast<int *>(base + OFF_HTP);
     float *hga = reinterpret_cast<float *>(base + OFF_HGA);
-    int *hfirst = reinterpret_cast<int *>(base + OFF_HFIRST);
-    int *hmult = reinterpret_cast<int *>(base + OFF_HMULT);
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(base + OFF_BARS);
     uint64_t *bar_free = bar_full + 2;
     uint64_t *bar_accum = bar_full + 4;
     volatile int *misc = reinterpret_cast<volatile int *>(base + OFF_MISC);
-    int *flag_s = reinterpret_cast<int *>(base + OFF_MISC) + M_FLAGS;
-    uint32_t *rowoff_s = reinterpret_cast<uint32_t *>(base + OFF_ROWOFF);
 
     const LimeNewsCache &C = args.cache;
     const LimeImpressions &I = args.imp;
     const int H = I.max_history;
-    const int nb = C.num_buckets;
     const int T = C.num_topics;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const __half *cand16 = reinterpret_cast<const __half *>(C.cand16);
     const __half *ctab16 = reinterpret_cast<const __half *>(C.ctab16);
 
-    for (int d = tid; d < kD; d += kThreads) bias_s[d] = C.gate_bias[d];
     if (tid == 0) {
         tc::mbar_init(bar_full + 0, 2 * kCompute);    // per compute thread: its cp.async copies + its O rows
         tc::mbar_init(bar_full + 1, 2 * kCompute);
@@ -558,15 +663,16 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
         tc::mbar_init(bar_free + 1, 1);
         tc::mbar_init(bar_accum, 1);
         tc::mbar_fence_init();
-        const int u0 = atomicAdd(args.work_counter, 1);
-        misc[M_NEXT] = u0;
-        misc[M_NEXT2] = atomicAdd(args.work_counter, 1);
-        const bool in0 = u0 < args.imp.num_units;
-        misc[M_NIMP] = in0 ? args.imp.unit_imp[u0] : 0;
-        misc[M_NP0] = in0 ? args.imp.unit_pair0[u0] : 0;
-        misc[M_NCNT] = in0 ? args.imp.unit_count[u0] : 0;
     }
-    if (warp == kMmaWarp) tc::tmem_alloc(reinterpret_cast<uint32_t *>(base + OFF_MISC) + M_TMEM, 256);
+    int next_unit = 0;               // issuer warp: the unit whose front end it runs next
+    if (warp == kMmaWarp) {
+        tc::tmem_alloc(reinterpret_cast<uint32_t *>(base + OFF_MISC) + M_TMEM, 256);
+        int u0 = 0;
+        if (lane == 0) u0 = atomicAdd(args.work_counter, 1);
+        u0 = __shfl_sync(0xffffffffu, u0, 0);
+        front_meta(args, base + OFF_UB, u0, lane, hkn, hkt, htp, hga);
+        front_dedup(args, base + OFF_UB, lane, hkn, hkt, htp, hga);
+    }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -581,139 +687,45 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
 #endif
     uint32_t use0 = 0, use1 = 0;     // uses of the two ring halves so far (every role counts the same sequence)
     uint32_t pass_iter = 0;          // passes processed so far (phase of bar_accum)
+    int ubi = 0;                     // unit buffer of the current unit
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            misc[M_UNIT] = misc[M_NEXT];
-            misc[M_NEXT] = misc[M_NEXT2];
-            misc[M_FLAGS] = 0;
-        }
-        __syncthreads();
-        const int unit = misc[M_UNIT];
+    for (;; ubi ^= 1) {
+        unsigned char *ub = base + OFF_UB + ubi * kUnitBuf;
+        volatile int *info = reinterpret_cast<volatile int *>(ub + UB_INFO);
+        const float *cscal = reinterpret_cast<const float *>(ub + UB_CSCAL);
+        const float *cw = reinterpret_cast<const float *>(ub + UB_CW);
+        const int *cnews = reinterpret_cast<const int *>(ub + UB_CNEWS);
+        const int *ctab = reinterpret_cast<const int *>(ub + UB_CTAB);
+        const int *cP = reinterpret_cast<const int *>(ub + UB_CP);
+        const int *ctopic = reinterpret_cast<const int *>(ub + UB_CTOPIC);
+        const int *unews = reinterpret_cast<const int *>(ub + UB_UNEWS);
+        const int *utab = reinterpret_cast<const int *>(ub + UB_UTAB);
+        const int *umask = reinterpret_cast<const int *>(ub + UB_UMASK);
+        const int *utopic = reinterpret_cast<const int *>(ub + UB_UTOPIC);
+        const float *umult = reinterpret_cast<const float *>(ub + UB_UMULT);
+        const float *ump0 = reinterpret_cast<const float *>(ub + UB_UMP0);
+        const float *ump1 = reinterpret_cast<const float *>(ub + UB_UMP1);
+        const float *ugabs = reinterpret_cast<const float *>(ub + UB_UGABS);
+        int *flag_s = reinterpret_cast<int *>(ub + UB_INFO) + UI_FLAGS;
+
+        const int unit = info[UI_UNIT];
         if (unit >= I.num_units) break;
 #ifdef LIME_TC_PHASE_CLOCKS
         if (tid == 0) { t_last = clock64(); ++prof[9]; }
 #endif
-        // staged one unit ahead by the MMA warp, which rewrites them only after the barriers of phase 0
-        const int imp = misc[M_NIMP], pair0 = misc[M_NP0], cnt = misc[M_NCNT];
-        const int pz0 = args.prefix_main < H ? args.prefix_main : H;
-        const int pz1 = args.prefix_tail < H ? args.prefix_tail : H;
-
-        // ---------------- phase 0: unit metadata; L2 prefetch of the NEXT unit's cache rows --------
-        for (int h = tid; h < H; h += kThreads) {
-            const long long o = (long long)imp * H + h;
-            int n = I.hist_news[o];
-            n = (n < 0 || n >= C.news_num) ? 0 : n;
-            hkn[h] = n;
-            const float2 mt = __ldg(reinterpret_cast<const float2 *>(C.news_meta + (size_t)n * LIME_META_LD));
-            const int tp = __float_as_int(mt.x);
-            const float ga = mt.y;
-            const int mk = I.hist_mask[o] != 0 ? 1 : 0;
-            const int bf = bucketize_seconds(I.hist_fresh[o], args.bucket_scale, nb);
-            const int bl = bucketize_seconds(I.hist_life[o], args.bucket_scale, nb);
-            hkt[h] = 2 * (bf * nb + bl) + mk;          // second key word: bucket pair and mask
-            htp[h] = (tp < 0 || tp >= T) ? 0 : tp;
-            hga[h] = ga;
-        }
-        // (candidates on warps 4.., history slots on warps 0..: the two dependent load chains run side by side)
-        for (int c = (tid + kThreads - 128) % kThreads; c < cnt; c += kThreads) {
-            const long long p = (long long)pair0 + c;
-            int n = I.cand_news[p];
-            n = (n < 0 || n >= C.news_num) ? 0 : n;
-            cnews[c] = n;
-            const float fr = I.cand_fresh[p], lf = I.cand_life[p];
-            const int tb = bucketize_seconds(fr, args.bucket_scale, nb) * nb + bucketize_seconds(lf, args.bucket_scale, nb);
-            ctab[c] = tb;
-            cw[c] = lifetime_weight(I.cand_remaining ? I.cand_remaining[p] : __fsub_rn(lf, fr), C);
-            cP[c] = (args.pair_index_base + p >= args.tail_start) ? args.prefix_tail : args.prefix_main;
-            prefetch_l2_bulk(cand16 + (size_t)n * kC16, kC16 * 2);      // the operand rows this unit streams in phase 2
-            const float4 m0 = ldg4(C.news_meta + (size_t)n * LIME_META_LD), m1 = ldg4(C.news_meta + (size_t)n * LIME_META_LD + 4);
-            const float *ctr = C.cand_tab + (size_t)tb * LIME_CTAB_LD;
-            const int tp = __float_as_int(m0.x);
-            ctopic[c] = (tp < 0 || tp >= T) ? 0 : tp;
-            cscal[c * 4 + 0] = m0.w + __ldg(ctr + LIME_CAND_SCAL + 3);
-            cscal[c * 4 + 1] = m1.x + __ldg(ctr + LIME_CAND_SCAL + 4);
-            cscal[c * 4 + 2] = m1.y + __ldg(ctr + LIME_CAND_SCAL + 5);
-            cscal[c * 4 + 3] = m1.z + __ldg(ctr + LIME_CAND_SCAL + 6);
-            if (!(m0.z <= kWAbsMax)) atomicOr(flag_s, 4);   // fp16 operand range
+        const int pair0 = info[UI_PAIR0], cnt = info[UI_CNT], U = info[UI_U];
+        for (int c = tid; c < cnt; c += kThreads) {
             pool_s[c * 4 + 0] = -INFINITY;
             pool_s[c * 4 + 1] = 0.0f;
             pool_s[c * 4 + 2] = 0.0f;
             pool_s[c * 4 + 3] = 0.0f;
         }
-        __syncthreads();
-        LIME_TICK(0);
-
-        // element offsets of the 128 M operand rows inside cand16 / ctab16 (0xffffffff: unused row)
-        if (tid >= kCompute - 128 && tid < kCompute) {
-            const int r = tid - (kCompute - 128);
-            int c, k;
-            m_row_owner(r >> 5, r & 31, c, k);
-            const bool ok = c < cnt;
-            const int cc = ok ? c : 0;
-            rowoff_s[r] = ok ? (uint32_t)cnews[cc] * (uint32_t)kC16 + (uint32_t)(k * 2 * kD) : 0xffffffffu;
-            rowoff_s[128 + r] = (uint32_t)ctab[cc] * (uint32_t)kC16 + (uint32_t)(k * 2 * kD);
-        }
-        // ---------------- dedup of the history slots: (news, bucket pair, mask) -> unique rows -----
-        // warp w takes the reference slots w, w + 7, ...; a lane holds the keys of slots lane and lane + 32, two ballots
-        // give the set of equal slots: its lowest member is the unique row, its size the multiplicity
-        if (warp < kCWarps) {
-            const int ha = lane, hb = lane + 32;
-            const int k1a = ha < H ? hkn[ha] : -1 - ha, k2a = ha < H ? hkt[ha] : -1;
-            const int k1b = hb < H ? hkn[hb] : -1 - hb, k2b = hb < H ? hkt[hb] : -1;
-            const unsigned p0lo = pz0 >= 32 ? 0xffffffffu : (1u << pz0) - 1u, p0hi = pz0 > 32 ? (1u << (pz0 - 32)) - 1u : 0u;
-            const unsigned p1lo = pz1 >= 32 ? 0xffffffffu : (1u << pz1) - 1u, p1hi = pz1 > 32 ? (1u << (pz1 - 32)) - 1u : 0u;
-            for (int r = warp; r < H; r += kCWarps) {
-                const int r1 = hkn[r], r2 = hkt[r];
-                const unsigned m0 = __ballot_sync(0xffffffffu, k1a == r1 && k2a == r2);
-                const unsigned m1 = __ballot_sync(0xffffffffu, k1b == r1 && k2b == r2);
-                if (lane == 0) {
-                    hfirst[r] = m0 ? __ffs(m0) - 1 : 31 + __ffs(m1);
-                    hmult[r] = (__popc(m0) + __popc(m1)) | ((__popc(m0 & p0lo) + __popc(m1 & p0hi)) << 8) |
-                               ((__popc(m0 & p1lo) + __popc(m1 & p1hi)) << 16);
-                }
-            }
-        }
-        __syncthreads();
-        if (warp == 0) {      // compaction: unique rows in slot order
-            const int ha = lane, hb = lane + 32;
-            const bool isfa = ha < H && hfirst[ha < H ? ha : 0] == ha, isfb = hb < H && hfirst[hb < H ? hb : 0] == hb;
-            const unsigned b0 = __ballot_sync(0xffffffffu, isfa), b1 = __ballot_sync(0xffffffffu, isfb);
-            const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int h = half ? hb : ha;
-                if (half ? isfb : isfa) {
-                    const int u = half ? __popc(b0) + __popc(b1 & lt) : __popc(b0 & lt);
-                    const int k2 = hkt[h], pk = hmult[h];
-                    unews[u] = hkn[h];
-                    utab[u] = k2 >> 1;
-                    umask[u] = k2 & 1;
-                    utopic[u] = htp[h];
-                    ugabs[u] = hga[h];
-                    umult[u] = (float)(pk & 0xff);
-                    ump0[u] = (float)((pk >> 8) & 0xff);
-                    ump1[u] = (float)((pk >> 16) & 0xff);
-                    prefetch_l2_bulk(C.hist_rows + (size_t)hkn[h] * LIME_HIST_LD, 2 * kD * 4);      // vc | gw, read in phase 2
-                }
-            }
-            int nun = (ha < H ? hkt[ha] & 1 : 0) + (hb < H ? hkt[hb] & 1 : 0);      // unmasked history slots
-            nun = __reduce_add_sync(0xffffffffu, nun);
-            if (lane == 0) {
-                misc[M_U] = __popc(b0) + __popc(b1);
-                misc[M_NUN] = nun;
-            }
-        }
-        __syncthreads();
-        const int U = misc[M_U];
-        LIME_TICK(1);
 
         // ================= roles ======================================================================
         if (warp < kCWarps) {
             // ---------------- phase 1: candidate-aware attention weights a[u][c] (layers.py:66-81) ------
-            if (U <= 32) attention<8>(C, T, U, cnt, misc[M_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
-            else         attention<16>(C, T, U, cnt, misc[M_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
+            if (U <= 32) attention<8>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
+            else         attention<16>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
             bar_compute();
             LIME_TICK(2);
 
@@ -757,8 +769,14 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             }
             bar_compute();
             LIME_TICK(3);
+        } else {
+            // issuer warp: claim the next work unit and run part 1 of its front end while the compute warps are in phase 1
+            // (part 2 runs after this unit's last MMA)
+            if (lane == 0) next_unit = atomicAdd(args.work_counter, 1);
+            next_unit = __shfl_sync(0xffffffffu, next_unit, 0);
+            front_meta(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, next_unit, lane, hkn, hkt, htp, hga);
         }
-        // the number of passes is known to the other roles at the first CTA barrier below; pass 0 always exists
+        // the number of passes is known to the issuer at the first CTA barrier below; pass 0 always exists
         int npass = 1;
         for (int pass = 0; pass < npass; ++pass) {
             if (warp < kCWarps) {
@@ -768,39 +786,13 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
                 const int nrows = min(G, U - u0);
                 if (tid == 0) misc[M_NPAD] = (nodes * nrows + 15) & ~15;      // published by the first full-barrier arrive
                 if (nodes == 2) {
-                    if (nrows > kRPT) produce_operands<2, 2>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, bias_s, s01_s, flag_s, rowoff_s, cand16, ctab16, bar_full, bar_free, use0, use1);
-                    else            produce_operands<2, 1>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, bias_s, s01_s, flag_s, rowoff_s, cand16, ctab16, bar_full, bar_free, use0, use1);
+                    if (nrows > kRPT) produce_operands<2, 2>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, s01_s, flag_s, cnews, ctab, cnt, cand16, ctab16, bar_full, bar_free, use0, use1);
+                    else              produce_operands<2, 1>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, s01_s, flag_s, cnews, ctab, cnt, cand16, ctab16, bar_full, bar_free, use0, use1);
                 } else {
-                    produce_operands<4, 1>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, bias_s, s01_s, flag_s, rowoff_s, cand16, ctab16, bar_full, bar_free, use0, use1);
+                    produce_operands<4, 1>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, s01_s, flag_s, cnews, ctab, cnt, cand16, ctab16, bar_full, bar_free, use0, use1);
                 }
-            } else if (warp == kMmaWarp) {
+            } else {
                 // ---------------- MMA issuer -------------------------------------------------------------
-                // first (the compute warps are still in phase 1): pull the NEXT unit's impression arrays into L2 (the cache
-                // rows are prefetched by their own unit: a whole unit of look-ahead for 296 CTAs overflows the L2)
-                if (pass == 0) {
-                    const int nxt = misc[M_NEXT];
-                    if (lane == 0) misc[M_NEXT2] = atomicAdd(args.work_counter, 1);
-                    if (nxt < I.num_units) {
-                        const int nimp = I.unit_imp[nxt], np0 = I.unit_pair0[nxt], ncnt = I.unit_count[nxt];
-                        if (lane == 0) {
-                            misc[M_NIMP] = nimp;
-                            misc[M_NP0] = np0;
-                            misc[M_NCNT] = ncnt;
-                        }
-                        const long long ho = (long long)nimp * H;
-                        for (int j = lane; 32 * j < H; j += 32) prefetch_l2(I.hist_news + ho + 32 * j);
-                        for (int j = lane; 32 * j < ncnt; j += 32) prefetch_l2(I.cand_news + np0 + 32 * j);
-                        // the impression arrays themselves (phase 0 of the next unit reads them)
-                        if (lane < 2) prefetch_l2(I.hist_mask + ho + 32 * lane);
-                        if (lane < 3) {
-                            prefetch_l2(I.hist_fresh + ho + 32 * lane);
-                            prefetch_l2(I.hist_life + ho + 32 * lane);
-                            prefetch_l2(I.cand_fresh + np0 + 32 * lane);
-                            prefetch_l2(I.cand_life + np0 + 32 * lane);
-                            if (I.cand_remaining) prefetch_l2(I.cand_remaining + np0 + 32 * lane);
-                        }
-                    }
-                }
                 const uint32_t sb = tc::smem_u32(base);
                 uint32_t idesc = 0;
                 for (int kc = 0; kc < kStages; ++kc) {
@@ -898,9 +890,12 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
                             args.scores[(long long)pair0 + c] = (ms_new / (float)P + cscal[c * 4 + 3] + acc_new / l_new) * cw[c];
                     }
                 }
+            } else if (pass == npass - 1) {
+                // ---------------- issuer warp: front end of the NEXT unit, in the shadow of this epilogue --------
+                front_dedup(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, lane, hkn, hkt, htp, hga);
             }
             ++pass_iter;
-            __syncthreads();   // out_s (aliasing the O operand) is free again; TMEM may be overwritten
+            __syncthreads();   // out_s (aliasing the O operand) is free again; TMEM may be overwritten; next unit buffer ready
             LIME_TICK(7);
         }
 
@@ -910,24 +905,27 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
         }
 
         // ---------------- P > H: user-node rows take part in the GraphSAGE mean (userEncoders.py:121,153) -------
-        if ((args.prefix_main > H || args.prefix_tail > H) && warp < kCWarps) {
-            for (int c = warp; c < cnt; c += kCWarps) {
-                const int P = cP[c];
-                if (P > H) {
-                    int jn = P - H - 1;
-                    jn = jn < C.user_nodes ? jn : C.user_nodes - 1;
-                    const float *uu = C.un_prefix + (size_t)jn * kD;
-                    const float *hr2 = C.hist_rows + (size_t)cnews[c] * LIME_HIST_LD + LIME_HIST_VC;
-                    const float *tr2 = C.hist_tab + (size_t)ctab[c] * LIME_HTAB_LD;
-                    float un = 0.f;
-                    for (int d = lane; d < kD; d += 32) un = fmaf(hr2[d] + tr2[d], uu[d], un);
-                    un = warp_sum(un);
-                    if (lane == 0) {
-                        const float bs = (pool_s[c * 4 + 3] + un) / (float)P + cscal[c * 4 + 3] + pool_s[c * 4 + 2] / pool_s[c * 4 + 1];
-                        args.scores[(long long)pair0 + c] = bs * cw[c];
+        if (args.prefix_main > H || args.prefix_tail > H) {
+            if (warp < kCWarps) {
+                for (int c = warp; c < cnt; c += kCWarps) {
+                    const int P = cP[c];
+                    if (P > H) {
+                        int jn = P - H - 1;
+                        jn = jn < C.user_nodes ? jn : C.user_nodes - 1;
+                        const float *uu = C.un_prefix + (size_t)jn * kD;
+                        const float *hr2 = C.hist_rows + (size_t)cnews[c] * LIME_HIST_LD + LIME_HIST_VC;
+                        const float *tr2 = C.hist_tab + (size_t)ctab[c] * LIME_HTAB_LD;
+                        float un = 0.f;
+                        for (int d = lane; d < kD; d += 32) un = fmaf(hr2[d] + tr2[d], uu[d], un);
+                        un = warp_sum(un);
+                        if (lane == 0) {
+                            const float bs = (pool_s[c * 4 + 3] + un) / (float)P + cscal[c * 4 + 3] + pool_s[c * 4 + 2] / pool_s[c * 4 + 1];
+                            args.scores[(long long)pair0 + c] = bs * cw[c];
+                        }
                     }
                 }
             }
+            __syncthreads();   // pool_s is re-initialised at the top of the next unit
         }
         LIME_TICK(8);
     }
