@@ -264,6 +264,7 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
     // thread: no register room for that, the two rows overlap each other's latency instead)
     constexpr bool kPipe = TPT == 1;
     float4 nx[TPT][4];
+    float4 nbias = ldg4(C.gate_bias + 4 * sub);      // gate bias' of the next stage's 4 dims (prefetched like the rows)
 #pragma unroll
     for (int t = 0; t < TPT; ++t) {
         if (!kPipe) break;
@@ -293,6 +294,8 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
             gg[t][0] = nx[t][2].x + nx[t][3].x; gg[t][1] = nx[t][2].y + nx[t][3].y;
             gg[t][2] = nx[t][2].z + nx[t][3].z; gg[t][3] = nx[t][2].w + nx[t][3].w;
         }
+        const float4 bias_now = nbias;
+        if (d0 + 32 < kD) nbias = ldg4(C.gate_bias + d0 + 32);
         if (kPipe && d0 + 32 < kD) {
 #pragma unroll
             for (int t = 0; t < TPT; ++t) {
@@ -303,8 +306,7 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
             }
         }
         if (d0 < kD) {      // the slot is free: this thread waited for it when it issued the stage's copies
-            const float4 bb4 = ldg4(C.gate_bias + d0);
-            const float bb[4] = {bb4.x, bb4.y, bb4.z, bb4.w};
+            const float bb[4] = {bias_now.x, bias_now.y, bias_now.z, bias_now.w};
 #pragma unroll
             for (int t = 0; t < TPT; ++t) {
                 if (ok[t]) {
@@ -575,13 +577,15 @@ __device__ __forceinline__ void front_meta(const ScoreArgs &args, unsigned char 
     __syncwarp();
 }
 
-// Part 2, during the previous unit's epilogue: deduplication of the history slots into unique operand rows.
+// Part 2, during the previous unit's epilogue: deduplication of the history slots into unique operand rows.  Slots with
+// equal (news, bucket pair, mask) are one row.  A lane owns the slots lane and lane + 32 and scans all H keys (broadcast
+// reads, no cross-lane dependency): lowest equal slot = the unique row, number of equal slots = its multiplicity (overall
+// and inside the two GraphSAGE prefixes); one ballot pair then compacts the unique rows in slot order.
 __device__ __forceinline__ void front_dedup(const ScoreArgs &args, unsigned char *ub, int lane, const int *hkn, const int *hkt,
                                             const int *htp, const float *hga) {
-    const LimeImpressions &I = args.imp;
-    const int H = I.max_history;
     int *info = reinterpret_cast<int *>(ub + UB_INFO);
-    if (info[UI_UNIT] >= I.num_units) return;
+    if (info[UI_UNIT] >= args.imp.num_units) return;
+    const int H = args.imp.max_history;
     int *unews = reinterpret_cast<int *>(ub + UB_UNEWS);
     int *utab = reinterpret_cast<int *>(ub + UB_UTAB);
     int *umask = reinterpret_cast<int *>(ub + UB_UMASK);
@@ -590,40 +594,53 @@ __device__ __forceinline__ void front_dedup(const ScoreArgs &args, unsigned char
     float *ump0 = reinterpret_cast<float *>(ub + UB_UMP0);
     float *ump1 = reinterpret_cast<float *>(ub + UB_UMP1);
     float *ugabs = reinterpret_cast<float *>(ub + UB_UGABS);
-    // ---- dedup: slots with equal (news, bucket pair, mask) are one operand row.  A lane holds the keys of slots lane and
-    // lane + 32; two ballots per reference slot give the set of equal slots (lowest member = the unique row, size = the
-    // multiplicity); slots already absorbed by an earlier reference are skipped (the zero padding is one iteration).
     const int pz0 = args.prefix_main < H ? args.prefix_main : H, pz1 = args.prefix_tail < H ? args.prefix_tail : H;
     const int ha = lane, hb = lane + 32;
     const int k1a = ha < H ? hkn[ha] : -1 - ha, k2a = ha < H ? hkt[ha] : -1;
     const int k1b = hb < H ? hkn[hb] : -1 - hb, k2b = hb < H ? hkt[hb] : -1;
-    const unsigned p0lo = pz0 >= 32 ? 0xffffffffu : (1u << pz0) - 1u, p0hi = pz0 > 32 ? (1u << (pz0 - 32)) - 1u : 0u;
-    const unsigned p1lo = pz1 >= 32 ? 0xffffffffu : (1u << pz1) - 1u, p1hi = pz1 > 32 ? (1u << (pz1 - 32)) - 1u : 0u;
-    unsigned seen0 = 0, seen1 = 0;     // slots already assigned to a unique row (warp-uniform)
-    int U = 0;
-    for (int r = 0; r < H; ++r) {
-        if ((r < 32 ? seen0 >> r : seen1 >> (r - 32)) & 1u) continue;
-        const int r1 = hkn[r], r2 = hkt[r];
-        const unsigned m0 = __ballot_sync(0xffffffffu, k1a == r1 && k2a == r2);
-        const unsigned m1 = __ballot_sync(0xffffffffu, k1b == r1 && k2b == r2);
-        seen0 |= m0;
-        seen1 |= m1;
-        if (lane == 0) {
-            unews[U] = r1;
-            utab[U] = r2 >> 1;
-            umask[U] = r2 & 1;
-            utopic[U] = htp[r];
-            ugabs[U] = hga[r];
-            umult[U] = (float)(__popc(m0) + __popc(m1));
-            ump0[U] = (float)(__popc(m0 & p0lo) + __popc(m1 & p0hi));
-            ump1[U] = (float)(__popc(m0 & p1lo) + __popc(m1 & p1hi));
-        }
-        ++U;
+    int fa = 99, fb = 99, na = 0, nb_ = 0, na0 = 0, nb0 = 0, na1 = 0, nb1 = 0;
+#pragma unroll 4
+    for (int j = H - 1; j >= 0; --j) {          // downwards: the last hit is the lowest equal slot
+        const int n = hkn[j], t = hkt[j];
+        const bool ea = k1a == n && k2a == t, eb = k1b == n && k2b == t;
+        fa = ea ? j : fa;
+        fb = eb ? j : fb;
+        na += ea;
+        nb_ += eb;
+        na0 += ea && j < pz0;
+        nb0 += eb && j < pz0;
+        na1 += ea && j < pz1;
+        nb1 += eb && j < pz1;
+    }
+    const bool isfa = ha < H && fa == ha, isfb = hb < H && fb == hb;
+    const unsigned b0 = __ballot_sync(0xffffffffu, isfa), b1 = __ballot_sync(0xffffffffu, isfb);
+    const unsigned lt = (1u << lane) - 1u;
+    if (isfa) {
+        const int u = __popc(b0 & lt);
+        unews[u] = k1a;
+        utab[u] = k2a >> 1;
+        umask[u] = k2a & 1;
+        utopic[u] = htp[ha];
+        ugabs[u] = hga[ha];
+        umult[u] = (float)na;
+        ump0[u] = (float)na0;
+        ump1[u] = (float)na1;
+    }
+    if (isfb) {
+        const int u = __popc(b0) + __popc(b1 & lt);
+        unews[u] = k1b;
+        utab[u] = k2b >> 1;
+        umask[u] = k2b & 1;
+        utopic[u] = htp[hb];
+        ugabs[u] = hga[hb];
+        umult[u] = (float)nb_;
+        ump0[u] = (float)nb0;
+        ump1[u] = (float)nb1;
     }
     int nun = (ha < H ? k2a & 1 : 0) + (hb < H ? k2b & 1 : 0);      // unmasked history slots
     nun = __reduce_add_sync(0xffffffffu, nun);
     if (lane == 0) {
-        info[UI_U] = U;
+        info[UI_U] = __popc(b0) + __popc(b1);
         info[UI_NUN] = nun;
     }
     __syncwarp();
