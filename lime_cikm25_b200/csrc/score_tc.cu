@@ -510,28 +510,22 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
     }
 }
 
-// Front end of one work unit, executed by ONE warp (the MMA issuer) in two parts while the compute warps work on the
-// previous unit.  Part 1, during its attention phase: unit metadata (history keys, bucket pairs, topic ids; candidate
-// rows, lifetime weights, folded scalars).  Writes the unit buffer `ub` and the front-end scratch.
-__device__ __forceinline__ void front_meta(const ScoreArgs &args, unsigned char *ub, int unit, int lane, int *hkn, int *hkt,
+// Front end of one work unit, executed by ONE warp (the MMA issuer) while the compute warps work on the previous unit.
+// Part 1, during its attention phase: the history slots (keys, bucket pairs, topic ids, gate bounds) into the front-end
+// scratch.  Parts 2 and 3, during its epilogue: dedup of the slots, then the candidates (cache rows, lifetime weights,
+// folded scalars).  All results land in the unit buffer `ub`.
+__device__ __forceinline__ void front_hist(const ScoreArgs &args, unsigned char *ub, int unit, int lane, int *hkn, int *hkt,
                                            int *htp, float *hga) {
     const LimeNewsCache &C = args.cache;
     const LimeImpressions &I = args.imp;
     const int H = I.max_history, nb = C.num_buckets, T = C.num_topics;
     int *info = reinterpret_cast<int *>(ub + UB_INFO);
-    float *cscal = reinterpret_cast<float *>(ub + UB_CSCAL);
-    float *cw = reinterpret_cast<float *>(ub + UB_CW);
-    int *cnews = reinterpret_cast<int *>(ub + UB_CNEWS);
-    int *ctab = reinterpret_cast<int *>(ub + UB_CTAB);
-    int *cP = reinterpret_cast<int *>(ub + UB_CP);
-    int *ctopic = reinterpret_cast<int *>(ub + UB_CTOPIC);
     if (unit >= I.num_units) {
         if (lane == 0) info[UI_UNIT] = unit;
         __syncwarp();
         return;
     }
     const int imp = I.unit_imp[unit], pair0 = I.unit_pair0[unit], cnt = I.unit_count[unit];
-    int flags = 0;
     for (int h = lane; h < H; h += 32) {
         const long long o = (long long)imp * H + h;
         int n = I.hist_news[o];
@@ -546,6 +540,36 @@ __device__ __forceinline__ void front_meta(const ScoreArgs &args, unsigned char 
         htp[h] = (tp < 0 || tp >= T) ? 0 : tp;
         hga[h] = mt.y;
     }
+    // the candidate arrays of the unit: L2 by the time part 3 reads them
+    for (int j = lane; 32 * j < cnt; j += 32) {
+        prefetch_l2(I.cand_news + pair0 + 32 * j);
+        prefetch_l2(I.cand_fresh + pair0 + 32 * j);
+        prefetch_l2(I.cand_life + pair0 + 32 * j);
+        if (I.cand_remaining) prefetch_l2(I.cand_remaining + pair0 + 32 * j);
+    }
+    if (lane == 0) {
+        info[UI_UNIT] = unit;
+        info[UI_IMP] = imp;
+        info[UI_PAIR0] = pair0;
+        info[UI_CNT] = cnt;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char *ub, int lane) {
+    const LimeNewsCache &C = args.cache;
+    const LimeImpressions &I = args.imp;
+    const int nb = C.num_buckets, T = C.num_topics;
+    int *info = reinterpret_cast<int *>(ub + UB_INFO);
+    if (info[UI_UNIT] >= I.num_units) return;
+    float *cscal = reinterpret_cast<float *>(ub + UB_CSCAL);
+    float *cw = reinterpret_cast<float *>(ub + UB_CW);
+    int *cnews = reinterpret_cast<int *>(ub + UB_CNEWS);
+    int *ctab = reinterpret_cast<int *>(ub + UB_CTAB);
+    int *cP = reinterpret_cast<int *>(ub + UB_CP);
+    int *ctopic = reinterpret_cast<int *>(ub + UB_CTOPIC);
+    const int pair0 = info[UI_PAIR0], cnt = info[UI_CNT];
+    int flags = 0;
     for (int c = lane; c < cnt; c += 32) {
         const long long p = (long long)pair0 + c;
         int n = I.cand_news[p];
@@ -567,13 +591,7 @@ __device__ __forceinline__ void front_meta(const ScoreArgs &args, unsigned char 
         if (!(m0.z <= kWAbsMax)) flags = 4;        // beyond the fp16 operand range: exact kernel
     }
     flags = __reduce_or_sync(0xffffffffu, flags);
-    if (lane == 0) {
-        info[UI_UNIT] = unit;
-        info[UI_IMP] = imp;
-        info[UI_PAIR0] = pair0;
-        info[UI_CNT] = cnt;
-        info[UI_FLAGS] = flags;
-    }
+    if (lane == 0) info[UI_FLAGS] = flags;
     __syncwarp();
 }
 
@@ -687,8 +705,9 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
         int u0 = 0;
         if (lane == 0) u0 = atomicAdd(args.work_counter, 1);
         u0 = __shfl_sync(0xffffffffu, u0, 0);
-        front_meta(args, base + OFF_UB, u0, lane, hkn, hkt, htp, hga);
+        front_hist(args, base + OFF_UB, u0, lane, hkn, hkt, htp, hga);
         front_dedup(args, base + OFF_UB, lane, hkn, hkt, htp, hga);
+        front_cand(args, base + OFF_UB, lane);
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -788,10 +807,10 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             LIME_TICK(3);
         } else {
             // issuer warp: claim the next work unit and run part 1 of its front end while the compute warps are in phase 1
-            // (part 2 runs after this unit's last MMA)
+            // (parts 2 and 3 run after this unit's last MMA)
             if (lane == 0) next_unit = atomicAdd(args.work_counter, 1);
             next_unit = __shfl_sync(0xffffffffu, next_unit, 0);
-            front_meta(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, next_unit, lane, hkn, hkt, htp, hga);
+            front_hist(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, next_unit, lane, hkn, hkt, htp, hga);
         }
         // the number of passes is known to the issuer at the first CTA barrier below; pass 0 always exists
         int npass = 1;
@@ -910,6 +929,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             } else if (pass == npass - 1) {
                 // ---------------- issuer warp: front end of the NEXT unit, in the shadow of this epilogue --------
                 front_dedup(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, lane, hkn, hkt, htp, hga);
+                front_cand(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, lane);
             }
             ++pass_iter;
             __syncthreads();   // out_s (aliasing the O operand) is free again; TMEM may be overwritten; next unit buffer ready

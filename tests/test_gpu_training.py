@@ -104,7 +104,8 @@ def test_news_encoder_gradients(lib):
     (v64 * R.double()).sum().backward()
     assert rel(v.detach().cpu(), v64.detach()) < 1e-4
     # the same computation by torch's own fp32 CPU kernels: the yardstick for fp32 rounding through the
-    # transformer layer (a gradient is accepted within 1e-3 of fp64 AND within 4x of what torch-fp32 achieves)
+    # transformer layer (a gradient is accepted within 1e-3 of fp64 AND within 4x of what torch-fp32 achieves, plus 2e-4:
+    # the embedding gradients are accumulated with atomics, their error moves by ~1e-4 from run to run)
     sd32 = {k: t.detach().float().requires_grad_(t.dtype.is_floating_point) for k, t in sd.items()}
     v32 = O.lime_news(sd32, tl(news.title_text), tl(news.body_text), tl(news.category), tl(news.subCategory),
                       torch.as_tensor(fresh), torch.as_tensor(life), cfg, torch.float32)
@@ -119,7 +120,7 @@ def test_news_encoder_gradients(lib):
             continue
         assert p.grad is not None, name
         err, err32 = rel(p.grad.cpu(), g64), rel(sd32[name].grad, g64)
-        assert err < 1e-3 and err < 4 * err32 + 1e-4, (name, err, err32)
+        assert err < 1e-3 and err < 4 * err32 + 2e-4, (name, err, err32)
         worst = max(worst, err)
         checked += 1
     assert checked >= 40
