@@ -193,6 +193,54 @@ __device__ __forceinline__ void split4(const float (&x)[4], uint2 &hi, uint2 &lo
     lo = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
 }
 
+// Candidate operand (M side) of a unit: warp w streams the row groups w, w + 7, w + 14 of every stage with cp.async --
+// lane = (row in group, 16-byte chunk), one instruction moves the 64 contiguous bytes of a stage for 8 operand rows.
+// cp.async.mbarrier.arrive.noinc publishes a stage when this thread's copies have landed (no thread waits for the data).
+struct ACopy {
+    uint32_t on[3], ot[3];       // element offsets of this thread's 3 operand rows inside cand16 / ctab16 (0xffffffff: unused)
+    uint32_t dst;
+    int rsub, ch;
+    __device__ __forceinline__ void init(unsigned char *base, int tid, const int *cnews, const int *ctab, int cnt) {
+        rsub = (tid >> 2) & 7;
+        ch = tid & 3;
+        const int g0 = tid >> 5;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int g = g0 + kCWarps * i;
+            int c = kTile, k = 0;
+            if (g < 16) m_row_owner(g >> 2, 8 * (g & 3) + rsub, c, k);
+            const bool rok = c < cnt;
+            const int cc = rok ? c : 0;
+            on[i] = rok ? (uint32_t)cnews[cc] * (uint32_t)kC16 + (uint32_t)(k * 2 * kD) : 0xffffffffu;
+            ot[i] = (uint32_t)ctab[cc] * (uint32_t)kC16 + (uint32_t)(k * 2 * kD);
+        }
+        dst = tc::smem_u32(base) + OFF_A + (uint32_t)g0 * 1024u + (uint32_t)rsub * 128u;
+    }
+    // stage kc -> ring slot kc & 1 (waits until the MMAs of the slot's previous use have drained it)
+    __device__ __forceinline__ void issue(int kc, const __half *cand16, const __half *ctab16, uint64_t *bar_full,
+                                          uint64_t *bar_free, uint32_t &use0, uint32_t &use1) const {
+        const int s = kc & 1;
+        const uint32_t uses = s ? use1 : use0;
+        if (uses >= 1) tc::mbar_wait(bar_free + s, (uses - 1) & 1u);
+        if (kc < kStages - 1 || ch < (kD - 32 * (kStages - 1)) / 8) {
+            const uint32_t d = dst + (uint32_t)(((4 * s + ch) ^ rsub) << 4);
+            const int eo = 32 * kc + 8 * ch;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                if (on[i] != 0xffffffffu) {
+                    const uint32_t di = d + (uint32_t)(kCWarps * i) * 1024u;
+                    cp_async16(di, cand16 + on[i] + eo);
+                    cp_async16(di + kAImg, cand16 + on[i] + kD + eo);
+                    cp_async16(di + 2 * kAImg, ctab16 + ot[i] + eo);
+                    cp_async16(di + 3 * kAImg, ctab16 + ot[i] + kD + eo);
+                }
+            }
+        }
+        cp_async_mbar_arrive_noinc(bar_full + s);
+        if (s) ++use1; else ++use0;
+    }
+};
+
 // Operand production of one pass: NODES rows of O per unique history row u0 <= u < u0 + nrows (fp16 hi / lo
 // images, K stages of 32 dims through the two halves of the 64-dim tile) and the node sums (sum o, sum o^2).
 // Executed by the 256 compute threads; a thread owns 4 dims of a row per stage (8 threads per row) and, when
@@ -203,47 +251,12 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
                                                  const int *unews, const int *utab, const float *mid_s,
                                                  const float *whalf_s, float *s01_s, int *flag_s, const int *cnews,
                                                  const int *ctab, int cnt, const __half *cand16, const __half *ctab16,
-                                                 uint64_t *bar_full, uint64_t *bar_free, uint32_t &use0, uint32_t &use1) {
+                                                 uint64_t *bar_full, uint64_t *bar_free, uint32_t &use0, uint32_t &use1,
+                                                 int pre_issued) {
     const int sub = tid & 7;
-    // candidate operand (M side): warp w streams the row groups w, w + 7, w + 14 of every stage with cp.async -- lane =
-    // (row in group, 16-byte chunk), one instruction moves the 64 contiguous bytes of a stage for 8 operand rows.  The
-    // copies of stage k + 1 are issued right after the O rows of stage k, so they fly while stage k + 1 is evaluated;
-    // cp.async.mbarrier.arrive.noinc publishes them when they land (no thread waits for the data).
-    const int a_rsub = (tid >> 2) & 7, a_ch = tid & 3, a_g0 = tid >> 5;
-    uint32_t a_on[3], a_ot[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const int g = a_g0 + kCWarps * i;          // element offsets of operand row 8 g + a_rsub inside cand16 / ctab16
-        int c = kTile, k = 0;
-        if (g < 16) m_row_owner(g >> 2, 8 * (g & 3) + a_rsub, c, k);
-        const bool rok = c < cnt;
-        const int cc = rok ? c : 0;
-        a_on[i] = rok ? (uint32_t)cnews[cc] * (uint32_t)kC16 + (uint32_t)(k * 2 * kD) : 0xffffffffu;
-        a_ot[i] = (uint32_t)ctab[cc] * (uint32_t)kC16 + (uint32_t)(k * 2 * kD);
-    }
-    const uint32_t a_dst = tc::smem_u32(base) + OFF_A + (uint32_t)a_g0 * 1024u + (uint32_t)a_rsub * 128u;
-    auto issue_copies = [&](int kc) {       // stage kc -> ring slot kc & 1 (waits until the MMAs of stage kc - 2 have drained it)
-        const int s = kc & 1;
-        const uint32_t uses = s ? use1 : use0;
-        if (uses >= 1) tc::mbar_wait(bar_free + s, (uses - 1) & 1u);
-        if (kc < kStages - 1 || a_ch < (kD - 32 * (kStages - 1)) / 8) {
-            const uint32_t dst = a_dst + (uint32_t)(((4 * s + a_ch) ^ a_rsub) << 4);
-            const int eo = 32 * kc + 8 * a_ch;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                if (a_on[i] != 0xffffffffu) {
-                    const uint32_t di = dst + (uint32_t)(kCWarps * i) * 1024u;
-                    cp_async16(di, cand16 + a_on[i] + eo);
-                    cp_async16(di + kAImg, cand16 + a_on[i] + kD + eo);
-                    cp_async16(di + 2 * kAImg, ctab16 + a_ot[i] + eo);
-                    cp_async16(di + 3 * kAImg, ctab16 + a_ot[i] + kD + eo);
-                }
-            }
-        }
-        cp_async_mbar_arrive_noinc(bar_full + s);
-        if (s) ++use1; else ++use0;
-    };
-    issue_copies(0);
+    ACopy ac;
+    ac.init(base, tid, cnews, ctab, cnt);
+    for (int kc = pre_issued; kc < 1; ++kc) ac.issue(kc, cand16, ctab16, bar_full, bar_free, use0, use1);
     bool ok[TPT];
     const float *hrow[TPT], *trow[TPT];
     float aj[TPT][NODES], ps[TPT][2 * NODES];
@@ -260,55 +273,46 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
 #pragma unroll
         for (int i = 0; i < 2 * NODES; ++i) ps[t][i] = 0.0f;
     }
-    // one row per thread: stage kc + 1's global loads are in flight while stage kc is evaluated (two rows per
-    // thread: no register room for that, the two rows overlap each other's latency instead)
-    constexpr bool kPipe = TPT == 1;
-    float4 nx[TPT][4];
+    // the first row of a thread: stage kc + 1's global loads are in flight while stage kc is evaluated; the second row
+    // (passes with more than 28 rows): loaded at the start of its stage, consumed after the first row's arithmetic
+    float4 nx[4], nx1[4];
     float4 nbias = ldg4(C.gate_bias + 4 * sub);      // gate bias' of the next stage's 4 dims (prefetched like the rows)
-#pragma unroll
-    for (int t = 0; t < TPT; ++t) {
-        if (!kPipe) break;
-        const int d0 = 4 * sub;
-        nx[t][0] = ldg4(hrow[t] + LIME_HIST_VC + d0);
-        nx[t][1] = ldg4(trow[t] + d0);
-        nx[t][2] = ldg4(hrow[t] + LIME_HIST_GW + d0);
-        nx[t][3] = ldg4(trow[t] + kD + d0);
-    }
+    nx[0] = ldg4(hrow[0] + LIME_HIST_VC + 4 * sub);
+    nx[1] = ldg4(trow[0] + 4 * sub);
+    nx[2] = ldg4(hrow[0] + LIME_HIST_GW + 4 * sub);
+    nx[3] = ldg4(trow[0] + kD + 4 * sub);
     for (int kc = 0; kc < kStages; ++kc) {
         const int s = kc & 1;
         const int d0 = 32 * kc + 4 * sub;
-        float v[TPT][4], gg[TPT][4];
-        if (!kPipe && d0 < kD) {
-#pragma unroll
-            for (int t = 0; t < TPT; ++t) {
-                nx[t][0] = ldg4(hrow[t] + LIME_HIST_VC + d0);
-                nx[t][1] = ldg4(trow[t] + d0);
-                nx[t][2] = ldg4(hrow[t] + LIME_HIST_GW + d0);
-                nx[t][3] = ldg4(trow[t] + kD + d0);
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < TPT; ++t) {
-            v[t][0] = (nx[t][0].x + nx[t][1].x) * kOScale; v[t][1] = (nx[t][0].y + nx[t][1].y) * kOScale;
-            v[t][2] = (nx[t][0].z + nx[t][1].z) * kOScale; v[t][3] = (nx[t][0].w + nx[t][1].w) * kOScale;
-            gg[t][0] = nx[t][2].x + nx[t][3].x; gg[t][1] = nx[t][2].y + nx[t][3].y;
-            gg[t][2] = nx[t][2].z + nx[t][3].z; gg[t][3] = nx[t][2].w + nx[t][3].w;
-        }
+        float v[4], gg[4];
+        v[0] = (nx[0].x + nx[1].x) * kOScale; v[1] = (nx[0].y + nx[1].y) * kOScale;
+        v[2] = (nx[0].z + nx[1].z) * kOScale; v[3] = (nx[0].w + nx[1].w) * kOScale;
+        gg[0] = nx[2].x + nx[3].x; gg[1] = nx[2].y + nx[3].y;
+        gg[2] = nx[2].z + nx[3].z; gg[3] = nx[2].w + nx[3].w;
         const float4 bias_now = nbias;
-        if (d0 + 32 < kD) nbias = ldg4(C.gate_bias + d0 + 32);
-        if (kPipe && d0 + 32 < kD) {
-#pragma unroll
-            for (int t = 0; t < TPT; ++t) {
-                nx[t][0] = ldg4(hrow[t] + LIME_HIST_VC + d0 + 32);
-                nx[t][1] = ldg4(trow[t] + d0 + 32);
-                nx[t][2] = ldg4(hrow[t] + LIME_HIST_GW + d0 + 32);
-                nx[t][3] = ldg4(trow[t] + kD + d0 + 32);
-            }
+        if (TPT == 2 && d0 < kD) {
+            nx1[0] = ldg4(hrow[TPT - 1] + LIME_HIST_VC + d0);
+            nx1[1] = ldg4(trow[TPT - 1] + d0);
+            nx1[2] = ldg4(hrow[TPT - 1] + LIME_HIST_GW + d0);
+            nx1[3] = ldg4(trow[TPT - 1] + kD + d0);
+        }
+        if (d0 + 32 < kD) {
+            nbias = ldg4(C.gate_bias + d0 + 32);
+            nx[0] = ldg4(hrow[0] + LIME_HIST_VC + d0 + 32);
+            nx[1] = ldg4(trow[0] + d0 + 32);
+            nx[2] = ldg4(hrow[0] + LIME_HIST_GW + d0 + 32);
+            nx[3] = ldg4(trow[0] + kD + d0 + 32);
         }
         if (d0 < kD) {      // the slot is free: this thread waited for it when it issued the stage's copies
             const float bb[4] = {bias_now.x, bias_now.y, bias_now.z, bias_now.w};
 #pragma unroll
             for (int t = 0; t < TPT; ++t) {
+                if (t == 1) {
+                    v[0] = (nx1[0].x + nx1[1].x) * kOScale; v[1] = (nx1[0].y + nx1[1].y) * kOScale;
+                    v[2] = (nx1[0].z + nx1[1].z) * kOScale; v[3] = (nx1[0].w + nx1[1].w) * kOScale;
+                    gg[0] = nx1[2].x + nx1[3].x; gg[1] = nx1[2].y + nx1[3].y;
+                    gg[2] = nx1[2].z + nx1[3].z; gg[3] = nx1[2].w + nx1[3].w;
+                }
                 if (ok[t]) {
                     const int nrow0 = NODES * ((tid >> 3) + kRPT * t);
 #pragma unroll
@@ -318,8 +322,8 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
                         float o[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float den = ex2_approx(fmaf(a, gg[t][e], bb[e])) + 1.0f;
-                            o[e] = fmaf(-(v[t][e] * oma), rcp_approx(den), v[t][e]);
+                            const float den = ex2_approx(fmaf(a, gg[e], bb[e])) + 1.0f;
+                            o[e] = fmaf(-(v[e] * oma), rcp_approx(den), v[e]);
                             ps[t][2 * j] += o[e];
                             ps[t][2 * j + 1] = fmaf(o[e], o[e], ps[t][2 * j + 1]);
                         }
@@ -334,7 +338,7 @@ __device__ __forceinline__ void produce_operands(unsigned char *base, const Lime
         }
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(bar_full + s);
-        if (kc + 1 < kStages) issue_copies(kc + 1);
+        if (kc + 1 < kStages && kc + 1 >= pre_issued) ac.issue(kc + 1, cand16, ctab16, bar_full, bar_free, use0, use1);
     }
     // node sums of the row: sum o, sum o^2 per node, over the 8 lanes that share the row
 #pragma unroll
@@ -759,9 +763,21 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
 
         // ================= roles ======================================================================
         if (warp < kCWarps) {
+            // the candidate operand of the first two stages goes out now (both ring slots are free since the previous
+            // unit's epilogue): it lands during the attention phase
+            {
+                ACopy ac;
+                ac.init(base, tid, cnews, ctab, cnt);
+                ac.issue(0, cand16, ctab16, bar_full, bar_free, use0, use1);
+                ac.issue(1, cand16, ctab16, bar_full, bar_free, use0, use1);
+            }
             // ---------------- phase 1: candidate-aware attention weights a[u][c] (layers.py:66-81) ------
-            if (U <= 32) attention<8>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
-            else         attention<16>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
+            // lanes per candidate = the smallest power of two that covers the U rows with 4 rows per lane: short (deduplicated)
+            // histories put more candidates into a round (7 warps x 32 / LPC), and a round costs one table-load latency
+            if (U <= 8)       attention<2>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
+            else if (U <= 16) attention<4>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
+            else if (U <= 32) attention<8>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
+            else              attention<16>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
             bar_compute();
             LIME_TICK(2);
 
@@ -806,11 +822,12 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             bar_compute();
             LIME_TICK(3);
         } else {
-            // issuer warp: claim the next work unit and run part 1 of its front end while the compute warps are in phase 1
-            // (parts 2 and 3 run after this unit's last MMA)
+            // issuer warp: claim the next work unit and run parts 1 and 2 of its front end while the compute warps are in
+            // phase 1 (part 3 runs after this unit's last MMA)
             if (lane == 0) next_unit = atomicAdd(args.work_counter, 1);
             next_unit = __shfl_sync(0xffffffffu, next_unit, 0);
             front_hist(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, next_unit, lane, hkn, hkt, htp, hga);
+            front_dedup(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, lane, hkn, hkt, htp, hga);
         }
         // the number of passes is known to the issuer at the first CTA barrier below; pass 0 always exists
         int npass = 1;
@@ -822,10 +839,10 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
                 const int nrows = min(G, U - u0);
                 if (tid == 0) misc[M_NPAD] = (nodes * nrows + 15) & ~15;      // published by the first full-barrier arrive
                 if (nodes == 2) {
-                    if (nrows > kRPT) produce_operands<2, 2>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, s01_s, flag_s, cnews, ctab, cnt, cand16, ctab16, bar_full, bar_free, use0, use1);
-                    else              produce_operands<2, 1>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, s01_s, flag_s, cnews, ctab, cnt, cand16, ctab16, bar_full, bar_free, use0, use1);
+                    if (nrows > kRPT) produce_operands<2, 2>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, s01_s, flag_s, cnews, ctab, cnt, cand16, ctab16, bar_full, bar_free, use0, use1, pass == 0 ? 2 : 0);
+                    else              produce_operands<2, 1>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, s01_s, flag_s, cnews, ctab, cnt, cand16, ctab16, bar_full, bar_free, use0, use1, pass == 0 ? 2 : 0);
                 } else {
-                    produce_operands<4, 1>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, s01_s, flag_s, cnews, ctab, cnt, cand16, ctab16, bar_full, bar_free, use0, use1);
+                    produce_operands<4, 1>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, s01_s, flag_s, cnews, ctab, cnt, cand16, ctab16, bar_full, bar_free, use0, use1, pass == 0 ? 2 : 0);
                 }
             } else {
                 // ---------------- MMA issuer -------------------------------------------------------------
@@ -928,7 +945,6 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
                 }
             } else if (pass == npass - 1) {
                 // ---------------- issuer warp: front end of the NEXT unit, in the shadow of this epilogue --------
-                front_dedup(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, lane, hkn, hkt, htp, hga);
                 front_cand(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, lane);
             }
             ++pass_iter;
