@@ -233,6 +233,79 @@ def test_properties_at_scale(lib):
     assert rel(b.cpu().numpy(), a[torch.as_tensor(order).to(DEV)].cpu().numpy()) < 1e-5
 
 
+def test_dedup_of_repeated_history_rows(lib):
+    """The tensor-core kernel merges history slots with equal (news, bucket pair, mask) into one operand row with a
+    multiplicity.  Exercise every way the multiplicity enters: repeated clicked news inside the unmasked part (both
+    attention softmaxes, pooling), the same news with a different bucket pair or a different mask (must NOT merge),
+    a history that is one single row, and GraphSAGE prefixes that cut through a run of equal slots (main and tail)."""
+    H = 50
+    cfg = make_config(vocabulary_size=400, batch_size=32, max_history_num=H, word_embedding_init="skip")
+    model = L.Model(cfg)
+    model.initialize()
+    synth.synthetic_parameters(model, 11)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).eval()
+    news = synth.make_news_table(120, vocabulary_size=400, seed=3)
+    imp = synth.make_impressions(4, news.news_num, max_history=H, cand_fixed=9, near_zero_frac=0.5, seed=17)
+    imp.hist_mask[:] = True
+    # impression 0: slots 3, 4, 17, 40 are the same click (same news, same ages); slot 41 the same news, other ages
+    for h in (4, 17, 40, 41):
+        imp.hist_news[0, h] = imp.hist_news[0, 3]
+    for h in (4, 17, 40):
+        imp.hist_fresh[0, h], imp.hist_life[0, h] = imp.hist_fresh[0, 3], imp.hist_life[0, 3]
+    imp.hist_fresh[0, 41], imp.hist_life[0, 41] = 5e6, 700.0
+    # impression 1: the masked tail repeats a clicked (news, ages) pair: equal keys except for the mask
+    imp.hist_mask[1, 30:] = False
+    imp.hist_news[1, 30:] = imp.hist_news[1, 2]
+    imp.hist_fresh[1, 30:], imp.hist_life[1, 30:] = imp.hist_fresh[1, 2], imp.hist_life[1, 2]
+    # impression 2: the whole history is one row
+    imp.hist_news[2, :] = imp.hist_news[2, 0]
+    imp.hist_fresh[2, :], imp.hist_life[2, :] = imp.hist_fresh[2, 0], imp.hist_life[2, 0]
+    # impression 3: short history, zero padding (the common case)
+    imp.hist_mask[3, 6:] = False
+    imp.hist_news[3, 6:] = 0
+    imp.hist_fresh[3, 6:] = 0
+    imp.hist_life[3, 6:] = 0
+    model.config.use_remaining_lifetime_weighting = False
+    try:
+        with torch.no_grad():
+            cache = util.build_news_cache(model, news)
+            dimp = engine.DeviceImpressions(imp, DEV)
+            want = _stage_b_oracle(model, sd, cfg, cache, news, imp, 5)
+            out = {}
+            for name, mode in (("tc", ops.SCORE_AUTO), ("exact", ops.SCORE_EXACT)):
+                ops.score_configure(mode, 1e-6)
+                out[name] = model.scoring.score(cache.hist_rows, cache.cand_rows, dimp, prefix_main=5, cand16=cache.cand16,
+                                                meta=cache.meta).cpu().numpy()
+                assert int(dimp.work_counter[1]) == 0            # nothing handed to the fallback
+                # the last 13 pairs form a short mini-batch of the reference: prefix 4 cuts the run of slots 3, 4
+                out[name + "_tail"] = model.scoring.score(cache.hist_rows, cache.cand_rows, dimp, prefix_main=18,
+                                                          tail_start=imp.num_pairs - 13, prefix_tail=4, cand16=cache.cand16,
+                                                          meta=cache.meta).cpu().numpy()
+    finally:
+        ops.score_configure(ops.SCORE_AUTO, 1e-6)
+    assert rel(out["tc"], want) < TOL and rel(out["exact"], want) < TOL
+    assert rel(out["tc"], out["exact"]) < 5e-5 and rel(out["tc_tail"], out["exact_tail"]) < 5e-5
+    assert np.abs(out["tc_tail"] - out["tc"]).max() > 1e-4        # the prefix really matters on this data
+
+
+def test_split_f16_pairs_and_news_meta(lib):
+    """Cache-build helpers of the tensor-core path: x * 1024 = hi + lo to 2^-21, layout [k][hi 400 | lo 400]; the meta
+    sector repeats the cached topic id / bounds / folded scalars."""
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(37, 1720, generator=g) * torch.logspace(-4, 1, 1720)).to(DEV)
+    x[5, 7] = 0.0
+    stamp = torch.zeros(37, device=DEV)
+    pairs = ops.split_f16_pairs(x, 3, absmax=stamp)
+    assert pairs.dtype == torch.float16 and pairs.shape == (37, 2400)
+    p = pairs.double().view(37, 3, 2, 400)
+    back = (p[:, :, 0] + p[:, :, 1]).reshape(37, 1200) / 1024.0
+    ref = x[:, :1200].double()
+    # 2^-21 relative; values below 1e-4 put their lo half into the fp16 subnormals (6e-8 resolution / 1024)
+    assert bool(((back - ref).abs() <= 2.0 ** -20 * ref.abs() + 1e-10).all())
+    assert torch.equal(stamp, x[:, :1200].abs().max(dim=1).values)
+
+
 def test_compute_scores_drop_in(lib, tmp_path, monkeypatch):
     """util.compute_scores with the reference's signature: rank file + truth file round trip."""
     import types
