@@ -212,6 +212,9 @@ def run_b200(args):
     from lime_cikm25_b200 import _lib, engine, parallel, synth, util
     import torch.distributed as dist
 
+    # the contract is ONE JSON line on stdout: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes there too
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank, world, local = parallel.init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
