@@ -25,6 +25,16 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
+# The contract is ONE JSON line on stdout, but libraries write there too (NCCL prints "NCCL version ..." on the first
+# communicator): file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 METRIC = "eval_impressions_per_sec"
 UNIT = "impressions/s"
 D, H = 400, 50
@@ -148,7 +158,7 @@ def run_reference(args):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, imp):
@@ -212,9 +222,6 @@ def run_b200(args):
     from lime_cikm25_b200 import _lib, engine, parallel, synth, util
     import torch.distributed as dist
 
-    # the contract is ONE JSON line on stdout: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) goes there too
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
     rank, world, local = parallel.init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
@@ -385,7 +392,7 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(args, cfg, news, imp, sd_cpu)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
