@@ -41,12 +41,22 @@ D, H = 400, 50
 
 
 def parse_args():
+    a = _parse_args()
+    if a.news is None:
+        a.news = 73844 if a.shape == "adressa" else 65238
+    return a
+
+
+def _parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--news", type=int, default=65238, help="news in the vector cache (MIND: 65,238)")
+    ap.add_argument("--shape", default="mind", choices=["mind", "adressa"],
+                    help="synthetic data shape: MIND (default, BASELINE.json configs[1]) or Adressa (configs[3]: 73,844 news with "
+                         "full 128-token bodies and short titles, 601,215 users)")
+    ap.add_argument("--news", type=int, default=None, help="news in the vector cache (MIND: 65,238; Adressa: 73,844)")
     ap.add_argument("--vocab", type=int, default=40000)
     ap.add_argument("--impressions", type=int, default=73152, help="impressions per step per GPU (MIND-small dev size)")
     ap.add_argument("--batch-size", type=int, default=32, help="reference mini-batch size (GraphSAGE prefix)")
@@ -101,8 +111,12 @@ def make_setup(args, rank, need_news_text=True):
     from lime_cikm25_b200 import synth
     from lime_cikm25_b200.config import default_config as make_config
     cfg = make_config(vocabulary_size=args.vocab, batch_size=args.batch_size, word_embedding_init="skip")
-    news = synth.make_news_table(args.news, vocabulary_size=args.vocab, seed=1)
-    imp = synth.make_impressions(args.impressions, news.news_num, seed=100 + rank)
+    if args.shape == "adressa":      # README.md:15 of the reference: title mean 6.63, bodies always truncated to the full 128 tokens
+        news = synth.make_news_table(args.news, vocabulary_size=args.vocab, seed=1, body_full=True, title_mean=6.63)
+        imp = synth.make_impressions(args.impressions, news.news_num, num_users=601215, seed=100 + rank)
+    else:
+        news = synth.make_news_table(args.news, vocabulary_size=args.vocab, seed=1)
+        imp = synth.make_impressions(args.impressions, news.news_num, seed=100 + rank)
     return cfg, news, imp
 
 
@@ -163,8 +177,9 @@ def run_reference(args):
 
 def workload_config(args, imp):
     C = np.diff(imp.cand_off)
-    return {"workload": "MIND-large-shaped eval (BASELINE.json configs[1]): %d-news fp32 vector cache, "
-                        "impression scoring + AUC/MRR/nDCG@5/10" % args.news,
+    name = ("Adressa-shaped eval (BASELINE.json configs[3]; full 128-token bodies)" if args.shape == "adressa"
+            else "MIND-large-shaped eval (BASELINE.json configs[1])")
+    return {"workload": "%s: %d-news fp32 vector cache, impression scoring + AUC/MRR/nDCG@5/10" % (name, args.news),
             "news": args.news, "impressions_per_step_per_gpu": imp.num_impressions,
             "pairs_per_step_per_gpu": int(imp.num_pairs), "history": H, "mean_candidates": float(C.mean()),
             "max_candidates": int(C.max()), "reference_batch_size": args.batch_size, "num_buckets": 10,
