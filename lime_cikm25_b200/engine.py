@@ -401,7 +401,7 @@ class ScoringEngine:
             cand16 = self.split_candidates(cand_rows)
             meta = self.news_meta(hist_rows, cand_rows)
         cache = self.cache_struct(hist_rows, cand_rows, cand16, meta)
-        self._keepalive = (cand16, meta)
+        self._keepalive = (cand16, meta)      # derived operands stay referenced until the next call (the launch is asynchronous)
         st = dimp.struct()
         if out is None:
             out = torch.empty(dimp.num_pairs, dtype=torch.float32, device=hist_rows.device)
