@@ -38,6 +38,7 @@
 // full/free mbarriers) -> epilogue TMEM -> lg / y / z -> pooling softmax + GraphSAGE mean + lifetime weight.
 #include "score_common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "tc05.cuh"
 
@@ -1054,6 +1055,9 @@ int launch_score_tc(const ScoreArgs &a, cudaStream_t st) {
     }
     LIME_CUDA(cudaMemsetAsync(a.work_counter, 0, 4 * sizeof(int32_t), st));   // work counter, fallback count, exact counter, stats
     int grid = 2 * num_sms();
+    if (const char *e = getenv("LIME_TC_ONE_CTA_PER_SM")) {      // experiment knob: concurrency vs shared resources
+        if (e[0] == '1') grid = num_sms();
+    }
     if (grid > a.imp.num_units) grid = a.imp.num_units;
     score_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
     LIME_LAUNCH_CHECK("score_tc_kernel");
