@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LIME_B200_ABI_VERSION 3
+#define LIME_B200_ABI_VERSION 4
 
 /* Compile-time model geometry of the LIME-CROWN-CROWN configuration (config.py:54-91 defaults). */
 #define LIME_D        400   /* lime_output_dim == news_embedding_dim == attention_dim          */
@@ -53,12 +53,12 @@ extern "C" {
 #define LIME_CAND_ABSMAX 1207 /* max |w1 w2 w3| of the row, written by lime_split_f16_pairs (fp16 operand range check) */
 #define LIME_META_LD 8      /* news_meta row: topic id | gw absmax | w absmax | B1 | B2 | B3 | cb | pad */
 #define LIME_CAND16_SCALE 1024.0f /* cand16 / ctab16 hold scale * w (keeps the lo halves out of the fp16 subnormals) */
-#define LIME_CAND16_LD 2400 /* fp16 elements per row of cand16 / ctab16: per folded vector k the 400 hi halves, then the 400 lo halves */
+#define LIME_CAND16_LD 2400 /* fp16 elements per row of cand16 / ctab16: [hi | lo][k = w1 w2 w3][400] -- an operand-row triple is 3 consecutive 800-byte rows */
 #define LIME_HTAB_LD   800  /* per (freshness bucket, lifetime bucket): [ T | gwT ]            */
 #define LIME_CTAB_LD   1208 /* per bucket pair: [ w1T | w2T | w3T | scalT(8) ]                 */
 /* Tensor-core scoring path (score_tc.cu): history rows per impression, candidates per work unit. */
-#define LIME_TC_MAX_HISTORY 52
-#define LIME_TC_TILE_C      42
+#define LIME_TC_MAX_HISTORY 56
+#define LIME_TC_TILE_C      34  /* + the unit's distinct (freshness, lifetime) bucket pairs <= 40 operand-row triples */
 #define LIME_TOPIC_TAB_LD   12  /* 10 head logits of a (candidate topic, history topic) pair, padded */
 #define LIME_TC_MAX_TOPICS  1024
 
@@ -201,11 +201,13 @@ typedef struct {
  * Two kernels implement the same arithmetic:
  *   - exact   (score.cu): every (candidate, history row) gate evaluated element by element; any H <= 224.
  *   - tensor  (score_tc.cu, H <= LIME_TC_MAX_HISTORY): history slots with the same (news, bucket pair, mask) are
- *     deduplicated; per unique row the gated vector is evaluated at 2 (or 4) Chebyshev nodes of the attention
- *     weight a over the unit's candidates, the 3 dots with every candidate are tcgen05 MMAs on fp16 hi/lo pairs
- *     (candidate side pre-split in cand16 / ctab16, fp32 accumulation in TMEM), and each pair interpolates in a.
- *     A unit whose a-spread makes the interpolation bound exceed the tolerance, or that holds an operand beyond
- *     the fp16 range, is re-scored by the exact kernel in the same call.
+ *     deduplicated; per unique row the gated vector and its derivative in the attention weight a are evaluated
+ *     once, at the centre of a's range over the unit's candidates (economised second-order expansion), the 3 dots
+ *     with every candidate are tcgen05 MMAs on fp16 hi/lo pairs (candidate side pre-split in cand16 / ctab16,
+ *     the unit's distinct bucket-pair rows as extra operand rows, fp32 accumulation in TMEM), and each pair
+ *     evaluates the expansion at its own a.  A unit whose a-spread makes the remainder bound exceed the
+ *     tolerance, that holds an operand beyond the fp16 range, or has more distinct bucket pairs than spare
+ *     operand rows, is re-scored by the exact kernel in the same call.
  * lime_score_configure(mode, tolerance): mode 0 = tensor path with exact fallback (default,
  * tolerance 1e-6 on the gate), 1 = exact only, 2 = tensor path with every unit forced through the
  * fallback (tests).  Process-wide. */
@@ -294,11 +296,13 @@ int lime_dropout(const float *x, int64_t ldx, float *y, int64_t ldy, int64_t row
 /* ---- training: CROWN user encoder + click score, N candidates per sample (userEncoders.py:101-175,
  * layers.py:52-93, util.py:23-49).  Dense layers are lime_linear / lime_gemm; these are the pieces between. */
 /* a[b, h] of CandidateAware_ClickedNewsAttention from Qp = query_proj(t_c) [B,N,400], Kp = key_proj(t_h)
- * [B,H,400], mask [B,H] (layers.py:66-81; attention dropout not applied) and its backward. */
+ * [B,H,400], mask [B,H] (layers.py:66-81) and its backward.  p_drop: dropout on the per-head attention weights
+ * (layers.py:36,74, nn.Dropout(0.2) in training; 0 in eval), stateless mask of (seed, sample, index) -- the backward
+ * call must pass the forward's p_drop and seed. */
 int lime_ca_attention_fwd(const float *Qp, const float *Kp, const uint8_t *mask, int32_t B, int32_t N, int32_t H,
-                          float *a, void *stream);
+                          float p_drop, uint64_t seed, float *a, void *stream);
 int lime_ca_attention_bwd(const float *Qp, const float *Kp, const uint8_t *mask, int32_t B, int32_t N, int32_t H,
-                          const float *da, float *dQp, float *dKp, void *stream);
+                          float p_drop, uint64_t seed, const float *da, float *dQp, float *dKp, void *stream);
 /* wc = a * v per row (layers.py:84) */
 int lime_row_scale_fwd(const float *v, const float *a, int64_t rows, int d, float *out, void *stream);
 int lime_row_scale_bwd(const float *v, const float *a, const float *dwc, int64_t rows, int d, float *dv, float *da,

@@ -237,20 +237,21 @@ class BucketPairs(torch.autograd.Function):
 
 # ---- user encoder + click score (csrc/train_user.cu) -------------------------------------------------
 class CAAttention(torch.autograd.Function):
-    """(Qp [B*N,400], Kp [B*H,400], mask uint8 [B,H]) -> a [B*H] (layers.py:66-81)."""
+    """(Qp [B*N,400], Kp [B*H,400], mask uint8 [B,H]) -> a [B*H] (layers.py:66-81); p_drop / seed: the dropout on
+    the per-head attention weights (layers.py:36,74), same stateless mask in forward and backward."""
 
     @staticmethod
-    def forward(ctx, Qp, Kp, mask, B, N, H):
-        ctx.dims = (B, N, H)
+    def forward(ctx, Qp, Kp, mask, B, N, H, p_drop=0.0, seed=0):
+        ctx.dims = (B, N, H, float(p_drop), int(seed))
         ctx.save_for_backward(Qp, Kp, mask)
-        return ops.ca_attention_fwd(Qp, Kp, mask, B, N, H)
+        return ops.ca_attention_fwd(Qp, Kp, mask, B, N, H, p_drop, seed)
 
     @staticmethod
     def backward(ctx, da):
         Qp, Kp, mask = ctx.saved_tensors
-        B, N, H = ctx.dims
-        dQ, dK = ops.ca_attention_bwd(Qp, Kp, mask, B, N, H, _c(da))
-        return dQ, dK, None, None, None, None
+        B, N, H, p_drop, seed = ctx.dims
+        dQ, dK = ops.ca_attention_bwd(Qp, Kp, mask, B, N, H, _c(da), p_drop, seed)
+        return dQ, dK, None, None, None, None, None, None
 
 
 class RowScale(torch.autograd.Function):

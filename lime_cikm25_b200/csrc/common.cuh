@@ -57,6 +57,20 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// Stateless counter-based generator of the training dropouts: (seed, element index) -> 32 random bits via two rounds of a
+// 64-bit mix; forward and backward evaluate the same mask.  drop_scale = keep / (1 - p).
+__device__ __forceinline__ uint32_t mix_bits(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (uint32_t)(z >> 32);
+}
+__device__ __forceinline__ float drop_scale(uint64_t seed, uint64_t idx, float p) {
+    const float u = (float)mix_bits(seed, idx) * (1.0f / 4294967296.0f);
+    return u >= p ? 1.0f / (1.0f - p) : 0.0f;
+}
+
 // FreshnessEncoder.bucketize (newsEncoders.py:53-58), bit-exact with the reference's fp32 op
 // sequence AS ATen EXECUTES IT ON CUDA (the reference asserts a GPU, config.py:212):
 // clamp(min=1) -> log -> "divide" by the CPU 0-dim tensor torch.log(torch.tensor(86400.)) =

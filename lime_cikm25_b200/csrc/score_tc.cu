@@ -1,41 +1,47 @@
-// Stage B on the tensor cores: impression scoring for H <= 56 history rows (sm_100a, tcgen05 + TMEM).
+// Stage B on the tensor cores: impression scoring for H <= 56 history rows (sm_100a, tcgen05 + TMEM).  Round 2.
 //
-// Same arithmetic as score.cu (see its header for the algebra and the reference lines), restructured so
-// that the 400-wide gate sigmoid is no longer evaluated per (candidate, history row):
+// Same arithmetic as score.cu (see its header for the algebra and the reference lines:
+// layers.py:52-93, userEncoders.py:121-171, util.py:23-49), restructured so that the 400-wide gate sigmoid is
+// evaluated ONCE per unique history row of a work unit instead of once per (candidate, history row):
 //
-//   o_h(a) = v_h * (1 - (1 - a) * sigmoid(a * W_g v_h + b_g))       depends on the candidate only through
-//                                                                     the scalar attention weight a = a[c][h].
-//   Over the <= 42 candidates of a work unit, a[.][h] spans an interval [mid_h - w_h, mid_h + w_h].  o_h is
-//   analytic in a, so it is evaluated EXACTLY at 2 (or 4) Chebyshev nodes a_j of that interval and every
-//   candidate interpolates:  o_h(a[c][h]) = sum_j L_j(t) o_h(a_j),  t = (a[c][h] - mid_h) / w_h.
-//   The reductions a pair needs are linear in o (dots with the candidate's 3 folded vectors, sum o) or are
-//   scalar functions of a (sum o^2), so they interpolate the same way:
-//       D_k[c][h] = sum_j L_j(t) * ( w_k[c][:] . O[nodes*h + j][:] ),   O = [o_h(a_j)],  k = 1..3
-//   and  W . O^T  (3C x 400) x (400 x nodes*H)  is ONE GEMM per work unit -> tcgen05.mma.
-//   Interpolation error of the gate:  2 nodes  w^2 (0.0962 g^2 + 0.5 |g|) / 4,   4 nodes
-//   w^4 (0.125 g^4 + 0.5 |g|^3) / 192,  g = max_d |W_g v_h|; a unit where even 4 nodes exceed the tolerance
-//   (default 1e-6, below the 2^-22 of the ex2.approx the exact kernel uses) is appended to a device-side
-//   list and re-scored by the exact kernel.  fp32 fidelity of the dots: both GEMM operands are fp16 hi + lo
-//   pairs (11 + 11 significant bits), D += Whi Ohi + Whi Olo + Wlo Ohi with fp32 accumulation in TMEM.
+//   o_h(a) = v_h * (1 - f(a)),  f(a) = (1 - a) * sigmoid(a * W_g v_h + b_g)     depends on the candidate only through
+//                                                                                 the scalar attention weight a = a[c][h].
+//   Over the candidates of a work unit a[.][h] spans [mid_h - w_h, mid_h + w_h].  o_h is analytic in a, so with
+//   t = (a[c][h] - mid_h) / w_h in [-1, 1]
+//       o_h(a) = c0_h + t * c1_h + R,      c0 = v (1 - f - (w^2/4) f''),   c1 = -w v f'      (all at a = mid_h)
+//   i.e. the second-order Taylor polynomial with t^2 replaced by its best constant 1/2 on [-1, 1] (Chebyshev
+//   economisation): |R| <= |v| (w^2 max|f''| / 4 + w^3 max|f'''| / 6), the error of 2-node Chebyshev interpolation,
+//   from ONE sigmoid per (row, dim).  |f''| <= 0.0962 g^2 + 0.5 |g|, |f'''| <= 0.125 |g|^3 + 0.2887 g^2,
+//   g = max_d |W_g v_h|.  A unit whose bound exceeds the tolerance (default 1e-6, below the 2^-22 of ex2.approx) is
+//   appended to a device-side list and re-scored by the exact kernel.
+//   Everything a pair needs is linear in o (dots with the candidate's 3 folded vectors, sum o) or quadratic
+//   (sum o^2 = sum c0^2 + 2 t sum c0 c1 + t^2 sum c1^2), so per unit the dots are ONE GEMM
+//       W [3 C x 400] . [c0 ; c1]^T        -> tcgen05.mma, fp32 accumulation in TMEM.
 //
-// What changed against the first tensor-core version (round 1c, 19.2 ms per bench step):
-//   * history rows are DEDUPLICATED per unit: slots with the same (news, bucket pair, mask) -- in practice
-//     the padding of a short history, dataset.py:123-128 -- are one operand row with a multiplicity that
-//     enters the two softmaxes, the pooling and the GraphSAGE mean.  H = 50 slots -> ~26 rows on average.
-//   * the candidate side is the M operand (TMEM lanes) and is NOT produced by compute threads any more: the
-//     cache holds every folded candidate vector already split into fp16 hi / lo (cand16, ctab16), a loader
-//     warp streams the rows with cp.async straight into the swizzled operand tile; the bucket-pair part
-//     is a second K range (K = 400 news + 400 table) instead of a register add + split.
-//   * the history side is the N operand: N = nodes * rows <= 112, so the MMA work follows the deduplicated
-//     row count; the epilogue thread owns a (candidate, k) lane and walks the columns -- the Lagrange
-//     combination is in-thread (no shuffles), lg / y / z lanes are warp-uniform.
-//   * candidate-aware attention: 8 lanes per candidate, head logits pre-scaled by log2(e), no max pass
-//     (the table's |logit| bound is checked by the host), multiplicity-weighted sums.
+// Precision (fp32 fidelity on fp16 tensor cores): W = Whi + Wlo and c0 = Ohi + Olo are fp16 pairs (11 + 11 bits);
+// the derivative operand c1 is |t w f'/(1 - f)| ~ 1e-3 of c0, so ONE fp16 product carries it (its rounding error,
+// 2^-12 relative to c1, is 2^-22 relative to the result).  Per K step of 16:
+//       D[:, 0 .. 3Up)    += Whi . [Ohi ; Olo ; O1hi]^T      (B operand = the three images stacked along N)
+//       D[:, 3Up .. 4Up)  += Wlo . [Ohi]^T
+//   = 2 MMAs instead of the 6 (3 split products x news / table halves of K) of round 1; the shared-memory operand
+//   bytes per K step drop from 36 KB to <= 12 KB, which was the round-1 bottleneck (tensor pipe operand reads).
 //
-// CTA = 8 compute warps + 1 MMA-issuer warp + 1 loader warp, persistent, TWO per SM (113 KB of shared
-// memory and 256 TMEM columns each).  Per unit: metadata + dedup -> attention a[c][u] -> nodes ->
-// 13 K-stages of 32 dims (the two 32-dim halves of the 64-dim SWIZZLE_128B tile are a 2-stage ring with
-// full/free mbarriers) -> epilogue TMEM -> lg / y / z -> pooling softmax + GraphSAGE mean + lifetime weight.
+// The bucket-pair (freshness, lifetime) part of a candidate vector, w(c) = w_news(c) + w_tab(bp_c), is no longer
+// a second K range: the DISTINCT bucket pairs of a unit (typically 4-6) are extra M rows of the same MMA
+// (rows = 3 x (candidates + distinct pairs) <= 120) and the epilogue adds row bp_c to row c through shared memory.
+//
+// What else changed against round 1:
+//   * the pooling softmax / GraphSAGE mean run inside the epilogue (online softmax per TMEM lane triple, shuffles
+//     between the 3 lanes of a candidate): the lg / y / z round trip through shared memory and its phase are gone;
+//   * operand production is a dynamic task list (8 rows x 32 dims per warp task, round-robin over 7 warps), so short
+//     (deduplicated) histories keep every warp busy; the candidate-operand copies (cp.async, 64 contiguous bytes
+//     per row per instruction) are tasks of the same list, two stages ahead, over a ring of four 32-dim slots;
+//   * history rows are read as fp32 [v | W_g v] straight from the cache (no per-node re-evaluation).
+//
+// CTA = 7 compute warps + 1 MMA-issuer / front-end warp, persistent, TWO per SM (<= 113 KB of shared memory and
+// 256 TMEM columns each).  Per unit: front end (metadata, dedup of history slots and of candidate bucket pairs;
+// issuer warp, one unit ahead) -> attention a[u][c] -> centres mid / w, t = (a - mid) / w -> 13 K stages of
+// 32 dims -> epilogue + pooling -> score.
 #include "score_common.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -46,51 +52,56 @@ namespace lime {
 namespace {
 
 constexpr int kD = LIME_D;
-constexpr int kCWarps = 7;                      // compute warps (8 warps per CTA -> 4 per SM sub-partition at two CTAs per SM: 128 registers, no spills)
+constexpr int kCWarps = 7;                      // compute warps (8 warps per CTA -> 4 per SM sub-partition at two CTAs per SM: 128 registers)
 constexpr int kCompute = kCWarps * 32;
-constexpr int kMmaWarp = kCWarps;               // warp 7 issues the MMAs
-constexpr int kRPT = kCompute / 8;              // operand rows produced per pass by one task slot (8 threads per row): 28
+constexpr int kMmaWarp = kCWarps;               // warp 7 issues the MMAs and runs the front end of the next unit
 constexpr int kThreads = kCompute + 32;
 constexpr int kH = LIME_TC_MAX_HISTORY;         // 56 history slots at most
-constexpr int kTile = LIME_TC_TILE_C;           // 42 candidates per unit -> 126 of the 128 M rows
-constexpr int kQ3 = kTile - 32;                 // candidates living in TMEM quadrant 3
-constexpr int kBRows = 112;                     // N rows of the O operand: nodes * unique rows of a pass
+constexpr int kTile = LIME_TC_TILE_C;           // candidates per unit handed out by the host
+constexpr int kTriples = 40;                    // M rows = 3 x (candidates + distinct bucket pairs): 10 triples per TMEM quadrant
+constexpr int kMaxBp = 10;                      // distinct bucket pairs of a unit that fit beside its candidates
+constexpr int kAS = kTriples;                   // row stride of a_s / t_s  ([u][c])
 constexpr int kStages = 13;                     // 32-wide K stages over D = 400 (the last holds 16 dims)
-constexpr int kAImg = 128 * 128;                // one 64-dim image of the candidate operand (hi or lo)
-constexpr int kBImg = kBRows * 128;
+constexpr int kWTile = 32768, kWImg = 16384;    // one 64-dim candidate tile = hi image + lo image of 128 rows x 128 B
+constexpr int kGroups = 7;                      // row groups of 8 unique history rows (56 / 8)
+constexpr int kCopyTasks = 3;                   // candidate-operand copy tasks per stage
 constexpr int kTabLd = LIME_TOPIC_TAB_LD;
-constexpr int kAS = kTile;                      // row stride of a_s / lg / y / z  ([u][c])
+constexpr int kTabStride = 32;                  // tab_s[u][3 * bp + k] (float2), 3 * kMaxBp <= 32
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
 // Both operands are scaled by a power of two before the fp16 hi / lo split, so that the lo halves of typical values
-// (|w| ~ 1e-2, |o| ~ 1e-1) stay in the normal fp16 range (>= 6.1e-5) instead of losing bits as subnormals; the
-// accumulators are un-scaled in the epilogue (exact: powers of two).
+// (|w| ~ 1e-2, |o| ~ 1e-1) stay in the normal fp16 range (>= 6.1e-5); the accumulators are un-scaled in the epilogue.
 constexpr float kWScale = LIME_CAND16_SCALE;    // cand16 / ctab16 hold w * 1024
 constexpr float kOScale = 256.0f;               // O operand holds o * 256
 constexpr float kUnscale = 1.0f / (kWScale * kOScale);
 constexpr float kS1Max = 1073741824.0f;         // sum (256 o)^2 <= 2^30  =>  every |256 o| <= 32768 (fp16 operand range)
 constexpr float kWAbsMax = 32768.0f / kWScale;  // |w| beyond this leaves the fp16 operand range -> exact kernel
-constexpr int kC16 = LIME_CAND16_LD;            // fp16 elements per cand16 / ctab16 row: [k][hi | lo][400]
+constexpr int kC16 = LIME_CAND16_LD;            // fp16 elements per cand16 / ctab16 row: [hi | lo][k][400]
 
 // shared-memory map (bytes from the 1024-aligned base)
-constexpr int OFF_A = 0;                                      // 4 images: news hi, news lo, table hi, table lo
-constexpr int OFF_BHI = 4 * kAImg, OFF_BLO = OFF_BHI + kBImg;
-constexpr int OFF_OUT = OFF_BHI;                              // alias (after the MMAs): lg / y / z [52][42]
-constexpr int OFF_AS = OFF_BLO + kBImg;                       // a[u][c]
-constexpr int OFF_S01 = OFF_AS + kH * kAS * 4;                // node sums [52][8]
-constexpr int OFF_MID = OFF_S01 + kH * 8 * 4;
+constexpr int OFF_W = 0;                                      // 2 tiles x (hi, lo) x 128 rows x 128 B: four 32-dim ring slots
+constexpr int OFF_O = 2 * kWTile;                             // [Ohi ; Olo ; O1hi] x Up rows x 128 B (two 32-dim half slots)
+constexpr int kOBytes = 3 * 64 * 128;
+constexpr int OFF_TAB = OFF_O;                                // alias (after the MMAs): table-row results [u][32] float2
+constexpr int OFF_T = OFF_O + kOBytes;                        // a[u][c], then t[u][c]
+constexpr int OFF_SUM = OFF_T + kH * kAS * 4;                 // [stage parity][u][8]: sum c0, c1, c0^2, c0 c1, c1^2
+constexpr int OFF_MID = OFF_SUM + 2 * kH * 8 * 4;
 constexpr int OFF_WINV = OFF_MID + kH * 4;
 constexpr int OFF_WHALF = OFF_WINV + kH * 4;
-constexpr int OFF_POOL = OFF_WHALF + kH * 4;                  // [42][4]  running m, l, acc, ms
-// Per-unit arrays written by the front end (unit metadata + dedup): DOUBLE BUFFERED, the MMA-issuer warp prepares unit
-// i + 1 while the compute warps are in the epilogue / pooling of unit i
-constexpr int kCArr = 48 * 4, kUArr = kH * 4;
-constexpr int UB_CSCAL = 0;                                   // [42][4]  B1 B2 B3 cb
-constexpr int UB_CW = UB_CSCAL + kTile * 16;
+constexpr int OFF_PART = OFF_WHALF + kH * 4;                  // [2][40][4] partial pooling state of the two warps of a quadrant
+constexpr int OFF_POOL = OFF_PART;                            // alias: [40][4]  merged m, l, acc, ms of the unit (P > H path)
+// Per-unit arrays written by the front end: DOUBLE BUFFERED, the issuer warp prepares unit i + 1 while the compute
+// warps work on unit i
+constexpr int kCArr = kTriples * 4, kUArr = kH * 4;
+constexpr int UB_CSCAL = 0;                                   // [40][4]  B1 B2 B3 cb
+constexpr int UB_CW = UB_CSCAL + kTriples * 16;
 constexpr int UB_CNEWS = UB_CW + kCArr;
-constexpr int UB_CTAB = UB_CNEWS + kCArr;
-constexpr int UB_CP = UB_CTAB + kCArr;
+constexpr int UB_CTAB = UB_CNEWS + kCArr;                     // bucket-pair id of the candidate
+constexpr int UB_CBIDX = UB_CTAB + kCArr;                     // ... and its index among the unit's distinct pairs
+constexpr int UB_CP = UB_CBIDX + kCArr;
 constexpr int UB_CTOPIC = UB_CP + kCArr;
-constexpr int UB_UNEWS = UB_CTOPIC + kCArr;
+constexpr int UB_BTAB = UB_CTOPIC + kCArr;                    // [12] distinct bucket pairs
+constexpr int UB_UNEWS = UB_BTAB + 48;
 constexpr int UB_UTAB = UB_UNEWS + kUArr;
 constexpr int UB_UMASK = UB_UTAB + kUArr;
 constexpr int UB_UTOPIC = UB_UMASK + kUArr;
@@ -98,38 +109,33 @@ constexpr int UB_UMULT = UB_UTOPIC + kUArr;                   // float multiplic
 constexpr int UB_UMP0 = UB_UMULT + kUArr;                     // float multiplicity inside the GraphSAGE prefix (main)
 constexpr int UB_UMP1 = UB_UMP0 + kUArr;                      // ... (tail batch)
 constexpr int UB_UGABS = UB_UMP1 + kUArr;
-constexpr int UB_INFO = UB_UGABS + kUArr;                     // ints: unit, impression, first pair, count, U, unmasked slots, flags
+constexpr int UB_WROW = UB_UGABS + kUArr;                     // [120] uint2: source element offset, destination byte offset of an operand row
+constexpr int UB_INFO = UB_WROW + 3 * kTriples * 8;           // ints: unit, impression, first pair, count, U, unmasked slots, flags, bucket pairs
 constexpr int kUnitBuf = UB_INFO + 32;
-constexpr int OFF_UB = OFF_POOL + kTile * 16;
+constexpr int OFF_UB = OFF_PART + 2 * kTriples * 16;
 // front-end scratch (one warp): keys, topic ids, gate bounds of the H history slots
 constexpr int OFF_HKN = OFF_UB + 2 * kUnitBuf, OFF_HKT = OFF_HKN + kUArr, OFF_HTP = OFF_HKT + kUArr, OFF_HGA = OFF_HTP + kUArr;
-constexpr int OFF_BARS = OFF_HGA + kUArr;                     // full[2] free[2] accum
-constexpr int OFF_MISC = OFF_BARS + 64;                       // tmem slot, nodes, passes, N
+constexpr int OFF_BARS = OFF_HGA + kUArr;                     // wfull[4] wfree[4] ofull[2] ofree[2] accum
+constexpr int OFF_MISC = OFF_BARS + 128;                      // tmem slot
 constexpr int OFF_PROF = OFF_MISC + 64;                       // phase clocks of thread 0 (diagnostic)
 constexpr int kSmemBytes = OFF_PROF + 128 + 1024;
-static_assert(3 * kH * kAS * 4 <= 2 * kBImg, "epilogue alias overflows the O operand images");
+static_assert(kH * kTabStride * 8 <= kOBytes, "table-row alias overflows the O operand tile");
 static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
-static_assert(3 * kTile <= 128 && kTile <= 48 && kTile >= 32, "candidate rows: 32 per k in TMEM quadrants 0-2, the rest in quadrant 3");
-static_assert(3 * kQ3 <= 32, "quadrant 3 holds (tile - 32) candidates x 3");
-static_assert(OFF_BARS % 8 == 0 && OFF_AS % 16 == 0 && OFF_S01 % 16 == 0 && OFF_UB % 16 == 0 && kUnitBuf % 16 == 0 &&
-              OFF_BHI % 1024 == 0 && OFF_BLO % 1024 == 0, "alignment");
-static_assert(2 * kH <= kBRows && kBRows % 16 == 0 && kBRows <= 128 && kH % 4 == 0 && kH <= 64 && 4 * kH <= 2 * kBRows, "N operand");
-static_assert(kH <= 2 * kRPT && kH <= kCompute / 4 && kBRows / 4 <= kRPT, "row mappings of the compute threads");
+static_assert(kTile + 1 <= kTriples && 3 * kMaxBp <= kTabStride, "unit capacity");
+static_assert(OFF_BARS % 8 == 0 && OFF_T % 16 == 0 && OFF_SUM % 16 == 0 && OFF_UB % 16 == 0 && kUnitBuf % 16 == 0 &&
+              OFF_O % 1024 == 0 && UB_WROW % 8 == 0 && OFF_PART % 16 == 0, "alignment");
+static_assert(kH <= 8 * kGroups && kH % 8 == 0 && kH <= 64, "row groups");
 
-// misc ints
-enum { M_TMEM = 0, M_NODES = 2, M_NPASS = 3, M_NPAD = 4 };
+enum { M_TMEM = 0 };
 // unit info ints
-enum { UI_UNIT = 0, UI_IMP = 1, UI_PAIR0 = 2, UI_CNT = 3, UI_U = 4, UI_NUN = 5, UI_FLAGS = 6 };
-
-// Chebyshev nodes on [-1, 1]: 4-node and 2-node sets
-constexpr float kX0 = -0.92387953251128674f, kX1 = -0.38268343236508977f;
-constexpr float kX2 = 0.38268343236508977f, kX3 = 0.92387953251128674f;
-constexpr float kY0 = -0.70710678118654752f, kY1 = 0.70710678118654752f;
+enum { UI_UNIT = 0, UI_IMP = 1, UI_PAIR0 = 2, UI_CNT = 3, UI_U = 4, UI_NUN = 5, UI_FLAGS = 6, UI_NBP = 7 };
+// barrier indices (uint64 each)
+enum { B_WFULL = 0, B_WFREE = 4, B_OFULL = 8, B_OFREE = 10, B_ACCUM = 12 };
 
 // Phase timing (diagnostic): thread 0 of every CTA accumulates clock64() deltas per phase; lime_score_phase_clocks reads
-// and clears the totals.  Slots: 0 metadata, 1 dedup, 2 attention, 3 nodes, 4 operand production (incl. ring waits),
-// 5 wait for the last MMA, 6 epilogue, 7 pooling, 8 final score, 9 units, 10 barrier at the end of production.
-// Compiled in only with -DLIME_TC_PHASE_CLOCKS (make PHASE_CLOCKS=1): the extra live registers cost spills.
+// and clears the totals.  Slots: 2 attention, 3 centres, 4 operand production (incl. ring waits), 5 wait for the last
+// MMA, 6 epilogue + pooling, 7 merge + score, 8 tail, 9 units.
+// Compiled in only with -DLIME_TC_PHASE_CLOCKS (make PHASE_CLOCKS=1).
 __device__ unsigned long long g_phase_clocks[16];
 #ifdef LIME_TC_PHASE_CLOCKS
 #define LIME_TICK(slot)                                                  \
@@ -144,21 +150,7 @@ __device__ unsigned long long g_phase_clocks[16];
 #define LIME_TICK(slot) do { } while (0)
 #endif
 
-template <int NODES> __device__ __forceinline__ float node_x(int j) {
-    if (NODES == 2) return j == 0 ? kY0 : kY1;
-    return j == 0 ? kX0 : j == 1 ? kX1 : j == 2 ? kX2 : kX3;
-}
-
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
-__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
-#if defined(LIME_TC_NO_ROW_PREFETCH)
-    (void)p; (void)bytes;
-#elif defined(LIME_TC_LINE_PREFETCH)
-    for (uint32_t o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(p) + o));
-#else
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-#endif
-}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -166,265 +158,160 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(n) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(kCompute) : "memory"); }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
 
-// (candidate, folded vector k) of M row 32 * quadrant + lane (= TMEM lane): k = 0..2 fill quadrants 0..2 for
-// c < 32, the remaining candidates share quadrant 3; c = kTile marks an unused row
-__device__ __forceinline__ void m_row_owner(int quadrant, int lane, int &c, int &k) {
-    if (quadrant < 3) {
-        c = lane;
-        k = quadrant;
-    } else {
-        k = lane / kQ3;
-        c = 32 + lane - k * kQ3;
-        if (k > 2) {
-            k = 2;
-            c = kTile;
+// M row (= TMEM lane) of operand row k of triple j: 10 triples per quadrant (lanes 30, 31 of a quadrant stay unused),
+// so the 3 rows of a candidate live in one warp of the epilogue
+__device__ __forceinline__ int m_row(int j, int k) { return 32 * (j / 10) + 3 * (j % 10) + k; }
+
+// uses of a ring slot per pass: W slot s (stage kc & 3), O half h (stage kc & 1)
+__device__ __forceinline__ uint32_t w_uses(int s) { return s == 0 ? 4u : 3u; }
+__device__ __forceinline__ uint32_t o_uses(int h) { return h == 0 ? 7u : 6u; }
+
+// pack 2 fp32 -> fp16x2 (round to nearest), returns also the rounded values as fp32
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+// ---- candidate operand (M side): one copy task = every kCopyTasks-th instruction slot of stage kc -------------------
+// A slot is 8 operand rows x 64 contiguous bytes (lane = (row in slot, 16-byte chunk)); rows come from the unit's
+// row table (candidate rows of cand16, bucket-pair rows of ctab16).  cp.async.mbarrier.arrive.noinc publishes the
+// stage when this thread's copies have landed (no thread waits for the data).
+__device__ __forceinline__ void copy_task(unsigned char *base, const __half *cand16, const __half *ctab16,
+                                          const uint2 *wrow, int n3, int kc, int sub, int lane) {
+    const int c4 = lane & 3, rs = lane >> 2;
+    if (kc < kStages - 1 || c4 < (kD - 32 * (kStages - 1)) / 8) {
+        const uint32_t wbase = tc::smem_u32(base) + OFF_W + (uint32_t)((kc >> 1) & 1) * kWTile;
+        const int chunk = 4 * (kc & 1) + c4;
+        const int eo = 32 * kc + 8 * c4;
+        const int nslots = (2 * n3 + 7) >> 3;
+        for (int slot = sub; slot < nslots; slot += kCopyTasks) {
+            const int ri = 8 * slot + rs;
+            if (ri < 2 * n3) {
+                const int hl = ri >= n3 ? 1 : 0;
+                const uint2 rw = wrow[ri - hl * n3];
+                const __half *src = ((rw.x & 0x80000000u) ? ctab16 : cand16) + (size_t)(rw.x & 0x7fffffffu) + hl * (3 * kD) + eo;
+                const uint32_t dst = wbase + (uint32_t)hl * kWImg + rw.y + (uint32_t)((chunk ^ ((rw.y >> 7) & 7)) << 4);
+                cp_async16(dst, src);
+            }
         }
     }
 }
-
-// 4 fp32 -> 4 fp16 hi + 4 fp16 lo (x = hi + lo to 2^-22: 11 + 11 significant bits)
-__device__ __forceinline__ void split4(const float (&x)[4], uint2 &hi, uint2 &lo) {
-    const __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
-    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-    const __half2 l0 = __floats2half2_rn(x[0] - f0.x, x[1] - f0.y), l1 = __floats2half2_rn(x[2] - f1.x, x[3] - f1.y);
-    hi = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-    lo = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+// Ring protocol (both rings): EVERY compute warp waits for and arrives on every stage's barriers, whether or not it
+// holds a task of the stage -- an mbarrier parity wait is only meaningful for a waiter that has observed every earlier
+// phase (a warp that skipped stages could be two phases behind and alias the parity), and a phase cannot run ahead of
+// a warp whose arrival it needs.
+__device__ __forceinline__ void w_slot_wait(uint64_t *bars, int kc, uint32_t pass_iter) {
+    const int s = kc & 3;
+    const uint32_t fill = pass_iter * w_uses(s) + (uint32_t)(kc >> 2);
+    if (fill >= 1) tc::mbar_wait(bars + B_WFREE + s, (fill - 1) & 1u, 100 + kc);
+}
+__device__ __forceinline__ void o_slot_wait(uint64_t *bars, int kc, uint32_t pass_iter) {
+    const int h = kc & 1;
+    const uint32_t fill = pass_iter * o_uses(h) + (uint32_t)(kc >> 1);
+    if (fill >= 1) tc::mbar_wait(bars + B_OFREE + h, (fill - 1) & 1u, 200 + kc);
 }
 
-// Candidate operand (M side) of a unit: warp w streams the row groups w, w + 7, w + 14 of every stage with cp.async --
-// lane = (row in group, 16-byte chunk), one instruction moves the 64 contiguous bytes of a stage for 8 operand rows.
-// cp.async.mbarrier.arrive.noinc publishes a stage when this thread's copies have landed (no thread waits for the data).
-struct ACopy {
-    uint32_t on[3], ot[3];       // element offsets of this thread's 3 operand rows inside cand16 / ctab16 (0xffffffff: unused)
-    uint32_t dst;
-    int rsub, ch;
-    __device__ __forceinline__ void init(unsigned char *base, int tid, const int *cnews, const int *ctab, int cnt) {
-        rsub = (tid >> 2) & 7;
-        ch = tid & 3;
-        const int g0 = tid >> 5;
+// ---- history operand (N side): one production task = 8 unique rows x 32 dims of stage kc ------------------------------
+// lane = (row in group r = lane & 7, 8-dim chunk c4 = lane >> 3): a quarter warp writes 8 different rows of the same
+// chunk column, which the 128-byte swizzle spreads over all banks (conflict-free 16-byte stores).
+__device__ __forceinline__ void produce_task(unsigned char *base, const LimeNewsCache &C, int kc, int g, int nrows, int Up,
+                                             int lane, const int *unews, const int *utab, const float *mid_s,
+                                             const float *whalf_s, float *sum_s, uint64_t *bars, uint32_t pass_iter) {
+    const int r = lane & 7, c4 = lane >> 3;
+    const int h = kc & 1;
+    const int u = 8 * g + r;
+    const int d0 = 32 * kc + 8 * c4;
+    const bool ok = u < nrows && d0 < kD;
+    float c0[8], c1[8];
+    float ps[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ok) {
+        const float *hrow = C.hist_rows + (size_t)unews[u] * LIME_HIST_LD;
+        const float *trow = C.hist_tab + (size_t)utab[u] * LIME_HTAB_LD;
+        float4 vn[2], vt[2], gn[2], gt[2], bb[2];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int g = g0 + kCWarps * i;
-            int c = kTile, k = 0;
-            if (g < 16) m_row_owner(g >> 2, 8 * (g & 3) + rsub, c, k);
-            const bool rok = c < cnt;
-            const int cc = rok ? c : 0;
-            on[i] = rok ? (uint32_t)cnews[cc] * (uint32_t)kC16 + (uint32_t)(k * 2 * kD) : 0xffffffffu;
-            ot[i] = (uint32_t)ctab[cc] * (uint32_t)kC16 + (uint32_t)(k * 2 * kD);
+        for (int i = 0; i < 2; ++i) {
+            vn[i] = ldg4(hrow + LIME_HIST_VC + d0 + 4 * i);
+            gn[i] = ldg4(hrow + LIME_HIST_GW + d0 + 4 * i);
+            vt[i] = ldg4(trow + d0 + 4 * i);
+            gt[i] = ldg4(trow + kD + d0 + 4 * i);
+            bb[i] = ldg4(C.gate_bias + d0 + 4 * i);
         }
-        dst = tc::smem_u32(base) + OFF_A + (uint32_t)g0 * 1024u + (uint32_t)rsub * 128u;
-    }
-    // stage kc -> ring slot kc & 1 (waits until the MMAs of the slot's previous use have drained it)
-    __device__ __forceinline__ void issue(int kc, const __half *cand16, const __half *ctab16, uint64_t *bar_full,
-                                          uint64_t *bar_free, uint32_t &use0, uint32_t &use1) const {
-        const int s = kc & 1;
-        const uint32_t uses = s ? use1 : use0;
-        if (uses >= 1) tc::mbar_wait(bar_free + s, (uses - 1) & 1u);
-        if (kc < kStages - 1 || ch < (kD - 32 * (kStages - 1)) / 8) {
-            const uint32_t d = dst + (uint32_t)(((4 * s + ch) ^ rsub) << 4);
-            const int eo = 32 * kc + 8 * ch;
+        const float a = mid_s[u], w = whalf_s[u];
+        const float om = 1.0f - a;
+        const float oml = -om * kLn2;                  // d/da of the gate argument in natural units: g = -ln2 * g'
+        const float nwv = -kOScale * w;                // c1 = -256 w v f'
+        const float nso = -kOScale * om;               // 256 (1 - om s)
+        const float kq = kOScale * 0.25f * w * w * kLn2;   // + 256 (w^2/4) ln2 r' n  ( = -256 (w^2/4) f'' )
+        const float vv[8] = {vn[0].x + vt[0].x, vn[0].y + vt[0].y, vn[0].z + vt[0].z, vn[0].w + vt[0].w,
+                             vn[1].x + vt[1].x, vn[1].y + vt[1].y, vn[1].z + vt[1].z, vn[1].w + vt[1].w};
+        const float gg[8] = {gn[0].x + gt[0].x, gn[0].y + gt[0].y, gn[0].z + gt[0].z, gn[0].w + gt[0].w,
+                             gn[1].x + gt[1].x, gn[1].y + gt[1].y, gn[1].z + gt[1].z, gn[1].w + gt[1].w};
+        const float bs[8] = {bb[0].x, bb[0].y, bb[0].z, bb[0].w, bb[1].x, bb[1].y, bb[1].z, bb[1].w};
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                if (on[i] != 0xffffffffu) {
-                    const uint32_t di = d + (uint32_t)(kCWarps * i) * 1024u;
-                    cp_async16(di, cand16 + on[i] + eo);
-                    cp_async16(di + kAImg, cand16 + on[i] + kD + eo);
-                    cp_async16(di + 2 * kAImg, ctab16 + ot[i] + eo);
-                    cp_async16(di + 3 * kAImg, ctab16 + ot[i] + kD + eo);
-                }
-            }
-        }
-        cp_async_mbar_arrive_noinc(bar_full + s);
-        if (s) ++use1; else ++use0;
-    }
-};
-
-// Operand production of one pass: NODES rows of O per unique history row u0 <= u < u0 + nrows (fp16 hi / lo
-// images, K stages of 32 dims through the two halves of the 64-dim tile) and the node sums (sum o, sum o^2).
-// Executed by the 256 compute threads; a thread owns 4 dims of a row per stage (8 threads per row) and, when
-// the pass holds more than 28 rows, the same dims of row + 28.  use0/use1 count the uses of the two ring
-// halves over the kernel's lifetime (mbarrier phases).
-template <int NODES, int TPT>
-__device__ __forceinline__ void produce_operands(unsigned char *base, const LimeNewsCache &C, int u0, int nrows, int tid,
-                                                 const int *unews, const int *utab, const float *mid_s,
-                                                 const float *whalf_s, float *s01_s, int *flag_s, const int *cnews,
-                                                 const int *ctab, int cnt, const __half *cand16, const __half *ctab16,
-                                                 uint64_t *bar_full, uint64_t *bar_free, uint32_t &use0, uint32_t &use1,
-                                                 int pre_issued) {
-    const int sub = tid & 7;
-    ACopy ac;
-    ac.init(base, tid, cnews, ctab, cnt);
-    for (int kc = pre_issued; kc < 1; ++kc) ac.issue(kc, cand16, ctab16, bar_full, bar_free, use0, use1);
-    bool ok[TPT];
-    const float *hrow[TPT], *trow[TPT];
-    float aj[TPT][NODES], ps[TPT][2 * NODES];
-#pragma unroll
-    for (int t = 0; t < TPT; ++t) {
-        const int ul = (tid >> 3) + kRPT * t;
-        ok[t] = ul < nrows;
-        const int u = u0 + (ok[t] ? ul : 0);
-        const float mid = mid_s[u], wh = whalf_s[u];
-#pragma unroll
-        for (int j = 0; j < NODES; ++j) aj[t][j] = fmaf(wh, node_x<NODES>(j), mid);
-        hrow[t] = C.hist_rows + (size_t)unews[u] * LIME_HIST_LD;
-        trow[t] = C.hist_tab + (size_t)utab[u] * LIME_HTAB_LD;
-#pragma unroll
-        for (int i = 0; i < 2 * NODES; ++i) ps[t][i] = 0.0f;
-    }
-    // the first row of a thread: stage kc + 1's global loads are in flight while stage kc is evaluated; the second row
-    // (passes with more than 28 rows): loaded at the start of its stage, consumed after the first row's arithmetic
-    float4 nx[4], nx1[4];
-    float4 nbias = ldg4(C.gate_bias + 4 * sub);      // gate bias' of the next stage's 4 dims (prefetched like the rows)
-    nx[0] = ldg4(hrow[0] + LIME_HIST_VC + 4 * sub);
-    nx[1] = ldg4(trow[0] + 4 * sub);
-    nx[2] = ldg4(hrow[0] + LIME_HIST_GW + 4 * sub);
-    nx[3] = ldg4(trow[0] + kD + 4 * sub);
-    for (int kc = 0; kc < kStages; ++kc) {
-        const int s = kc & 1;
-        const int d0 = 32 * kc + 4 * sub;
-        float v[4], gg[4];
-        v[0] = (nx[0].x + nx[1].x) * kOScale; v[1] = (nx[0].y + nx[1].y) * kOScale;
-        v[2] = (nx[0].z + nx[1].z) * kOScale; v[3] = (nx[0].w + nx[1].w) * kOScale;
-        gg[0] = nx[2].x + nx[3].x; gg[1] = nx[2].y + nx[3].y;
-        gg[2] = nx[2].z + nx[3].z; gg[3] = nx[2].w + nx[3].w;
-        const float4 bias_now = nbias;
-        if (TPT == 2 && d0 < kD) {
-            nx1[0] = ldg4(hrow[TPT - 1] + LIME_HIST_VC + d0);
-            nx1[1] = ldg4(trow[TPT - 1] + d0);
-            nx1[2] = ldg4(hrow[TPT - 1] + LIME_HIST_GW + d0);
-            nx1[3] = ldg4(trow[TPT - 1] + kD + d0);
-        }
-        if (d0 + 32 < kD) {
-            nbias = ldg4(C.gate_bias + d0 + 32);
-            nx[0] = ldg4(hrow[0] + LIME_HIST_VC + d0 + 32);
-            nx[1] = ldg4(trow[0] + d0 + 32);
-            nx[2] = ldg4(hrow[0] + LIME_HIST_GW + d0 + 32);
-            nx[3] = ldg4(trow[0] + kD + d0 + 32);
-        }
-        if (d0 < kD) {      // the slot is free: this thread waited for it when it issued the stage's copies
-            const float bb[4] = {bias_now.x, bias_now.y, bias_now.z, bias_now.w};
-#pragma unroll
-            for (int t = 0; t < TPT; ++t) {
-                if (t == 1) {
-                    v[0] = (nx1[0].x + nx1[1].x) * kOScale; v[1] = (nx1[0].y + nx1[1].y) * kOScale;
-                    v[2] = (nx1[0].z + nx1[1].z) * kOScale; v[3] = (nx1[0].w + nx1[1].w) * kOScale;
-                    gg[0] = nx1[2].x + nx1[3].x; gg[1] = nx1[2].y + nx1[3].y;
-                    gg[2] = nx1[2].z + nx1[3].z; gg[3] = nx1[2].w + nx1[3].w;
-                }
-                if (ok[t]) {
-                    const int nrow0 = NODES * ((tid >> 3) + kRPT * t);
-#pragma unroll
-                    for (int j = 0; j < NODES; ++j) {
-                        // o = v (1 - (1 - a_j) sigmoid(a_j W_g v + b_g)),  sigmoid(z) = 1 / (1 + 2^z'),  z' = -log2(e) z
-                        const float a = aj[t][j], oma = 1.0f - a;
-                        float o[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float den = ex2_approx(fmaf(a, gg[e], bb[e])) + 1.0f;
-                            o[e] = fmaf(-(v[e] * oma), rcp_approx(den), v[e]);
-                            ps[t][2 * j] += o[e];
-                            ps[t][2 * j + 1] = fmaf(o[e], o[e], ps[t][2 * j + 1]);
-                        }
-                        uint2 hi, lo;
-                        split4(o, hi, lo);
-                        const uint32_t off = tc::sw128_offset(nrow0 + j, 4 * s + (sub >> 1)) + 8u * (sub & 1);
-                        *reinterpret_cast<uint2 *>(base + OFF_BHI + off) = hi;
-                        *reinterpret_cast<uint2 *>(base + OFF_BLO + off) = lo;
-                    }
-                }
-            }
-        }
-        tc::fence_proxy_async_smem();
-        tc::mbar_arrive(bar_full + s);
-        if (kc + 1 < kStages && kc + 1 >= pre_issued) ac.issue(kc + 1, cand16, ctab16, bar_full, bar_free, use0, use1);
-    }
-    // node sums of the row: sum o, sum o^2 per node, over the 8 lanes that share the row
-#pragma unroll
-    for (int t = 0; t < TPT; ++t) {
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-#pragma unroll
-            for (int i = 0; i < 2 * NODES; ++i) ps[t][i] += __shfl_xor_sync(0xffffffffu, ps[t][i], o);
-        }
-        if (ok[t] && sub == 0) {
-            const int u = u0 + (tid >> 3) + kRPT * t;
-            bool in_range = true;
-#pragma unroll
-            for (int j = 0; j < NODES; ++j) {
-                s01_s[u * 8 + 2 * j] = ps[t][2 * j] * (1.0f / kOScale);
-                s01_s[u * 8 + 2 * j + 1] = ps[t][2 * j + 1] * (1.0f / (kOScale * kOScale));
-                in_range = in_range && (ps[t][2 * j + 1] <= kS1Max);
-            }
-            if (!in_range) atomicOr(flag_s, 4);   // outside the fp16 operand range (or NaN): exact kernel
+        for (int e = 0; e < 8; ++e) {
+            // s = sigmoid(x) = 1 / (1 + 2^z'),  z' = a g' + b'  (g', b' pre-scaled by -log2 e);  with g = -ln2 g':
+            //   f = om s,  f' = -s + om g s (1 - s),  f'' = g s (1 - s) (om g (1 - 2 s) - 2)
+            const float s = rcp_approx(ex2_approx(fmaf(a, gg[e], bs[e])) + 1.0f);
+            const float rp = fmaf(-s, s, s) * gg[e];               // s (1 - s) g'
+            const float f1 = fmaf(oml, rp, -s);                    // f'
+            const float n2 = fmaf(oml * gg[e], fmaf(-2.0f, s, 1.0f), -2.0f);
+            const float tm = fmaf(kq, rp * n2, fmaf(nso, s, kOScale));
+            c0[e] = vv[e] * tm;
+            c1[e] = (vv[e] * nwv) * f1;
+            ps[0] += c0[e];
+            ps[1] += c1[e];
+            ps[2] = fmaf(c0[e], c0[e], ps[2]);
+            ps[3] = fmaf(c0[e], c1[e], ps[3]);
+            ps[4] = fmaf(c1[e], c1[e], ps[4]);
         }
     }
-}
-
-// Epilogue of one pass: a compute thread owns one accumulator row (TMEM lane) = one (candidate, k) and walks
-// the columns (unique history row, node) of the pass; warps w and w + 4 share a TMEM quadrant and alternate
-// over the 16-column blocks (quadrant 3, the candidates beyond 32, has warp 3 alone).  Writes out[k][u][c]  (k = 0: pooling logit, 1: pooled value, 2: GraphSAGE term).
-template <int NODES>
-__device__ __forceinline__ void epilogue(uint32_t tmem, int warp, int lane, int u0, int nrows, int cnt, float ln_eps,
-                                         const float *a_s, const float *mid_s, const float *winv_s, const float *s01_s,
-                                         const float *cscal, float *out_s) {
-    constexpr int UPB = 16 / NODES;               // unique rows per 16-column block
-    const int qd = warp & 3;
-    int c, k;
-    m_row_owner(qd, lane, c, k);
-    const bool valid = c < cnt;
-    const int cc = valid ? c : 0;
-    const float bk = cscal[cc * 4 + k];
-    float *outk = out_s + k * (kH * kAS);
-    const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16);
-    const int nblocks = (NODES * nrows + 15) >> 4;
-    const int bstep = qd + 4 < kCWarps ? 2 : 1;      // quadrants whose partner warp w + 4 is the MMA issuer are walked by one warp
-    for (int b = bstep == 2 ? warp >> 2 : 0; b < nblocks; b += bstep) {
-      {
-        // the two accumulators of the block (news part, table part): both loads are issued before the single wait
-        uint32_t rn[16], rt[16];
-        tc::tmem_ld16_nowait(taddr + 16 * b, rn);
-        tc::tmem_ld16_nowait(taddr + 128 + 16 * b, rt);
-        tc::tmem_ld_wait();
-        float v[16];
+    o_slot_wait(bars, kc, pass_iter);      // the slot is free once the MMAs of its previous use have drained it
+    if (ok) {
+        uint4 hi, lo, d1;
+        split2(c0[0], c0[1], hi.x, lo.x);
+        split2(c0[2], c0[3], hi.y, lo.y);
+        split2(c0[4], c0[5], hi.z, lo.z);
+        split2(c0[6], c0[7], hi.w, lo.w);
+        d1.x = pack_h2(c1[0], c1[1]);
+        d1.y = pack_h2(c1[2], c1[3]);
+        d1.z = pack_h2(c1[4], c1[5]);
+        d1.w = pack_h2(c1[6], c1[7]);
+        unsigned char *ob = base + OFF_O + tc::sw128_offset(u, 4 * h + c4);     // Up is a multiple of 8: same swizzle phase in the 3 images
+        *reinterpret_cast<uint4 *>(ob) = hi;
+        *reinterpret_cast<uint4 *>(ob + (size_t)Up * 128) = lo;
+        *reinterpret_cast<uint4 *>(ob + (size_t)Up * 256) = d1;
+    }
+    // Row sums over the 4 chunk lanes of a row, then added to the row's accumulator of this stage parity.  No atomics
+    // (bit-reproducible results): a row belongs to one task per stage, and the tasks of stages kc - 2 and kc are ordered
+    // by the ring (this task has just observed the completion of stage kc - 2's MMAs, which follow its arrivals).
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rn[i]) + __uint_as_float(rt[i]);
-#pragma unroll
-        for (int i = 0; i < UPB; ++i) {
-            const int ul = UPB * b + i;
-            if (ul < nrows) {
-                const int u = u0 + ul;
-                float t = (a_s[u * kAS + cc] - mid_s[u]) * winv_s[u];
-                t = fminf(fmaxf(t, -1.0f), 1.0f);
-                float p, s0, s1;
-                if (NODES == 2) {
-                    const float4 ss = *reinterpret_cast<const float4 *>(s01_s + u * 8);
-                    const float l1 = fmaf(t, 0.5f / kY1, 0.5f), l0 = 1.0f - l1;      // (t - y0) / (y1 - y0)
-                    p = fmaf(l1, v[2 * i + 1], l0 * v[2 * i]);
-                    s0 = fmaf(l1, ss.z, l0 * ss.x);
-                    s1 = fmaf(l1, ss.w, l0 * ss.y);
-                } else {
-                    const float4 sa = *reinterpret_cast<const float4 *>(s01_s + u * 8);
-                    const float4 sb = *reinterpret_cast<const float4 *>(s01_s + u * 8 + 4);
-                    const float t0 = t - kX0, t1 = t - kX1, t2 = t - kX2, t3 = t - kX3;
-                    const float l0 = t1 * t2 * t3 * (1.0f / ((kX0 - kX1) * (kX0 - kX2) * (kX0 - kX3)));
-                    const float l1 = t0 * t2 * t3 * (1.0f / ((kX1 - kX0) * (kX1 - kX2) * (kX1 - kX3)));
-                    const float l2 = t0 * t1 * t3 * (1.0f / ((kX2 - kX0) * (kX2 - kX1) * (kX2 - kX3)));
-                    const float l3 = t0 * t1 * t2 * (1.0f / ((kX3 - kX0) * (kX3 - kX1) * (kX3 - kX2)));
-                    p = l0 * v[4 * i] + l1 * v[4 * i + 1] + l2 * v[4 * i + 2] + l3 * v[4 * i + 3];
-                    s0 = l0 * sa.x + l1 * sa.z + l2 * sb.x + l3 * sb.z;
-                    s1 = l0 * sa.y + l1 * sa.w + l2 * sb.y + l3 * sb.w;
-                }
-                // LayerNorm folded into the dot: the candidate vectors are mean-centred, so x.w = rstd * (o.w)
-                const float mu = s0 * (1.0f / kD);
-                const float var = fmaxf(fmaf(-mu, mu, s1 * (1.0f / kD)), 0.0f);
-                const float rstd = rsqrtf(var + ln_eps) * kUnscale;
-                if (valid) outk[u * kAS + c] = fmaf(rstd, p, bk);
-            }
-        }
-      }
+    for (int i = 0; i < 5; ++i) {
+        ps[i] += __shfl_xor_sync(0xffffffffu, ps[i], 8);
+        ps[i] += __shfl_xor_sync(0xffffffffu, ps[i], 16);
+    }
+    if (c4 == 0 && u < nrows) {
+        float *acc = sum_s + (h * kH + u) * 8;
+        const float4 a0 = *reinterpret_cast<const float4 *>(acc);
+        *reinterpret_cast<float4 *>(acc) = make_float4(a0.x + ps[0], a0.y + ps[1], a0.z + ps[2], a0.w + ps[3]);
+        acc[4] += ps[4];
     }
 }
 
@@ -516,9 +403,9 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
 }
 
 // Front end of one work unit, executed by ONE warp (the MMA issuer) while the compute warps work on the previous unit.
-// Part 1, during its attention phase: the history slots (keys, bucket pairs, topic ids, gate bounds) into the front-end
-// scratch.  Parts 2 and 3, during its epilogue: dedup of the slots, then the candidates (cache rows, lifetime weights,
-// folded scalars).  All results land in the unit buffer `ub`.
+// Part 1: the history slots (keys, bucket pairs, topic ids, gate bounds) into the front-end scratch.  Part 2: dedup of
+// the slots.  Part 3: the candidates (cache rows, lifetime weights, folded scalars), dedup of their bucket pairs and
+// the operand row table.  All results land in the unit buffer `ub`.
 __device__ __forceinline__ void front_hist(const ScoreArgs &args, unsigned char *ub, int unit, int lane, int *hkn, int *hkt,
                                            int *htp, float *hga) {
     const LimeNewsCache &C = args.cache;
@@ -571,10 +458,18 @@ __device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char 
     float *cw = reinterpret_cast<float *>(ub + UB_CW);
     int *cnews = reinterpret_cast<int *>(ub + UB_CNEWS);
     int *ctab = reinterpret_cast<int *>(ub + UB_CTAB);
+    int *cbidx = reinterpret_cast<int *>(ub + UB_CBIDX);
     int *cP = reinterpret_cast<int *>(ub + UB_CP);
     int *ctopic = reinterpret_cast<int *>(ub + UB_CTOPIC);
-    const int pair0 = info[UI_PAIR0], cnt = info[UI_CNT];
+    int *btab = reinterpret_cast<int *>(ub + UB_BTAB);
+    uint2 *wrow = reinterpret_cast<uint2 *>(ub + UB_WROW);
+    const int pair0 = info[UI_PAIR0];
+    int cnt = info[UI_CNT];
     int flags = 0;
+    if (cnt > kTriples - 1) {          // the host built the units for a larger tile: exact kernel
+        cnt = kTriples - 1;
+        flags = 4;
+    }
     for (int c = lane; c < cnt; c += 32) {
         const long long p = (long long)pair0 + c;
         int n = I.cand_news[p];
@@ -593,17 +488,55 @@ __device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char 
         cscal[c * 4 + 1] = m1.x + __ldg(ctr + LIME_CAND_SCAL + 4);
         cscal[c * 4 + 2] = m1.y + __ldg(ctr + LIME_CAND_SCAL + 5);
         cscal[c * 4 + 3] = m1.z + __ldg(ctr + LIME_CAND_SCAL + 6);
-        if (!(m0.z <= kWAbsMax)) flags = 4;        // beyond the fp16 operand range: exact kernel
+        if (!(m0.z <= kWAbsMax)) flags |= 4;       // beyond the fp16 operand range: exact kernel
+    }
+    __syncwarp();
+    // distinct bucket pairs of the unit's candidates (all-pairs scan of <= 39 keys, two candidates per lane)
+    const int ca = lane, cb = lane + 32;
+    const int ka = ca < cnt ? ctab[ca] : -1 - ca, kb = cb < cnt ? ctab[cb] : -1 - cb;
+    int fa = 99, fb = 99;
+    for (int j = cnt - 1; j >= 0; --j) {
+        const int t = ctab[j];
+        fa = t == ka ? j : fa;
+        fb = t == kb ? j : fb;
+    }
+    const bool isfa = ca < cnt && fa == ca, isfb = cb < cnt && fb == cb;
+    const unsigned b0 = __ballot_sync(0xffffffffu, isfa), b1 = __ballot_sync(0xffffffffu, isfb);
+    const int nb0 = __popc(b0);
+    int nbp = nb0 + __popc(b1);
+    auto compact = [&](int f) { return f < 32 ? __popc(b0 & ((1u << f) - 1u)) : nb0 + __popc(b1 & ((1u << (f - 32)) - 1u)); };
+    if (ca < cnt) cbidx[ca] = min(compact(fa), kMaxBp - 1);
+    if (cb < cnt) cbidx[cb] = min(compact(fb), kMaxBp - 1);
+    if (isfa && compact(ca) < kMaxBp) btab[compact(ca)] = ka;
+    if (isfb && compact(cb) < kMaxBp) btab[compact(cb)] = kb;
+    if (nbp > kMaxBp || cnt + nbp > kTriples) {     // more bucket pairs than spare operand rows: exact kernel
+        flags |= 4;
+        nbp = min(min(nbp, kMaxBp), kTriples - cnt);
+    }
+    __syncwarp();
+    // operand row table: source element offset (bit 31: ctab16) and destination byte offset inside an image
+    const int nt = cnt + nbp;
+    for (int ri = lane; ri < 3 * nt; ri += 32) {
+        const int j = ri / 3, k = ri - 3 * j;
+        const uint32_t src = j < cnt ? (uint32_t)cnews[j] * (uint32_t)kC16 + (uint32_t)(k * kD)
+                                     : (0x80000000u | ((uint32_t)btab[j - cnt] * (uint32_t)kC16 + (uint32_t)(k * kD)));
+        const int m = m_row(j, k);
+        wrow[ri] = make_uint2(src, (uint32_t)((m >> 3) * 1024 + (m & 7) * 128));
     }
     flags = __reduce_or_sync(0xffffffffu, flags);
-    if (lane == 0) info[UI_FLAGS] = flags;
+    if (lane == 0) {
+        info[UI_FLAGS] = flags;
+        info[UI_NBP] = nbp;
+        info[UI_CNT] = cnt;
+    }
     __syncwarp();
 }
 
-// Part 2, during the previous unit's epilogue: deduplication of the history slots into unique operand rows.  Slots with
-// equal (news, bucket pair, mask) are one row.  A lane owns the slots lane and lane + 32 and scans all H keys (broadcast
-// reads, no cross-lane dependency): lowest equal slot = the unique row, number of equal slots = its multiplicity (overall
-// and inside the two GraphSAGE prefixes); one ballot pair then compacts the unique rows in slot order.
+// Part 2: deduplication of the history slots into unique operand rows.  Slots with equal (news, bucket pair, mask) --
+// in practice the padding of a short history, dataset.py:123-128 -- are one row.  A lane owns the slots lane and
+// lane + 32 and scans all H keys (broadcast reads, no cross-lane dependency): lowest equal slot = the unique row,
+// number of equal slots = its multiplicity (overall and inside the two GraphSAGE prefixes); one ballot pair then
+// compacts the unique rows in slot order.
 __device__ __forceinline__ void front_dedup(const ScoreArgs &args, unsigned char *ub, int lane, const int *hkn, const int *hkt,
                                             const int *htp, const float *hga) {
     int *info = reinterpret_cast<int *>(ub + UB_INFO);
@@ -672,21 +605,19 @@ __device__ __forceinline__ void front_dedup(const ScoreArgs &args, unsigned char
 __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs args) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float *out_s = reinterpret_cast<float *>(base + OFF_OUT);
-    float *a_s = reinterpret_cast<float *>(base + OFF_AS);
-    float *s01_s = reinterpret_cast<float *>(base + OFF_S01);
+    float2 *tab_s = reinterpret_cast<float2 *>(base + OFF_TAB);
+    float *t_s = reinterpret_cast<float *>(base + OFF_T);
+    float *sum_s = reinterpret_cast<float *>(base + OFF_SUM);
     float *mid_s = reinterpret_cast<float *>(base + OFF_MID);
     float *winv_s = reinterpret_cast<float *>(base + OFF_WINV);
     float *whalf_s = reinterpret_cast<float *>(base + OFF_WHALF);
+    float *part_s = reinterpret_cast<float *>(base + OFF_PART);
     float *pool_s = reinterpret_cast<float *>(base + OFF_POOL);
     int *hkn = reinterpret_cast<int *>(base + OFF_HKN);
     int *hkt = reinterpret_cast<int *>(base + OFF_HKT);
     int *htp = reinterpret_cast<int *>(base + OFF_HTP);
     float *hga = reinterpret_cast<float *>(base + OFF_HGA);
-    uint64_t *bar_full = reinterpret_cast<uint64_t *>(base + OFF_BARS);
-    uint64_t *bar_free = bar_full + 2;
-    uint64_t *bar_accum = bar_full + 4;
-    volatile int *misc = reinterpret_cast<volatile int *>(base + OFF_MISC);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + OFF_BARS);
 
     const LimeNewsCache &C = args.cache;
     const LimeImpressions &I = args.imp;
@@ -697,11 +628,15 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
     const __half *ctab16 = reinterpret_cast<const __half *>(C.ctab16);
 
     if (tid == 0) {
-        tc::mbar_init(bar_full + 0, 2 * kCompute);    // per compute thread: its cp.async copies + its O rows
-        tc::mbar_init(bar_full + 1, 2 * kCompute);
-        tc::mbar_init(bar_free + 0, 1);
-        tc::mbar_init(bar_free + 1, 1);
-        tc::mbar_init(bar_accum, 1);
+        for (int s = 0; s < 4; ++s) {
+            tc::mbar_init(bars + B_WFULL + s, kCompute);           // every compute thread, once its copies (if any) have landed
+            tc::mbar_init(bars + B_WFREE + s, 1);
+        }
+        for (int h = 0; h < 2; ++h) {
+            tc::mbar_init(bars + B_OFULL + h, kCWarps);             // one arrival per compute warp
+            tc::mbar_init(bars + B_OFREE + h, 1);
+        }
+        tc::mbar_init(bars + B_ACCUM, 1);
         tc::mbar_fence_init();
     }
     int next_unit = 0;               // issuer warp: the unit whose front end it runs next
@@ -726,8 +661,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
     }
     long long t_last = clock64();
 #endif
-    uint32_t use0 = 0, use1 = 0;     // uses of the two ring halves so far (every role counts the same sequence)
-    uint32_t pass_iter = 0;          // passes processed so far (phase of bar_accum)
+    uint32_t pass_iter = 0;          // passes (= units) processed so far: every role derives the barrier phases from it
     int ubi = 0;                     // unit buffer of the current unit
 
     for (;; ubi ^= 1) {
@@ -737,6 +671,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
         const float *cw = reinterpret_cast<const float *>(ub + UB_CW);
         const int *cnews = reinterpret_cast<const int *>(ub + UB_CNEWS);
         const int *ctab = reinterpret_cast<const int *>(ub + UB_CTAB);
+        const int *cbidx = reinterpret_cast<const int *>(ub + UB_CBIDX);
         const int *cP = reinterpret_cast<const int *>(ub + UB_CP);
         const int *ctopic = reinterpret_cast<const int *>(ub + UB_CTOPIC);
         const int *unews = reinterpret_cast<const int *>(ub + UB_UNEWS);
@@ -747,6 +682,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
         const float *ump0 = reinterpret_cast<const float *>(ub + UB_UMP0);
         const float *ump1 = reinterpret_cast<const float *>(ub + UB_UMP1);
         const float *ugabs = reinterpret_cast<const float *>(ub + UB_UGABS);
+        const uint2 *wrow = reinterpret_cast<const uint2 *>(ub + UB_WROW);
         int *flag_s = reinterpret_cast<int *>(ub + UB_INFO) + UI_FLAGS;
 
         const int unit = info[UI_UNIT];
@@ -754,41 +690,37 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
 #ifdef LIME_TC_PHASE_CLOCKS
         if (tid == 0) { t_last = clock64(); ++prof[9]; }
 #endif
-        const int pair0 = info[UI_PAIR0], cnt = info[UI_CNT], U = info[UI_U];
-        for (int c = tid; c < cnt; c += kThreads) {
-            pool_s[c * 4 + 0] = -INFINITY;
-            pool_s[c * 4 + 1] = 0.0f;
-            pool_s[c * 4 + 2] = 0.0f;
-            pool_s[c * 4 + 3] = 0.0f;
-        }
+        const int pair0 = info[UI_PAIR0], cnt = info[UI_CNT], U = info[UI_U], nbp = info[UI_NBP];
+        const int n3 = 3 * (cnt + nbp);
+        const int Up = (U + 15) & ~15;
+        const int ngroups = (U + 7) >> 3;
 
         // ================= roles ======================================================================
         if (warp < kCWarps) {
-            // the candidate operand of the first two stages goes out now (both ring slots are free since the previous
-            // unit's epilogue): it lands during the attention phase
-            {
-                ACopy ac;
-                ac.init(base, tid, cnews, ctab, cnt);
-                ac.issue(0, cand16, ctab16, bar_full, bar_free, use0, use1);
-                ac.issue(1, cand16, ctab16, bar_full, bar_free, use0, use1);
+            // the candidate operand of the first two stages goes out now (all ring slots are free since the previous
+            // unit's last MMA): it lands during the attention phase
+            for (int st = 0; st < 2; ++st) {
+                w_slot_wait(bars, st, pass_iter);
+                if (warp / kCopyTasks == st) copy_task(base, cand16, ctab16, wrow, n3, st, warp % kCopyTasks, lane);
+                cp_async_mbar_arrive_noinc(bars + B_WFULL + st);
             }
+            for (int i = tid; i < 2 * kH * 8; i += kCompute) sum_s[i] = 0.0f;
             // ---------------- phase 1: candidate-aware attention weights a[u][c] (layers.py:66-81) ------
-            // lanes per candidate = the smallest power of two that covers the U rows with 4 rows per lane: short (deduplicated)
-            // histories put more candidates into a round (7 warps x 32 / LPC), and a round costs one table-load latency
-            if (U <= 8)       attention<2>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
-            else if (U <= 16) attention<4>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
-            else if (U <= 32) attention<8>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
-            else              attention<16>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, a_s);
+            // lanes per candidate = the smallest power of two that covers the U rows with 4 rows per lane
+            if (U <= 8)       attention<2>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
+            else if (U <= 16) attention<4>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
+            else if (U <= 32) attention<8>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
+            else              attention<16>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
             bar_compute();
             LIME_TICK(2);
 
-            // ---------------- interpolation nodes per unique row (4 lanes per row) --------------------
+            // ---------------- centres: expansion point and half width per unique row (4 lanes per row) ----
             {
                 const int u = tid >> 2, l4 = tid & 3;
                 const int uc = u < U ? u : U - 1;
                 float lo = INFINITY, hi = -INFINITY;
                 for (int c = l4; c < cnt; c += 4) {
-                    const float a = a_s[uc * kAS + c];
+                    const float a = t_s[uc * kAS + c];
                     lo = fminf(lo, a);
                     hi = fmaxf(hi, a);
                 }
@@ -797,165 +729,222 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
                     lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
                     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
                 }
-                if (u < U && l4 == 0) {
-                    const float wh = fmaxf(0.5f * (hi - lo), 1e-7f);
-                    mid_s[u] = 0.5f * (hi + lo);
-                    whalf_s[u] = wh;
-                    winv_s[u] = 1.0f / wh;
-                    // Interpolation error of f(a) = (1 - a) sigmoid(g a + b) on [mid - w, mid + w] with n Chebyshev
-                    // nodes: max|d^n f| w^n / (n! 2^(n-1));  |d^2 f| <= 0.0962 g^2 + 0.5 |g|,
-                    // |d^4 f| <= 0.125 g^4 + 0.5 |g|^3.  g is bounded by the cached max |W_g vc| of the news plus
-                    // the max over the bucket-pair table.
-                    const float gabs = (ugabs[u] + C.tab_gw_absmax) * (1.0f / kLog2e);
-                    const float w2 = wh * wh, g2 = gabs * gabs;
-                    const float err2 = w2 * (0.0962f * g2 + 0.5f * gabs) * 0.25f;
-                    const float err4 = w2 * w2 * (0.125f * g2 * g2 + 0.5f * g2 * gabs) * (1.0f / 192.0f);
-                    if (!(err2 <= args.interp_tol)) atomicOr(flag_s, 1);          // 2 nodes are not enough
-                    if (!(err4 <= args.interp_tol)) atomicOr(flag_s, 2);          // 4 nodes are not enough: exact kernel
+                const float wh = fmaxf(0.5f * (hi - lo), 1e-7f);
+                const float mid = 0.5f * (hi + lo), winv = 1.0f / wh;
+                if (u < U) {
+                    // t = (a - mid) / w in [-1, 1], in place
+                    for (int c = l4; c < cnt; c += 4) {
+                        const float t = (t_s[u * kAS + c] - mid) * winv;
+                        t_s[u * kAS + c] = fminf(fmaxf(t, -1.0f), 1.0f);
+                    }
+                    if (l4 == 0) {
+                        mid_s[u] = mid;
+                        whalf_s[u] = wh;
+                        winv_s[u] = winv;
+                        // Remainder of the economised expansion of f(a) = (1 - a) sigmoid(g a + b) on [mid - w, mid + w]:
+                        // w^2 max|f''| / 4 + w^3 max|f'''| / 6; g is bounded by the cached max |W_g vc| of the news plus the
+                        // max over the bucket-pair table.
+                        const float gabs = (ugabs[u] + C.tab_gw_absmax) * (1.0f / kLog2e);
+                        const float w2 = wh * wh, g2 = gabs * gabs;
+                        const float err = w2 * (0.0962f * g2 + 0.5f * gabs) * 0.25f +
+                                          w2 * wh * (0.125f * g2 * gabs + 0.2887f * g2) * (1.0f / 6.0f);
+                        if (!(err <= args.interp_tol)) atomicOr(flag_s, 2);      // exact kernel
+                    }
                 }
             }
             bar_compute();
-            if (tid == 0) {
-                const int nd = (flag_s[0] & 1) ? 4 : 2;
-                misc[M_NODES] = nd;
-                misc[M_NPASS] = (nd * U + kBRows - 1) / kBRows;
-            }
-            bar_compute();
             LIME_TICK(3);
+
+            // ---------------- operand production + candidate copies -----------------------------------------
+            // per stage s: kCopyTasks copy tasks for stage s + 2 and one production task per row group of stage s, dealt
+            // round-robin to the 7 warps (the deal continues across stages, so short histories keep every warp busy)
+            {
+                const int per = kCopyTasks + ngroups;
+                int first = warp;                      // this warp's first task index inside the stage
+                for (int s = 0; s < kStages; ++s) {
+                    if (s + 2 < kStages) w_slot_wait(bars, s + 2, pass_iter);
+                    for (int idx = first; idx < per; idx += kCWarps) {
+                        if (idx < kCopyTasks) {
+                            if (s + 2 < kStages) copy_task(base, cand16, ctab16, wrow, n3, s + 2, idx, lane);
+                        } else {
+                            produce_task(base, C, s, idx - kCopyTasks, U, Up, lane, unews, utab, mid_s, whalf_s, sum_s, bars, pass_iter);
+                        }
+                    }
+                    if (s + 2 < kStages) cp_async_mbar_arrive_noinc(bars + B_WFULL + ((s + 2) & 3));
+                    o_slot_wait(bars, s, pass_iter);
+                    tc::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(bars + B_OFULL + (s & 1));
+                    // continue the deal: the next stage's task `first` is the one after this warp's last of this stage
+                    int nxt = first;
+                    while (nxt < per) nxt += kCWarps;
+                    first = nxt - per;
+                }
+            }
+            LIME_TICK(4);
         } else {
-            // issuer warp: claim the next work unit and run parts 1 and 2 of its front end while the compute warps are in
-            // phase 1 (part 3 runs after this unit's last MMA)
+            // ---------------- issuer warp --------------------------------------------------------------
+            // claim the next work unit and run parts 1 and 2 of its front end while the compute warps are in phase 1
             if (lane == 0) next_unit = atomicAdd(args.work_counter, 1);
             next_unit = __shfl_sync(0xffffffffu, next_unit, 0);
             front_hist(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, next_unit, lane, hkn, hkt, htp, hga);
             front_dedup(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, lane, hkn, hkt, htp, hga);
-        }
-        // the number of passes is known to the issuer at the first CTA barrier below; pass 0 always exists
-        int npass = 1;
-        for (int pass = 0; pass < npass; ++pass) {
-            if (warp < kCWarps) {
-                const int nodes = misc[M_NODES];
-                const int G = kBRows / nodes;
-                const int u0 = pass * G;
-                const int nrows = min(G, U - u0);
-                if (tid == 0) misc[M_NPAD] = (nodes * nrows + 15) & ~15;      // published by the first full-barrier arrive
-                if (nodes == 2) {
-                    if (nrows > kRPT) produce_operands<2, 2>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, s01_s, flag_s, cnews, ctab, cnt, cand16, ctab16, bar_full, bar_free, use0, use1, pass == 0 ? 2 : 0);
-                    else              produce_operands<2, 1>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, s01_s, flag_s, cnews, ctab, cnt, cand16, ctab16, bar_full, bar_free, use0, use1, pass == 0 ? 2 : 0);
-                } else {
-                    produce_operands<4, 1>(base, C, u0, nrows, tid, unews, utab, mid_s, whalf_s, s01_s, flag_s, cnews, ctab, cnt, cand16, ctab16, bar_full, bar_free, use0, use1, pass == 0 ? 2 : 0);
-                }
-            } else {
-                // ---------------- MMA issuer -------------------------------------------------------------
-                const uint32_t sb = tc::smem_u32(base);
-                uint32_t idesc = 0;
-                for (int kc = 0; kc < kStages; ++kc) {
-                    const int s = kc & 1;
-                    const uint32_t uses = s ? use1 : use0;
-                    tc::mbar_wait(bar_full + s, uses & 1u);
-                    tc::fence_after_sync();
-                    if (kc == 0) idesc = tc::idesc_f16_f32(128, misc[M_NPAD]);
-                    if (lane == 0) {
-                        const int ksteps = kc < kStages - 1 ? 2 : (kD - 32 * (kStages - 1)) / 16;
-                        const uint64_t bhi = tc::smem_desc_sw128(sb + OFF_BHI), blo = tc::smem_desc_sw128(sb + OFF_BLO);
-                        const uint64_t a_nh = tc::smem_desc_sw128(sb + OFF_A), a_nl = tc::smem_desc_sw128(sb + OFF_A + kAImg);
-                        const uint64_t a_th = tc::smem_desc_sw128(sb + OFF_A + 2 * kAImg), a_tl = tc::smem_desc_sw128(sb + OFF_A + 3 * kAImg);
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t k2 = (uint64_t)(2 * (2 * s + ks));   // 32 bytes per K step of 16
-                            // two accumulators (news part: columns 0.., table part: columns 128..): half as many
-                            // accumulation steps each; the epilogue adds them in fp32
-                            tc::mma_f16(tmem, a_nl + k2, bhi + k2, idesc, (kc | ks) != 0);
-                            tc::mma_f16(tmem, a_nh + k2, blo + k2, idesc, true);
-                            tc::mma_f16(tmem, a_nh + k2, bhi + k2, idesc, true);
-                            tc::mma_f16(tmem + 128, a_tl + k2, bhi + k2, idesc, (kc | ks) != 0);
-                            tc::mma_f16(tmem + 128, a_th + k2, blo + k2, idesc, true);
-                            tc::mma_f16(tmem + 128, a_th + k2, bhi + k2, idesc, true);
-                        }
-                        tc::mma_commit(bar_free + s);
-                        if (kc == kStages - 1) tc::mma_commit(bar_accum);
-                    }
-                    __syncwarp();
-                    if (s) ++use1; else ++use0;
-                }
-            }
-            LIME_TICK(4);
-            __syncthreads();   // node sums, flags and the pass count are visible to every role
-            LIME_TICK(10);
-            npass = misc[M_NPASS];
-
-            if (warp < kCWarps) {
-                // ---------------- epilogue: TMEM -> Lagrange combination -> LayerNorm folding ---------
-                const int nodes = misc[M_NODES];
-                const int G = kBRows / nodes;
-                const int u0 = pass * G;
-                const int nrows = min(G, U - u0);
-                tc::mbar_wait(bar_accum, pass_iter & 1u);
+            const uint32_t sb = tc::smem_u32(base);
+            const uint32_t idesc1 = tc::idesc_f16_f32(128, 3 * Up), idesc2 = tc::idesc_f16_f32(128, Up);
+            const uint64_t bdesc = tc::smem_desc_sw128(sb + OFF_O);
+            for (int kc = 0; kc < kStages; ++kc) {
+                const int s = kc & 3, h = kc & 1;
+                tc::mbar_wait(bars + B_WFULL + s, (pass_iter * w_uses(s) + (uint32_t)(kc >> 2)) & 1u, 300 + kc);
+                tc::mbar_wait(bars + B_OFULL + h, (pass_iter * o_uses(h) + (uint32_t)(kc >> 1)) & 1u, 400 + kc);
                 tc::fence_after_sync();
-                LIME_TICK(5);
-                if (nodes == 2) epilogue<2>(tmem, warp, lane, u0, nrows, cnt, args.ln_eps, a_s, mid_s, winv_s, s01_s, cscal, out_s);
-                else            epilogue<4>(tmem, warp, lane, u0, nrows, cnt, args.ln_eps, a_s, mid_s, winv_s, s01_s, cscal, out_s);
-                tc::fence_before_sync();
-                bar_compute();
-                LIME_TICK(6);
+                if (lane == 0) {
+                    const int ksteps = kc < kStages - 1 ? 2 : (kD - 32 * (kStages - 1)) / 16;
+                    const uint32_t wt = sb + OFF_W + (uint32_t)((kc >> 1) & 1) * kWTile;
+                    const uint64_t ahi = tc::smem_desc_sw128(wt), alo = tc::smem_desc_sw128(wt + kWImg);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t k2 = (uint64_t)(2 * (2 * h + ks));   // 32 bytes per K step of 16
+                        tc::mma_f16(tmem, ahi + k2, bdesc + k2, idesc1, (kc | ks) != 0);
+                        tc::mma_f16(tmem + 3 * Up, alo + k2, bdesc + k2, idesc2, (kc | ks) != 0);
+                    }
+                    tc::mma_commit(bars + B_WFREE + s);
+                    tc::mma_commit(bars + B_OFREE + h);
+                    if (kc == kStages - 1) tc::mma_commit(bars + B_ACCUM);
+                }
+                __syncwarp();
+            }
+            // part 3 of the next unit's front end, in the shadow of this unit's epilogue
+            front_cand(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, lane);
+        }
 
-                // ---------------- candidate-query pooling over the rows of this pass (online softmax) -----
-                // 8 lanes per candidate; multiplicities weight the softmax sum, the pooled value and the mean
-                const float *lg_s = out_s, *y_s = out_s + kH * kAS, *z_s = out_s + 2 * kH * kAS;
-                const int l8 = lane & 7, g = lane >> 3;
-                for (int c0 = 4 * warp; c0 < cnt; c0 += 4 * kCWarps) {
-                    const int c = c0 + g;
-                    const bool cvalid = c < cnt;
-                    const int cc = cvalid ? c : cnt - 1;
-                    const float *mp = cP[cc] == args.prefix_main ? ump0 : ump1;
-                    float m = -INFINITY;
-                    for (int ul = l8; ul < nrows; ul += 8) m = fmaxf(m, lg_s[(u0 + ul) * kAS + cc]);
+        if (warp < kCWarps) {
+            // ---------------- epilogue: TMEM -> table rows -> Taylor combination -> LayerNorm folding -> pooling ----
+            tc::mbar_wait(bars + B_ACCUM, pass_iter & 1u, 500);
+            tc::fence_after_sync();
+            LIME_TICK(5);
+            const int qd = warp & 3;
+            const bool paired = qd + 4 < kCWarps;            // quadrants 0..2 are walked by warps qd and qd + 4 in turn
+            const int hb = warp >> 2;
+            const int ti = lane / 3, k = lane - 3 * ti;
+            const int j = 10 * qd + ti;
+            const bool is_c = ti < 10 && j < cnt;
+            const bool is_t = ti < 10 && j >= cnt && j < cnt + nbp;
+            const int cc = is_c ? j : 0;
+            const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16);
+            const int nblocks = (U + 7) >> 3;
+            const int b0 = paired ? hb : 0, bstep = paired ? 2 : 1;
+            for (int i = tid; i < U * 8; i += kCompute) sum_s[i] += sum_s[kH * 8 + i];      // even + odd stages
+            // pass A: the bucket-pair rows of this quadrant publish (p0, p1) per unique row
+            if (10 * qd + 10 > cnt && 10 * qd < cnt + nbp) {
+                const int jt = 3 * (j - cnt) + k;
+                for (int b = b0; b < nblocks; b += bstep) {
+                    uint32_t x0[8], x1[8], x2[8], x3[8];
+                    tmem_ld8_nowait(taddr + 8 * b, x0);
+                    tmem_ld8_nowait(taddr + Up + 8 * b, x1);
+                    tmem_ld8_nowait(taddr + 2 * Up + 8 * b, x2);
+                    tmem_ld8_nowait(taddr + 3 * Up + 8 * b, x3);
+                    tc::tmem_ld_wait();
+                    if (is_t) {
 #pragma unroll
-                    for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                    float l = 0.f, acc = 0.f, ms = 0.f;
-                    for (int ul = l8; ul < nrows; ul += 8) {
-                        const int u = u0 + ul;
-                        const float e = umult[u] * ex2_approx((lg_s[u * kAS + cc] - m) * kLog2e);
-                        l += e;
-                        acc = fmaf(e, y_s[u * kAS + cc], acc);
-                        ms = fmaf(mp[u], z_s[u * kAS + cc], ms);
-                    }
-#pragma unroll
-                    for (int o = 1; o < 8; o <<= 1) {
-                        l += __shfl_xor_sync(0xffffffffu, l, o);
-                        acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                        ms += __shfl_xor_sync(0xffffffffu, ms, o);
-                    }
-                    if (cvalid && l8 == 0) {
-                        const float m_old = pool_s[c * 4 + 0];
-                        const float m_new = fmaxf(m_old, m);
-                        const float f_old = ex2_approx((m_old - m_new) * kLog2e);    // 0 on the first pass (m_old = -inf)
-                        const float f_new = ex2_approx((m - m_new) * kLog2e);
-                        const float l_new = fmaf(pool_s[c * 4 + 1], f_old, l * f_new);
-                        const float acc_new = fmaf(pool_s[c * 4 + 2], f_old, acc * f_new);
-                        const float ms_new = pool_s[c * 4 + 3] + ms;
-                        pool_s[c * 4 + 0] = m_new;
-                        pool_s[c * 4 + 1] = l_new;
-                        pool_s[c * 4 + 2] = acc_new;
-                        pool_s[c * 4 + 3] = ms_new;
-                        // lifetime-weighted click score (util.py:23-49) once the last pass is in; the rare P > H case
-                        // (user-node rows in the GraphSAGE mean) is finished after the pass loop
-                        const int P = cP[c];
-                        if (pass == npass - 1 && P <= H)
-                            args.scores[(long long)pair0 + c] = (ms_new / (float)P + cscal[c * 4 + 3] + acc_new / l_new) * cw[c];
+                        for (int i = 0; i < 8; ++i) {
+                            const int u = 8 * b + i;
+                            if (u < U)
+                                tab_s[u * kTabStride + jt] = make_float2(__uint_as_float(x0[i]) + __uint_as_float(x1[i]) + __uint_as_float(x3[i]),
+                                                                         __uint_as_float(x2[i]));
+                        }
                     }
                 }
-            } else if (pass == npass - 1) {
-                // ---------------- issuer warp: front end of the NEXT unit, in the shadow of this epilogue --------
-                front_cand(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, lane);
             }
-            ++pass_iter;
-            __syncthreads();   // out_s (aliasing the O operand) is free again; TMEM may be overwritten; next unit buffer ready
+            bar_compute();
+            // pass B: candidates.  Lane (candidate, k): k = 0 pooling logit, 1 pooled value, 2 GraphSAGE term; the softmax
+            // state (m, l) is kept redundantly by the 3 lanes of a candidate, acc / ms are meaningful on lanes k = 1 / 2.
+            const float bk = cscal[cc * 4 + k];
+            const int tj = 3 * cbidx[cc] + k;
+            const float *mp = cP[cc] == args.prefix_main ? ump0 : ump1;
+            float m_run = -INFINITY, l_run = 0.0f, acc = 0.0f, ms = 0.0f;
+            for (int b = b0; b < nblocks; b += bstep) {
+                uint32_t x0[8], x1[8], x2[8], x3[8];
+                tmem_ld8_nowait(taddr + 8 * b, x0);
+                tmem_ld8_nowait(taddr + Up + 8 * b, x1);
+                tmem_ld8_nowait(taddr + 2 * Up + 8 * b, x2);
+                tmem_ld8_nowait(taddr + 3 * Up + 8 * b, x3);
+                tc::tmem_ld_wait();
+                float val[8], lg[8];
+                float bm = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int u = min(8 * b + i, U - 1);
+                    const float2 tb = tab_s[u * kTabStride + tj];
+                    const float t = t_s[u * kAS + cc];
+                    const float4 sa = *reinterpret_cast<const float4 *>(sum_s + u * 8);
+                    const float q2 = sum_s[u * 8 + 4];
+                    const float p0 = __uint_as_float(x0[i]) + __uint_as_float(x1[i]) + __uint_as_float(x3[i]) + tb.x;
+                    const float p = fmaf(t, __uint_as_float(x2[i]) + tb.y, p0);
+                    const float s0 = fmaf(t, sa.y, sa.x) * (1.0f / kOScale);
+                    const float s1 = fmaf(t, fmaf(t, q2, 2.0f * sa.w), sa.z) * (1.0f / (kOScale * kOScale));
+                    // LayerNorm folded into the dot: the candidate vectors are mean-centred, so x.w = rstd * (o.w)
+                    const float mu = s0 * (1.0f / kD);
+                    const float var = fmaxf(fmaf(-mu, mu, s1 * (1.0f / kD)), 0.0f);
+                    const float rstd = rsqrtf(var + args.ln_eps) * kUnscale;
+                    val[i] = fmaf(rstd, p, bk);
+                    lg[i] = __shfl_sync(0xffffffffu, val[i], lane - k);
+                    if (8 * b + i < U) bm = fmaxf(bm, lg[i]);
+                }
+                const float m_new = fmaxf(m_run, bm);
+                const float sc = ex2_approx((m_run - m_new) * kLog2e);       // 0 on the first block (m_run = -inf)
+                l_run *= sc;
+                acc *= sc;
+                m_run = m_new;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int u = 8 * b + i;
+                    if (u < U) {
+                        const float e = umult[u] * ex2_approx((lg[i] - m_new) * kLog2e);
+                        l_run += e;
+                        acc = fmaf(e, val[i], acc);
+                        ms = fmaf(mp[u], val[i], ms);
+                    }
+                }
+            }
+            if (is_c) {
+                float *pp = part_s + (hb * kTriples + j) * 4;
+                if (k == 0) { pp[0] = m_run; pp[1] = l_run; }
+                if (k == 1) pp[2] = acc;
+                if (k == 2) pp[3] = ms;
+            }
+            // fp16 operand range of the O rows (or NaN): exact kernel
+            if (tid < U && !(sum_s[tid * 8 + 2] <= kS1Max)) atomicOr(flag_s, 4);
+            tc::fence_before_sync();
+            bar_compute();
+            LIME_TICK(6);
+            // merge the two halves of a quadrant, lifetime-weighted click score (util.py:23-49); the rare P > H case
+            // (user-node rows in the GraphSAGE mean) is finished below
+            if (tid < cnt) {
+                const int c = tid;
+                const float *p0 = part_s + c * 4, *p1 = part_s + (kTriples + c) * 4;
+                float m = p0[0], l = p0[1], a2 = p0[2], s2 = p0[3];
+                if (c < 30 && nblocks > 1) {
+                    const float m1 = p1[0];
+                    const float mn = fmaxf(m, m1);
+                    const float f0 = ex2_approx((m - mn) * kLog2e), f1 = ex2_approx((m1 - mn) * kLog2e);
+                    l = fmaf(l, f0, p1[1] * f1);
+                    a2 = fmaf(a2, f0, p1[2] * f1);
+                    s2 += p1[3];
+                    m = mn;
+                }
+                pool_s[c * 4 + 0] = m;
+                pool_s[c * 4 + 1] = l;
+                pool_s[c * 4 + 2] = a2;
+                pool_s[c * 4 + 3] = s2;
+                const int P = cP[c];
+                if (P <= H) args.scores[(long long)pair0 + c] = (s2 / (float)P + cscal[c * 4 + 3] + a2 / l) * cw[c];
+            }
             LIME_TICK(7);
         }
+        ++pass_iter;
+        __syncthreads();   // the O tile (aliased by tab_s) and TMEM may be overwritten; the next unit buffer is ready
 
         if (tid == 0) {
             if ((flag_s[0] & 6) != 0) args.fallback_list[atomicAdd(args.fallback_count, 1)] = unit;
-            if (flag_s[0] & 1) atomicAdd(args.fallback_count + 2, 1);   // statistics: 4-node units
         }
 
         // ---------------- P > H: user-node rows take part in the GraphSAGE mean (userEncoders.py:121,153) -------
@@ -979,7 +968,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
                     }
                 }
             }
-            __syncthreads();   // pool_s is re-initialised at the top of the next unit
+            __syncthreads();   // pool_s is rewritten by the next unit
         }
         LIME_TICK(8);
     }
@@ -1019,8 +1008,9 @@ __global__ void topic_pair_table_kernel(const float *__restrict__ topics, int64_
     }
 }
 
-// src [rows, lds] fp32, `blocks` blocks of 400 columns -> dst [rows, blocks * 800] fp16: per block the 400 hi
-// halves followed by the 400 lo halves (scale * x = hi + lo to 2^-22); absmax[row * ldo] = max |x| of the row
+// src [rows, lds] fp32, `blocks` blocks of 400 columns -> dst [rows, 2 * blocks * 400] fp16: the hi halves of all blocks,
+// then the lo halves (scale * x = hi + lo to 2^-22), i.e. [hi | lo][block][400]: one operand-row triple of the scoring
+// kernel is 3 consecutive 800-byte rows; absmax[row * ldo] = max |x| of the row
 __global__ void split_f16_pairs_kernel(const float *__restrict__ src, int64_t lds, int blocks, float scale,
                                        __half *__restrict__ dst, float *__restrict__ absmax, int64_t ldo) {
     __shared__ float red[4];
@@ -1029,13 +1019,12 @@ __global__ void split_f16_pairs_kernel(const float *__restrict__ src, int64_t ld
     __half *d = dst + row * (int64_t)blocks * 2 * kD;
     float mx = 0.0f;
     for (int e = threadIdx.x; e < blocks * kD; e += blockDim.x) {
-        const int k = e / kD, dd = e - k * kD;
         const float x = s[e];
         const float xs = x * scale;
         const __half h = __float2half_rn(xs);
         const __half l = __float2half_rn(xs - __half2float(h));
-        d[k * 2 * kD + dd] = h;
-        d[k * 2 * kD + kD + dd] = l;
+        d[e] = h;
+        d[blocks * kD + e] = l;
         mx = fmaxf(mx, fabsf(x));
         if (x != x) mx = INFINITY;
     }
@@ -1048,11 +1037,7 @@ __global__ void split_f16_pairs_kernel(const float *__restrict__ src, int64_t ld
 }  // namespace
 
 int launch_score_tc(const ScoreArgs &a, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        LIME_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        attr_set = true;
-    }
+    LIME_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));   // per device, cheap
     LIME_CUDA(cudaMemsetAsync(a.work_counter, 0, 4 * sizeof(int32_t), st));   // work counter, fallback count, exact counter, stats
     int grid = 2 * num_sms();
     if (const char *e = getenv("LIME_TC_ONE_CTA_PER_SM")) {      // experiment knob: concurrency vs shared resources

@@ -10,6 +10,7 @@
 
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace lime {
 namespace tc {
@@ -39,10 +40,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#ifdef LIME_TC_DEBUG_WAIT
+// debug build: a wait that does not complete within ~0.2 s reports itself and traps (finds protocol deadlocks on the GPU box)
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int tag = -1) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 400000000ll) {
+            if ((threadIdx.x & 31) == 0)
+                printf("mbar_wait timeout: block %d warp %d bar@%u parity %u tag %d\n", (int)blockIdx.x, (int)threadIdx.x >> 5,
+                       smem_u32(bar), parity, tag);
+            const long long t1 = clock64();
+            while (clock64() - t1 < 1000000000ll) {      // let every other stuck waiter report before the trap
+            }
+            __trap();
+        }
+    }
+}
+#else
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int = -1) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+#endif
 
 // generic-proxy writes (st.shared) -> visible to the async proxy (tensor core operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -451,14 +451,6 @@ content_fuse_bwd_kernel(const float *__restrict__ title, const float *__restrict
 // Inverted dropout with a stateless counter-based generator (forward and backward apply the same
 // mask: y = x * keep / (1 - p)).  element index -> 32 random bits via two rounds of a 64-bit mix.
 // =================================================================================================
-__device__ __forceinline__ uint32_t mix_bits(uint64_t seed, uint64_t idx) {
-    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    return (uint32_t)(z >> 32);
-}
-
 __global__ void dropout_kernel(const float *__restrict__ x, int64_t ldx, float *__restrict__ y, int64_t ldy, int64_t rows,
                                int cols, float p, uint64_t seed) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -14,7 +14,8 @@ constexpr int kUHd = kUD / kUHeads;     // 40
 // ---------------------------------------------------------------------------------------------
 // Candidate-aware attention weights (layers.py:66-81):
 //   S[hd][n][h] = Q_n[hd] . K_h[hd] / sqrt(D);  masked_fill(mask == 0, -1e9);  P = softmax_h(S)
-//   qw = softmax_n(||Q_n||_2);  agg[h] = sum_n qw_n sum_hd P[hd][n][h];  a = softmax_h(agg)   (unmasked)
+//   P~ = dropout(P, p) (layers.py:36,74: nn.Dropout(0.2) on the attention weights; stateless mask of (seed, sample, index))
+//   qw = softmax_n(||Q_n||_2);  agg[h] = sum_n qw_n sum_hd P~[hd][n][h];  a = softmax_h(agg)   (unmasked)
 // Shared memory: Q [N][400], K [H][400], P [10*N][H], small vectors.
 // ---------------------------------------------------------------------------------------------
 struct CaSmem {
@@ -35,9 +36,10 @@ __host__ __device__ inline size_t ca_smem_floats(int N, int H) {
     return (size_t)N * kUD + (size_t)H * kUD + (size_t)kUHeads * N * H + 2 * N + 2 * H + 8;
 }
 
-// forward pieces shared by the forward and backward kernels; on return P, qn, qw, agg, a are valid
+// forward pieces shared by the forward and backward kernels; on return P (before the dropout), qn, qw, agg, a are valid
 __device__ void ca_forward(const CaSmem &s, const float *__restrict__ Qp, const float *__restrict__ Kp,
-                           const uint8_t *__restrict__ mask, int N, int H, float scale) {
+                           const uint8_t *__restrict__ mask, int N, int H, float scale, float p_drop, uint64_t seed,
+                           uint64_t base_idx) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     for (int i = tid; i < N * kUD; i += nt) s.Q[i] = Qp[i];
     for (int i = tid; i < H * kUD; i += nt) s.K[i] = Kp[i];
@@ -85,7 +87,10 @@ __device__ void ca_forward(const CaSmem &s, const float *__restrict__ Qp, const 
         float acc = 0.0f;
         for (int n = 0; n < N; ++n) {
             float t = 0.0f;
-            for (int hd = 0; hd < kUHeads; ++hd) t += s.P[(hd * N + n) * H + h];
+            for (int hd = 0; hd < kUHeads; ++hd) {
+                const int idx = (hd * N + n) * H + h;
+                t += p_drop > 0.0f ? s.P[idx] * drop_scale(seed, base_idx + idx, p_drop) : s.P[idx];
+            }
             acc = fmaf(s.qw[n], t, acc);
         }
         s.agg[h] = acc;
@@ -105,23 +110,26 @@ __device__ void ca_forward(const CaSmem &s, const float *__restrict__ Qp, const 
 
 __global__ void __launch_bounds__(256)
 ca_attn_fwd_kernel(const float *__restrict__ Qp, const float *__restrict__ Kp, const uint8_t *__restrict__ mask, int N, int H,
-                   float scale, float *__restrict__ a_out) {
+                   float scale, float p_drop, uint64_t seed, float *__restrict__ a_out) {
     extern __shared__ float sm[];
     const CaSmem s = ca_carve(sm, N, H);
     const int b = blockIdx.x;
-    ca_forward(s, Qp + (size_t)b * N * kUD, Kp + (size_t)b * H * kUD, mask + (size_t)b * H, N, H, scale);
+    ca_forward(s, Qp + (size_t)b * N * kUD, Kp + (size_t)b * H * kUD, mask + (size_t)b * H, N, H, scale, p_drop, seed,
+               (uint64_t)b * kUHeads * N * H);
     for (int h = threadIdx.x; h < H; h += blockDim.x) a_out[(size_t)b * H + h] = s.a[h];
 }
 
 __global__ void __launch_bounds__(256)
 ca_attn_bwd_kernel(const float *__restrict__ Qp, const float *__restrict__ Kp, const uint8_t *__restrict__ mask, int N, int H,
-                   float scale, const float *__restrict__ da, float *__restrict__ dQp, float *__restrict__ dKp) {
+                   float scale, float p_drop, uint64_t seed, const float *__restrict__ da, float *__restrict__ dQp,
+                   float *__restrict__ dKp) {
     extern __shared__ float sm[];
     const CaSmem s = ca_carve(sm, N, H);
     __shared__ float dagg[64], dqw[64], red[2];
     const int b = blockIdx.x;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-    ca_forward(s, Qp + (size_t)b * N * kUD, Kp + (size_t)b * H * kUD, mask + (size_t)b * H, N, H, scale);
+    const uint64_t base_idx = (uint64_t)b * kUHeads * N * H;
+    ca_forward(s, Qp + (size_t)b * N * kUD, Kp + (size_t)b * H * kUD, mask + (size_t)b * H, N, H, scale, p_drop, seed, base_idx);
     const float *dab = da + (size_t)b * H;
     // a = softmax(agg):  dagg = a (da - sum a da)
     if (warp == 0) {
@@ -136,7 +144,10 @@ ca_attn_bwd_kernel(const float *__restrict__ Qp, const float *__restrict__ Kp, c
         float t = 0.0f;
         for (int h = lane; h < H; h += 32) {
             float ps = 0.0f;
-            for (int hd = 0; hd < kUHeads; ++hd) ps += s.P[(hd * N + n) * H + h];
+            for (int hd = 0; hd < kUHeads; ++hd) {
+                const int idx = (hd * N + n) * H + h;
+                ps += p_drop > 0.0f ? s.P[idx] * drop_scale(seed, base_idx + idx, p_drop) : s.P[idx];
+            }
             t = fmaf(dagg[h], ps, t);
         }
         t = warp_sum(t);
@@ -149,15 +160,21 @@ ca_attn_bwd_kernel(const float *__restrict__ Qp, const float *__restrict__ Kp, c
         red[0] = t;
     }
     __syncthreads();
-    // dS[hd][n][h] = P (dP - sum_h dP P) * scale with dP = dagg_h qw_n  (in place of P)
+    // dS[hd][n][h] = P (dP - sum_h dP P) * scale with dP = dagg_h qw_n * dropout scale  (in place of P)
     for (int row = warp; row < kUHeads * N; row += nw) {
         const int n = row % N;
         float *p = s.P + row * H;
         float t = 0.0f;
-        for (int h = lane; h < H; h += 32) t = fmaf(dagg[h] * s.qw[n], p[h], t);
+        for (int h = lane; h < H; h += 32) {
+            const float m = p_drop > 0.0f ? drop_scale(seed, base_idx + row * H + h, p_drop) : 1.0f;
+            t = fmaf(dagg[h] * s.qw[n] * m, p[h], t);
+        }
         t = warp_sum(t);
         // masked_fill: no gradient reaches the logits of masked history slots (they are the constant -1e9)
-        for (int h = lane; h < H; h += 32) p[h] = mask[(size_t)b * H + h] ? p[h] * (dagg[h] * s.qw[n] - t) * scale : 0.0f;
+        for (int h = lane; h < H; h += 32) {
+            const float m = p_drop > 0.0f ? drop_scale(seed, base_idx + row * H + h, p_drop) : 1.0f;
+            p[h] = mask[(size_t)b * H + h] ? p[h] * (dagg[h] * s.qw[n] * m - t) * scale : 0.0f;
+        }
     }
     __syncthreads();
     // dQ_n = sum_h dS K_h (per head) + dqn_n Q_n / ||Q_n||,  dqn = qw (dqw - sum qw dqw)
@@ -411,27 +428,27 @@ using namespace lime;
 static inline unsigned blocks_for(int64_t total, int per) { return (unsigned)((total + per - 1) / per); }
 
 extern "C" int lime_ca_attention_fwd(const float *Qp, const float *Kp, const uint8_t *mask, int32_t B, int32_t N, int32_t H,
-                                     float *a, void *stream) {
+                                     float p_drop, uint64_t seed, float *a, void *stream) {
     LIME_CHECK_ARG(Qp && Kp && mask && a, "lime_ca_attention_fwd: null argument");
     LIME_CHECK_ARG(N >= 1 && N <= 64 && H >= 1 && H <= 64, "lime_ca_attention_fwd: N=%d, H=%d must be in [1,64]", N, H);
     if (B <= 0) return 0;
     const size_t smem = sizeof(float) * ca_smem_floats(N, H);
     LIME_CHECK_ARG(smem <= 232448, "lime_ca_attention_fwd: N=%d, H=%d needs %zu B of shared memory", N, H, smem);
     LIME_CUDA(cudaFuncSetAttribute(ca_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ca_attn_fwd_kernel<<<B, 256, smem, as_stream(stream)>>>(Qp, Kp, mask, N, H, 1.0f / sqrtf((float)kUD), a);
+    ca_attn_fwd_kernel<<<B, 256, smem, as_stream(stream)>>>(Qp, Kp, mask, N, H, 1.0f / sqrtf((float)kUD), p_drop, seed, a);
     LIME_LAUNCH_CHECK("ca_attn_fwd_kernel");
     return 0;
 }
 
 extern "C" int lime_ca_attention_bwd(const float *Qp, const float *Kp, const uint8_t *mask, int32_t B, int32_t N, int32_t H,
-                                     const float *da, float *dQp, float *dKp, void *stream) {
+                                     float p_drop, uint64_t seed, const float *da, float *dQp, float *dKp, void *stream) {
     LIME_CHECK_ARG(Qp && Kp && mask && da && dQp && dKp, "lime_ca_attention_bwd: null argument");
     LIME_CHECK_ARG(N >= 1 && N <= 64 && H >= 1 && H <= 64, "lime_ca_attention_bwd: N=%d, H=%d must be in [1,64]", N, H);
     if (B <= 0) return 0;
     const size_t smem = sizeof(float) * ca_smem_floats(N, H);
     LIME_CHECK_ARG(smem <= 232448 - 1024, "lime_ca_attention_bwd: N=%d, H=%d needs %zu B of shared memory", N, H, smem);
     LIME_CUDA(cudaFuncSetAttribute(ca_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ca_attn_bwd_kernel<<<B, 256, smem, as_stream(stream)>>>(Qp, Kp, mask, N, H, 1.0f / sqrtf((float)kUD), da, dQp, dKp);
+    ca_attn_bwd_kernel<<<B, 256, smem, as_stream(stream)>>>(Qp, Kp, mask, N, H, 1.0f / sqrtf((float)kUD), p_drop, seed, da, dQp, dKp);
     LIME_LAUNCH_CHECK("ca_attn_bwd_kernel");
     return 0;
 }

@@ -33,7 +33,7 @@ HIST_LD, CAND_LD, HTAB_LD, CTAB_LD = 852, 1720, 800, 1208
 HIST_GW, HIST_T, HIST_TOPIC_ID, HIST_GW_ABSMAX = 400, 800, 850, 851
 CAND_SCAL, CAND_TQ, CAND_NFOLD, CAND_TOPIC_ID, CAND_ABSMAX = 1200, 1208, 1207, 1718, 1207
 F16_SAFE = 32768.0 / ops.CAND16_SCALE      # |w| beyond this leaves the fp16 operand range after scaling
-TOPIC_TAB_LD, MAX_TOPICS, TC_MAX_HISTORY = 12, 1024, 52
+TOPIC_TAB_LD, MAX_TOPICS, TC_MAX_HISTORY = 12, 1024, 56
 TOPIC, TOPIC_LD, HEADS = 50, 52, 10
 LOG2E = 1.4426950408889634
 

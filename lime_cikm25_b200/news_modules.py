@@ -266,9 +266,23 @@ class LIME(nn.Module):
     def forward(self, title_text, title_mask, title_entity, content_text, content_mask, content_entity,
                 category, subCategory, user_embedding, news_freshness, news_user_topic_lifetime):
         """-> [B, n, 400] = project(content || freshness) (reference :140-153)."""
-        _require_eval(self, "LIME.forward")
         from . import ops
         B, n = title_text.shape[0], title_text.shape[1]
+        if self.training:
+            # differentiable path (training.py): the same kernels with their backward, dropout applied
+            from . import training
+            self._fwd_calls = getattr(self, "_fwd_calls", 0) + 1
+            i32 = torch.int32
+            fr = news_freshness.reshape(B, -1).float()
+            lf = news_user_topic_lifetime.reshape(B, -1).float().expand_as(fr)
+            vec = training.encode_news(self, title_text.reshape(B * n, -1).to(i32).contiguous(),
+                                       content_text.reshape(B * n, -1).to(i32).contiguous(),
+                                       category.reshape(-1).to(i32).contiguous(), subCategory.reshape(-1).to(i32).contiguous(),
+                                       fr.reshape(-1).contiguous(), lf.reshape(-1).contiguous(),
+                                       seed=int(getattr(self.config, "seed", 0)) * 1000003 + self._fwd_calls * 307 + 3)
+            self.auxiliary_loss = torch.zeros((), dtype=torch.float32, device=vec.device)      # category loss * alpha (= 0)
+            self.base_news_encoder.auxiliary_loss = self.auxiliary_loss
+            return vec.view(B, n, self.news_embedding_dim)
         content = self.base_news_encoder(title_text, title_mask, title_entity, content_text, content_mask,
                                          content_entity, category, subCategory, user_embedding,
                                          news_freshness, news_user_topic_lifetime).view(B * n, -1)

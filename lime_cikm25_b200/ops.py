@@ -332,18 +332,19 @@ def _f32(t, name):
     return _ptr(t, torch.float32, name)
 
 
-def ca_attention_fwd(Qp, Kp, mask, B, N, H):
+def ca_attention_fwd(Qp, Kp, mask, B, N, H, p_drop=0.0, seed=0):
     lib = _lib.require_device()
     a = torch.empty((B * H,), dtype=torch.float32, device=Qp.device)
-    check(lib.lime_ca_attention_fwd(_f32(Qp, "Qp"), _f32(Kp, "Kp"), _ptr(mask, torch.uint8, "mask"), B, N, H, a.data_ptr(),
-                                    _stream()), "lime_ca_attention_fwd")
+    check(lib.lime_ca_attention_fwd(_f32(Qp, "Qp"), _f32(Kp, "Kp"), _ptr(mask, torch.uint8, "mask"), B, N, H,
+                                    float(p_drop), int(seed) & (2 ** 64 - 1), a.data_ptr(), _stream()), "lime_ca_attention_fwd")
     return a
 
 
-def ca_attention_bwd(Qp, Kp, mask, B, N, H, da):
+def ca_attention_bwd(Qp, Kp, mask, B, N, H, da, p_drop=0.0, seed=0):
     lib = _lib.require_device()
     dQ, dK = torch.empty_like(Qp), torch.empty_like(Kp)
-    check(lib.lime_ca_attention_bwd(_f32(Qp, "Qp"), _f32(Kp, "Kp"), _ptr(mask, torch.uint8, "mask"), B, N, H, _f32(da, "da"),
+    check(lib.lime_ca_attention_bwd(_f32(Qp, "Qp"), _f32(Kp, "Kp"), _ptr(mask, torch.uint8, "mask"), B, N, H,
+                                    float(p_drop), int(seed) & (2 ** 64 - 1), _f32(da, "da"),
                                     dQ.data_ptr(), dK.data_ptr(), _stream()), "lime_ca_attention_bwd")
     return dQ, dK
 

@@ -78,14 +78,14 @@ def encode_news(lime, title_text, body_text, category, subCategory, freshness, l
     return A.linear(fresh, pw[:, cd:], None, residual=A.linear(content, pw[:, :cd], lime.project.bias))
 
 
-def user_scores(model, hist_vec, cand_vec, hist_cat, hist_sub, cand_cat, cand_sub, hist_mask, remaining, B, H, N, seed=0):
-    """CROWN user encoder + lifetime-weighted click score, training layout.
-    hist_vec [B*H,400], cand_vec [B*N,400] (LIME vectors), int32 category ids flat, mask uint8 [B,H],
-    remaining [B*N] fp32 seconds -> logits [B, N] (userEncoders.py:101-175, util.py:23-49)."""
-    ue, lime, cfg = model.user_encoder, model.news_encoder, model.config
+def user_representation(ue, hist_vec, cand_vec, hist_cat, hist_sub, cand_cat, cand_sub, hist_mask, B, H, N, seed=0):
+    """userEncoders.CROWN.forward after the history encode (userEncoders.py:103-105,114-175):
+    hist_vec [B*H,400], cand_vec [B*N,400] (LIME vectors), int32 category ids flat, mask uint8 [B,H]
+    -> user representation [B*N, 400], every step a liblime_b200 kernel with its backward."""
+    lime, cfg = ue.news_encoder, ue.config
     ca = ue.candidate_aware_attn
     sage = ue.graph_sage.convs[0]
-    p = float(cfg.dropout_rate) if model.training else 0.0
+    p = float(cfg.dropout_rate) if ue.training else 0.0
     # topic representations from LIME's frozen tables + category_affine (userEncoders.py:103-105,115-117)
     pad_h = torch.zeros(B * H, 2, dtype=torch.float32, device=hist_vec.device)
     pad_c = torch.zeros(B * N, 2, dtype=torch.float32, device=hist_vec.device)
@@ -93,7 +93,7 @@ def user_scores(model, hist_vec, cand_vec, hist_cat, hist_sub, cand_cat, cand_su
     tc = torch.cat([topic_representation(lime, cand_cat, cand_sub), pad_c], dim=1)            # [B*N, 52]
     Qp = A.linear(tc, F.pad(ca.query_proj.weight, (0, 2)), ca.query_proj.bias)                # layers.py:66
     Kp = A.linear(th, F.pad(ca.key_proj.weight, (0, 2)), ca.key_proj.bias)                    # layers.py:67
-    a = A.CAAttention.apply(Qp, Kp, hist_mask, B, N, H)                                        # [B*H]
+    a = A.CAAttention.apply(Qp, Kp, hist_mask, B, N, H, 0.2 if ue.training else 0.0, seed + 61)   # [B*H]; p = 0.2 fixed, layers.py:36,74
     wc = A.RowScale.apply(hist_vec, a)                                                         # layers.py:84
     z = A.linear(wc, ca.gate_proj.weight, ca.gate_proj.bias)
     o = A.GateMix.apply(z, wc, hist_vec)                                                       # layers.py:87-88
@@ -105,11 +105,22 @@ def user_scores(model, hist_vec, cand_vec, hist_cat, hist_sub, cand_cat, cand_su
     # candidate-query pooling (userEncoders.py:158-171)
     Kg = A.linear(g, ue.K.weight, None)
     q = A.linear(cand_vec, ue.Q.weight, ue.Q.bias)
-    u = A.Pool.apply(Kg, q, g, B, N, H)
-    rw = model.remaining_lifetime_weighting
+    return A.Pool.apply(Kg, q, g, B, N, H)
+
+
+def click_scores(rw, u, cand_vec, remaining, B, N):
+    """RemainingLifetimeWeighting.forward (util.py:23-49): u, cand_vec [B*N, 400], remaining [B*N] -> [B, N]."""
     s = A.ClickScore.apply(u, cand_vec, remaining.reshape(-1).float().contiguous(), rw.alpha, rw.beta,
                            rw.use_remaining_lifetime_weighting, rw.use_expired_penalty)
     return s.view(B, N)
+
+
+def user_scores(model, hist_vec, cand_vec, hist_cat, hist_sub, cand_cat, cand_sub, hist_mask, remaining, B, H, N, seed=0):
+    """CROWN user encoder + lifetime-weighted click score, training layout -> logits [B, N]
+    (userEncoders.py:101-175, util.py:23-49)."""
+    u = user_representation(model.user_encoder, hist_vec, cand_vec, hist_cat, hist_sub, cand_cat, cand_sub, hist_mask,
+                            B, H, N, seed)
+    return click_scores(model.remaining_lifetime_weighting, u, cand_vec, remaining, B, N)
 
 
 def model_forward(model, user_category, user_subCategory, user_title_text, user_content_text, user_freshness,

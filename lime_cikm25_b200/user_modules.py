@@ -3,9 +3,10 @@
 Keeps the reference's constructor signature, attributes, ``initialize()`` and ``state_dict`` keys
 (reference userEncoders.py:16-89; PyG key names ``graph_sage.convs.0.lin_l.{weight,bias}``,
 ``graph_sage.convs.0.lin_r.weight``, ``lightgcn.embedding.weight``).  The arithmetic of
-``forward`` (candidate-aware attention -> GraphSAGE mean aggregation -> candidate-query pooling) is
-fused with the click score in csrc/score.cu and is reached through ``Model.forward`` /
-``util.score_impressions``.
+``forward`` (candidate-aware attention -> GraphSAGE mean aggregation -> candidate-query pooling)
+returns the [B, N, D] user representation through the kernels of csrc/train_user.cu; the eval hot
+path (``Model.forward`` / ``util.score_impressions``) fuses the same arithmetic with the click score
+in csrc/score_tc.cu / score.cu and never materialises it.
 """
 from __future__ import annotations
 
@@ -115,9 +116,32 @@ class CROWN(UserEncoder):
                 user_subCategory, user_history_mask, user_history_graph, user_history_category_mask,
                 user_history_category_indices, user_embedding, candidate_news_representation,
                 user_freshness, user_user_topic_lifetime):
-        """On the B200 path the user representation is never materialised: the history attention,
-        GraphSAGE aggregation, candidate-query pooling and the click score are one kernel, reached via
-        ``Model.forward`` (same 26 tensors).  A stand-alone [B,N,D] user vector is not produced."""
-        raise _lib.LimeError(
-            "userEncoders.CROWN.forward is fused into the scoring kernel on the B200 path; call "
-            "Model.forward / util.score_impressions (same inputs) — no PyTorch fallback exists")
+        """-> user representation [B, N, D] (reference userEncoders.py:101-175), every step a liblime_b200 kernel
+        (training.py composes them; each has its backward, so this is also the training path of a reference
+        ``Model`` built over these plugin classes).  ``Model.forward`` of this package does not come through
+        here in eval mode: it scores with the fused kernel, which never materialises the user vector."""
+        from . import training
+        B, H = user_category.shape[0], user_category.shape[1]
+        N = candidate_news_representation.shape[1]
+        i32 = torch.int32
+        calls = getattr(self, "_fwd_calls", 0) + 1
+        self._fwd_calls = calls
+        seed = int(getattr(self.config, "seed", 0)) * 1000003 + calls * 211 + 7
+        if self.training:
+            flat = lambda t: t.reshape(B * H, -1).to(i32).contiguous()
+            hist = training.encode_news(self.news_encoder, flat(user_title_text), flat(user_content_text),
+                                        user_category.reshape(-1).to(i32).contiguous(),
+                                        user_subCategory.reshape(-1).to(i32).contiguous(),
+                                        user_freshness.reshape(-1).float().contiguous(),
+                                        user_user_topic_lifetime.reshape(-1).float().contiguous(), seed)
+        else:
+            hist = self.news_encoder(user_title_text, user_title_mask, user_title_entity, user_content_text,
+                                     user_content_mask, user_content_entity, user_category, user_subCategory,
+                                     user_embedding, user_freshness, user_user_topic_lifetime)
+        D = self.news_embedding_dim
+        u = training.user_representation(
+            self, hist.reshape(B * H, D).contiguous(), candidate_news_representation.reshape(B * N, D).contiguous(),
+            user_category.reshape(-1).to(i32).contiguous(), user_subCategory.reshape(-1).to(i32).contiguous(),
+            category.reshape(-1).to(i32).contiguous(), subCategory.reshape(-1).to(i32).contiguous(),
+            user_history_mask.to(torch.uint8).contiguous(), B, H, N, seed)
+        return u.view(B, N, D)

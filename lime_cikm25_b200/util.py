@@ -18,9 +18,9 @@ from .synth import Impressions, NewsTable
 
 
 class RemainingLifetimeWeighting(nn.Module):
-    """Holder of the lifetime-weighting hyper-parameters (reference util.py:15-21).  The weight
-    ``sigmoid(alpha r)`` (times beta when expired) and its product with the dot-product score are
-    computed inside csrc/score.cu (lifetime_weight)."""
+    """Remaining-lifetime-guided weighting of the dot-product score (reference util.py:15-49).
+    ``forward`` runs lime_click_score_fwd (and its backward when gradients are recorded); the fused
+    eval kernels evaluate the same weight inline (score_common.cuh: lifetime_weight)."""
 
     def __init__(self, config):
         super().__init__()
@@ -33,8 +33,11 @@ class RemainingLifetimeWeighting(nn.Module):
         pass
 
     def forward(self, user_embedding, news_embedding, remaining_lifetime):
-        raise _lib.LimeError("RemainingLifetimeWeighting is fused into the scoring kernel on the B200 "
-                             "path (Model.forward / evaluate_impressions)")
+        """[B, N, D], [B, N, D], [B, N] -> weighted matching score [B, N] (util.py:23-49)."""
+        from . import training
+        B, N, D = user_embedding.shape
+        return training.click_scores(self, user_embedding.reshape(B * N, D).contiguous(),
+                                     news_embedding.reshape(B * N, D).contiguous(), remaining_lifetime, B, N)
 
 
 @dataclass

@@ -185,3 +185,32 @@ def build_reference_model(cfg, seed=0, word_embedding=None):
         finally:
             os.chdir(cwd)
     return m
+
+
+def load_reference_model_over_plugins():
+    """The reference's OWN ``model.py`` (unmodified source, loaded from REFERENCE_ROOT) with its three plugin imports --
+    ``newsEncoders``, ``userEncoders`` and ``util.RemainingLifetimeWeighting`` -- resolved to lime_cikm25_b200's drop-in
+    modules (variant 1).  Returns the module; ``.Model(config)`` is the reference's class."""
+    import importlib.util
+    if not reference_available():
+        raise RuntimeError("reference tree not found at " + REFERENCE_ROOT)
+    _install_stubs()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import lime_cikm25_b200.news_modules as b_news
+    import lime_cikm25_b200.user_modules as b_user
+    import lime_cikm25_b200.util as b_util
+    saved = {k: sys.modules.get(k) for k in ("newsEncoders", "userEncoders", "util")}
+    sys.modules["newsEncoders"], sys.modules["userEncoders"], sys.modules["util"] = b_news, b_user, b_util
+    try:
+        spec = importlib.util.spec_from_file_location("ref_model_over_b200", os.path.join(REFERENCE_ROOT, "model.py"))
+        mod = importlib.util.module_from_spec(spec)
+        with contextlib.redirect_stdout(io.StringIO()):
+            spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod

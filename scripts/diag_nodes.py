@@ -36,8 +36,8 @@ with torch.no_grad():
         from lime_cikm25_b200 import _lib
         buf = (ctypes.c_uint64 * 16)()
         _lib.load().lime_score_phase_clocks(buf)
-        names = ["meta", "dedup", "attn", "nodes", "produce", "mma_wait", "epilogue", "pool", "final", "units", "prod_barrier", "P_fence+arrive", "P_wait_free", "P_copy_issue", "P_loads(v,gg)", "P_compute+store"]
-        tot = sum(buf[i] for i in (0, 1, 2, 3, 4, 5, 6, 7, 8, 10))
-        print("  phase clocks per unit (thread 0): " + "  ".join("%s %.0f" % (n, buf[i] / max(buf[9], 1)) for i, n in enumerate(names) if i != 9) + "  | total %.0f" % (tot / max(buf[9], 1)))
+        names = ["-", "-", "attn", "centres", "produce", "mma_wait", "epilogue+pool", "merge", "tail", "units", "-", "-", "-", "-", "-", "-"]
+        tot = sum(buf[i] for i in (2, 3, 4, 5, 6, 7, 8))
+        print("  phase clocks per unit (thread 0): " + "  ".join("%s %.0f" % (n, buf[i] / max(buf[9], 1)) for i, n in enumerate(names) if i != 9 and n != "-") + "  | total %.0f" % (tot / max(buf[9], 1)))
         wc = dimp.work_counter[:4].tolist()
-        print(json.dumps({"tol": tol, "units": dimp.num_units, "four_node": wc[3], "fallback": wc[1], "ms": e0.elapsed_time(e1) / 3}))
+        print(json.dumps({"tol": tol, "units": dimp.num_units, "fallback": wc[1], "ms": e0.elapsed_time(e1) / 3}))

@@ -105,6 +105,59 @@ def test_cached_impression_eval_matches_reference(lib, case, golden_dir):
     assert rel(base, g["base_scores"]) < TOL
 
 
+def _reference_style_forward(model, tb):
+    """model.py:158-181 spelled out over the plugin classes: unsqueeze the candidate tensors (eval), news_encoder ->
+    user_encoder -> remaining_lifetime_weighting.  tb = the 25 dataset tensors on the device."""
+    (uid, ucat, usub, utt, utm, ute, uct, ucm, uce, ufr, ulf, umask, ugraph, ucmask, ucidx,
+     ncat, nsub, ntt, ntm, nte, nct, ncm, nce, nfr, nlf) = tb
+    rem = nlf - nfr
+    if ncat.dim() == 1:
+        ncat, nsub, ntt, ntm, nct, ncm, nte, nce, nfr, nlf, rem = (x.unsqueeze(1) for x in (ncat, nsub, ntt, ntm, nct, ncm, nte, nce, nfr, nlf, rem))
+    news_rep = model.news_encoder(ntt, ntm, nte, nct, ncm, nce, ncat, nsub, None, news_freshness=nfr, news_user_topic_lifetime=nlf)
+    user_rep = model.user_encoder(utt, utm, ute, uct, ucm, uce, ncat, nsub, ucat, usub, umask, ugraph, ucmask, ucidx, None,
+                                  news_rep, user_freshness=ufr, user_user_topic_lifetime=ulf)
+    assert user_rep.shape == news_rep.shape
+    return model.remaining_lifetime_weighting(user_rep, news_rep, rem)
+
+
+@pytest.mark.parametrize("case", ["small_bs8", "bs64"])
+def test_plugin_classes_compose_like_reference_model(lib, case, golden_dir):
+    """The plugin classes are real modules: news_encoder -> userEncoders.CROWN.forward -> [B,N,D] ->
+    RemainingLifetimeWeighting.forward, composed as the reference's model.py:171-181 does, reproduce the reference's
+    scores (P < H and P > H cases), and agree with this package's fused Model.forward."""
+    cfg, news, imp, g, sd, model = load_case(case, golden_dir)
+    out, fused = [], []
+    with torch.no_grad():
+        for batch in synth.impressions_to_pair_batches(news, imp, cfg.batch_size):
+            tb = [torch.as_tensor(x).to(DEV) for x in batch]
+            logits = _reference_style_forward(model, tb)
+            assert logits.shape == (len(batch[0]), 1)
+            out.append(logits.squeeze(1).cpu())
+            fused.append(model(*tb, tb[24] - tb[23]).squeeze(1).cpu())
+    scores = torch.cat(out).numpy()
+    assert rel(scores, g["scores"]) < TOL
+    assert rel(scores, torch.cat(fused).numpy()) < TOL
+
+
+def test_reference_model_py_over_plugin_classes(lib, golden_dir):
+    """INTEGRATION.md section A variant 1, literally: the reference's own model.py with its newsEncoders / userEncoders /
+    util imports resolved to this package.  Needs /root/reference (build container) AND a GPU: skipped elsewhere."""
+    from oracle import ref_import
+    if not ref_import.reference_available():
+        pytest.skip("reference tree not present (GPU box)")
+    cfg, news, imp, g, sd, model = load_case("small_bs8", golden_dir)
+    ref_model = ref_import.load_reference_model_over_plugins().Model(cfg)
+    missing, unexpected = ref_model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.endswith("pe") for k in missing), (missing, unexpected)
+    ref_model = ref_model.to(DEV).eval()
+    out = []
+    with torch.no_grad():
+        for batch in synth.impressions_to_pair_batches(news, imp, cfg.batch_size):
+            tb = [torch.as_tensor(x).to(DEV) for x in batch]
+            out.append(ref_model(*tb, tb[24] - tb[23]).squeeze(1).cpu())
+    assert rel(torch.cat(out).numpy(), g["scores"]) < TOL
+
+
 def _stage_b_oracle(model, sd, cfg, cache, news, imp, prefix):
     """CPU oracle of the user encoder + click score on the GPU-built LIME vectors (isolates Stage B)."""
     se = model.scoring
@@ -379,10 +432,11 @@ def test_bf16_mode_metrics(lib, golden_dir):
 
 
 def test_tensor_core_scoring_paths(lib):
-    """Every branch of lime_score_impressions on one impression set: 2-node units (default), 4-node units (tolerance
-    between the two interpolation bounds), all units through the exact-fallback list (tolerance 0), exact kernel
-    only; edge impressions: empty history (uniform attention), one candidate (zero-width node interval), 300
-    candidates (9 units), and operands beyond the fp16 range (flagged for the exact kernel)."""
+    """Every branch of lime_score_impressions on one impression set: expansion units (default tolerance), a tolerance
+    below the expansion's remainder bound (those units are re-scored by the exact kernel in the same call), all
+    units through the exact-fallback list (tolerance 0), exact kernel only; edge impressions: empty history
+    (uniform attention), one candidate (zero-width interval), 300 candidates (9 units), and operands beyond the
+    fp16 range (flagged for the exact kernel)."""
     cfg = make_config(vocabulary_size=600, batch_size=32, word_embedding_init="skip")
     model = L.Model(cfg)
     model.initialize()
@@ -409,7 +463,7 @@ def test_tensor_core_scoring_paths(lib):
         with torch.no_grad():
             cache = util.build_news_cache(model, news)
             dimp = engine.DeviceImpressions(imp, DEV)
-            for name, (mode, tol) in dict(two=(ops.SCORE_AUTO, 1e-6), four=(ops.SCORE_AUTO, 1e-13), forced=(ops.SCORE_FORCE_FALLBACK, 1e-6),
+            for name, (mode, tol) in dict(two=(ops.SCORE_AUTO, 1e-6), tight=(ops.SCORE_AUTO, 1e-13), forced=(ops.SCORE_FORCE_FALLBACK, 1e-6),
                                           exact=(ops.SCORE_EXACT, 1e-6)).items():
                 ops.score_configure(mode, tol)
                 out[name] = util.score_impressions(model, cache, dimp, 32).clone()
@@ -425,10 +479,10 @@ def test_tensor_core_scoring_paths(lib):
     finally:
         ops.score_configure(ops.SCORE_AUTO, 1e-6)
     ex = out["exact"].cpu().numpy()
-    assert fallback["two"] == 0 and fallback["four"] == 0 and fallback["forced"] == dimp.num_units
+    assert fallback["two"] == 0 and 0 < fallback["tight"] <= dimp.num_units and fallback["forced"] == dimp.num_units
     assert torch.equal(out["forced"], out["exact"])
-    assert rel(out["two"].cpu().numpy(), ex) < 5e-5 and rel(out["four"].cpu().numpy(), ex) < 5e-5
-    assert float((out["two"] - out["four"]).abs().max()) > 0        # the two node counts are different code paths
+    assert rel(out["two"].cpu().numpy(), ex) < 5e-5 and rel(out["tight"].cpu().numpy(), ex) < 5e-5
+    assert float((out["two"] - out["tight"]).abs().max()) > 0       # expansion vs exact re-scoring: different code paths
     assert fb_big >= 1                                              # flagged, re-scored exactly
     users = [i for i in range(imp.num_impressions) if int(imp.hist_news[2, 0]) in imp.hist_news[i]]
     sel = np.concatenate([np.arange(imp.cand_off[i], imp.cand_off[i + 1]) for i in users])
