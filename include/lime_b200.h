@@ -147,18 +147,25 @@ typedef struct {
     /* per-news cache built by the Python host from the entry points above */
     const float *hist_rows;     /* [news_num, LIME_HIST_LD]                                      */
     const float *cand_rows;     /* [news_num, LIME_CAND_LD]                                      */
-    const float *hist_tab;      /* [nb*nb, LIME_HTAB_LD]                                         */
+    const float *hist_tab;      /* [tab_replicas, nb*nb, LIME_HTAB_LD]: identical copies; the tensor-core kernel reads copy
+                                   blockIdx % tab_replicas (every CTA gathers the same few hot rows at every stage: one copy
+                                   serialises them in a handful of L2 slices), the exact kernel copy 0             */
     const float *cand_tab;      /* [nb*nb, LIME_CTAB_LD]                                         */
     const float *gate_bias;     /* [LIME_D]  -log2(e) * gate_proj.bias                           */
     const float *un_prefix;     /* [config.batch_size, LIME_D] prefix sums of lin_l(user_node_embedding) */
     const float *topic_table;   /* [num_topics, num_topics, LIME_TOPIC_TAB_LD] from lime_topic_pair_table,
                                    or NULL (then only the exact kernel can run)                      */
-    const void  *cand16;        /* [news_num, LIME_CAND16_LD] fp16: w1 w2 w3 of cand_rows as hi/lo pairs
-                                   (lime_split_f16_pairs), or NULL (exact kernel only)               */
-    const void  *ctab16;        /* [nb*nb, LIME_CAND16_LD] fp16: the same for cand_tab               */
+    const void  *cand16;        /* [news_num + tab_replicas*nb*nb, LIME_CAND16_LD] fp16: w1 w2 w3 of cand_rows as hi/lo pairs
+                                   (lime_split_f16_pairs), FOLLOWED by tab_replicas copies of the nb*nb rows of ctab16 (one
+                                   operand array for candidate and bucket-pair rows), or NULL (exact kernel only)      */
+    const void  *ctab16;        /* [nb*nb, LIME_CAND16_LD] fp16: the same for cand_tab (source of the tail of cand16) */
     const float *news_meta;     /* [news_num, LIME_META_LD]: the scalars phase 0 of the tensor-core kernel needs, packed
                                    into one 32-byte sector per news (2 MB for 65k news: L2 resident) -- topic id (int32
                                    bits), gw absmax, w absmax, B1, B2, B3, cb, 0; or NULL (exact kernel only)   */
+    const float *hist_vg;       /* [news_num, 2*LIME_D]: vc and gw of hist_rows interleaved in groups of 4 dims
+                                   (v0..3 g0..3 v4..7 g4..7 ...), 32-byte aligned rows: one 256-bit load fetches both
+                                   operands of 4 dims (tensor-core kernel only; NULL: exact kernel only)                */
+    const float *htab_vg;       /* [tab_replicas, nb*nb, 2*LIME_D]: hist_tab in the same interleaved layout             */
     int32_t news_num;
     int32_t num_buckets;
     int32_t user_nodes;         /* config.batch_size (rows of user_node_embedding)               */
@@ -171,6 +178,7 @@ typedef struct {
     float   topic_logit_absmax; /* max |entry| of topic_table (entries are log2(e)-scaled logits): the tensor-core
                                    path runs its softmax without a max pass and requires this <= 64   */
     int32_t tc_tables_ok;       /* nonzero: ctab16 holds no value beyond the fp16 operand range      */
+    int32_t tab_replicas;       /* copies of the bucket-pair tables in hist_tab and in the tail of cand16 (>= 1) */
 } LimeNewsCache;
 
 typedef struct {

@@ -20,10 +20,11 @@ class LimeNewsCache(C.Structure):
         ("hist_rows", C.c_void_p), ("cand_rows", C.c_void_p), ("hist_tab", C.c_void_p),
         ("cand_tab", C.c_void_p), ("gate_bias", C.c_void_p), ("un_prefix", C.c_void_p),
         ("topic_table", C.c_void_p), ("cand16", C.c_void_p), ("ctab16", C.c_void_p), ("news_meta", C.c_void_p),
+        ("hist_vg", C.c_void_p), ("htab_vg", C.c_void_p),
         ("news_num", C.c_int32), ("num_buckets", C.c_int32), ("user_nodes", C.c_int32), ("num_topics", C.c_int32),
         ("tab_gw_absmax", C.c_float), ("sigmoid_alpha", C.c_float), ("penalty_beta", C.c_float),
         ("use_lifetime_weighting", C.c_int32), ("use_expired_penalty", C.c_int32),
-        ("topic_logit_absmax", C.c_float), ("tc_tables_ok", C.c_int32),
+        ("topic_logit_absmax", C.c_float), ("tc_tables_ok", C.c_int32), ("tab_replicas", C.c_int32),
     ]
 
 

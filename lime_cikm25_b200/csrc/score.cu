@@ -588,7 +588,7 @@ extern "C" int lime_score_impressions(const LimeNewsCache *cache, const LimeImpr
 
     const bool tc_ok = g_score_mode != 1 && H <= LIME_TC_MAX_HISTORY && TC <= LIME_TC_TILE_C &&
                        cache->topic_table != nullptr && cache->num_topics >= 1 && cache->cand16 != nullptr &&
-                       cache->ctab16 != nullptr && cache->news_meta != nullptr && cache->tc_tables_ok != 0 && cache->topic_logit_absmax <= 64.0f;
+                       cache->ctab16 != nullptr && cache->news_meta != nullptr && cache->hist_vg != nullptr && cache->htab_vg != nullptr && cache->tc_tables_ok != 0 && cache->topic_logit_absmax <= 64.0f;
     if (!tc_ok) return launch_score_exact(a, imp->num_units, st);
 
     // fast path: interpolated gate + tcgen05 dots; units whose error bound exceeds the tolerance are

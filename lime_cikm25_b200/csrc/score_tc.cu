@@ -64,7 +64,7 @@ constexpr int kAS = kTriples;                   // row stride of a_s / t_s  ([u]
 constexpr int kStages = 13;                     // 32-wide K stages over D = 400 (the last holds 16 dims)
 constexpr int kWTile = 32768, kWImg = 16384;    // one 64-dim candidate tile = hi image + lo image of 128 rows x 128 B
 constexpr int kGroups = 7;                      // row groups of 8 unique history rows (56 / 8)
-constexpr int kCopyTasks = 3;                   // candidate-operand copy tasks per stage
+constexpr int kCopyTasks = kCWarps;             // candidate-operand copy shares per stage: every compute warp takes one
 constexpr int kTabLd = LIME_TOPIC_TAB_LD;
 constexpr int kTabStride = 32;                  // tab_s[u][3 * bp + k] (float2), 3 * kMaxBp <= 32
 constexpr float kLog2e = 1.4426950408889634f;
@@ -84,8 +84,8 @@ constexpr int OFF_O = 2 * kWTile;                             // [Ohi ; Olo ; O1
 constexpr int kOBytes = 3 * 64 * 128;
 constexpr int OFF_TAB = OFF_O;                                // alias (after the MMAs): table-row results [u][32] float2
 constexpr int OFF_T = OFF_O + kOBytes;                        // a[u][c], then t[u][c]
-constexpr int OFF_SUM = OFF_T + kH * kAS * 4;                 // [stage parity][u][8]: sum c0, c1, c0^2, c0 c1, c1^2
-constexpr int OFF_MID = OFF_SUM + 2 * kH * 8 * 4;
+constexpr int OFF_SUM = OFF_T + kH * kAS * 4;                 // [u][8]: sum c0, c1, c0^2, c0 c1, c1^2
+constexpr int OFF_MID = OFF_SUM + kH * 8 * 4;
 constexpr int OFF_WINV = OFF_MID + kH * 4;
 constexpr int OFF_WHALF = OFF_WINV + kH * 4;
 constexpr int OFF_PART = OFF_WHALF + kH * 4;                  // [2][40][4] partial pooling state of the two warps of a quadrant
@@ -118,9 +118,11 @@ constexpr int OFF_HKN = OFF_UB + 2 * kUnitBuf, OFF_HKT = OFF_HKN + kUArr, OFF_HT
 constexpr int OFF_BARS = OFF_HGA + kUArr;                     // wfull[4] wfree[4] ofull[2] ofree[2] accum
 constexpr int OFF_MISC = OFF_BARS + 128;                      // tmem slot
 constexpr int OFF_PROF = OFF_MISC + 64;                       // phase clocks of thread 0 (diagnostic)
-constexpr int kSmemBytes = OFF_PROF + 128 + 1024;
+constexpr int OFF_BIAS = OFF_PROF + 128;                      // gate bias [400]: read by every lane at every stage
+constexpr int kSmemBytes = OFF_BIAS + kD * 4;
 static_assert(kH * kTabStride * 8 <= kOBytes, "table-row alias overflows the O operand tile");
 static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
+static_assert(OFF_BIAS % 16 == 0, "alignment");
 static_assert(kTile + 1 <= kTriples && 3 * kMaxBp <= kTabStride, "unit capacity");
 static_assert(OFF_BARS % 8 == 0 && OFF_T % 16 == 0 && OFF_SUM % 16 == 0 && OFF_UB % 16 == 0 && kUnitBuf % 16 == 0 &&
               OFF_O % 1024 == 0 && UB_WROW % 8 == 0 && OFF_PART % 16 == 0, "alignment");
@@ -162,6 +164,12 @@ __device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, uint32_t n) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(n) : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// one instruction brings a whole cache row into L2 (the front end runs a unit ahead of the warps that read the row)
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+#ifndef LIME_TC_NO_ROW_PREFETCH
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#endif
+}
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(kCompute) : "memory"); }
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -194,23 +202,32 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
 // A slot is 8 operand rows x 64 contiguous bytes (lane = (row in slot, 16-byte chunk)); rows come from the unit's
 // row table (candidate rows of cand16, bucket-pair rows of ctab16).  cp.async.mbarrier.arrive.noinc publishes the
 // stage when this thread's copies have landed (no thread waits for the data).
-__device__ __forceinline__ void copy_task(unsigned char *base, const __half *cand16, const __half *ctab16,
-                                          const uint2 *wrow, int n3, int kc, int sub, int lane) {
+__device__ __forceinline__ void copy_task(unsigned char *base, const unsigned char *w16, const uint2 *wrow, int n3, int kc,
+                                          int sub, int lane) {
+    constexpr int kIter = (2 * 3 * kTriples / 8 + kCopyTasks - 1) / kCopyTasks;      // slots per warp and stage (5)
     const int c4 = lane & 3, rs = lane >> 2;
+#ifdef LIME_TC_DIAG_NOCOPY       // timing diagnostic only (wrong results): no candidate-operand copies
+    return;
+#endif
     if (kc < kStages - 1 || c4 < (kD - 32 * (kStages - 1)) / 8) {
         const uint32_t wbase = tc::smem_u32(base) + OFF_W + (uint32_t)((kc >> 1) & 1) * kWTile;
-        const int chunk = 4 * (kc & 1) + c4;
-        const int eo = 32 * kc + 8 * c4;
-        const int nslots = (2 * n3 + 7) >> 3;
-        for (int slot = sub; slot < nslots; slot += kCopyTasks) {
-            const int ri = 8 * slot + rs;
-            if (ri < 2 * n3) {
-                const int hl = ri >= n3 ? 1 : 0;
-                const uint2 rw = wrow[ri - hl * n3];
-                const __half *src = ((rw.x & 0x80000000u) ? ctab16 : cand16) + (size_t)(rw.x & 0x7fffffffu) + hl * (3 * kD) + eo;
-                const uint32_t dst = wbase + (uint32_t)hl * kWImg + rw.y + (uint32_t)((chunk ^ ((rw.y >> 7) & 7)) << 4);
-                cp_async16(dst, src);
-            }
+        const uint32_t chunk = (uint32_t)(4 * (kc & 1) + c4);
+        const unsigned char *src0 = w16 + 64 * kc + 16 * c4;
+        uint2 rw[kIter];
+        bool on[kIter], lo[kIter];
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+            int ri = 8 * (sub + kCopyTasks * i) + rs;
+            on[i] = ri < 2 * n3;
+            lo[i] = ri >= n3;
+            ri -= lo[i] ? n3 : 0;
+            rw[i] = wrow[on[i] ? ri : 0];
+        }
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+            if (on[i])
+                cp_async16(wbase + (lo[i] ? kWImg : 0) + rw[i].y + ((chunk ^ ((rw[i].y >> 7) & 7u)) << 4),
+                           src0 + rw[i].x + (lo[i] ? 6 * kD : 0));
         }
     }
 }
@@ -229,90 +246,93 @@ __device__ __forceinline__ void o_slot_wait(uint64_t *bars, int kc, uint32_t pas
     if (fill >= 1) tc::mbar_wait(bars + B_OFREE + h, (fill - 1) & 1u, 200 + kc);
 }
 
-// ---- history operand (N side): one production task = 8 unique rows x 32 dims of stage kc ------------------------------
-// lane = (row in group r = lane & 7, 8-dim chunk c4 = lane >> 3): a quarter warp writes 8 different rows of the same
-// chunk column, which the 128-byte swizzle spreads over all banks (conflict-free 16-byte stores).
-__device__ __forceinline__ void produce_task(unsigned char *base, const LimeNewsCache &C, int kc, int g, int nrows, int Up,
-                                             int lane, const int *unews, const int *utab, const float *mid_s,
-                                             const float *whalf_s, float *sum_s, uint64_t *bars, uint32_t pass_iter) {
-    const int r = lane & 7, c4 = lane >> 3;
-    const int h = kc & 1;
-    const int u = 8 * g + r;
-    const int d0 = 32 * kc + 8 * c4;
-    const bool ok = u < nrows && d0 < kD;
-    float c0[8], c1[8];
-    float ps[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    if (ok) {
-        const float *hrow = C.hist_rows + (size_t)unews[u] * LIME_HIST_LD;
-        const float *trow = C.hist_tab + (size_t)utab[u] * LIME_HTAB_LD;
-        float4 vn[2], vt[2], gn[2], gt[2], bb[2];
+// ---- history operand (N side) -------------------------------------------------------------------------------------
+// Fixed ownership: lane = (row slot j = lane >> 3, quad q = lane & 7 of the stage's 32 dims); "virtual warp" vw = warp
+// (+ 7 in the second pass, histories with more than 26 unique rows) owns the rows 8 (vw >> 1) + P[4 (vw & 1) + j],
+// P = [0 4 1 5 2 6 3 7]: the two rows of a half warp differ in bit 2 of the row number, which the 128-byte swizzle turns
+// into opposite 64-byte halves of the bank space -- the 8-byte stores of a warp are conflict-free.  Everything that
+// depends on the row only (cache pointers, expansion point, half width) is hoisted out of the stage loop, the five row
+// sums stay in registers for the whole unit, and the global loads run one stage ahead of the arithmetic.
+struct Quad {                // 4 dims of a cache row: per-news part (DRAM), bucket-pair part (L2) and gate bias (shared memory)
+    float4 vn, gn, vt, gt, bb;
+};
+// v and g of 4 dims with ONE 256-bit load (hist_vg / htab_vg interleave them): two global loads per quad instead of four,
+// so the loads of the next stage and of the current one never share a scoreboard slot
+__device__ __forceinline__ void ldg8(const float *p, float4 &a, float4 &b) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+struct RowCtx {
+    const float *hrow, *trow, *bias;
+    float a, oml, nwv, nso, kq;
+    bool ok;
+};
+__device__ __forceinline__ void quad_load(Quad &q, const RowCtx &c, int d) {
+#ifdef LIME_TC_DIAG_NOLOAD       // timing diagnostic only (wrong results): no global loads in the production loop
+    q.vn = q.gn = q.vt = q.gt = q.bb = make_float4(0.01f * d, 0.02f, 0.03f, 0.04f);
+    return;
+#endif
+    if (c.ok && d < kD) {
+#if defined(LIME_TC_DIAG_SKIP) && LIME_TC_DIAG_SKIP == 1      // timing diagnostics only (wrong results)
+        q.vn = q.gn = make_float4(0.01f, 0.02f, 0.03f, 0.04f);
+#else
+        ldg8(c.hrow + 2 * d, q.vn, q.gn);
+#endif
+#if defined(LIME_TC_DIAG_SKIP) && LIME_TC_DIAG_SKIP == 2
+        q.vt = q.gt = make_float4(0.01f, 0.02f, 0.03f, 0.04f);
+#else
+        ldg8(c.trow + 2 * d, q.vt, q.gt);
+#endif
+        q.bb = *reinterpret_cast<const float4 *>(c.bias + d);      // shared memory
+    }
+}
+__device__ __forceinline__ void row_ctx_init(RowCtx &rc, const LimeNewsCache &C, const float *bias_s, const float *htab, int u,
+                                             int U, const int *unews, const int *utab, const float *mid_s, const float *whalf_s) {
+    rc.ok = u < U;
+    rc.bias = bias_s;
+    rc.hrow = rc.trow = nullptr;
+    rc.a = rc.oml = rc.nwv = rc.nso = rc.kq = 0.0f;
+    if (rc.ok) {
+        rc.hrow = C.hist_vg + (size_t)unews[u] * (2 * kD);
+        rc.trow = htab + (size_t)utab[u] * (2 * kD);
+        rc.a = mid_s[u];
+        const float w = whalf_s[u];
+        const float om = 1.0f - rc.a;
+        rc.oml = -om * kLn2;                              // d/da of the gate argument in natural units: g = -ln2 * g'
+        rc.nwv = -kOScale * w;                            // c1 = -256 w v f'
+        rc.nso = -kOScale * om;                           // 256 (1 - om s)
+        rc.kq = kOScale * 0.25f * w * w * kLn2;           // + 256 (w^2/4) ln2 r' n  ( = -256 (w^2/4) f'' )
+    }
+}
+// 4 elements: s = sigmoid(x) = 1 / (1 + 2^z'),  z' = a g' + b'  (g', b' pre-scaled by -log2 e);  with g = -ln2 g':
+//   f = om s,  f' = -s + om g s (1 - s),  f'' = g s (1 - s) (om g (1 - 2 s) - 2)
+//   c0 = 256 v (1 - f - (w^2/4) f''),  c1 = -256 w v f'
+__device__ __forceinline__ void quad_eval(const Quad &q, const RowCtx &c, float (&ps)[5], uint32_t &hi0, uint32_t &hi1,
+                                          uint32_t &lo0, uint32_t &lo1, uint32_t &d0, uint32_t &d1) {
+    const float vv[4] = {q.vn.x + q.vt.x, q.vn.y + q.vt.y, q.vn.z + q.vt.z, q.vn.w + q.vt.w};
+    const float gg[4] = {q.gn.x + q.gt.x, q.gn.y + q.gt.y, q.gn.z + q.gt.z, q.gn.w + q.gt.w};
+    const float bs[4] = {q.bb.x, q.bb.y, q.bb.z, q.bb.w};
+    float c0[4], c1[4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            vn[i] = ldg4(hrow + LIME_HIST_VC + d0 + 4 * i);
-            gn[i] = ldg4(hrow + LIME_HIST_GW + d0 + 4 * i);
-            vt[i] = ldg4(trow + d0 + 4 * i);
-            gt[i] = ldg4(trow + kD + d0 + 4 * i);
-            bb[i] = ldg4(C.gate_bias + d0 + 4 * i);
-        }
-        const float a = mid_s[u], w = whalf_s[u];
-        const float om = 1.0f - a;
-        const float oml = -om * kLn2;                  // d/da of the gate argument in natural units: g = -ln2 * g'
-        const float nwv = -kOScale * w;                // c1 = -256 w v f'
-        const float nso = -kOScale * om;               // 256 (1 - om s)
-        const float kq = kOScale * 0.25f * w * w * kLn2;   // + 256 (w^2/4) ln2 r' n  ( = -256 (w^2/4) f'' )
-        const float vv[8] = {vn[0].x + vt[0].x, vn[0].y + vt[0].y, vn[0].z + vt[0].z, vn[0].w + vt[0].w,
-                             vn[1].x + vt[1].x, vn[1].y + vt[1].y, vn[1].z + vt[1].z, vn[1].w + vt[1].w};
-        const float gg[8] = {gn[0].x + gt[0].x, gn[0].y + gt[0].y, gn[0].z + gt[0].z, gn[0].w + gt[0].w,
-                             gn[1].x + gt[1].x, gn[1].y + gt[1].y, gn[1].z + gt[1].z, gn[1].w + gt[1].w};
-        const float bs[8] = {bb[0].x, bb[0].y, bb[0].z, bb[0].w, bb[1].x, bb[1].y, bb[1].z, bb[1].w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            // s = sigmoid(x) = 1 / (1 + 2^z'),  z' = a g' + b'  (g', b' pre-scaled by -log2 e);  with g = -ln2 g':
-            //   f = om s,  f' = -s + om g s (1 - s),  f'' = g s (1 - s) (om g (1 - 2 s) - 2)
-            const float s = rcp_approx(ex2_approx(fmaf(a, gg[e], bs[e])) + 1.0f);
-            const float rp = fmaf(-s, s, s) * gg[e];               // s (1 - s) g'
-            const float f1 = fmaf(oml, rp, -s);                    // f'
-            const float n2 = fmaf(oml * gg[e], fmaf(-2.0f, s, 1.0f), -2.0f);
-            const float tm = fmaf(kq, rp * n2, fmaf(nso, s, kOScale));
-            c0[e] = vv[e] * tm;
-            c1[e] = (vv[e] * nwv) * f1;
-            ps[0] += c0[e];
-            ps[1] += c1[e];
-            ps[2] = fmaf(c0[e], c0[e], ps[2]);
-            ps[3] = fmaf(c0[e], c1[e], ps[3]);
-            ps[4] = fmaf(c1[e], c1[e], ps[4]);
-        }
+    for (int e = 0; e < 4; ++e) {
+        const float s = rcp_approx(ex2_approx(fmaf(c.a, gg[e], bs[e])) + 1.0f);
+        const float rp = fmaf(-s, s, s) * gg[e];               // s (1 - s) g'
+        const float f1 = fmaf(c.oml, rp, -s);                  // f'
+        const float n2 = fmaf(c.oml * gg[e], fmaf(-2.0f, s, 1.0f), -2.0f);
+        const float tm = fmaf(c.kq, rp * n2, fmaf(c.nso, s, kOScale));
+        c0[e] = vv[e] * tm;
+        c1[e] = (vv[e] * c.nwv) * f1;
+        ps[0] += c0[e];
+        ps[1] += c1[e];
+        ps[2] = fmaf(c0[e], c0[e], ps[2]);
+        ps[3] = fmaf(c0[e], c1[e], ps[3]);
+        ps[4] = fmaf(c1[e], c1[e], ps[4]);
     }
-    o_slot_wait(bars, kc, pass_iter);      // the slot is free once the MMAs of its previous use have drained it
-    if (ok) {
-        uint4 hi, lo, d1;
-        split2(c0[0], c0[1], hi.x, lo.x);
-        split2(c0[2], c0[3], hi.y, lo.y);
-        split2(c0[4], c0[5], hi.z, lo.z);
-        split2(c0[6], c0[7], hi.w, lo.w);
-        d1.x = pack_h2(c1[0], c1[1]);
-        d1.y = pack_h2(c1[2], c1[3]);
-        d1.z = pack_h2(c1[4], c1[5]);
-        d1.w = pack_h2(c1[6], c1[7]);
-        unsigned char *ob = base + OFF_O + tc::sw128_offset(u, 4 * h + c4);     // Up is a multiple of 8: same swizzle phase in the 3 images
-        *reinterpret_cast<uint4 *>(ob) = hi;
-        *reinterpret_cast<uint4 *>(ob + (size_t)Up * 128) = lo;
-        *reinterpret_cast<uint4 *>(ob + (size_t)Up * 256) = d1;
-    }
-    // Row sums over the 4 chunk lanes of a row, then added to the row's accumulator of this stage parity.  No atomics
-    // (bit-reproducible results): a row belongs to one task per stage, and the tasks of stages kc - 2 and kc are ordered
-    // by the ring (this task has just observed the completion of stage kc - 2's MMAs, which follow its arrivals).
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        ps[i] += __shfl_xor_sync(0xffffffffu, ps[i], 8);
-        ps[i] += __shfl_xor_sync(0xffffffffu, ps[i], 16);
-    }
-    if (c4 == 0 && u < nrows) {
-        float *acc = sum_s + (h * kH + u) * 8;
-        const float4 a0 = *reinterpret_cast<const float4 *>(acc);
-        *reinterpret_cast<float4 *>(acc) = make_float4(a0.x + ps[0], a0.y + ps[1], a0.z + ps[2], a0.w + ps[3]);
-        acc[4] += ps[4];
-    }
+    split2(c0[0], c0[1], hi0, lo0);
+    split2(c0[2], c0[3], hi1, lo1);
+    d0 = pack_h2(c1[0], c1[1]);
+    d1 = pack_h2(c1[2], c1[3]);
 }
 
 // Candidate-aware attention weights a[u][c] (layers.py:66-81) of one work unit.  LPC lanes share a candidate, a lane owns
@@ -450,6 +470,7 @@ __device__ __forceinline__ void front_hist(const ScoreArgs &args, unsigned char 
 
 __device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char *ub, int lane) {
     const LimeNewsCache &C = args.cache;
+    const uint32_t tab_row0 = (blockIdx.x % (unsigned)(C.tab_replicas > 0 ? C.tab_replicas : 1)) * (uint32_t)(C.num_buckets * C.num_buckets);
     const LimeImpressions &I = args.imp;
     const int nb = C.num_buckets, T = C.num_topics;
     int *info = reinterpret_cast<int *>(ub + UB_INFO);
@@ -489,6 +510,7 @@ __device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char 
         cscal[c * 4 + 2] = m1.y + __ldg(ctr + LIME_CAND_SCAL + 5);
         cscal[c * 4 + 3] = m1.z + __ldg(ctr + LIME_CAND_SCAL + 6);
         if (!(m0.z <= kWAbsMax)) flags |= 4;       // beyond the fp16 operand range: exact kernel
+        prefetch_l2_bulk(reinterpret_cast<const unsigned char *>(C.cand16) + (size_t)n * (2 * kC16), 2 * kC16);
     }
     __syncwarp();
     // distinct bucket pairs of the unit's candidates (all-pairs scan of <= 39 keys, two candidates per lane)
@@ -514,12 +536,17 @@ __device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char 
         nbp = min(min(nbp, kMaxBp), kTriples - cnt);
     }
     __syncwarp();
-    // operand row table: source element offset (bit 31: ctab16) and destination byte offset inside an image
+    // operand row table: source byte offset inside cand16 (bucket-pair rows follow the news rows) and destination byte
+    // offset inside an image
     const int nt = cnt + nbp;
     for (int ri = lane; ri < 3 * nt; ri += 32) {
         const int j = ri / 3, k = ri - 3 * j;
-        const uint32_t src = j < cnt ? (uint32_t)cnews[j] * (uint32_t)kC16 + (uint32_t)(k * kD)
-                                     : (0x80000000u | ((uint32_t)btab[j - cnt] * (uint32_t)kC16 + (uint32_t)(k * kD)));
+#ifdef LIME_TC_DIAG_WROW0        // timing diagnostic only (wrong results): every candidate copies news 1..8 -> L2 hits, no DRAM
+        const uint32_t row = j < cnt ? (uint32_t)(1 + (j & 7)) : (uint32_t)C.news_num + tab_row0 + (uint32_t)btab[j - cnt];
+#else
+        const uint32_t row = j < cnt ? (uint32_t)cnews[j] : (uint32_t)C.news_num + tab_row0 + (uint32_t)btab[j - cnt];
+#endif
+        const uint32_t src = row * (uint32_t)(2 * kC16) + (uint32_t)(k * 2 * kD);        // bytes
         const int m = m_row(j, k);
         wrow[ri] = make_uint2(src, (uint32_t)((m >> 3) * 1024 + (m & 7) * 128));
     }
@@ -571,6 +598,8 @@ __device__ __forceinline__ void front_dedup(const ScoreArgs &args, unsigned char
     const bool isfa = ha < H && fa == ha, isfb = hb < H && fb == hb;
     const unsigned b0 = __ballot_sync(0xffffffffu, isfa), b1 = __ballot_sync(0xffffffffu, isfb);
     const unsigned lt = (1u << lane) - 1u;
+    if (isfa) prefetch_l2_bulk(args.cache.hist_vg + (size_t)k1a * (2 * kD), 2 * kD * 4);
+    if (isfb) prefetch_l2_bulk(args.cache.hist_vg + (size_t)k1b * (2 * kD), 2 * kD * 4);
     if (isfa) {
         const int u = __popc(b0 & lt);
         unews[u] = k1a;
@@ -603,8 +632,12 @@ __device__ __forceinline__ void front_dedup(const ScoreArgs &args, unsigned char
 }
 
 __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs args) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // Every shared-memory pointer below is derived from this array by pointer arithmetic only (no integer round trip), so
+    // the compiler keeps the shared state space and emits LDS / STS instead of generic loads; the operand tiles need
+    // the 1024-byte alignment of the 128-byte swizzle, which the declaration requests and the first thread verifies.
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *base = smem_raw;
+    if (threadIdx.x == 0 && (tc::smem_u32(smem_raw) & 1023u) != 0) __trap();
     float2 *tab_s = reinterpret_cast<float2 *>(base + OFF_TAB);
     float *t_s = reinterpret_cast<float *>(base + OFF_T);
     float *sum_s = reinterpret_cast<float *>(base + OFF_SUM);
@@ -624,9 +657,14 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
     const int H = I.max_history;
     const int T = C.num_topics;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const __half *cand16 = reinterpret_cast<const __half *>(C.cand16);
-    const __half *ctab16 = reinterpret_cast<const __half *>(C.ctab16);
+    const unsigned char *w16 = reinterpret_cast<const unsigned char *>(C.cand16);   // news rows, then the nb^2 bucket-pair rows
 
+    // this CTA's copy of the bucket-pair tables (history role; the candidate role's copy sits in the tail of cand16)
+    const int nb2 = C.num_buckets * C.num_buckets;
+    const int rep = (int)(blockIdx.x % (unsigned)(C.tab_replicas > 0 ? C.tab_replicas : 1));
+    const float *htab = C.htab_vg + (size_t)rep * nb2 * (2 * kD);
+    float *bias_s = reinterpret_cast<float *>(base + OFF_BIAS);
+    for (int i = tid; i < kD; i += kThreads) bias_s[i] = C.gate_bias[i];
     if (tid == 0) {
         for (int s = 0; s < 4; ++s) {
             tc::mbar_init(bars + B_WFULL + s, kCompute);           // every compute thread, once its copies (if any) have landed
@@ -701,10 +739,9 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             // unit's last MMA): it lands during the attention phase
             for (int st = 0; st < 2; ++st) {
                 w_slot_wait(bars, st, pass_iter);
-                if (warp / kCopyTasks == st) copy_task(base, cand16, ctab16, wrow, n3, st, warp % kCopyTasks, lane);
+                copy_task(base, w16, wrow, n3, st, warp, lane);
                 cp_async_mbar_arrive_noinc(bars + B_WFULL + st);
             }
-            for (int i = tid; i < 2 * kH * 8; i += kCompute) sum_s[i] = 0.0f;
             // ---------------- phase 1: candidate-aware attention weights a[u][c] (layers.py:66-81) ------
             // lanes per candidate = the smallest power of two that covers the U rows with 4 rows per lane
             if (U <= 8)       attention<2>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
@@ -756,29 +793,77 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             LIME_TICK(3);
 
             // ---------------- operand production + candidate copies -----------------------------------------
-            // per stage s: kCopyTasks copy tasks for stage s + 2 and one production task per row group of stage s, dealt
-            // round-robin to the 7 warps (the deal continues across stages, so short histories keep every warp busy)
+            // per stage s: every warp copies its share of the candidate operand of stage s + 2, then produces 32 dims of
+            // its 8 rows
             {
-                const int per = kCopyTasks + ngroups;
-                int first = warp;                      // this warp's first task index inside the stage
+                const int j = lane >> 3, q = lane & 7;
+                const int npass = (8 * ((warp + kCWarps) >> 1) + (((warp + kCWarps) & 1) ? 2 : 0)) < U ? 2 : 1;   // warp-uniform
+                RowCtx rc[2];
+                int urow[2];
+                float ps[2][5];
+                Quad qn[2];
+                unsigned char *orow[2];
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    const int vw = warp + kCWarps * p, x = 4 * (vw & 1) + j;
+                    urow[p] = 8 * (vw >> 1) + (x >> 1) + 4 * (x & 1);
+                    row_ctx_init(rc[p], C, bias_s, htab, p < npass ? urow[p] : U, U, unews, utab, mid_s, whalf_s);
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) ps[p][i] = 0.0f;
+                    quad_load(qn[p], rc[p], 4 * q);                   // stage 0
+                    orow[p] = base + OFF_O + (rc[p].ok ? (urow[p] >> 3) * 1024 + (urow[p] & 7) * 128 : 0) + 8 * (q & 1);
+                }
                 for (int s = 0; s < kStages; ++s) {
-                    if (s + 2 < kStages) w_slot_wait(bars, s + 2, pass_iter);
-                    for (int idx = first; idx < per; idx += kCWarps) {
-                        if (idx < kCopyTasks) {
-                            if (s + 2 < kStages) copy_task(base, cand16, ctab16, wrow, n3, s + 2, idx, lane);
-                        } else {
-                            produce_task(base, C, s, idx - kCopyTasks, U, Up, lane, unews, utab, mid_s, whalf_s, sum_s, bars, pass_iter);
+                    if (s + 2 < kStages) {
+                        w_slot_wait(bars, s + 2, pass_iter);
+                        LIME_TICK(10);
+                        copy_task(base, w16, wrow, n3, s + 2, warp, lane);
+                        cp_async_mbar_arrive_noinc(bars + B_WFULL + ((s + 2) & 3));
+                        LIME_TICK(11);
+                    }
+                    const int d = 32 * s + 4 * q;
+                    uint2 hi[2], lo[2], d1[2];
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) {
+                        if (p < npass) {
+                            const Quad qa = qn[p];
+                            quad_load(qn[p], rc[p], d + 32);          // the same quad of the next stage
+                            if (rc[p].ok && d < kD) quad_eval(qa, rc[p], ps[p], hi[p].x, hi[p].y, lo[p].x, lo[p].y, d1[p].x, d1[p].y);
                         }
                     }
-                    if (s + 2 < kStages) cp_async_mbar_arrive_noinc(bars + B_WFULL + ((s + 2) & 3));
-                    o_slot_wait(bars, s, pass_iter);
+                    LIME_TICK(12);
+                    o_slot_wait(bars, s, pass_iter);      // the slot is free once the MMAs of its previous use have drained it
+                    LIME_TICK(13);
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) {
+                        if (p < npass && rc[p].ok && d < kD) {
+                            // Up is a multiple of 8: the three images share the swizzle phase of the row
+                            unsigned char *ob = orow[p] + (((uint32_t)(4 * (s & 1) + (q >> 1)) ^ (uint32_t)(urow[p] & 7)) << 4);
+                            *reinterpret_cast<uint2 *>(ob) = hi[p];
+                            *reinterpret_cast<uint2 *>(ob + (size_t)Up * 128) = lo[p];
+                            *reinterpret_cast<uint2 *>(ob + (size_t)Up * 256) = d1[p];
+                        }
+                    }
                     tc::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(bars + B_OFULL + (s & 1));
-                    // continue the deal: the next stage's task `first` is the one after this warp's last of this stage
-                    int nxt = first;
-                    while (nxt < per) nxt += kCWarps;
-                    first = nxt - per;
+                    LIME_TICK(14);
+                }
+                // row sums over the 8 quad lanes of a row (fixed order: bit-reproducible)
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    if (p < npass) {
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            ps[p][i] += __shfl_xor_sync(0xffffffffu, ps[p][i], 1);
+                            ps[p][i] += __shfl_xor_sync(0xffffffffu, ps[p][i], 2);
+                            ps[p][i] += __shfl_xor_sync(0xffffffffu, ps[p][i], 4);
+                        }
+                        if (q == 0 && rc[p].ok) {
+                            *reinterpret_cast<float4 *>(sum_s + urow[p] * 8) = make_float4(ps[p][0], ps[p][1], ps[p][2], ps[p][3]);
+                            sum_s[urow[p] * 8 + 4] = ps[p][4];
+                        }
+                    }
                 }
             }
             LIME_TICK(4);
@@ -794,8 +879,20 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             const uint64_t bdesc = tc::smem_desc_sw128(sb + OFF_O);
             for (int kc = 0; kc < kStages; ++kc) {
                 const int s = kc & 3, h = kc & 1;
+#ifdef LIME_TC_PHASE_CLOCKS
+                const long long tw0 = clock64();
+#endif
                 tc::mbar_wait(bars + B_WFULL + s, (pass_iter * w_uses(s) + (uint32_t)(kc >> 2)) & 1u, 300 + kc);
+#ifdef LIME_TC_PHASE_CLOCKS
+                const long long tw1 = clock64();
+#endif
                 tc::mbar_wait(bars + B_OFULL + h, (pass_iter * o_uses(h) + (uint32_t)(kc >> 1)) & 1u, 400 + kc);
+#ifdef LIME_TC_PHASE_CLOCKS
+                if (lane == 0) {
+                    atomicAdd(&g_phase_clocks[0], (unsigned long long)(tw1 - tw0));
+                    atomicAdd(&g_phase_clocks[1], (unsigned long long)(clock64() - tw1));
+                }
+#endif
                 tc::fence_after_sync();
                 if (lane == 0) {
                     const int ksteps = kc < kStages - 1 ? 2 : (kD - 32 * (kStages - 1)) / 16;
@@ -832,7 +929,6 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             const uint32_t taddr = tmem + ((uint32_t)(32 * qd) << 16);
             const int nblocks = (U + 7) >> 3;
             const int b0 = paired ? hb : 0, bstep = paired ? 2 : 1;
-            for (int i = tid; i < U * 8; i += kCompute) sum_s[i] += sum_s[kH * 8 + i];      // even + odd stages
             // pass A: the bucket-pair rows of this quadrant publish (p0, p1) per unique row
             if (10 * qd + 10 > cnt && 10 * qd < cnt + nbp) {
                 const int jt = 3 * (j - cnt) + k;

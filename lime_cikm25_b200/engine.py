@@ -11,9 +11,10 @@ Layout of the per-news cache in HBM (fp32; DESIGN.md "HBM layout"):
                           7 scalars (1200..1206), tq 50x10 (1208..1707), qb 10 (1708..1717)
   hist_tab  [nb*nb, 800]  the same two history vectors for T[bf,bl] = W_f tanh(dense(E_f|E_l)) + b
   cand_tab  [nb*nb, 1208] the same candidate block for T[bf,bl] (+ the constants coming from Q.bias)
-  cand16    [news, 2400]  fp16: w1 w2 w3 of cand_rows as hi/lo pairs (x = hi + lo to 2^-22), the M operand
-                          of the tensor-core scoring kernel, streamed by cp.async without touching registers
-  ctab16    [nb*nb, 2400] fp16: the same for cand_tab
+  cand16    [news + R*nb*nb, 2400]  fp16 [hi | lo][w1 w2 w3][400]: cand_rows as hi/lo pairs (x = hi + lo to 2^-22),
+                          the M operand of the tensor-core scoring kernel, streamed by cp.async without touching
+                          registers; the tail holds R = 32 copies of the same for cand_tab (ctab16): every CTA of the
+                          scoring kernel reads its own copy of the hot bucket-pair rows (hist_tab likewise)
 
 A LIME news vector is v(news, bf, bl) = vc[news] + T[bf, bl]; everything the scoring kernel needs is
 linear in v, so it is cached as a per-news part plus a per-bucket-pair part.
@@ -34,8 +35,16 @@ HIST_GW, HIST_T, HIST_TOPIC_ID, HIST_GW_ABSMAX = 400, 800, 850, 851
 CAND_SCAL, CAND_TQ, CAND_NFOLD, CAND_TOPIC_ID, CAND_ABSMAX = 1200, 1208, 1207, 1718, 1207
 F16_SAFE = 32768.0 / ops.CAND16_SCALE      # |w| beyond this leaves the fp16 operand range after scaling
 TOPIC_TAB_LD, MAX_TOPICS, TC_MAX_HISTORY = 12, 1024, 56
+TAB_REPLICAS = 32      # copies of the bucket-pair tables read by the tensor-core kernel (spreads the hot rows over L2 slices)
 TOPIC, TOPIC_LD, HEADS = 50, 52, 10
 LOG2E = 1.4426950408889634
+
+
+def interleave_vg(rows):
+    """[n, >= 800] fp32 (v | g) -> [n, 800] with v and g interleaved in groups of 4 dims (v0..3 g0..3 v4..7 ...):
+    the tensor-core scoring kernel fetches both operands of 4 dims with one 256-bit load (layout copy: plumbing)."""
+    n = rows.shape[0]
+    return torch.stack([rows[:, :D].reshape(n, D // 4, 4), rows[:, D:2 * D].reshape(n, D // 4, 4)], dim=2).reshape(n, 2 * D).contiguous()
 
 
 def _fingerprint(params):
@@ -310,6 +319,8 @@ class ScoringEngine:
         ctab = torch.zeros(nb2, CTAB_LD, **f32)
         ops.linear(htab[:, :D], G, bias=cconst, out=ctab[:, :CAND_NFOLD], n=CAND_NFOLD)
         F["hist_tab"], F["cand_tab"] = htab, ctab
+        F["hist_tab_rep"] = htab.unsqueeze(0).repeat(TAB_REPLICAS, 1, 1).contiguous()      # plumbing copy
+        F["htab_vg"] = interleave_vg(htab).unsqueeze(0).repeat(TAB_REPLICAS, 1, 1).contiguous()
         tabmax = torch.empty(2, nb2, **f32)
         ops.row_absmax(htab[:, D:], tabmax[0])
         F["ctab16"] = ops.split_f16_pairs(ctab, 3, absmax=tabmax[1])
@@ -349,9 +360,16 @@ class ScoringEngine:
         return hist, cand
 
     def split_candidates(self, cand_rows):
-        """cand16 [n, 2400] fp16: the folded candidate vectors as hi/lo pairs; stamps max |w| of every row
-        into cand_rows[:, 1207] (the scoring kernel sends rows beyond the fp16 range to the exact kernel)."""
-        return ops.split_f16_pairs(cand_rows, 3, absmax=cand_rows[:, CAND_ABSMAX])
+        """cand16 [n + nb*nb, 2400] fp16: the folded candidate vectors as hi/lo pairs, followed by the nb*nb
+        bucket-pair rows (ctab16) -- one operand array, so the scoring kernel addresses candidate rows and
+        bucket-pair rows alike; stamps max |w| of every row into cand_rows[:, 1207] (the scoring kernel sends
+        rows beyond the fp16 range to the exact kernel)."""
+        F = self.fold()
+        n, nb2 = cand_rows.shape[0], F["ctab16"].shape[0]
+        c16 = torch.empty(n + TAB_REPLICAS * nb2, 2400, dtype=torch.float16, device=cand_rows.device)
+        ops.split_f16_pairs(cand_rows, 3, absmax=cand_rows[:, CAND_ABSMAX], out=c16[:n])
+        c16[n:].view(TAB_REPLICAS, nb2, 2400).copy_(F["ctab16"].unsqueeze(0).expand(TAB_REPLICAS, nb2, 2400))
+        return c16
 
     @staticmethod
     def news_meta(hist_rows, cand_rows):
@@ -364,17 +382,18 @@ class ScoringEngine:
         meta[:, 3:7].copy_(cand_rows[:, CAND_SCAL + 3:CAND_SCAL + 7])
         return meta
 
-    def cache_struct(self, hist_rows, cand_rows, cand16=None, meta=None):
+    def cache_struct(self, hist_rows, cand_rows, cand16=None, meta=None, hist_vg=None):
         F = self.fold()
         cfg = self.cfg
         table, T = self.topic_table()
         return LimeNewsCache(
             hist_rows=hist_rows.data_ptr(), cand_rows=cand_rows.data_ptr(),
-            hist_tab=F["hist_tab"].data_ptr(), cand_tab=F["cand_tab"].data_ptr(),
+            hist_tab=F["hist_tab_rep"].data_ptr(), cand_tab=F["cand_tab"].data_ptr(), tab_replicas=TAB_REPLICAS,
             gate_bias=F["gate_bias"].data_ptr(), un_prefix=F["un_prefix"].data_ptr(),
             topic_table=table.data_ptr() if table is not None else None, num_topics=T,
             cand16=cand16.data_ptr() if cand16 is not None else None, ctab16=F["ctab16"].data_ptr(),
             news_meta=meta.data_ptr() if meta is not None else None,
+            hist_vg=hist_vg.data_ptr() if hist_vg is not None else None, htab_vg=F["htab_vg"].data_ptr(),
             topic_logit_absmax=self._topic_absmax, tc_tables_ok=F["tc_tables_ok"],
             tab_gw_absmax=F["tab_gw_absmax"],
             news_num=hist_rows.shape[0], num_buckets=cfg.num_buckets,
@@ -392,16 +411,17 @@ class ScoringEngine:
         return hist_rows[:, :D] + F["hist_tab"][:, :D].index_select(0, idx.reshape(-1))
 
     def score(self, hist_rows, cand_rows, dimp, prefix_main, tail_start=None, prefix_tail=None,
-              pair_index_base=0, out=None, cand16=None, meta=None):
+              pair_index_base=0, out=None, cand16=None, meta=None, hist_vg=None):
         """Launch the fused scoring kernel over a DeviceImpressions set -> fp32 scores [P].
         ``cand16`` / ``meta``: split_candidates(cand_rows) and news_meta(hist_rows, cand_rows) if the caller keeps
         them (NewsVectorCache does); derived here otherwise."""
         lib = _lib.require_device()
-        if (cand16 is None or meta is None) and dimp.max_history <= TC_MAX_HISTORY:
+        if (cand16 is None or meta is None or hist_vg is None) and dimp.max_history <= TC_MAX_HISTORY:
             cand16 = self.split_candidates(cand_rows)
             meta = self.news_meta(hist_rows, cand_rows)
-        cache = self.cache_struct(hist_rows, cand_rows, cand16, meta)
-        self._keepalive = (cand16, meta)      # derived operands stay referenced until the next call (the launch is asynchronous)
+            hist_vg = interleave_vg(hist_rows)
+        cache = self.cache_struct(hist_rows, cand_rows, cand16, meta, hist_vg)
+        self._keepalive = (cand16, meta, hist_vg)      # derived operands stay referenced until the next call (the launch is asynchronous)
         st = dimp.struct()
         if out is None:
             out = torch.empty(dimp.num_pairs, dtype=torch.float32, device=hist_rows.device)

@@ -199,13 +199,16 @@ def row_absmax(m, out):
 CAND16_SCALE = 1024.0      # LIME_CAND16_SCALE
 
 
-def split_f16_pairs(src, blocks=3, absmax=None, scale=CAND16_SCALE):
-    """lime_split_f16_pairs: fp32 [rows, >= blocks*400] (row-major view) -> fp16 [rows, blocks*800] with, per
-    block of 400 columns, the hi halves then the lo halves (operand format of the tensor-core scoring
-    kernel).  ``absmax``: optional 1-D (strided) fp32 view receiving max |x| per row."""
+def split_f16_pairs(src, blocks=3, absmax=None, scale=CAND16_SCALE, out=None):
+    """lime_split_f16_pairs: fp32 [rows, >= blocks*400] (row-major view) -> fp16 [rows, blocks*800]: the hi halves
+    of the ``blocks`` vectors, then their lo halves (operand format of the tensor-core scoring kernel).
+    ``absmax``: optional 1-D (strided) fp32 view receiving max |x| per row; ``out``: optional contiguous
+    destination (a row range of a larger operand array)."""
     lib = _lib.require_device()
     rows = src.shape[0]
-    dst = torch.empty(rows, blocks * 800, dtype=torch.float16, device=src.device)
+    dst = out if out is not None else torch.empty(rows, blocks * 800, dtype=torch.float16, device=src.device)
+    if dst.dtype != torch.float16 or not dst.is_contiguous() or tuple(dst.shape) != (rows, blocks * 800):
+        raise _lib.LimeError("split_f16_pairs: out must be a contiguous fp16 [rows, blocks*800] tensor")
     check(lib.lime_split_f16_pairs(_ptr(src, torch.float32, "src"), _rowmajor(src, "src"), rows, blocks, float(scale), dst.data_ptr(),
                                    _ptr(absmax, torch.float32, "absmax") if absmax is not None else None,
                                    absmax.stride(0) if absmax is not None else 0, _stream()), "lime_split_f16_pairs")

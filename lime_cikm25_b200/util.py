@@ -47,13 +47,14 @@ class NewsVectorCache:
     cand_rows: torch.Tensor     # [news_num, 1720] fp32
     cand16: torch.Tensor = None  # [news_num, 2400] fp16 hi/lo pairs of cand_rows[:, :1200] (tensor-core scoring operand)
     meta: torch.Tensor = None    # [news_num, 8] fp32 per-news scalars of the tensor-core kernel's phase 0
+    hist_vg: torch.Tensor = None  # [news_num, 800] fp32: vc | gw of hist_rows interleaved by 4 dims (one 256-bit load per quad)
 
     @property
     def news_num(self):
         return int(self.hist_rows.shape[0])
 
     def nbytes(self):
-        return self.hist_rows.numel() * 4 + self.cand_rows.numel() * 4 + (self.cand16.numel() * 2 if self.cand16 is not None else 0) + (self.meta.numel() * 4 if self.meta is not None else 0)
+        return self.hist_rows.numel() * 4 + self.cand_rows.numel() * 4 + (self.cand16.numel() * 2 if self.cand16 is not None else 0) + (self.meta.numel() * 4 if self.meta is not None else 0) + (self.hist_vg.numel() * 4 if self.hist_vg is not None else 0)
 
 
 def build_news_cache(model, news: NewsTable, device=None, chunk=2048) -> NewsVectorCache:
@@ -66,7 +67,9 @@ def build_news_cache(model, news: NewsTable, device=None, chunk=2048) -> NewsVec
                                               t(news.subCategory), chunk=chunk)
         cand16 = model.scoring.split_candidates(cand)
         meta = model.scoring.news_meta(hist, cand)
-    return NewsVectorCache(hist, cand, cand16, meta)
+        from .engine import interleave_vg
+        hist_vg = interleave_vg(hist)
+    return NewsVectorCache(hist, cand, cand16, meta, hist_vg)
 
 
 def _tail(total_pairs, batch_size):
@@ -84,7 +87,7 @@ def score_impressions(model, cache: NewsVectorCache, dimp: DeviceImpressions, ba
     tail_start, prefix_tail = _tail(total, batch_size)
     return model.scoring.score(cache.hist_rows, cache.cand_rows, dimp, prefix_main=batch_size,
                                tail_start=tail_start, prefix_tail=prefix_tail,
-                               pair_index_base=pair_index_base, out=out, cand16=cache.cand16, meta=cache.meta)
+                               pair_index_base=pair_index_base, out=out, cand16=cache.cand16, meta=cache.meta, hist_vg=cache.hist_vg)
 
 
 def evaluate_device(model, cache, dimp, batch_size, pair_index_base=0, total_pairs=None, group=None,

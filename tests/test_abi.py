@@ -31,7 +31,7 @@ def test_abi_version(lib):
 
 def test_struct_sizes_match_header(lib):
     # the ctypes mirrors against sizeof() as compiled from include/lime_b200.h
-    assert ctypes.sizeof(_lib.LimeNewsCache) == lib.lime_sizeof_news_cache() == 10 * 8 + 12 * 4
+    assert ctypes.sizeof(_lib.LimeNewsCache) == lib.lime_sizeof_news_cache() == 12 * 8 + 12 * 4
     assert ctypes.sizeof(_lib.LimeImpressions) == lib.lime_sizeof_impressions() == 11 * 8 + 3 * 4 + 4
 
 
