@@ -61,7 +61,8 @@ constexpr int kTile = LIME_TC_TILE_C;           // candidates per unit handed ou
 constexpr int kTriples = 40;                    // M rows = 3 x (candidates + distinct bucket pairs): 10 triples per TMEM quadrant
 constexpr int kMaxBp = 10;                      // distinct bucket pairs of a unit that fit beside its candidates
 constexpr int kAS = kTriples;                   // row stride of a_s / t_s  ([u][c])
-constexpr int kStages = 13;                     // 32-wide K stages over D = 400 (the last holds 16 dims)
+constexpr int kStages = 13;                     // 32-wide candidate-operand stages over D = 400 (the last holds 16 dims)
+constexpr int kOStages = 7;                     // 64-wide O stages
 constexpr int kWTile = 32768, kWImg = 16384;    // one 64-dim candidate tile = hi image + lo image of 128 rows x 128 B
 constexpr int kGroups = 7;                      // row groups of 8 unique history rows (56 / 8)
 constexpr int kCopyTasks = kCWarps;             // candidate-operand copy shares per stage: every compute warp takes one
@@ -132,7 +133,7 @@ enum { M_TMEM = 0 };
 // unit info ints
 enum { UI_UNIT = 0, UI_IMP = 1, UI_PAIR0 = 2, UI_CNT = 3, UI_U = 4, UI_NUN = 5, UI_FLAGS = 6, UI_NBP = 7 };
 // barrier indices (uint64 each)
-enum { B_WFULL = 0, B_WFREE = 4, B_OFULL = 8, B_OFREE = 10, B_ACCUM = 12 };
+enum { B_WFULL = 0, B_OFULL = 8, B_OFREE = 10, B_ACCUM = 12 };
 
 // Phase timing (diagnostic): thread 0 of every CTA accumulates clock64() deltas per phase; lime_score_phase_clocks reads
 // and clears the totals.  Slots: 2 attention, 3 centres, 4 operand production (incl. ring waits), 5 wait for the last
@@ -183,7 +184,6 @@ __device__ __forceinline__ int m_row(int j, int k) { return 32 * (j / 10) + 3 * 
 
 // uses of a ring slot per pass: W slot s (stage kc & 3), O half h (stage kc & 1)
 __device__ __forceinline__ uint32_t w_uses(int s) { return s == 0 ? 4u : 3u; }
-__device__ __forceinline__ uint32_t o_uses(int h) { return h == 0 ? 7u : 6u; }
 
 // pack 2 fp32 -> fp16x2 (round to nearest), returns also the rounded values as fp32
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -231,19 +231,16 @@ __device__ __forceinline__ void copy_task(unsigned char *base, const unsigned ch
         }
     }
 }
-// Ring protocol (both rings): EVERY compute warp waits for and arrives on every stage's barriers, whether or not it
-// holds a task of the stage -- an mbarrier parity wait is only meaningful for a waiter that has observed every earlier
-// phase (a warp that skipped stages could be two phases behind and alias the parity), and a phase cannot run ahead of
-// a warp whose arrival it needs.
-__device__ __forceinline__ void w_slot_wait(uint64_t *bars, int kc, uint32_t pass_iter) {
-    const int s = kc & 3;
-    const uint32_t fill = pass_iter * w_uses(s) + (uint32_t)(kc >> 2);
-    if (fill >= 1) tc::mbar_wait(bars + B_WFREE + s, (fill - 1) & 1u, 100 + kc);
-}
-__device__ __forceinline__ void o_slot_wait(uint64_t *bars, int kc, uint32_t pass_iter) {
-    const int h = kc & 1;
-    const uint32_t fill = pass_iter * o_uses(h) + (uint32_t)(kc >> 1);
-    if (fill >= 1) tc::mbar_wait(bars + B_OFREE + h, (fill - 1) & 1u, 200 + kc);
+// Ring protocol.  The O operand is ONE 64-dim tile, produced and consumed once per O stage (7 per unit); the candidate
+// operand keeps four 32-dim slots (two tiles), two per O stage.  EVERY compute warp waits for and arrives on every O
+// stage, whether or not it holds rows -- an mbarrier parity wait is only meaningful for a waiter that has observed
+// every earlier phase, and a phase cannot run ahead of a warp whose arrival it needs.  The completion of O stage kb's
+// MMAs (O_FREE) also frees its two candidate slots: there is no separate barrier for them.
+// (Measured: a stage costs one memory + barrier round trip of 2-3 thousand clocks almost independently of its size,
+// so 7 fat stages beat 13 thin ones.)
+__device__ __forceinline__ void o_free_wait(uint64_t *bars, int kb, uint32_t pass_iter) {
+    const uint32_t fill = pass_iter * (uint32_t)kOStages + (uint32_t)kb;
+    if (fill >= 1) tc::mbar_wait(bars + B_OFREE, (fill - 1) & 1u, 200 + kb);
 }
 
 // ---- history operand (N side) -------------------------------------------------------------------------------------
@@ -253,8 +250,8 @@ __device__ __forceinline__ void o_slot_wait(uint64_t *bars, int kc, uint32_t pas
 // into opposite 64-byte halves of the bank space -- the 8-byte stores of a warp are conflict-free.  Everything that
 // depends on the row only (cache pointers, expansion point, half width) is hoisted out of the stage loop, the five row
 // sums stay in registers for the whole unit, and the global loads run one stage ahead of the arithmetic.
-struct Quad {                // 4 dims of a cache row: per-news part (DRAM), bucket-pair part (L2) and gate bias (shared memory)
-    float4 vn, gn, vt, gt, bb;
+struct Quad {                // 4 dims of a cache row: per-news part (DRAM) and bucket-pair part (L2); the gate bias is
+    float4 vn, gn, vt, gt;   // read from shared memory when the quad is evaluated
 };
 // v and g of 4 dims with ONE 256-bit load (hist_vg / htab_vg interleave them): two global loads per quad instead of four,
 // so the loads of the next stage and of the current one never share a scoreboard slot
@@ -270,7 +267,7 @@ struct RowCtx {
 };
 __device__ __forceinline__ void quad_load(Quad &q, const RowCtx &c, int d) {
 #ifdef LIME_TC_DIAG_NOLOAD       // timing diagnostic only (wrong results): no global loads in the production loop
-    q.vn = q.gn = q.vt = q.gt = q.bb = make_float4(0.01f * d, 0.02f, 0.03f, 0.04f);
+    q.vn = q.gn = q.vt = q.gt = make_float4(0.01f * d, 0.02f, 0.03f, 0.04f);
     return;
 #endif
     if (c.ok && d < kD) {
@@ -284,7 +281,7 @@ __device__ __forceinline__ void quad_load(Quad &q, const RowCtx &c, int d) {
 #else
         ldg8(c.trow + 2 * d, q.vt, q.gt);
 #endif
-        q.bb = *reinterpret_cast<const float4 *>(c.bias + d);      // shared memory
+
     }
 }
 __device__ __forceinline__ void row_ctx_init(RowCtx &rc, const LimeNewsCache &C, const float *bias_s, const float *htab, int u,
@@ -308,11 +305,12 @@ __device__ __forceinline__ void row_ctx_init(RowCtx &rc, const LimeNewsCache &C,
 // 4 elements: s = sigmoid(x) = 1 / (1 + 2^z'),  z' = a g' + b'  (g', b' pre-scaled by -log2 e);  with g = -ln2 g':
 //   f = om s,  f' = -s + om g s (1 - s),  f'' = g s (1 - s) (om g (1 - 2 s) - 2)
 //   c0 = 256 v (1 - f - (w^2/4) f''),  c1 = -256 w v f'
-__device__ __forceinline__ void quad_eval(const Quad &q, const RowCtx &c, float (&ps)[5], uint32_t &hi0, uint32_t &hi1,
+__device__ __forceinline__ void quad_eval(const Quad &q, const RowCtx &c, int d, float (&ps)[5], uint32_t &hi0, uint32_t &hi1,
                                           uint32_t &lo0, uint32_t &lo1, uint32_t &d0, uint32_t &d1) {
     const float vv[4] = {q.vn.x + q.vt.x, q.vn.y + q.vt.y, q.vn.z + q.vt.z, q.vn.w + q.vt.w};
     const float gg[4] = {q.gn.x + q.gt.x, q.gn.y + q.gt.y, q.gn.z + q.gt.z, q.gn.w + q.gt.w};
-    const float bs[4] = {q.bb.x, q.bb.y, q.bb.z, q.bb.w};
+    const float4 bb = *reinterpret_cast<const float4 *>(c.bias + d);      // shared memory
+    const float bs[4] = {bb.x, bb.y, bb.z, bb.w};
     float c0[4], c1[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -340,7 +338,7 @@ __device__ __forceinline__ void quad_eval(const Quad &q, const RowCtx &c, float 
 // exponentials stay in registers for both softmaxes.  Head logits come pre-scaled by log2(e) from the topic-pair table
 // (no max pass: the host checks the table's |logit| bound); masked slots (mask == 0 -> -1e9, layers.py:72) contribute
 // exactly 0 unless every slot is masked, in which case both softmaxes are uniform over the H slots.
-template <int LPC>
+template <int LPC, int NW>
 __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, int cnt, int nun, int warp, int lane,
                                           const int *ctopic, const int *utopic, const int *umask, const float *umult,
                                           float *a_s) {
@@ -356,7 +354,7 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
         w[i] = (in && umask[u] != 0) ? mu[i] : 0.0f;
         tp[i] = in ? utopic[u] : 0;
     }
-    for (int c0 = CPW * warp; c0 < cnt; c0 += CPW * kCWarps) {
+    for (int c0 = CPW * warp; c0 < cnt; c0 += CPW * NW) {
         const int c = c0 + g;
         const bool cvalid = c < cnt;
         const int cc = cvalid ? c : cnt - 1;
@@ -468,7 +466,7 @@ __device__ __forceinline__ void front_hist(const ScoreArgs &args, unsigned char 
     __syncwarp();
 }
 
-__device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char *ub, int lane) {
+__device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char *ub, int lane, bool pf = true) {
     const LimeNewsCache &C = args.cache;
     const uint32_t tab_row0 = (blockIdx.x % (unsigned)(C.tab_replicas > 0 ? C.tab_replicas : 1)) * (uint32_t)(C.num_buckets * C.num_buckets);
     const LimeImpressions &I = args.imp;
@@ -510,7 +508,7 @@ __device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char 
         cscal[c * 4 + 2] = m1.y + __ldg(ctr + LIME_CAND_SCAL + 5);
         cscal[c * 4 + 3] = m1.z + __ldg(ctr + LIME_CAND_SCAL + 6);
         if (!(m0.z <= kWAbsMax)) flags |= 4;       // beyond the fp16 operand range: exact kernel
-        prefetch_l2_bulk(reinterpret_cast<const unsigned char *>(C.cand16) + (size_t)n * (2 * kC16), 2 * kC16);
+        if (pf) prefetch_l2_bulk(reinterpret_cast<const unsigned char *>(C.cand16) + (size_t)n * (2 * kC16), 2 * kC16);
     }
     __syncwarp();
     // distinct bucket pairs of the unit's candidates (all-pairs scan of <= 39 keys, two candidates per lane)
@@ -565,7 +563,7 @@ __device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char 
 // number of equal slots = its multiplicity (overall and inside the two GraphSAGE prefixes); one ballot pair then
 // compacts the unique rows in slot order.
 __device__ __forceinline__ void front_dedup(const ScoreArgs &args, unsigned char *ub, int lane, const int *hkn, const int *hkt,
-                                            const int *htp, const float *hga) {
+                                            const int *htp, const float *hga, bool pf = true) {
     int *info = reinterpret_cast<int *>(ub + UB_INFO);
     if (info[UI_UNIT] >= args.imp.num_units) return;
     const int H = args.imp.max_history;
@@ -598,8 +596,8 @@ __device__ __forceinline__ void front_dedup(const ScoreArgs &args, unsigned char
     const bool isfa = ha < H && fa == ha, isfb = hb < H && fb == hb;
     const unsigned b0 = __ballot_sync(0xffffffffu, isfa), b1 = __ballot_sync(0xffffffffu, isfb);
     const unsigned lt = (1u << lane) - 1u;
-    if (isfa) prefetch_l2_bulk(args.cache.hist_vg + (size_t)k1a * (2 * kD), 2 * kD * 4);
-    if (isfb) prefetch_l2_bulk(args.cache.hist_vg + (size_t)k1b * (2 * kD), 2 * kD * 4);
+    if (pf && isfa) prefetch_l2_bulk(args.cache.hist_vg + (size_t)k1a * (2 * kD), 2 * kD * 4);
+    if (pf && isfb) prefetch_l2_bulk(args.cache.hist_vg + (size_t)k1b * (2 * kD), 2 * kD * 4);
     if (isfa) {
         const int u = __popc(b0 & lt);
         unews[u] = k1a;
@@ -666,14 +664,9 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
     float *bias_s = reinterpret_cast<float *>(base + OFF_BIAS);
     for (int i = tid; i < kD; i += kThreads) bias_s[i] = C.gate_bias[i];
     if (tid == 0) {
-        for (int s = 0; s < 4; ++s) {
-            tc::mbar_init(bars + B_WFULL + s, kCompute);           // every compute thread, once its copies (if any) have landed
-            tc::mbar_init(bars + B_WFREE + s, 1);
-        }
-        for (int h = 0; h < 2; ++h) {
-            tc::mbar_init(bars + B_OFULL + h, kCWarps);             // one arrival per compute warp
-            tc::mbar_init(bars + B_OFREE + h, 1);
-        }
+        for (int s = 0; s < 4; ++s) tc::mbar_init(bars + B_WFULL + s, kCompute);   // every compute thread, once its copies (if any) have landed
+        tc::mbar_init(bars + B_OFULL, kCWarps);                 // one arrival per compute warp
+        tc::mbar_init(bars + B_OFREE, 1);
         tc::mbar_init(bars + B_ACCUM, 1);
         tc::mbar_fence_init();
     }
@@ -735,19 +728,18 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
 
         // ================= roles ======================================================================
         if (warp < kCWarps) {
-            // the candidate operand of the first two stages goes out now (all ring slots are free since the previous
+            // the candidate operand of the first two O stages goes out now (all four slots are free since the previous
             // unit's last MMA): it lands during the attention phase
-            for (int st = 0; st < 2; ++st) {
-                w_slot_wait(bars, st, pass_iter);
+            for (int st = 0; st < 4; ++st) {
                 copy_task(base, w16, wrow, n3, st, warp, lane);
                 cp_async_mbar_arrive_noinc(bars + B_WFULL + st);
             }
             // ---------------- phase 1: candidate-aware attention weights a[u][c] (layers.py:66-81) ------
             // lanes per candidate = the smallest power of two that covers the U rows with 4 rows per lane
-            if (U <= 8)       attention<2>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
-            else if (U <= 16) attention<4>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
-            else if (U <= 32) attention<8>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
-            else              attention<16>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
+            if (U <= 8)       attention<2, kCWarps>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
+            else if (U <= 16) attention<4, kCWarps>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
+            else if (U <= 32) attention<8, kCWarps>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
+            else              attention<16, kCWarps>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
             bar_compute();
             LIME_TICK(2);
 
@@ -793,15 +785,13 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             LIME_TICK(3);
 
             // ---------------- operand production + candidate copies -----------------------------------------
-            // per stage s: every warp copies its share of the candidate operand of stage s + 2, then produces 32 dims of
-            // its 8 rows
+            // per O stage: 64 dims of this warp's rows, then its share of the candidate operand of the next O stage
             {
                 const int j = lane >> 3, q = lane & 7;
                 const int npass = (8 * ((warp + kCWarps) >> 1) + (((warp + kCWarps) & 1) ? 2 : 0)) < U ? 2 : 1;   // warp-uniform
                 RowCtx rc[2];
                 int urow[2];
                 float ps[2][5];
-                Quad qn[2];
                 unsigned char *orow[2];
 #pragma unroll
                 for (int p = 0; p < 2; ++p) {
@@ -810,44 +800,66 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
                     row_ctx_init(rc[p], C, bias_s, htab, p < npass ? urow[p] : U, U, unews, utab, mid_s, whalf_s);
 #pragma unroll
                     for (int i = 0; i < 5; ++i) ps[p][i] = 0.0f;
-                    quad_load(qn[p], rc[p], 4 * q);                   // stage 0
                     orow[p] = base + OFF_O + (rc[p].ok ? (urow[p] >> 3) * 1024 + (urow[p] & 7) * 128 : 0) + 8 * (q & 1);
                 }
-                for (int s = 0; s < kStages; ++s) {
-                    if (s + 2 < kStages) {
-                        w_slot_wait(bars, s + 2, pass_iter);
-                        LIME_TICK(10);
-                        copy_task(base, w16, wrow, n3, s + 2, warp, lane);
-                        cp_async_mbar_arrive_noinc(bars + B_WFULL + ((s + 2) & 3));
-                        LIME_TICK(11);
-                    }
-                    const int d = 32 * s + 4 * q;
-                    uint2 hi[2], lo[2], d1[2];
+                // one quad of each 32-dim half of the stage per lane and row: dims 64 kb + 4 q and 64 kb + 32 + 4 q
+                auto store_quad = [&](int p, int h, uint2 hi, uint2 lo, uint2 d1) {
+                    // Up is a multiple of 8: the three images share the swizzle phase of the row
+                    unsigned char *ob = orow[p] + (((uint32_t)(4 * h + (q >> 1)) ^ (uint32_t)(urow[p] & 7)) << 4);
+                    *reinterpret_cast<uint2 *>(ob) = hi;
+                    *reinterpret_cast<uint2 *>(ob + (size_t)Up * 128) = lo;
+                    *reinterpret_cast<uint2 *>(ob + (size_t)Up * 256) = d1;
+                };
+                // steps (stage, row pass) in order (0,0) [(0,1)] (1,0) ...: the loads of a step are issued one step ahead
+                Quad na, nb;
+                quad_load(na, rc[0], 4 * q);
+                quad_load(nb, rc[0], 32 + 4 * q);
+                for (int kb = 0; kb < kOStages; ++kb) {
+                    const int dA = 64 * kb + 4 * q, dB = dA + 32;
+                    const bool okA = dA < kD, okB = dB < kD;
 #pragma unroll
                     for (int p = 0; p < 2; ++p) {
                         if (p < npass) {
-                            const Quad qa = qn[p];
-                            quad_load(qn[p], rc[p], d + 32);          // the same quad of the next stage
-                            if (rc[p].ok && d < kD) quad_eval(qa, rc[p], ps[p], hi[p].x, hi[p].y, lo[p].x, lo[p].y, d1[p].x, d1[p].y);
-                        }
-                    }
-                    LIME_TICK(12);
-                    o_slot_wait(bars, s, pass_iter);      // the slot is free once the MMAs of its previous use have drained it
-                    LIME_TICK(13);
-#pragma unroll
-                    for (int p = 0; p < 2; ++p) {
-                        if (p < npass && rc[p].ok && d < kD) {
-                            // Up is a multiple of 8: the three images share the swizzle phase of the row
-                            unsigned char *ob = orow[p] + (((uint32_t)(4 * (s & 1) + (q >> 1)) ^ (uint32_t)(urow[p] & 7)) << 4);
-                            *reinterpret_cast<uint2 *>(ob) = hi[p];
-                            *reinterpret_cast<uint2 *>(ob + (size_t)Up * 128) = lo[p];
-                            *reinterpret_cast<uint2 *>(ob + (size_t)Up * 256) = d1[p];
+                            const Quad ca = na, cb = nb;
+                            if (p + 1 < npass) {                      // next step: the lane's second row, same stage
+                                quad_load(na, rc[1], dA);
+                                quad_load(nb, rc[1], dB);
+                            } else {                                  // next step: the first row, next stage
+                                quad_load(na, rc[0], dA + 64);
+                                quad_load(nb, rc[0], dB + 64);
+                            }
+                            uint2 hi, lo, d1;
+                            const bool a0 = rc[p].ok && okA, b0 = rc[p].ok && okB;
+                            if (a0) quad_eval(ca, rc[p], dA, ps[p], hi.x, hi.y, lo.x, lo.y, d1.x, d1.y);
+                            if (p == 0) {
+                                LIME_TICK(12);
+                                o_free_wait(bars, kb, pass_iter);     // the tile is free once the MMAs of the previous stage have drained it
+                                LIME_TICK(13);
+                            }
+                            if (a0) store_quad(p, 0, hi, lo, d1);
+                            if (b0) {
+                                quad_eval(cb, rc[p], dB, ps[p], hi.x, hi.y, lo.x, lo.y, d1.x, d1.y);
+                                store_quad(p, 1, hi, lo, d1);
+                            }
                         }
                     }
                     tc::fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(bars + B_OFULL + (s & 1));
+                    if (lane == 0) tc::mbar_arrive(bars + B_OFULL);
                     LIME_TICK(14);
+                    // the two candidate slots of the previous O stage are free (its MMAs completed: observed above): the
+                    // next O stage's candidate operand goes into them, one production stage ahead of its MMAs
+                    if (kb >= 1) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int st = 2 * kb + 2 + h;
+                            if (st < kStages) {
+                                copy_task(base, w16, wrow, n3, st, warp, lane);
+                                cp_async_mbar_arrive_noinc(bars + B_WFULL + (st & 3));
+                            }
+                        }
+                    }
+                    LIME_TICK(11);
                 }
                 // row sums over the 8 quad lanes of a row (fixed order: bit-reproducible)
 #pragma unroll
@@ -877,35 +889,40 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             const uint32_t sb = tc::smem_u32(base);
             const uint32_t idesc1 = tc::idesc_f16_f32(128, 3 * Up), idesc2 = tc::idesc_f16_f32(128, Up);
             const uint64_t bdesc = tc::smem_desc_sw128(sb + OFF_O);
-            for (int kc = 0; kc < kStages; ++kc) {
-                const int s = kc & 3, h = kc & 1;
+            for (int kb = 0; kb < kOStages; ++kb) {
 #ifdef LIME_TC_PHASE_CLOCKS
                 const long long tw0 = clock64();
 #endif
-                tc::mbar_wait(bars + B_WFULL + s, (pass_iter * w_uses(s) + (uint32_t)(kc >> 2)) & 1u, 300 + kc);
+                tc::mbar_wait(bars + B_OFULL, (pass_iter * (uint32_t)kOStages + (uint32_t)kb) & 1u, 400 + kb);
 #ifdef LIME_TC_PHASE_CLOCKS
-                const long long tw1 = clock64();
+                if (lane == 0) atomicAdd(&g_phase_clocks[1], (unsigned long long)(clock64() - tw0));
 #endif
-                tc::mbar_wait(bars + B_OFULL + h, (pass_iter * o_uses(h) + (uint32_t)(kc >> 1)) & 1u, 400 + kc);
+                for (int h = 0; h < 2; ++h) {
+                    const int kc = 2 * kb + h, s = kc & 3;
+                    if (kc >= kStages) break;
 #ifdef LIME_TC_PHASE_CLOCKS
-                if (lane == 0) {
-                    atomicAdd(&g_phase_clocks[0], (unsigned long long)(tw1 - tw0));
-                    atomicAdd(&g_phase_clocks[1], (unsigned long long)(clock64() - tw1));
-                }
+                    const long long tw1 = clock64();
 #endif
-                tc::fence_after_sync();
-                if (lane == 0) {
-                    const int ksteps = kc < kStages - 1 ? 2 : (kD - 32 * (kStages - 1)) / 16;
-                    const uint32_t wt = sb + OFF_W + (uint32_t)((kc >> 1) & 1) * kWTile;
-                    const uint64_t ahi = tc::smem_desc_sw128(wt), alo = tc::smem_desc_sw128(wt + kWImg);
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint64_t k2 = (uint64_t)(2 * (2 * h + ks));   // 32 bytes per K step of 16
-                        tc::mma_f16(tmem, ahi + k2, bdesc + k2, idesc1, (kc | ks) != 0);
-                        tc::mma_f16(tmem + 3 * Up, alo + k2, bdesc + k2, idesc2, (kc | ks) != 0);
+                    tc::mbar_wait(bars + B_WFULL + s, (pass_iter * w_uses(s) + (uint32_t)(kc >> 2)) & 1u, 300 + kc);
+#ifdef LIME_TC_PHASE_CLOCKS
+                    if (lane == 0) atomicAdd(&g_phase_clocks[0], (unsigned long long)(clock64() - tw1));
+#endif
+                    tc::fence_after_sync();
+                    if (lane == 0) {
+                        const int ksteps = kc < kStages - 1 ? 2 : (kD - 32 * (kStages - 1)) / 16;
+                        const uint32_t wt = sb + OFF_W + (uint32_t)(kb & 1) * kWTile;
+                        const uint64_t ahi = tc::smem_desc_sw128(wt), alo = tc::smem_desc_sw128(wt + kWImg);
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t k2 = (uint64_t)(2 * (2 * h + ks));   // 32 bytes per K step of 16
+                            tc::mma_f16(tmem, ahi + k2, bdesc + k2, idesc1, (kc | ks) != 0);
+                            tc::mma_f16(tmem + 3 * Up, alo + k2, bdesc + k2, idesc2, (kc | ks) != 0);
+                        }
                     }
-                    tc::mma_commit(bars + B_WFREE + s);
-                    tc::mma_commit(bars + B_OFREE + h);
-                    if (kc == kStages - 1) tc::mma_commit(bars + B_ACCUM);
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    tc::mma_commit(bars + B_OFREE);
+                    if (kb == kOStages - 1) tc::mma_commit(bars + B_ACCUM);
                 }
                 __syncwarp();
             }
