@@ -58,7 +58,9 @@ extern "C" {
 #define LIME_CTAB_LD   1208 /* per bucket pair: [ w1T | w2T | w3T | scalT(8) ]                 */
 /* Tensor-core scoring path (score_tc.cu): history rows per impression, candidates per work unit. */
 #define LIME_TC_MAX_HISTORY 56
-#define LIME_TC_TILE_C      34  /* + the unit's distinct (freshness, lifetime) bucket pairs <= 40 operand-row triples */
+#define LIME_TC_TILE_C      39  /* candidates of a unit + its distinct (freshness, lifetime) bucket pairs <= 40 operand-row
+                                   triples: the host sizes the units accordingly (engine.build_units), a unit that still does
+                                   not fit is re-scored by the exact kernel */
 #define LIME_TOPIC_TAB_LD   12  /* 10 head logits of a (candidate topic, history topic) pair, padded */
 #define LIME_TC_MAX_TOPICS  1024
 

@@ -35,6 +35,7 @@ HIST_GW, HIST_T, HIST_TOPIC_ID, HIST_GW_ABSMAX = 400, 800, 850, 851
 CAND_SCAL, CAND_TQ, CAND_NFOLD, CAND_TOPIC_ID, CAND_ABSMAX = 1200, 1208, 1207, 1718, 1207
 F16_SAFE = 32768.0 / ops.CAND16_SCALE      # |w| beyond this leaves the fp16 operand range after scaling
 TOPIC_TAB_LD, MAX_TOPICS, TC_MAX_HISTORY = 12, 1024, 56
+TC_TRIPLES = 40         # operand-row triples of a tensor-core work unit: candidates + distinct bucket pairs
 TAB_REPLICAS = 32      # copies of the bucket-pair tables read by the tensor-core kernel (spreads the hot rows over L2 slices)
 TOPIC, TOPIC_LD, HEADS = 50, 52, 10
 LOG2E = 1.4426950408889634
@@ -443,18 +444,58 @@ def choose_tile_c(max_history):
     return tc
 
 
-def build_units(cand_off, tile_c):
-    """Work units of the scoring kernel: every impression's candidate list is cut into runs of at
-    most ``tile_c`` consecutive candidates.  Returns (unit_imp, unit_pair0, unit_count) as int64."""
+def _host_bucket_pairs(fresh, life, nb):
+    """Approximate (freshness, lifetime) bucket pair per candidate on the host -- used ONLY to size work units (how many
+    distinct pairs a run of candidates holds); the scoring kernel derives the exact buckets itself and sends a unit that
+    still does not fit to the exact kernel, so a knife-edge disagreement costs speed, never correctness."""
+    def b(x):
+        x = np.maximum(np.asarray(x, np.float32), np.float32(1.0))
+        v = np.log(x).astype(np.float32) * np.float32(1.0 / math.log(86400.0)) * np.float32(nb / 7.0)
+        return np.clip(v.astype(np.int64), 0, nb - 1)
+    return b(fresh) * nb + b(life)
+
+
+def build_units(cand_off, tile_c, cand_bp=None, triples=None):
+    """Work units of the scoring kernel: every impression's candidate list is cut into runs of consecutive candidates.
+    Without ``cand_bp``: runs of at most ``tile_c``.  With ``cand_bp`` (bucket-pair id per candidate) and ``triples``
+    (operand-row triples of the tensor-core kernel, 40): greedy runs with candidates + distinct bucket pairs <= triples
+    (the pairs ride along as extra operand rows), at most ``tile_c`` candidates.
+    Returns (unit_imp, unit_pair0, unit_count) as int64."""
     cand_off = np.asarray(cand_off, np.int64)
     counts = np.diff(cand_off)
-    nun = (counts + tile_c - 1) // tile_c
-    unit_imp = np.repeat(np.arange(counts.shape[0], dtype=np.int64), nun)
-    first = np.cumsum(nun) - nun
-    kk = np.arange(unit_imp.shape[0], dtype=np.int64) - first[unit_imp]
-    unit_pair0 = cand_off[:-1][unit_imp] + kk * tile_c
-    unit_count = np.minimum(tile_c, counts[unit_imp] - kk * tile_c)
-    return unit_imp, unit_pair0, unit_count
+    if cand_bp is None:
+        nun = (counts + tile_c - 1) // tile_c
+        unit_imp = np.repeat(np.arange(counts.shape[0], dtype=np.int64), nun)
+        first = np.cumsum(nun) - nun
+        kk = np.arange(unit_imp.shape[0], dtype=np.int64) - first[unit_imp]
+        unit_pair0 = cand_off[:-1][unit_imp] + kk * tile_c
+        unit_count = np.minimum(tile_c, counts[unit_imp] - kk * tile_c)
+        return unit_imp, unit_pair0, unit_count
+    cand_bp = np.asarray(cand_bp, np.int64)
+    ui, up, uc = [], [], []
+    # impressions whose candidates + (at most that many) pairs fit one unit need no scan
+    safe = 2 * counts <= triples
+    for i in range(counts.shape[0]):
+        n, o = int(counts[i]), int(cand_off[i])
+        if n == 0:
+            continue
+        if safe[i]:
+            ui.append(i); up.append(o); uc.append(n)
+            continue
+        b = cand_bp[o:o + n].tolist()
+        j = 0
+        while j < n:
+            seen, c = set(), 0
+            while j + c < n and c < tile_c:
+                x = b[j + c]
+                if c + 1 + len(seen) + (x not in seen) > triples:
+                    break
+                seen.add(x)
+                c += 1
+            c = max(c, 1)
+            ui.append(i); up.append(o + j); uc.append(c)
+            j += c
+    return np.asarray(ui, np.int64), np.asarray(up, np.int64), np.asarray(uc, np.int64)
 
 
 class DeviceImpressions:
@@ -488,13 +529,18 @@ class DeviceImpressions:
         self.work_counter = torch.zeros(int(_lib.load().lime_score_scratch_ints(self.num_units)), dtype=torch.int32, device=dev)
         return self
 
-    def __init__(self, imp, device, tile_c=None, cand_remaining=None):
+    def __init__(self, imp, device, tile_c=None, cand_remaining=None, num_buckets=10):
         H = imp.hist_news.shape[1]
         self.tile_c = int(tile_c or choose_tile_c(H))
         self.max_history = H
         self.num_pairs = int(imp.cand_news.shape[0])
         self.num_impressions = int(imp.hist_news.shape[0])
-        unit_imp, unit_pair0, unit_count = build_units(imp.cand_off, self.tile_c)
+        if H <= TC_MAX_HISTORY and tile_c is None and num_buckets is not None:
+            # tensor-core path: a unit's candidates and its distinct bucket pairs share the 40 operand-row triples
+            bp = _host_bucket_pairs(imp.cand_fresh, imp.cand_life, int(num_buckets))
+            unit_imp, unit_pair0, unit_count = build_units(imp.cand_off, self.tile_c, bp, TC_TRIPLES)
+        else:
+            unit_imp, unit_pair0, unit_count = build_units(imp.cand_off, self.tile_c)
         self.num_units = int(unit_imp.shape[0])
         self.host = dict(
             hist_news=np.ascontiguousarray(imp.hist_news, np.int32),

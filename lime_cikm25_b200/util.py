@@ -207,7 +207,7 @@ def compute_scores(model, corpus, batch_size, mode, result_file, dataset):
         imp.labels = _read_truth(mode + "/ref/truth-%s.txt" % dataset, imp.cand_off)
     with torch.no_grad():
         cache = build_news_cache(model, news, device)
-        dimp = DeviceImpressions(imp, device, cand_remaining=remaining)
+        dimp = DeviceImpressions(imp, device, cand_remaining=remaining, num_buckets=config.num_buckets)
         metrics, det = evaluate_impressions(model, cache, dimp, batch_size, return_details=True)
     write_rank_file(result_file, det["ranks"].cpu(), imp.cand_off)
     if labeled:

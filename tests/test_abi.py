@@ -38,9 +38,9 @@ def test_struct_sizes_match_header(lib):
 def test_smem_budget_query(lib):
     from lime_cikm25_b200.engine import choose_tile_c
     assert lib.lime_score_smem_bytes(50, 48) < 232448
-    assert choose_tile_c(50) == 34 and choose_tile_c(56) == 34          # tensor-core path: 3 * (34 + bucket pairs) <= 120 M rows
+    assert choose_tile_c(50) == 39 and choose_tile_c(56) == 39          # tensor-core path: 3 * (candidates + bucket pairs) <= 120 M rows
     assert choose_tile_c(64) in (8, 16, 24, 32, 40, 48)                 # beyond 56 slots: exact kernel
-    assert lib.lime_score_smem_bytes(56, 34) <= 232448                  # the exact kernel doubles as the fallback
+    assert lib.lime_score_smem_bytes(56, 39) <= 232448                  # the exact kernel doubles as the fallback
     assert choose_tile_c(200) in (8, 16, 24, 32, 40, 48)
     assert lib.lime_score_scratch_ints(10) == 14
     assert lib.lime_score_smem_bytes(200, choose_tile_c(200)) <= 232448
