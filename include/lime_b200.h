@@ -101,7 +101,10 @@ int lime_embed_pe(const float *E, int64_t vocab, const int32_t *ids, int64_t row
 /* nn.MultiheadAttention core of the TransformerEncoderLayer (:244-247), no mask:
  * qkv [n_news*T, 3*d] (q | k | v) -> ctx [n_news*T, d], softmax(q k^T / sqrt(d/nhead)) v per head.
  * Supported: T in {32, 128}, d/nhead <= 32.                                                      */
-int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, void *stream);
+int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, float p_drop, uint64_t seed,
+             int64_t news0, void *stream);
+/* p_drop / seed: dropout on the attention weights (training; 0 in eval), stateless mask of (seed, news0 + news, head, i, j)
+ * -- news0 is the global index of the call's first news, so a chunked call sees the mask of the whole batch */
 /* nn.LayerNorm over the last dim (eps as given). */
 int lime_layernorm(const float *x, int64_t ldx, const float *gamma, const float *beta, float *y,
                    int64_t ldy, int64_t rows, int d, float eps, void *stream);
@@ -290,6 +293,7 @@ int lime_scatter_add_rows(const float *src, int64_t lds, const int32_t *ids, int
                           int64_t ldt, int64_t table_rows, void *stream);
 /* backward of lime_mha: dctx [n_news*T, d] -> dqkv [n_news*T, 3d] */
 int lime_mha_bwd(const float *qkv, const float *dctx, float *dqkv, int64_t n_news, int T, int d, int nhead,
+                 float p_drop, uint64_t seed, int64_t news0,
                  void *stream);
 /* backward of lime_intent_pool: dout [n, D] -> dpre, de [n, k, D], dw2 [D] (accumulated) */
 int lime_intent_pool_bwd(const float *pre, const float *e, const float *w2, const float *dout, int64_t lddo,

@@ -52,7 +52,7 @@ PROTOTYPES = {
     "lime_linear_bf16": (C.c_int, _LINEAR),
     "lime_gemm_strided": (C.c_int, [P, I64, I64, P, I64, I64, P, I64, C.c_int, C.c_int, C.c_int, F32, P]),
     "lime_embed_pe": (C.c_int, [P, I64, P, I64, C.c_int, C.c_int, P, P, P]),
-    "lime_mha": (C.c_int, [P, P, I64, C.c_int, C.c_int, C.c_int, P]),
+    "lime_mha": (C.c_int, [P, P, I64, C.c_int, C.c_int, C.c_int, F32, C.c_uint64, I64, P]),
     "lime_layernorm": (C.c_int, [P, I64, P, P, P, I64, I64, C.c_int, F32, P]),
     "lime_layernorm_meanpool": (C.c_int, [P, P, P, P, I64, I64, C.c_int, C.c_int, F32, P]),
     "lime_topic_rep": (C.c_int, [P, P, P, P, P, P, I64, P, I64, C.c_int, P]),
@@ -82,7 +82,7 @@ PROTOTYPES = {
     "lime_layernorm_bwd": (C.c_int, [P, I64, P, P, I64, C.c_int, P, I64, P, P, I64, C.c_int, F32, P]),
     "lime_gather_rows": (C.c_int, [P, I64, I64, P, I64, C.c_int, P, I64, P]),
     "lime_scatter_add_rows": (C.c_int, [P, I64, P, I64, C.c_int, P, I64, I64, P]),
-    "lime_mha_bwd": (C.c_int, [P, P, P, I64, C.c_int, C.c_int, C.c_int, P]),
+    "lime_mha_bwd": (C.c_int, [P, P, P, I64, C.c_int, C.c_int, C.c_int, F32, C.c_uint64, I64, P]),
     "lime_intent_pool_bwd": (C.c_int, [P, P, P, P, I64, P, P, P, I64, C.c_int, C.c_int, P]),
     "lime_content_fuse_bwd": (C.c_int, [P, P, P, I64, I64, C.c_int, P, P, P]),
     "lime_dropout": (C.c_int, [P, I64, P, I64, I64, C.c_int, F32, C.c_uint64, P]),

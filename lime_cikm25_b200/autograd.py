@@ -130,19 +130,21 @@ class Gather(torch.autograd.Function):
 
 
 class MHA(torch.autograd.Function):
+    """nn.MultiheadAttention core; p_drop / seed: dropout on the attention weights (same stateless mask both ways)."""
+
     @staticmethod
-    def forward(ctx, qkv, n, T, d, heads):
+    def forward(ctx, qkv, n, T, d, heads, p_drop=0.0, seed=0):
         out = torch.empty((qkv.shape[0], d), dtype=torch.float32, device=qkv.device)
-        ops.mha(qkv, out, n, T, d, heads)
-        ctx.dims = (n, T, d, heads)
+        ops.mha(qkv, out, n, T, d, heads, p_drop, seed)
+        ctx.dims = (n, T, d, heads, float(p_drop), int(seed))
         ctx.save_for_backward(qkv)
         return out
 
     @staticmethod
     def backward(ctx, dctx):
         (qkv,) = ctx.saved_tensors
-        n, T, d, heads = ctx.dims
-        return ops.mha_bwd(qkv, _c(dctx), n, T, d, heads), None, None, None, None
+        n, T, d, heads, p_drop, seed = ctx.dims
+        return ops.mha_bwd(qkv, _c(dctx), n, T, d, heads, p_drop, seed), None, None, None, None, None, None
 
 
 class IntentPool(torch.autograd.Function):

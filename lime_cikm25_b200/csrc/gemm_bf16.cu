@@ -53,9 +53,11 @@ __global__ void __launch_bounds__(GB_THREADS, 2)
 linear_bf16_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ W, int64_t ldw,
                    const float *__restrict__ bias, const float *__restrict__ residual, int64_t ldr,
                    float *__restrict__ C, int64_t ldc, int64_t m, int n, int k, int bn, int act, uint32_t idesc) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *base = reinterpret_cast<unsigned char *>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // pointer arithmetic on the declared array only (an integer round trip would lose the shared state space and turn
+    // every access below into a generic load / store); the declaration requests the swizzle's 1024-byte alignment
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *base = smem_raw;
+    if (threadIdx.x == 0 && (tc::smem_u32(smem_raw) & 1023u) != 0) __trap();
     uint64_t *bars = reinterpret_cast<uint64_t *>(base + GB_STAGES * GB_STAGE_BYTES);
     uint64_t *full = bars, *empty = bars + GB_STAGES, *accum = bars + 2 * GB_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * GB_STAGES + 1);
@@ -239,9 +241,11 @@ __global__ void __launch_bounds__(GB_THREADS, 2)
 gemm_bf16_general_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ B, int64_t ldb,
                          float *__restrict__ C, int64_t ldc, int64_t m, int n, int64_t k, int64_t k_per_split, int bn,
                          float alpha, int accumulate, uint32_t idesc) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *base = reinterpret_cast<unsigned char *>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // pointer arithmetic on the declared array only (an integer round trip would lose the shared state space and turn
+    // every access below into a generic load / store); the declaration requests the swizzle's 1024-byte alignment
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *base = smem_raw;
+    if (threadIdx.x == 0 && (tc::smem_u32(smem_raw) & 1023u) != 0) __trap();
     uint64_t *bars = reinterpret_cast<uint64_t *>(base + GB_STAGES * GB_STAGE_BYTES);
     uint64_t *full = bars, *empty = bars + GB_STAGES, *accum = bars + 2 * GB_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * GB_STAGES + 1);
@@ -350,11 +354,8 @@ extern "C" int lime_linear_bf16(const float *A, int64_t lda, const float *W, int
     const int64_t mtiles = (m + GB_M - 1) / GB_M;
     const int nt = (n + bn - 1) / bn;
     LIME_CHECK_ARG(mtiles * nt < (int64_t)1 << 31, "lime_linear_bf16: m too large for one launch (%lld rows)", (long long)m);
-    static bool attr_set = false;
-    if (!attr_set) {
-        LIME_CUDA(cudaFuncSetAttribute(linear_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM));
-        attr_set = true;
-    }
+    // per device and cheap: set on every call (a process-wide "done" flag would miss a second GPU or a second thread)
+    LIME_CUDA(cudaFuncSetAttribute(linear_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM));
     linear_bf16_kernel<<<(unsigned)(mtiles * nt), GB_THREADS, GB_SMEM, as_stream(stream)>>>(
         A, lda, W, ldw, bias, residual, ldr, C, ldc, m, n, k, bn, act, tc::idesc_bf16_f32(GB_M, bn));
     LIME_LAUNCH_CHECK("linear_bf16_kernel");
@@ -398,11 +399,7 @@ extern "C" int lime_gemm_bf16(const float *A, int64_t lda, int a_kmajor, const f
     dim3 grid((unsigned)tiles, (unsigned)splits);
 #define LIME_LAUNCH_GB(AK, BK)                                                                                         \
     do {                                                                                                               \
-        static bool attr = false;                                                                                      \
-        if (!attr) {                                                                                                   \
-            LIME_CUDA(cudaFuncSetAttribute(gemm_bf16_general_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM)); \
-            attr = true;                                                                                               \
-        }                                                                                                              \
+        LIME_CUDA(cudaFuncSetAttribute(gemm_bf16_general_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM)); \
         gemm_bf16_general_kernel<AK, BK><<<grid, GB_THREADS, GB_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k, kps, bn, alpha,   \
                                                                           accumulate, idesc);                          \
     } while (0)

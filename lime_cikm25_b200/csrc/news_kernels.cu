@@ -35,7 +35,8 @@ embed_pe_kernel(const float *__restrict__ E, int64_t vocab, const int32_t *__res
 // at the same time, so all K/V reads are warp broadcasts.  Online softmax in chunks of 8 keys.
 template <int T>
 __global__ void __launch_bounds__(128)
-mha_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int nhead, int hd, float scale) {
+mha_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int nhead, int hd, float scale, float p_drop,
+           uint64_t seed, int64_t news0) {
     constexpr int G = 128 / T;
     constexpr int HP = 32;
     __shared__ __align__(16) float Ks[G][T][HP];
@@ -72,6 +73,10 @@ mha_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int nh
         acc[e] = 0.0f;
     }
     float m = -INFINITY, l = 0.0f;
+    // dropout on the attention weights (nn.MultiheadAttention(dropout=p) inside nn.TransformerEncoderLayer,
+    // newsEncoders.py:244-247): P~ = P * keep / (1 - p) with the stateless mask of (seed, news, head, i, j); the
+    // softmax normaliser l keeps every term, only the value accumulation is masked
+    const uint64_t drop0 = (((uint64_t)(news0 + news) * nhead + head) * T + i) * T;
     for (int j0 = 0; j0 < T; j0 += 8) {
         float s[8];
 #pragma unroll
@@ -98,8 +103,9 @@ mha_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int nh
         for (int e = 0; e < HP; ++e) acc[e] *= corr;
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-            const float p = __expf(s[jj] - mn);
+            float p = __expf(s[jj] - mn);
             l += p;
+            if (p_drop > 0.0f) p *= drop_scale(seed, drop0 + j0 + jj, p_drop);
             const float4 *vr = reinterpret_cast<const float4 *>(&Vs[g][j0 + jj][0]);
 #pragma unroll
             for (int e4 = 0; e4 < HP / 4; ++e4) {
@@ -345,7 +351,8 @@ extern "C" int lime_embed_pe(const float *E, int64_t vocab, const int32_t *ids, 
     return 0;
 }
 
-extern "C" int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, void *stream) {
+extern "C" int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, float p_drop, uint64_t seed,
+                        int64_t news0, void *stream) {
     LIME_CHECK_ARG(qkv && ctx, "lime_mha: null argument");
     LIME_CHECK_ARG(nhead > 0 && d % nhead == 0 && d / nhead <= 32, "lime_mha: head dim %d unsupported (<= 32)", nhead ? d / nhead : -1);
     LIME_CHECK_ARG(T == 32 || T == 128, "lime_mha: T=%d unsupported (32 or 128)", T);
@@ -355,10 +362,10 @@ extern "C" int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int
     const float scale = 1.0f / sqrtf((float)hd);
     if (T == 32) {
         dim3 grid((nhead + 3) / 4, (unsigned)n_news);
-        mha_kernel<32><<<grid, 128, 0, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale);
+        mha_kernel<32><<<grid, 128, 0, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale, p_drop, seed, news0);
     } else {
         dim3 grid(nhead, (unsigned)n_news);
-        mha_kernel<128><<<grid, 128, 0, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale);
+        mha_kernel<128><<<grid, 128, 0, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale, p_drop, seed, news0);
     }
     LIME_LAUNCH_CHECK("mha_kernel");
     return 0;

@@ -256,7 +256,7 @@ __global__ void scatter_add_rows_kernel(const float *__restrict__ src, int64_t l
 template <int T>
 __global__ void __launch_bounds__(T)
 mha_bwd_kernel(const float *__restrict__ qkv, const float *__restrict__ dctx, float *__restrict__ dqkv, int d, int nhead,
-               int hd, float scale) {
+               int hd, float scale, float p_drop, uint64_t seed, int64_t news0) {
     constexpr int HP = 33;                    // head dim (<= 32) padded: conflict-free row reads
     extern __shared__ float sm[];
     float *Qs = sm, *Ks = Qs + T * HP, *Vs = Ks + T * HP, *Os = Vs + T * HP, *st = Os + T * HP;   // st: [3][T]
@@ -280,6 +280,8 @@ mha_bwd_kernel(const float *__restrict__ qkv, const float *__restrict__ dctx, fl
         q[e] = Qs[i * HP + e] * scale;
         o[e] = Os[i * HP + e];
     }
+    // attention-weight dropout of the forward (same stateless mask): O = (P * M) V, so dP = M * (dO V^T) and dV uses P * M
+    const uint64_t drop_nh = ((uint64_t)(news0 + news) * nhead + head) * T;
     // pass 1: row maximum
     float m = -INFINITY;
     for (int j = 0; j < T; ++j) {
@@ -305,6 +307,7 @@ mha_bwd_kernel(const float *__restrict__ qkv, const float *__restrict__ dctx, fl
         }
         const float p = expf(a - m);
         l += p;
+        if (p_drop > 0.0f) dp *= drop_scale(seed, (drop_nh + i) * T + j, p_drop);
         pd = fmaf(p, dp, pd);
         const float pdp = p * dp;
 #pragma unroll
@@ -343,10 +346,12 @@ mha_bwd_kernel(const float *__restrict__ qkv, const float *__restrict__ dctx, fl
             dp = fmaf(Os[r * HP + e], vj[e], dp);
         }
         const float p = expf(a - st[r]) * st[T + r];
-        const float ds = p * (dp - st[2 * T + r]) * scale;
+        const float mm = p_drop > 0.0f ? drop_scale(seed, (drop_nh + r) * T + i, p_drop) : 1.0f;
+        const float ds = p * (dp * mm - st[2 * T + r]) * scale;
+        const float pm = p * mm;
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-            dv[e] = fmaf(p, Os[r * HP + e], dv[e]);
+            dv[e] = fmaf(pm, Os[r * HP + e], dv[e]);
             dk[e] = fmaf(ds, Qs[r * HP + e], dk[e]);
         }
     }
@@ -561,7 +566,7 @@ extern "C" int lime_scatter_add_rows(const float *src, int64_t lds, const int32_
 }
 
 extern "C" int lime_mha_bwd(const float *qkv, const float *dctx, float *dqkv, int64_t n_news, int T, int d, int nhead,
-                            void *stream) {
+                            float p_drop, uint64_t seed, int64_t news0, void *stream) {
     LIME_CHECK_ARG(qkv && dctx && dqkv, "lime_mha_bwd: null argument");
     LIME_CHECK_ARG((T == 32 || T == 128) && d % nhead == 0 && d / nhead <= 32, "lime_mha_bwd: unsupported shape T=%d d=%d heads=%d", T, d, nhead);
     if (n_news <= 0) return 0;
@@ -571,14 +576,10 @@ extern "C" int lime_mha_bwd(const float *qkv, const float *dctx, float *dqkv, in
     dim3 grid(nhead, (unsigned)n_news);
     const size_t smem = sizeof(float) * (4 * (size_t)T * 33 + 3 * (size_t)T);
     if (T == 32) {
-        mha_bwd_kernel<32><<<grid, 32, smem, as_stream(stream)>>>(qkv, dctx, dqkv, d, nhead, hd, scale);
+        mha_bwd_kernel<32><<<grid, 32, smem, as_stream(stream)>>>(qkv, dctx, dqkv, d, nhead, hd, scale, p_drop, seed, news0);
     } else {
-        static bool attr = false;
-        if (!attr) {
-            LIME_CUDA(cudaFuncSetAttribute(mha_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
-        }
-        mha_bwd_kernel<128><<<grid, 128, smem, as_stream(stream)>>>(qkv, dctx, dqkv, d, nhead, hd, scale);
+        LIME_CUDA(cudaFuncSetAttribute(mha_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mha_bwd_kernel<128><<<grid, 128, smem, as_stream(stream)>>>(qkv, dctx, dqkv, d, nhead, hd, scale, p_drop, seed, news0);
     }
     LIME_LAUNCH_CHECK("mha_bwd_kernel");
     return 0;

@@ -58,7 +58,7 @@ def _check_geometry(cfg):
                 intent_num=3, attention_dim=400, category_embedding_dim=50, subCategory_embedding_dim=50,
                 lime_output_dim=400, fusion_method="concat", num_layers=1,
                 use_candidate_ware_clicked_news_attention=True, use_residual_connection=True,
-                click_predictor="dot_product")
+                click_predictor="dot_product", alpha=0.0)      # alpha != 0: the category-predictor auxiliary loss is not built
     for k, v in want.items():
         if getattr(cfg, k) != v:
             raise NotImplementedError("lime_cikm25_b200 supports %s=%r only (got %r)" % (k, v, getattr(cfg, k)))

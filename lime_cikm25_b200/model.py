@@ -17,6 +17,12 @@ from .engine import DeviceImpressions, ScoringEngine
 from .util import RemainingLifetimeWeighting
 
 
+def _rank():
+    """Data-parallel rank (0 without a process group): mixed into the dropout seed so the ranks draw different masks."""
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
 class Model(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -78,7 +84,7 @@ class Model(nn.Module):
                 self, user_category, user_subCategory, user_title_text, user_content_text, user_freshness,
                 user_user_topic_lifetime, user_history_mask, news_category, news_subCategory, news_title_text,
                 news_content_text, news_freshness, news_user_topic_lifetime, remaining_lifetime,
-                seed=int(getattr(self.config, "seed", 0)) * 1000003 + self._train_calls * 101)
+                seed=int(getattr(self.config, "seed", 0)) * 1000003 + self._train_calls * 101 + _rank() * 7919)
             self.news_encoder.auxiliary_loss = torch.zeros((), device=logits.device)   # category loss * alpha (= 0)
             self.news_encoder.base_news_encoder.auxiliary_loss = self.news_encoder.auxiliary_loss
             return logits

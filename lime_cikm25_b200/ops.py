@@ -89,10 +89,12 @@ def embed_pe(E, ids, T, pe, out):
     return out
 
 
-def mha(qkv, ctx, n_news, T, d, nhead):
+def mha(qkv, ctx, n_news, T, d, nhead, p_drop=0.0, seed=0):
     lib = _lib.require_device()
-    check(lib.lime_mha(_ptr(qkv, torch.float32, "qkv"), _ptr(ctx, torch.float32, "ctx"), n_news, T, d,
-                       nhead, _stream()), "lime_mha")
+    for lo in range(0, n_news, 65535):
+        hi = min(n_news, lo + 65535)
+        check(lib.lime_mha(qkv[lo * T:].data_ptr(), ctx[lo * T:].data_ptr(), hi - lo, T, d, nhead, float(p_drop),
+                           int(seed) & (2 ** 64 - 1), lo, _stream()), "lime_mha")
     return ctx
 
 
@@ -289,13 +291,13 @@ def scatter_add_rows(src, ids, dtable):
     return dtable
 
 
-def mha_bwd(qkv, dctx, n_news, T, d, nhead):
+def mha_bwd(qkv, dctx, n_news, T, d, nhead, p_drop=0.0, seed=0):
     lib = _lib.require_device()
     dqkv = torch.empty_like(qkv)
     for lo in range(0, n_news, 65535):
         hi = min(n_news, lo + 65535)
         check(lib.lime_mha_bwd(qkv[lo * T:].data_ptr(), dctx[lo * T:].data_ptr(), dqkv[lo * T:].data_ptr(), hi - lo, T, d,
-                               nhead, _stream()), "lime_mha_bwd")
+                               nhead, float(p_drop), int(seed) & (2 ** 64 - 1), lo, _stream()), "lime_mha_bwd")
     return dqkv
 
 

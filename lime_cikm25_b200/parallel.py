@@ -58,4 +58,4 @@ def all_reduce_sums(sums, group=None):
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
     s = sums.tolist()
-    return tuple(x / s[4] for x in s[:4])
+    return tuple((x / s[4]) if s[4] > 0 else float("nan") for x in s[:4])

@@ -3,11 +3,13 @@ sample, trainer.py:131-146): the same math as the eval path, composed from diffe
 forward and backward are liblime_b200.so kernels (autograd.py).  No news-vector cache here: weights
 change every step, so every news of the mini-batch is encoded (B * (H + N) encodes, as the reference).
 
-Dropout: the reference drops activations at 7 sites with torch's RNG, which cannot be reproduced; this
-path applies inverted dropout with its own stateless generator after the positional encoding, on the
-category embeddings and on the user-node rows.  The dropouts inside nn.TransformerEncoderLayer and the
-fixed p = 0.2 attention dropout of layers.py:36,74 are not applied (documented deviation; gradient
-parity is tested with every p = 0).
+Dropout: the reference drops activations with torch's RNG, whose streams cannot be reproduced; this path
+applies inverted dropout at the SAME sites with its own stateless counter-based generator (the backward
+re-evaluates the forward's mask): word embeddings, after the positional encoding, inside
+nn.TransformerEncoderLayer (attention weights, after out_proj, after the FFN activation, after linear2),
+category embeddings, the fixed p = 0.2 on the candidate-aware attention weights (layers.py:36,74) and the
+user-node rows.  Gradient parity is tested with every p = 0, the masks by their
+statistics (tests/test_gpu_training.py).
 """
 from __future__ import annotations
 
@@ -21,19 +23,31 @@ RELU, TANH = ops.ACT_RELU, ops.ACT_TANH
 
 
 def _branch(base, ids, T, transformer, pos_encoder, heads, p, seed):
-    """One transformer branch (title or body): int32 ids [n, T] -> mean-pooled features [n, 300]."""
+    """One transformer branch (title or body): int32 ids [n, T] -> mean-pooled features [n, 300].
+    Dropout sites as the reference places them (inverted dropout, stateless masks): word embeddings
+    (newsEncoders.py:311-312), after the positional encoding (:828), and inside nn.TransformerEncoderLayer
+    (:244-247, post-LN): attention weights, after out_proj, after the FFN activation, after linear2."""
     n = ids.shape[0]
     l = transformer.layers[0]
     d = base.word_embedding.weight.shape[1]
     pe = pos_encoder.pe.reshape(-1, d)
-    x0 = A.EmbedPE.apply(base.word_embedding.weight, ids.reshape(-1).contiguous(), T, pe)
-    x0 = A.dropout(x0, p, seed)
+    if p > 0:
+        w = A.dropout(A.Gather.apply(base.word_embedding.weight, ids.reshape(-1).contiguous()), p, seed)
+        x0 = A.dropout(w + pe[:T].repeat(n, 1), p, seed + 1)
+    else:
+        x0 = A.EmbedPE.apply(base.word_embedding.weight, ids.reshape(-1).contiguous(), T, pe)
     qkv = A.linear(x0, l.self_attn.in_proj_weight, l.self_attn.in_proj_bias)
-    ctx = A.MHA.apply(qkv, n, T, d, heads)
-    y = A.linear(ctx, l.self_attn.out_proj.weight, l.self_attn.out_proj.bias, residual=x0)
+    ctx = A.MHA.apply(qkv, n, T, d, heads, p, seed + 2)
+    if p > 0:
+        y = A.dropout(A.linear(ctx, l.self_attn.out_proj.weight, l.self_attn.out_proj.bias), p, seed + 3) + x0
+    else:
+        y = A.linear(ctx, l.self_attn.out_proj.weight, l.self_attn.out_proj.bias, residual=x0)
     x1 = A.LayerNorm.apply(y, l.norm1.weight, l.norm1.bias, l.norm1.eps)
-    hf = A.linear(x1, l.linear1.weight, l.linear1.bias, act=RELU)
-    y2 = A.linear(hf, l.linear2.weight, l.linear2.bias, residual=x1)
+    hf = A.dropout(A.linear(x1, l.linear1.weight, l.linear1.bias, act=RELU), p, seed + 4)
+    if p > 0:
+        y2 = A.dropout(A.linear(hf, l.linear2.weight, l.linear2.bias), p, seed + 5) + x1
+    else:
+        y2 = A.linear(hf, l.linear2.weight, l.linear2.bias, residual=x1)
     return A.LayerNormMeanPool.apply(y2, l.norm2.weight, l.norm2.bias, n, T, l.norm2.eps)
 
 

@@ -91,26 +91,38 @@ def score_impressions(model, cache: NewsVectorCache, dimp: DeviceImpressions, ba
 
 
 def evaluate_device(model, cache, dimp, batch_size, pair_index_base=0, total_pairs=None, group=None,
-                    scores_out=None, want_ranks=True):
+                    scores_out=None, want_ranks=True, sharded=False):
     """The device-side part of evaluate_impressions, fully asynchronous: 3 kernel launches (score,
-    rank+metrics, reduce) and, in a process group, one all-reduce.  Returns device tensors."""
+    rank+metrics, reduce) and -- ONLY when the caller says the impression set is sharded over a process
+    group (``group`` given, or ``sharded=True`` for the default group) -- one all-reduce of the five
+    partial sums, which every rank of that group must then enter.  A plain call never issues a
+    collective: the reference's own distributed flow evaluates on rank 0 alone (trainer.py:342), and an
+    implicit all-reduce there would wait for ranks that never call.  Returns device tensors."""
     scores = score_impressions(model, cache, dimp, batch_size, pair_index_base, total_pairs, out=scores_out)
     ranks, per_imp = ops.rank_metrics(scores, dimp.dev["labels"], dimp.dev["cand_off"], want_ranks=want_ranks)
     sums = ops.metrics_reduce(per_imp)
-    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+    if group is not None or sharded:
         torch.distributed.all_reduce(sums, group=group)
     return scores, ranks, per_imp, sums
 
 
+def _means(s):
+    """(auc, mrr, ndcg5, ndcg10) from the five sums; NaN when no impression carries both classes of labels
+    (an unlabeled test set: the reference returns None there, util.py:124-129)."""
+    n = s[4]
+    return tuple((x / n) if n > 0 else float("nan") for x in s[:4])
+
+
 def evaluate_impressions(model, cache, dimp, batch_size, pair_index_base=0, total_pairs=None,
-                         group=None, return_details=False):
+                         group=None, return_details=False, sharded=False):
     """Scores -> per-impression stable ranks -> (auc, mrr, ndcg5, ndcg10) averaged over impressions,
-    all on the device.  With a ``torch.distributed`` process group the five partial sums are
-    all-reduced (NCCL), so every rank returns the global means."""
+    all on the device.  ``group`` / ``sharded=True``: ``dimp`` is this rank's shard of one impression
+    set; the five partial sums are all-reduced (NCCL) and every rank of the group -- all of them must
+    call -- returns the global means."""
     scores, ranks, per_imp, sums = evaluate_device(model, cache, dimp, batch_size, pair_index_base,
-                                                   total_pairs, group)
+                                                   total_pairs, group, sharded=sharded)
     s = sums.tolist()                                # device -> host read of the step's result
-    result = tuple(x / s[4] for x in s[:4])
+    result = _means(s)
     if return_details:
         return result, dict(scores=scores, ranks=ranks, per_impression=per_imp, sums=sums)
     return result
@@ -208,8 +220,9 @@ def compute_scores(model, corpus, batch_size, mode, result_file, dataset):
     with torch.no_grad():
         cache = build_news_cache(model, news, device)
         dimp = DeviceImpressions(imp, device, cand_remaining=remaining, num_buckets=config.num_buckets)
+        # never a collective here: the reference calls compute_scores on rank 0 only (trainer.py:342)
         metrics, det = evaluate_impressions(model, cache, dimp, batch_size, return_details=True)
     write_rank_file(result_file, det["ranks"].cpu(), imp.cand_off)
     if labeled:
         return metrics
-    return None, None, None, None
+    return None, None, None, None            # unlabeled MIND-large test set: prediction file only (util.py:124-129)

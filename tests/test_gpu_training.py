@@ -229,3 +229,71 @@ def test_training_step_bf16_mode(lib):
         n_checked += 1
     assert n_checked >= 50
     assert dot / (n32 ** 0.5 * nb16 ** 0.5) > 0.995    # the full gradient vector keeps its direction
+
+
+def _mha_dropout_reference(qkv, n, T, d, heads, keep):
+    """torch fp64 attention with a GIVEN keep/(1-p) matrix [n, heads, T, T] on the attention weights."""
+    hd = d // heads
+    q, k, v = (qkv[:, i * d:(i + 1) * d].reshape(n, T, heads, hd).permute(0, 2, 1, 3) for i in range(3))
+    P = torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, dim=-1) * keep
+    return (P @ v).permute(0, 2, 1, 3).reshape(n * T, d)
+
+
+def test_mha_attention_dropout_mask_and_gradients(lib):
+    """nn.MultiheadAttention(dropout=p) inside the TransformerEncoderLayer (newsEncoders.py:244-247): the kernel's
+    stateless mask has the right statistics, is a function of the seed only, and forward / backward agree with fp64
+    autograd evaluated with the SAME mask (recovered from a uniform-attention probe)."""
+    from lime_cikm25_b200 import autograd as A
+    n, T, d, heads, p = 3, 32, 300, 10, 0.3
+    hd = d // heads
+    # probe: q = k = 0 -> uniform weights 1/T; v = one-hot over the key index in the first head dims is not possible
+    # (hd = 30 < T), so probe the mask column by column: v_j = 1 for one key j at a time
+    keep = torch.zeros(n, heads, T, T, dtype=torch.float64)
+    for j in range(T):
+        probe = torch.zeros(n * T, 3 * d, device=DEV)
+        probe.view(n, T, 3 * d)[:, j, 2 * d:] = 1.0
+        out = torch.empty(n * T, d, device=DEV)
+        ops.mha(probe, out, n, T, d, heads, p, 1234)
+        keep[:, :, :, j] = out.view(n, T, heads, hd)[:, :, :, 0].permute(0, 2, 1).double().cpu() * T
+    vals = keep.unique()
+    assert len(vals) == 2 and abs(float(vals[0])) == 0.0 and abs(float(vals[1]) - 1 / (1 - p)) < 1e-5   # inverted dropout
+    assert abs(float((keep > 0).double().mean()) - (1 - p)) < 0.02                                       # keep rate
+    out2 = torch.empty(n * T, d, device=DEV)
+    ops.mha(probe, out2, n, T, d, heads, p, 1235)
+    assert not torch.equal(out, out2)                                                                    # another seed, another mask
+    qkv = randn(n * T, 3 * d, seed=7).requires_grad_()
+    g = randn(n * T, d, seed=8)
+    y = A.MHA.apply(qkv, n, T, d, heads, p, 1234)
+    y.backward(g)
+    q64 = qkv.detach().double().cpu().requires_grad_()
+    z = _mha_dropout_reference(q64, n, T, d, heads, keep)
+    z.backward(g.double().cpu())
+    assert rel(y.detach().cpu(), z.detach()) < 5e-5
+    assert rel(qkv.grad.cpu(), q64.grad) < 5e-5
+
+
+def test_training_dropout_sites_are_live(lib):
+    """With dropout_rate > 0 the training forward is stochastic across calls (the per-call seed advances) and finite;
+    eval mode and p = 0 stay deterministic.  Covers the fixed p = 0.2 of the candidate-aware attention too
+    (layers.py:36,74): with config.dropout_rate = 0 the training logits still differ from call to call."""
+    cfg = make_config(vocabulary_size=300, batch_size=4, word_embedding_init="skip", dropout_rate=0.0)
+    model = L.Model(cfg)
+    model.initialize()
+    synth.synthetic_parameters(model, 11)
+    model = model.to(DEV).train()
+    news = synth.make_news_table(60, vocabulary_size=300, seed=3)
+    batch = [torch.as_tensor(x).to(DEV) for x in synth.make_train_batch(news, 4, seed=5)]
+    with torch.no_grad():
+        a = model(*batch, batch[24] - batch[23]).clone()
+        b = model(*batch, batch[24] - batch[23]).clone()
+        assert torch.isfinite(a).all() and not torch.equal(a, b)          # p = 0.2 on the CA attention weights
+        ue = model.user_encoder
+        ue.eval()                                                         # that dropout off: deterministic again
+        c = model(*batch, batch[24] - batch[23]).clone()
+        d_ = model(*batch, batch[24] - batch[23]).clone()
+        assert torch.equal(c, d_)
+        ue.train()
+        model.config.dropout_rate = 0.2
+        e = model(*batch, batch[24] - batch[23]).clone()
+        assert torch.isfinite(e).all() and float((e - a).abs().max()) > 0
+    model.config.dropout_rate = 0.0
