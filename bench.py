@@ -65,6 +65,11 @@ def _parse_args():
     ap.add_argument("--bf16-encoder", action="store_true", help="run the 4 transformer GEMMs on tcgen05 (bf16 mode)")
     ap.add_argument("--train-steps", type=int, default=4, help="timed training steps of the secondary train_step report (0 = skip)")
     ap.add_argument("--train-batch", type=int, default=32, help="samples per rank per training step (BASELINE.json configs[2])")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank scores its own --impressions set; strong: ONE set of --impressions is sharded over the "
+                         "ranks by parallel.shard_impressions (balanced by sum(H + C))")
+    ap.add_argument("--parity-impressions", type=int, default=12, help="impressions of the sampled fp64-oracle check (0 = skip)")
+    ap.add_argument("--ref-cuda-batches", type=int, default=6, help="mini-batches of the reference-algorithm-on-CUDA leg (0 = skip)")
     return ap.parse_args()
 
 
@@ -107,7 +112,7 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def make_setup(args, rank, need_news_text=True):
+def make_setup(args, rank, need_news_text=True, world=1):
     from lime_cikm25_b200 import synth
     from lime_cikm25_b200.config import default_config as make_config
     cfg = make_config(vocabulary_size=args.vocab, batch_size=args.batch_size, word_embedding_init="skip")
@@ -116,7 +121,7 @@ def make_setup(args, rank, need_news_text=True):
         imp = synth.make_impressions(args.impressions, news.news_num, num_users=601215, seed=100 + rank)
     else:
         news = synth.make_news_table(args.news, vocabulary_size=args.vocab, seed=1)
-        imp = synth.make_impressions(args.impressions, news.news_num, seed=100 + rank)
+        imp = synth.make_impressions(args.impressions, news.news_num, seed=100 + (0 if args.scaling == "strong" else rank))
     return cfg, news, imp
 
 
@@ -162,8 +167,8 @@ def run_reference(args):
     model.initialize()
     synth.synthetic_parameters(model, seed=0)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    steps = max(1, min(args.steps, 12))
-    warm = max(1, min(args.warmup, 2))
+    steps = max(1, args.steps)            # one step = one reference mini-batch of 32 pairs (about 1 s on 16 cores)
+    warm = max(1, args.warmup)
     cb = cpu_baseline(args, cfg, news, imp, sd, steps=steps, warmup=warm)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
@@ -173,6 +178,78 @@ def run_reference(args):
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def ref_cuda_leg(args, cfg, news, imp, model_sd, dev):
+    """The reference's ALGORITHM on the GPU: the oracle port (same op sequence as the reference's PyTorch modules, one
+    (user, candidate) pair per sample, 51 news encodes per pair, util.py:88-112 batching) with every tensor on the
+    device -- the stand-in for 'the reference's own PyTorch CUDA eval throughput' of the north star (the reference itself
+    cannot be installed: no packaging, absent dependencies)."""
+    from oracle import lime_oracle as O
+    from lime_cikm25_b200 import synth
+    bs = args.batch_size
+    sd = {k: v.to(dev) for k, v in model_sd.items()}
+    batches = []
+    for b in synth.impressions_to_pair_batches(news, imp.slice(0, min(imp.num_impressions, 64)), bs):
+        if len(b[0]) == bs:
+            batches.append([torch.as_tensor(x).to(dev) for x in b])
+        if len(batches) >= args.ref_cuda_batches + 2:
+            break
+    cbar = float(np.mean(np.diff(imp.cand_off)))
+    try:
+        with torch.no_grad():
+            for b in batches[:2]:
+                O.model_forward(sd, b, cfg)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for b in batches[2:]:
+                O.model_forward(sd, b, cfg)
+            e1.record()
+            torch.cuda.synchronize()
+        n = len(batches) - 2
+        pairs_s = bs * n / (e0.elapsed_time(e1) * 1e-3)
+        return {"value": pairs_s / cbar, "unit": UNIT, "pairs_per_sec": pairs_s, "kind": "port-on-cuda",
+                "sample": "%d mini-batches of %d pairs, each pair re-encoding %d news (torch eager fp32 on the device)" % (n, bs, H + 1)}
+    except Exception as e:      # the oracle is written for CPU tensors; report instead of failing the bench line
+        return {"value": None, "unit": UNIT, "kind": "port-on-cuda", "error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+
+def parity_sample(args, model, cfg, cache, news, imp, model_sd, scores, dev):
+    """Checker on the headline configuration itself: a few impressions' scores from the timed kernel vs the fp64 CPU
+    oracle of the user encoder + click score evaluated on the same cached LIME vectors (Stage B in isolation)."""
+    from oracle import lime_oracle as O
+    se = model.scoring
+    rng = np.random.default_rng(7)
+    pick = np.sort(rng.choice(imp.num_impressions, size=min(args.parity_impressions, imp.num_impressions), replace=False))
+    Hh = imp.hist_news.shape[1]
+    sd64 = model_sd          # the oracle casts every weight to the dtype it is asked for (fp64 below)
+    worst, npairs = 0.0, 0
+    tail_start = (imp.num_pairs // args.batch_size) * args.batch_size
+    got_all = scores.cpu().numpy()
+    ref_all, got_sel = [], []
+    for i in pick:
+        hn = torch.as_tensor(imp.hist_news[i]).long()
+        hv = se.lime_vectors(cache.hist_rows[hn.to(dev)], torch.as_tensor(imp.hist_fresh[i]).to(dev),
+                             torch.as_tensor(imp.hist_life[i]).to(dev)).cpu().double()
+        for p in range(int(imp.cand_off[i]), int(imp.cand_off[i + 1])):
+            cn = int(imp.cand_news[p])
+            cv = se.lime_vectors(cache.hist_rows[cn:cn + 1], torch.as_tensor(imp.cand_fresh[p:p + 1]).to(dev),
+                                 torch.as_tensor(imp.cand_life[p:p + 1]).to(dev)).cpu().double()
+            prefix = args.batch_size if p < tail_start else max(1, imp.num_pairs - tail_start)
+            u = O.crown_user(sd64, hv.view(1, Hh, -1), torch.as_tensor(news.category[hn]).view(1, Hh),
+                             torch.as_tensor(news.subCategory[hn]).view(1, Hh), torch.as_tensor(news.category[cn:cn + 1]).view(1, 1),
+                             torch.as_tensor(news.subCategory[cn:cn + 1]).view(1, 1), torch.as_tensor(imp.hist_mask[i]).view(1, Hh),
+                             cv.view(1, 1, -1), cfg, dtype=torch.float64, prefix_len=prefix)
+            r = torch.tensor(float(np.float32(imp.cand_life[p]) - np.float32(imp.cand_fresh[p])))
+            ref_all.append(float((u * cv.view(1, 1, -1)).sum() * O.lifetime_weight(r, cfg)))
+            got_sel.append(float(got_all[p]))
+            npairs += 1
+    ref, got = np.asarray(ref_all), np.asarray(got_sel)
+    floor = 0.1 * float(np.sqrt(np.mean(ref * ref))) + 1e-30
+    worst = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), floor)))
+    return {"impressions": int(len(pick)), "pairs": npairs, "max_rel": worst, "tolerance": 1e-4,
+            "oracle": "fp64 CPU oracle of userEncoders.CROWN.forward + RemainingLifetimeWeighting on the cached LIME vectors"}
 
 
 def workload_config(args, imp):
@@ -243,7 +320,10 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib = _lib.require_device()
-    cfg, news, imp = make_setup(args, rank)
+    cfg, news, imp = make_setup(args, rank, world=world)
+    pair_base, total_pairs = 0, None
+    if args.scaling == "strong" and world > 1:
+        imp, pair_base, total_pairs = parallel.shard_impressions(imp, rank, world)
     model = L.Model(cfg)
     model.initialize()
     synth.synthetic_parameters(model, seed=0)
@@ -274,7 +354,8 @@ def run_b200(args):
     bs = args.batch_size
 
     def step():
-        return util.evaluate_device(model, cache, dimp, bs, scores_out=scores, want_ranks=False)
+        return util.evaluate_device(model, cache, dimp, bs, pair_base, total_pairs, scores_out=scores, want_ranks=False,
+                                    sharded=world > 1)
 
     def barrier():
         if world > 1:
@@ -297,11 +378,12 @@ def run_b200(args):
         ms = e0.elapsed_time(e1)
         launches = int(lib.lime_launch_count())
         result = sums.tolist()
+        fallback_units = int(dimp.work_counter[1])      # units of the last timed step that the exact kernel re-scored
         # ---- the dominant kernel alone (roofline numerator) ----
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record()
         for _ in range(args.steps):
-            util.score_impressions(model, cache, dimp, bs, out=scores)
+            util.score_impressions(model, cache, dimp, bs, pair_base, total_pairs, out=scores)
         k1.record()
         torch.cuda.synchronize()
         kernel_ms = k0.elapsed_time(k1) / args.steps
@@ -316,7 +398,8 @@ def run_b200(args):
         ev_done = [torch.cuda.Event(), torch.cuda.Event()]
 
         def e2e_step_fn(d):
-            return util.evaluate_device(model, cache, d, bs, scores_out=scores, want_ranks=False)
+            return util.evaluate_device(model, cache, d, bs, pair_base, total_pairs, scores_out=scores, want_ranks=False,
+                                        sharded=world > 1)
 
         barrier()
         t0 = time.perf_counter()
@@ -339,6 +422,14 @@ def run_b200(args):
         e2e_s = time.perf_counter() - t0
         assert abs(s[0] - result[0]) <= 1e-9 * max(1.0, abs(result[0])), "e2e path disagrees with the resident path"
         clocks = sampler.stop() if sampler else None
+        parity = ref_cuda = None
+        if rank == 0 and world == 1:
+            util.score_impressions(model, cache, dimp, bs, pair_base, total_pairs, out=scores)
+            torch.cuda.synchronize()
+            if args.parity_impressions > 0:
+                parity = parity_sample(args, model, cfg, cache, news, imp, sd_cpu, scores, dev)
+            if args.ref_cuda_batches > 0:
+                ref_cuda = ref_cuda_leg(args, cfg, news, imp, sd_cpu, dev)
 
     train = None
     if args.train_steps > 0:
@@ -354,7 +445,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms, e2e_ms = t.tolist()
-    total_imp, total_pairs = tot.tolist()
+    total_imp, total_pairs_all = tot.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -377,21 +468,26 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": total_imp * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, imp),
-        "pairs_per_sec": total_pairs * args.steps / (ms * 1e-3),
+        "pairs_per_sec": total_pairs_all * args.steps / (ms * 1e-3),
         "e2e": {"value": total_imp * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": dimp.h2d_bytes(), "d2h_bytes_per_step": 40,
-                "overlap": "H2D of step i+1 (copy stream, second device buffer) overlaps the kernels of step i"},
+                "overlap": "H2D of step i+1 (copy stream, second device buffer) overlaps the kernels of step i",
+                "cache_build_included": False,
+                "note": "per-step inputs are the impression arrays; the news-vector cache is per checkpoint (cache_build, eval_wall_one_checkpoint)"},
+        "eval_wall_one_checkpoint": {"seconds": cache_s + ms * 1e-3 / args.steps, "cache_build_s": cache_s, "scoring_step_s": ms * 1e-3 / args.steps,
+                                     "what": "one checkpoint evaluated on one impression set: news-vector cache build + one eval step"},
+        "fallback_units": fallback_units, "units_per_step_per_gpu": int(dimp.num_units),
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "lime::score_tc_kernel", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                      "note": "kernel_ms = one lime_score_impressions call (score_tc_kernel + the usually empty exact-"
-                             "fallback launch), CUDA events. traffic (ncu, one launch) exceeds the algorithmic bytes: a "
-                             "unique history row is cached as vc|gw (3200 B), a candidate as fp16 hi/lo pairs of w1|w2|w3 "
-                             "(4800 B) instead of one 1600 B vector. No pipe is saturated (issue 31 %, LSU 14 %, tensor 10 %): "
-                             "the kernel is bound by the serialised per-unit phases of its two CTAs per SM, DESIGN.md section 3"},
+                             "fallback launch), CUDA events. traffic = ncu dram bytes of one launch (profiles/score_traffic.json): "
+                             "a unique history row is read as vc|gw (3200 B), a candidate as fp16 hi/lo pairs of w1|w2|w3 (4800 B). "
+                             "No pipe is saturated: the kernel is bound by the memory + barrier round trip of its 7 operand stages "
+                             "per unit (DESIGN.md section 3)"},
         "clocks": clocks,
         "cache_build": {"seconds": cache_s, "news_per_sec": news.news_num / cache_s,
                         "tflops": news.news_num * 241.3e6 / cache_s / 1e12,
@@ -402,6 +498,12 @@ def run_b200(args):
         "metrics": {"auc": result[0] / result[4], "mrr": result[1] / result[4],
                     "ndcg5": result[2] / result[4], "ndcg10": result[3] / result[4]},
     }
+    if parity is not None:
+        line["parity_sample"] = parity
+    if ref_cuda is not None:
+        line["ref_cuda"] = ref_cuda
+        if ref_cuda.get("value"):
+            line["vs_ref_cuda"] = line["e2e"]["value"] / ref_cuda["value"]
     if train is not None:
         line["train_step"] = train
     if world == 1 and not args.no_cpu_baseline:

@@ -107,7 +107,7 @@ def user_representation(ue, hist_vec, cand_vec, hist_cat, hist_sub, cand_cat, ca
     tc = torch.cat([topic_representation(lime, cand_cat, cand_sub), pad_c], dim=1)            # [B*N, 52]
     Qp = A.linear(tc, F.pad(ca.query_proj.weight, (0, 2)), ca.query_proj.bias)                # layers.py:66
     Kp = A.linear(th, F.pad(ca.key_proj.weight, (0, 2)), ca.key_proj.bias)                    # layers.py:67
-    a = A.CAAttention.apply(Qp, Kp, hist_mask, B, N, H, 0.2 if ue.training else 0.0, seed + 61)   # [B*H]; p = 0.2 fixed, layers.py:36,74
+    a = A.CAAttention.apply(Qp, Kp, hist_mask, B, N, H, float(ca.dropout.p) if ue.training else 0.0, seed + 61)   # [B*H]; nn.Dropout(0.2), layers.py:36,74
     wc = A.RowScale.apply(hist_vec, a)                                                         # layers.py:84
     z = A.linear(wc, ca.gate_proj.weight, ca.gate_proj.bias)
     o = A.GateMix.apply(z, wc, hist_vec)                                                       # layers.py:87-88

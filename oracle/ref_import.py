@@ -159,8 +159,9 @@ def load_reference():
         import layers as ref_layers                      # noqa
         import util as ref_util                          # noqa
         import evaluate as ref_eval                      # noqa
+        import dataset as ref_dataset                    # noqa
     return types.SimpleNamespace(model=ref_model, newsEncoders=ref_news, userEncoders=ref_user,
-                                 layers=ref_layers, util=ref_util, evaluate=ref_eval)
+                                 layers=ref_layers, util=ref_util, evaluate=ref_eval, dataset=ref_dataset)
 
 
 def build_reference_model(cfg, seed=0, word_embedding=None):

@@ -343,16 +343,16 @@ def test_dedup_of_repeated_history_rows(lib):
 
 
 def test_split_f16_pairs_and_news_meta(lib):
-    """Cache-build helpers of the tensor-core path: x * 1024 = hi + lo to 2^-21, layout [k][hi 400 | lo 400]; the meta
-    sector repeats the cached topic id / bounds / folded scalars."""
+    """Cache-build helpers of the tensor-core path: x * 1024 = hi + lo to 2^-21, layout [hi | lo][k][400] (an operand-row
+    triple = 3 consecutive 800-byte rows); the meta sector repeats the cached topic id / bounds / folded scalars."""
     g = torch.Generator().manual_seed(5)
     x = (torch.randn(37, 1720, generator=g) * torch.logspace(-4, 1, 1720)).to(DEV)
     x[5, 7] = 0.0
     stamp = torch.zeros(37, device=DEV)
     pairs = ops.split_f16_pairs(x, 3, absmax=stamp)
     assert pairs.dtype == torch.float16 and pairs.shape == (37, 2400)
-    p = pairs.double().view(37, 3, 2, 400)
-    back = (p[:, :, 0] + p[:, :, 1]).reshape(37, 1200) / 1024.0
+    p = pairs.double().view(37, 2, 3, 400)
+    back = (p[:, 0] + p[:, 1]).reshape(37, 1200) / 1024.0
     ref = x[:, :1200].double()
     # 2^-21 relative; values below 1e-4 put their lo half into the fp16 subnormals (6e-8 resolution / 1024)
     assert bool(((back - ref).abs() <= 2.0 ** -20 * ref.abs() + 1e-10).all())

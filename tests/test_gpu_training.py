@@ -81,6 +81,9 @@ def _make(case_seed, batch_size=4, **over):
     model = L.Model(cfg)
     model.initialize()
     synth.synthetic_parameters(model, case_seed)
+    for m in model.modules():                 # as the reference-side pin does: every nn.Dropout, incl. the hard-coded 0.2 of layers.py:36
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
     sd = {k: v.detach().clone().double().requires_grad_(v.dtype.is_floating_point) for k, v in model.state_dict().items()}
     return cfg, model.to(DEV).train(), sd
 
