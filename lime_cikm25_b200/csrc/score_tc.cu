@@ -43,8 +43,11 @@
 // issuer warp, one unit ahead) -> attention a[u][c] -> centres mid / w, t = (a - mid) / w -> 13 K stages of
 // 32 dims -> epilogue + pooling -> score.
 #include "score_common.cuh"
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+
+#include <mutex>
 
 #include "tc05.cuh"
 
@@ -65,7 +68,6 @@ constexpr int kStages = 13;                     // 32-wide candidate-operand sta
 constexpr int kOStages = 7;                     // 64-wide O stages
 constexpr int kWTile = 32768, kWImg = 16384;    // one 64-dim candidate tile = hi image + lo image of 128 rows x 128 B
 constexpr int kGroups = 7;                      // row groups of 8 unique history rows (56 / 8)
-constexpr int kCopyTasks = kCWarps;             // candidate-operand copy shares per stage: every compute warp takes one
 constexpr int kTabLd = LIME_TOPIC_TAB_LD;
 constexpr int kTabStride = 32;                  // tab_s[u][3 * bp + k] (float2), 3 * kMaxBp <= 32
 constexpr float kLog2e = 1.4426950408889634f;
@@ -110,13 +112,13 @@ constexpr int UB_UMULT = UB_UTOPIC + kUArr;                   // float multiplic
 constexpr int UB_UMP0 = UB_UMULT + kUArr;                     // float multiplicity inside the GraphSAGE prefix (main)
 constexpr int UB_UMP1 = UB_UMP0 + kUArr;                      // ... (tail batch)
 constexpr int UB_UGABS = UB_UMP1 + kUArr;
-constexpr int UB_WROW = UB_UGABS + kUArr;                     // [120] uint2: source element offset, destination byte offset of an operand row
-constexpr int UB_INFO = UB_WROW + 3 * kTriples * 8;           // ints: unit, impression, first pair, count, U, unmasked slots, flags, bucket pairs
+constexpr int UB_WROW = UB_UGABS + kUArr;                     // [40] uint2: per operand-row triple, the row of the cand16 tensor map (hi rows; lo rows = + 3) and the destination byte offset inside an image
+constexpr int UB_INFO = UB_WROW + kTriples * 8;           // ints: unit, impression, first pair, count, U, unmasked slots, flags, bucket pairs
 constexpr int kUnitBuf = UB_INFO + 32;
 constexpr int OFF_UB = OFF_PART + 2 * kTriples * 16;
 // front-end scratch (one warp): keys, topic ids, gate bounds of the H history slots
 constexpr int OFF_HKN = OFF_UB + 2 * kUnitBuf, OFF_HKT = OFF_HKN + kUArr, OFF_HTP = OFF_HKT + kUArr, OFF_HGA = OFF_HTP + kUArr;
-constexpr int OFF_BARS = OFF_HGA + kUArr;                     // wfull[4] wfree[4] ofull[2] ofree[2] accum
+constexpr int OFF_BARS = OFF_HGA + kUArr;                     // wfull[2] ... ofull ofree accum
 constexpr int OFF_MISC = OFF_BARS + 128;                      // tmem slot
 constexpr int OFF_PROF = OFF_MISC + 64;                       // phase clocks of thread 0 (diagnostic)
 constexpr int OFF_BIAS = OFF_PROF + 128;                      // gate bias [400]: read by every lane at every stage
@@ -154,13 +156,6 @@ __device__ unsigned long long g_phase_clocks[16];
 #endif
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-// arrive on the mbarrier once every cp.async issued so far by this thread has completed (counts as one arrival)
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, uint32_t n) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(n) : "memory");
 }
@@ -182,8 +177,8 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
 // so the 3 rows of a candidate live in one warp of the epilogue
 __device__ __forceinline__ int m_row(int j, int k) { return 32 * (j / 10) + 3 * (j % 10) + k; }
 
-// uses of a ring slot per pass: W slot s (stage kc & 3), O half h (stage kc & 1)
-__device__ __forceinline__ uint32_t w_uses(int s) { return s == 0 ? 4u : 3u; }
+// fills of candidate tile t per unit: O stages 0 2 4 6 use tile 0, stages 1 3 5 tile 1
+__device__ __forceinline__ uint32_t w_uses(int t) { return t == 0 ? 4u : 3u; }
 
 // pack 2 fp32 -> fp16x2 (round to nearest), returns also the rounded values as fp32
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -198,37 +193,37 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
-// ---- candidate operand (M side): one copy task = every kCopyTasks-th instruction slot of stage kc -------------------
-// A slot is 8 operand rows x 64 contiguous bytes (lane = (row in slot, 16-byte chunk)); rows come from the unit's
-// row table (candidate rows of cand16, bucket-pair rows of ctab16).  cp.async.mbarrier.arrive.noinc publishes the
-// stage when this thread's copies have landed (no thread waits for the data).
-__device__ __forceinline__ void copy_task(unsigned char *base, const unsigned char *w16, const uint2 *wrow, int n3, int kc,
-                                          int sub, int lane) {
-    constexpr int kIter = (2 * 3 * kTriples / 8 + kCopyTasks - 1) / kCopyTasks;      // slots per warp and stage (5)
-    const int c4 = lane & 3, rs = lane >> 2;
+// ---- candidate operand (M side): TMA ---------------------------------------------------------------------------------
+// cand16 is a 2-D tensor [6 x rows][400] of fp16 (row pitch 800 B): per cache row the hi images of w1 w2 w3, then the lo
+// images.  One box = 64 dims x 3 rows = one operand-row triple of one image, written by the TMA unit straight into the
+// K-major SWIZZLE_128B tile (the swizzle follows the shared-memory address bits, so a box may start at any 128-byte row
+// of the tile); the last O stage reads dims 384..447, of which 400.. are out of bounds and arrive as zeros.  The 2 x (candidates
+// + bucket pairs) <= 80 boxes of a tile are issued by the compute warps, at most one per lane (12 lanes per warp); the tile's
+// mbarrier completes on the byte count (no thread waits for the data, no register or generic-proxy store is involved).
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *map, int col, int row, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(col), "r"(row), "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+// compute warp `warp`: its share (every kCWarps-th box, one box per lane) of the candidate tile of O stage kb -> tile kb & 1.
+// Warp 0 also posts the byte count (a complete_tx that overtakes it only drives the transaction count negative for a while).
+__device__ __forceinline__ void issue_w_tile(unsigned char *base, uint64_t *bars, const CUtensorMap *map, const uint2 *wrow, int nt,
+                                             int kb, int warp, int lane) {
+    uint64_t *bar = bars + B_WFULL + (kb & 1);
 #ifdef LIME_TC_DIAG_NOCOPY       // timing diagnostic only (wrong results): no candidate-operand copies
+    if (warp == 0 && lane == 0) tc::mbar_arrive(bar);
     return;
 #endif
-    if (kc < kStages - 1 || c4 < (kD - 32 * (kStages - 1)) / 8) {
-        const uint32_t wbase = tc::smem_u32(base) + OFF_W + (uint32_t)((kc >> 1) & 1) * kWTile;
-        const uint32_t chunk = (uint32_t)(4 * (kc & 1) + c4);
-        const unsigned char *src0 = w16 + 64 * kc + 16 * c4;
-        uint2 rw[kIter];
-        bool on[kIter], lo[kIter];
-#pragma unroll
-        for (int i = 0; i < kIter; ++i) {
-            int ri = 8 * (sub + kCopyTasks * i) + rs;
-            on[i] = ri < 2 * n3;
-            lo[i] = ri >= n3;
-            ri -= lo[i] ? n3 : 0;
-            rw[i] = wrow[on[i] ? ri : 0];
-        }
-#pragma unroll
-        for (int i = 0; i < kIter; ++i) {
-            if (on[i])
-                cp_async16(wbase + (lo[i] ? kWImg : 0) + rw[i].y + ((chunk ^ ((rw[i].y >> 7) & 7u)) << 4),
-                           src0 + rw[i].x + (lo[i] ? 6 * kD : 0));
-        }
+    if (warp == 0 && lane == 0) mbar_expect_tx(bar, (uint32_t)nt * 2u * 3u * 128u);
+    const uint32_t wt = tc::smem_u32(base) + OFF_W + (uint32_t)(kb & 1) * kWTile;
+    const int b = warp + kCWarps * lane;
+    if (b < 2 * nt) {
+        const int lo = b >= nt ? 1 : 0;
+        const uint2 rw = wrow[b - (lo ? nt : 0)];
+        tma_load_box(wt + (lo ? kWImg : 0) + rw.y, map, 64 * kb, (int)rw.x + 3 * lo, bar);
     }
 }
 // Ring protocol.  The O operand is ONE 64-dim tile, produced and consumed once per O stage (7 per unit); the candidate
@@ -534,19 +529,16 @@ __device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char 
         nbp = min(min(nbp, kMaxBp), kTriples - cnt);
     }
     __syncwarp();
-    // operand row table: source byte offset inside cand16 (bucket-pair rows follow the news rows) and destination byte
-    // offset inside an image
+    // operand-row triples: row of the cand16 tensor map (6 rows per cache row; the bucket-pair rows follow the news rows)
+    // and destination byte offset inside an image (3 consecutive 128-byte rows)
     const int nt = cnt + nbp;
-    for (int ri = lane; ri < 3 * nt; ri += 32) {
-        const int j = ri / 3, k = ri - 3 * j;
+    for (int j = lane; j < nt; j += 32) {
 #ifdef LIME_TC_DIAG_WROW0        // timing diagnostic only (wrong results): every candidate copies news 1..8 -> L2 hits, no DRAM
         const uint32_t row = j < cnt ? (uint32_t)(1 + (j & 7)) : (uint32_t)C.news_num + tab_row0 + (uint32_t)btab[j - cnt];
 #else
         const uint32_t row = j < cnt ? (uint32_t)cnews[j] : (uint32_t)C.news_num + tab_row0 + (uint32_t)btab[j - cnt];
 #endif
-        const uint32_t src = row * (uint32_t)(2 * kC16) + (uint32_t)(k * 2 * kD);        // bytes
-        const int m = m_row(j, k);
-        wrow[ri] = make_uint2(src, (uint32_t)((m >> 3) * 1024 + (m & 7) * 128));
+        wrow[j] = make_uint2(6u * row, (uint32_t)m_row(j, 0) * 128u);
     }
     flags = __reduce_or_sync(0xffffffffu, flags);
     if (lane == 0) {
@@ -629,7 +621,7 @@ __device__ __forceinline__ void front_dedup(const ScoreArgs &args, unsigned char
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs args) {
+__global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs args, const __grid_constant__ CUtensorMap wmap) {
     // Every shared-memory pointer below is derived from this array by pointer arithmetic only (no integer round trip), so
     // the compiler keeps the shared state space and emits LDS / STS instead of generic loads; the operand tiles need
     // the 1024-byte alignment of the 128-byte swizzle, which the declaration requests and the first thread verifies.
@@ -655,7 +647,6 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
     const int H = I.max_history;
     const int T = C.num_topics;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned char *w16 = reinterpret_cast<const unsigned char *>(C.cand16);   // news rows, then the nb^2 bucket-pair rows
 
     // this CTA's copy of the bucket-pair tables (history role; the candidate role's copy sits in the tail of cand16)
     const int nb2 = C.num_buckets * C.num_buckets;
@@ -664,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
     float *bias_s = reinterpret_cast<float *>(base + OFF_BIAS);
     for (int i = tid; i < kD; i += kThreads) bias_s[i] = C.gate_bias[i];
     if (tid == 0) {
-        for (int s = 0; s < 4; ++s) tc::mbar_init(bars + B_WFULL + s, kCompute);   // every compute thread, once its copies (if any) have landed
+        for (int s = 0; s < 2; ++s) tc::mbar_init(bars + B_WFULL + s, 1);      // one arrive.expect_tx per fill; the TMA unit completes the bytes
         tc::mbar_init(bars + B_OFULL, kCWarps);                 // one arrival per compute warp
         tc::mbar_init(bars + B_OFREE, 1);
         tc::mbar_init(bars + B_ACCUM, 1);
@@ -722,18 +713,15 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
         if (tid == 0) { t_last = clock64(); ++prof[9]; }
 #endif
         const int pair0 = info[UI_PAIR0], cnt = info[UI_CNT], U = info[UI_U], nbp = info[UI_NBP];
-        const int n3 = 3 * (cnt + nbp);
         const int Up = (U + 15) & ~15;
         const int ngroups = (U + 7) >> 3;
 
         // ================= roles ======================================================================
         if (warp < kCWarps) {
-            // the candidate operand of the first two O stages goes out now (all four slots are free since the previous
-            // unit's last MMA): it lands during the attention phase
-            for (int st = 0; st < 4; ++st) {
-                copy_task(base, w16, wrow, n3, st, warp, lane);
-                cp_async_mbar_arrive_noinc(bars + B_WFULL + st);
-            }
+            // the candidate operand of the first two O stages goes out now (both tiles are free since the previous unit's
+            // last MMA): it lands during the attention phase
+            issue_w_tile(base, bars, &wmap, wrow, cnt + nbp, 0, warp, lane);
+            issue_w_tile(base, bars, &wmap, wrow, cnt + nbp, 1, warp, lane);
             // ---------------- phase 1: candidate-aware attention weights a[u][c] (layers.py:66-81) ------
             // lanes per candidate = the smallest power of two that covers the U rows with 4 rows per lane
             if (U <= 8)       attention<2, kCWarps>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
@@ -847,18 +835,9 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(bars + B_OFULL);
                     LIME_TICK(14);
-                    // the two candidate slots of the previous O stage are free (its MMAs completed: observed above): the
-                    // next O stage's candidate operand goes into them, one production stage ahead of its MMAs
-                    if (kb >= 1) {
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int st = 2 * kb + 2 + h;
-                            if (st < kStages) {
-                                copy_task(base, w16, wrow, n3, st, warp, lane);
-                                cp_async_mbar_arrive_noinc(bars + B_WFULL + (st & 3));
-                            }
-                        }
-                    }
+                    // the candidate tile of the previous O stage is free (its MMAs completed: observed above): the next O
+                    // stage's candidate operand goes into it, one production stage ahead of its MMAs
+                    if (kb >= 1 && kb + 1 < kOStages) issue_w_tile(base, bars, &wmap, wrow, cnt + nbp, kb + 1, warp, lane);
                     LIME_TICK(11);
                 }
                 // row sums over the 8 quad lanes of a row (fixed order: bit-reproducible)
@@ -897,34 +876,30 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
 #ifdef LIME_TC_PHASE_CLOCKS
                 if (lane == 0) atomicAdd(&g_phase_clocks[1], (unsigned long long)(clock64() - tw0));
 #endif
-                for (int h = 0; h < 2; ++h) {
-                    const int kc = 2 * kb + h, s = kc & 3;
-                    if (kc >= kStages) break;
+                {
+                    const int tl = kb & 1;
 #ifdef LIME_TC_PHASE_CLOCKS
                     const long long tw1 = clock64();
 #endif
-                    tc::mbar_wait(bars + B_WFULL + s, (pass_iter * w_uses(s) + (uint32_t)(kc >> 2)) & 1u, 300 + kc);
+                    tc::mbar_wait(bars + B_WFULL + tl, (pass_iter * w_uses(tl) + (uint32_t)(kb >> 1)) & 1u, 300 + kb);
 #ifdef LIME_TC_PHASE_CLOCKS
                     if (lane == 0) atomicAdd(&g_phase_clocks[0], (unsigned long long)(clock64() - tw1));
 #endif
                     tc::fence_after_sync();
                     if (lane == 0) {
-                        const int ksteps = kc < kStages - 1 ? 2 : (kD - 32 * (kStages - 1)) / 16;
-                        const uint32_t wt = sb + OFF_W + (uint32_t)(kb & 1) * kWTile;
+                        const int ksteps = kb < kOStages - 1 ? 4 : (kD - 64 * (kOStages - 1)) / 16;
+                        const uint32_t wt = sb + OFF_W + (uint32_t)tl * kWTile;
                         const uint64_t ahi = tc::smem_desc_sw128(wt), alo = tc::smem_desc_sw128(wt + kWImg);
                         for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t k2 = (uint64_t)(2 * (2 * h + ks));   // 32 bytes per K step of 16
-                            tc::mma_f16(tmem, ahi + k2, bdesc + k2, idesc1, (kc | ks) != 0);
-                            tc::mma_f16(tmem + 3 * Up, alo + k2, bdesc + k2, idesc2, (kc | ks) != 0);
+                            const uint64_t k2 = (uint64_t)(2 * ks);             // 32 bytes per K step of 16
+                            tc::mma_f16(tmem, ahi + k2, bdesc + k2, idesc1, (kb | ks) != 0);
+                            tc::mma_f16(tmem + 3 * Up, alo + k2, bdesc + k2, idesc2, (kb | ks) != 0);
                         }
+                        tc::mma_commit(bars + B_OFREE);
+                        if (kb == kOStages - 1) tc::mma_commit(bars + B_ACCUM);
                     }
                     __syncwarp();
                 }
-                if (lane == 0) {
-                    tc::mma_commit(bars + B_OFREE);
-                    if (kb == kOStages - 1) tc::mma_commit(bars + B_ACCUM);
-                }
-                __syncwarp();
             }
             // part 3 of the next unit's front end, in the shadow of this unit's epilogue
             front_cand(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, lane);
@@ -1149,15 +1124,53 @@ __global__ void split_f16_pairs_kernel(const float *__restrict__ src, int64_t ld
 
 }  // namespace
 
+// The cand16 tensor map (TMA descriptor) of the candidate operand: encoded on the host by the driver's
+// cuTensorMapEncodeTiled (resolved through the runtime, no link-time dependency on libcuda), cached per (pointer, rows).
+static int cand16_tensor_map(const void *cand16, uint64_t rows, CUtensorMap *out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static std::mutex mu;
+    static EncodeFn encode = nullptr;
+    static const void *c_ptr = nullptr;
+    static uint64_t c_rows = 0;
+    static CUtensorMap c_map;
+    std::lock_guard<std::mutex> lock(mu);
+    if (encode == nullptr) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        LIME_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        LIME_CHECK_ARG(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    if (c_ptr != cand16 || c_rows != rows) {
+        const cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)(6 * rows)};          // innermost first
+        const cuuint64_t strides[1] = {(cuuint64_t)(kD * 2)};                          // bytes between rows
+        const cuuint32_t box[2] = {64, 3}, estr[2] = {1, 1};
+        const CUresult r = encode(&c_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(cand16), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        LIME_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(cand16, %llu rows) failed: CUresult %d", (unsigned long long)rows, (int)r);
+        c_ptr = cand16;
+        c_rows = rows;
+    }
+    *out = c_map;
+    return 0;
+}
+
 int launch_score_tc(const ScoreArgs &a, cudaStream_t st) {
     LIME_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));   // per device, cheap
     LIME_CUDA(cudaMemsetAsync(a.work_counter, 0, 4 * sizeof(int32_t), st));   // work counter, fallback count, exact counter, stats
+    const int reps = a.cache.tab_replicas > 0 ? a.cache.tab_replicas : 1;
+    CUtensorMap wmap;
+    if (int rc = cand16_tensor_map(a.cache.cand16, (uint64_t)a.cache.news_num + (uint64_t)reps * a.cache.num_buckets * a.cache.num_buckets, &wmap))
+        return rc;
     int grid = 2 * num_sms();
     if (const char *e = getenv("LIME_TC_ONE_CTA_PER_SM")) {      // experiment knob: concurrency vs shared resources
         if (e[0] == '1') grid = num_sms();
     }
     if (grid > a.imp.num_units) grid = a.imp.num_units;
-    score_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
+    score_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(a, wmap);
     LIME_LAUNCH_CHECK("score_tc_kernel");
     return 0;
 }
