@@ -416,11 +416,17 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
 }
 
 // Front end of one work unit, executed by ONE warp (the MMA issuer) while the compute warps work on the previous unit.
-// Part 1: the history slots (keys, bucket pairs, topic ids, gate bounds) into the front-end scratch.  Part 2: dedup of
-// the slots.  Part 3: the candidates (cache rows, lifetime weights, folded scalars), dedup of their bucket pairs and
-// the operand row table.  All results land in the unit buffer `ub`.
-__device__ __forceinline__ void front_hist(const ScoreArgs &args, unsigned char *ub, int unit, int lane, int *hkn, int *hkt,
-                                           int *htp, float *hga) {
+// front_history: the history slots (news, bucket pair, mask, topic id, gate bound), two slots per lane, deduplicated into
+// unique operand rows.  front_cand: the candidates (cache rows, lifetime weights, folded scalars), the distinct bucket
+// pairs among them and the operand-triple table of the TMA copies.  All results land in the unit buffer `ub`.
+//
+// Deduplication: slots with equal (news, bucket pair, mask) -- in practice the zero padding of a short history,
+// dataset.py:123-128 -- are ONE operand row whose multiplicity enters the two attention softmaxes, the pooling softmax
+// and the GraphSAGE prefix means.  Equal keys are found with match.any inside each half (slots 0..31 / 32..63); across the
+// halves only the group of slot 31 is merged (a padding run that starts in the first half covers the whole second half;
+// any other duplicate pair split by the halves stays two rows, which is merely not deduplicated).
+__device__ __forceinline__ uint32_t prefix_bits(int n) { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : (1u << n) - 1u); }
+__device__ __forceinline__ void front_history(const ScoreArgs &args, unsigned char *ub, int unit, int lane) {
     const LimeNewsCache &C = args.cache;
     const LimeImpressions &I = args.imp;
     const int H = I.max_history, nb = C.num_buckets, T = C.num_topics;
@@ -431,37 +437,89 @@ __device__ __forceinline__ void front_hist(const ScoreArgs &args, unsigned char 
         return;
     }
     const int imp = I.unit_imp[unit], pair0 = I.unit_pair0[unit], cnt = I.unit_count[unit];
-    for (int h = lane; h < H; h += 32) {
-        const long long o = (long long)imp * H + h;
-        int n = I.hist_news[o];
-        n = (n < 0 || n >= C.news_num) ? 0 : n;
-        const float2 mt = __ldg(reinterpret_cast<const float2 *>(C.news_meta + (size_t)n * LIME_META_LD));
-        const int tp = __float_as_int(mt.x);
-        const int mk = I.hist_mask[o] != 0 ? 1 : 0;
-        const int bf = bucketize_seconds(I.hist_fresh[o], args.bucket_scale, nb);
-        const int bl = bucketize_seconds(I.hist_life[o], args.bucket_scale, nb);
-        hkn[h] = n;
-        hkt[h] = 2 * (bf * nb + bl) + mk;          // second key word: bucket pair and mask
-        htp[h] = (tp < 0 || tp >= T) ? 0 : tp;
-        hga[h] = mt.y;
-    }
-    // the candidate arrays of the unit: L2 by the time part 3 reads them
+    // raw slot arrays of both slots first, then the dependent news_meta sectors (topic id | max |W_g vc|)
+    const bool va = lane < H, vb = lane + 32 < H;
+    const long long oa = (long long)imp * H + lane, ob = oa + 32;
+    int na = va ? I.hist_news[oa] : 0, nbn = vb ? I.hist_news[ob] : 0;
+    const int mka = va && I.hist_mask[oa] != 0 ? 1 : 0, mkb = vb && I.hist_mask[ob] != 0 ? 1 : 0;
+    const float fra = va ? I.hist_fresh[oa] : 1.0f, frb = vb ? I.hist_fresh[ob] : 1.0f;
+    const float lfa = va ? I.hist_life[oa] : 1.0f, lfb = vb ? I.hist_life[ob] : 1.0f;
+    na = (na < 0 || na >= C.news_num) ? 0 : na;
+    nbn = (nbn < 0 || nbn >= C.news_num) ? 0 : nbn;
+    const float2 mta = __ldg(reinterpret_cast<const float2 *>(C.news_meta + (size_t)na * LIME_META_LD));
+    const float2 mtb = __ldg(reinterpret_cast<const float2 *>(C.news_meta + (size_t)nbn * LIME_META_LD));
+    // the candidate arrays of the unit: L2 by the time front_cand reads them
     for (int j = lane; 32 * j < cnt; j += 32) {
         prefetch_l2(I.cand_news + pair0 + 32 * j);
         prefetch_l2(I.cand_fresh + pair0 + 32 * j);
         prefetch_l2(I.cand_life + pair0 + 32 * j);
         if (I.cand_remaining) prefetch_l2(I.cand_remaining + pair0 + 32 * j);
     }
+    const int bpa = bucketize_seconds(fra, args.bucket_scale, nb) * nb + bucketize_seconds(lfa, args.bucket_scale, nb);
+    const int bpb = bucketize_seconds(frb, args.bucket_scale, nb) * nb + bucketize_seconds(lfb, args.bucket_scale, nb);
+    // keys: (news, 2 * bucket pair + mask); slots beyond H get keys that match nothing
+    const unsigned long long ka = va ? ((unsigned long long)(unsigned)na << 32) | (unsigned)(2 * bpa + mka)
+                                     : 0xffffffff00000000ull | (unsigned)lane;
+    const unsigned long long kb = vb ? ((unsigned long long)(unsigned)nbn << 32) | (unsigned)(2 * bpb + mkb)
+                                     : 0xfffffffe00000000ull | (unsigned)lane;
+    const unsigned maa = __match_any_sync(0xffffffffu, ka), mbb = __match_any_sync(0xffffffffu, kb);
+    const unsigned long long k31 = __shfl_sync(0xffffffffu, ka, 31);
+    const bool dupb = vb && kb == k31;                       // second-half slot that belongs to the group of slot 31
+    const unsigned bdup = __ballot_sync(0xffffffffu, dupb);
+    const bool in31 = va && ka == k31;
+    const bool isfa = va && (__ffs(maa) - 1 == lane);
+    const bool isfb = vb && !dupb && (__ffs(mbb) - 1 == lane);
+    const unsigned b0 = __ballot_sync(0xffffffffu, isfa), b1 = __ballot_sync(0xffffffffu, isfb);
+    const unsigned lt = (1u << lane) - 1u;
+    const int pz0 = args.prefix_main < H ? args.prefix_main : H, pz1 = args.prefix_tail < H ? args.prefix_tail : H;
+    const unsigned pa0 = prefix_bits(pz0), pb0 = prefix_bits(pz0 - 32), pa1 = prefix_bits(pz1), pb1 = prefix_bits(pz1 - 32);
+    int *unews = reinterpret_cast<int *>(ub + UB_UNEWS);
+    int *utab = reinterpret_cast<int *>(ub + UB_UTAB);
+    int *umask = reinterpret_cast<int *>(ub + UB_UMASK);
+    int *utopic = reinterpret_cast<int *>(ub + UB_UTOPIC);
+    float *umult = reinterpret_cast<float *>(ub + UB_UMULT);
+    float *ump0 = reinterpret_cast<float *>(ub + UB_UMP0);
+    float *ump1 = reinterpret_cast<float *>(ub + UB_UMP1);
+    float *ugabs = reinterpret_cast<float *>(ub + UB_UGABS);
+    if (isfa) {
+        const int u = __popc(b0 & lt);
+        const int tp = __float_as_int(mta.x);
+        prefetch_l2_bulk(C.hist_vg + (size_t)na * (2 * kD), 2 * kD * 4);
+        unews[u] = na;
+        utab[u] = bpa;
+        umask[u] = mka;
+        utopic[u] = (tp < 0 || tp >= T) ? 0 : tp;
+        ugabs[u] = mta.y;
+        umult[u] = (float)(__popc(maa) + (in31 ? __popc(bdup) : 0));
+        ump0[u] = (float)(__popc(maa & pa0) + (in31 ? __popc(bdup & pb0) : 0));
+        ump1[u] = (float)(__popc(maa & pa1) + (in31 ? __popc(bdup & pb1) : 0));
+    }
+    if (isfb) {
+        const int u = __popc(b0) + __popc(b1 & lt);
+        const int tp = __float_as_int(mtb.x);
+        prefetch_l2_bulk(C.hist_vg + (size_t)nbn * (2 * kD), 2 * kD * 4);
+        unews[u] = nbn;
+        utab[u] = bpb;
+        umask[u] = mkb;
+        utopic[u] = (tp < 0 || tp >= T) ? 0 : tp;
+        ugabs[u] = mtb.y;
+        umult[u] = (float)__popc(mbb);
+        ump0[u] = (float)__popc(mbb & pb0);
+        ump1[u] = (float)__popc(mbb & pb1);
+    }
+    const int nun = __reduce_add_sync(0xffffffffu, mka + mkb);      // unmasked history slots
     if (lane == 0) {
         info[UI_UNIT] = unit;
         info[UI_IMP] = imp;
         info[UI_PAIR0] = pair0;
         info[UI_CNT] = cnt;
+        info[UI_U] = __popc(b0) + __popc(b1);
+        info[UI_NUN] = nun;
     }
     __syncwarp();
 }
 
-__device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char *ub, int lane, bool pf = true) {
+__device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char *ub, int lane) {
     const LimeNewsCache &C = args.cache;
     const uint32_t tab_row0 = (blockIdx.x % (unsigned)(C.tab_replicas > 0 ? C.tab_replicas : 1)) * (uint32_t)(C.num_buckets * C.num_buckets);
     const LimeImpressions &I = args.imp;
@@ -484,46 +542,61 @@ __device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char 
         cnt = kTriples - 1;
         flags = 4;
     }
-    for (int c = lane; c < cnt; c += 32) {
-        const long long p = (long long)pair0 + c;
-        int n = I.cand_news[p];
-        n = (n < 0 || n >= C.news_num) ? 0 : n;
-        const float fr = I.cand_fresh[p], lf = I.cand_life[p];
-        const float4 m0 = ldg4(C.news_meta + (size_t)n * LIME_META_LD), m1 = ldg4(C.news_meta + (size_t)n * LIME_META_LD + 4);
-        const int tb = bucketize_seconds(fr, args.bucket_scale, nb) * nb + bucketize_seconds(lf, args.bucket_scale, nb);
-        const float *ctr = C.cand_tab + (size_t)tb * LIME_CTAB_LD;
-        const int tp = __float_as_int(m0.x);
-        cnews[c] = n;
-        ctab[c] = tb;
-        cw[c] = lifetime_weight(I.cand_remaining ? I.cand_remaining[p] : __fsub_rn(lf, fr), C);
-        cP[c] = (args.pair_index_base + p >= args.tail_start) ? args.prefix_tail : args.prefix_main;
-        ctopic[c] = (tp < 0 || tp >= T) ? 0 : tp;
-        cscal[c * 4 + 0] = m0.w + __ldg(ctr + LIME_CAND_SCAL + 3);
-        cscal[c * 4 + 1] = m1.x + __ldg(ctr + LIME_CAND_SCAL + 4);
-        cscal[c * 4 + 2] = m1.y + __ldg(ctr + LIME_CAND_SCAL + 5);
-        cscal[c * 4 + 3] = m1.z + __ldg(ctr + LIME_CAND_SCAL + 6);
-        if (!(m0.z <= kWAbsMax)) flags |= 4;       // beyond the fp16 operand range: exact kernel
-        if (pf) prefetch_l2_bulk(reinterpret_cast<const unsigned char *>(C.cand16) + (size_t)n * (2 * kC16), 2 * kC16);
+    // two candidates per lane (c = lane, lane + 32): raw arrays first, then the dependent cache sectors
+    int key[2], nn[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int c = lane + 32 * r;
+        key[r] = -1 - c;
+        nn[r] = 0;
+        if (c < cnt) {
+            const long long p = (long long)pair0 + c;
+            int n = I.cand_news[p];
+            n = (n < 0 || n >= C.news_num) ? 0 : n;
+            const float fr = I.cand_fresh[p], lf = I.cand_life[p];
+            const float rem = I.cand_remaining ? I.cand_remaining[p] : __fsub_rn(lf, fr);
+            const float4 m0 = ldg4(C.news_meta + (size_t)n * LIME_META_LD), m1 = ldg4(C.news_meta + (size_t)n * LIME_META_LD + 4);
+            prefetch_l2_bulk(reinterpret_cast<const unsigned char *>(C.cand16) + (size_t)n * (2 * kC16), 2 * kC16);
+            const int tb = bucketize_seconds(fr, args.bucket_scale, nb) * nb + bucketize_seconds(lf, args.bucket_scale, nb);
+            const float *ctr = C.cand_tab + (size_t)tb * LIME_CTAB_LD + LIME_CAND_SCAL + 3;
+            const float4 ct = make_float4(__ldg(ctr), __ldg(ctr + 1), __ldg(ctr + 2), __ldg(ctr + 3));
+            const int tp = __float_as_int(m0.x);
+            key[r] = tb;
+            nn[r] = n;
+            cnews[c] = n;
+            ctab[c] = tb;
+            cw[c] = lifetime_weight(rem, C);
+            cP[c] = (args.pair_index_base + p >= args.tail_start) ? args.prefix_tail : args.prefix_main;
+            ctopic[c] = (tp < 0 || tp >= T) ? 0 : tp;
+            *reinterpret_cast<float4 *>(cscal + c * 4) = make_float4(m0.w + ct.x, m1.x + ct.y, m1.y + ct.z, m1.z + ct.w);
+            if (!(m0.z <= kWAbsMax)) flags |= 4;       // beyond the fp16 operand range: exact kernel
+        }
     }
-    __syncwarp();
-    // distinct bucket pairs of the unit's candidates (all-pairs scan of <= 39 keys, two candidates per lane)
-    const int ca = lane, cb = lane + 32;
-    const int ka = ca < cnt ? ctab[ca] : -1 - ca, kb = cb < cnt ? ctab[cb] : -1 - cb;
-    int fa = 99, fb = 99;
-    for (int j = cnt - 1; j >= 0; --j) {
-        const int t = ctab[j];
-        fa = t == ka ? j : fa;
-        fb = t == kb ? j : fb;
+    // distinct bucket pairs of the unit's candidates: match.any inside each half, the (<= 7) candidates of the second half
+    // are looked up in the first half one by one
+    const unsigned ma = __match_any_sync(0xffffffffu, key[0]), mb = __match_any_sync(0xffffffffu, key[1]);
+    unsigned cross = 0;
+    for (int b = 0; 32 + b < cnt; ++b) {
+        const int kv = __shfl_sync(0xffffffffu, key[1], b);
+        const unsigned eq = __ballot_sync(0xffffffffu, key[0] == kv);
+        cross = lane == b ? eq : cross;
     }
-    const bool isfa = ca < cnt && fa == ca, isfb = cb < cnt && fb == cb;
+    const bool va = lane < cnt, vb = lane + 32 < cnt;
+    const bool isfa = va && (__ffs(ma) - 1 == lane);
+    const bool isfb = vb && cross == 0u && (__ffs(mb) - 1 == lane);
     const unsigned b0 = __ballot_sync(0xffffffffu, isfa), b1 = __ballot_sync(0xffffffffu, isfb);
     const int nb0 = __popc(b0);
     int nbp = nb0 + __popc(b1);
-    auto compact = [&](int f) { return f < 32 ? __popc(b0 & ((1u << f) - 1u)) : nb0 + __popc(b1 & ((1u << (f - 32)) - 1u)); };
-    if (ca < cnt) cbidx[ca] = min(compact(fa), kMaxBp - 1);
-    if (cb < cnt) cbidx[cb] = min(compact(fb), kMaxBp - 1);
-    if (isfa && compact(ca) < kMaxBp) btab[compact(ca)] = ka;
-    if (isfb && compact(cb) < kMaxBp) btab[compact(cb)] = kb;
+    if (va) {
+        const int ia = __popc(b0 & ((1u << (__ffs(ma) - 1)) - 1u));
+        cbidx[lane] = min(ia, kMaxBp - 1);
+        if (isfa && ia < kMaxBp) btab[ia] = key[0];
+    }
+    if (vb) {
+        const int ib = cross != 0u ? __popc(b0 & ((1u << (__ffs(cross) - 1)) - 1u)) : nb0 + __popc(b1 & ((1u << (__ffs(mb) - 1)) - 1u));
+        cbidx[lane + 32] = min(ib, kMaxBp - 1);
+        if (isfb && ib < kMaxBp) btab[ib] = key[1];
+    }
     if (nbp > kMaxBp || cnt + nbp > kTriples) {     // more bucket pairs than spare operand rows: exact kernel
         flags |= 4;
         nbp = min(min(nbp, kMaxBp), kTriples - cnt);
@@ -545,78 +618,6 @@ __device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char 
         info[UI_FLAGS] = flags;
         info[UI_NBP] = nbp;
         info[UI_CNT] = cnt;
-    }
-    __syncwarp();
-}
-
-// Part 2: deduplication of the history slots into unique operand rows.  Slots with equal (news, bucket pair, mask) --
-// in practice the padding of a short history, dataset.py:123-128 -- are one row.  A lane owns the slots lane and
-// lane + 32 and scans all H keys (broadcast reads, no cross-lane dependency): lowest equal slot = the unique row,
-// number of equal slots = its multiplicity (overall and inside the two GraphSAGE prefixes); one ballot pair then
-// compacts the unique rows in slot order.
-__device__ __forceinline__ void front_dedup(const ScoreArgs &args, unsigned char *ub, int lane, const int *hkn, const int *hkt,
-                                            const int *htp, const float *hga, bool pf = true) {
-    int *info = reinterpret_cast<int *>(ub + UB_INFO);
-    if (info[UI_UNIT] >= args.imp.num_units) return;
-    const int H = args.imp.max_history;
-    int *unews = reinterpret_cast<int *>(ub + UB_UNEWS);
-    int *utab = reinterpret_cast<int *>(ub + UB_UTAB);
-    int *umask = reinterpret_cast<int *>(ub + UB_UMASK);
-    int *utopic = reinterpret_cast<int *>(ub + UB_UTOPIC);
-    float *umult = reinterpret_cast<float *>(ub + UB_UMULT);
-    float *ump0 = reinterpret_cast<float *>(ub + UB_UMP0);
-    float *ump1 = reinterpret_cast<float *>(ub + UB_UMP1);
-    float *ugabs = reinterpret_cast<float *>(ub + UB_UGABS);
-    const int pz0 = args.prefix_main < H ? args.prefix_main : H, pz1 = args.prefix_tail < H ? args.prefix_tail : H;
-    const int ha = lane, hb = lane + 32;
-    const int k1a = ha < H ? hkn[ha] : -1 - ha, k2a = ha < H ? hkt[ha] : -1;
-    const int k1b = hb < H ? hkn[hb] : -1 - hb, k2b = hb < H ? hkt[hb] : -1;
-    int fa = 99, fb = 99, na = 0, nb_ = 0, na0 = 0, nb0 = 0, na1 = 0, nb1 = 0;
-#pragma unroll 4
-    for (int j = H - 1; j >= 0; --j) {          // downwards: the last hit is the lowest equal slot
-        const int n = hkn[j], t = hkt[j];
-        const bool ea = k1a == n && k2a == t, eb = k1b == n && k2b == t;
-        fa = ea ? j : fa;
-        fb = eb ? j : fb;
-        na += ea;
-        nb_ += eb;
-        na0 += ea && j < pz0;
-        nb0 += eb && j < pz0;
-        na1 += ea && j < pz1;
-        nb1 += eb && j < pz1;
-    }
-    const bool isfa = ha < H && fa == ha, isfb = hb < H && fb == hb;
-    const unsigned b0 = __ballot_sync(0xffffffffu, isfa), b1 = __ballot_sync(0xffffffffu, isfb);
-    const unsigned lt = (1u << lane) - 1u;
-    if (pf && isfa) prefetch_l2_bulk(args.cache.hist_vg + (size_t)k1a * (2 * kD), 2 * kD * 4);
-    if (pf && isfb) prefetch_l2_bulk(args.cache.hist_vg + (size_t)k1b * (2 * kD), 2 * kD * 4);
-    if (isfa) {
-        const int u = __popc(b0 & lt);
-        unews[u] = k1a;
-        utab[u] = k2a >> 1;
-        umask[u] = k2a & 1;
-        utopic[u] = htp[ha];
-        ugabs[u] = hga[ha];
-        umult[u] = (float)na;
-        ump0[u] = (float)na0;
-        ump1[u] = (float)na1;
-    }
-    if (isfb) {
-        const int u = __popc(b0) + __popc(b1 & lt);
-        unews[u] = k1b;
-        utab[u] = k2b >> 1;
-        umask[u] = k2b & 1;
-        utopic[u] = htp[hb];
-        ugabs[u] = hga[hb];
-        umult[u] = (float)nb_;
-        ump0[u] = (float)nb0;
-        ump1[u] = (float)nb1;
-    }
-    int nun = (ha < H ? k2a & 1 : 0) + (hb < H ? k2b & 1 : 0);      // unmasked history slots
-    nun = __reduce_add_sync(0xffffffffu, nun);
-    if (lane == 0) {
-        info[UI_U] = __popc(b0) + __popc(b1);
-        info[UI_NUN] = nun;
     }
     __syncwarp();
 }
@@ -667,8 +668,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
         int u0 = 0;
         if (lane == 0) u0 = atomicAdd(args.work_counter, 1);
         u0 = __shfl_sync(0xffffffffu, u0, 0);
-        front_hist(args, base + OFF_UB, u0, lane, hkn, hkt, htp, hga);
-        front_dedup(args, base + OFF_UB, lane, hkn, hkt, htp, hga);
+        front_history(args, base + OFF_UB, u0, lane);
         front_cand(args, base + OFF_UB, lane);
     }
     tc::fence_before_sync();
@@ -861,10 +861,15 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
         } else {
             // ---------------- issuer warp --------------------------------------------------------------
             // claim the next work unit and run parts 1 and 2 of its front end while the compute warps are in phase 1
+#ifdef LIME_TC_PHASE_CLOCKS
+            const long long tf0 = clock64();
+#endif
             if (lane == 0) next_unit = atomicAdd(args.work_counter, 1);
             next_unit = __shfl_sync(0xffffffffu, next_unit, 0);
-            front_hist(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, next_unit, lane, hkn, hkt, htp, hga);
-            front_dedup(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, lane, hkn, hkt, htp, hga);
+            front_history(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, next_unit, lane);
+#ifdef LIME_TC_PHASE_CLOCKS
+            if (lane == 0) atomicAdd(&g_phase_clocks[10], (unsigned long long)(clock64() - tf0));
+#endif
             const uint32_t sb = tc::smem_u32(base);
             const uint32_t idesc1 = tc::idesc_f16_f32(128, 3 * Up), idesc2 = tc::idesc_f16_f32(128, Up);
             const uint64_t bdesc = tc::smem_desc_sw128(sb + OFF_O);
@@ -902,7 +907,13 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
                 }
             }
             // part 3 of the next unit's front end, in the shadow of this unit's epilogue
+#ifdef LIME_TC_PHASE_CLOCKS
+            const long long tf1 = clock64();
+#endif
             front_cand(args, base + OFF_UB + (ubi ^ 1) * kUnitBuf, lane);
+#ifdef LIME_TC_PHASE_CLOCKS
+            if (lane == 0) atomicAdd(&g_phase_clocks[15], (unsigned long long)(clock64() - tf1));
+#endif
         }
 
         if (warp < kCWarps) {

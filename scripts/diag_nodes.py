@@ -36,7 +36,7 @@ with torch.no_grad():
         from lime_cikm25_b200 import _lib
         buf = (ctypes.c_uint64 * 16)()
         _lib.load().lime_score_phase_clocks(buf)
-        names = ["I:wait_Wfull", "I:wait_Ofull", "attn", "centres", "produce", "mma_wait", "epilogue+pool", "merge", "tail", "units", "P:w_slot_wait", "P:copy", "P:compute", "P:o_slot_wait", "P:store+arrive", "-"]
+        names = ["I:wait_Wfull", "I:wait_Ofull", "attn", "centres", "produce", "mma_wait", "epilogue+pool", "merge", "tail", "units", "I:front_hist+dedup", "P:copy", "P:compute", "P:o_slot_wait", "P:store+arrive", "I:front_cand"]
         tot = sum(buf[i] for i in (2, 3, 4, 5, 6, 7, 8))
         print("  phase clocks per unit (thread 0): " + "  ".join("%s %.0f" % (n, buf[i] / max(buf[9], 1)) for i, n in enumerate(names) if i != 9 and n != "-") + "  | total %.0f" % (tot / max(buf[9], 1)))
         wc = dimp.work_counter[:4].tolist()
