@@ -180,7 +180,7 @@ typedef struct {
     float   penalty_beta;       /* config.penalty_scaling_beta                                   */
     int32_t use_lifetime_weighting; /* config.use_remaining_lifetime_weighting                   */
     int32_t use_expired_penalty;    /* config.use_expired_penalty                                */
-    float   topic_logit_absmax; /* max |entry| of topic_table (entries are log2(e)-scaled logits): the tensor-core
+    float   topic_logit_absmax; /* max |log2(entry)| of topic_table (entries are exponentials of the head logits): the tensor-core
                                    path runs its softmax without a max pass and requires this <= 64   */
     int32_t tc_tables_ok;       /* nonzero: ctab16 holds no value beyond the fp16 operand range      */
     int32_t tab_replicas;       /* copies of the bucket-pair tables in hist_tab and in the tail of cand16 (>= 1) */
@@ -235,7 +235,7 @@ int lime_score_impressions(const LimeNewsCache *cache, const LimeImpressions *im
 int     lime_score_configure(int32_t mode, float tolerance);
 /* Candidate-aware attention logits depend on the news only through their (category, subCategory)
  * pair (layers.py:66-70 on the 50-d topic representations), so they are tabulated once per checkpoint:
- *   out[(tc * T + th) * LIME_TOPIC_TAB_LD + head] = log2(e) * Q_head(topic tc) . K_head(topic th) / sqrt(D)
+ *   out[(tc * T + th) * LIME_TOPIC_TAB_LD + head] = exp(Q_head(topic tc) . K_head(topic th) / sqrt(D))   (softmax numerators)
  * topics [T, ldt]: topic representation of every distinct topic (50 used columns);
  * tq [T, ldq]: the [50*10 | 10] candidate-role affine image of the same topics (LIME_CAND_TQ block). */
 int     lime_topic_pair_table(const float *topics, int64_t ldt, const float *tq, int64_t ldq, int32_t T,

@@ -328,17 +328,17 @@ __device__ __forceinline__ void quad_eval(const Quad &q, const RowCtx &c, int d,
     d1 = pack_h2(c1[2], c1[3]);
 }
 
-// Candidate-aware attention weights a[u][c] (layers.py:66-81) of one work unit.  LPC lanes share a candidate, a lane owns
-// the unique rows u = l + LPC * i (i < 4): all 12 table loads of a lane are issued before the first exponential, the 40
-// exponentials stay in registers for both softmaxes.  Head logits come pre-scaled by log2(e) from the topic-pair table
-// (no max pass: the host checks the table's |logit| bound); masked slots (mask == 0 -> -1e9, layers.py:72) contribute
-// exactly 0 unless every slot is masked, in which case both softmaxes are uniform over the H slots.
-template <int LPC, int NW>
-__device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, int cnt, int nun, int warp, int lane,
-                                          const int *ctopic, const int *utopic, const int *umask, const float *umult,
-                                          float *a_s) {
-    constexpr int CPW = 32 / LPC;                 // candidates per warp and round
-    const int l = lane & (LPC - 1), g = lane / LPC;
+// Candidate-aware attention weights a[u][c] (layers.py:66-81) of one work unit.  LPC = 2^lpc_log2 lanes share a candidate,
+// a lane owns the unique rows u = l + LPC * i (i < 4): all 12 table loads of a lane are issued before the first use.  The
+// topic-pair table holds the EXPONENTIALS of the head logits (no max pass: the host checks the table's |logit| bound), so
+// the first softmax costs no MUFU at all; masked slots (mask == 0 -> -1e9, layers.py:72) contribute exactly 0 unless every
+// slot is masked, in which case both softmaxes are uniform over the H slots.  One copy of the code for every LPC (the
+// cross-lane sums are run-time loops): the kernel has to stay inside the instruction cache.
+__device__ __forceinline__ void attention(const float *__restrict__ table, int T, int U, int cnt, int nun, int warp, int lane,
+                                       int lpc_log2, const int *ctopic, const int *utopic, const int *umask, const float *umult,
+                                       float *a_s) {
+    const int LPC = 1 << lpc_log2, CPW = 32 >> lpc_log2;      // candidates per warp and round
+    const int l = lane & (LPC - 1), g = lane >> lpc_log2;
     float w[4], mu[4];
     int tp[4];
 #pragma unroll
@@ -349,14 +349,14 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
         w[i] = (in && umask[u] != 0) ? mu[i] : 0.0f;
         tp[i] = in ? utopic[u] : 0;
     }
-    for (int c0 = CPW * warp; c0 < cnt; c0 += CPW * NW) {
+    for (int c0 = CPW * warp; c0 < cnt; c0 += CPW * kCWarps) {
         const int c = c0 + g;
         const bool cvalid = c < cnt;
         const int cc = cvalid ? c : cnt - 1;
         float e2[4];
         float s2 = 0.0f;
         if (nun > 0) {
-            const float *trow = C.topic_table + (size_t)ctopic[cc] * T * kTabLd;
+            const float *trow = table + (size_t)ctopic[cc] * T * kTabLd;
             float4 x[4][3];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -365,7 +365,7 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
                 x[i][1] = ldg4(r0 + 4);
                 x[i][2] = ldg4(r0 + 8);
             }
-            float e[4][LIME_CA_HEADS], sum[LIME_CA_HEADS];
+            float sum[LIME_CA_HEADS];
 #pragma unroll
             for (int hd = 0; hd < LIME_CA_HEADS; ++hd) sum[hd] = 0.0f;
 #pragma unroll
@@ -373,12 +373,9 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
                 const float xs[LIME_CA_HEADS] = {x[i][0].x, x[i][0].y, x[i][0].z, x[i][0].w, x[i][1].x,
                                                  x[i][1].y, x[i][1].z, x[i][1].w, x[i][2].x, x[i][2].y};
 #pragma unroll
-                for (int hd = 0; hd < LIME_CA_HEADS; ++hd) {
-                    e[i][hd] = ex2_approx(xs[hd]);
-                    sum[hd] = fmaf(w[i], e[i][hd], sum[hd]);
-                }
+                for (int hd = 0; hd < LIME_CA_HEADS; ++hd) sum[hd] = fmaf(w[i], xs[hd], sum[hd]);
             }
-#pragma unroll
+#pragma unroll 1
             for (int o = 1; o < LPC; o <<= 1) {
 #pragma unroll
                 for (int hd = 0; hd < LIME_CA_HEADS; ++hd) sum[hd] += __shfl_xor_sync(0xffffffffu, sum[hd], o);
@@ -387,9 +384,11 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
             for (int hd = 0; hd < LIME_CA_HEADS; ++hd) sum[hd] = __fdividef(1.0f, sum[hd]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
+                const float xs[LIME_CA_HEADS] = {x[i][0].x, x[i][0].y, x[i][0].z, x[i][0].w, x[i][1].x,
+                                                 x[i][1].y, x[i][1].z, x[i][1].w, x[i][2].x, x[i][2].y};
                 float agg = 0.0f;
 #pragma unroll
-                for (int hd = 0; hd < LIME_CA_HEADS; ++hd) agg = fmaf(e[i][hd], sum[hd], agg);
+                for (int hd = 0; hd < LIME_CA_HEADS; ++hd) agg = fmaf(xs[hd], sum[hd], agg);
                 agg = w[i] > 0.0f ? agg : 0.0f;
                 // second, unmasked softmax over the history (layers.py:81); agg in [0, 10]: no max needed
                 e2[i] = ex2_approx(agg * kLog2e);
@@ -402,7 +401,7 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
                 s2 += mu[i];
             }
         }
-#pragma unroll
+#pragma unroll 1
         for (int o = 1; o < LPC; o <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         const float inv2 = __fdividef(1.0f, s2);
         if (cvalid) {
@@ -425,6 +424,10 @@ __device__ __forceinline__ void attention(const LimeNewsCache &C, int T, int U, 
 // and the GraphSAGE prefix means.  Equal keys are found with match.any inside each half (slots 0..31 / 32..63); across the
 // halves only the group of slot 31 is merged (a padding run that starts in the first half covers the whole second half;
 // any other duplicate pair split by the halves stays two rows, which is merely not deduplicated).
+// one copy of the bit-exact (accurate logf) bucketisation in the kernel image
+__device__ __noinline__ int bucket_pair(float fresh, float life, float scale, int nb) {
+    return bucketize_seconds(fresh, scale, nb) * nb + bucketize_seconds(life, scale, nb);
+}
 __device__ __forceinline__ uint32_t prefix_bits(int n) { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : (1u << n) - 1u); }
 __device__ __forceinline__ void front_history(const ScoreArgs &args, unsigned char *ub, int unit, int lane) {
     const LimeNewsCache &C = args.cache;
@@ -455,8 +458,8 @@ __device__ __forceinline__ void front_history(const ScoreArgs &args, unsigned ch
         prefetch_l2(I.cand_life + pair0 + 32 * j);
         if (I.cand_remaining) prefetch_l2(I.cand_remaining + pair0 + 32 * j);
     }
-    const int bpa = bucketize_seconds(fra, args.bucket_scale, nb) * nb + bucketize_seconds(lfa, args.bucket_scale, nb);
-    const int bpb = bucketize_seconds(frb, args.bucket_scale, nb) * nb + bucketize_seconds(lfb, args.bucket_scale, nb);
+    const int bpa = bucket_pair(fra, lfa, args.bucket_scale, nb);
+    const int bpb = bucket_pair(frb, lfb, args.bucket_scale, nb);
     // keys: (news, 2 * bucket pair + mask); slots beyond H get keys that match nothing
     const unsigned long long ka = va ? ((unsigned long long)(unsigned)na << 32) | (unsigned)(2 * bpa + mka)
                                      : 0xffffffff00000000ull | (unsigned)lane;
@@ -557,7 +560,7 @@ __device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char 
             const float rem = I.cand_remaining ? I.cand_remaining[p] : __fsub_rn(lf, fr);
             const float4 m0 = ldg4(C.news_meta + (size_t)n * LIME_META_LD), m1 = ldg4(C.news_meta + (size_t)n * LIME_META_LD + 4);
             prefetch_l2_bulk(reinterpret_cast<const unsigned char *>(C.cand16) + (size_t)n * (2 * kC16), 2 * kC16);
-            const int tb = bucketize_seconds(fr, args.bucket_scale, nb) * nb + bucketize_seconds(lf, args.bucket_scale, nb);
+            const int tb = bucket_pair(fr, lf, args.bucket_scale, nb);
             const float *ctr = C.cand_tab + (size_t)tb * LIME_CTAB_LD + LIME_CAND_SCAL + 3;
             const float4 ct = make_float4(__ldg(ctr), __ldg(ctr + 1), __ldg(ctr + 2), __ldg(ctr + 3));
             const int tp = __float_as_int(m0.x);
@@ -622,7 +625,7 @@ __device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char 
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs args, const __grid_constant__ CUtensorMap wmap) {
+__global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const __grid_constant__ ScoreArgs args, const __grid_constant__ CUtensorMap wmap) {
     // Every shared-memory pointer below is derived from this array by pointer arithmetic only (no integer round trip), so
     // the compiler keeps the shared state space and emits LDS / STS instead of generic loads; the operand tiles need
     // the 1024-byte alignment of the 128-byte swizzle, which the declaration requests and the first thread verifies.
@@ -724,10 +727,8 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
             issue_w_tile(base, bars, &wmap, wrow, cnt + nbp, 1, warp, lane);
             // ---------------- phase 1: candidate-aware attention weights a[u][c] (layers.py:66-81) ------
             // lanes per candidate = the smallest power of two that covers the U rows with 4 rows per lane
-            if (U <= 8)       attention<2, kCWarps>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
-            else if (U <= 16) attention<4, kCWarps>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
-            else if (U <= 32) attention<8, kCWarps>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
-            else              attention<16, kCWarps>(C, T, U, cnt, info[UI_NUN], warp, lane, ctopic, utopic, umask, umult, t_s);
+            attention(C.topic_table, T, U, cnt, info[UI_NUN], warp, lane, U <= 8 ? 1 : (U <= 16 ? 2 : (U <= 32 ? 3 : 4)), ctopic, utopic,
+                      umask, umult, t_s);
             bar_compute();
             LIME_TICK(2);
 
@@ -1082,8 +1083,8 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const ScoreArgs a
     if (warp == kMmaWarp) tc::tmem_dealloc(tmem, 256);
 }
 
-// out[(tc * T + th) * 12 + head] = log2(e) * ( sum_k tq[tc][k * 10 + head] * topics[th][k] + tq[tc][500 + head] )
-// (pre-scaled so that the scoring kernel's softmax is a bare ex2)
+// out[(tc * T + th) * 12 + head] = exp( sum_k tq[tc][k * 10 + head] * topics[th][k] + tq[tc][500 + head] ), the numerator of
+// the head softmax (ex2.approx of the log2(e)-scaled logit, as the scoring kernel used to evaluate it per pair)
 __global__ void topic_pair_table_kernel(const float *__restrict__ topics, int64_t ldt, const float *__restrict__ tq,
                                         int64_t ldq, int T, float *__restrict__ out) {
     __shared__ float q_s[LIME_TOPIC * LIME_CA_HEADS + LIME_CA_HEADS];
@@ -1101,9 +1102,9 @@ __global__ void topic_pair_table_kernel(const float *__restrict__ topics, int64_
         }
         float *o = out + ((size_t)tcand * T + th) * kTabLd;
 #pragma unroll
-        for (int hd = 0; hd < LIME_CA_HEADS; ++hd) o[hd] = acc[hd] * kLog2e;
-        o[10] = 0.0f;
-        o[11] = 0.0f;
+        for (int hd = 0; hd < LIME_CA_HEADS; ++hd) o[hd] = ex2_approx(acc[hd] * kLog2e);
+        o[10] = 1.0f;
+        o[11] = 1.0f;
     }
 }
 

@@ -197,7 +197,7 @@ class ScoringEngine:
         self._topic_ids = {}          # (category, subCategory) key -> compact id
         self._topic_vec = []          # [52] topic representation per id (device)
         self._topic_tq = []           # [510] candidate-role affine image per id (device)
-        self._topic_table = None      # [T, T, 12] log2(e)-scaled head logits, rebuilt when the registry grows
+        self._topic_table = None      # [T, T, 12] exponentials of the head logits, rebuilt when the registry grows
         self._topic_table_n = 0
         self._topic_absmax = 0.0
 
@@ -233,7 +233,7 @@ class ScoringEngine:
                                             tab.data_ptr(), torch.cuda.current_stream().cuda_stream),
                   "lime_topic_pair_table")
             self._topic_table, self._topic_table_n = tab, T
-            self._topic_absmax = float(tab.abs().max())      # one scalar per registry change (host read)
+            self._topic_absmax = float(tab.log2().abs().max())      # max |log2(e)-scaled logit|; one scalar per registry change (host read)
         return self._topic_table, T
 
     # -- fold the user-encoder weights (once per checkpoint) ---------------------------------------
