@@ -66,6 +66,10 @@ constexpr int kMaxBp = 10;                      // distinct bucket pairs of a un
 constexpr int kAS = kTriples;                   // row stride of a_s / t_s  ([u][c])
 constexpr int kStages = 13;                     // 32-wide candidate-operand stages over D = 400 (the last holds 16 dims)
 constexpr int kOStages = 7;                     // 64-wide O stages
+#ifndef LIME_TC_PF_STAGES
+#define LIME_TC_PF_STAGES 1
+#endif
+constexpr int kPfStages = LIME_TC_PF_STAGES;    // L2 prefetch distance of the history rows, in O stages (0 = none)
 constexpr int kWTile = 32768, kWImg = 16384;    // one 64-dim candidate tile = hi image + lo image of 128 rows x 128 B
 constexpr int kGroups = 7;                      // row groups of 8 unique history rows (56 / 8)
 constexpr int kTabLd = LIME_TOPIC_TAB_LD;
@@ -276,8 +280,10 @@ __device__ __forceinline__ void quad_load(Quad &q, const RowCtx &c, int d) {
 #else
         ldg8(c.trow + 2 * d, q.vt, q.gt);
 #endif
-
     }
+    // the same quad kPfStages stages on: the news row slice comes from DRAM, and a whole unit of look-ahead for every CTA
+    // does not fit the L2 (measured: the unit-ahead row prefetch of the front end changes nothing)
+    if (kPfStages > 0 && c.ok && d + 64 * kPfStages < kD) prefetch_l2(c.hrow + 2 * (d + 64 * kPfStages));
 }
 __device__ __forceinline__ void row_ctx_init(RowCtx &rc, const LimeNewsCache &C, const float *bias_s, const float *htab, int u,
                                              int U, const int *unews, const int *utab, const float *mid_s, const float *whalf_s) {
@@ -487,7 +493,6 @@ __device__ __forceinline__ void front_history(const ScoreArgs &args, unsigned ch
     if (isfa) {
         const int u = __popc(b0 & lt);
         const int tp = __float_as_int(mta.x);
-        prefetch_l2_bulk(C.hist_vg + (size_t)na * (2 * kD), 2 * kD * 4);
         unews[u] = na;
         utab[u] = bpa;
         umask[u] = mka;
@@ -500,7 +505,6 @@ __device__ __forceinline__ void front_history(const ScoreArgs &args, unsigned ch
     if (isfb) {
         const int u = __popc(b0) + __popc(b1 & lt);
         const int tp = __float_as_int(mtb.x);
-        prefetch_l2_bulk(C.hist_vg + (size_t)nbn * (2 * kD), 2 * kD * 4);
         unews[u] = nbn;
         utab[u] = bpb;
         umask[u] = mkb;
