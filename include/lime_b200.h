@@ -88,6 +88,13 @@ int lime_linear(const float *A, int64_t lda, const float *W, int64_t ldw, const 
 int lime_linear_bf16(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias,
                      const float *residual, int64_t ldr, float *C, int64_t ldc,
                      int64_t m, int n, int k, int act, void *stream);
+/* The dense layer of "bf16 mode" on bf16 ACTIVATIONS (Stage A cache build): A [m, lda] and W [n, ldw] are bf16 with the
+ * contraction length k padded to a multiple of 64 (<= 512) by zero columns, bias / residual fp32, C bf16 (c_is_bf16 != 0;
+ * columns n..ldc-1 are written as zeros so that C can be the next layer's A) or fp32.  TMA-fed, W slice resident in shared
+ * memory, two TMEM accumulators (csrc/gemm_tma.cu).  Replaces the same reference lines as lime_linear.                   */
+int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, int64_t ldw, const float *bias, const float *residual,
+                         int64_t ldr, void *C, int64_t ldc, int32_t c_is_bf16, int64_t m, int32_t n, int32_t k, int32_t act,
+                         void *stream);
 /* Small general GEMM with arbitrary strides (weight folding, done once per checkpoint):
  * C[i*ldc + j] = alpha * sum_k A[i*sam + k*sak] * B[k*sbk + j*sbn]                                */
 int lime_gemm_strided(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbk,
@@ -98,16 +105,25 @@ int lime_gemm_strided(const float *A, int64_t sam, int64_t sak, const float *B, 
 /* word_embedding(ids) + PositionalEncoding (:311-315, :806-828): out[r, :] = E[ids[r], :] + pe[r % T, :] */
 int lime_embed_pe(const float *E, int64_t vocab, const int32_t *ids, int64_t rows, int T, int d,
                   const float *pe, float *out, void *stream);
+/* lime_embed_pe with a second, bf16 image of every row: out16 [rows, ld16] (columns d..ld16-1 zero), the A operand of
+ * lime_linear_bf16_tma; out stays the fp32 residual stream. */
+int lime_embed_pe_bf16(const float *E, int64_t vocab, const int32_t *ids, int64_t rows, int T, int d, const float *pe,
+                       float *out, void *out16, int32_t ld16, void *stream);
 /* nn.MultiheadAttention core of the TransformerEncoderLayer (:244-247), no mask:
  * qkv [n_news*T, 3*d] (q | k | v) -> ctx [n_news*T, d], softmax(q k^T / sqrt(d/nhead)) v per head.
  * Supported: T in {32, 128}, d/nhead <= 32.                                                      */
 int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, float p_drop, uint64_t seed,
              int64_t news0, void *stream);
+/* the same on bf16 activations (eval only): qkv [n_news*T, ldq] bf16 -> ctx [n_news*T, ldo] bf16, columns d..ldo-1 zero */
+int lime_mha_bf16(const void *qkv, int64_t ldq, void *ctx, int64_t ldo, int64_t n_news, int T, int d, int nhead, void *stream);
 /* p_drop / seed: dropout on the attention weights (training; 0 in eval), stateless mask of (seed, news0 + news, head, i, j)
  * -- news0 is the global index of the call's first news, so a chunked call sees the mask of the whole batch */
 /* nn.LayerNorm over the last dim (eps as given). */
 int lime_layernorm(const float *x, int64_t ldx, const float *gamma, const float *beta, float *y,
                    int64_t ldy, int64_t rows, int d, float eps, void *stream);
+/* lime_layernorm with a second, bf16 image of every row: y16 [rows, ld16] (columns d..ld16-1 zero) */
+int lime_layernorm_bf16(const float *x, int64_t ldx, const float *gamma, const float *beta, float *y, int64_t ldy,
+                        void *y16, int32_t ld16, int64_t rows, int d, float eps, void *stream);
 /* LayerNorm of every token followed by the unmasked mean over the T tokens of a news (:317,:321):
  * x [n_news*T, d] -> out[n, :d] (row stride ldo). */
 int lime_layernorm_meanpool(const float *x, const float *gamma, const float *beta, float *out,

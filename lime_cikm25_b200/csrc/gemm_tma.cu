@@ -1,0 +1,281 @@
+// Dense layer of the news encoder on bf16 ACTIVATIONS (Stage A, "bf16 mode"), sm_100a: TMA + tcgen05 + TMEM.
+//   C = act(A . W^T + bias) + residual      A [m, k] bf16, W [n, k] bf16 (k padded to a multiple of 64 with zeros),
+//                                           bias / residual fp32, C bf16 or fp32, fp32 accumulation in TMEM.
+// Replaces, for newsEncoders.py:244-247 (the four GEMMs of nn.TransformerEncoderLayer, 87 % of the encoder's FLOPs), the
+// fp32-in / fp32-out kernel of gemm_bf16.cu whose producers converted every operand tile from fp32 inside the kernel.
+//
+// The shapes are skinny (k = 320 or 512, n <= 900, m = news x tokens = millions), so the kernel is organised around what
+// is re-used:  ONE persistent CTA per SM owns one N tile (bn <= 256 columns) for its whole life and keeps that slice of
+// W RESIDENT in shared memory (bn x k bf16 <= 160 KB, loaded once by TMA); it then streams 128-row tiles of A through a
+// 3-deep TMA ring (16 KB per 64-wide K block).  Per output tile the tensor core runs k/16 MMAs (M = 128, N = bn) into
+// one of TWO TMEM accumulators (2 x 256 columns), so the epilogue of tile i (TMEM -> registers -> bias / act / residual
+// -> global) overlaps the MMAs of tile i + 1.  The CTAs that share an M tile (one per N tile) run at the same time on
+// neighbouring SMs: A comes from HBM once and from L2 otherwise.
+//
+// Warp roles (192 threads): warps 0-3 epilogue (warp w owns TMEM lanes 32w..32w+31 = rows of the tile), warp 4 TMA
+// producer (one elected lane), warp 5 TMEM allocation + MMA issue (one elected lane).
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+
+#include "tc05.cuh"
+
+namespace lime {
+namespace {
+
+constexpr int GT_M = 128, GT_STAGES = 3, GT_A_BYTES = GT_M * 128;
+constexpr int GT_W_MAX = 160 * 1024;           // resident W slice
+constexpr int GT_THREADS = 192;
+constexpr int GT_SMEM = GT_W_MAX + GT_STAGES * GT_A_BYTES + 1024 /* bias slice */ + 256 /* barriers */;
+static_assert(GT_SMEM + 1024 <= 232448, "shared memory");
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float act_apply(int act, float x) {
+    if (act == 1) return fmaxf(x, 0.0f);
+    if (act == 2) return tanhf(x);
+    return x;
+}
+
+// barriers (uint64 each)
+enum { GB_WFULL = 0, GB_AFULL = 1, GB_AEMPTY = 1 + GT_STAGES, GB_ACCFULL = 1 + 2 * GT_STAGES, GB_ACCEMPTY = 3 + 2 * GT_STAGES };
+
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap,
+                const float *__restrict__ bias, const float *__restrict__ residual, int64_t ldr, void *__restrict__ Cout,
+                int64_t ldc, int c_bf16, int64_t m, int n, int nkb, int bn, int n_tiles, int act) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *base = smem_raw;
+    if (threadIdx.x == 0 && (tc::smem_u32(smem_raw) & 1023u) != 0) __trap();
+    unsigned char *w_s = base;                                     // [nkb][bn rows x 128 B]
+    unsigned char *a_s = base + GT_W_MAX;                          // [GT_STAGES][128 rows x 128 B]
+    float *bias_s = reinterpret_cast<float *>(base + GT_W_MAX + GT_STAGES * GT_A_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + GT_W_MAX + GT_STAGES * GT_A_BYTES + 1024);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nt = (int)(blockIdx.x % (unsigned)n_tiles);          // this CTA's N tile, for its whole life
+    const int col0 = nt * bn;
+    const int64_t m_tiles = (m + GT_M - 1) / GT_M;
+    const int64_t mt0 = blockIdx.x / (unsigned)n_tiles, mt_step = gridDim.x / (unsigned)n_tiles;
+
+    if (tid == 0) {
+        tc::mbar_init(bars + GB_WFULL, 1);
+        for (int s = 0; s < GT_STAGES; ++s) {
+            tc::mbar_init(bars + GB_AFULL + s, 1);
+            tc::mbar_init(bars + GB_AEMPTY + s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(bars + GB_ACCFULL + a, 1);
+            tc::mbar_init(bars + GB_ACCEMPTY + a, 4);              // one arrival per epilogue warp
+        }
+        tc::mbar_fence_init();
+    }
+    for (int i = tid; i < bn; i += GT_THREADS) bias_s[i] = (bias != nullptr && col0 + i < n) ? bias[col0 + i] : 0.0f;
+    if (warp == 5) tc::tmem_alloc(tmem_slot, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            mbar_expect_tx(bars + GB_WFULL, (uint32_t)(nkb * bn * 128));
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(tc::smem_u32(w_s) + (uint32_t)(kb * bn * 128), &wmap, 64 * kb, col0, bars + GB_WFULL);
+            uint32_t it = 0;
+            for (int64_t mt = mt0; mt < m_tiles; mt += mt_step) {
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = (int)(it % GT_STAGES);
+                    const uint32_t ph = (it / GT_STAGES) & 1u;
+                    tc::mbar_wait(bars + GB_AEMPTY + s, ph ^ 1u);
+                    mbar_expect_tx(bars + GB_AFULL + s, GT_A_BYTES);
+                    tma_load_2d(tc::smem_u32(a_s) + (uint32_t)(s * GT_A_BYTES), &amap, 64 * kb, (int)(mt * GT_M), bars + GB_AFULL + s);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            const uint32_t idesc = tc::idesc_bf16_f32(GT_M, bn);
+            tc::mbar_wait(bars + GB_WFULL, 0);
+            tc::fence_after_sync();
+            uint32_t it = 0, tile = 0;
+            for (int64_t mt = mt0; mt < m_tiles; mt += mt_step, ++tile) {
+                const uint32_t acc = tile & 1u;
+                tc::mbar_wait(bars + GB_ACCEMPTY + acc, ((tile >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
+                tc::fence_after_sync();
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = (int)(it % GT_STAGES);
+                    tc::mbar_wait(bars + GB_AFULL + s, (it / GT_STAGES) & 1u);
+                    tc::fence_after_sync();
+                    const uint64_t da = tc::smem_desc_sw128(tc::smem_u32(a_s) + (uint32_t)(s * GT_A_BYTES));
+                    const uint64_t db = tc::smem_desc_sw128(tc::smem_u32(w_s) + (uint32_t)(kb * bn * 128));
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        tc::mma_bf16(tmem + acc * 256u, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (kb | ks) != 0);
+                    tc::mma_commit(bars + GB_AEMPTY + s);
+                }
+                tc::mma_commit(bars + GB_ACCFULL + acc);
+            }
+        }
+    } else {
+        // ---------------- epilogue (warps 0-3) ----------------
+        uint32_t tile = 0;
+        const int ncols = min(bn, n - col0);                       // real columns of this N tile
+        const bool pad = c_bf16 && nt == n_tiles - 1;              // bf16 output: the padding columns [n, ldc) are written as zeros
+        for (int64_t mt = mt0; mt < m_tiles; mt += mt_step, ++tile) {
+            const uint32_t acc = tile & 1u;
+            tc::mbar_wait(bars + GB_ACCFULL + acc, (tile >> 1) & 1u);
+            tc::fence_after_sync();
+            const int64_t r = mt * GT_M + warp * 32 + lane;
+            const uint32_t tlane = tmem + acc * 256u + ((uint32_t)(warp * 32) << 16);
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tlane + (uint32_t)c0, v);
+                if (r < m) {
+                    const int c = col0 + c0;
+                    const int lim = min(32, ncols - c0);
+                    float x[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) x[e] = act_apply(act, __uint_as_float(v[e]) + bias_s[c0 + e]);
+                    if (residual != nullptr) {
+                        const float *rp = residual + r * ldr + c;
+                        if (lim == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 rr = __ldg(reinterpret_cast<const float4 *>(rp) + q);
+                                x[4 * q] += rr.x; x[4 * q + 1] += rr.y; x[4 * q + 2] += rr.z; x[4 * q + 3] += rr.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e)
+                                if (e < lim) x[e] += rp[e];
+                        }
+                    }
+                    if (c_bf16) {
+                        __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(Cout) + r * ldc + c;
+                        if (lim == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 o;
+                                o.x = tc::pack_bf16(x[8 * q], x[8 * q + 1]);
+                                o.y = tc::pack_bf16(x[8 * q + 2], x[8 * q + 3]);
+                                o.z = tc::pack_bf16(x[8 * q + 4], x[8 * q + 5]);
+                                o.w = tc::pack_bf16(x[8 * q + 6], x[8 * q + 7]);
+                                reinterpret_cast<uint4 *>(op)[q] = o;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e)
+                                if (e < lim) op[e] = __float2bfloat16_rn(x[e]);
+                        }
+                    } else {
+                        float *op = reinterpret_cast<float *>(Cout) + r * ldc + c;
+                        if (lim == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) reinterpret_cast<float4 *>(op)[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e)
+                                if (e < lim) op[e] = x[e];
+                        }
+                    }
+                }
+            }
+            if (pad && r < m) {
+                __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(Cout) + r * ldc;
+                for (int64_t c = n; c < ldc; ++c) op[c] = __float2bfloat16_rn(0.0f);
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(bars + GB_ACCEMPTY + acc);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 5) tc::tmem_dealloc(tmem, 512);
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                             const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int tensor_map_bf16_2d(CUtensorMap *out, const void *ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+    static std::mutex mu;
+    static EncodeFn encode = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (encode == nullptr) {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            LIME_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+            LIME_CHECK_ARG(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+            encode = reinterpret_cast<EncodeFn>(fn);
+        }
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)(ld * 2)};
+    const cuuint32_t box[2] = {64, box_rows}, estr[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LIME_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: CUresult %d (cols %llu rows %llu ld %llu)", (int)r,
+                   (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld);
+    return 0;
+}
+
+}  // namespace
+}  // namespace lime
+
+extern "C" int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, int64_t ldw, const float *bias,
+                                    const float *residual, int64_t ldr, void *C, int64_t ldc, int32_t c_is_bf16,
+                                    int64_t m, int32_t n, int32_t k, int32_t act, void *stream) {
+    using namespace lime;
+    LIME_CHECK_ARG(A && W && C, "lime_linear_bf16_tma: null argument");
+    LIME_CHECK_ARG(k >= 64 && k % 64 == 0 && k <= 512, "lime_linear_bf16_tma: k=%d must be a multiple of 64 in [64, 512] (pad with zeros)", k);
+    LIME_CHECK_ARG(n >= 1 && lda >= k && ldw >= k && lda % 8 == 0 && ldw % 8 == 0 && ldc >= n,
+                   "lime_linear_bf16_tma: bad leading dimensions (lda %lld ldw %lld ldc %lld, n %d k %d)", (long long)lda,
+                   (long long)ldw, (long long)ldc, n, k);
+    LIME_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "lime_linear_bf16_tma: operands must be 16-byte aligned");
+    LIME_CHECK_ARG(act >= 0 && act <= 2, "lime_linear_bf16_tma: act=%d", act);
+    if (m <= 0) return 0;
+    const int nkb = k / 64;
+    // N tile: the widest multiple of 32 (<= 256) whose W slice fits the resident area, then balanced over the tiles
+    int bn_max = GT_W_MAX / (nkb * 128);
+    bn_max = bn_max > 256 ? 256 : (bn_max / 32) * 32;
+    const int n_tiles = (n + bn_max - 1) / bn_max;
+    int bn = (((n + n_tiles - 1) / n_tiles) + 31) / 32 * 32;
+    LIME_CHECK_ARG(bn <= bn_max && n_tiles <= 64, "lime_linear_bf16_tma: n=%d does not tile", n);
+    CUtensorMap amap, wmap;
+    if (int rc = tensor_map_bf16_2d(&amap, A, (uint64_t)k, (uint64_t)m, (uint64_t)lda, GT_M)) return rc;
+    if (int rc = tensor_map_bf16_2d(&wmap, W, (uint64_t)k, (uint64_t)n, (uint64_t)ldw, (uint32_t)bn)) return rc;
+    LIME_CUDA(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
+    const int64_t m_tiles = (m + GT_M - 1) / GT_M;
+    int groups = num_sms() / n_tiles;
+    if (groups < 1) groups = 1;
+    if (groups > m_tiles) groups = (int)m_tiles;
+    gemm_tma_kernel<<<groups * n_tiles, GT_THREADS, GT_SMEM, as_stream(stream)>>>(amap, wmap, bias, residual, ldr, C, ldc, c_is_bf16, m, n,
+                                                                                    nkb, bn, n_tiles, act);
+    LIME_LAUNCH_CHECK("gemm_tma_kernel");
+    return 0;
+}

@@ -2,6 +2,7 @@
 // newsEncoders.CROWN.forward (newsEncoders.py:302-373) and FreshnessEncoder (:53-83) that is not a
 // dense layer.  The dense layers are lime_linear / lime_linear_bf16.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace lime {
 
@@ -29,14 +30,46 @@ embed_pe_kernel(const float *__restrict__ E, int64_t vocab, const int32_t *__res
     reinterpret_cast<float4 *>(out)[idx] = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
 }
 
+// the same with a second, bf16 image of the row (the A operand of the TMA GEMM): [rows, ld16], columns d.. zero
+__global__ void __launch_bounds__(256)
+embed_pe_bf16_kernel(const float *__restrict__ E, int64_t vocab, const int32_t *__restrict__ ids, int64_t rows, int T, int d4,
+                     const float *__restrict__ pe, float *__restrict__ out, __nv_bfloat16 *__restrict__ out16, int ld16) {
+    const int q4 = ld16 / 4;                         // 4-element pieces per bf16 row (incl. padding)
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * q4) return;
+    const int64_t r = idx / q4;
+    const int q = (int)(idx - r * q4);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < d4) {
+        int64_t id = ids[r];
+        id = (id < 0 || id >= vocab) ? 0 : id;
+        const float4 e = reinterpret_cast<const float4 *>(E)[id * d4 + q];
+        const float4 p = reinterpret_cast<const float4 *>(pe)[(r % T) * d4 + q];
+        o = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+        reinterpret_cast<float4 *>(out)[r * d4 + q] = o;
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t *>(&lo);
+    pk.y = *reinterpret_cast<uint32_t *>(&hi);
+    *reinterpret_cast<uint2 *>(out16 + r * ld16 + 4 * q) = pk;
+}
+
 // ---- multi-head self-attention core, no mask (nn.MultiheadAttention inside the encoder layer) ---
 // 128 threads: one query row per thread, G = 128/T heads of one news per block.  K and V of the
 // block's heads sit in shared memory (rows padded to 32 floats); every thread walks the same key j
 // at the same time, so all K/V reads are warp broadcasts.  Online softmax in chunks of 8 keys.
-template <int T>
+__device__ __forceinline__ float ldf(const float *p) { return *p; }
+__device__ __forceinline__ float ldf(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float *p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+
+// QT / OT = float (fp32 mode and the training path) or bf16 (Stage A in bf16 mode: qkv [rows, ldq] from the TMA GEMM, ctx
+// [rows, ldo] is the next GEMM's A operand, K-padded with zeros to ldo columns)
+template <int T, typename QT, typename OT>
 __global__ void __launch_bounds__(128)
-mha_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int nhead, int hd, float scale, float p_drop,
-           uint64_t seed, int64_t news0) {
+mha_kernel(const QT *__restrict__ qkv, OT *__restrict__ ctx, int64_t ld, int64_t ldo, int d, int nhead, int hd, float scale,
+           float p_drop, uint64_t seed, int64_t news0) {
     constexpr int G = 128 / T;
     constexpr int HP = 32;
     __shared__ __align__(16) float Ks[G][T][HP];
@@ -44,8 +77,7 @@ mha_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int nh
     const int64_t news = blockIdx.y;
     const int head0 = blockIdx.x * G;
     const int tid = threadIdx.x;
-    const int64_t ld = 3 * (int64_t)d;
-    const float *base = qkv + news * T * ld;
+    const QT *base = qkv + news * T * ld;
 
     for (int idx = tid; idx < G * T * HP; idx += 128) {
         const int e = idx % HP;
@@ -54,8 +86,8 @@ mha_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int nh
         const int head = head0 + g;
         float kv = 0.f, vv = 0.f;
         if (head < nhead && e < hd) {
-            kv = base[j * ld + d + head * hd + e];
-            vv = base[j * ld + 2 * d + head * hd + e];
+            kv = ldf(base + j * ld + d + head * hd + e);
+            vv = ldf(base + j * ld + 2 * d + head * hd + e);
         }
         Ks[g][j][e] = kv;
         Vs[g][j][e] = vv;
@@ -69,7 +101,7 @@ mha_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int nh
     float q[HP], acc[HP];
 #pragma unroll
     for (int e = 0; e < HP; ++e) {
-        q[e] = (e < hd) ? base[i * ld + head * hd + e] * scale : 0.0f;
+        q[e] = (e < hd) ? ldf(base + i * ld + head * hd + e) * scale : 0.0f;
         acc[e] = 0.0f;
     }
     float m = -INFINITY, l = 0.0f;
@@ -119,10 +151,150 @@ mha_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int nh
         m = mn;
     }
     const float inv = 1.0f / l;
-    float *o = ctx + (news * T + i) * (int64_t)d + head * hd;
+    OT *o = ctx + (news * T + i) * ldo + head * hd;
 #pragma unroll
     for (int e = 0; e < HP; ++e)
-        if (e < hd) o[e] = acc[e] * inv;
+        if (e < hd) stf(o + e, acc[e] * inv);
+    if (head == nhead - 1) {                    // K padding of the next GEMM's operand
+        for (int64_t c = d; c < ldo; ++c) stf(ctx + (news * T + i) * ldo + c, 0.0f);
+    }
+}
+
+// ---- the same attention core on the tensor cores, bf16 activations (Stage A in bf16 mode) ---------------------------
+// One CTA = one news, 8 warps; a warp owns 16 query rows of one head, so T / 16 warps cover a head and 8 / (T / 16)
+// heads are in flight per pass (T = 128: one head per pass, T = 32: four).  Q, K, V head slices sit in shared memory as
+// [T][40] bf16 (30 dims, zero padded; the 80-byte pitch keeps ldmatrix conflict-free).  S = Q K^T by mma.m16n8k16 with
+// the whole key range in registers (T / 8 accumulator tiles: no online softmax needed), softmax on the accumulator
+// fragments (row max / sum across the 4 lanes of a quad), P re-used in place as the A fragments of O = P V (V through
+// ldmatrix.trans).  tcgen05 would need M = 128 query rows per instruction and a TMEM round trip for the softmax of a
+// 30-dim head; the warp-level MMA keeps the 9 % of the encoder's FLOPs that live here off the FP32 pipe.
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void *p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void *p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+template <int T>
+__global__ void __launch_bounds__(256)
+mha_tc_kernel(const __nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restrict__ ctx, int64_t ld, int64_t ldo, int d, int nhead,
+              int hd, float scale_log2e) {
+    constexpr int WPH = T / 16;                 // warps per head
+    constexpr int HPC = 8 / WPH;                // heads per pass
+    constexpr int P = 40;                       // shared-memory row pitch (bf16 elements)
+    constexpr int NT = T / 8;                   // key tiles of S
+    __shared__ __align__(16) __nv_bfloat16 Qs[HPC][T][P];
+    __shared__ __align__(16) __nv_bfloat16 Ks[HPC][T][P];
+    __shared__ __align__(16) __nv_bfloat16 Vs[HPC][T][P];
+    const int64_t news = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const __nv_bfloat16 *base = qkv + news * T * ld;
+    const int hw = hd / 2;                      // bf16 pairs per head slice (hd even)
+    // zero the padding columns once (dims hd..31 must be zero, 32..39 are never read)
+    for (int i = tid; i < HPC * T * 3; i += 256) {
+        const int m = i % 3, r = (i / 3) % T, g = i / (3 * T);
+        __nv_bfloat16 *row = m == 0 ? &Qs[g][r][0] : (m == 1 ? &Ks[g][r][0] : &Vs[g][r][0]);
+        for (int c = hd; c < 32; ++c) row[c] = __float2bfloat16_rn(0.0f);
+    }
+    const int g = warp / WPH, r0 = 16 * (warp % WPH);
+    for (int head0 = 0; head0 < nhead; head0 += HPC) {
+        __syncthreads();                        // the previous pass no longer reads the tiles
+        for (int i = tid; i < HPC * 3 * T * hw; i += 256) {
+            const int c = i % hw, r = (i / hw) % T, m = (i / (hw * T)) % 3, gg = i / (hw * T * 3);
+            const int head = head0 + gg;
+            if (head < nhead) {
+                const uint32_t v = *reinterpret_cast<const uint32_t *>(base + r * ld + m * d + head * hd + 2 * c);
+                __nv_bfloat16 *row = m == 0 ? &Qs[gg][r][0] : (m == 1 ? &Ks[gg][r][0] : &Vs[gg][r][0]);
+                *reinterpret_cast<uint32_t *>(row + 2 * c) = v;
+            }
+        }
+        __syncthreads();
+        const int head = head0 + g;
+        if (head >= nhead) continue;
+        // ---- S = Q K^T (16 x T per warp) ----
+        uint32_t qa[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ldsm_x4(qa[ks], &Qs[g][r0 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * ks + 8 * (lane >> 4)]);
+        float sacc[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.0f;
+            uint32_t kb[4];
+            ldsm_x4(kb, &Ks[g][8 * j + (lane & 7)][8 * (lane >> 3)]);
+            mma_bf16_16816(sacc[j], qa[0], kb[0], kb[1]);
+            mma_bf16_16816(sacc[j], qa[1], kb[2], kb[3]);
+        }
+        // ---- softmax over the keys: rows lane / 4 (c0, c1) and lane / 4 + 8 (c2, c3) ----
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            m0 = fmaxf(m0, fmaxf(sacc[j][0], sacc[j][1]));
+            m1 = fmaxf(m1, fmaxf(sacc[j][2], sacc[j][3]));
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float l0 = 0.0f, l1 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            sacc[j][0] = exp2f((sacc[j][0] - m0) * scale_log2e);
+            sacc[j][1] = exp2f((sacc[j][1] - m0) * scale_log2e);
+            sacc[j][2] = exp2f((sacc[j][2] - m1) * scale_log2e);
+            sacc[j][3] = exp2f((sacc[j][3] - m1) * scale_log2e);
+            l0 += sacc[j][0] + sacc[j][1];
+            l1 += sacc[j][2] + sacc[j][3];
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        // ---- O = P V (16 x 32 per warp) ----
+        float oacc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.0f;
+#pragma unroll
+        for (int kk = 0; kk < T / 16; ++kk) {
+            uint32_t pa[4];
+            pa[0] = pack2_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
+            pa[1] = pack2_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
+            pa[2] = pack2_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+            pa[3] = pack2_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
+#pragma unroll
+            for (int jp = 0; jp < 2; ++jp) {
+                uint32_t vb[4];
+                ldsm_x4_trans(vb, &Vs[g][16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
+                mma_bf16_16816(oacc[2 * jp], pa, vb[0], vb[1]);
+                mma_bf16_16816(oacc[2 * jp + 1], pa, vb[2], vb[3]);
+            }
+        }
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        __nv_bfloat16 *o0 = ctx + (news * T + r0 + (lane >> 2)) * ldo + head * hd, *o1 = o0 + 8 * ldo;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = 8 * j + 2 * (lane & 3);
+            if (c < hd) {
+                *reinterpret_cast<uint32_t *>(o0 + c) = pack2_bf16(oacc[j][0] * i0, oacc[j][1] * i0);
+                *reinterpret_cast<uint32_t *>(o1 + c) = pack2_bf16(oacc[j][2] * i1, oacc[j][3] * i1);
+            }
+        }
+    }
+    // K padding of the next GEMM's operand
+    for (int64_t i = tid; i < (int64_t)T * (ldo - d); i += 256) {
+        const int64_t r = i / (ldo - d), c = d + i % (ldo - d);
+        ctx[(news * T + r) * ldo + c] = __float2bfloat16_rn(0.0f);
+    }
 }
 
 // ---- LayerNorm (two-pass, like ATen) ------------------------------------------------------------
@@ -168,6 +340,23 @@ layernorm_kernel(const float *__restrict__ x, int64_t ldx, const float *__restri
     for (int i = 0; i < kLnMaxPerLane; ++i) {
         const int c = lane + 32 * i;
         if (c < d) y[r * ldy + c] = o[i];
+    }
+}
+
+// the same with a second, bf16 image of the row (the A operand of the TMA GEMM): [rows, ld16], columns d.. zero
+__global__ void __launch_bounds__(256)
+layernorm_bf16_kernel(const float *__restrict__ x, int64_t ldx, const float *__restrict__ gamma, const float *__restrict__ beta,
+                      float *__restrict__ y, int64_t ldy, __nv_bfloat16 *__restrict__ y16, int ld16, int64_t rows, int d, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    float o[kLnMaxPerLane];
+    ln_row(x + r * ldx, d, lane, eps, gamma, beta, o);
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        if (c < d) y[r * ldy + c] = o[i];
+        if (c < ld16) y16[r * ld16 + c] = __float2bfloat16_rn(c < d ? o[i] : 0.0f);
     }
 }
 
@@ -351,6 +540,18 @@ extern "C" int lime_embed_pe(const float *E, int64_t vocab, const int32_t *ids, 
     return 0;
 }
 
+extern "C" int lime_embed_pe_bf16(const float *E, int64_t vocab, const int32_t *ids, int64_t rows, int T, int d, const float *pe,
+                                  float *out, void *out16, int32_t ld16, void *stream) {
+    LIME_CHECK_ARG(E && ids && pe && out && out16, "lime_embed_pe_bf16: null argument");
+    LIME_CHECK_ARG((d & 3) == 0 && T > 0 && vocab > 0 && ld16 >= d && (ld16 & 7) == 0, "lime_embed_pe_bf16: d=%d ld16=%d", d, ld16);
+    if (rows <= 0) return 0;
+    const int64_t total = rows * (ld16 / 4);
+    embed_pe_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(E, vocab, ids, rows, T, d / 4, pe, out,
+                                                                                       reinterpret_cast<__nv_bfloat16 *>(out16), ld16);
+    LIME_LAUNCH_CHECK("embed_pe_bf16_kernel");
+    return 0;
+}
+
 extern "C" int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, float p_drop, uint64_t seed,
                         int64_t news0, void *stream) {
     LIME_CHECK_ARG(qkv && ctx, "lime_mha: null argument");
@@ -362,10 +563,40 @@ extern "C" int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int
     const float scale = 1.0f / sqrtf((float)hd);
     if (T == 32) {
         dim3 grid((nhead + 3) / 4, (unsigned)n_news);
-        mha_kernel<32><<<grid, 128, 0, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale, p_drop, seed, news0);
+        mha_kernel<32, float, float><<<grid, 128, 0, as_stream(stream)>>>(qkv, ctx, 3 * (int64_t)d, d, d, nhead, hd, scale, p_drop, seed, news0);
     } else {
         dim3 grid(nhead, (unsigned)n_news);
-        mha_kernel<128><<<grid, 128, 0, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale, p_drop, seed, news0);
+        mha_kernel<128, float, float><<<grid, 128, 0, as_stream(stream)>>>(qkv, ctx, 3 * (int64_t)d, d, d, nhead, hd, scale, p_drop, seed, news0);
+    }
+    LIME_LAUNCH_CHECK("mha_kernel");
+    return 0;
+}
+
+extern "C" int lime_mha_bf16(const void *qkv, int64_t ldq, void *ctx, int64_t ldo, int64_t n_news, int T, int d, int nhead,
+                             void *stream) {
+    LIME_CHECK_ARG(qkv && ctx, "lime_mha_bf16: null argument");
+    LIME_CHECK_ARG(nhead > 0 && d % nhead == 0 && d / nhead <= 32, "lime_mha_bf16: head dim %d unsupported (<= 32)", nhead ? d / nhead : -1);
+    LIME_CHECK_ARG(T == 32 || T == 128, "lime_mha_bf16: T=%d unsupported (32 or 128)", T);
+    LIME_CHECK_ARG(ldq >= 3 * d && ldo >= d, "lime_mha_bf16: bad leading dimensions");
+    LIME_CHECK_ARG(n_news <= 65535, "lime_mha_bf16: at most 65535 news per call (got %lld)", (long long)n_news);
+    if (n_news <= 0) return 0;
+    const int hd = d / nhead;
+    const float scale = 1.0f / sqrtf((float)hd);
+    const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16 *>(qkv);
+    __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(ctx);
+    if (hd % 2 == 0 && d % 2 == 0 && ldq % 2 == 0 && ldo % 2 == 0 && ((uintptr_t)qkv & 3) == 0 && ((uintptr_t)ctx & 3) == 0) {
+        const float sl = scale * 1.4426950408889634f;
+        if (T == 32) mha_tc_kernel<32><<<(unsigned)n_news, 256, 0, as_stream(stream)>>>(q, o, ldq, ldo, d, nhead, hd, sl);
+        else mha_tc_kernel<128><<<(unsigned)n_news, 256, 0, as_stream(stream)>>>(q, o, ldq, ldo, d, nhead, hd, sl);
+        LIME_LAUNCH_CHECK("mha_tc_kernel");
+        return 0;
+    }
+    if (T == 32) {
+        dim3 grid((nhead + 3) / 4, (unsigned)n_news);
+        mha_kernel<32, __nv_bfloat16, __nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(q, o, ldq, ldo, d, nhead, hd, scale, 0.0f, 0, 0);
+    } else {
+        dim3 grid(nhead, (unsigned)n_news);
+        mha_kernel<128, __nv_bfloat16, __nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(q, o, ldq, ldo, d, nhead, hd, scale, 0.0f, 0, 0);
     }
     LIME_LAUNCH_CHECK("mha_kernel");
     return 0;
@@ -378,6 +609,17 @@ extern "C" int lime_layernorm(const float *x, int64_t ldx, const float *gamma, c
     if (rows <= 0) return 0;
     layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(x, ldx, gamma, beta, y, ldy, rows, d, eps);
     LIME_LAUNCH_CHECK("layernorm_kernel");
+    return 0;
+}
+
+extern "C" int lime_layernorm_bf16(const float *x, int64_t ldx, const float *gamma, const float *beta, float *y, int64_t ldy,
+                                   void *y16, int32_t ld16, int64_t rows, int d, float eps, void *stream) {
+    LIME_CHECK_ARG(x && gamma && beta && y && y16, "lime_layernorm_bf16: null argument");
+    LIME_CHECK_ARG(d > 0 && d <= 32 * kLnMaxPerLane && ld16 >= d && ld16 <= 32 * kLnMaxPerLane, "lime_layernorm_bf16: d=%d ld16=%d unsupported (<= 512)", d, ld16);
+    if (rows <= 0) return 0;
+    layernorm_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(x, ldx, gamma, beta, y, ldy,
+                                                                                   reinterpret_cast<__nv_bfloat16 *>(y16), ld16, rows, d, eps);
+    LIME_LAUNCH_CHECK("layernorm_bf16_kernel");
     return 0;
 }
 

@@ -110,6 +110,15 @@ class NewsEncoderEngine:
                         n2_w=l.norm2.weight.detach(), n2_b=l.norm2.bias.detach(),
                         eps1=l.norm1.eps, eps2=l.norm2.eps)
         P["title"], P["body"] = tr(base.title_transformer), tr(base.body_transformer)
+
+        def pad16(w):        # [n, k] fp32 -> bf16 [n, k padded to a multiple of 64 with zeros]: operand of lime_linear_bf16_tma
+            n_, k_ = w.shape
+            o = torch.zeros(n_, (k_ + 63) // 64 * 64, dtype=torch.bfloat16, device=dev)
+            o[:, :k_].copy_(w)
+            return o
+        for br in (P["title"], P["body"]):
+            for name in ("in_w", "out_w", "l1_w", "l2_w"):
+                br[name + "16"] = pad16(br[name])
         P["title_pe"] = base.title_pos_encoder.pe.detach().reshape(-1, 300).contiguous()
         P["body_pe"] = base.body_pos_encoder.pe.detach().reshape(-1, 300).contiguous()
         pw = m.project.weight.detach()                    # [400, 1800] = [W_c | W_f]
@@ -136,6 +145,28 @@ class NewsEncoderEngine:
         y2 = ops.linear(hf, W["l2_w"], W["l2_b"], residual=x1, out=y, bf16=self.bf16)
         ops.layernorm_meanpool(y2, W["n2_w"], W["n2_b"], feat, n, T, eps=W["eps2"])
 
+    def _branch_bf16(self, ids, T, W, pe, feat):
+        """The same branch in bf16 mode: bf16 activations feed TMA + tcgen05 GEMMs (lime_linear_bf16_tma); the residual
+        stream and both LayerNorm inputs stay fp32."""
+        base = self.m.base_news_encoder
+        n = ids.shape[0]
+        rows = n * T
+        dev = ids.device
+        E = base.word_embedding.weight.detach()
+        kp = W["in_w16"].shape[1]                                                   # 300 -> 320
+        x0 = torch.empty(rows, 300, dtype=torch.float32, device=dev)
+        x0b = torch.empty(rows, kp, dtype=torch.bfloat16, device=dev)
+        ops.embed_pe_bf16(E, ids, T, pe, x0, x0b)
+        qkv = ops.linear_tma(x0b, W["in_w16"], W["in_b"], ld_out=904)               # bf16 [rows, 904] (16-byte rows)
+        ctxb = torch.empty(rows, kp, dtype=torch.bfloat16, device=dev)
+        ops.mha_bf16(qkv, ctxb, n, T, 300, self.cfg.head_num)
+        del qkv
+        y = ops.linear_tma(ctxb, W["out_w16"], W["out_b"], residual=x0, out_bf16=False)
+        x1, x1b = ops.layernorm_bf16(y, W["n1_w"], W["n1_b"], x0, x0b, eps=W["eps1"])      # reuse x0 / x0b
+        hf = ops.linear_tma(x1b, W["l1_w16"], W["l1_b"], act=ops.ACT_RELU)           # bf16 [rows, 512]
+        y2 = ops.linear_tma(hf, W["l2_w16"], W["l2_b"], residual=x1, out=y)
+        ops.layernorm_meanpool(y2, W["n2_w"], W["n2_b"], feat, n, T, eps=W["eps2"])
+
     def encode_content(self, title_text, body_text, category, subCategory):
         """newsEncoders.CROWN.forward, flat over news: int32 [n,32], [n,128], [n], [n] -> fp32 [n,900]."""
         P = self.prepare()
@@ -145,8 +176,9 @@ class NewsEncoderEngine:
         f32 = dict(dtype=torch.float32, device=dev)
         feat_t = torch.empty(n, 352, **f32)
         feat_b = torch.empty(n, 352, **f32)
-        self._branch(title_text, 32, P["title"], P["title_pe"], feat_t)
-        self._branch(body_text, 128, P["body"], P["body_pe"], feat_b)
+        branch = self._branch_bf16 if self.bf16 else self._branch
+        branch(title_text, 32, P["title"], P["title_pe"], feat_t)
+        branch(body_text, 128, P["body"], P["body_pe"], feat_b)
         # category-aware intent disentanglement (:340-356): topic from CROWN's own tables
         for feat in (feat_t, feat_b):
             ops.topic_rep(base.category_embedding.weight.detach(), base.subCategory_embedding.weight.detach(),

@@ -65,6 +65,50 @@ def linear(a, w, bias=None, residual=None, act=ACT_NONE, out=None, n=None, k=Non
     return out
 
 
+def linear_tma(a16, w16, bias=None, residual=None, act=ACT_NONE, out=None, n=None, out_bf16=True, ld_out=None):
+    """Stage A dense layer on bf16 activations (lime_linear_bf16_tma): a16 [m, kp] bf16, w16 [n, kp] bf16 (kp = the
+    contraction length padded to a multiple of 64 with zero columns), bias / residual fp32.  Returns bf16 [m, ld_out]
+    (padding columns zero: the next layer's operand) or fp32 [m, n]."""
+    lib = _lib.require_device()
+    m, kp = a16.shape
+    n = w16.shape[0] if n is None else n
+    if out is None:
+        out = (torch.empty((m, ld_out or n), dtype=torch.bfloat16, device=a16.device) if out_bf16
+               else torch.empty((m, n), dtype=torch.float32, device=a16.device))
+    ldr = _rowmajor(residual, "residual") if residual is not None else 0
+    check(lib.lime_linear_bf16_tma(_ptr(a16, torch.bfloat16, "a16"), _rowmajor(a16, "a16"), _ptr(w16, torch.bfloat16, "w16"),
+                                   _rowmajor(w16, "w16"), _ptr(bias, torch.float32, "bias"),
+                                   _ptr(residual, torch.float32, "residual"), ldr, out.data_ptr(), _rowmajor(out, "out"),
+                                   1 if out.dtype == torch.bfloat16 else 0, m, n, kp, act, _stream()), "lime_linear_bf16_tma")
+    return out
+
+
+def embed_pe_bf16(E, ids, T, pe, out, out16):
+    lib = _lib.require_device()
+    check(lib.lime_embed_pe_bf16(_ptr(E, torch.float32, "E"), E.shape[0], _ptr(ids, torch.int32, "ids"), ids.numel(), T,
+                                 E.shape[1], _ptr(pe, torch.float32, "pe"), _ptr(out, torch.float32, "out"),
+                                 _ptr(out16, torch.bfloat16, "out16"), out16.shape[1], _stream()), "lime_embed_pe_bf16")
+    return out, out16
+
+
+def mha_bf16(qkv16, ctx16, n_news, T, d, nhead):
+    lib = _lib.require_device()
+    for lo in range(0, n_news, 65535):
+        hi = min(n_news, lo + 65535)
+        check(lib.lime_mha_bf16(qkv16[lo * T:].data_ptr(), qkv16.stride(0), ctx16[lo * T:].data_ptr(), ctx16.stride(0),
+                                hi - lo, T, d, nhead, _stream()), "lime_mha_bf16")
+    return ctx16
+
+
+def layernorm_bf16(x, gamma, beta, out, out16, eps=1e-5):
+    lib = _lib.require_device()
+    check(lib.lime_layernorm_bf16(_ptr(x, torch.float32, "x"), _rowmajor(x, "x"), _ptr(gamma, torch.float32, "gamma"),
+                                  _ptr(beta, torch.float32, "beta"), _ptr(out, torch.float32, "out"), _rowmajor(out, "out"),
+                                  _ptr(out16, torch.bfloat16, "out16"), out16.shape[1], x.shape[0], x.shape[1], eps,
+                                  _stream()), "lime_layernorm_bf16")
+    return out, out16
+
+
 def gemm_strided(a, b, alpha=1.0, out=None):
     """out = alpha * a @ b for arbitrary-stride 2-D views (weight folding only)."""
     lib = _lib.require_device()

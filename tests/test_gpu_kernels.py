@@ -94,6 +94,55 @@ def test_linear_bf16_tcgen05(lib, m, n, k, act):
     assert float(big[:, :4].abs().sum()) == 0 and float(big[:, 4 + n:].abs().sum()) == 0
 
 
+@pytest.mark.parametrize("m,n,k", [(128, 32, 64), (1, 7, 52), (300, 900, 300), (1000, 300, 512), (77, 512, 300),
+                                   (40000, 300, 300), (20000, 900, 300), (513, 256, 64)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_linear_bf16_tma(lib, m, n, k, act):
+    """Stage A dense layer on bf16 activations (TMA + resident W slice + two TMEM accumulators): equals an fp64 matmul
+    of the bf16 operands up to fp32 accumulation error; fp32 output with residual, bf16 output with zeroed padding."""
+    kp = (k + 63) // 64 * 64
+    a, w, b = randn(m, k, seed=1), randn(n, k, seed=2, scale=k ** -0.5), randn(n, seed=3)
+    r = randn(m, n, seed=4)
+    a16 = torch.zeros(m, kp, dtype=torch.bfloat16, device=DEV)
+    w16 = torch.zeros(n, kp, dtype=torch.bfloat16, device=DEV)
+    a16[:, :k], w16[:, :k] = a, w
+    z = a16.double() @ w16.double().t() + b.double()
+    z = [z, torch.relu(z)][act]
+    got = ops.linear_tma(a16, w16, b, residual=r, act=act, out_bf16=False)
+    close(got, z + r.double(), 1e-5)
+    ld = (n + 7) // 8 * 8 + 8
+    got16 = ops.linear_tma(a16, w16, b, act=act, ld_out=ld)
+    assert got16.dtype == torch.bfloat16 and got16.shape == (m, ld)
+    assert torch.equal(got16[:, :n], z.float().bfloat16()) or float((got16[:, :n].double() - z).abs().max()) <= 2.0 ** -7 * float(z.abs().max())
+    assert float(got16[:, n:].float().abs().sum()) == 0.0
+
+
+def test_stage_a_bf16_glue(lib):
+    """bf16 images written beside the fp32 rows: embed_pe_bf16, layernorm_bf16, mha_bf16 against their fp32 twins."""
+    n, T, d, heads = 5, 32, 300, 10
+    E, pe = randn(50, d, seed=1), randn(T, d, seed=2)
+    ids = torch.arange(n * T, device=DEV, dtype=torch.int32) % 50
+    x, x16 = torch.empty(n * T, d, device=DEV), torch.full((n * T, 320), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.embed_pe_bf16(E, ids, T, pe, x, x16)
+    want = torch.empty(n * T, d, device=DEV)
+    ops.embed_pe(E, ids, T, pe, want)
+    assert torch.equal(x, want) and torch.equal(x16[:, :d], want.bfloat16()) and float(x16[:, d:].float().abs().sum()) == 0
+    g, bta = randn(d, seed=3), randn(d, seed=4)
+    y, y16 = torch.empty_like(x), torch.full((n * T, 320), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.layernorm_bf16(x, g, bta, y, y16)
+    wy = ops.layernorm(x, g, bta, torch.empty_like(x))
+    assert torch.equal(y, wy) and torch.equal(y16[:, :d], wy.bfloat16()) and float(y16[:, d:].float().abs().sum()) == 0
+    for TT in (32, 128):
+        nn_ = 3
+        qkv = randn(nn_ * TT, 904, seed=5).bfloat16()
+        ctx16 = torch.full((nn_ * TT, 320), 7.0, dtype=torch.bfloat16, device=DEV)
+        ops.mha_bf16(qkv, ctx16, nn_, TT, d, heads)
+        ctx = torch.empty(nn_ * TT, d, device=DEV)
+        ops.mha(qkv[:, :900].float().contiguous(), ctx, nn_, TT, d, heads)
+        assert float((ctx16[:, :d].float() - ctx).abs().max()) <= 2.0 ** -7 * float(ctx.abs().max())
+        assert float(ctx16[:, d:].float().abs().sum()) == 0
+
+
 def test_linear_strided_views(lib):
     big_a = randn(50, 852, seed=5)
     big_w = randn(400, 1800, seed=6, scale=0.03)
