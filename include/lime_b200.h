@@ -114,7 +114,9 @@ int lime_embed_pe_bf16(const float *E, int64_t vocab, const int32_t *ids, int64_
  * Supported: T in {32, 128}, d/nhead <= 32.                                                      */
 int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, float p_drop, uint64_t seed,
              int64_t news0, void *stream);
-/* the same on bf16 activations (eval only): qkv [n_news*T, ldq] bf16 -> ctx [n_news*T, ldo] bf16, columns d..ldo-1 zero */
+/* the same on bf16 activations and the tensor cores (eval only): qkv [n_news*T, ldq] bf16 in the HEAD-PADDED layout
+ * q | k | v, each nhead slices of 32 columns (d/nhead real ones, the rest exact zeros: permute and zero-pad the rows of
+ * in_proj_weight / in_proj_bias) -> ctx [n_news*T, ldo] bf16 in the plain layout, columns d..ldo-1 zero */
 int lime_mha_bf16(const void *qkv, int64_t ldq, void *ctx, int64_t ldo, int64_t n_news, int T, int d, int nhead, void *stream);
 /* p_drop / seed: dropout on the attention weights (training; 0 in eval), stateless mask of (seed, news0 + news, head, i, j)
  * -- news0 is the global index of the call's first news, so a chunked call sees the mask of the whole batch */

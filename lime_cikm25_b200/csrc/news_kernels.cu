@@ -186,109 +186,120 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
+// Head-padded layout (``hp`` = 32): qkv [rows, 3 * nhead * 32] holds q | k | v with every head slice padded to 32
+// columns (the in_proj weight rows are permuted and zero-padded on the host, so the padding columns are exact zeros):
+// a head slice of a row is 64 contiguous, 16-byte aligned bytes and goes to shared memory by cp.async, one head pass
+// ahead of the arithmetic (two tile sets).
+__device__ __forceinline__ void cp_async_16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
 template <int T>
 __global__ void __launch_bounds__(256)
 mha_tc_kernel(const __nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restrict__ ctx, int64_t ld, int64_t ldo, int d, int nhead,
               int hd, float scale_log2e) {
     constexpr int WPH = T / 16;                 // warps per head
     constexpr int HPC = 8 / WPH;                // heads per pass
-    constexpr int P = 40;                       // shared-memory row pitch (bf16 elements)
+    constexpr int P = 40;                       // shared-memory row pitch (bf16 elements): 80 bytes, ldmatrix conflict-free
     constexpr int NT = T / 8;                   // key tiles of S
-    __shared__ __align__(16) __nv_bfloat16 Qs[HPC][T][P];
-    __shared__ __align__(16) __nv_bfloat16 Ks[HPC][T][P];
-    __shared__ __align__(16) __nv_bfloat16 Vs[HPC][T][P];
+    constexpr int HP = 32;                      // padded head width in qkv
+    extern __shared__ __align__(16) unsigned char mha_smem[];
+    typedef __nv_bfloat16 Tile[HPC][T][P];
+    Tile *tiles = reinterpret_cast<Tile *>(mha_smem);          // [2 sets][3 matrices]
     const int64_t news = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const __nv_bfloat16 *base = qkv + news * T * ld;
-    const int hw = hd / 2;                      // bf16 pairs per head slice (hd even)
-    // zero the padding columns once (dims hd..31 must be zero, 32..39 are never read)
-    for (int i = tid; i < HPC * T * 3; i += 256) {
-        const int m = i % 3, r = (i / 3) % T, g = i / (3 * T);
-        __nv_bfloat16 *row = m == 0 ? &Qs[g][r][0] : (m == 1 ? &Ks[g][r][0] : &Vs[g][r][0]);
-        for (int c = hd; c < 32; ++c) row[c] = __float2bfloat16_rn(0.0f);
-    }
+    const int npass = (nhead + HPC - 1) / HPC;
+    auto issue = [&](int pass) {
+        Tile *set = tiles + 3 * (pass & 1);
+        for (int i = tid; i < HPC * 3 * T * 4; i += 256) {
+            const int c = i & 3, r = (i >> 2) % T, m = (i / (4 * T)) % 3, gg = i / (4 * T * 3);
+            const int head = pass * HPC + gg;
+            if (head < nhead) cp_async_16(&set[m][gg][r][8 * c], base + r * ld + (m * nhead + head) * HP + 8 * c);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     const int g = warp / WPH, r0 = 16 * (warp % WPH);
-    for (int head0 = 0; head0 < nhead; head0 += HPC) {
-        __syncthreads();                        // the previous pass no longer reads the tiles
-        for (int i = tid; i < HPC * 3 * T * hw; i += 256) {
-            const int c = i % hw, r = (i / hw) % T, m = (i / (hw * T)) % 3, gg = i / (hw * T * 3);
-            const int head = head0 + gg;
-            if (head < nhead) {
-                const uint32_t v = *reinterpret_cast<const uint32_t *>(base + r * ld + m * d + head * hd + 2 * c);
-                __nv_bfloat16 *row = m == 0 ? &Qs[gg][r][0] : (m == 1 ? &Ks[gg][r][0] : &Vs[gg][r][0]);
-                *reinterpret_cast<uint32_t *>(row + 2 * c) = v;
-            }
+    issue(0);
+    for (int pass = 0; pass < npass; ++pass) {
+        if (pass + 1 < npass) {
+            issue(pass + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const int head = head0 + g;
-        if (head >= nhead) continue;
-        // ---- S = Q K^T (16 x T per warp) ----
-        uint32_t qa[2][4];
+        Tile *set = tiles + 3 * (pass & 1);
+        const int head = pass * HPC + g;
+        if (head < nhead) {
+            // ---- S = Q K^T (16 x T per warp) ----
+            uint32_t qa[2][4];
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) ldsm_x4(qa[ks], &Qs[g][r0 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * ks + 8 * (lane >> 4)]);
-        float sacc[NT][4];
+            for (int ks = 0; ks < 2; ++ks) ldsm_x4(qa[ks], &set[0][g][r0 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * ks + 8 * (lane >> 4)]);
+            float sacc[NT][4];
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.0f;
-            uint32_t kb[4];
-            ldsm_x4(kb, &Ks[g][8 * j + (lane & 7)][8 * (lane >> 3)]);
-            mma_bf16_16816(sacc[j], qa[0], kb[0], kb[1]);
-            mma_bf16_16816(sacc[j], qa[1], kb[2], kb[3]);
-        }
-        // ---- softmax over the keys: rows lane / 4 (c0, c1) and lane / 4 + 8 (c2, c3) ----
-        float m0 = -INFINITY, m1 = -INFINITY;
+            for (int j = 0; j < NT; ++j) {
+                sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.0f;
+                uint32_t kb[4];
+                ldsm_x4(kb, &set[1][g][8 * j + (lane & 7)][8 * (lane >> 3)]);
+                mma_bf16_16816(sacc[j], qa[0], kb[0], kb[1]);
+                mma_bf16_16816(sacc[j], qa[1], kb[2], kb[3]);
+            }
+            // ---- softmax over the keys: rows lane / 4 (c0, c1) and lane / 4 + 8 (c2, c3) ----
+            float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            m0 = fmaxf(m0, fmaxf(sacc[j][0], sacc[j][1]));
-            m1 = fmaxf(m1, fmaxf(sacc[j][2], sacc[j][3]));
-        }
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-        float l0 = 0.0f, l1 = 0.0f;
+            for (int j = 0; j < NT; ++j) {
+                m0 = fmaxf(m0, fmaxf(sacc[j][0], sacc[j][1]));
+                m1 = fmaxf(m1, fmaxf(sacc[j][2], sacc[j][3]));
+            }
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+            float l0 = 0.0f, l1 = 0.0f;
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            sacc[j][0] = exp2f((sacc[j][0] - m0) * scale_log2e);
-            sacc[j][1] = exp2f((sacc[j][1] - m0) * scale_log2e);
-            sacc[j][2] = exp2f((sacc[j][2] - m1) * scale_log2e);
-            sacc[j][3] = exp2f((sacc[j][3] - m1) * scale_log2e);
-            l0 += sacc[j][0] + sacc[j][1];
-            l1 += sacc[j][2] + sacc[j][3];
-        }
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        // ---- O = P V (16 x 32 per warp) ----
-        float oacc[4][4];
+            for (int j = 0; j < NT; ++j) {
+                sacc[j][0] = exp2f((sacc[j][0] - m0) * scale_log2e);
+                sacc[j][1] = exp2f((sacc[j][1] - m0) * scale_log2e);
+                sacc[j][2] = exp2f((sacc[j][2] - m1) * scale_log2e);
+                sacc[j][3] = exp2f((sacc[j][3] - m1) * scale_log2e);
+                l0 += sacc[j][0] + sacc[j][1];
+                l1 += sacc[j][2] + sacc[j][3];
+            }
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+            // ---- O = P V (16 x 32 per warp) ----
+            float oacc[4][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.0f;
+            for (int j = 0; j < 4; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.0f;
 #pragma unroll
-        for (int kk = 0; kk < T / 16; ++kk) {
-            uint32_t pa[4];
-            pa[0] = pack2_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
-            pa[1] = pack2_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
-            pa[2] = pack2_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
-            pa[3] = pack2_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
+            for (int kk = 0; kk < T / 16; ++kk) {
+                uint32_t pa[4];
+                pa[0] = pack2_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
+                pa[1] = pack2_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
+                pa[2] = pack2_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+                pa[3] = pack2_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
 #pragma unroll
-            for (int jp = 0; jp < 2; ++jp) {
-                uint32_t vb[4];
-                ldsm_x4_trans(vb, &Vs[g][16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
-                mma_bf16_16816(oacc[2 * jp], pa, vb[0], vb[1]);
-                mma_bf16_16816(oacc[2 * jp + 1], pa, vb[2], vb[3]);
+                for (int jp = 0; jp < 2; ++jp) {
+                    uint32_t vb[4];
+                    ldsm_x4_trans(vb, &set[2][g][16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
+                    mma_bf16_16816(oacc[2 * jp], pa, vb[0], vb[1]);
+                    mma_bf16_16816(oacc[2 * jp + 1], pa, vb[2], vb[3]);
+                }
+            }
+            const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+            __nv_bfloat16 *o0 = ctx + (news * T + r0 + (lane >> 2)) * ldo + head * hd, *o1 = o0 + 8 * ldo;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 8 * j + 2 * (lane & 3);
+                if (c < hd) {
+                    *reinterpret_cast<uint32_t *>(o0 + c) = pack2_bf16(oacc[j][0] * i0, oacc[j][1] * i0);
+                    *reinterpret_cast<uint32_t *>(o1 + c) = pack2_bf16(oacc[j][2] * i1, oacc[j][3] * i1);
+                }
             }
         }
-        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-        __nv_bfloat16 *o0 = ctx + (news * T + r0 + (lane >> 2)) * ldo + head * hd, *o1 = o0 + 8 * ldo;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = 8 * j + 2 * (lane & 3);
-            if (c < hd) {
-                *reinterpret_cast<uint32_t *>(o0 + c) = pack2_bf16(oacc[j][0] * i0, oacc[j][1] * i0);
-                *reinterpret_cast<uint32_t *>(o1 + c) = pack2_bf16(oacc[j][2] * i1, oacc[j][3] * i1);
-            }
-        }
+        __syncthreads();                        // the set is refilled two passes on
     }
     // K padding of the next GEMM's operand
     for (int64_t i = tid; i < (int64_t)T * (ldo - d); i += 256) {
@@ -575,30 +586,25 @@ extern "C" int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int
 extern "C" int lime_mha_bf16(const void *qkv, int64_t ldq, void *ctx, int64_t ldo, int64_t n_news, int T, int d, int nhead,
                              void *stream) {
     LIME_CHECK_ARG(qkv && ctx, "lime_mha_bf16: null argument");
-    LIME_CHECK_ARG(nhead > 0 && d % nhead == 0 && d / nhead <= 32, "lime_mha_bf16: head dim %d unsupported (<= 32)", nhead ? d / nhead : -1);
+    LIME_CHECK_ARG(nhead > 0 && d % nhead == 0 && d / nhead <= 32 && (d / nhead) % 2 == 0, "lime_mha_bf16: head dim %d unsupported (even, <= 32)", nhead ? d / nhead : -1);
     LIME_CHECK_ARG(T == 32 || T == 128, "lime_mha_bf16: T=%d unsupported (32 or 128)", T);
-    LIME_CHECK_ARG(ldq >= 3 * d && ldo >= d, "lime_mha_bf16: bad leading dimensions");
-    LIME_CHECK_ARG(n_news <= 65535, "lime_mha_bf16: at most 65535 news per call (got %lld)", (long long)n_news);
+    LIME_CHECK_ARG(ldq >= 3 * nhead * 32 && ldq % 8 == 0 && ldo >= d && ldo % 2 == 0 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)ctx & 3) == 0,
+                   "lime_mha_bf16: qkv must be head-padded [rows, >= %d] with 16-byte aligned rows", 3 * nhead * 32);
+    LIME_CHECK_ARG(n_news <= 0x7fffffff, "lime_mha_bf16: too many news");
     if (n_news <= 0) return 0;
     const int hd = d / nhead;
-    const float scale = 1.0f / sqrtf((float)hd);
+    const float sl = 1.4426950408889634f / sqrtf((float)hd);
     const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16 *>(qkv);
     __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(ctx);
-    if (hd % 2 == 0 && d % 2 == 0 && ldq % 2 == 0 && ldo % 2 == 0 && ((uintptr_t)qkv & 3) == 0 && ((uintptr_t)ctx & 3) == 0) {
-        const float sl = scale * 1.4426950408889634f;
-        if (T == 32) mha_tc_kernel<32><<<(unsigned)n_news, 256, 0, as_stream(stream)>>>(q, o, ldq, ldo, d, nhead, hd, sl);
-        else mha_tc_kernel<128><<<(unsigned)n_news, 256, 0, as_stream(stream)>>>(q, o, ldq, ldo, d, nhead, hd, sl);
-        LIME_LAUNCH_CHECK("mha_tc_kernel");
-        return 0;
-    }
+    const int smem = 2 * 3 * 128 * 40 * 2;       // two sets of Q, K, V tiles (HPC * T = 128 rows either way)
     if (T == 32) {
-        dim3 grid((nhead + 3) / 4, (unsigned)n_news);
-        mha_kernel<32, __nv_bfloat16, __nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(q, o, ldq, ldo, d, nhead, hd, scale, 0.0f, 0, 0);
+        LIME_CUDA(cudaFuncSetAttribute(mha_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mha_tc_kernel<32><<<(unsigned)n_news, 256, smem, as_stream(stream)>>>(q, o, ldq, ldo, d, nhead, hd, sl);
     } else {
-        dim3 grid(nhead, (unsigned)n_news);
-        mha_kernel<128, __nv_bfloat16, __nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(q, o, ldq, ldo, d, nhead, hd, scale, 0.0f, 0, 0);
+        LIME_CUDA(cudaFuncSetAttribute(mha_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mha_tc_kernel<128><<<(unsigned)n_news, 256, smem, as_stream(stream)>>>(q, o, ldq, ldo, d, nhead, hd, sl);
     }
-    LIME_LAUNCH_CHECK("mha_kernel");
+    LIME_LAUNCH_CHECK("mha_tc_kernel");
     return 0;
 }
 

@@ -116,9 +116,18 @@ class NewsEncoderEngine:
             o = torch.zeros(n_, (k_ + 63) // 64 * 64, dtype=torch.bfloat16, device=dev)
             o[:, :k_].copy_(w)
             return o
+        heads = int(self.cfg.head_num)
+        hd = 300 // heads
+
+        def head_pad(t):     # in_proj rows q | k | v, each [heads * hd, ...] -> heads slices of 32 rows (zero rows after the hd real ones)
+            o = torch.zeros((3, heads, 32) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            o[:, :, :hd] = t.reshape((3, heads, hd) + tuple(t.shape[1:]))
+            return o.reshape((3 * heads * 32,) + tuple(t.shape[1:]))
         for br in (P["title"], P["body"]):
-            for name in ("in_w", "out_w", "l1_w", "l2_w"):
+            for name in ("out_w", "l1_w", "l2_w"):
                 br[name + "16"] = pad16(br[name])
+            br["in_w16"] = pad16(head_pad(br["in_w"]))          # head-padded q | k | v: the layout lime_mha_bf16 reads
+            br["in_b_hp"] = head_pad(br["in_b"])
         P["title_pe"] = base.title_pos_encoder.pe.detach().reshape(-1, 300).contiguous()
         P["body_pe"] = base.body_pos_encoder.pe.detach().reshape(-1, 300).contiguous()
         pw = m.project.weight.detach()                    # [400, 1800] = [W_c | W_f]
@@ -157,7 +166,7 @@ class NewsEncoderEngine:
         x0 = torch.empty(rows, 300, dtype=torch.float32, device=dev)
         x0b = torch.empty(rows, kp, dtype=torch.bfloat16, device=dev)
         ops.embed_pe_bf16(E, ids, T, pe, x0, x0b)
-        qkv = ops.linear_tma(x0b, W["in_w16"], W["in_b"], ld_out=904)               # bf16 [rows, 904] (16-byte rows)
+        qkv = ops.linear_tma(x0b, W["in_w16"], W["in_b_hp"])                        # bf16 [rows, 960], head-padded q | k | v
         ctxb = torch.empty(rows, kp, dtype=torch.bfloat16, device=dev)
         ops.mha_bf16(qkv, ctxb, n, T, 300, self.cfg.head_num)
         del qkv

@@ -105,3 +105,26 @@ def test_sharded_metric_reduction_gloo_world2():
     for rank, means, base, n in out:
         assert np.allclose(means, want, rtol=0, atol=1e-12)
     assert out[0][2] == 0 and out[1][2] == out[0][3] and out[0][3] + out[1][3] == imp.num_pairs
+
+
+def test_dp_launcher_dry_run_world2():
+    """lime_cikm25_b200.main (reference main.py:28 + trainer.py:246-426) with --world_size 2 on CPU: mp.spawn, gloo
+    rendezvous on 127.0.0.1, the DistributedSampler-equivalent partition covers every sample each epoch, the dev
+    shards cover the impression set, and both ranks leave through barrier + destroy_process_group (exit code 0)."""
+    from lime_cikm25_b200 import main as launcher
+    assert launcher.main(["--world_size", "2", "--dry-run", "--epoch", "2", "--master-port", str(_free_port()),
+                          "--synthetic-train", "101", "--synthetic-dev", "37"]) == 0
+
+
+def test_dp_launcher_behaviors_feed_the_dataset():
+    """The synthetic behaviours have the tuple layout Train_Dataset reads (dataset.py:41-76): negative sampling and the
+    padded history seconds work on them, and the single-process dry run partitions trivially."""
+    from lime_cikm25_b200 import dataset as D, main as launcher
+    beh = launcher.make_train_behaviors(20, 500, 50, seed=1)
+    np.random.seed(0)
+    s, f, l = D.negative_sampling(beh, 4)
+    assert s.shape == (20, 5) and (s[:, 0] == [b[3] for b in beh]).all()
+    assert all(len(D.pad_history_seconds(b[9], 50)) == 50 for b in beh)
+    args = launcher.parse_args(["--dry-run", "--epoch", "1", "--synthetic-train", "20", "--synthetic-dev", "8"])
+    hist = launcher.run_worker(0, 1, args)
+    assert hist == [(1, 20, 8)]

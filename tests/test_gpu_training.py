@@ -300,3 +300,15 @@ def test_training_dropout_sites_are_live(lib):
         e = model(*batch, batch[24] - batch[23]).clone()
         assert torch.isfinite(e).all() and float((e - a).abs().max()) > 0
     model.config.dropout_rate = 0.0
+
+
+@pytest.mark.gpu
+def test_dp_launcher_single_gpu(lib, tmp_path):
+    """lime_cikm25_b200.main end to end on one GPU: two epochs of device-gathered mini-batches (negative sampling,
+    DistributedSampler-equivalent order), the dev evaluation after each epoch, best checkpoint + dev log written."""
+    from lime_cikm25_b200 import main as launcher
+    args = launcher.parse_args(["--epoch", "2", "--batch_size", "8", "--synthetic-news", "300", "--synthetic-train", "24",
+                                "--synthetic-dev", "16", "--vocabulary_size", "800", "--result-dir", str(tmp_path)])
+    hist = launcher.run_worker(0, 1, args, log=lambda *a: None)
+    assert len(hist) == 2 and all(np.isfinite(h[1]) and 0.0 <= h[2] <= 1.0 for h in hist)
+    assert (tmp_path / "dev_log.txt").exists() and (tmp_path / "LIME-CROWN-CROWN").exists() or len(list(tmp_path.iterdir())) == 2
