@@ -6,14 +6,14 @@
 //
 // The shapes are skinny (k = 320 or 512, n <= 900, m = news x tokens = millions), so the kernel is organised around what
 // is re-used:  ONE persistent CTA per SM owns one N tile (bn <= 256 columns) for its whole life and keeps that slice of
-// W RESIDENT in shared memory (bn x k bf16 <= 160 KB, loaded once by TMA); it then streams 128-row tiles of A through a
+// W RESIDENT in shared memory (bn x k bf16 <= 112 KB, loaded once by TMA); it then streams 128-row tiles of A through a
 // 3-deep TMA ring (16 KB per 64-wide K block).  Per output tile the tensor core runs k/16 MMAs (M = 128, N = bn) into
 // one of TWO TMEM accumulators (2 x 256 columns), so the epilogue of tile i (TMEM -> registers -> bias / act / residual
 // -> global) overlaps the MMAs of tile i + 1.  The CTAs that share an M tile (one per N tile) run at the same time on
 // neighbouring SMs: A comes from HBM once and from L2 otherwise.
 //
-// Warp roles (192 threads): warps 0-3 epilogue (warp w owns TMEM lanes 32w..32w+31 = rows of the tile), warp 4 TMA
-// producer (one elected lane), warp 5 TMEM allocation + MMA issue (one elected lane).
+// Warp roles (320 threads): warps 0-7 epilogue (warp w owns TMEM lanes 32 (w & 3).. = rows of the tile and every second
+// 32-column chunk), warp 8 TMA producer (one elected lane), warp 9 TMEM allocation + MMA issue (one elected lane).
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -25,10 +25,18 @@
 namespace lime {
 namespace {
 
-constexpr int GT_M = 128, GT_STAGES = 3, GT_A_BYTES = GT_M * 128;
-constexpr int GT_W_MAX = 160 * 1024;           // resident W slice
-constexpr int GT_THREADS = 192;
-constexpr int GT_SMEM = GT_W_MAX + GT_STAGES * GT_A_BYTES + 1024 /* bias slice */ + 256 /* barriers */;
+#ifndef LIME_GT_STAGES
+#define LIME_GT_STAGES 3
+#endif
+constexpr int GT_M = 128, GT_STAGES = LIME_GT_STAGES, GT_A_BYTES = GT_M * 128;
+constexpr int GT_W_MAX = (160 - 16 * GT_STAGES) * 1024;   // resident W slice: what the A ring and the staging tiles leave
+constexpr int GT_STAGE_BYTES = 4096;           // epilogue staging tile of one warp: 32 rows x 128 B (two per warp)
+#ifndef LIME_GT_EPI_WARPS
+#define LIME_GT_EPI_WARPS 8
+#endif
+constexpr int GT_EPI_WARPS = LIME_GT_EPI_WARPS;   // two epilogue warps per TMEM lane quadrant, alternating 32-column chunks (measured: 4 -> 8 warps takes the bf16-output GEMMs from 0.48 to 0.32 ms per 262k rows; staging the tile through shared memory for row-contiguous stores was slower)
+constexpr int GT_THREADS = 32 * (GT_EPI_WARPS + 2);
+constexpr int GT_SMEM = GT_W_MAX + GT_STAGES * GT_A_BYTES + 2 * GT_EPI_WARPS * GT_STAGE_BYTES + 1024 /* bias slice */ + 256 /* barriers */;
 static_assert(GT_SMEM + 1024 <= 232448, "shared memory");
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
@@ -36,6 +44,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -58,10 +72,13 @@ __device__ __forceinline__ float act_apply(int act, float x) {
 }
 
 // barriers (uint64 each)
-enum { GB_WFULL = 0, GB_AFULL = 1, GB_AEMPTY = 1 + GT_STAGES, GB_ACCFULL = 1 + 2 * GT_STAGES, GB_ACCEMPTY = 3 + 2 * GT_STAGES };
+enum { GB_WFULL = 0, GB_AFULL = 1, GB_AEMPTY = 1 + GT_STAGES, GB_ACCFULL = 1 + 2 * GT_STAGES, GB_ACCEMPTY = 3 + 2 * GT_STAGES,
+       GB_RES = 5 + 2 * GT_STAGES /* one per epilogue warp */, GB_COUNT = GB_RES + GT_EPI_WARPS };
+static_assert(GB_COUNT * 8 + 8 <= 256, "barrier area");
 
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap,
+                const __grid_constant__ CUtensorMap cmap, const __grid_constant__ CUtensorMap rmap, int tma_epilogue, int ncov,
                 const float *__restrict__ bias, const float *__restrict__ residual, int64_t ldr, void *__restrict__ Cout,
                 int64_t ldc, int c_bf16, int64_t m, int n, int nkb, int bn, int n_tiles, int act) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -69,9 +86,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     if (threadIdx.x == 0 && (tc::smem_u32(smem_raw) & 1023u) != 0) __trap();
     unsigned char *w_s = base;                                     // [nkb][bn rows x 128 B]
     unsigned char *a_s = base + GT_W_MAX;                          // [GT_STAGES][128 rows x 128 B]
-    float *bias_s = reinterpret_cast<float *>(base + GT_W_MAX + GT_STAGES * GT_A_BYTES);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(base + GT_W_MAX + GT_STAGES * GT_A_BYTES + 1024);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+    unsigned char *stage_s = base + GT_W_MAX + GT_STAGES * GT_A_BYTES;          // [GT_EPI_WARPS][2][4096], 1024-byte aligned
+    float *bias_s = reinterpret_cast<float *>(stage_s + 2 * GT_EPI_WARPS * GT_STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(bias_s) + 1024);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + GB_COUNT);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nt = (int)(blockIdx.x % (unsigned)n_tiles);          // this CTA's N tile, for its whole life
@@ -87,18 +105,19 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             tc::mbar_init(bars + GB_ACCFULL + a, 1);
-            tc::mbar_init(bars + GB_ACCEMPTY + a, 4);              // one arrival per epilogue warp
+            tc::mbar_init(bars + GB_ACCEMPTY + a, GT_EPI_WARPS);   // one arrival per epilogue warp
         }
+        for (int w = 0; w < GT_EPI_WARPS; ++w) tc::mbar_init(bars + GB_RES + w, 1);
         tc::mbar_fence_init();
     }
     for (int i = tid; i < bn; i += GT_THREADS) bias_s[i] = (bias != nullptr && col0 + i < n) ? bias[col0 + i] : 0.0f;
-    if (warp == 5) tc::tmem_alloc(tmem_slot, 512);
+    if (warp == GT_EPI_WARPS + 1) tc::tmem_alloc(tmem_slot, 512);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == GT_EPI_WARPS) {
         // ---------------- TMA producer ----------------
         if (lane == 0) {
             mbar_expect_tx(bars + GB_WFULL, (uint32_t)(nkb * bn * 128));
@@ -114,7 +133,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == GT_EPI_WARPS + 1) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             const uint32_t idesc = tc::idesc_bf16_f32(GT_M, bn);
@@ -140,25 +159,126 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
             }
         }
     } else {
-        // ---------------- epilogue (warps 0-3) ----------------
+        // ---------------- epilogue (warps 0-7) ----------------
+        const int quad = warp & 3, half = warp >> 2;
         uint32_t tile = 0;
+        if (tma_epilogue) {
+            // ---- TMA epilogue: the output leaves as 32 x 32 boxes (rows x columns) by cp.async.bulk.tensor stores ----
+            // TMEM hands every lane one ROW of the tile, and a plain store from that layout touches 32 rows per instruction:
+            // measured, the four GEMMs then run at 1.6 TB/s of output traffic, 2.5x slower than their main loops (0.126 ms vs
+            // 0.315 ms for the in_proj GEMM of 262k rows).  Here a lane writes its row into a swizzled 32-row staging tile in
+            // shared memory (128-byte rows = 32 fp32 or 64 bf16 columns, SWIZZLE_128B: conflict-free 16-byte stores) and one lane
+            // hands the tile to the TMA unit, which writes whole lines and clips the box at the tensor's edge (no tail code;
+            // the zero padding columns of a bf16 output are part of the box).  An fp32 residual comes the same way: TMA-loaded
+            // into the staging tile, added in place.  Two staging tiles per warp alternate.
+            const int ncols_t = min(bn, ncov - col0);              // columns of this N tile inside the stored width
+            unsigned char *my_stage = stage_s + warp * 2 * GT_STAGE_BYTES;
+            uint64_t *rbar = bars + GB_RES + warp;
+            uint32_t chunk_it = 0, res_it = 0;
+            for (int64_t mt = mt0; mt < m_tiles; mt += mt_step, ++tile) {
+                const uint32_t acc = tile & 1u;
+                const int row0 = (int)(mt * GT_M) + quad * 32;
+                const uint32_t tlane = tmem + acc * 256u + ((uint32_t)(quad * 32) << 16);
+                bool waited = false;
+                const int cw = c_bf16 ? 64 : 32;                   // columns per box: 128-byte rows either way
+                for (int c0 = cw * half; c0 < ncols_t; c0 += cw * (GT_EPI_WARPS / 4), ++chunk_it) {
+                    unsigned char *buf = my_stage + (chunk_it & 1u) * GT_STAGE_BYTES;
+                    if (lane == 0) {
+                        bulk_wait_read<1>();                       // the store that last read this tile (two chunks ago) is done with it
+                        if (residual != nullptr) {
+                            mbar_expect_tx(rbar, 32 * 32 * 4);
+                            tma_load_2d(tc::smem_u32(buf), &rmap, col0 + c0, row0, rbar);
+                        }
+                    }
+                    __syncwarp();
+                    if (!waited) {                                 // (the residual of the first chunk is in flight while the MMAs finish)
+                        tc::mbar_wait(bars + GB_ACCFULL + acc, (tile >> 1) & 1u);
+                        tc::fence_after_sync();
+                        waited = true;
+                    }
+                    // 128-byte rows, SWIZZLE_128B: 16-byte unit u of row r at position u ^ (r & 7)
+                    if (c_bf16) {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {           // bn is a multiple of 64 here: both halves are columns of this tile
+                            uint32_t v[32];
+                            tmem_ld32(tlane + (uint32_t)(c0 + 32 * hh), v);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float4 b0 = *reinterpret_cast<const float4 *>(bias_s + c0 + 32 * hh + 8 * u);
+                                const float4 b1 = *reinterpret_cast<const float4 *>(bias_s + c0 + 32 * hh + 8 * u + 4);
+                                uint4 o;
+                                o.x = tc::pack_bf16(act_apply(act, __uint_as_float(v[8 * u]) + b0.x), act_apply(act, __uint_as_float(v[8 * u + 1]) + b0.y));
+                                o.y = tc::pack_bf16(act_apply(act, __uint_as_float(v[8 * u + 2]) + b0.z), act_apply(act, __uint_as_float(v[8 * u + 3]) + b0.w));
+                                o.z = tc::pack_bf16(act_apply(act, __uint_as_float(v[8 * u + 4]) + b1.x), act_apply(act, __uint_as_float(v[8 * u + 5]) + b1.y));
+                                o.w = tc::pack_bf16(act_apply(act, __uint_as_float(v[8 * u + 6]) + b1.z), act_apply(act, __uint_as_float(v[8 * u + 7]) + b1.w));
+                                *reinterpret_cast<uint4 *>(buf + lane * 128 + 16 * ((4 * hh + u) ^ (lane & 7))) = o;
+                            }
+                        }
+                    } else {
+                        uint32_t v[32];
+                        tmem_ld32(tlane + (uint32_t)c0, v);
+                        if (residual != nullptr) {
+                            tc::mbar_wait(rbar, res_it & 1u);
+                            ++res_it;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float4 bb = *reinterpret_cast<const float4 *>(bias_s + c0 + 4 * u);
+                            float4 *p = reinterpret_cast<float4 *>(buf + lane * 128 + 16 * (u ^ (lane & 7)));
+                            float4 y = make_float4(act_apply(act, __uint_as_float(v[4 * u]) + bb.x), act_apply(act, __uint_as_float(v[4 * u + 1]) + bb.y),
+                                                   act_apply(act, __uint_as_float(v[4 * u + 2]) + bb.z), act_apply(act, __uint_as_float(v[4 * u + 3]) + bb.w));
+                            if (residual != nullptr) {
+                                const float4 rv = *p;
+                                y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
+                            }
+                            *p = y;
+                        }
+                    }
+                    tc::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&cmap, col0 + c0, row0, tc::smem_u32(buf));
+                        bulk_commit();
+                    }
+                }
+                if (!waited) {                                     // a warp without a chunk in this N tile still takes part in the hand-over
+                    tc::mbar_wait(bars + GB_ACCFULL + acc, (tile >> 1) & 1u);
+                    tc::fence_after_sync();
+                }
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(bars + GB_ACCEMPTY + acc);
+            }
+            if (lane == 0) bulk_wait_read<0>();                    // shared memory must outlive the last stores' reads
+            __syncwarp();
+        } else {
         const int ncols = min(bn, n - col0);                       // real columns of this N tile
         const bool pad = c_bf16 && nt == n_tiles - 1;              // bf16 output: the padding columns [n, ldc) are written as zeros
         for (int64_t mt = mt0; mt < m_tiles; mt += mt_step, ++tile) {
             const uint32_t acc = tile & 1u;
             tc::mbar_wait(bars + GB_ACCFULL + acc, (tile >> 1) & 1u);
             tc::fence_after_sync();
-            const int64_t r = mt * GT_M + warp * 32 + lane;
-            const uint32_t tlane = tmem + acc * 256u + ((uint32_t)(warp * 32) << 16);
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
+            const int64_t r = mt * GT_M + quad * 32 + lane;
+            const uint32_t tlane = tmem + acc * 256u + ((uint32_t)(quad * 32) << 16);
+            for (int c0 = 32 * half; c0 < ncols; c0 += 8 * GT_EPI_WARPS) {
                 uint32_t v[32];
                 tmem_ld32(tlane + (uint32_t)c0, v);
+#ifdef LIME_GT_NOSTORE           // timing diagnostic only (wrong results): the epilogue drains TMEM and stores nothing
+                if (v[0] == 0x7fc12345u && r < m) reinterpret_cast<float *>(Cout)[0] = 1.0f;
+                continue;
+#endif
                 if (r < m) {
                     const int c = col0 + c0;
                     const int lim = min(32, ncols - c0);
                     float x[32];
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) x[e] = act_apply(act, __uint_as_float(v[e]) + bias_s[c0 + e]);
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(bias_s + c0 + 4 * q);
+                        x[4 * q] = act_apply(act, __uint_as_float(v[4 * q]) + bb.x);
+                        x[4 * q + 1] = act_apply(act, __uint_as_float(v[4 * q + 1]) + bb.y);
+                        x[4 * q + 2] = act_apply(act, __uint_as_float(v[4 * q + 2]) + bb.z);
+                        x[4 * q + 3] = act_apply(act, __uint_as_float(v[4 * q + 3]) + bb.w);
+                    }
                     if (residual != nullptr) {
                         const float *rp = residual + r * ldr + c;
                         if (lim == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
@@ -203,7 +323,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                     }
                 }
             }
-            if (pad && r < m) {
+            if (pad && half == 0 && r < m) {
                 __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(Cout) + r * ldc;
                 for (int64_t c = n; c < ldc; ++c) op[c] = __float2bfloat16_rn(0.0f);
             }
@@ -211,16 +331,18 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(bars + GB_ACCEMPTY + acc);
         }
+        }
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 5) tc::tmem_dealloc(tmem, 512);
+    if (warp == GT_EPI_WARPS + 1) tc::tmem_dealloc(tmem, 512);
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int tensor_map_bf16_2d(CUtensorMap *out, const void *ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+int tensor_map_2d(CUtensorMap *out, CUtensorMapDataType dt, int esize, const void *ptr, uint64_t cols, uint64_t rows, uint64_t ld,
+                  uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle sw) {
     static std::mutex mu;
     static EncodeFn encode = nullptr;
     {
@@ -234,14 +356,16 @@ int tensor_map_bf16_2d(CUtensorMap *out, const void *ptr, uint64_t cols, uint64_
         }
     }
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)(ld * 2)};
-    const cuuint32_t box[2] = {64, box_rows}, estr[2] = {1, 1};
-    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint64_t strides[1] = {(cuuint64_t)(ld * esize)};
+    const cuuint32_t box[2] = {box_cols, box_rows}, estr[2] = {1, 1};
+    const CUresult r = encode(out, dt, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LIME_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed: CUresult %d (cols %llu rows %llu ld %llu)", (int)r,
                    (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld);
     return 0;
+}
+int tensor_map_bf16_2d(CUtensorMap *out, const void *ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+    return tensor_map_2d(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, cols, rows, ld, 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 }  // namespace
@@ -260,22 +384,42 @@ extern "C" int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, i
     LIME_CHECK_ARG(act >= 0 && act <= 2, "lime_linear_bf16_tma: act=%d", act);
     if (m <= 0) return 0;
     const int nkb = k / 64;
+    // TMA epilogue (stores, and the residual loads): needs 16-byte aligned rows; bf16 output without residual, or fp32 output with an
+    // optional fp32 residual (the combinations Stage A uses); anything else takes the plain-store epilogue
+    const int esz = c_is_bf16 ? 2 : 4;
+    const bool tma_epi = ((uintptr_t)C & 15) == 0 && (ldc * esz) % 16 == 0 && m < (int64_t)1 << 31 && !(c_is_bf16 && residual != nullptr) &&
+                         (residual == nullptr || (((uintptr_t)residual & 15) == 0 && (ldr * 4) % 16 == 0 && ldr >= n));
+    const int ncov = tma_epi && c_is_bf16 ? (int)ldc : n;          // stored width: a bf16 output includes its zero padding columns
+    LIME_CHECK_ARG(ncov - n < 64, "lime_linear_bf16_tma: ldc %lld leaves more than 63 padding columns after n %d", (long long)ldc, n);
     // N tile: the widest multiple of 32 (<= 256) whose W slice fits the resident area, then balanced over the tiles
     int bn_max = GT_W_MAX / (nkb * 128);
     bn_max = bn_max > 256 ? 256 : (bn_max / 32) * 32;
-    const int n_tiles = (n + bn_max - 1) / bn_max;
-    int bn = (((n + n_tiles - 1) / n_tiles) + 31) / 32 * 32;
+    const int gran = tma_epi && c_is_bf16 ? 64 : 32;              // bf16 boxes are 64 columns wide
+    bn_max = bn_max / gran * gran;
+    const int n_tiles = (ncov + bn_max - 1) / bn_max;
+    int bn = (((ncov + n_tiles - 1) / n_tiles) + gran - 1) / gran * gran;
     LIME_CHECK_ARG(bn <= bn_max && n_tiles <= 64, "lime_linear_bf16_tma: n=%d does not tile", n);
-    CUtensorMap amap, wmap;
+    CUtensorMap amap, wmap, cmap, rmap;
     if (int rc = tensor_map_bf16_2d(&amap, A, (uint64_t)k, (uint64_t)m, (uint64_t)lda, GT_M)) return rc;
     if (int rc = tensor_map_bf16_2d(&wmap, W, (uint64_t)k, (uint64_t)n, (uint64_t)ldw, (uint32_t)bn)) return rc;
+    cmap = amap;
+    rmap = amap;
+    if (tma_epi) {
+        if (int rc = tensor_map_2d(&cmap, c_is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, esz, C, (uint64_t)ncov,
+                                   (uint64_t)m, (uint64_t)ldc, c_is_bf16 ? 64 : 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))
+            return rc;
+        if (residual != nullptr)
+            if (int rc = tensor_map_2d(&rmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, residual, (uint64_t)n, (uint64_t)m, (uint64_t)ldr, 32, 32,
+                                       CU_TENSOR_MAP_SWIZZLE_128B))
+                return rc;
+    }
     LIME_CUDA(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
     const int64_t m_tiles = (m + GT_M - 1) / GT_M;
     int groups = num_sms() / n_tiles;
     if (groups < 1) groups = 1;
     if (groups > m_tiles) groups = (int)m_tiles;
-    gemm_tma_kernel<<<groups * n_tiles, GT_THREADS, GT_SMEM, as_stream(stream)>>>(amap, wmap, bias, residual, ldr, C, ldc, c_is_bf16, m, n,
-                                                                                    nkb, bn, n_tiles, act);
+    gemm_tma_kernel<<<groups * n_tiles, GT_THREADS, GT_SMEM, as_stream(stream)>>>(amap, wmap, cmap, rmap, tma_epi ? 1 : 0, ncov, bias, residual, ldr,
+                                                                                    C, ldc, c_is_bf16, m, n, nkb, bn, n_tiles, act);
     LIME_LAUNCH_CHECK("gemm_tma_kernel");
     return 0;
 }
