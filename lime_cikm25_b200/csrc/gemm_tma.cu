@@ -92,6 +92,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + GB_COUNT);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool res_pre = act >= 16;                                // LIME_ACT_RES_FIRST: the residual joins the sum BEFORE the activation
+    act &= 15;
     const int nt = (int)(blockIdx.x % (unsigned)n_tiles);          // this CTA's N tile, for its whole life
     const int col0 = nt * bn;
     const int64_t m_tiles = (m + GT_M - 1) / GT_M;
@@ -225,12 +227,13 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                         for (int u = 0; u < 8; ++u) {
                             const float4 bb = *reinterpret_cast<const float4 *>(bias_s + c0 + 4 * u);
                             float4 *p = reinterpret_cast<float4 *>(buf + lane * 128 + 16 * (u ^ (lane & 7)));
-                            float4 y = make_float4(act_apply(act, __uint_as_float(v[4 * u]) + bb.x), act_apply(act, __uint_as_float(v[4 * u + 1]) + bb.y),
-                                                   act_apply(act, __uint_as_float(v[4 * u + 2]) + bb.z), act_apply(act, __uint_as_float(v[4 * u + 3]) + bb.w));
-                            if (residual != nullptr) {
-                                const float4 rv = *p;
-                                y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
-                            }
+                            float4 y = make_float4(__uint_as_float(v[4 * u]) + bb.x, __uint_as_float(v[4 * u + 1]) + bb.y,
+                                                   __uint_as_float(v[4 * u + 2]) + bb.z, __uint_as_float(v[4 * u + 3]) + bb.w);
+                            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (residual != nullptr) rv = *p;
+                            if (res_pre) { y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w; }
+                            y = make_float4(act_apply(act, y.x), act_apply(act, y.y), act_apply(act, y.z), act_apply(act, y.w));
+                            if (!res_pre) { y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w; }
                             *p = y;
                         }
                     }
@@ -274,10 +277,14 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float4 bb = *reinterpret_cast<const float4 *>(bias_s + c0 + 4 * q);
-                        x[4 * q] = act_apply(act, __uint_as_float(v[4 * q]) + bb.x);
-                        x[4 * q + 1] = act_apply(act, __uint_as_float(v[4 * q + 1]) + bb.y);
-                        x[4 * q + 2] = act_apply(act, __uint_as_float(v[4 * q + 2]) + bb.z);
-                        x[4 * q + 3] = act_apply(act, __uint_as_float(v[4 * q + 3]) + bb.w);
+                        x[4 * q] = __uint_as_float(v[4 * q]) + bb.x;
+                        x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
+                        x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
+                        x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
+                    }
+                    if (!res_pre) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) x[e] = act_apply(act, x[e]);
                     }
                     if (residual != nullptr) {
                         const float *rp = residual + r * ldr + c;
@@ -292,6 +299,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                             for (int e = 0; e < 32; ++e)
                                 if (e < lim) x[e] += rp[e];
                         }
+                    }
+                    if (res_pre) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) x[e] = act_apply(act, x[e]);
                     }
                     if (c_bf16) {
                         __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(Cout) + r * ldc + c;
@@ -381,7 +392,7 @@ extern "C" int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, i
                    "lime_linear_bf16_tma: bad leading dimensions (lda %lld ldw %lld ldc %lld, n %d k %d)", (long long)lda,
                    (long long)ldw, (long long)ldc, n, k);
     LIME_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "lime_linear_bf16_tma: operands must be 16-byte aligned");
-    LIME_CHECK_ARG(act >= 0 && act <= 2, "lime_linear_bf16_tma: act=%d", act);
+    LIME_CHECK_ARG((act & 15) >= 0 && (act & 15) <= 2 && (act >> 4) <= 1, "lime_linear_bf16_tma: act=%d", act);
     if (m <= 0) return 0;
     const int nkb = k / 64;
     // TMA epilogue (stores, and the residual loads): needs 16-byte aligned rows; bf16 output without residual, or fp32 output with an

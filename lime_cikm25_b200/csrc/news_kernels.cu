@@ -563,6 +563,47 @@ extern "C" int lime_embed_pe_bf16(const float *E, int64_t vocab, const int32_t *
     return 0;
 }
 
+// fp32 rows -> two bf16 images hi = bf16(x), lo = bf16(x - hi) of [rows, ld16] (columns d.. zero): the operands of the
+// three-pass "bf16x3" dense layer (x . w ~ xh . wh + xl . wh + xh . wl, 2^-16 relative per product) of the fp32-accurate
+// tensor-core mode
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float *__restrict__ x, int64_t ldx, int64_t rows, int d, __nv_bfloat16 *__restrict__ hi,
+                  __nv_bfloat16 *__restrict__ lo, int ld16) {
+    const int q4 = ld16 / 4;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * q4) return;
+    const int64_t r = idx / q4;
+    const int c = 4 * (int)(idx - r * q4);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c + 4 <= d && ((reinterpret_cast<uintptr_t>(x + r * ldx + c) & 15) == 0)) {
+        const float4 t = *reinterpret_cast<const float4 *>(x + r * ldx + c);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        for (int e = 0; e < 4; ++e)
+            if (c + e < d) v[e] = x[r * ldx + c + e];
+    }
+    float h[4], l[4];
+    for (int e = 0; e < 4; ++e) {
+        h[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+        l[e] = v[e] - h[e];
+    }
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(h[0], h[1]), h1 = __floats2bfloat162_rn(h[2], h[3]);
+    __nv_bfloat162 l0 = __floats2bfloat162_rn(l[0], l[1]), l1 = __floats2bfloat162_rn(l[2], l[3]);
+    *reinterpret_cast<uint2 *>(hi + r * ld16 + c) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+    *reinterpret_cast<uint2 *>(lo + r * ld16 + c) = make_uint2(*reinterpret_cast<uint32_t *>(&l0), *reinterpret_cast<uint32_t *>(&l1));
+}
+
+extern "C" int lime_split_bf16_pairs(const float *x, int64_t ldx, int64_t rows, int32_t d, void *hi, void *lo, int32_t ld16, void *stream) {
+    LIME_CHECK_ARG(x && hi && lo, "lime_split_bf16_pairs: null argument");
+    LIME_CHECK_ARG(d >= 1 && ld16 >= d && (ld16 & 7) == 0 && ldx >= d, "lime_split_bf16_pairs: d=%d ld16=%d ldx=%lld", d, ld16, (long long)ldx);
+    if (rows <= 0) return 0;
+    const int64_t total = rows * (ld16 / 4);
+    split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, ldx, rows, d, reinterpret_cast<__nv_bfloat16 *>(hi),
+                                                                                    reinterpret_cast<__nv_bfloat16 *>(lo), ld16);
+    LIME_LAUNCH_CHECK("split_bf16_kernel");
+    return 0;
+}
+
 extern "C" int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, float p_drop, uint64_t seed,
                         int64_t news0, void *stream) {
     LIME_CHECK_ARG(qkv && ctx, "lime_mha: null argument");

@@ -75,7 +75,8 @@ class NewsEncoderEngine:
         self.cfg = cfg
         self._prep = None
         self._fp = None
-        self.bf16 = False        # "bf16 mode": the 4 transformer GEMMs on tcgen05 (lime_linear_bf16)
+        self.bf16 = False        # "bf16 mode": bf16 activations, the 4 transformer GEMMs by TMA + tcgen05 (lime_linear_bf16_tma)
+        self.x3 = False          # "fp32x3 mode": fp32 activations, every transformer GEMM as 3 bf16 tensor-core passes on hi / lo pairs
 
     # -- weights -----------------------------------------------------------------------------------
     def _params(self):
@@ -128,6 +129,9 @@ class NewsEncoderEngine:
                 br[name + "16"] = pad16(br[name])
             br["in_w16"] = pad16(head_pad(br["in_w"]))          # head-padded q | k | v: the layout lime_mha_bf16 reads
             br["in_b_hp"] = head_pad(br["in_b"])
+            for name in ("in_w", "out_w", "l1_w", "l2_w"):        # bf16 pairs w = hi + lo for the fp32x3 mode
+                hi = br[name].to(torch.bfloat16)
+                br[name + "_hi"], br[name + "_lo"] = pad16(hi.float()), pad16(br[name] - hi.float())
         P["title_pe"] = base.title_pos_encoder.pe.detach().reshape(-1, 300).contiguous()
         P["body_pe"] = base.body_pos_encoder.pe.detach().reshape(-1, 300).contiguous()
         pw = m.project.weight.detach()                    # [400, 1800] = [W_c | W_f]
@@ -176,6 +180,34 @@ class NewsEncoderEngine:
         y2 = ops.linear_tma(hf, W["l2_w16"], W["l2_b"], residual=x1, out=y)
         ops.layernorm_meanpool(y2, W["n2_w"], W["n2_b"], feat, n, T, eps=W["eps2"])
 
+    def _branch_x3(self, ids, T, W, pe, feat):
+        """The same branch in the fp32x3 mode: every transformer GEMM as three accumulating bf16 tensor-core passes on hi / lo
+        operand pairs (ops.linear_x3, ~2^-16 relative per product: fp32-level accuracy), activations fp32 throughout."""
+        base = self.m.base_news_encoder
+        n = ids.shape[0]
+        rows = n * T
+        dev = ids.device
+        E = base.word_embedding.weight.detach()
+        x0 = torch.empty(rows, 300, dtype=torch.float32, device=dev)
+        ops.embed_pe(E, ids, T, pe, x0)
+        xh, xl = ops.split_bf16(x0)
+        qkv = ops.linear_x3(xh, xl, W["in_w_hi"], W["in_w_lo"], W["in_b"])
+        del xh, xl
+        ctx = torch.empty(rows, 300, dtype=torch.float32, device=dev)
+        ops.mha(qkv, ctx, n, T, 300, self.cfg.head_num)
+        del qkv
+        ch, cl = ops.split_bf16(ctx)
+        y = ops.linear_x3(ch, cl, W["out_w_hi"], W["out_w_lo"], W["out_b"], residual=x0)
+        del ch, cl
+        x1 = ops.layernorm(y, W["n1_w"], W["n1_b"], out=ctx, eps=W["eps1"])       # reuse ctx
+        xh, xl = ops.split_bf16(x1)
+        hf = ops.linear_x3(xh, xl, W["l1_w_hi"], W["l1_w_lo"], W["l1_b"], act=ops.ACT_RELU)
+        del xh, xl
+        hh, hl = ops.split_bf16(hf)
+        del hf
+        y2 = ops.linear_x3(hh, hl, W["l2_w_hi"], W["l2_w_lo"], W["l2_b"], residual=x1, out=y)
+        ops.layernorm_meanpool(y2, W["n2_w"], W["n2_b"], feat, n, T, eps=W["eps2"])
+
     def encode_content(self, title_text, body_text, category, subCategory):
         """newsEncoders.CROWN.forward, flat over news: int32 [n,32], [n,128], [n], [n] -> fp32 [n,900]."""
         P = self.prepare()
@@ -185,7 +217,7 @@ class NewsEncoderEngine:
         f32 = dict(dtype=torch.float32, device=dev)
         feat_t = torch.empty(n, 352, **f32)
         feat_b = torch.empty(n, 352, **f32)
-        branch = self._branch_bf16 if self.bf16 else self._branch
+        branch = self._branch_bf16 if self.bf16 else (self._branch_x3 if self.x3 else self._branch)
         branch(title_text, 32, P["title"], P["title_pe"], feat_t)
         branch(body_text, 128, P["body"], P["body_pe"], feat_b)
         # category-aware intent disentanglement (:340-356): topic from CROWN's own tables

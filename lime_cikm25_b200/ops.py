@@ -83,6 +83,33 @@ def linear_tma(a16, w16, bias=None, residual=None, act=ACT_NONE, out=None, n=Non
     return out
 
 
+ACT_RES_FIRST = 16
+
+
+def split_bf16(x, kp=None):
+    """fp32 [rows, d] -> (hi, lo) bf16 [rows, kp] with x = hi + lo to 2^-17 (kp = d padded to a multiple of 64, zero columns)."""
+    lib = _lib.require_device()
+    rows, d = x.shape
+    kp = kp or (d + 63) // 64 * 64
+    hi = torch.empty(rows, kp, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(rows, kp, dtype=torch.bfloat16, device=x.device)
+    check(lib.lime_split_bf16_pairs(_ptr(x, torch.float32, "x"), _rowmajor(x, "x"), rows, d, hi.data_ptr(), lo.data_ptr(), kp, _stream()),
+          "lime_split_bf16_pairs")
+    return hi, lo
+
+
+def linear_x3(xh, xl, wh, wl, bias=None, residual=None, act=ACT_NONE, out=None, n=None):
+    """fp32-accurate dense layer on the tensor cores: out = act(x . w^T + bias) + residual with x = xh + xl, w = wh + wl as bf16
+    pairs, three accumulating lime_linear_bf16_tma passes (xh.wh [+ residual], + xl.wh, + xh.wl + bias then act).  With an
+    activation the residual must be None (the accumulating passes add BEFORE the activation)."""
+    assert act == ACT_NONE or residual is None
+    n = wh.shape[0] if n is None else n
+    out = linear_tma(xh, wh, None, residual=residual, out=out, n=n, out_bf16=False)
+    linear_tma(xl, wh, None, residual=out, out=out, n=n, out_bf16=False)
+    linear_tma(xh, wl, bias, residual=out, act=act | ACT_RES_FIRST, out=out, n=n, out_bf16=False)
+    return out
+
+
 def embed_pe_bf16(E, ids, T, pe, out, out16):
     lib = _lib.require_device()
     check(lib.lime_embed_pe_bf16(_ptr(E, torch.float32, "E"), E.shape[0], _ptr(ids, torch.int32, "ids"), ids.numel(), T,

@@ -15,13 +15,14 @@ model = model.cuda().eval()
 ref = None
 with torch.no_grad():
     model.scoring.fold()
-    for mode in (False, True, True):
-        model.news_encoder.engine.bf16 = mode
+    for mode in (False, "x3", "x3", True, True):
+        model.news_encoder.engine.bf16 = mode is True
+        model.news_encoder.engine.x3 = mode == "x3"
         torch.cuda.synchronize(); t0 = time.perf_counter()
         cache = util.build_news_cache(model, news, "cuda", **({"chunk": chunk} if chunk else {}))
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
         if ref is None:
             ref = cache.hist_rows[:, :400].clone()
         err = float((cache.hist_rows[:, :400] - ref).abs().max() / ref.abs().max())
-        print("bf16=%s  %.1f ms  %.0f news/s  %.1f TFLOP/s  max |dv| / max |v| vs fp32 = %.2e" % (mode, dt * 1e3, n_news / dt, n_news * 241.3e6 / dt / 1e12, err))
+        print("mode=%s  %.1f ms  %.0f news/s  %.1f TFLOP/s  max |dv| / max |v| vs fp32 = %.2e" % (mode, dt * 1e3, n_news / dt, n_news * 241.3e6 / dt / 1e12, err))
         del cache

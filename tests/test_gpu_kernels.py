@@ -117,6 +117,20 @@ def test_linear_bf16_tma(lib, m, n, k, act):
     assert float(got16[:, n:].float().abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("m,n,k", [(300, 900, 300), (1000, 300, 512), (77, 512, 300), (5, 7, 52)])
+def test_linear_x3_fp32_accurate(lib, m, n, k):
+    """Three accumulating bf16 tensor-core passes on hi / lo operand pairs reproduce the fp32 layer to ~1e-5 of the row scale
+    (bf16 alone: 1e-2), with the residual after (no activation) or the partial sums before the activation (ReLU)."""
+    a, w, b, r = randn(m, k, seed=1), randn(n, k, seed=2, scale=k ** -0.5), randn(n, seed=3), randn(m, n, seed=4)
+    ah, al = ops.split_bf16(a)
+    assert float((ah.float()[:, :k] + al.float()[:, :k] - a).abs().max()) <= 2.0 ** -16 * float(a.abs().max())
+    assert float(ah[:, k:].float().abs().sum()) == 0 and float(al[:, k:].float().abs().sum()) == 0
+    wh, wl = ops.split_bf16(w)
+    z = a.double() @ w.double().t() + b.double()
+    close(ops.linear_x3(ah, al, wh, wl, b, residual=r), z + r.double(), 5e-5)
+    close(ops.linear_x3(ah, al, wh, wl, b, act=ops.ACT_RELU), torch.relu(z), 5e-5)
+
+
 def test_stage_a_bf16_glue(lib):
     """bf16 images written beside the fp32 rows: embed_pe_bf16, layernorm_bf16, mha_bf16 against their fp32 twins."""
     n, T, d, heads = 5, 32, 300, 10

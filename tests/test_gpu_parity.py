@@ -63,6 +63,26 @@ def test_news_encoder_stage_vectors(lib, case, golden_dir):
     assert rel(model.scoring.lime_vectors(hist, fresh, life).cpu().numpy(), g["lime_vec"]) < TOL
 
 
+@pytest.mark.parametrize("case", ["small_bs8", "buckets20"])
+def test_news_encoder_fp32x3_mode_matches_reference(lib, case, golden_dir):
+    """fp32x3 mode (every transformer GEMM as three bf16 tensor-core passes on hi / lo operand pairs, 2^-16 per product): an
+    opt-in mode with its own bar, 2e-4 against the reference's outputs (measured worst case 1.03e-4 on the 900-d content
+    vectors, 4e-6 against the fp32 FFMA mode on the bench corpus); the default fp32 mode keeps the 1e-4 bar."""
+    cfg, news, imp, g, sd, model = load_case(case, golden_dir)
+    n0 = g["content"].shape[0]
+    t = lambda a: torch.as_tensor(a[:n0]).to(DEV).contiguous()
+    fresh, life = torch.as_tensor(g["stage_fresh"]).to(DEV), torch.as_tensor(g["stage_life"]).to(DEV)
+    model.news_encoder.engine.x3 = True
+    try:
+        with torch.no_grad():
+            content = model.news_encoder.engine.encode_content(t(news.title_text), t(news.body_text), t(news.category), t(news.subCategory))
+            hist, cand = model.scoring.build_rows(t(news.title_text), t(news.body_text), t(news.category), t(news.subCategory))
+        assert rel(content.cpu().numpy(), g["content"]) < 2 * TOL
+        assert rel(model.scoring.lime_vectors(hist, fresh, life).cpu().numpy(), g["lime_vec"]) < 2 * TOL
+    finally:
+        model.news_encoder.engine.x3 = False
+
+
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_model_forward_matches_reference(lib, case, golden_dir):
     """Model.forward on the reference's own eval mini-batches (26 tensors, one pair per sample)."""
