@@ -362,6 +362,9 @@ class ScoringEngine:
         gb = ca.gate_proj.bias.detach().clone().view(1, D)
         ops.scale_rows(gb, None, -LOG2E)
         F["Gg"], F["gate_bias"] = Gg, gb.view(-1)
+        # bf16 pairs of the two per-news fold matrices (the tensor-core modes of Stage A run them as fp32x3 passes)
+        for name in ("G", "Gg"):
+            F[name + "_hi"], F[name + "_lo"] = ops.split_bf16(F[name])
         # topic attention: S[head,h] = (W_k,head^T Q_head) . t_h + Q_head . b_k,head, all / sqrt(D),
         # with Q = W_q t_c + b_q   (layers.py:66-70)  ->  affine map of t_c into [50*10 + 10]
         Wq, bq = ca.query_proj.weight.detach(), ca.query_proj.bias.detach()
@@ -422,11 +425,19 @@ class ScoringEngine:
             content = self.news.encode_content(tt, bt, ct, sb)
             h, c = hist[lo:hi], cand[lo:hi]
             ops.linear(content, Wc, out=h[:, :D])                                   # vc
-            ops.linear(h[:, :D], F["Gg"], out=h[:, HIST_GW:HIST_GW + D])            # gw
+            tc_mode = self.news.bf16 or self.news.x3        # tensor-core modes: the two folds as fp32x3 passes (2^-16 per product)
+            if tc_mode:
+                vh, vl = ops.split_bf16(h[:, :D])
+                ops.linear_x3(vh, vl, F["Gg_hi"], F["Gg_lo"], out=h[:, HIST_GW:HIST_GW + D])
+            else:
+                ops.linear(h[:, :D], F["Gg"], out=h[:, HIST_GW:HIST_GW + D])        # gw
             ops.topic_rep(lime.category_embedding.weight.detach(), lime.subCategory_embedding.weight.detach(),
                           lime.category_affine.weight.detach(), lime.category_affine.bias.detach(),
                           ct, sb, h[:, HIST_T:], TOPIC_LD)
-            ops.linear(h[:, :D], F["G"], out=c[:, :CAND_NFOLD], n=CAND_NFOLD)       # w1 w2 w3 + scalars
+            if tc_mode:
+                ops.linear_x3(vh, vl, F["G_hi"], F["G_lo"], out=c[:, :CAND_NFOLD], n=CAND_NFOLD)
+            else:
+                ops.linear(h[:, :D], F["G"], out=c[:, :CAND_NFOLD], n=CAND_NFOLD)   # w1 w2 w3 + scalars
             ops.linear(h[:, HIST_T:HIST_T + TOPIC_LD], F["Atq"], F["atq0"],
                        out=c[:, CAND_TQ:CAND_TQ + TOPIC * HEADS + HEADS])           # tq, qb
         ops.row_absmax(hist[:, HIST_GW:HIST_GW + D], hist[:, HIST_GW_ABSMAX])

@@ -57,10 +57,13 @@ class NewsVectorCache:
         return self.hist_rows.numel() * 4 + self.cand_rows.numel() * 4 + (self.cand16.numel() * 2 if self.cand16 is not None else 0) + (self.meta.numel() * 4 if self.meta is not None else 0) + (self.hist_vg.numel() * 4 if self.hist_vg is not None else 0)
 
 
-def build_news_cache(model, news: NewsTable, device=None, chunk=2048) -> NewsVectorCache:
+def build_news_cache(model, news: NewsTable, device=None, chunk=None) -> NewsVectorCache:
     """Encode every news of the corpus once (the reference re-encodes 50 history news per scored
     pair, dataset.py:192-227 + util.py:88-112)."""
     device = device or next(model.parameters()).device
+    if chunk is None:       # news per encoder pass: the tensor-core modes amortise their per-launch weight loads over more rows
+        eng = model.news_encoder.engine
+        chunk = 8192 if (eng.bf16 or eng.x3) else 2048
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.int32)).to(device)
     with torch.no_grad():
         hist, cand = model.scoring.build_rows(t(news.title_text), t(news.body_text), t(news.category),
