@@ -28,16 +28,22 @@ def remaining_lifetime(config, news_category, news_freshness, news_user_topic_li
     raise ValueError("Invalid lifetime_type")
 
 
-def allreduce_gradients(params, group=None):
-    """Data-parallel gradient averaging: ONE all-reduce over a flat fp32 buffer of every gradient that
-    exists (NCCL over NVLink on the box, gloo in the CPU tests), then scattered back.  Identical to what
-    DistributedDataParallel computes (mean over ranks), done after backward so that the clip-by-global-
-    norm of trainer.py:147 sees the reduced gradients, as with DDP + clip_grad_norm_ (trainer.py:334-337)."""
+def allreduce_gradients(params, group=None, flat=None):
+    """Data-parallel gradient averaging: ONE all-reduce over a flat fp32 buffer of every gradient (NCCL over NVLink on
+    the box, gloo in the CPU tests).  Identical to what DistributedDataParallel computes (mean over ranks), done after
+    backward so that the clip-by-global-norm of trainer.py:147 sees the reduced gradients, as with DDP +
+    clip_grad_norm_ (trainer.py:334-337).  ``flat``: the buffer the parameters' ``.grad`` tensors are views of
+    (``Trainer`` keeps one, like DDP's gradient_as_bucket_view): reduced in place, no gather / scatter copies.  Without
+    it the gradients are concatenated, reduced and copied back."""
     if not (dist.is_available() and dist.is_initialized()):
         return 0
     world = dist.get_world_size(group)
     if world == 1:
         return 0
+    if flat is not None:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        return flat.numel() * 4
     # every rank must contribute the same layout: parameters without a gradient on this rank send zeros
     plist = [p for p in params if p.requires_grad]
     flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in plist])
@@ -61,6 +67,18 @@ class Trainer:
         self.optimizer = optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=config.lr,
                                     weight_decay=config.weight_decay)
         self.gradient_clip_norm = config.gradient_clip_norm
+        # every .grad is a view of ONE flat buffer (zeroed per step instead of zero_grad's set-to-None): autograd accumulates
+        # into the views in place, the data-parallel all-reduce runs on the buffer itself
+        # (only with weight_decay == 0, the reference default: a parameter that never receives a gradient -- the dead ISAB /
+        # MAB blocks -- then sees a zero gradient, which Adam ignores exactly like the reference's ``grad is None``)
+        plist = [p for p in model.parameters() if p.requires_grad]
+        self._flat = None
+        if plist and config.weight_decay == 0:
+            self._flat = torch.zeros(sum(p.numel() for p in plist), dtype=torch.float32, device=plist[0].device)
+            off = 0
+            for p in plist:
+                p.grad = self._flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
 
     def step(self, batch):
         """batch: the 25 tensors of Train_Dataset.__getitem__ (dataset.py:105-141), already on the device."""
@@ -73,9 +91,12 @@ class Trainer:
             loss = loss + model.news_encoder.auxiliary_loss.mean()
         if model.user_encoder.auxiliary_loss is not None:                    # trainer.py:140-142
             loss = loss + model.user_encoder.auxiliary_loss.mean()
-        self.optimizer.zero_grad()
+        if self._flat is not None:
+            self._flat.zero_()                                              # == optimizer.zero_grad(), keeping the views
+        else:
+            self.optimizer.zero_grad()
         loss.backward()
-        self.allreduce_bytes = allreduce_gradients(model.parameters(), self.group)
+        self.allreduce_bytes = allreduce_gradients(model.parameters(), self.group, flat=self._flat)
         if self.gradient_clip_norm > 0:
             nn.utils.clip_grad_norm_(model.parameters(), self.gradient_clip_norm)
         self.optimizer.step()
