@@ -94,14 +94,18 @@ int lime_linear_bf16(const float *A, int64_t lda, const float *W, int64_t ldw, c
  * memory, two TMEM accumulators (csrc/gemm_tma.cu).  Replaces the same reference lines as lime_linear.                   */
 int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, int64_t ldw, const float *bias, const float *residual,
                          int64_t ldr, void *C, int64_t ldc, int32_t c_is_bf16, int64_t m, int32_t n, int32_t k, int32_t act,
-                         void *stream);
+                         float alpha, int32_t ab_is_fp16, void *stream);
+/* alpha scales the accumulator before bias / residual (C = act(alpha A . W^T + bias) + residual); ab_is_fp16 != 0: A and W are
+ * fp16 instead of bf16 (the hi / lo pairs of the fp32x3 mode, pre-scaled by powers of two: alpha undoes the scaling). */
 /* act | LIME_ACT_RES_FIRST: the residual joins the sum BEFORE the activation, C = act(A . W^T + bias + residual): the
  * accumulating passes of the three-pass bf16x3 layer (residual = C, in place). */
 #define LIME_ACT_RES_FIRST 16
-/* fp32 rows -> bf16 pair hi = bf16(x), lo = bf16(x - hi), each [rows, ld16] with columns d..ld16-1 zero: x = hi + lo to 2^-17.
- * With the same split of W, x . W^T ~ xh . Wh^T + xl . Wh^T + xh . Wl^T reproduces the fp32 product to ~2^-16 relative on the
- * tensor cores (three lime_linear_bf16_tma passes accumulating in place): the "fp32x3" encoder mode. */
-int lime_split_bf16_pairs(const float *x, int64_t ldx, int64_t rows, int32_t d, void *hi, void *lo, int32_t ld16, void *stream);
+/* fp32 rows -> 16-bit pair hi = r16(scale x), lo = r16(scale x - hi), each [rows, ld16] with columns d..ld16-1 zero; fp16 pairs
+ * (as_fp16 != 0: scale x = hi + lo to 2^-22, scale a power of two that keeps hi below 65504) or bf16 pairs (2^-17).
+ * With the same split of W, x . W^T ~ xh . Wh^T + xl . Wh^T + xh . Wl^T reproduces the fp32 product on the tensor cores
+ * (three lime_linear_bf16_tma passes accumulating in place): the "fp32x3" encoder mode. */
+int lime_split_bf16_pairs(const float *x, int64_t ldx, int64_t rows, int32_t d, void *hi, void *lo, int32_t ld16, float scale,
+                          int32_t as_fp16, void *stream);
 /* Small general GEMM with arbitrary strides (weight folding, done once per checkpoint):
  * C[i*ldc + j] = alpha * sum_k A[i*sam + k*sak] * B[k*sbk + j*sbn]                                */
 int lime_gemm_strided(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbk,

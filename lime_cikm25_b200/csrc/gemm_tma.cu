@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap,
                 const __grid_constant__ CUtensorMap cmap, const __grid_constant__ CUtensorMap rmap, int tma_epilogue, int ncov,
                 const float *__restrict__ bias, const float *__restrict__ residual, int64_t ldr, void *__restrict__ Cout,
-                int64_t ldc, int c_bf16, int64_t m, int n, int nkb, int bn, int n_tiles, int act) {
+                int64_t ldc, int c_bf16, int64_t m, int n, int nkb, int bn, int n_tiles, int act, float alpha, int ab_fp16) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *base = smem_raw;
     if (threadIdx.x == 0 && (tc::smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -138,7 +138,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     } else if (warp == GT_EPI_WARPS + 1) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
-            const uint32_t idesc = tc::idesc_bf16_f32(GT_M, bn);
+            const uint32_t idesc = ab_fp16 ? tc::idesc_f16_f32(GT_M, bn) : tc::idesc_bf16_f32(GT_M, bn);
             tc::mbar_wait(bars + GB_WFULL, 0);
             tc::fence_after_sync();
             uint32_t it = 0, tile = 0;
@@ -209,10 +209,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                                 const float4 b0 = *reinterpret_cast<const float4 *>(bias_s + c0 + 32 * hh + 8 * u);
                                 const float4 b1 = *reinterpret_cast<const float4 *>(bias_s + c0 + 32 * hh + 8 * u + 4);
                                 uint4 o;
-                                o.x = tc::pack_bf16(act_apply(act, __uint_as_float(v[8 * u]) + b0.x), act_apply(act, __uint_as_float(v[8 * u + 1]) + b0.y));
-                                o.y = tc::pack_bf16(act_apply(act, __uint_as_float(v[8 * u + 2]) + b0.z), act_apply(act, __uint_as_float(v[8 * u + 3]) + b0.w));
-                                o.z = tc::pack_bf16(act_apply(act, __uint_as_float(v[8 * u + 4]) + b1.x), act_apply(act, __uint_as_float(v[8 * u + 5]) + b1.y));
-                                o.w = tc::pack_bf16(act_apply(act, __uint_as_float(v[8 * u + 6]) + b1.z), act_apply(act, __uint_as_float(v[8 * u + 7]) + b1.w));
+                                o.x = tc::pack_bf16(act_apply(act, fmaf(alpha, __uint_as_float(v[8 * u]), b0.x)), act_apply(act, fmaf(alpha, __uint_as_float(v[8 * u + 1]), b0.y)));
+                                o.y = tc::pack_bf16(act_apply(act, fmaf(alpha, __uint_as_float(v[8 * u + 2]), b0.z)), act_apply(act, fmaf(alpha, __uint_as_float(v[8 * u + 3]), b0.w)));
+                                o.z = tc::pack_bf16(act_apply(act, fmaf(alpha, __uint_as_float(v[8 * u + 4]), b1.x)), act_apply(act, fmaf(alpha, __uint_as_float(v[8 * u + 5]), b1.y)));
+                                o.w = tc::pack_bf16(act_apply(act, fmaf(alpha, __uint_as_float(v[8 * u + 6]), b1.z)), act_apply(act, fmaf(alpha, __uint_as_float(v[8 * u + 7]), b1.w)));
                                 *reinterpret_cast<uint4 *>(buf + lane * 128 + 16 * ((4 * hh + u) ^ (lane & 7))) = o;
                             }
                         }
@@ -227,8 +227,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                         for (int u = 0; u < 8; ++u) {
                             const float4 bb = *reinterpret_cast<const float4 *>(bias_s + c0 + 4 * u);
                             float4 *p = reinterpret_cast<float4 *>(buf + lane * 128 + 16 * (u ^ (lane & 7)));
-                            float4 y = make_float4(__uint_as_float(v[4 * u]) + bb.x, __uint_as_float(v[4 * u + 1]) + bb.y,
-                                                   __uint_as_float(v[4 * u + 2]) + bb.z, __uint_as_float(v[4 * u + 3]) + bb.w);
+                            float4 y = make_float4(fmaf(alpha, __uint_as_float(v[4 * u]), bb.x), fmaf(alpha, __uint_as_float(v[4 * u + 1]), bb.y),
+                                                   fmaf(alpha, __uint_as_float(v[4 * u + 2]), bb.z), fmaf(alpha, __uint_as_float(v[4 * u + 3]), bb.w));
                             float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (residual != nullptr) rv = *p;
                             if (res_pre) { y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w; }
@@ -277,10 +277,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float4 bb = *reinterpret_cast<const float4 *>(bias_s + c0 + 4 * q);
-                        x[4 * q] = __uint_as_float(v[4 * q]) + bb.x;
-                        x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb.y;
-                        x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb.z;
-                        x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb.w;
+                        x[4 * q] = fmaf(alpha, __uint_as_float(v[4 * q]), bb.x);
+                        x[4 * q + 1] = fmaf(alpha, __uint_as_float(v[4 * q + 1]), bb.y);
+                        x[4 * q + 2] = fmaf(alpha, __uint_as_float(v[4 * q + 2]), bb.z);
+                        x[4 * q + 3] = fmaf(alpha, __uint_as_float(v[4 * q + 3]), bb.w);
                     }
                     if (!res_pre) {
 #pragma unroll
@@ -384,7 +384,7 @@ int tensor_map_bf16_2d(CUtensorMap *out, const void *ptr, uint64_t cols, uint64_
 
 extern "C" int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, int64_t ldw, const float *bias,
                                     const float *residual, int64_t ldr, void *C, int64_t ldc, int32_t c_is_bf16,
-                                    int64_t m, int32_t n, int32_t k, int32_t act, void *stream) {
+                                    int64_t m, int32_t n, int32_t k, int32_t act, float alpha, int32_t ab_is_fp16, void *stream) {
     using namespace lime;
     LIME_CHECK_ARG(A && W && C, "lime_linear_bf16_tma: null argument");
     LIME_CHECK_ARG(k >= 64 && k % 64 == 0 && k <= 512, "lime_linear_bf16_tma: k=%d must be a multiple of 64 in [64, 512] (pad with zeros)", k);
@@ -430,7 +430,7 @@ extern "C" int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, i
     if (groups < 1) groups = 1;
     if (groups > m_tiles) groups = (int)m_tiles;
     gemm_tma_kernel<<<groups * n_tiles, GT_THREADS, GT_SMEM, as_stream(stream)>>>(amap, wmap, cmap, rmap, tma_epi ? 1 : 0, ncov, bias, residual, ldr,
-                                                                                    C, ldc, c_is_bf16, m, n, nkb, bn, n_tiles, act);
+                                                                                    C, ldc, c_is_bf16, m, n, nkb, bn, n_tiles, act, alpha, ab_is_fp16);
     LIME_LAUNCH_CHECK("gemm_tma_kernel");
     return 0;
 }

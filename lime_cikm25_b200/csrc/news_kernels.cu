@@ -3,6 +3,7 @@
 // dense layer.  The dense layers are lime_linear / lime_linear_bf16.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace lime {
 
@@ -563,12 +564,14 @@ extern "C" int lime_embed_pe_bf16(const float *E, int64_t vocab, const int32_t *
     return 0;
 }
 
-// fp32 rows -> two bf16 images hi = bf16(x), lo = bf16(x - hi) of [rows, ld16] (columns d.. zero): the operands of the
-// three-pass "bf16x3" dense layer (x . w ~ xh . wh + xl . wh + xh . wl, 2^-16 relative per product) of the fp32-accurate
-// tensor-core mode
+// fp32 rows -> two 16-bit images hi = r16(s x), lo = r16(s x - hi) of [rows, ld16] (columns d.. zero): the operands of the
+// three-pass dense layer (x . w ~ xh . wh + xl . wh + xh . wl) of the fp32-accurate tensor-core mode.  fp16 pairs carry
+// 11 + 11 bits (2^-22 relative; s = a power of two that keeps the lo halves of typical values out of the subnormals), bf16
+// pairs 8 + 8 bits (2^-17).
+template <bool F16>
 __global__ void __launch_bounds__(256)
-split_bf16_kernel(const float *__restrict__ x, int64_t ldx, int64_t rows, int d, __nv_bfloat16 *__restrict__ hi,
-                  __nv_bfloat16 *__restrict__ lo, int ld16) {
+split16_kernel(const float *__restrict__ x, int64_t ldx, int64_t rows, int d, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo,
+               int ld16, float scale) {
     const int q4 = ld16 / 4;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * q4) return;
@@ -582,25 +585,37 @@ split_bf16_kernel(const float *__restrict__ x, int64_t ldx, int64_t rows, int d,
         for (int e = 0; e < 4; ++e)
             if (c + e < d) v[e] = x[r * ldx + c + e];
     }
-    float h[4], l[4];
+    uint16_t h[4], l[4];
     for (int e = 0; e < 4; ++e) {
-        h[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
-        l[e] = v[e] - h[e];
+        const float xs = v[e] * scale;
+        if (F16) {
+            const __half hh = __float2half_rn(xs);
+            const __half ll = __float2half_rn(xs - __half2float(hh));
+            h[e] = *reinterpret_cast<const uint16_t *>(&hh);
+            l[e] = *reinterpret_cast<const uint16_t *>(&ll);
+        } else {
+            const __nv_bfloat16 hh = __float2bfloat16_rn(xs);
+            const __nv_bfloat16 ll = __float2bfloat16_rn(xs - __bfloat162float(hh));
+            h[e] = *reinterpret_cast<const uint16_t *>(&hh);
+            l[e] = *reinterpret_cast<const uint16_t *>(&ll);
+        }
     }
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(h[0], h[1]), h1 = __floats2bfloat162_rn(h[2], h[3]);
-    __nv_bfloat162 l0 = __floats2bfloat162_rn(l[0], l[1]), l1 = __floats2bfloat162_rn(l[2], l[3]);
-    *reinterpret_cast<uint2 *>(hi + r * ld16 + c) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
-    *reinterpret_cast<uint2 *>(lo + r * ld16 + c) = make_uint2(*reinterpret_cast<uint32_t *>(&l0), *reinterpret_cast<uint32_t *>(&l1));
+    *reinterpret_cast<uint2 *>(hi + r * ld16 + c) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+    *reinterpret_cast<uint2 *>(lo + r * ld16 + c) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
 }
 
-extern "C" int lime_split_bf16_pairs(const float *x, int64_t ldx, int64_t rows, int32_t d, void *hi, void *lo, int32_t ld16, void *stream) {
+extern "C" int lime_split_bf16_pairs(const float *x, int64_t ldx, int64_t rows, int32_t d, void *hi, void *lo, int32_t ld16, float scale,
+                                     int32_t as_fp16, void *stream) {
     LIME_CHECK_ARG(x && hi && lo, "lime_split_bf16_pairs: null argument");
     LIME_CHECK_ARG(d >= 1 && ld16 >= d && (ld16 & 7) == 0 && ldx >= d, "lime_split_bf16_pairs: d=%d ld16=%d ldx=%lld", d, ld16, (long long)ldx);
     if (rows <= 0) return 0;
     const int64_t total = rows * (ld16 / 4);
-    split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, ldx, rows, d, reinterpret_cast<__nv_bfloat16 *>(hi),
-                                                                                    reinterpret_cast<__nv_bfloat16 *>(lo), ld16);
-    LIME_LAUNCH_CHECK("split_bf16_kernel");
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (as_fp16)
+        split16_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(x, ldx, rows, d, reinterpret_cast<uint16_t *>(hi), reinterpret_cast<uint16_t *>(lo), ld16, scale);
+    else
+        split16_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(x, ldx, rows, d, reinterpret_cast<uint16_t *>(hi), reinterpret_cast<uint16_t *>(lo), ld16, scale);
+    LIME_LAUNCH_CHECK("split16_kernel");
     return 0;
 }
 

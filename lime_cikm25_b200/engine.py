@@ -76,7 +76,7 @@ class NewsEncoderEngine:
         self._prep = None
         self._fp = None
         self.bf16 = False        # "bf16 mode": bf16 activations, the 4 transformer GEMMs by TMA + tcgen05 (lime_linear_bf16_tma)
-        self.x3 = False          # "fp32x3 mode": fp32 activations, every transformer GEMM as 3 bf16 tensor-core passes on hi / lo pairs
+        self.x3 = False          # "fp32x3 mode" (opt-in; default = the fp32 FFMA kernels, the strict-parity mode): fp32 activations, every transformer GEMM as 3 bf16 tensor-core passes on hi / lo pairs
 
     # -- weights -----------------------------------------------------------------------------------
     def _params(self):
@@ -129,9 +129,8 @@ class NewsEncoderEngine:
                 br[name + "16"] = pad16(br[name])
             br["in_w16"] = pad16(head_pad(br["in_w"]))          # head-padded q | k | v: the layout lime_mha_bf16 reads
             br["in_b_hp"] = head_pad(br["in_b"])
-            for name in ("in_w", "out_w", "l1_w", "l2_w"):        # bf16 pairs w = hi + lo for the fp32x3 mode
-                hi = br[name].to(torch.bfloat16)
-                br[name + "_hi"], br[name + "_lo"] = pad16(hi.float()), pad16(br[name] - hi.float())
+            for name in ("in_w", "out_w", "l1_w", "l2_w"):        # fp16 pairs 2^10 w = hi + lo for the fp32x3 mode
+                br[name + "_hi"], br[name + "_lo"] = ops.split16(br[name], scale=ops.X3_W_SCALE)
         P["title_pe"] = base.title_pos_encoder.pe.detach().reshape(-1, 300).contiguous()
         P["body_pe"] = base.body_pos_encoder.pe.detach().reshape(-1, 300).contiguous()
         pw = m.project.weight.detach()                    # [400, 1800] = [W_c | W_f]
@@ -190,22 +189,23 @@ class NewsEncoderEngine:
         E = base.word_embedding.weight.detach()
         x0 = torch.empty(rows, 300, dtype=torch.float32, device=dev)
         ops.embed_pe(E, ids, T, pe, x0)
-        xh, xl = ops.split_bf16(x0)
-        qkv = ops.linear_x3(xh, xl, W["in_w_hi"], W["in_w_lo"], W["in_b"])
+        sa, al = ops.X3_ACT_SCALE, 1.0 / (ops.X3_ACT_SCALE * ops.X3_W_SCALE)
+        xh, xl = ops.split16(x0, scale=sa)
+        qkv = ops.linear_x3(xh, xl, W["in_w_hi"], W["in_w_lo"], W["in_b"], alpha=al)
         del xh, xl
         ctx = torch.empty(rows, 300, dtype=torch.float32, device=dev)
         ops.mha(qkv, ctx, n, T, 300, self.cfg.head_num)
         del qkv
-        ch, cl = ops.split_bf16(ctx)
-        y = ops.linear_x3(ch, cl, W["out_w_hi"], W["out_w_lo"], W["out_b"], residual=x0)
+        ch, cl = ops.split16(ctx, scale=sa)
+        y = ops.linear_x3(ch, cl, W["out_w_hi"], W["out_w_lo"], W["out_b"], residual=x0, alpha=al)
         del ch, cl
         x1 = ops.layernorm(y, W["n1_w"], W["n1_b"], out=ctx, eps=W["eps1"])       # reuse ctx
-        xh, xl = ops.split_bf16(x1)
-        hf = ops.linear_x3(xh, xl, W["l1_w_hi"], W["l1_w_lo"], W["l1_b"], act=ops.ACT_RELU)
+        xh, xl = ops.split16(x1, scale=sa)
+        hf = ops.linear_x3(xh, xl, W["l1_w_hi"], W["l1_w_lo"], W["l1_b"], act=ops.ACT_RELU, alpha=al)
         del xh, xl
-        hh, hl = ops.split_bf16(hf)
+        hh, hl = ops.split16(hf, scale=sa)
         del hf
-        y2 = ops.linear_x3(hh, hl, W["l2_w_hi"], W["l2_w_lo"], W["l2_b"], residual=x1, out=y)
+        y2 = ops.linear_x3(hh, hl, W["l2_w_hi"], W["l2_w_lo"], W["l2_b"], residual=x1, out=y, alpha=al)
         ops.layernorm_meanpool(y2, W["n2_w"], W["n2_b"], feat, n, T, eps=W["eps2"])
 
     def encode_content(self, title_text, body_text, category, subCategory):
@@ -364,7 +364,7 @@ class ScoringEngine:
         F["Gg"], F["gate_bias"] = Gg, gb.view(-1)
         # bf16 pairs of the two per-news fold matrices (the tensor-core modes of Stage A run them as fp32x3 passes)
         for name in ("G", "Gg"):
-            F[name + "_hi"], F[name + "_lo"] = ops.split_bf16(F[name])
+            F[name + "_hi"], F[name + "_lo"] = ops.split16(F[name], scale=ops.X3_W_SCALE)
         # topic attention: S[head,h] = (W_k,head^T Q_head) . t_h + Q_head . b_k,head, all / sqrt(D),
         # with Q = W_q t_c + b_q   (layers.py:66-70)  ->  affine map of t_c into [50*10 + 10]
         Wq, bq = ca.query_proj.weight.detach(), ca.query_proj.bias.detach()
@@ -427,15 +427,16 @@ class ScoringEngine:
             ops.linear(content, Wc, out=h[:, :D])                                   # vc
             tc_mode = self.news.bf16 or self.news.x3        # tensor-core modes: the two folds as fp32x3 passes (2^-16 per product)
             if tc_mode:
-                vh, vl = ops.split_bf16(h[:, :D])
-                ops.linear_x3(vh, vl, F["Gg_hi"], F["Gg_lo"], out=h[:, HIST_GW:HIST_GW + D])
+                al = 1.0 / (ops.X3_ACT_SCALE * ops.X3_W_SCALE)
+                vh, vl = ops.split16(h[:, :D], scale=ops.X3_ACT_SCALE)
+                ops.linear_x3(vh, vl, F["Gg_hi"], F["Gg_lo"], out=h[:, HIST_GW:HIST_GW + D], alpha=al)
             else:
                 ops.linear(h[:, :D], F["Gg"], out=h[:, HIST_GW:HIST_GW + D])        # gw
             ops.topic_rep(lime.category_embedding.weight.detach(), lime.subCategory_embedding.weight.detach(),
                           lime.category_affine.weight.detach(), lime.category_affine.bias.detach(),
                           ct, sb, h[:, HIST_T:], TOPIC_LD)
             if tc_mode:
-                ops.linear_x3(vh, vl, F["G_hi"], F["G_lo"], out=c[:, :CAND_NFOLD], n=CAND_NFOLD)
+                ops.linear_x3(vh, vl, F["G_hi"], F["G_lo"], out=c[:, :CAND_NFOLD], n=CAND_NFOLD, alpha=al)
             else:
                 ops.linear(h[:, :D], F["G"], out=c[:, :CAND_NFOLD], n=CAND_NFOLD)   # w1 w2 w3 + scalars
             ops.linear(h[:, HIST_T:HIST_T + TOPIC_LD], F["Atq"], F["atq0"],

@@ -65,7 +65,7 @@ def linear(a, w, bias=None, residual=None, act=ACT_NONE, out=None, n=None, k=Non
     return out
 
 
-def linear_tma(a16, w16, bias=None, residual=None, act=ACT_NONE, out=None, n=None, out_bf16=True, ld_out=None):
+def linear_tma(a16, w16, bias=None, residual=None, act=ACT_NONE, out=None, n=None, out_bf16=True, ld_out=None, alpha=1.0):
     """Stage A dense layer on bf16 activations (lime_linear_bf16_tma): a16 [m, kp] bf16, w16 [n, kp] bf16 (kp = the
     contraction length padded to a multiple of 64 with zero columns), bias / residual fp32.  Returns bf16 [m, ld_out]
     (padding columns zero: the next layer's operand) or fp32 [m, n]."""
@@ -76,37 +76,50 @@ def linear_tma(a16, w16, bias=None, residual=None, act=ACT_NONE, out=None, n=Non
         out = (torch.empty((m, ld_out or n), dtype=torch.bfloat16, device=a16.device) if out_bf16
                else torch.empty((m, n), dtype=torch.float32, device=a16.device))
     ldr = _rowmajor(residual, "residual") if residual is not None else 0
-    check(lib.lime_linear_bf16_tma(_ptr(a16, torch.bfloat16, "a16"), _rowmajor(a16, "a16"), _ptr(w16, torch.bfloat16, "w16"),
+    if a16.dtype != w16.dtype or a16.dtype not in (torch.bfloat16, torch.float16):
+        raise TypeError("a16 / w16 must both be bfloat16 or both float16")
+    check(lib.lime_linear_bf16_tma(_ptr(a16, a16.dtype, "a16"), _rowmajor(a16, "a16"), _ptr(w16, a16.dtype, "w16"),
                                    _rowmajor(w16, "w16"), _ptr(bias, torch.float32, "bias"),
                                    _ptr(residual, torch.float32, "residual"), ldr, out.data_ptr(), _rowmajor(out, "out"),
-                                   1 if out.dtype == torch.bfloat16 else 0, m, n, kp, act, _stream()), "lime_linear_bf16_tma")
+                                   1 if out.dtype == torch.bfloat16 else 0, m, n, kp, act, float(alpha),
+                                   1 if a16.dtype == torch.float16 else 0, _stream()), "lime_linear_bf16_tma")
     return out
 
 
 ACT_RES_FIRST = 16
 
 
-def split_bf16(x, kp=None):
-    """fp32 [rows, d] -> (hi, lo) bf16 [rows, kp] with x = hi + lo to 2^-17 (kp = d padded to a multiple of 64, zero columns)."""
+def split16(x, kp=None, scale=1.0, fp16=True):
+    """fp32 [rows, d] -> (hi, lo) 16-bit pair [rows, kp] with scale * x = hi + lo (fp16: to 2^-22, bf16: to 2^-17); kp = d padded
+    to a multiple of 64 with zero columns."""
     lib = _lib.require_device()
     rows, d = x.shape
     kp = kp or (d + 63) // 64 * 64
-    hi = torch.empty(rows, kp, dtype=torch.bfloat16, device=x.device)
-    lo = torch.empty(rows, kp, dtype=torch.bfloat16, device=x.device)
-    check(lib.lime_split_bf16_pairs(_ptr(x, torch.float32, "x"), _rowmajor(x, "x"), rows, d, hi.data_ptr(), lo.data_ptr(), kp, _stream()),
-          "lime_split_bf16_pairs")
+    dt = torch.float16 if fp16 else torch.bfloat16
+    hi = torch.empty(rows, kp, dtype=dt, device=x.device)
+    lo = torch.empty(rows, kp, dtype=dt, device=x.device)
+    check(lib.lime_split_bf16_pairs(_ptr(x, torch.float32, "x"), _rowmajor(x, "x"), rows, d, hi.data_ptr(), lo.data_ptr(), kp,
+                                    float(scale), 1 if fp16 else 0, _stream()), "lime_split_bf16_pairs")
     return hi, lo
 
 
-def linear_x3(xh, xl, wh, wl, bias=None, residual=None, act=ACT_NONE, out=None, n=None):
-    """fp32-accurate dense layer on the tensor cores: out = act(x . w^T + bias) + residual with x = xh + xl, w = wh + wl as bf16
-    pairs, three accumulating lime_linear_bf16_tma passes (xh.wh [+ residual], + xl.wh, + xh.wl + bias then act).  With an
-    activation the residual must be None (the accumulating passes add BEFORE the activation)."""
+def split_bf16(x, kp=None):
+    return split16(x, kp, 1.0, fp16=False)
+
+
+X3_ACT_SCALE, X3_W_SCALE = 16.0, 1024.0      # fp16 pairs of the fp32x3 mode: activations * 2^4, weights * 2^10 (hi < 65504, lo out of the subnormals)
+
+
+def linear_x3(xh, xl, wh, wl, bias=None, residual=None, act=ACT_NONE, out=None, n=None, alpha=1.0):
+    """fp32-accurate dense layer on the tensor cores: out = act(alpha x . w^T + bias) + residual with x = xh + xl, w = wh + wl as
+    16-bit pairs (fp16: 2^-21 per product; alpha undoes their power-of-two scaling), three accumulating lime_linear_bf16_tma
+    passes (xh.wh [+ residual], + xl.wh, + xh.wl + bias then act).  With an activation the residual must be None (the
+    accumulating passes add BEFORE the activation)."""
     assert act == ACT_NONE or residual is None
     n = wh.shape[0] if n is None else n
-    out = linear_tma(xh, wh, None, residual=residual, out=out, n=n, out_bf16=False)
-    linear_tma(xl, wh, None, residual=out, out=out, n=n, out_bf16=False)
-    linear_tma(xh, wl, bias, residual=out, act=act | ACT_RES_FIRST, out=out, n=n, out_bf16=False)
+    out = linear_tma(xh, wh, None, residual=residual, out=out, n=n, out_bf16=False, alpha=alpha)
+    linear_tma(xl, wh, None, residual=out, out=out, n=n, out_bf16=False, alpha=alpha)
+    linear_tma(xh, wl, bias, residual=out, act=act | ACT_RES_FIRST, out=out, n=n, out_bf16=False, alpha=alpha)
     return out
 
 

@@ -118,17 +118,21 @@ def test_linear_bf16_tma(lib, m, n, k, act):
 
 
 @pytest.mark.parametrize("m,n,k", [(300, 900, 300), (1000, 300, 512), (77, 512, 300), (5, 7, 52)])
-def test_linear_x3_fp32_accurate(lib, m, n, k):
-    """Three accumulating bf16 tensor-core passes on hi / lo operand pairs reproduce the fp32 layer to ~1e-5 of the row scale
-    (bf16 alone: 1e-2), with the residual after (no activation) or the partial sums before the activation (ReLU)."""
+@pytest.mark.parametrize("fp16", [True, False])
+def test_linear_x3_fp32_accurate(lib, m, n, k, fp16):
+    """Three accumulating tensor-core passes on hi / lo operand pairs reproduce the fp32 layer: fp16 pairs (pre-scaled by powers
+    of two, undone by alpha) to ~1e-6 of the row scale, bf16 pairs to ~3e-5 (one bf16 product: 1e-2); the residual after (no
+    activation) or the partial sums before the activation (ReLU)."""
     a, w, b, r = randn(m, k, seed=1), randn(n, k, seed=2, scale=k ** -0.5), randn(n, seed=3), randn(m, n, seed=4)
-    ah, al = ops.split_bf16(a)
-    assert float((ah.float()[:, :k] + al.float()[:, :k] - a).abs().max()) <= 2.0 ** -16 * float(a.abs().max())
+    sa, sw = (ops.X3_ACT_SCALE, ops.X3_W_SCALE) if fp16 else (1.0, 1.0)
+    ah, al = ops.split16(a, scale=sa, fp16=fp16)
+    assert float((ah.float()[:, :k] + al.float()[:, :k] - sa * a).abs().max()) <= (2.0 ** -21 if fp16 else 2.0 ** -16) * sa * float(a.abs().max())
     assert float(ah[:, k:].float().abs().sum()) == 0 and float(al[:, k:].float().abs().sum()) == 0
-    wh, wl = ops.split_bf16(w)
+    wh, wl = ops.split16(w, scale=sw, fp16=fp16)
     z = a.double() @ w.double().t() + b.double()
-    close(ops.linear_x3(ah, al, wh, wl, b, residual=r), z + r.double(), 5e-5)
-    close(ops.linear_x3(ah, al, wh, wl, b, act=ops.ACT_RELU), torch.relu(z), 5e-5)
+    tol = 6e-6 if fp16 else 5e-5          # (fp16 pairs: the remaining error is the tensor core's own fp32 accumulation)
+    close(ops.linear_x3(ah, al, wh, wl, b, residual=r, alpha=1.0 / (sa * sw)), z + r.double(), tol)
+    close(ops.linear_x3(ah, al, wh, wl, b, act=ops.ACT_RELU, alpha=1.0 / (sa * sw)), torch.relu(z), tol)
 
 
 def test_stage_a_bf16_glue(lib):

@@ -65,9 +65,10 @@ def test_news_encoder_stage_vectors(lib, case, golden_dir):
 
 @pytest.mark.parametrize("case", ["small_bs8", "buckets20"])
 def test_news_encoder_fp32x3_mode_matches_reference(lib, case, golden_dir):
-    """fp32x3 mode (every transformer GEMM as three bf16 tensor-core passes on hi / lo operand pairs, 2^-16 per product): an
-    opt-in mode with its own bar, 2e-4 against the reference's outputs (measured worst case 1.03e-4 on the 900-d content
-    vectors, 4e-6 against the fp32 FFMA mode on the bench corpus); the default fp32 mode keeps the 1e-4 bar."""
+    """fp32x3 mode (every transformer GEMM as three tensor-core passes on fp16 hi / lo operand pairs, 2^-21 per product): the
+    encoder outputs meet the same 1e-4 bar against the reference's vectors as the fp32 FFMA mode (measured worst element 1.9e-5
+    vs 9.6e-6).  It stays opt-in because the scoring stage amplifies the difference: with it as the default, one logit of
+    test_bucket_sweep_and_flags leaves the 1e-4 bar."""
     cfg, news, imp, g, sd, model = load_case(case, golden_dir)
     n0 = g["content"].shape[0]
     t = lambda a: torch.as_tensor(a[:n0]).to(DEV).contiguous()
@@ -77,8 +78,8 @@ def test_news_encoder_fp32x3_mode_matches_reference(lib, case, golden_dir):
         with torch.no_grad():
             content = model.news_encoder.engine.encode_content(t(news.title_text), t(news.body_text), t(news.category), t(news.subCategory))
             hist, cand = model.scoring.build_rows(t(news.title_text), t(news.body_text), t(news.category), t(news.subCategory))
-        assert rel(content.cpu().numpy(), g["content"]) < 2 * TOL
-        assert rel(model.scoring.lime_vectors(hist, fresh, life).cpu().numpy(), g["lime_vec"]) < 2 * TOL
+        assert rel(content.cpu().numpy(), g["content"]) < TOL
+        assert rel(model.scoring.lime_vectors(hist, fresh, life).cpu().numpy(), g["lime_vec"]) < TOL
     finally:
         model.news_encoder.engine.x3 = False
 
