@@ -6,8 +6,8 @@
 //
 // The shapes are skinny (k = 320 or 512, n <= 900, m = news x tokens = millions), so the kernel is organised around what
 // is re-used:  ONE persistent CTA per SM owns one N tile (bn <= 256 columns) for its whole life and keeps that slice of
-// W RESIDENT in shared memory (bn x k bf16 <= 112 KB, loaded once by TMA); it then streams 128-row tiles of A through a
-// 3-deep TMA ring (16 KB per 64-wide K block).  Per output tile the tensor core runs k/16 MMAs (M = 128, N = bn) into
+// W RESIDENT in shared memory (bn x k bf16 <= 160 KB, loaded once by TMA); it then streams 128-row tiles of A through a
+// 2-deep TMA ring (16 KB per 64-wide K block; measured: 2 stages + one staging tile per warp + a 256-column W slice beat 3 + 2 + 128).  Per output tile the tensor core runs k/16 MMAs (M = 128, N = bn) into
 // one of TWO TMEM accumulators (2 x 256 columns), so the epilogue of tile i (TMEM -> registers -> bias / act / residual
 // -> global) overlaps the MMAs of tile i + 1.  The CTAs that share an M tile (one per N tile) run at the same time on
 // neighbouring SMs: A comes from HBM once and from L2 otherwise.
@@ -26,17 +26,21 @@ namespace lime {
 namespace {
 
 #ifndef LIME_GT_STAGES
-#define LIME_GT_STAGES 3
+#define LIME_GT_STAGES 2
 #endif
 constexpr int GT_M = 128, GT_STAGES = LIME_GT_STAGES, GT_A_BYTES = GT_M * 128;
-constexpr int GT_W_MAX = (160 - 16 * GT_STAGES) * 1024;   // resident W slice: what the A ring and the staging tiles leave
-constexpr int GT_STAGE_BYTES = 4096;           // epilogue staging tile of one warp: 32 rows x 128 B (two per warp)
+#ifndef LIME_GT_STAGE_BUFS
+#define LIME_GT_STAGE_BUFS 1
+#endif
+constexpr int GT_STAGE_BUFS = LIME_GT_STAGE_BUFS;   // epilogue staging tiles per warp
+constexpr int GT_STAGE_BYTES = 4096;           // epilogue staging tile of one warp: 32 rows x 128 B
+constexpr int GT_W_MAX = (224 - 16 * GT_STAGES - 32 * GT_STAGE_BUFS) * 1024;   // resident W slice: what the A ring and the staging tiles leave
 #ifndef LIME_GT_EPI_WARPS
 #define LIME_GT_EPI_WARPS 8
 #endif
 constexpr int GT_EPI_WARPS = LIME_GT_EPI_WARPS;   // two epilogue warps per TMEM lane quadrant, alternating 32-column chunks (measured: 4 -> 8 warps takes the bf16-output GEMMs from 0.48 to 0.32 ms per 262k rows; staging the tile through shared memory for row-contiguous stores was slower)
 constexpr int GT_THREADS = 32 * (GT_EPI_WARPS + 2);
-constexpr int GT_SMEM = GT_W_MAX + GT_STAGES * GT_A_BYTES + 2 * GT_EPI_WARPS * GT_STAGE_BYTES + 1024 /* bias slice */ + 256 /* barriers */;
+constexpr int GT_SMEM = GT_W_MAX + GT_STAGES * GT_A_BYTES + GT_STAGE_BUFS * GT_EPI_WARPS * GT_STAGE_BYTES + 1024 /* bias slice */ + 256 /* barriers */;
 static_assert(GT_SMEM + 1024 <= 232448, "shared memory");
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
@@ -87,7 +91,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     unsigned char *w_s = base;                                     // [nkb][bn rows x 128 B]
     unsigned char *a_s = base + GT_W_MAX;                          // [GT_STAGES][128 rows x 128 B]
     unsigned char *stage_s = base + GT_W_MAX + GT_STAGES * GT_A_BYTES;          // [GT_EPI_WARPS][2][4096], 1024-byte aligned
-    float *bias_s = reinterpret_cast<float *>(stage_s + 2 * GT_EPI_WARPS * GT_STAGE_BYTES);
+    float *bias_s = reinterpret_cast<float *>(stage_s + GT_STAGE_BUFS * GT_EPI_WARPS * GT_STAGE_BYTES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(bias_s) + 1024);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + GB_COUNT);
 
@@ -174,7 +178,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
             // the zero padding columns of a bf16 output are part of the box).  An fp32 residual comes the same way: TMA-loaded
             // into the staging tile, added in place.  Two staging tiles per warp alternate.
             const int ncols_t = min(bn, ncov - col0);              // columns of this N tile inside the stored width
-            unsigned char *my_stage = stage_s + warp * 2 * GT_STAGE_BYTES;
+            unsigned char *my_stage = stage_s + warp * GT_STAGE_BUFS * GT_STAGE_BYTES;
             uint64_t *rbar = bars + GB_RES + warp;
             uint32_t chunk_it = 0, res_it = 0;
             for (int64_t mt = mt0; mt < m_tiles; mt += mt_step, ++tile) {
@@ -184,9 +188,9 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                 bool waited = false;
                 const int cw = c_bf16 ? 64 : 32;                   // columns per box: 128-byte rows either way
                 for (int c0 = cw * half; c0 < ncols_t; c0 += cw * (GT_EPI_WARPS / 4), ++chunk_it) {
-                    unsigned char *buf = my_stage + (chunk_it & 1u) * GT_STAGE_BYTES;
+                    unsigned char *buf = my_stage + (chunk_it % GT_STAGE_BUFS) * GT_STAGE_BYTES;
                     if (lane == 0) {
-                        bulk_wait_read<1>();                       // the store that last read this tile (two chunks ago) is done with it
+                        bulk_wait_read<GT_STAGE_BUFS - 1>();       // the store that last read this tile is done with it
                         if (residual != nullptr) {
                             mbar_expect_tx(rbar, 32 * 32 * 4);
                             tma_load_2d(tc::smem_u32(buf), &rmap, col0 + c0, row0, rbar);
