@@ -62,7 +62,7 @@ constexpr int kThreads = kCompute + 32;
 constexpr int kH = LIME_TC_MAX_HISTORY;         // 56 history slots at most
 constexpr int kTile = LIME_TC_TILE_C;           // candidates per unit handed out by the host
 constexpr int kTriples = 40;                    // M rows = 3 x (candidates + distinct bucket pairs): 10 triples per TMEM quadrant
-constexpr int kMaxBp = 10;                      // distinct bucket pairs of a unit that fit beside its candidates
+constexpr int kMaxBp = 20;                      // distinct bucket pairs of a unit that fit beside its candidates (50 lifetime buckets: about one pair per candidate)
 constexpr int kAS = kTriples;                   // row stride of a_s / t_s  ([u][c])
 constexpr int kStages = 13;                     // 32-wide candidate-operand stages over D = 400 (the last holds 16 dims)
 constexpr int kOStages = 7;                     // 64-wide O stages
@@ -73,7 +73,7 @@ constexpr int kPfStages = LIME_TC_PF_STAGES;    // L2 prefetch distance of the h
 constexpr int kWTile = 32768, kWImg = 16384;    // one 64-dim candidate tile = hi image + lo image of 128 rows x 128 B
 constexpr int kGroups = 7;                      // row groups of 8 unique history rows (56 / 8)
 constexpr int kTabLd = LIME_TOPIC_TAB_LD;
-constexpr int kTabStride = 32;                  // tab_s[u][3 * bp + k] (float2), 3 * kMaxBp <= 32
+constexpr int kTabStride = 64;                  // tab_s[u][3 * bp + k] (float2), 3 * kMaxBp <= 64
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 // Both operands are scaled by a power of two before the fp16 hi / lo split, so that the lo halves of typical values
@@ -89,7 +89,7 @@ constexpr int kC16 = LIME_CAND16_LD;            // fp16 elements per cand16 / ct
 constexpr int OFF_W = 0;                                      // 2 tiles x (hi, lo) x 128 rows x 128 B: four 32-dim ring slots
 constexpr int OFF_O = 2 * kWTile;                             // [Ohi ; Olo ; O1hi] x Up rows x 128 B (two 32-dim half slots)
 constexpr int kOBytes = 3 * 64 * 128;
-constexpr int OFF_TAB = OFF_O;                                // alias (after the MMAs): table-row results [u][32] float2
+constexpr int OFF_TAB = OFF_W;                                // alias (after the MMAs; the candidate tiles are refilled by the next unit only): table-row results [u][64] float2
 constexpr int OFF_T = OFF_O + kOBytes;                        // a[u][c], then t[u][c]
 constexpr int OFF_SUM = OFF_T + kH * kAS * 4;                 // [u][8]: sum c0, c1, c0^2, c0 c1, c1^2
 constexpr int OFF_MID = OFF_SUM + kH * 8 * 4;
@@ -107,8 +107,8 @@ constexpr int UB_CTAB = UB_CNEWS + kCArr;                     // bucket-pair id 
 constexpr int UB_CBIDX = UB_CTAB + kCArr;                     // ... and its index among the unit's distinct pairs
 constexpr int UB_CP = UB_CBIDX + kCArr;
 constexpr int UB_CTOPIC = UB_CP + kCArr;
-constexpr int UB_BTAB = UB_CTOPIC + kCArr;                    // [12] distinct bucket pairs
-constexpr int UB_UNEWS = UB_BTAB + 48;
+constexpr int UB_BTAB = UB_CTOPIC + kCArr;                    // [24] distinct bucket pairs
+constexpr int UB_UNEWS = UB_BTAB + 96;
 constexpr int UB_UTAB = UB_UNEWS + kUArr;
 constexpr int UB_UMASK = UB_UTAB + kUArr;
 constexpr int UB_UTOPIC = UB_UMASK + kUArr;
@@ -127,7 +127,7 @@ constexpr int OFF_MISC = OFF_BARS + 128;                      // tmem slot
 constexpr int OFF_PROF = OFF_MISC + 64;                       // phase clocks of thread 0 (diagnostic)
 constexpr int OFF_BIAS = OFF_PROF + 128;                      // gate bias [400]: read by every lane at every stage
 constexpr int kSmemBytes = OFF_BIAS + kD * 4;
-static_assert(kH * kTabStride * 8 <= kOBytes, "table-row alias overflows the O operand tile");
+static_assert(kH * kTabStride * 8 <= 2 * kWTile, "table-row alias overflows the candidate tiles");
 static_assert(2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM");
 static_assert(OFF_BIAS % 16 == 0, "alignment");
 static_assert(kTile + 1 <= kTriples && 3 * kMaxBp <= kTabStride, "unit capacity");
@@ -1045,7 +1045,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const __grid_cons
             LIME_TICK(7);
         }
         ++pass_iter;
-        __syncthreads();   // the O tile (aliased by tab_s) and TMEM may be overwritten; the next unit buffer is ready
+        __syncthreads();   // the candidate tiles (aliased by tab_s), the O tile and TMEM may be overwritten; the next unit buffer is ready
 
         if (tid == 0) {
             if ((flag_s[0] & 6) != 0) args.fallback_list[atomicAdd(args.fallback_count, 1)] = unit;

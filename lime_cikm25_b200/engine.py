@@ -506,6 +506,8 @@ class ScoringEngine:
             cand16 = self.split_candidates(cand_rows)
             meta = self.news_meta(hist_rows, cand_rows)
             hist_vg = interleave_vg(hist_rows)
+        if getattr(dimp, "planned_buckets", None) is not None:
+            dimp.replan(self.cfg.num_buckets)         # the unit list follows the model's bucketisation
         cache = self.cache_struct(hist_rows, cand_rows, cand16, meta, hist_vg)
         self._keepalive = (cand16, meta, hist_vg)      # derived operands stay referenced until the next call (the launch is asynchronous)
         st = dimp.struct()
@@ -540,11 +542,12 @@ def _host_bucket_pairs(fresh, life, nb):
     return b(fresh) * nb + b(life)
 
 
-def build_units(cand_off, tile_c, cand_bp=None, triples=None):
+def build_units(cand_off, tile_c, cand_bp=None, triples=None, max_pairs=20):
     """Work units of the scoring kernel: every impression's candidate list is cut into runs of consecutive candidates.
     Without ``cand_bp``: runs of at most ``tile_c``.  With ``cand_bp`` (bucket-pair id per candidate) and ``triples``
     (operand-row triples of the tensor-core kernel, 40): greedy runs with candidates + distinct bucket pairs <= triples
-    (the pairs ride along as extra operand rows), at most ``tile_c`` candidates.
+    (the pairs ride along as extra operand rows) and at most ``max_pairs`` distinct pairs (the kernel's kMaxBp), at most
+    ``tile_c`` candidates.
     Returns (unit_imp, unit_pair0, unit_count) as int64."""
     cand_off = np.asarray(cand_off, np.int64)
     counts = np.diff(cand_off)
@@ -559,7 +562,7 @@ def build_units(cand_off, tile_c, cand_bp=None, triples=None):
     cand_bp = np.asarray(cand_bp, np.int64)
     ui, up, uc = [], [], []
     # impressions whose candidates + (at most that many) pairs fit one unit need no scan
-    safe = 2 * counts <= triples
+    safe = (2 * counts <= triples) & (counts <= max_pairs)
     for i in range(counts.shape[0]):
         n, o = int(counts[i]), int(cand_off[i])
         if n == 0:
@@ -573,7 +576,7 @@ def build_units(cand_off, tile_c, cand_bp=None, triples=None):
             seen, c = set(), 0
             while j + c < n and c < tile_c:
                 x = b[j + c]
-                if c + 1 + len(seen) + (x not in seen) > triples:
+                if c + 1 + len(seen) + (x not in seen) > triples or len(seen) + (x not in seen) > max_pairs:
                     break
                 seen.add(x)
                 c += 1
@@ -620,10 +623,13 @@ class DeviceImpressions:
         self.max_history = H
         self.num_pairs = int(imp.cand_news.shape[0])
         self.num_impressions = int(imp.hist_news.shape[0])
+        self._fixed_tile = tile_c is not None
+        self.planned_buckets = None
         if H <= TC_MAX_HISTORY and tile_c is None and num_buckets is not None:
             # tensor-core path: a unit's candidates and its distinct bucket pairs share the 40 operand-row triples
             bp = _host_bucket_pairs(imp.cand_fresh, imp.cand_life, int(num_buckets))
             unit_imp, unit_pair0, unit_count = build_units(imp.cand_off, self.tile_c, bp, TC_TRIPLES)
+            self.planned_buckets = int(num_buckets)
         else:
             unit_imp, unit_pair0, unit_count = build_units(imp.cand_off, self.tile_c)
         self.num_units = int(unit_imp.shape[0])
@@ -648,6 +654,22 @@ class DeviceImpressions:
         self.work_counter = torch.zeros(int(_lib.load().lime_score_scratch_ints(self.num_units)), dtype=torch.int32,
                                         device=device)
         self.upload()
+
+    def replan(self, num_buckets):
+        """Rebuild the unit list for a model with ``num_buckets`` lifetime buckets (the planner packs candidates + distinct
+        bucket pairs into a unit, so the bucketisation must be the model's: a list planned for another bucket count is
+        still scored correctly, but its over-full units all take the exact-kernel fallback)."""
+        if self._fixed_tile or self.max_history > TC_MAX_HISTORY or self.planned_buckets == int(num_buckets) or "cand_off" not in self.host:
+            return
+        bp = _host_bucket_pairs(self.host["cand_fresh"], self.host["cand_life"], int(num_buckets))
+        unit_imp, unit_pair0, unit_count = build_units(self.host["cand_off"], self.tile_c, bp, TC_TRIPLES)
+        self.planned_buckets = int(num_buckets)
+        self.num_units = int(unit_imp.shape[0])
+        for k, v in (("unit_imp", unit_imp), ("unit_pair0", unit_pair0), ("unit_count", unit_count)):
+            self.host[k] = v.astype(np.int32)
+            self.pinned[k] = torch.from_numpy(self.host[k]).pin_memory()
+            self.dev[k] = self.pinned[k].to(self.device, non_blocking=True)
+        self.work_counter = torch.zeros(int(_lib.load().lime_score_scratch_ints(self.num_units)), dtype=torch.int32, device=self.device)
 
     def h2d_bytes(self):
         return int(sum(v.numel() * v.element_size() for v in self.pinned.values()))
