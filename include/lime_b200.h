@@ -257,6 +257,23 @@ typedef struct {
 int64_t lime_sizeof_news_cache(void);
 int64_t lime_sizeof_impressions(void);
 
+/* Histories longer than LIME_TC_MAX_HISTORY slots on the tensor-core kernel (BASELINE.json configs[4]: history 100 / 200).
+ * `imp` is the original set (H = imp->max_history <= 224, its unit list serves the exact-kernel fallback); `chunked` holds the
+ * same impressions cut into `chunks` pieces of Hc = H / chunks <= LIME_TC_MAX_HISTORY slots: pseudo-impression k * num_impressions
+ * + i = slots [k Hc, (k + 1) Hc) of impression i, candidate arrays replicated chunk-major (pair k * num_pairs + p), unit list
+ * planned for the tensor-core kernel.  A pre-pass computes the candidate-aware attention weights over the FULL history
+ * (layers.py:66-81: both softmaxes run over all H slots), the scoring kernel evaluates every chunk with those weights and
+ * writes its partial pooling state (online softmax + GraphSAGE prefix sum), a merge kernel combines the chunks into the
+ * lifetime-weighted score.  If any chunk unit is flagged (remainder bound, fp16 range, operand rows) the exact kernel re-scores
+ * the whole set in the same call.  scratch: lime_score_long_scratch_ints(chunked->num_units, imp->num_units) int32; work:
+ * lime_score_long_work_floats(num_pairs, H, chunks) floats (attention matrix, partial states). */
+int64_t lime_score_long_scratch_ints(int32_t chunked_units, int32_t orig_units);
+int64_t lime_score_long_work_floats(int64_t num_pairs, int32_t max_history, int32_t chunks);
+int lime_score_impressions_long(const LimeNewsCache *cache, const LimeImpressions *imp, const LimeImpressions *chunked,
+                                int32_t chunks, int64_t num_pairs, int32_t num_impressions, int64_t pair_index_base,
+                                int32_t prefix_main, int64_t tail_start, int32_t prefix_tail, float *scores, int32_t *scratch,
+                                float *work, void *stream);
+
 int lime_score_impressions(const LimeNewsCache *cache, const LimeImpressions *imp,
                            int64_t pair_index_base, int32_t prefix_main, int64_t tail_start,
                            int32_t prefix_tail, float *scores, int32_t *scratch,

@@ -69,6 +69,10 @@ PROTOTYPES = {
     "lime_row_absmax": (C.c_int, [P, I64, I64, C.c_int, P, I64, P]),
     "lime_score_impressions": (C.c_int, [C.POINTER(LimeNewsCache), C.POINTER(LimeImpressions), I64, I32,
                                          I64, I32, P, P, P]),
+    "lime_score_long_scratch_ints": (I64, [I32, I32]),
+    "lime_score_long_work_floats": (I64, [I64, I32, I32]),
+    "lime_score_impressions_long": (C.c_int, [C.POINTER(LimeNewsCache), C.POINTER(LimeImpressions), C.POINTER(LimeImpressions), I32, I64,
+                                              I32, I64, I32, I64, I32, P, P, P, P]),
     "lime_split_f16_pairs": (C.c_int, [P, I64, I64, I32, F32, P, P, I64, P]),
     "lime_score_phase_clocks": (C.c_int, [P]),
     "lime_score_smem_bytes": (I64, [I32, I32]),

@@ -568,7 +568,7 @@ extern "C" int lime_score_impressions(const LimeNewsCache *cache, const LimeImpr
                    "lime_score_impressions: prefix_tail %d not in [1, %d]", prefix_tail, H + cache->user_nodes);
     if (imp->num_units <= 0) return 0;
 
-    ScoreArgs a;
+    ScoreArgs a = {};
     a.cache = *cache;
     a.imp = *imp;
     a.pair_index_base = pair_index_base;
@@ -599,4 +599,85 @@ extern "C" int lime_score_impressions(const LimeNewsCache *cache, const LimeImpr
     a.unit_list = scratch + 4;
     a.unit_list_count = scratch + 1;
     return launch_score_exact(a, imp->num_units, st);
+}
+
+// ---- histories longer than the tensor-core kernel's 56 slots (BASELINE.json configs[4]: history 100 / 200) ------------------
+extern "C" int64_t lime_score_long_scratch_ints(int32_t chunked_units, int32_t orig_units) {
+    return lime_score_scratch_ints(chunked_units) + 32 + (int64_t)(orig_units > 0 ? orig_units : 0);
+}
+extern "C" int64_t lime_score_long_work_floats(int64_t num_pairs, int32_t max_history, int32_t chunks) {
+    if (num_pairs <= 0 || chunks <= 0) return 0;
+    return (num_pairs * (int64_t)max_history + 3) / 4 * 4 + 4 * num_pairs * chunks + 2 * num_pairs;
+}
+
+namespace lime {
+namespace {
+__global__ void long_fallback_setup_kernel(const int *fallback_count, int orig_units, int *count_out, int *list_out) {
+    const int n = *fallback_count > 0 ? orig_units : 0;       // any flagged chunk unit: the exact kernel re-scores the whole set
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count_out = n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < orig_units; i += gridDim.x * blockDim.x) list_out[i] = i;
+}
+}  // namespace
+}  // namespace lime
+
+extern "C" int lime_score_impressions_long(const LimeNewsCache *cache, const LimeImpressions *imp, const LimeImpressions *chunked,
+                                           int32_t chunks, int64_t num_pairs, int32_t num_impressions, int64_t pair_index_base, int32_t prefix_main,
+                                           int64_t tail_start, int32_t prefix_tail, float *scores, int32_t *scratch, float *work,
+                                           void *stream) {
+    using namespace lime;
+    LIME_CHECK_ARG(cache && imp && chunked && scores && scratch && work, "lime_score_impressions_long: null argument");
+    const int H = imp->max_history, Hc = chunked->max_history;
+    LIME_CHECK_ARG(chunks >= 2 && Hc >= 1 && Hc <= LIME_TC_MAX_HISTORY && Hc * chunks == H && H <= 224,
+                   "lime_score_impressions_long: history %d is not %d chunks of %d <= %d slots", H, chunks, Hc, LIME_TC_MAX_HISTORY);
+    LIME_CHECK_ARG(prefix_main >= 1 && prefix_main <= H + cache->user_nodes && prefix_tail >= 1 && prefix_tail <= H + cache->user_nodes,
+                   "lime_score_impressions_long: prefix not in [1, %d]", H + cache->user_nodes);
+    LIME_CHECK_ARG(cache->topic_table != nullptr && cache->num_topics >= 1 && cache->cand16 != nullptr && cache->ctab16 != nullptr &&
+                       cache->news_meta != nullptr && cache->hist_vg != nullptr && cache->htab_vg != nullptr && cache->tc_tables_ok != 0 &&
+                       cache->topic_logit_absmax <= 64.0f && g_score_mode != 1,
+                   "lime_score_impressions_long: the cache does not carry the tensor-core operands (use lime_score_impressions)");
+    LIME_CHECK_ARG(chunked->tile_c <= LIME_TC_TILE_C, "lime_score_impressions_long: chunked unit list built for tile %d", chunked->tile_c);
+    if (imp->num_units <= 0 || num_pairs <= 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    float *a_matrix = work;
+    float4 *partial = reinterpret_cast<float4 *>(work + (num_pairs * (int64_t)H + 3) / 4 * 4);
+    float2 *cbw = reinterpret_cast<float2 *>(reinterpret_cast<float *>(partial) + 4 * num_pairs * chunks);
+
+    ScoreArgs o = {};                                   // the original set: attention pre-pass and the exact fallback
+    o.cache = *cache;
+    o.imp = *imp;
+    o.pair_index_base = pair_index_base;
+    o.tail_start = tail_start;
+    o.prefix_main = prefix_main;
+    o.prefix_tail = prefix_tail;
+    o.bucket_scale = (float)((double)cache->num_buckets / 7.0);
+    o.ln_eps = 1e-5f;
+    o.scores = scores;
+    if (int rc = launch_attention_long(o, a_matrix, chunks, Hc, num_pairs, st)) return rc;
+
+    ScoreArgs a = o;                                    // the chunked set on the tensor-core kernel
+    a.imp = *chunked;
+    a.scores = nullptr;
+    a.work_counter = scratch;
+    a.fallback_list = scratch + 4;
+    a.fallback_count = scratch + 1;
+    a.interp_tol = g_score_mode == 2 ? 0.0f : g_score_tol;
+    a.a_matrix = a_matrix;
+    a.partial_out = partial;
+    a.cbw_out = cbw;
+    a.chunk_impressions = num_impressions;
+    a.full_history = H;
+    a.chunk_pairs = num_pairs;
+    if (int rc = launch_score_tc(a, st)) return rc;
+    if (int rc = launch_merge_long(o, partial, cbw, chunks, num_pairs, scores, st)) return rc;
+    // a chunk unit the tensor-core kernel flagged (remainder bound, fp16 range, operand rows): the exact kernel re-scores the
+    // whole original set (device-side decision, normally an empty launch)
+    int32_t *tail = scratch + lime_score_scratch_ints(chunked->num_units);
+    long_fallback_setup_kernel<<<64, 256, 0, st>>>(scratch + 1, imp->num_units, tail, tail + 32);
+    LIME_LAUNCH_CHECK("long_fallback_setup_kernel");
+    o.work_counter = scratch + 2;
+    o.unit_list = tail + 32;
+    o.unit_list_count = tail;
+    o.fallback_list = nullptr;
+    o.fallback_count = nullptr;
+    return launch_score_exact(o, imp->num_units, st);
 }

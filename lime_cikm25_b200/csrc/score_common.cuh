@@ -22,6 +22,16 @@ struct ScoreArgs {
     int *fallback_list;          // score_tc_kernel: where flagged units are appended
     int *fallback_count;
     float interp_tol;            // score_tc_kernel: admissible interpolation error of the gate (<= 0: flag every unit)
+    // Long histories (H > LIME_TC_MAX_HISTORY) on the tensor-core kernel: the history is cut into chunks of `max_history` slots,
+    // every (impression, chunk) is a pseudo-impression (chunk-major: pseudo-impression k * chunk_impressions + i, pairs k *
+    // chunk_pairs + p), the attention weights over the FULL history come from a pre-pass (a_matrix) and the kernel writes the
+    // partial pooling state of its chunk instead of the score.  a_matrix == NULL: ordinary call.
+    const float *a_matrix;       // [chunks * chunk_pairs, max_history]
+    float4 *partial_out;         // [chunks * chunk_pairs]: m, l, acc of the pooling softmax, GraphSAGE prefix sum
+    float2 *cbw_out;             // [chunk_pairs]: cb, lifetime weight (written by chunk 0)
+    int chunk_impressions;       // real impressions
+    int full_history;            // H of the whole history
+    long long chunk_pairs;       // real pairs
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -51,6 +61,8 @@ __device__ __forceinline__ float lifetime_weight(float r, const LimeNewsCache &c
 // host-side launchers (each in its own translation unit)
 int launch_score_exact(const ScoreArgs &a, int grid_limit, cudaStream_t st);
 int launch_score_tc(const ScoreArgs &a, cudaStream_t st);
+int launch_attention_long(const ScoreArgs &orig, float *a_matrix, int chunks, int chunk_slots, long long total_pairs, cudaStream_t st);
+int launch_merge_long(const ScoreArgs &a, const float4 *partial, const float2 *cbw, int chunks, long long total_pairs, float *scores, cudaStream_t st);
 int64_t score_exact_smem(int H, int TC);
 
 }  // namespace lime

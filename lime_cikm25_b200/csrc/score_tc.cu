@@ -116,7 +116,8 @@ constexpr int UB_UMULT = UB_UTOPIC + kUArr;                   // float multiplic
 constexpr int UB_UMP0 = UB_UMULT + kUArr;                     // float multiplicity inside the GraphSAGE prefix (main)
 constexpr int UB_UMP1 = UB_UMP0 + kUArr;                      // ... (tail batch)
 constexpr int UB_UGABS = UB_UMP1 + kUArr;
-constexpr int UB_WROW = UB_UGABS + kUArr;                     // [40] uint2: per operand-row triple, the row of the cand16 tensor map (hi rows; lo rows = + 3) and the destination byte offset inside an image
+constexpr int UB_USLOT = UB_UGABS + kUArr;                    // first history slot of the unique row (long-history mode: index into the attention matrix)
+constexpr int UB_WROW = UB_USLOT + kUArr;                     // [40] uint2: per operand-row triple, the row of the cand16 tensor map (hi rows; lo rows = + 3) and the destination byte offset inside an image
 constexpr int UB_INFO = UB_WROW + kTriples * 8;           // ints: unit, impression, first pair, count, U, unmasked slots, flags, bucket pairs
 constexpr int kUnitBuf = UB_INFO + 32;
 constexpr int OFF_UB = OFF_PART + 2 * kTriples * 16;
@@ -480,7 +481,9 @@ __device__ __forceinline__ void front_history(const ScoreArgs &args, unsigned ch
     const bool isfb = vb && !dupb && (__ffs(mbb) - 1 == lane);
     const unsigned b0 = __ballot_sync(0xffffffffu, isfa), b1 = __ballot_sync(0xffffffffu, isfb);
     const unsigned lt = (1u << lane) - 1u;
-    const int pz0 = args.prefix_main < H ? args.prefix_main : H, pz1 = args.prefix_tail < H ? args.prefix_tail : H;
+    // GraphSAGE prefix inside this history (chunk h0.. of a long history: the part of the prefix that falls into the chunk)
+    const int h0 = args.a_matrix != nullptr ? (imp / args.chunk_impressions) * H : 0;
+    const int pz0 = min(max(args.prefix_main - h0, 0), H), pz1 = min(max(args.prefix_tail - h0, 0), H);
     const unsigned pa0 = prefix_bits(pz0), pb0 = prefix_bits(pz0 - 32), pa1 = prefix_bits(pz1), pb1 = prefix_bits(pz1 - 32);
     int *unews = reinterpret_cast<int *>(ub + UB_UNEWS);
     int *utab = reinterpret_cast<int *>(ub + UB_UTAB);
@@ -490,8 +493,10 @@ __device__ __forceinline__ void front_history(const ScoreArgs &args, unsigned ch
     float *ump0 = reinterpret_cast<float *>(ub + UB_UMP0);
     float *ump1 = reinterpret_cast<float *>(ub + UB_UMP1);
     float *ugabs = reinterpret_cast<float *>(ub + UB_UGABS);
+    int *uslot = reinterpret_cast<int *>(ub + UB_USLOT);
     if (isfa) {
         const int u = __popc(b0 & lt);
+        uslot[u] = lane;
         const int tp = __float_as_int(mta.x);
         unews[u] = na;
         utab[u] = bpa;
@@ -504,6 +509,7 @@ __device__ __forceinline__ void front_history(const ScoreArgs &args, unsigned ch
     }
     if (isfb) {
         const int u = __popc(b0) + __popc(b1 & lt);
+        uslot[u] = lane + 32;
         const int tp = __float_as_int(mtb.x);
         unews[u] = nbn;
         utab[u] = bpb;
@@ -573,7 +579,8 @@ __device__ __forceinline__ void front_cand(const ScoreArgs &args, unsigned char 
             cnews[c] = n;
             ctab[c] = tb;
             cw[c] = lifetime_weight(rem, C);
-            cP[c] = (args.pair_index_base + p >= args.tail_start) ? args.prefix_tail : args.prefix_main;
+            const long long p_real = args.a_matrix != nullptr ? p % args.chunk_pairs : p;       // pairs of a chunk: k * chunk_pairs + p
+            cP[c] = (args.pair_index_base + p_real >= args.tail_start) ? args.prefix_tail : args.prefix_main;
             ctopic[c] = (tp < 0 || tp >= T) ? 0 : tp;
             *reinterpret_cast<float4 *>(cscal + c * 4) = make_float4(m0.w + ct.x, m1.x + ct.y, m1.y + ct.z, m1.z + ct.w);
             if (!(m0.z <= kWAbsMax)) flags |= 4;       // beyond the fp16 operand range: exact kernel
@@ -731,8 +738,18 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const __grid_cons
             issue_w_tile(base, bars, &wmap, wrow, cnt + nbp, 1, warp, lane);
             // ---------------- phase 1: candidate-aware attention weights a[u][c] (layers.py:66-81) ------
             // lanes per candidate = the smallest power of two that covers the U rows with 4 rows per lane
-            attention(C.topic_table, T, U, cnt, info[UI_NUN], warp, lane, U <= 8 ? 1 : (U <= 16 ? 2 : (U <= 32 ? 3 : 4)), ctopic, utopic,
-                      umask, umult, t_s);
+            if (args.a_matrix != nullptr) {
+                // long-history mode: the weights over the FULL history were computed by the pre-pass; a unique row takes the
+                // weight of its first slot (duplicates share topic and mask, hence the weight)
+                const int *uslot = reinterpret_cast<const int *>(ub + UB_USLOT);
+                for (int idx = tid; idx < cnt * U; idx += kCompute) {
+                    const int c = idx / U, u = idx - c * U;
+                    t_s[u * kAS + c] = __ldg(args.a_matrix + ((long long)pair0 + c) * H + uslot[u]);
+                }
+            } else {
+                attention(C.topic_table, T, U, cnt, info[UI_NUN], warp, lane, U <= 8 ? 1 : (U <= 16 ? 2 : (U <= 32 ? 3 : 4)), ctopic, utopic,
+                          umask, umult, t_s);
+            }
             bar_compute();
             LIME_TICK(2);
 
@@ -1040,7 +1057,13 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const __grid_cons
                 pool_s[c * 4 + 2] = a2;
                 pool_s[c * 4 + 3] = s2;
                 const int P = cP[c];
-                if (P <= H) args.scores[(long long)pair0 + c] = (s2 / (float)P + cscal[c * 4 + 3] + a2 / l) * cw[c];
+                if (args.a_matrix != nullptr) {
+                    // long-history mode: the chunk's partial pooling state; lime_score_impressions_long merges the chunks
+                    args.partial_out[(long long)pair0 + c] = make_float4(m, l, a2, s2);
+                    if ((long long)pair0 < args.chunk_pairs) args.cbw_out[(long long)pair0 + c] = make_float2(cscal[c * 4 + 3], cw[c]);
+                } else if (P <= H) {
+                    args.scores[(long long)pair0 + c] = (s2 / (float)P + cscal[c * 4 + 3] + a2 / l) * cw[c];
+                }
             }
             LIME_TICK(7);
         }
@@ -1052,12 +1075,13 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const __grid_cons
         }
 
         // ---------------- P > H: user-node rows take part in the GraphSAGE mean (userEncoders.py:121,153) -------
-        if (args.prefix_main > H || args.prefix_tail > H) {
+        const int Hfull = args.a_matrix != nullptr ? args.full_history : H;
+        if ((args.prefix_main > Hfull || args.prefix_tail > Hfull) && (args.a_matrix == nullptr || (long long)pair0 < args.chunk_pairs)) {
             if (warp < kCWarps) {
                 for (int c = warp; c < cnt; c += kCWarps) {
                     const int P = cP[c];
-                    if (P > H) {
-                        int jn = P - H - 1;
+                    if (P > Hfull) {
+                        int jn = P - Hfull - 1;
                         jn = jn < C.user_nodes ? jn : C.user_nodes - 1;
                         const float *uu = C.un_prefix + (size_t)jn * kD;
                         const float *hr2 = C.hist_rows + (size_t)cnews[c] * LIME_HIST_LD + LIME_HIST_VC;
@@ -1066,8 +1090,12 @@ __global__ void __launch_bounds__(kThreads, 2) score_tc_kernel(const __grid_cons
                         for (int d = lane; d < kD; d += 32) un = fmaf(hr2[d] + tr2[d], uu[d], un);
                         un = warp_sum(un);
                         if (lane == 0) {
-                            const float bs = (pool_s[c * 4 + 3] + un) / (float)P + cscal[c * 4 + 3] + pool_s[c * 4 + 2] / pool_s[c * 4 + 1];
-                            args.scores[(long long)pair0 + c] = bs * cw[c];
+                            if (args.a_matrix != nullptr) {      // chunk 0 carries the user-node term of the prefix sum
+                                args.partial_out[(long long)pair0 + c].w = pool_s[c * 4 + 3] + un;
+                            } else {
+                                const float bs = (pool_s[c * 4 + 3] + un) / (float)P + cscal[c * 4 + 3] + pool_s[c * 4 + 2] / pool_s[c * 4 + 1];
+                                args.scores[(long long)pair0 + c] = bs * cw[c];
+                            }
                         }
                     }
                 }
@@ -1140,6 +1168,114 @@ __global__ void split_f16_pairs_kernel(const float *__restrict__ src, int64_t ld
 
 }  // namespace
 
+// ---- long histories: attention pre-pass and chunk merge --------------------------------------------------------------
+// Candidate-aware attention weights (layers.py:66-81) over the FULL history of H <= 224 slots, one warp per (impression,
+// candidate) pair, lanes over the slots (7 per lane).  Same arithmetic as attention(): numerators of the head softmaxes
+// from the exponential table, masked slots contribute 0, second softmax unmasked; all slots masked -> uniform.  Output in
+// the chunk-major layout the scoring kernel reads: a[(k * total_pairs + p) * chunk_slots + (h - k * chunk_slots)].
+__global__ void __launch_bounds__(256) attention_long_kernel(const ScoreArgs args, float *__restrict__ a_out, int chunks, int chunk_slots,
+                                                             long long total_pairs) {
+    const LimeNewsCache &C = args.cache;
+    const LimeImpressions &I = args.imp;
+    const int H = I.max_history, T = C.num_topics;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int unit = blockIdx.x;
+    const int imp = I.unit_imp[unit], pair0 = I.unit_pair0[unit], cnt = I.unit_count[unit];
+    constexpr int SPL = 7;                       // slots per lane (H <= 224)
+    int tp[SPL];
+    float w[SPL];
+    int nun = 0;
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) {
+        const int h = lane + 32 * i;
+        tp[i] = 0;
+        w[i] = 0.0f;
+        if (h < H) {
+            int n = I.hist_news[(long long)imp * H + h];
+            n = (n < 0 || n >= C.news_num) ? 0 : n;
+            const int t = __float_as_int(__ldg(C.news_meta + (size_t)n * LIME_META_LD));
+            tp[i] = (t < 0 || t >= T) ? 0 : t;
+            w[i] = I.hist_mask[(long long)imp * H + h] != 0 ? 1.0f : 0.0f;
+            nun += w[i] > 0.0f;
+        }
+    }
+    nun = __reduce_add_sync(0xffffffffu, nun);
+    for (int c = warp; c < cnt; c += 8) {
+        const long long p = (long long)pair0 + c;
+        int n = I.cand_news[p];
+        n = (n < 0 || n >= C.news_num) ? 0 : n;
+        int tc_ = __float_as_int(__ldg(C.news_meta + (size_t)n * LIME_META_LD));
+        tc_ = (tc_ < 0 || tc_ >= T) ? 0 : tc_;
+        const float *trow = C.topic_table + (size_t)tc_ * T * kTabLd;
+        float e2[SPL], s2 = 0.0f;
+        if (nun > 0) {
+            float sum[LIME_CA_HEADS];
+#pragma unroll
+            for (int hd = 0; hd < LIME_CA_HEADS; ++hd) sum[hd] = 0.0f;
+            float4 x[SPL][3];
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) {
+                const float *r0 = trow + (size_t)tp[i] * kTabLd;
+                x[i][0] = ldg4(r0);
+                x[i][1] = ldg4(r0 + 4);
+                x[i][2] = ldg4(r0 + 8);
+                const float xs[LIME_CA_HEADS] = {x[i][0].x, x[i][0].y, x[i][0].z, x[i][0].w, x[i][1].x,
+                                                 x[i][1].y, x[i][1].z, x[i][1].w, x[i][2].x, x[i][2].y};
+#pragma unroll
+                for (int hd = 0; hd < LIME_CA_HEADS; ++hd) sum[hd] = fmaf(w[i], xs[hd], sum[hd]);
+            }
+#pragma unroll
+            for (int hd = 0; hd < LIME_CA_HEADS; ++hd) sum[hd] = __fdividef(1.0f, warp_sum(sum[hd]));
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) {
+                const float xs[LIME_CA_HEADS] = {x[i][0].x, x[i][0].y, x[i][0].z, x[i][0].w, x[i][1].x,
+                                                 x[i][1].y, x[i][1].z, x[i][1].w, x[i][2].x, x[i][2].y};
+                float agg = 0.0f;
+#pragma unroll
+                for (int hd = 0; hd < LIME_CA_HEADS; ++hd) agg = fmaf(xs[hd], sum[hd], agg);
+                agg = w[i] > 0.0f ? agg : 0.0f;
+                e2[i] = lane + 32 * i < H ? ex2_approx(agg * kLog2e) : 0.0f;
+                s2 += e2[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) {
+                e2[i] = lane + 32 * i < H ? 1.0f : 0.0f;
+                s2 += e2[i];
+            }
+        }
+        const float inv2 = __fdividef(1.0f, warp_sum(s2));
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+            const int h = lane + 32 * i;
+            if (h < H) {
+                const int k = h / chunk_slots;
+                a_out[((long long)k * total_pairs + p) * chunk_slots + (h - k * chunk_slots)] = e2[i] * inv2;
+            }
+        }
+    }
+}
+
+// merge of the chunks' partial pooling states (online softmax) + lifetime-weighted click score (util.py:23-49)
+__global__ void __launch_bounds__(256) merge_long_kernel(const ScoreArgs args, const float4 *__restrict__ partial, const float2 *__restrict__ cbw,
+                                                         int chunks, long long total_pairs, float *__restrict__ scores) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total_pairs) return;
+    float m = -INFINITY, l = 0.0f, acc = 0.0f, s2 = 0.0f;
+    for (int k = 0; k < chunks; ++k) {
+        const float4 q = partial[(long long)k * total_pairs + p];
+        const float mn = fmaxf(m, q.x);
+        const float f0 = ex2_approx((m - mn) * kLog2e), f1 = ex2_approx((q.x - mn) * kLog2e);
+        l = fmaf(l, f0, q.y * f1);
+        acc = fmaf(acc, f0, q.z * f1);
+        s2 += q.w;
+        m = mn;
+    }
+    const float2 cw = cbw[p];
+    const int P = (args.pair_index_base + p >= args.tail_start) ? args.prefix_tail : args.prefix_main;
+    scores[p] = (s2 / (float)P + cw.x + acc / l) * cw.y;
+}
+
 // The cand16 tensor map (TMA descriptor) of the candidate operand: encoded on the host by the driver's
 // cuTensorMapEncodeTiled (resolved through the runtime, no link-time dependency on libcuda), cached per (pointer, rows).
 static int cand16_tensor_map(const void *cand16, uint64_t rows, CUtensorMap *out) {
@@ -1188,6 +1324,19 @@ int launch_score_tc(const ScoreArgs &a, cudaStream_t st) {
     if (grid > a.imp.num_units) grid = a.imp.num_units;
     score_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(a, wmap);
     LIME_LAUNCH_CHECK("score_tc_kernel");
+    return 0;
+}
+
+int launch_attention_long(const ScoreArgs &orig, float *a_matrix, int chunks, int chunk_slots, long long total_pairs, cudaStream_t st) {
+    attention_long_kernel<<<orig.imp.num_units, 256, 0, st>>>(orig, a_matrix, chunks, chunk_slots, total_pairs);
+    LIME_LAUNCH_CHECK("attention_long_kernel");
+    return 0;
+}
+
+int launch_merge_long(const ScoreArgs &a, const float4 *partial, const float2 *cbw, int chunks, long long total_pairs, float *scores,
+                      cudaStream_t st) {
+    merge_long_kernel<<<(unsigned)((total_pairs + 255) / 256), 256, 0, st>>>(a, partial, cbw, chunks, total_pairs, scores);
+    LIME_LAUNCH_CHECK("merge_long_kernel");
     return 0;
 }
 

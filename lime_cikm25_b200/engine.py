@@ -445,6 +445,22 @@ class ScoringEngine:
         self._register_topics(category, subCategory, hist, cand)
         return hist, cand
 
+    def _score_long(self, hist_rows, cand_rows, dimp, ch, prefix_main, tail_start, prefix_tail, pair_index_base, out, cand16, meta, hist_vg):
+        """Histories longer than the tensor-core kernel's 56 slots: lime_score_impressions_long on the chunked twin of ``dimp``."""
+        lib = _lib.require_device()
+        cache = self.cache_struct(hist_rows, cand_rows, cand16, meta, hist_vg)
+        self._keepalive = (cand16, meta, hist_vg)
+        if out is None:
+            out = torch.empty(dimp.num_pairs, dtype=torch.float32, device=hist_rows.device)
+        if tail_start is None:
+            tail_start, prefix_tail = 1 << 62, prefix_main
+        check(lib.lime_score_impressions_long(cache, dimp.struct(), ch.struct(), ch.chunks, dimp.num_pairs, dimp.num_impressions,
+                                              int(pair_index_base), int(prefix_main), int(tail_start), int(prefix_tail), out.data_ptr(),
+                                              ch.long_scratch.data_ptr(), ch.long_work.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream), "lime_score_impressions_long")
+        dimp.work_counter[:4].copy_(ch.long_scratch[:4])          # the caller reads the fallback count there
+        return out
+
     def split_candidates(self, cand_rows):
         """cand16 [n + nb*nb, 2400] fp16: the folded candidate vectors as hi/lo pairs, followed by the nb*nb
         bucket-pair rows (ctab16) -- one operand array, so the scoring kernel addresses candidate rows and
@@ -508,6 +524,11 @@ class ScoringEngine:
             hist_vg = interleave_vg(hist_rows)
         if getattr(dimp, "planned_buckets", None) is not None:
             dimp.replan(self.cfg.num_buckets)         # the unit list follows the model's bucketisation
+        if dimp.max_history > TC_MAX_HISTORY and cand16 is not None and ops.score_mode() != ops.SCORE_EXACT:
+            ch = dimp.chunked(self.cfg.num_buckets) if hasattr(dimp, "chunked") else None
+            if ch is not None:
+                return self._score_long(hist_rows, cand_rows, dimp, ch, prefix_main, tail_start, prefix_tail, pair_index_base, out,
+                                        cand16, meta, hist_vg)
         cache = self.cache_struct(hist_rows, cand_rows, cand16, meta, hist_vg)
         self._keepalive = (cand16, meta, hist_vg)      # derived operands stay referenced until the next call (the launch is asynchronous)
         st = dimp.struct()
@@ -670,6 +691,32 @@ class DeviceImpressions:
             self.pinned[k] = torch.from_numpy(self.host[k]).pin_memory()
             self.dev[k] = self.pinned[k].to(self.device, non_blocking=True)
         self.work_counter = torch.zeros(int(_lib.load().lime_score_scratch_ints(self.num_units)), dtype=torch.int32, device=self.device)
+
+    def chunked(self, num_buckets):
+        """The twin of a long-history set (H > 56) for lime_score_impressions_long: every impression cut into K pieces of
+        H / K <= 56 slots (pseudo-impression k * I + i), candidates replicated chunk-major; None if H does not divide."""
+        H = self.max_history
+        if getattr(self, "_chunked", None) is not None and self._chunked.planned_buckets == int(num_buckets):
+            return self._chunked
+        if "cand_off" not in getattr(self, "host", {}) or "cand_remaining" in self.host:
+            return None
+        K = next((k for k in range((H + TC_MAX_HISTORY - 1) // TC_MAX_HISTORY, H + 1) if H % k == 0 and H // k <= TC_MAX_HISTORY), None)
+        if K is None or H // K < 8:
+            return None
+        from .synth import Impressions
+        h, I_, Hc, P = self.host, self.num_impressions, H // K, self.num_pairs
+        cut = lambda a: np.ascontiguousarray(np.transpose(a.reshape(I_, K, Hc), (1, 0, 2)).reshape(K * I_, Hc))
+        off = np.concatenate([h["cand_off"][:-1] + k * P for k in range(K)] + [np.asarray([K * P], np.int64)])
+        imp = Impressions(cut(h["hist_news"]), cut(h["hist_mask"]), cut(h["hist_fresh"]), cut(h["hist_life"]), off,
+                          np.tile(h["cand_news"], K), np.tile(h["cand_fresh"], K), np.tile(h["cand_life"], K),
+                          np.tile(h["labels"], K), np.zeros(K * I_, np.int64))
+        ch = DeviceImpressions(imp, self.device, num_buckets=int(num_buckets))
+        lib = _lib.load()
+        ch.chunks = K
+        ch.long_scratch = torch.zeros(int(lib.lime_score_long_scratch_ints(ch.num_units, self.num_units)), dtype=torch.int32, device=self.device)
+        ch.long_work = torch.empty(int(lib.lime_score_long_work_floats(P, H, K)), dtype=torch.float32, device=self.device)
+        self._chunked = ch
+        return ch
 
     def h2d_bytes(self):
         return int(sum(v.numel() * v.element_size() for v in self.pinned.values()))

@@ -302,12 +302,19 @@ def split_f16_pairs(src, blocks=3, absmax=None, scale=CAND16_SCALE, out=None):
 
 
 SCORE_AUTO, SCORE_EXACT, SCORE_FORCE_FALLBACK = 0, 1, 2
+_score_mode = SCORE_AUTO
 
 
 def score_configure(mode=SCORE_AUTO, tolerance=1e-6):
     """lime_score_configure: 0 = tensor-core scoring with exact fallback (default), 1 = exact kernel
     only, 2 = tensor-core path with every unit forced through the fallback (tests)."""
+    global _score_mode
     check(_lib.load().lime_score_configure(int(mode), float(tolerance)), "lime_score_configure")
+    _score_mode = int(mode)
+
+
+def score_mode():
+    return _score_mode
 
 
 # ---- training kernels (csrc/train_kernels.cu) -------------------------------------------------------

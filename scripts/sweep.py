@@ -53,7 +53,7 @@ def point(name, H=50, cand_fixed=None, cand_mean=37.0, nb=10, news_num=20000, im
     C = np.diff(imp.cand_off).astype(np.float64)
     alg = float(np.sum((H + C) * (400 * 4 + 20) + H + 4 * C))
     out = {"point": name, "history": H, "mean_candidates": float(C.mean()), "num_buckets": nb, "news": news_num,
-           "impressions": impressions, "pairs": int(imp.num_pairs), "kernel": "score_tc" if H <= 56 else "score (exact)",
+           "impressions": impressions, "pairs": int(imp.num_pairs), "kernel": "score_tc" if H <= 56 else ("score_tc, %d chunks" % dimp.chunked(nb).chunks if dimp.chunked(nb) is not None else "score (exact)"),
            "ms_per_launch": ms, "impressions_per_sec": impressions / (ms * 1e-3), "pairs_per_sec": imp.num_pairs / (ms * 1e-3),
            "algorithmic_GBps": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / PEAK,
            "units_sent_to_exact_fallback": fallback, "cache_build_news_per_sec": news_num / cache_s}
@@ -68,7 +68,7 @@ if __name__ == "__main__":
     for C in (5, 20, 100, 300):
         rows.append(point("candidates=%d" % C, cand_fixed=C, impressions=max(2000, 400000 // C)))
     for H in (100, 200):
-        rows.append(point("history=%d" % H, H=H, impressions=1500, steps=2))
+        rows.append(point("history=%d" % H, H=H, impressions=10000))
     for nb in (20, 50):
         rows.append(point("buckets=%d" % nb, nb=nb))
     rows.append(point("Adressa-shaped (full 128-token bodies)", body_full=True, news_num=20000))

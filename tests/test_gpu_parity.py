@@ -509,3 +509,34 @@ def test_tensor_core_scoring_paths(lib):
     sel = np.concatenate([np.arange(imp.cand_off[i], imp.cand_off[i + 1]) for i in users])
     assert torch.equal(s_big[sel], s_big_exact[sel])
     assert np.isfinite(s_big.cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("H,prefix", [(100, 32), (200, 32), (112, 130)])
+def test_long_history_on_the_tensor_core_path(lib, H, prefix):
+    """H > 56 (BASELINE.json configs[4]): the history is cut into chunks of <= 56 slots, the attention weights over the FULL
+    history come from a pre-pass, every chunk runs on the tensor-core kernel and the partial pooling states are merged
+    (lime_score_impressions_long).  Same scores as the exact per-pair kernel, no unit handed to the fallback; ragged histories,
+    a masked tail, multi-unit impressions and a GraphSAGE prefix above H included."""
+    from lime_cikm25_b200 import ops
+    cfg = make_config(vocabulary_size=400, batch_size=128, max_history_num=H, word_embedding_init="skip")
+    model = L.Model(cfg)
+    model.initialize()
+    synth.synthetic_parameters(model, 5)
+    model = model.to(DEV).eval()
+    news = synth.make_news_table(300, vocabulary_size=400, seed=H)
+    imp = synth.make_impressions(40, news.news_num, max_history=H, cand_mean=30.0, near_zero_frac=0.3, seed=H + 1)
+    imp.hist_mask[1, H // 2:] = False
+    imp.hist_mask[2, :] = False
+    with torch.no_grad():
+        cache = util.build_news_cache(model, news)
+        dimp = engine.DeviceImpressions(imp, DEV)
+        got = model.scoring.score(cache.hist_rows, cache.cand_rows, dimp, prefix_main=prefix, cand16=cache.cand16, meta=cache.meta,
+                                  hist_vg=cache.hist_vg).cpu().numpy()
+        assert dimp.chunked(cfg.num_buckets) is not None and int(dimp.work_counter[1]) == 0
+        ops.score_configure(ops.SCORE_EXACT, 1e-6)
+        try:
+            want = model.scoring.score(cache.hist_rows, cache.cand_rows, engine.DeviceImpressions(imp, DEV), prefix_main=prefix,
+                                       cand16=cache.cand16, meta=cache.meta, hist_vg=cache.hist_vg).cpu().numpy()
+        finally:
+            ops.score_configure(ops.SCORE_AUTO, 1e-6)
+    assert rel(got, want) < TOL
