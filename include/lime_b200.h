@@ -103,7 +103,8 @@ int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, int64_t ldw,
 /* fp32 rows -> 16-bit pair hi = r16(scale x), lo = r16(scale x - hi), each [rows, ld16] with columns d..ld16-1 zero; fp16 pairs
  * (as_fp16 != 0: scale x = hi + lo to 2^-22, scale a power of two that keeps hi below 65504) or bf16 pairs (2^-17).
  * With the same split of W, x . W^T ~ xh . Wh^T + xl . Wh^T + xh . Wl^T reproduces the fp32 product on the tensor cores
- * (three lime_linear_bf16_tma passes accumulating in place): the "fp32x3" encoder mode. */
+ * (three lime_linear_bf16_tma passes accumulating in place): the "fp32x3" encoder mode.  lo may be NULL: only the rounded image
+ * hi is written (the operand cast of the bf16 training GEMMs). */
 int lime_split_bf16_pairs(const float *x, int64_t ldx, int64_t rows, int32_t d, void *hi, void *lo, int32_t ld16, float scale,
                           int32_t as_fp16, void *stream);
 /* Small general GEMM with arbitrary strides (weight folding, done once per checkpoint):

@@ -23,8 +23,44 @@ def set_bf16(enabled):
     BF16 = bool(enabled)
 
 
+# In bf16 mode the forward GEMM and dX = dY . W of every nn.Linear run on the TMA-fed tcgen05 kernel of the Stage A cache
+# build (lime_linear_bf16_tma, csrc/gemm_tma.cu: resident W slice, two TMEM accumulators) over bf16 casts of the operands;
+# dW = dY^T . X (contraction over the rows) stays on lime_gemm_bf16.  False: the round-1 kernels (lime_linear_bf16 /
+# lime_gemm_bf16 convert fp32 tiles in their producers).
+TMA = True
+_TMA_K = 512          # contraction length of one lime_linear_bf16_tma pass; longer ones accumulate in place
+
+
+def set_tma(enabled):
+    global TMA
+    TMA = bool(enabled)
+
+
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
+
+
+def _rows_ok(t):
+    return t.dim() == 2 and t.stride(1) == 1 and t.dtype == torch.float32
+
+
+def _linear_tma(a, w, bias, residual, act, out=None):
+    """act(a @ w.T + bias) + residual -> fp32 [m, n] through lime_linear_bf16_tma; a [m, k], w [n, k] fp32 (cast here).
+    Contractions longer than 512 run as accumulating passes (then without activation)."""
+    m, k = a.shape
+    n = w.shape[0]
+    kp = (k + 63) // 64 * 64
+    a16, w16 = ops.cast_bf16(a, kp), ops.cast_bf16(w, kp)
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    if kp <= _TMA_K:
+        return ops.linear_tma(a16, w16, bias, residual=residual, act=act, out=out, n=n, out_bf16=False)
+    assert act == 0
+    for c0 in range(0, kp, _TMA_K):
+        c1 = min(kp, c0 + _TMA_K)
+        ops.linear_tma(a16[:, c0:c1], w16[:, c0:c1], bias if c0 == 0 else None, residual=residual if c0 == 0 else out,
+                       out=out, n=n, out_bf16=False)
+    return out
 
 
 class Linear(torch.autograd.Function):
@@ -34,9 +70,14 @@ class Linear(torch.autograd.Function):
     def forward(ctx, x, w, b, act, residual):
         if act and residual is not None:
             raise ValueError("activation and residual cannot be combined (the activation output is needed)")
-        y = ops.linear(x, w, b, residual=residual, act=act, bf16=BF16)
+        tma = BF16 and TMA and x.shape[0] > 0 and _rows_ok(x) and _rows_ok(w) and (x.shape[1] <= _TMA_K or act == 0)
+        if tma:
+            y = _linear_tma(x, w, b, residual, act)
+        else:
+            y = ops.linear(x, w, b, residual=residual, act=act, bf16=BF16)
         ctx.act = act
         ctx.bf16 = BF16
+        ctx.tma = tma
         ctx.save_for_backward(x, w, y if act else None)
         ctx.has_b, ctx.has_res = b is not None, residual is not None
         return y
@@ -48,7 +89,12 @@ class Linear(torch.autograd.Function):
         dz = ops.act_bwd(dy, y, ctx.act) if ctx.act else dy
         m, k = x.shape
         n = w.shape[0]
-        dx = ops.gemm(dz, True, w, False, m, k, n, bf16=ctx.bf16) if ctx.needs_input_grad[0] else None
+        if not ctx.needs_input_grad[0]:
+            dx = None
+        elif ctx.tma:
+            dx = _linear_tma(dz, w.t().contiguous(), None, None, 0)       # dX = dZ . W: contraction over n
+        else:
+            dx = ops.gemm(dz, True, w, False, m, k, n, bf16=ctx.bf16)
         dw = ops.gemm(dz, False, x, False, n, k, m, bf16=ctx.bf16) if ctx.needs_input_grad[1] else None
         db = ops.col_sum(dz) if ctx.has_b and ctx.needs_input_grad[2] else None
         dres = dy if ctx.has_res and ctx.needs_input_grad[4] else None

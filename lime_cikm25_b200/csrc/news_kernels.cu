@@ -601,12 +601,13 @@ split16_kernel(const float *__restrict__ x, int64_t ldx, int64_t rows, int d, ui
         }
     }
     *reinterpret_cast<uint2 *>(hi + r * ld16 + c) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
-    *reinterpret_cast<uint2 *>(lo + r * ld16 + c) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+    if (lo != nullptr)       // lo == NULL: a plain rounded cast with zero padding (the bf16 training GEMMs)
+        *reinterpret_cast<uint2 *>(lo + r * ld16 + c) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
 }
 
 extern "C" int lime_split_bf16_pairs(const float *x, int64_t ldx, int64_t rows, int32_t d, void *hi, void *lo, int32_t ld16, float scale,
                                      int32_t as_fp16, void *stream) {
-    LIME_CHECK_ARG(x && hi && lo, "lime_split_bf16_pairs: null argument");
+    LIME_CHECK_ARG(x && hi, "lime_split_bf16_pairs: null argument");
     LIME_CHECK_ARG(d >= 1 && ld16 >= d && (ld16 & 7) == 0 && ldx >= d, "lime_split_bf16_pairs: d=%d ld16=%d ldx=%lld", d, ld16, (long long)ldx);
     if (rows <= 0) return 0;
     const int64_t total = rows * (ld16 / 4);

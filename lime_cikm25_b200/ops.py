@@ -107,6 +107,18 @@ def split_bf16(x, kp=None):
     return split16(x, kp, 1.0, fp16=False)
 
 
+def cast_bf16(x, kp=None):
+    """fp32 [rows, d] (row-major view) -> bf16 [rows, kp], round to nearest, columns d..kp-1 zero (kp = d padded to a multiple
+    of 64): the A / W operand of lime_linear_bf16_tma.  lime_split_bf16_pairs with lo = NULL."""
+    lib = _lib.require_device()
+    rows, d = x.shape
+    kp = kp or (d + 63) // 64 * 64
+    hi = torch.empty(rows, kp, dtype=torch.bfloat16, device=x.device)
+    check(lib.lime_split_bf16_pairs(_ptr(x, torch.float32, "x"), _rowmajor(x, "x"), rows, d, hi.data_ptr(), None, kp,
+                                    1.0, 0, _stream()), "lime_split_bf16_pairs")
+    return hi
+
+
 X3_ACT_SCALE, X3_W_SCALE = 16.0, 1024.0      # fp16 pairs of the fp32x3 mode: activations * 2^4, weights * 2^10 (hi < 65504, lo out of the subnormals)
 
 

@@ -11,6 +11,7 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 cfg = default_config(vocabulary_size=40000, batch_size=32, word_embedding_init="skip")
 news = synth.make_news_table(20000, vocabulary_size=40000, seed=1)
 autograd.set_bf16(True)
+autograd.set_tma(os.environ.get("LIME_TRAIN_TMA", "1") != "0")
 torch.manual_seed(0)
 model = L.Model(cfg); model.initialize(); synth.synthetic_parameters(model, seed=0)
 model = model.cuda().train()

@@ -62,8 +62,10 @@ def _grad_worker(rank, world, port, q):
     if rank == 0:
         params[2].grad = torch.ones(3, 3)            # a parameter that got no gradient on rank 1
     nbytes = trainer.allreduce_gradients(params)
-    q.put((rank, params[0].grad.clone(), params[1].grad.clone(),
-           None if params[2].grad is None else params[2].grad.clone(), nbytes))
+    # numpy, not torch tensors: a tensor travels through the queue as a file descriptor served by THIS process, which may have
+    # exited before the parent asks for it (ConnectionResetError)
+    q.put((rank, params[0].grad.numpy().copy(), params[1].grad.numpy().copy(),
+           None if params[2].grad is None else params[2].grad.numpy().copy(), nbytes))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -82,9 +84,9 @@ def test_gradient_allreduce_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, g0, g1, g2, nbytes in out:
-        assert torch.allclose(g0, torch.full((7, 5), 1.5)) and torch.allclose(g1, torch.arange(11.0) * 1.5)
+        assert np.allclose(g0, np.full((7, 5), 1.5)) and np.allclose(g1, np.arange(11.0) * 1.5)
         assert nbytes == (35 + 11 + 9) * 4
-    assert torch.allclose(out[0][3], torch.full((3, 3), 0.5)) and out[1][3] is None
+    assert np.allclose(out[0][3], np.full((3, 3), 0.5)) and out[1][3] is None
 
 
 def test_sharded_metric_reduction_gloo_world2():

@@ -196,6 +196,41 @@ def test_gemm_bf16_all_layouts(lib, ak, bk, m, n, k):
     assert rel(acc.cpu(), want.cpu()) < 5e-5
 
 
+@pytest.mark.parametrize("m,n,k", [(300, 900, 300), (70, 52, 100), (5000, 300, 512), (33, 400, 352), (257, 400, 900), (130, 1200, 352)])
+def test_linear_bf16_tma_path(lib, m, n, k):
+    """bf16 mode of nn.Linear on the TMA-fed tcgen05 kernel (forward and dX = dZ . W; contractions longer than 512 as
+    accumulating passes): equals fp64 products of the bf16-rounded operands up to fp32 accumulation, and the round-1
+    bf16 kernels it replaces."""
+    from lime_cikm25_b200 import autograd as A
+    bf = lambda t: t.detach().to(torch.bfloat16).double().cpu()
+    x, w, b = randn(m, k, seed=1).requires_grad_(), randn(n, k, seed=2, scale=k ** -0.5).requires_grad_(), randn(n, seed=3).requires_grad_()
+    r = randn(m, n, seed=4).requires_grad_()
+    g = randn(m, n, seed=5)
+    try:
+        A.set_bf16(True)
+        for act in ((0, 1) if k <= 512 else (0,)):
+            got = {}
+            for tma in (True, False):
+                A.set_tma(tma)
+                for t in (x, w, b, r):
+                    t.grad = None
+                y = A.linear(x, w, b, act=act, residual=None if act else r)
+                y.backward(g)
+                got[tma] = (y.detach().cpu(), x.grad.cpu(), w.grad.cpu(), b.grad.cpu())
+            z = bf(x) @ bf(w).t() + b.detach().double().cpu()
+            want_y = torch.relu(z) if act else z + r.detach().double().cpu()
+            dz = g.double().cpu() * ((got[True][0].double() > 0).double() if act else 1.0)
+            want_dx = bf(dz) @ bf(w)
+            want_dw = bf(dz).t() @ bf(x)
+            assert rel(got[True][0], want_y) < 5e-5, act
+            assert rel(got[True][1], want_dx) < 5e-5, act
+            assert rel(got[True][2], want_dw) < 5e-5 and rel(got[True][3], dz.sum(0)) < 5e-5, act
+            assert rel(got[True][0], got[False][0]) < 5e-5 and rel(got[True][1], got[False][1]) < 5e-5
+    finally:
+        A.set_bf16(False)
+        A.set_tma(True)
+
+
 def test_training_step_bf16_mode(lib):
     """bf16 mode of the training step: logits and the loss stay close to the fp32 path, gradients agree in
     direction.  16 samples and no lifetime weighting, so that every pair carries gradient (with 4 samples and
