@@ -323,6 +323,12 @@ int lime_gemm(const float *A, int64_t lda, int a_kmajor, const float *B, int64_t
 /* bf16 mode of lime_gemm: operands rounded to bf16, tcgen05 tensor cores, fp32 accumulation in TMEM. */
 int lime_gemm_bf16(const float *A, int64_t lda, int a_kmajor, const float *B, int64_t ldb, int b_kmajor, float *C,
                    int64_t ldc, int64_t m, int n, int64_t k, float alpha, int accumulate, void *stream);
+/* The weight gradient dW = dZ^T . X of an nn.Linear in bf16 mode on bf16 IMAGES of the operands (lime_split_bf16_pairs with
+ * lo = NULL): C[m, n] (+)= alpha * sum_{r < k} A[r, i] * B[r, j], A [k, lda] and B [k, ldb] bf16 row-major over the k token
+ * rows (lda, ldb multiples of 8, 16-byte aligned).  TMA-fed tcgen05 kernel, both operands MN-major, split-K over the rows
+ * with atomicAdd (csrc/gemm_tma.cu).  Replaces lime_gemm_bf16(dY, 0, X, 0) of the round-1 training path. */
+int lime_gemm_bf16_tn_tma(const void *A, int64_t lda, const void *B, int64_t ldb, float *C, int64_t ldc, int32_t m,
+                          int32_t n, int64_t k, float alpha, int32_t accumulate, void *stream);
 /* dx = dy * act'(.) evaluated from the OUTPUT y of the fused activation (1 relu, 2 tanh) */
 int lime_act_bwd(const float *dy, int64_t lddy, const float *y, int64_t ldy, float *dx, int64_t lddx,
                  int64_t rows, int cols, int act, void *stream);

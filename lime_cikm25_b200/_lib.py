@@ -86,6 +86,7 @@ PROTOTYPES = {
     "lime_metrics_reduce": (C.c_int, [P, I64, P, P]),
     "lime_gemm": (C.c_int, [P, I64, C.c_int, P, I64, C.c_int, P, I64, I64, C.c_int, I64, F32, C.c_int, P]),
     "lime_gemm_bf16": (C.c_int, [P, I64, C.c_int, P, I64, C.c_int, P, I64, I64, C.c_int, I64, F32, C.c_int, P]),
+    "lime_gemm_bf16_tn_tma": (C.c_int, [P, I64, P, I64, P, I64, I32, I32, I64, F32, I32, P]),
     "lime_act_bwd": (C.c_int, [P, I64, P, I64, P, I64, I64, C.c_int, C.c_int, P]),
     "lime_col_sum": (C.c_int, [P, I64, I64, C.c_int, P, P]),
     "lime_layernorm_bwd": (C.c_int, [P, I64, P, P, I64, C.c_int, P, I64, P, P, I64, C.c_int, F32, P]),

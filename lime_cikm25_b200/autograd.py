@@ -44,15 +44,12 @@ def _rows_ok(t):
     return t.dim() == 2 and t.stride(1) == 1 and t.dtype == torch.float32
 
 
-def _linear_tma(a, w, bias, residual, act, out=None):
-    """act(a @ w.T + bias) + residual -> fp32 [m, n] through lime_linear_bf16_tma; a [m, k], w [n, k] fp32 (cast here).
-    Contractions longer than 512 run as accumulating passes (then without activation)."""
-    m, k = a.shape
-    n = w.shape[0]
-    kp = (k + 63) // 64 * 64
-    a16, w16 = ops.cast_bf16(a, kp), ops.cast_bf16(w, kp)
+def _linear_tma(a16, w16, n, bias, residual, act, out=None):
+    """act(a @ w.T + bias) + residual -> fp32 [m, n] through lime_linear_bf16_tma on bf16 images a16 [m, kp], w16 [n, kp]
+    (ops.cast_bf16).  Contractions longer than 512 run as accumulating passes (then without activation)."""
+    m, kp = a16.shape
     if out is None:
-        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+        out = torch.empty((m, n), dtype=torch.float32, device=a16.device)
     if kp <= _TMA_K:
         return ops.linear_tma(a16, w16, bias, residual=residual, act=act, out=out, n=n, out_bf16=False)
     assert act == 0
@@ -72,13 +69,15 @@ class Linear(torch.autograd.Function):
             raise ValueError("activation and residual cannot be combined (the activation output is needed)")
         tma = BF16 and TMA and x.shape[0] > 0 and _rows_ok(x) and _rows_ok(w) and (x.shape[1] <= _TMA_K or act == 0)
         if tma:
-            y = _linear_tma(x, w, b, residual, act)
+            x16 = ops.cast_bf16(x)                       # kept for dW = dZ^T X (the fp32 x is not needed again)
+            y = _linear_tma(x16, ops.cast_bf16(w), w.shape[0], b, residual, act)
         else:
             y = ops.linear(x, w, b, residual=residual, act=act, bf16=BF16)
         ctx.act = act
         ctx.bf16 = BF16
         ctx.tma = tma
-        ctx.save_for_backward(x, w, y if act else None)
+        ctx.xshape = tuple(x.shape)
+        ctx.save_for_backward(x16 if tma else x, w, y if act else None)
         ctx.has_b, ctx.has_res = b is not None, residual is not None
         return y
 
@@ -87,15 +86,16 @@ class Linear(torch.autograd.Function):
         x, w, y = ctx.saved_tensors
         dy = _c(dy)
         dz = ops.act_bwd(dy, y, ctx.act) if ctx.act else dy
-        m, k = x.shape
+        m, k = ctx.xshape
         n = w.shape[0]
-        if not ctx.needs_input_grad[0]:
-            dx = None
-        elif ctx.tma:
-            dx = _linear_tma(dz, w.t().contiguous(), None, None, 0)       # dX = dZ . W: contraction over n
+        if ctx.tma:
+            dz16 = ops.cast_bf16(dz)                     # one bf16 image of dZ for both gradients
+            # dX = dZ . W (contraction over n) and dW = dZ^T . X (contraction over the rows, x = the saved bf16 image)
+            dx = _linear_tma(dz16, ops.cast_bf16(w.t().contiguous()), k, None, None, 0) if ctx.needs_input_grad[0] else None
+            dw = ops.gemm_tn_tma(dz16, x, n, k) if ctx.needs_input_grad[1] else None
         else:
-            dx = ops.gemm(dz, True, w, False, m, k, n, bf16=ctx.bf16)
-        dw = ops.gemm(dz, False, x, False, n, k, m, bf16=ctx.bf16) if ctx.needs_input_grad[1] else None
+            dx = ops.gemm(dz, True, w, False, m, k, n, bf16=ctx.bf16) if ctx.needs_input_grad[0] else None
+            dw = ops.gemm(dz, False, x, False, n, k, m, bf16=ctx.bf16) if ctx.needs_input_grad[1] else None
         db = ops.col_sum(dz) if ctx.has_b and ctx.needs_input_grad[2] else None
         dres = dy if ctx.has_res and ctx.needs_input_grad[4] else None
         return dx, dw, db, None, dres

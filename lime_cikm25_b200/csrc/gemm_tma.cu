@@ -353,6 +353,126 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     if (warp == GT_EPI_WARPS + 1) tc::tmem_dealloc(tmem, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient of an nn.Linear in bf16 mode, dW = dZ^T . X (trainer.py:131-146 differentiates newsEncoders.py:244-247):
+//   C[mo, no] (+)= alpha * sum_{r < k} A[r, i] * B[r, j]        A [k, lda], B [k, ldb] bf16, row-major over the TOKENS r
+// Both operands are MN-major for the tensor core (contiguous along the output dimension), so nothing is transposed: a TMA
+// box of 64 columns x 64 token rows with SWIZZLE_128B lands exactly as one 64-wide MN block of the canonical MN-major
+// layout (8 K-rows x 128 B atoms, 16-byte chunk c of K-row r at c ^ (r & 7)); the instruction descriptor's major bits
+// select it.  One CTA = one 128 x bn output tile (bn <= 256, whole 64-column blocks) over one K split; 4-stage TMA ring
+// (<= 48 KB per stage), warp 0 = producer, warp 1 = MMA issue, warps 2-5 = epilogue (atomicAdd when K is split).
+// Replaces gemm_bf16_general_kernel<0, 0> whose producers converted fp32 tiles through registers (50 TFLOP/s).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TN_STAGES = 4, TN_K = 64, TN_M = 128, TN_NMAX = 256;
+constexpr int TN_A_BYTES = TN_M * TN_K * 2, TN_B_BYTES = TN_NMAX * TN_K * 2, TN_STAGE = TN_A_BYTES + TN_B_BYTES;
+constexpr int TN_SMEM = TN_STAGES * TN_STAGE + 256;
+constexpr int TN_THREADS = 192;
+static_assert(TN_SMEM + 1024 <= 232448, "shared memory");
+
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128_tn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(8192 >> 4) << 16;     // leading byte offset: next 64-wide MN block
+    d |= (uint64_t)(1024 >> 4) << 32;     // stride byte offset: next group of 8 K-rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;               // SWIZZLE_128B
+    return d;
+}
+
+__global__ void __launch_bounds__(TN_THREADS, 1)
+gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap, float *__restrict__ C,
+                   int64_t ldc, int mo, int no, int64_t k, int64_t k_per_split, int bn, int n_tiles, float alpha, int accumulate,
+                   uint32_t idesc) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *base = smem_raw;
+    if (threadIdx.x == 0 && (tc::smem_u32(smem_raw) & 1023u) != 0) __trap();
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + TN_STAGES * TN_STAGE);
+    uint64_t *full = bars, *empty = bars + TN_STAGES, *accum = bars + 2 * TN_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TN_STAGES + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = (int)(blockIdx.x / (unsigned)n_tiles) * TN_M;
+    const int col0 = (int)(blockIdx.x % (unsigned)n_tiles) * bn;
+    const int64_t kbeg = (int64_t)blockIdx.y * k_per_split;
+    const int64_t kend = kbeg + k_per_split < k ? kbeg + k_per_split : k;
+    const int kchunks = (int)((kend - kbeg + TN_K - 1) / TN_K);
+    const int nblk = bn / 64;
+
+    if (tid == 0) {
+        for (int s = 0; s < TN_STAGES; ++s) {
+            tc::mbar_init(full + s, 1);
+            tc::mbar_init(empty + s, 1);
+        }
+        tc::mbar_init(accum, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, 256);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kc = 0; kc < kchunks; ++kc) {
+                const int s = kc % TN_STAGES;
+                tc::mbar_wait(empty + s, (((uint32_t)(kc / TN_STAGES)) & 1u) ^ 1u);
+                const uint32_t st = tc::smem_u32(base + s * TN_STAGE);
+                const int kr = (int)(kbeg + (int64_t)kc * TN_K);
+                // rows beyond k (and columns beyond the image) arrive as zeros; a box always counts its full size
+                mbar_expect_tx(full + s, (uint32_t)((2 + nblk) * 8192));
+                tma_load_2d(st, &amap, row0, kr, full + s);
+                tma_load_2d(st + 8192, &amap, row0 + 64, kr, full + s);
+                for (int b = 0; b < nblk; ++b) tma_load_2d(st + TN_A_BYTES + 8192 * b, &bmap, col0 + 64 * b, kr, full + s);
+            }
+        }
+    } else if (warp == 1) {
+        for (int kc = 0; kc < kchunks; ++kc) {
+            const int s = kc % TN_STAGES;
+            tc::mbar_wait(full + s, ((uint32_t)(kc / TN_STAGES)) & 1u);
+            tc::fence_after_sync();
+            if (lane == 0) {
+                const uint32_t st = tc::smem_u32(base + s * TN_STAGE);
+                const uint64_t da = smem_desc_mn_sw128_tn(st), db = smem_desc_mn_sw128_tn(st + TN_A_BYTES);
+                // rows past kend inside the last chunk belong to the next split (or are zeros past k): whole K steps only
+                const int64_t rem = kend - (kbeg + (int64_t)kc * TN_K);
+                const int ksteps = rem >= TN_K ? TN_K / 16 : (int)((rem + 15) / 16);
+                for (int ks = 0; ks < ksteps; ++ks)     // K step of 16 token rows = 2 groups of 8 K-rows = 2048 B
+                    tc::mma_bf16(tmem, da + (uint64_t)(128 * ks), db + (uint64_t)(128 * ks), idesc, (kc | ks) != 0);
+                tc::mma_commit(empty + s);
+                if (kc == kchunks - 1) tc::mma_commit(accum);
+            }
+            __syncwarp();
+        }
+    } else {
+        tc::mbar_wait(accum, 0);
+        tc::fence_after_sync();
+        const int q = warp & 3;                              // the TMEM lane quadrant this warp may read
+        const int r = row0 + 32 * q + lane;
+        const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
+        const bool atomic = gridDim.y > 1;
+        for (int c0 = 0; c0 < bn; c0 += 16) {
+            float v[16];
+            tc::tmem_ld16(tlane + (uint32_t)c0, v);
+            const int c = col0 + c0;
+            if (r >= mo || c >= no) continue;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                if (c + e < no) {
+                    float *o = C + (int64_t)r * ldc + c + e;
+                    const float x = alpha * v[e];
+                    if (atomic) atomicAdd(o, x);
+                    else *o = accumulate ? *o + x : x;
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, 256);
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -436,5 +556,52 @@ extern "C" int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, i
     gemm_tma_kernel<<<groups * n_tiles, GT_THREADS, GT_SMEM, as_stream(stream)>>>(amap, wmap, cmap, rmap, tma_epi ? 1 : 0, ncov, bias, residual, ldr,
                                                                                     C, ldc, c_is_bf16, m, n, nkb, bn, n_tiles, act, alpha, ab_is_fp16);
     LIME_LAUNCH_CHECK("gemm_tma_kernel");
+    return 0;
+}
+
+// dW = dZ^T . X on bf16 images (see gemm_tn_tma_kernel): C[m, n] (+)= alpha * sum_{r < k} A[r, i] * B[r, j]
+extern "C" int lime_gemm_bf16_tn_tma(const void *A, int64_t lda, const void *B, int64_t ldb, float *C, int64_t ldc, int32_t m,
+                                     int32_t n, int64_t k, float alpha, int32_t accumulate, void *stream) {
+    using namespace lime;
+    LIME_CHECK_ARG(A && B && C && m > 0 && n > 0 && k > 0, "lime_gemm_bf16_tn_tma: bad argument");
+    LIME_CHECK_ARG(lda >= m && ldb >= n && lda % 8 == 0 && ldb % 8 == 0 && ldc >= n, "lime_gemm_bf16_tn_tma: bad leading dimensions (lda %lld ldb %lld ldc %lld)",
+                   (long long)lda, (long long)ldb, (long long)ldc);
+    LIME_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "lime_gemm_bf16_tn_tma: operands must be 16-byte aligned");
+    LIME_CHECK_ARG(k < ((int64_t)1 << 31), "lime_gemm_bf16_tn_tma: k too large");
+    cudaStream_t st = as_stream(stream);
+    const int ntiles0 = (n + TN_NMAX - 1) / TN_NMAX;
+    int bn = (((n + ntiles0 - 1) / ntiles0) + 63) / 64 * 64;
+    if (bn > TN_NMAX) bn = TN_NMAX;
+    const int n_tiles = (n + bn - 1) / bn;
+    const int m_tiles = (m + TN_M - 1) / TN_M;
+    const int64_t tiles = (int64_t)m_tiles * n_tiles;
+    // one CTA per SM: split K until the grid covers the GPU about twice (tail balance), at least 512 token rows per split
+    int64_t splits = 1;
+    const int64_t target = 2LL * num_sms();
+    if (tiles < target && k >= 1024) {
+        splits = (target + tiles - 1) / tiles;
+        const int64_t max_splits = k / 512;
+        if (splits > max_splits) splits = max_splits;
+        if (splits > 65535) splits = 65535;
+        if (splits < 1) splits = 1;
+    }
+    int64_t kps = (k + splits - 1) / splits;
+    kps = (kps + TN_K - 1) / TN_K * TN_K;
+    splits = (k + kps - 1) / kps;
+    if (splits > 1 && !accumulate) {
+        if (ldc == n) {
+            LIME_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)m * n, st));
+        } else {
+            LIME_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * n, (size_t)m, st));
+        }
+    }
+    CUtensorMap amap, bmap;
+    if (int rc = tensor_map_2d(&amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, (uint64_t)lda, (uint64_t)k, (uint64_t)lda, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = tensor_map_2d(&bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, (uint64_t)ldb, (uint64_t)k, (uint64_t)ldb, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    const uint32_t idesc = tc::idesc_bf16_f32(TN_M, bn) | (1u << 15) | (1u << 16);       // both operands MN-major
+    LIME_CUDA(cudaFuncSetAttribute(gemm_tn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
+    dim3 grid((unsigned)tiles, (unsigned)splits);
+    gemm_tn_tma_kernel<<<grid, TN_THREADS, TN_SMEM, st>>>(amap, bmap, C, ldc, m, n, k, kps, bn, n_tiles, alpha, accumulate, idesc);
+    LIME_LAUNCH_CHECK("gemm_tn_tma_kernel");
     return 0;
 }

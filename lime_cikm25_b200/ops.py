@@ -342,6 +342,20 @@ def gemm(a, a_kmajor, b, b_kmajor, m, n, k, out=None, alpha=1.0, accumulate=Fals
     return out
 
 
+def gemm_tn_tma(a16, b16, m, n, out=None, alpha=1.0, accumulate=False):
+    """out[m, n] (+)= alpha * a16[:, :m].T @ b16[:, :n] over the rows (lime_gemm_bf16_tn_tma): the weight gradient
+    dW = dZ^T X on bf16 images [rows, ld] of dZ and X (cast_bf16)."""
+    lib = _lib.require_device()
+    if a16.dtype != torch.bfloat16 or b16.dtype != torch.bfloat16 or a16.shape[0] != b16.shape[0]:
+        raise TypeError("a16 / b16 must be bfloat16 images over the same rows")
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a16.device)
+    check(lib.lime_gemm_bf16_tn_tma(a16.data_ptr(), _rowmajor(a16, "a16"), b16.data_ptr(), _rowmajor(b16, "b16"),
+                                    _ptr(out, torch.float32, "out"), _rowmajor(out, "out"), m, n, a16.shape[0], float(alpha),
+                                    int(bool(accumulate)), _stream()), "lime_gemm_bf16_tn_tma")
+    return out
+
+
 def act_bwd(dy, y, act, out=None):
     lib = _lib.require_device()
     if out is None:

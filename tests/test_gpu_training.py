@@ -231,6 +231,21 @@ def test_linear_bf16_tma_path(lib, m, n, k):
         A.set_tma(True)
 
 
+@pytest.mark.parametrize("rows,m,n", [(70, 52, 100), (1000, 900, 300), (20000, 300, 512), (4133, 130, 52)])
+def test_gemm_tn_tma(lib, rows, m, n):
+    """dW = dZ^T X on bf16 images (TMA-fed tcgen05 kernel, MN-major operands, split-K with atomics): fp64 product of the
+    bf16-rounded operands up to fp32 accumulation; alpha and accumulate."""
+    a, b = randn(rows, m, seed=1), randn(rows, n, seed=2)
+    a16, b16 = ops.cast_bf16(a), ops.cast_bf16(b)
+    assert a16.shape[1] % 64 == 0 and torch.equal(a16[:, :m].float(), a.to(torch.bfloat16).float()) and float(a16[:, m:].abs().sum()) == 0
+    want = 0.5 * (a.to(torch.bfloat16).double().t() @ b.to(torch.bfloat16).double()).cpu()
+    got = ops.gemm_tn_tma(a16, b16, m, n, alpha=0.5)
+    assert rel(got.cpu(), want) < 5e-5
+    acc = torch.ones(m, n, device=DEV)
+    ops.gemm_tn_tma(a16, b16, m, n, out=acc, alpha=0.5, accumulate=True)
+    assert rel(acc.cpu(), want + 1.0) < 5e-5
+
+
 def test_training_step_bf16_mode(lib):
     """bf16 mode of the training step: logits and the loss stay close to the fp32 path, gradients agree in
     direction.  16 samples and no lifetime weighting, so that every pair carries gradient (with 4 samples and
