@@ -302,7 +302,7 @@ def train_report(args, cfg, news, dev, rank, world, bf16=False):
     ms = float(t.item())
     news_per_step = B * (H + 5)
     autograd.set_bf16(False)
-    return {"metric": "train_samples_per_sec", "gemm_mode": "bf16 tcgen05 (fp32 accumulate, fp32 master weights)" if bf16 else "fp32 FFMA", "value": B * world / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+    return {"metric": "train_samples_per_sec", "gemm_mode": "bf16: TMA + tcgen05 GEMMs for forward / dX / dW on bf16 operand images, mma.sync attention forward + backward (fp32 accumulate, fp32 master weights and activations)" if bf16 else "fp32 FFMA", "value": B * world / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
             "batch_per_gpu": B, "history": H, "candidates": 5, "dtype": "bf16" if bf16 else "f32", "dropout_rate": float(cfg.dropout_rate),
             "news_encodes_per_step_per_gpu": news_per_step, "loss": float(loss),
             "tflops": 3 * 241.3e6 * news_per_step / (ms * 1e-3) / 1e12,

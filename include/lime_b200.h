@@ -348,6 +348,14 @@ int lime_scatter_add_rows(const float *src, int64_t lds, const int32_t *ids, int
 int lime_mha_bwd(const float *qkv, const float *dctx, float *dqkv, int64_t n_news, int T, int d, int nhead,
                  float p_drop, uint64_t seed, int64_t news0,
                  void *stream);
+/* bf16 mode of lime_mha for the training layout (fp32 qkv / ctx, same dropout mask): S = Q K^T and O = (P M) V on the
+ * tensor cores (mma.sync m16n8k16), softmax in fp32 on the accumulator fragments. */
+int lime_mha_fwd_bf16(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, float p_drop, uint64_t seed,
+                      int64_t news0, void *stream);
+/* bf16 mode of lime_mha_bwd: q, k, v, dO rounded to bf16, every product of the backward on the tensor cores (mma.sync
+ * m16n8k16, fp32 accumulation), softmax statistics in fp32; same arguments and dropout mask. */
+int lime_mha_bwd_bf16(const float *qkv, const float *dctx, float *dqkv, int64_t n_news, int T, int d, int nhead,
+                      float p_drop, uint64_t seed, int64_t news0, void *stream);
 /* backward of lime_intent_pool: dout [n, D] -> dpre, de [n, k, D], dw2 [D] (accumulated) */
 int lime_intent_pool_bwd(const float *pre, const float *e, const float *w2, const float *dout, int64_t lddo,
                          float *dpre, float *de, float *dw2, int64_t n, int k, int D, void *stream);

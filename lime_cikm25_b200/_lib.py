@@ -93,6 +93,8 @@ PROTOTYPES = {
     "lime_gather_rows": (C.c_int, [P, I64, I64, P, I64, C.c_int, P, I64, P]),
     "lime_scatter_add_rows": (C.c_int, [P, I64, P, I64, C.c_int, P, I64, I64, P]),
     "lime_mha_bwd": (C.c_int, [P, P, P, I64, C.c_int, C.c_int, C.c_int, F32, C.c_uint64, I64, P]),
+    "lime_mha_fwd_bf16": (C.c_int, [P, P, I64, C.c_int, C.c_int, C.c_int, F32, C.c_uint64, I64, P]),
+    "lime_mha_bwd_bf16": (C.c_int, [P, P, P, I64, C.c_int, C.c_int, C.c_int, F32, C.c_uint64, I64, P]),
     "lime_intent_pool_bwd": (C.c_int, [P, P, P, P, I64, P, P, P, I64, C.c_int, C.c_int, P]),
     "lime_content_fuse_bwd": (C.c_int, [P, P, P, I64, I64, C.c_int, P, P, P]),
     "lime_dropout": (C.c_int, [P, I64, P, I64, I64, C.c_int, F32, C.c_uint64, P]),

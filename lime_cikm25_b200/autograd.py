@@ -181,7 +181,8 @@ class MHA(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, n, T, d, heads, p_drop=0.0, seed=0):
         out = torch.empty((qkv.shape[0], d), dtype=torch.float32, device=qkv.device)
-        ops.mha(qkv, out, n, T, d, heads, p_drop, seed)
+        ctx.bf16 = BF16 and TMA                  # bf16 mode: forward and backward on the tensor cores (lime_mha_{fwd,bwd}_bf16)
+        ops.mha(qkv, out, n, T, d, heads, p_drop, seed, bf16=ctx.bf16)
         ctx.dims = (n, T, d, heads, float(p_drop), int(seed))
         ctx.save_for_backward(qkv)
         return out
@@ -190,7 +191,7 @@ class MHA(torch.autograd.Function):
     def backward(ctx, dctx):
         (qkv,) = ctx.saved_tensors
         n, T, d, heads, p_drop, seed = ctx.dims
-        return ops.mha_bwd(qkv, _c(dctx), n, T, d, heads, p_drop, seed), None, None, None, None, None, None
+        return ops.mha_bwd(qkv, _c(dctx), n, T, d, heads, p_drop, seed, bf16=ctx.bf16), None, None, None, None, None, None
 
 
 class IntentPool(torch.autograd.Function):

@@ -309,6 +309,322 @@ mha_tc_kernel(const __nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restrict__
     }
 }
 
+
+// ---- backward of the attention core on the tensor cores (bf16 mode of the training step, trainer.py:131-146 through
+// newsEncoders.py:244-247) ----------------------------------------------------------------------------------------------
+// One CTA = one (news, head), T / 32 warps; fp32 q | k | v and dO head slices are rounded to bf16 tiles [T][40] on the way
+// into shared memory.  Phase 1, warp w = query rows 32 w .. 32 w + 31 in two 16-row blocks: S = Q K^T and dP = dO V^T by
+// mma.m16n8k16 with the whole key range in registers, softmax and rowdot = sum_j P dP on the accumulator fragments, the
+// attention-weight dropout mask of the forward re-evaluated per element (O = (P * M) V: dP <- M * dP, dV uses P * M),
+// dS = P (dP - rowdot) re-used in place as the A fragments of dQ = scale dS K; P * M and dS also go to shared memory as
+// bf16 [T][T + 8].  Phase 2, warp w = key rows 32 w ..: dK = scale dS^T Q and dV = (P M)^T dO with the A fragments read
+// through ldmatrix.trans.  Replaces mha_bwd_kernel<T> (FFMA, 7.5 ms of a 25 ms training step) in bf16 mode.
+template <int T>
+__global__ void __launch_bounds__(T)
+mha_bwd_tc_kernel(const float *__restrict__ qkv, const float *__restrict__ dctx, float *__restrict__ dqkv, int d, int nhead,
+                  int hd, float scale, float p_drop, uint64_t seed, int64_t news0) {
+    constexpr int P = 40;                       // pitch of the Q K V dO tiles (bf16 elements): 80 bytes, ldmatrix conflict-free
+    constexpr int PS = T + 8;                   // pitch of the P / dS tiles: (T + 8) * 2 bytes = an odd number of 16-byte chunks
+    constexpr int NT = T / 8;
+    extern __shared__ __align__(16) unsigned char mhab_smem[];
+    typedef __nv_bfloat16 Row[P];
+    typedef __nv_bfloat16 RowS[PS];
+    Row *Qs = reinterpret_cast<Row *>(mhab_smem), *Ks = Qs + T, *Vs = Ks + T, *Os = Vs + T;
+    RowS *Ps = reinterpret_cast<RowS *>(Os + T), *Ds = Ps + T;
+    const int64_t news = blockIdx.y;
+    const int head = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t2 = 2 * (lane & 3);
+    const int64_t ld = 3 * (int64_t)d;
+    const float *base = qkv + news * T * ld;
+    for (int idx = tid; idx < T * 32; idx += T) {
+        const int r = idx >> 5, e = idx & 31;
+        const bool ok = e < hd;
+        Qs[r][e] = __float2bfloat16_rn(ok ? base[r * ld + head * hd + e] : 0.0f);
+        Ks[r][e] = __float2bfloat16_rn(ok ? base[r * ld + d + head * hd + e] : 0.0f);
+        Vs[r][e] = __float2bfloat16_rn(ok ? base[r * ld + 2 * d + head * hd + e] : 0.0f);
+        Os[r][e] = __float2bfloat16_rn(ok ? dctx[(news * T + r) * (int64_t)d + head * hd + e] : 0.0f);
+    }
+    __syncthreads();
+    const uint64_t drop_nh = ((uint64_t)(news0 + news) * nhead + head) * T;
+    const float sl2 = scale * 1.4426950408889634f;
+    float *out = dqkv + news * T * ld + head * hd;
+
+    // ---------------- phase 1: query rows ----------------
+#pragma unroll 1
+    for (int mb = 0; mb < 2; ++mb) {
+        const int r0 = 32 * warp + 16 * mb;
+        uint32_t qa[2][4], oa[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            ldsm_x4(qa[ks], &Qs[r0 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * ks + 8 * (lane >> 4)]);
+            ldsm_x4(oa[ks], &Os[r0 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * ks + 8 * (lane >> 4)]);
+        }
+        float sacc[NT][4], pacc[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.0f;
+            pacc[j][0] = pacc[j][1] = pacc[j][2] = pacc[j][3] = 0.0f;
+            uint32_t kb[4], vb[4];
+            ldsm_x4(kb, &Ks[8 * j + (lane & 7)][8 * (lane >> 3)]);
+            ldsm_x4(vb, &Vs[8 * j + (lane & 7)][8 * (lane >> 3)]);
+            mma_bf16_16816(sacc[j], qa[0], kb[0], kb[1]);
+            mma_bf16_16816(sacc[j], qa[1], kb[2], kb[3]);
+            mma_bf16_16816(pacc[j], oa[0], vb[0], vb[1]);
+            mma_bf16_16816(pacc[j], oa[1], vb[2], vb[3]);
+        }
+        // softmax over the keys: rows g (c0, c1) and g + 8 (c2, c3)
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            m0 = fmaxf(m0, fmaxf(sacc[j][0], sacc[j][1]));
+            m1 = fmaxf(m1, fmaxf(sacc[j][2], sacc[j][3]));
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float l0 = 0.0f, l1 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            sacc[j][0] = exp2f((sacc[j][0] - m0) * sl2);
+            sacc[j][1] = exp2f((sacc[j][1] - m0) * sl2);
+            sacc[j][2] = exp2f((sacc[j][2] - m1) * sl2);
+            sacc[j][3] = exp2f((sacc[j][3] - m1) * sl2);
+            l0 += sacc[j][0] + sacc[j][1];
+            l1 += sacc[j][2] + sacc[j][3];
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        const int ra = r0 + g, rb = ra + 8;
+        float rd0 = 0.0f, rd1 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int c = 8 * j + t2;
+            float ms[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+            if (p_drop > 0.0f) {
+                ms[0] = drop_scale(seed, (drop_nh + ra) * T + c, p_drop);
+                ms[1] = drop_scale(seed, (drop_nh + ra) * T + c + 1, p_drop);
+                ms[2] = drop_scale(seed, (drop_nh + rb) * T + c, p_drop);
+                ms[3] = drop_scale(seed, (drop_nh + rb) * T + c + 1, p_drop);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                sacc[j][e] *= e < 2 ? i0 : i1;           // P
+                pacc[j][e] *= ms[e];                     // M * dP
+            }
+            rd0 = fmaf(sacc[j][0], pacc[j][0], fmaf(sacc[j][1], pacc[j][1], rd0));
+            rd1 = fmaf(sacc[j][2], pacc[j][2], fmaf(sacc[j][3], pacc[j][3], rd1));
+            *reinterpret_cast<uint32_t *>(&Ps[ra][c]) = pack2_bf16(sacc[j][0] * ms[0], sacc[j][1] * ms[1]);
+            *reinterpret_cast<uint32_t *>(&Ps[rb][c]) = pack2_bf16(sacc[j][2] * ms[2], sacc[j][3] * ms[3]);
+        }
+        rd0 += __shfl_xor_sync(0xffffffffu, rd0, 1);
+        rd0 += __shfl_xor_sync(0xffffffffu, rd0, 2);
+        rd1 += __shfl_xor_sync(0xffffffffu, rd1, 1);
+        rd1 += __shfl_xor_sync(0xffffffffu, rd1, 2);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int c = 8 * j + t2;
+            sacc[j][0] *= pacc[j][0] - rd0;              // dS = P (M dP - rowdot)
+            sacc[j][1] *= pacc[j][1] - rd0;
+            sacc[j][2] *= pacc[j][2] - rd1;
+            sacc[j][3] *= pacc[j][3] - rd1;
+            *reinterpret_cast<uint32_t *>(&Ds[ra][c]) = pack2_bf16(sacc[j][0], sacc[j][1]);
+            *reinterpret_cast<uint32_t *>(&Ds[rb][c]) = pack2_bf16(sacc[j][2], sacc[j][3]);
+        }
+        // dQ = scale dS K  (16 x 32 per block): dS accumulator fragments as A, K through ldmatrix.trans
+        float qacc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) qacc[j][0] = qacc[j][1] = qacc[j][2] = qacc[j][3] = 0.0f;
+#pragma unroll
+        for (int kk = 0; kk < T / 16; ++kk) {
+            uint32_t da[4];
+            da[0] = pack2_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
+            da[1] = pack2_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
+            da[2] = pack2_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+            da[3] = pack2_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
+#pragma unroll
+            for (int jp = 0; jp < 2; ++jp) {
+                uint32_t kb[4];
+                ldsm_x4_trans(kb, &Ks[16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
+                mma_bf16_16816(qacc[2 * jp], da, kb[0], kb[1]);
+                mma_bf16_16816(qacc[2 * jp + 1], da, kb[2], kb[3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = 8 * j + t2;
+            if (c < hd) {
+                out[ra * ld + c] = qacc[j][0] * scale;
+                out[rb * ld + c] = qacc[j][2] * scale;
+            }
+            if (c + 1 < hd) {
+                out[ra * ld + c + 1] = qacc[j][1] * scale;
+                out[rb * ld + c + 1] = qacc[j][3] * scale;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: key rows ----------------
+#pragma unroll 1
+    for (int mb = 0; mb < 2; ++mb) {
+        const int j0 = 32 * warp + 16 * mb;
+        float kacc[4][4], vacc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            kacc[j][0] = kacc[j][1] = kacc[j][2] = kacc[j][3] = 0.0f;
+            vacc[j][0] = vacc[j][1] = vacc[j][2] = vacc[j][3] = 0.0f;
+        }
+#pragma unroll 2
+        for (int kk = 0; kk < T / 16; ++kk) {
+            // A (m = key j, k = query i) = the transpose of the stored [i][j] tiles
+            uint32_t dsa[4], pma[4];
+            ldsm_x4_trans(dsa, &Ds[16 * kk + (lane & 7) + 8 * (lane >> 4)][j0 + 8 * ((lane >> 3) & 1)]);
+            ldsm_x4_trans(pma, &Ps[16 * kk + (lane & 7) + 8 * (lane >> 4)][j0 + 8 * ((lane >> 3) & 1)]);
+#pragma unroll
+            for (int jp = 0; jp < 2; ++jp) {
+                uint32_t qb[4], ob[4];
+                ldsm_x4_trans(qb, &Qs[16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
+                ldsm_x4_trans(ob, &Os[16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
+                mma_bf16_16816(kacc[2 * jp], dsa, qb[0], qb[1]);
+                mma_bf16_16816(kacc[2 * jp + 1], dsa, qb[2], qb[3]);
+                mma_bf16_16816(vacc[2 * jp], pma, ob[0], ob[1]);
+                mma_bf16_16816(vacc[2 * jp + 1], pma, ob[2], ob[3]);
+            }
+        }
+        const int ra = j0 + g, rb = ra + 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = 8 * j + t2;
+            if (c < hd) {
+                out[ra * ld + d + c] = kacc[j][0] * scale;
+                out[rb * ld + d + c] = kacc[j][2] * scale;
+                out[ra * ld + 2 * d + c] = vacc[j][0];
+                out[rb * ld + 2 * d + c] = vacc[j][2];
+            }
+            if (c + 1 < hd) {
+                out[ra * ld + d + c + 1] = kacc[j][1] * scale;
+                out[rb * ld + d + c + 1] = kacc[j][3] * scale;
+                out[ra * ld + 2 * d + c + 1] = vacc[j][1];
+                out[rb * ld + 2 * d + c + 1] = vacc[j][3];
+            }
+        }
+    }
+}
+
+
+// Forward of the same core for the TRAINING layout (fp32 q | k | v rows of width 3 d, fp32 ctx, attention-weight dropout):
+// one CTA per (news, head), warp w = query rows 32 w .., S = Q K^T, softmax, P * M, O = (P M) V on mma.m16n8k16.
+// bf16 mode of lime_mha (mha_kernel<T> stays the fp32 parity path).
+template <int T>
+__global__ void __launch_bounds__(T)
+mha_fwd_tc_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int nhead, int hd, float scale, float p_drop,
+                  uint64_t seed, int64_t news0) {
+    constexpr int P = 40;
+    constexpr int NT = T / 8;
+    __shared__ __align__(16) __nv_bfloat16 Qs[T][P], Ks[T][P], Vs[T][P];
+    const int64_t news = blockIdx.y;
+    const int head = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t2 = 2 * (lane & 3);
+    const int64_t ld = 3 * (int64_t)d;
+    const float *base = qkv + news * T * ld;
+    for (int idx = tid; idx < T * 32; idx += T) {
+        const int r = idx >> 5, e = idx & 31;
+        const bool ok = e < hd;
+        Qs[r][e] = __float2bfloat16_rn(ok ? base[r * ld + head * hd + e] : 0.0f);
+        Ks[r][e] = __float2bfloat16_rn(ok ? base[r * ld + d + head * hd + e] : 0.0f);
+        Vs[r][e] = __float2bfloat16_rn(ok ? base[r * ld + 2 * d + head * hd + e] : 0.0f);
+    }
+    __syncthreads();
+    const uint64_t drop_nh = ((uint64_t)(news0 + news) * nhead + head) * T;
+    const float sl2 = scale * 1.4426950408889634f;
+#pragma unroll 1
+    for (int mb = 0; mb < 2; ++mb) {
+        const int r0 = 32 * warp + 16 * mb;
+        uint32_t qa[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ldsm_x4(qa[ks], &Qs[r0 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * ks + 8 * (lane >> 4)]);
+        float sacc[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.0f;
+            uint32_t kb[4];
+            ldsm_x4(kb, &Ks[8 * j + (lane & 7)][8 * (lane >> 3)]);
+            mma_bf16_16816(sacc[j], qa[0], kb[0], kb[1]);
+            mma_bf16_16816(sacc[j], qa[1], kb[2], kb[3]);
+        }
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            m0 = fmaxf(m0, fmaxf(sacc[j][0], sacc[j][1]));
+            m1 = fmaxf(m1, fmaxf(sacc[j][2], sacc[j][3]));
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float l0 = 0.0f, l1 = 0.0f;
+        const int ra = r0 + g, rb = ra + 8;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            sacc[j][0] = exp2f((sacc[j][0] - m0) * sl2);
+            sacc[j][1] = exp2f((sacc[j][1] - m0) * sl2);
+            sacc[j][2] = exp2f((sacc[j][2] - m1) * sl2);
+            sacc[j][3] = exp2f((sacc[j][3] - m1) * sl2);
+            l0 += sacc[j][0] + sacc[j][1];
+            l1 += sacc[j][2] + sacc[j][3];
+            if (p_drop > 0.0f) {                             // the sums are taken BEFORE the mask: O = (softmax * M) V
+                const int c = 8 * j + t2;
+                sacc[j][0] *= drop_scale(seed, (drop_nh + ra) * T + c, p_drop);
+                sacc[j][1] *= drop_scale(seed, (drop_nh + ra) * T + c + 1, p_drop);
+                sacc[j][2] *= drop_scale(seed, (drop_nh + rb) * T + c, p_drop);
+                sacc[j][3] *= drop_scale(seed, (drop_nh + rb) * T + c + 1, p_drop);
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        float oacc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.0f;
+#pragma unroll
+        for (int kk = 0; kk < T / 16; ++kk) {
+            uint32_t pa[4];
+            pa[0] = pack2_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
+            pa[1] = pack2_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
+            pa[2] = pack2_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+            pa[3] = pack2_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
+#pragma unroll
+            for (int jp = 0; jp < 2; ++jp) {
+                uint32_t vb[4];
+                ldsm_x4_trans(vb, &Vs[16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
+                mma_bf16_16816(oacc[2 * jp], pa, vb[0], vb[1]);
+                mma_bf16_16816(oacc[2 * jp + 1], pa, vb[2], vb[3]);
+            }
+        }
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        float *o0 = ctx + (news * T + ra) * (int64_t)d + head * hd, *o1 = o0 + 8 * (int64_t)d;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = 8 * j + t2;
+            if (c < hd) {
+                o0[c] = oacc[j][0] * i0;
+                o1[c] = oacc[j][2] * i1;
+            }
+            if (c + 1 < hd) {
+                o0[c + 1] = oacc[j][1] * i0;
+                o1[c + 1] = oacc[j][3] * i1;
+            }
+        }
+    }
+}
+
 // ---- LayerNorm (two-pass, like ATen) ------------------------------------------------------------
 constexpr int kLnMaxPerLane = 16;   // d <= 512
 
@@ -755,5 +1071,42 @@ extern "C" int lime_row_absmax(const float *M, int64_t ld, int64_t rows, int col
     if (rows <= 0) return 0;
     row_absmax_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, as_stream(stream)>>>(M, ld, rows, cols, out, ldo);
     LIME_LAUNCH_CHECK("row_absmax_kernel");
+    return 0;
+}
+
+// bf16-mode backward of lime_mha on the tensor cores (same arguments as lime_mha_bwd, train_kernels.cu)
+extern "C" int lime_mha_bwd_bf16(const float *qkv, const float *dctx, float *dqkv, int64_t n_news, int T, int d, int nhead,
+                                 float p_drop, uint64_t seed, int64_t news0, void *stream) {
+    LIME_CHECK_ARG(qkv && dctx && dqkv, "lime_mha_bwd_bf16: null argument");
+    LIME_CHECK_ARG((T == 32 || T == 128) && d % nhead == 0 && d / nhead <= 32, "lime_mha_bwd_bf16: unsupported shape T=%d d=%d heads=%d", T, d, nhead);
+    if (n_news <= 0) return 0;
+    LIME_CHECK_ARG(n_news <= 65535, "lime_mha_bwd_bf16: at most 65535 news per call");
+    const int hd = d / nhead;
+    const float scale = 1.0f / sqrtf((float)hd);
+    dim3 grid(nhead, (unsigned)n_news);
+    const size_t smem = 2 * (4 * (size_t)T * 40 + 2 * (size_t)T * (T + 8));
+    if (T == 32) {
+        mha_bwd_tc_kernel<32><<<grid, 32, smem, as_stream(stream)>>>(qkv, dctx, dqkv, d, nhead, hd, scale, p_drop, seed, news0);
+    } else {
+        LIME_CUDA(cudaFuncSetAttribute(mha_bwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mha_bwd_tc_kernel<128><<<grid, 128, smem, as_stream(stream)>>>(qkv, dctx, dqkv, d, nhead, hd, scale, p_drop, seed, news0);
+    }
+    LIME_LAUNCH_CHECK("mha_bwd_tc_kernel");
+    return 0;
+}
+
+// bf16-mode forward of lime_mha for the training layout (fp32 in / out, dropout on the attention weights)
+extern "C" int lime_mha_fwd_bf16(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, float p_drop, uint64_t seed,
+                                 int64_t news0, void *stream) {
+    LIME_CHECK_ARG(qkv && ctx, "lime_mha_fwd_bf16: null argument");
+    LIME_CHECK_ARG((T == 32 || T == 128) && d % nhead == 0 && d / nhead <= 32, "lime_mha_fwd_bf16: unsupported shape T=%d d=%d heads=%d", T, d, nhead);
+    if (n_news <= 0) return 0;
+    LIME_CHECK_ARG(n_news <= 65535, "lime_mha_fwd_bf16: at most 65535 news per call");
+    const int hd = d / nhead;
+    const float scale = 1.0f / sqrtf((float)hd);
+    dim3 grid(nhead, (unsigned)n_news);
+    if (T == 32) mha_fwd_tc_kernel<32><<<grid, 32, 0, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale, p_drop, seed, news0);
+    else mha_fwd_tc_kernel<128><<<grid, 128, 0, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale, p_drop, seed, news0);
+    LIME_LAUNCH_CHECK("mha_fwd_tc_kernel");
     return 0;
 }

@@ -185,11 +185,13 @@ def embed_pe(E, ids, T, pe, out):
     return out
 
 
-def mha(qkv, ctx, n_news, T, d, nhead, p_drop=0.0, seed=0):
+def mha(qkv, ctx, n_news, T, d, nhead, p_drop=0.0, seed=0, bf16=False):
+    """attention core; bf16: lime_mha_fwd_bf16 (tensor cores, q k v and P rounded to bf16), the training step's bf16 mode"""
     lib = _lib.require_device()
+    fn = lib.lime_mha_fwd_bf16 if bf16 else lib.lime_mha
     for lo in range(0, n_news, 65535):
         hi = min(n_news, lo + 65535)
-        check(lib.lime_mha(qkv[lo * T:].data_ptr(), ctx[lo * T:].data_ptr(), hi - lo, T, d, nhead, float(p_drop),
+        check(fn(qkv[lo * T:].data_ptr(), ctx[lo * T:].data_ptr(), hi - lo, T, d, nhead, float(p_drop),
                            int(seed) & (2 ** 64 - 1), lo, _stream()), "lime_mha")
     return ctx
 
@@ -408,12 +410,14 @@ def scatter_add_rows(src, ids, dtable):
     return dtable
 
 
-def mha_bwd(qkv, dctx, n_news, T, d, nhead, p_drop=0.0, seed=0):
+def mha_bwd(qkv, dctx, n_news, T, d, nhead, p_drop=0.0, seed=0, bf16=False):
+    """backward of mha; bf16: lime_mha_bwd_bf16 (tensor cores, operands rounded to bf16), the training step's bf16 mode"""
     lib = _lib.require_device()
     dqkv = torch.empty_like(qkv)
+    fn = lib.lime_mha_bwd_bf16 if bf16 else lib.lime_mha_bwd
     for lo in range(0, n_news, 65535):
         hi = min(n_news, lo + 65535)
-        check(lib.lime_mha_bwd(qkv[lo * T:].data_ptr(), dctx[lo * T:].data_ptr(), dqkv[lo * T:].data_ptr(), hi - lo, T, d,
+        check(fn(qkv[lo * T:].data_ptr(), dctx[lo * T:].data_ptr(), dqkv[lo * T:].data_ptr(), hi - lo, T, d,
                                nhead, float(p_drop), int(seed) & (2 ** 64 - 1), lo, _stream()), "lime_mha_bwd")
     return dqkv
 

@@ -246,6 +246,27 @@ def test_gemm_tn_tma(lib, rows, m, n):
     assert rel(acc.cpu(), want + 1.0) < 5e-5
 
 
+@pytest.mark.parametrize("T,p", [(32, 0.0), (128, 0.0), (128, 0.25), (32, 0.25)])
+def test_mha_backward_bf16_tensor_cores(lib, T, p):
+    """bf16-mode backward of the attention core (mma.sync kernel: S, dP, dQ, dK, dV on the tensor cores, the forward's
+    dropout mask re-evaluated) against the fp32 FFMA backward it replaces: bf16 rounding of q, k, v, dO, P and dS only."""
+    n, d, heads = 7, 300, 10
+    qkv = randn(n * T, 3 * d, seed=11, scale=0.8)
+    dctx = randn(n * T, d, seed=12)
+    o32, o16 = torch.empty(n * T, d, device=DEV), torch.empty(n * T, d, device=DEV)
+    ops.mha(qkv, o32, n, T, d, heads, p, 1234)
+    ops.mha(qkv, o16, n, T, d, heads, p, 1234, bf16=True)
+    assert float((o16 - o32).norm() / o32.norm()) < 1e-2 and rel(o16.cpu(), o32.cpu()) < 0.5 and float((o16 - o32).abs().max()) > 0
+    want = ops.mha_bwd(qkv, dctx, n, T, d, heads, p, 1234)
+    got = ops.mha_bwd(qkv, dctx, n, T, d, heads, p, 1234, bf16=True)
+    for i, name in enumerate("qkv"):
+        a, b = got[:, i * d:(i + 1) * d].double().cpu(), want[:, i * d:(i + 1) * d].double().cpu()
+        err = float((a - b).norm() / b.norm())
+        assert err < 1.5e-2, (name, err)
+        assert rel(a, b) < 0.5, name                    # no single element off (a wrong fragment mapping is O(10) in this measure: the floor is 0.1 rms)
+    assert float((got - want).abs().max()) > 0
+
+
 def test_training_step_bf16_mode(lib):
     """bf16 mode of the training step: logits and the loss stay close to the fp32 path, gradients agree in
     direction.  16 samples and no lifetime weighting, so that every pair carries gradient (with 4 samples and
