@@ -107,6 +107,11 @@ int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, int64_t ldw,
  * hi is written (the operand cast of the bf16 training GEMMs). */
 int lime_split_bf16_pairs(const float *x, int64_t ldx, int64_t rows, int32_t d, void *hi, void *lo, int32_t ld16, float scale,
                           int32_t as_fp16, void *stream);
+/* bf16 image of x (as lime_split_bf16_pairs with lo = NULL, scale 1) AND colsum[c] += sum_r x[r, c] in the same pass: the operand
+ * cast of dZ and the bias gradient of an nn.Linear backward in bf16 training mode.  d, ldx multiples of 4, ld16 a multiple of 8
+ * (<= 1024), x and colsum 16-byte aligned; colsum [d] is accumulated (zero it first). */
+int lime_cast_bf16_colsum(const float *x, int64_t ldx, int64_t rows, int32_t d, void *out16, int32_t ld16, float *colsum,
+                          void *stream);
 /* Small general GEMM with arbitrary strides (weight folding, done once per checkpoint):
  * C[i*ldc + j] = alpha * sum_k A[i*sam + k*sak] * B[k*sbk + j*sbn]                                */
 int lime_gemm_strided(const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbk,
@@ -344,6 +349,11 @@ int lime_gather_rows(const float *table, int64_t ldt, int64_t table_rows, const 
                      float *out, int64_t ldo, void *stream);
 int lime_scatter_add_rows(const float *src, int64_t lds, const int32_t *ids, int64_t n, int d, float *dtable,
                           int64_t ldt, int64_t table_rows, void *stream);
+/* the same accumulation for large id lists with hot rows (word-embedding gradient): sorted_ids ascending, perm[k] = the row of
+ * src that belongs to sorted position k (torch.sort of the ids); runs of equal ids are summed in registers, one 128-bit
+ * reduction per run and 32-position chunk.  d <= 512, d / lds / ldt multiples of 4, 16-byte aligned bases. */
+int lime_scatter_add_rows_sorted(const float *src, int64_t lds, const int32_t *sorted_ids, const int64_t *perm, int64_t n,
+                                 int d, float *dtable, int64_t ldt, int64_t table_rows, void *stream);
 /* backward of lime_mha: dctx [n_news*T, d] -> dqkv [n_news*T, 3d] */
 int lime_mha_bwd(const float *qkv, const float *dctx, float *dqkv, int64_t n_news, int T, int d, int nhead,
                  float p_drop, uint64_t seed, int64_t news0,

@@ -53,6 +53,7 @@ PROTOTYPES = {
     "lime_gemm_strided": (C.c_int, [P, I64, I64, P, I64, I64, P, I64, C.c_int, C.c_int, C.c_int, F32, P]),
     "lime_linear_bf16_tma": (C.c_int, [P, I64, P, I64, P, P, I64, P, I64, I32, I64, I32, I32, I32, F32, I32, P]),
     "lime_split_bf16_pairs": (C.c_int, [P, I64, I64, I32, P, P, I32, F32, I32, P]),
+    "lime_cast_bf16_colsum": (C.c_int, [P, I64, I64, I32, P, I32, P, P]),
     "lime_embed_pe_bf16": (C.c_int, [P, I64, P, I64, C.c_int, C.c_int, P, P, P, I32, P]),
     "lime_mha_bf16": (C.c_int, [P, I64, P, I64, I64, C.c_int, C.c_int, C.c_int, P]),
     "lime_layernorm_bf16": (C.c_int, [P, I64, P, P, P, I64, P, I32, I64, C.c_int, F32, P]),
@@ -92,6 +93,7 @@ PROTOTYPES = {
     "lime_layernorm_bwd": (C.c_int, [P, I64, P, P, I64, C.c_int, P, I64, P, P, I64, C.c_int, F32, P]),
     "lime_gather_rows": (C.c_int, [P, I64, I64, P, I64, C.c_int, P, I64, P]),
     "lime_scatter_add_rows": (C.c_int, [P, I64, P, I64, C.c_int, P, I64, I64, P]),
+    "lime_scatter_add_rows_sorted": (C.c_int, [P, I64, P, P, I64, C.c_int, P, I64, I64, P]),
     "lime_mha_bwd": (C.c_int, [P, P, P, I64, C.c_int, C.c_int, C.c_int, F32, C.c_uint64, I64, P]),
     "lime_mha_fwd_bf16": (C.c_int, [P, P, I64, C.c_int, C.c_int, C.c_int, F32, C.c_uint64, I64, P]),
     "lime_mha_bwd_bf16": (C.c_int, [P, P, P, I64, C.c_int, C.c_int, C.c_int, F32, C.c_uint64, I64, P]),

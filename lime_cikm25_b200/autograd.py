@@ -88,15 +88,21 @@ class Linear(torch.autograd.Function):
         dz = ops.act_bwd(dy, y, ctx.act) if ctx.act else dy
         m, k = ctx.xshape
         n = w.shape[0]
+        db = None
         if ctx.tma:
-            dz16 = ops.cast_bf16(dz)                     # one bf16 image of dZ for both gradients
+            # one bf16 image of dZ for both gradients; the bias gradient comes out of the same pass over dZ
+            if ctx.has_b and ctx.needs_input_grad[2]:
+                dz16, db = ops.cast_bf16_colsum(dz)
+            else:
+                dz16 = ops.cast_bf16(dz)
             # dX = dZ . W (contraction over n) and dW = dZ^T . X (contraction over the rows, x = the saved bf16 image)
             dx = _linear_tma(dz16, ops.cast_bf16(w.t().contiguous()), k, None, None, 0) if ctx.needs_input_grad[0] else None
             dw = ops.gemm_tn_tma(dz16, x, n, k) if ctx.needs_input_grad[1] else None
         else:
             dx = ops.gemm(dz, True, w, False, m, k, n, bf16=ctx.bf16) if ctx.needs_input_grad[0] else None
             dw = ops.gemm(dz, False, x, False, n, k, m, bf16=ctx.bf16) if ctx.needs_input_grad[1] else None
-        db = ops.col_sum(dz) if ctx.has_b and ctx.needs_input_grad[2] else None
+        if db is None and ctx.has_b and ctx.needs_input_grad[2]:
+            db = ops.col_sum(dz)
         dres = dy if ctx.has_res and ctx.needs_input_grad[4] else None
         return dx, dw, db, None, dres
 

@@ -921,6 +921,31 @@ split16_kernel(const float *__restrict__ x, int64_t ldx, int64_t rows, int d, ui
         *reinterpret_cast<uint2 *>(lo + r * ld16 + c) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
 }
 
+
+// fp32 rows -> bf16 image (zero padded to ld16 columns) AND the column sums of the fp32 rows in the same pass: the operand
+// cast of dZ for dX / dW and the bias gradient db = sum_r dZ[r, :] of an nn.Linear backward (bf16 training mode) read dZ once.
+// Block = 256 rows; thread = (column quad, row phase); colsum is ACCUMULATED (one 128-bit reduction per thread).
+__global__ void __launch_bounds__(256)
+cast_bf16_colsum_kernel(const float *__restrict__ x, int64_t ldx, int64_t rows, int d, uint16_t *__restrict__ out16, int ld16,
+                        float *__restrict__ colsum) {
+    const int q4 = ld16 >> 2;                          // column quads per row (<= 256)
+    const int rpp = 256 / q4;                          // rows per pass
+    const int c4 = threadIdx.x % q4, rsub = threadIdx.x / q4;
+    if (rsub >= rpp) return;
+    const int c = 4 * c4;
+    const int64_t r0 = (int64_t)blockIdx.x * 256, r1 = r0 + 256 < rows ? r0 + 256 : rows;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = r0 + rsub; r < r1; r += rpp) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < d) v = *reinterpret_cast<const float4 *>(x + r * ldx + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2 *>(out16 + r * ld16 + c) = make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+    }
+    if (c < d)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum + c), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+}
+
 extern "C" int lime_split_bf16_pairs(const float *x, int64_t ldx, int64_t rows, int32_t d, void *hi, void *lo, int32_t ld16, float scale,
                                      int32_t as_fp16, void *stream) {
     LIME_CHECK_ARG(x && hi, "lime_split_bf16_pairs: null argument");
@@ -1108,5 +1133,17 @@ extern "C" int lime_mha_fwd_bf16(const float *qkv, float *ctx, int64_t n_news, i
     if (T == 32) mha_fwd_tc_kernel<32><<<grid, 32, 0, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale, p_drop, seed, news0);
     else mha_fwd_tc_kernel<128><<<grid, 128, 0, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale, p_drop, seed, news0);
     LIME_LAUNCH_CHECK("mha_fwd_tc_kernel");
+    return 0;
+}
+
+extern "C" int lime_cast_bf16_colsum(const float *x, int64_t ldx, int64_t rows, int32_t d, void *out16, int32_t ld16, float *colsum,
+                                     void *stream) {
+    LIME_CHECK_ARG(x && out16 && colsum, "lime_cast_bf16_colsum: null argument");
+    LIME_CHECK_ARG(d >= 4 && (d & 3) == 0 && ld16 >= d && (ld16 & 7) == 0 && ld16 <= 1024 && (ldx & 3) == 0 && ldx >= d &&
+                       (((uintptr_t)x | (uintptr_t)colsum) & 15) == 0 && ((uintptr_t)out16 & 7) == 0,
+                   "lime_cast_bf16_colsum: d=%d ld16=%d ldx=%lld (multiples of 4 / 8, ld16 <= 1024, 16-byte aligned)", d, ld16, (long long)ldx);
+    if (rows <= 0) return 0;
+    cast_bf16_colsum_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, as_stream(stream)>>>(x, ldx, rows, d, reinterpret_cast<uint16_t *>(out16), ld16, colsum);
+    LIME_LAUNCH_CHECK("cast_bf16_colsum_kernel");
     return 0;
 }

@@ -262,6 +262,61 @@ __global__ void scatter_add_rows4_kernel(const float *__restrict__ src, int64_t 
                  : "memory");
 }
 
+
+// The same scatter for LARGE id lists with hot rows (the word-embedding gradient: 281,600 token rows per step over a
+// Zipf-distributed vocabulary plus the pad id -- unsorted, the reductions of a hot row serialise in L2).  The caller sorts the
+// ids (sorted_ids, perm = the source row of every sorted position); a warp walks 32 consecutive sorted positions, keeps the
+// running sum of a run of equal ids in registers (lanes = 128-bit column groups) and issues one red.v4 per run and chunk.
+__global__ void __launch_bounds__(256)
+scatter_add_rows_sorted_kernel(const float *__restrict__ src, int64_t lds, const int32_t *__restrict__ sorted_ids,
+                               const int64_t *__restrict__ perm, int64_t n, int d4, float *__restrict__ dtable, int64_t ldt,
+                               int64_t nrows_table) {
+    const int lane = threadIdx.x & 31;
+    const int64_t k0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+    if (k0 >= n) return;
+    const int cnt = (int)((n - k0) < 32 ? (n - k0) : 32);
+    int64_t my_id = 0, my_row = 0;
+    if (lane < cnt) {
+        my_id = sorted_ids[k0 + lane];
+        my_id = (my_id < 0 || my_id >= nrows_table) ? 0 : my_id;
+        my_row = perm[k0 + lane];
+    }
+    constexpr int G = 4;                           // column groups per lane: d <= 512
+    float4 acc[G];
+#pragma unroll
+    for (int gI = 0; gI < G; ++gI) acc[gI] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t cur = __shfl_sync(0xffffffffu, my_id, 0);
+    auto flush = [&](int64_t id) {
+#pragma unroll
+        for (int gI = 0; gI < G; ++gI) {
+            const int c4 = lane + 32 * gI;
+            if (c4 < d4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dtable + id * ldt + 4 * c4), "f"(acc[gI].x),
+                             "f"(acc[gI].y), "f"(acc[gI].z), "f"(acc[gI].w)
+                             : "memory");
+            acc[gI] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+#pragma unroll 4
+    for (int i = 0; i < cnt; ++i) {
+        const int64_t id = __shfl_sync(0xffffffffu, my_id, i);
+        const int64_t row = __shfl_sync(0xffffffffu, my_row, i);
+        if (id != cur) {                            // warp-uniform
+            flush(cur);
+            cur = id;
+        }
+#pragma unroll
+        for (int gI = 0; gI < G; ++gI) {
+            const int c4 = lane + 32 * gI;
+            if (c4 < d4) {
+                const float4 v = *reinterpret_cast<const float4 *>(src + row * lds + 4 * c4);
+                acc[gI].x += v.x; acc[gI].y += v.y; acc[gI].z += v.z; acc[gI].w += v.w;
+            }
+        }
+    }
+    flush(cur);
+}
+
 // =================================================================================================
 // Self-attention core backward (nn.MultiheadAttention without mask): one CTA per (news, head), one thread per
 // token.  Nothing of size T x T is stored: thread i first derives the softmax statistics of query row i
@@ -603,6 +658,21 @@ extern "C" int lime_scatter_add_rows(const float *src, int64_t lds, const int32_
     scatter_add_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(src, lds, ids, n, d, dtable, ldt,
                                                                                          table_rows);
     LIME_LAUNCH_CHECK("scatter_add_rows_kernel");
+    return 0;
+}
+
+
+extern "C" int lime_scatter_add_rows_sorted(const float *src, int64_t lds, const int32_t *sorted_ids, const int64_t *perm, int64_t n,
+                                            int d, float *dtable, int64_t ldt, int64_t table_rows, void *stream) {
+    LIME_CHECK_ARG(src && sorted_ids && perm && dtable && d > 0 && table_rows > 0, "lime_scatter_add_rows_sorted: bad argument");
+    LIME_CHECK_ARG((d & 3) == 0 && d <= 512 && (lds & 3) == 0 && (ldt & 3) == 0 && (((uintptr_t)src | (uintptr_t)dtable) & 15) == 0,
+                   "lime_scatter_add_rows_sorted: d=%d, lds=%lld, ldt=%lld must be multiples of 4 (d <= 512), 16-byte aligned bases", d,
+                   (long long)lds, (long long)ldt);
+    if (n <= 0) return 0;
+    const int64_t warps = (n + 31) / 32;
+    scatter_add_rows_sorted_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, as_stream(stream)>>>(src, lds, sorted_ids, perm, n, d / 4, dtable,
+                                                                                             ldt, table_rows);
+    LIME_LAUNCH_CHECK("scatter_add_rows_sorted_kernel");
     return 0;
 }
 

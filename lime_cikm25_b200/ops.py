@@ -122,6 +122,21 @@ def cast_bf16(x, kp=None):
 X3_ACT_SCALE, X3_W_SCALE = 16.0, 1024.0      # fp16 pairs of the fp32x3 mode: activations * 2^4, weights * 2^10 (hi < 65504, lo out of the subnormals)
 
 
+def cast_bf16_colsum(x, kp=None):
+    """(bf16 image [rows, kp] of x, column sums [d] of x) in one pass over x (lime_cast_bf16_colsum); falls back to cast_bf16 +
+    col_sum for shapes the fused kernel does not take."""
+    lib = _lib.require_device()
+    rows, d = x.shape
+    kp = kp or (d + 63) // 64 * 64
+    if d % 4 or kp > 1024 or x.stride(0) % 4 or x.data_ptr() % 16 or rows == 0:
+        return cast_bf16(x, kp), col_sum(x)
+    out16 = torch.empty(rows, kp, dtype=torch.bfloat16, device=x.device)
+    cs = torch.zeros(d, dtype=torch.float32, device=x.device)
+    check(lib.lime_cast_bf16_colsum(_ptr(x, torch.float32, "x"), _rowmajor(x, "x"), rows, d, out16.data_ptr(), kp,
+                                    _ptr(cs, torch.float32, "colsum"), _stream()), "lime_cast_bf16_colsum")
+    return out16, cs
+
+
 def linear_x3(xh, xl, wh, wl, bias=None, residual=None, act=ACT_NONE, out=None, n=None, alpha=1.0):
     """fp32-accurate dense layer on the tensor cores: out = act(alpha x . w^T + bias) + residual with x = xh + xl, w = wh + wl as
     16-bit pairs (fp16: 2^-21 per product; alpha undoes their power-of-two scaling), three accumulating lime_linear_bf16_tma
@@ -401,8 +416,22 @@ def gather_rows(table, ids, out=None):
     return out
 
 
+SCATTER_SORT_MIN = 8192      # id lists at least this long are sorted first (hot rows: pad id, frequent words)
+
+
 def scatter_add_rows(src, ids, dtable):
+    """dtable[ids[r]] += src[r].  Long id lists (the word-embedding gradient) go through lime_scatter_add_rows_sorted:
+    torch.sort of the ids (plumbing), then runs of equal ids are summed in registers before one vector reduction."""
     lib = _lib.require_device()
+    n, d = ids.numel(), src.shape[1]
+    if (n >= SCATTER_SORT_MIN and d % 4 == 0 and d <= 512 and src.stride(0) % 4 == 0 and dtable.stride(0) % 4 == 0
+            and src.data_ptr() % 16 == 0 and dtable.data_ptr() % 16 == 0):
+        sorted_ids, perm = torch.sort(ids.reshape(-1))
+        check(lib.lime_scatter_add_rows_sorted(_ptr(src, torch.float32, "src"), _rowmajor(src, "src"),
+                                               _ptr(sorted_ids, torch.int32, "ids"), _ptr(perm, torch.int64, "perm"), n, d,
+                                               _ptr(dtable, torch.float32, "dtable"), _rowmajor(dtable, "dtable"),
+                                               dtable.shape[0], _stream()), "lime_scatter_add_rows_sorted")
+        return dtable
     check(lib.lime_scatter_add_rows(_ptr(src, torch.float32, "src"), _rowmajor(src, "src"),
                                     _ptr(ids, torch.int32, "ids"), ids.numel(), src.shape[1],
                                     _ptr(dtable, torch.float32, "dtable"), _rowmajor(dtable, "dtable"),

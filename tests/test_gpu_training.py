@@ -267,6 +267,30 @@ def test_mha_backward_bf16_tensor_cores(lib, T, p):
     assert float((got - want).abs().max()) > 0
 
 
+@pytest.mark.parametrize("n,V,d", [(20000, 500, 300), (9000, 40, 52), (1000, 50, 300), (8200, 3, 400)])
+def test_scatter_add_rows_hot_ids(lib, n, V, d):
+    """Embedding gradient with hot rows (pad id, frequent words): the sorted, run-compressed kernel (long id lists) and the
+    plain vector-reduction kernel against an fp64 index_add; out-of-range ids fall on row 0 in both."""
+    g = gen(n)
+    ids = (torch.rand(n, generator=g) ** 3 * V).to(torch.int32)
+    ids[::5] = 0
+    ids[7], ids[11] = -3, V + 5
+    src = randn(n, d, seed=3)
+    table = torch.ones(V, d, device=DEV)
+    ops.scatter_add_rows(src, ids.to(DEV), table)
+    want = torch.ones(V, d, dtype=torch.float64)
+    want.index_add_(0, ids.clamp(0, V + 100).where((ids >= 0) & (ids < V), torch.zeros_like(ids)).long(), src.double().cpu())
+    assert rel(table.cpu(), want) < 2e-4            # fp32 accumulation of thousands of rows onto the hot ids
+
+
+@pytest.mark.parametrize("rows,d", [(1000, 300), (4133, 900), (70, 52), (513, 512)])
+def test_cast_bf16_colsum(lib, rows, d):
+    x = randn(rows, d, seed=9)
+    x16, cs = ops.cast_bf16_colsum(x)
+    assert torch.equal(x16, ops.cast_bf16(x)) and x16.shape[1] % 64 == 0
+    assert rel(cs.cpu(), x.double().sum(0).cpu()) < 1e-5
+
+
 def test_training_step_bf16_mode(lib):
     """bf16 mode of the training step: logits and the loss stay close to the fp32 path, gradients agree in
     direction.  16 samples and no lifetime weighting, so that every pair carries gradient (with 4 samples and
