@@ -64,8 +64,11 @@ class Trainer:
 
     def __init__(self, model, config, group=None):
         self.model, self.config, self.group = model, config, group
-        self.optimizer = optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=config.lr,
-                                    weight_decay=config.weight_decay)
+        params = [p for p in model.parameters() if p.requires_grad]
+        # the reference's Adam (trainer.py:33); on the device torch's fused implementation of the same update (one multi-tensor
+        # kernel per step instead of a dozen foreach passes over the 18 M parameters)
+        fused = bool(params) and all(p.is_cuda and p.dtype == torch.float32 for p in params)
+        self.optimizer = optim.Adam(params, lr=config.lr, weight_decay=config.weight_decay, **({"fused": True} if fused else {}))
         self.gradient_clip_norm = config.gradient_clip_norm
         # every .grad is a view of ONE flat buffer (zeroed per step instead of zero_grad's set-to-None): autograd accumulates
         # into the views in place, the data-parallel all-reduce runs on the buffer itself
@@ -98,6 +101,12 @@ class Trainer:
         loss.backward()
         self.allreduce_bytes = allreduce_gradients(model.parameters(), self.group, flat=self._flat)
         if self.gradient_clip_norm > 0:
-            nn.utils.clip_grad_norm_(model.parameters(), self.gradient_clip_norm)
+            if self._flat is not None:
+                # clip_grad_norm_ (trainer.py:147) on the flat buffer every .grad is a view of: the global 2-norm is the norm of
+                # the concatenation, the same clamp(max_norm / (norm + 1e-6), max=1) factor -- 2 kernels instead of foreach passes
+                total = torch.linalg.vector_norm(self._flat)
+                self._flat.mul_((self.gradient_clip_norm / (total + 1e-6)).clamp(max=1.0))
+            else:
+                nn.utils.clip_grad_norm_(model.parameters(), self.gradient_clip_norm)
         self.optimizer.step()
         return loss.detach()

@@ -176,6 +176,31 @@ def test_training_step_gradients(lib, bs, B):
     print("training step: %d parameters, worst gradient error %.2e" % (checked, worst))
 
 
+def test_trainer_step_is_the_reference_update(lib):
+    """Trainer.step (flat gradient buffer, clip on the buffer, fused Adam) = the reference's step (trainer.py:131-148):
+    zero_grad, backward, nn.utils.clip_grad_norm_, plain torch.optim.Adam -- same parameters after two steps."""
+    import copy
+    from lime_cikm25_b200.trainer import Trainer, negative_log_softmax
+    cfg, model, _ = _make(41, batch_size=4, use_remaining_lifetime_weighting=False)
+    cfg.gradient_clip_norm = 0.05                                  # small enough for the clip to bite
+    ref = copy.deepcopy(model)
+    news = synth.make_news_table(40, vocabulary_size=cfg.vocabulary_size, seed=4)
+    tb = [torch.as_tensor(x).to(DEV) for x in synth.make_train_batch(news, 4, seed=6)]
+    tr = Trainer(model, cfg)
+    opt = torch.optim.Adam([p for p in ref.parameters() if p.requires_grad], lr=cfg.lr, weight_decay=cfg.weight_decay)
+    for _ in range(2):
+        loss = tr.step(tb)
+        opt.zero_grad()
+        want = negative_log_softmax(ref(*tb, tb[24] - tb[23]))
+        want.backward()
+        norm = torch.nn.utils.clip_grad_norm_(ref.parameters(), cfg.gradient_clip_norm)
+        opt.step()
+        assert float(norm) > cfg.gradient_clip_norm and abs(float(loss) - float(want)) < 1e-5 * abs(float(want)) + 1e-6
+    for (name, p), q in zip(model.named_parameters(), ref.parameters()):
+        assert torch.allclose(p, q, rtol=1e-4, atol=2e-5), name   # split-K atomics: gradients are not bit-reproducible (lr = 1e-4: a wrong update is 1e-4 .. 2e-4)
+    assert any(float(p.grad.abs().max()) > 0 for p in model.parameters() if p.grad is not None)
+
+
 @pytest.mark.parametrize("ak,bk", [(True, True), (True, False), (False, True), (False, False)])
 @pytest.mark.parametrize("m,n,k", [(128, 64, 64), (900, 300, 5000), (5000, 300, 900), (130, 512, 300), (400, 52, 1760)])
 def test_gemm_bf16_all_layouts(lib, ak, bk, m, n, k):
