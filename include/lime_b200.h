@@ -377,6 +377,16 @@ int lime_content_fuse_bwd(const float *title, const float *body, const float *dc
  * on the gradient with the same seed */
 int lime_dropout(const float *x, int64_t ldx, float *y, int64_t ldy, int64_t rows, int cols, float p,
                  uint64_t seed, void *stream);
+/* fused forms with the SAME masks: y = x * m(seed) [* m(seed2) if two_masks] [+ res if res != NULL] (the post-LN residual
+ * branches dropout(sublayer(x)) + x of nn.TransformerEncoderLayer, newsEncoders.py:244-247, in one pass; two masks = the
+ * backward of lime_embed_pe_dropout).  cols and leading dimensions multiples of 4, 16-byte aligned bases. */
+int lime_dropout_fused(const float *x, int64_t ldx, const float *res, int64_t ldr, float *y, int64_t ldy, int64_t rows,
+                       int cols, float p, uint64_t seed, uint64_t seed2, int two_masks, void *stream);
+/* training-mode embedding path in one pass (newsEncoders.py:311-315, :828): out[r, c] = m_x * (m_w * E[ids[r], c] + pe[r % T, c]),
+ * m_w / m_x the dropout masks of (seed_w, r d + c) / (seed_x, r d + c) -- what lime_gather_rows, lime_dropout, the positional add
+ * and a second lime_dropout compute.  E [vocab, d] and out [rows, d] contiguous, d a multiple of 4. */
+int lime_embed_pe_dropout(const float *E, int64_t vocab, const int32_t *ids, int64_t rows, int T, int d, const float *pe,
+                          float p, uint64_t seed_w, uint64_t seed_x, float *out, void *stream);
 
 /* ---- training: CROWN user encoder + click score, N candidates per sample (userEncoders.py:101-175,
  * layers.py:52-93, util.py:23-49).  Dense layers are lime_linear / lime_gemm; these are the pieces between. */

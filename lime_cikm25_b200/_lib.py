@@ -100,6 +100,8 @@ PROTOTYPES = {
     "lime_intent_pool_bwd": (C.c_int, [P, P, P, P, I64, P, P, P, I64, C.c_int, C.c_int, P]),
     "lime_content_fuse_bwd": (C.c_int, [P, P, P, I64, I64, C.c_int, P, P, P]),
     "lime_dropout": (C.c_int, [P, I64, P, I64, I64, C.c_int, F32, C.c_uint64, P]),
+    "lime_dropout_fused": (C.c_int, [P, I64, P, I64, P, I64, I64, C.c_int, F32, C.c_uint64, C.c_uint64, C.c_int, P]),
+    "lime_embed_pe_dropout": (C.c_int, [P, I64, P, I64, C.c_int, C.c_int, P, F32, C.c_uint64, C.c_uint64, P, P]),
     "lime_ca_attention_fwd": (C.c_int, [P, P, P, I32, I32, I32, F32, C.c_uint64, P, P]),
     "lime_ca_attention_bwd": (C.c_int, [P, P, P, I32, I32, I32, F32, C.c_uint64, P, P, P, P]),
     "lime_row_scale_fwd": (C.c_int, [P, P, I64, C.c_int, P, P]),

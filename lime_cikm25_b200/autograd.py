@@ -267,6 +267,52 @@ def dropout(x, p, seed):
     return Dropout.apply(x, p, seed) if p > 0 else x
 
 
+def _quad_ok(*ts):
+    return all(t.dim() == 2 and t.stride(1) == 1 and t.shape[1] % 4 == 0 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0
+               for t in ts)
+
+
+class DropoutAdd(torch.autograd.Function):
+    """dropout(x) + res in one pass (the post-LN residual branches of nn.TransformerEncoderLayer)."""
+
+    @staticmethod
+    def forward(ctx, x, res, p, seed):
+        ctx.p, ctx.seed = p, seed
+        return ops.dropout_fused(x, p, seed, res=res)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        return ops.dropout(dy, ctx.p, ctx.seed), dy, None, None
+
+
+def dropout_add(x, res, p, seed):
+    if p <= 0:
+        return x + res
+    if _quad_ok(x, res):
+        return DropoutAdd.apply(x, res, p, seed)
+    return Dropout.apply(x, p, seed) + res
+
+
+class EmbedPEDropout(torch.autograd.Function):
+    """dropout(dropout(word_embedding(ids)) + pe): one forward pass, one backward pass + the embedding scatter."""
+
+    @staticmethod
+    def forward(ctx, E, ids, T, pe, p, seed_w, seed_x):
+        ctx.save_for_backward(ids)
+        ctx.meta = (E.shape, p, seed_w, seed_x)
+        return ops.embed_pe_dropout(E, ids, T, pe, p, seed_w, seed_x)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        shape, p, seed_w, seed_x = ctx.meta
+        g = ops.dropout_fused(_c(dout), p, seed_x, seed2=seed_w)
+        dE = torch.zeros(shape, dtype=torch.float32, device=dout.device)
+        ops.scatter_add_rows(g, ids.reshape(-1), dE)
+        return dE, None, None, None, None, None, None
+
+
 class BucketPairs(torch.autograd.Function):
     """[Ef[bf] | El[bl]] for every (bf, bl) -> [nb*nb, 2*dim]."""
 

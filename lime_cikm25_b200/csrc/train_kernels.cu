@@ -556,6 +556,58 @@ __global__ void dropout4_kernel(const float *__restrict__ x, int64_t ldx, float 
     *reinterpret_cast<float4 *>(y + r * ldy + c) = o;
 }
 
+
+// Fused forms of the dropout sites of a transformer branch (bf16 and fp32 training alike, same masks as dropout_kernel):
+//   y = x * m(seed) [* m(seed2)] [+ res]          4 columns per thread
+// "+ res": dropout(out_proj(.)) + x and dropout(linear2(.)) + x1 (newsEncoders.py:244-247, post-LN residuals) in one pass;
+// two masks: the backward of the embedding path below.
+__global__ void dropout_fused4_kernel(const float *__restrict__ x, int64_t ldx, const float *__restrict__ res, int64_t ldr,
+                                      float *__restrict__ y, int64_t ldy, int64_t rows, int cols4, float p, uint64_t seed,
+                                      uint64_t seed2, int two) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols4) return;
+    const int64_t r = idx / cols4;
+    const int c = 4 * (int)(idx - r * cols4);
+    const float4 v = *reinterpret_cast<const float4 *>(x + r * ldx + c);
+    const uint64_t e0 = (uint64_t)(r * (4 * (int64_t)cols4) + c);
+    float m[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        m[e] = drop_scale(seed, e0 + e, p);
+        if (two) m[e] *= drop_scale(seed2, e0 + e, p);
+    }
+    float4 o = make_float4(v.x * m[0], v.y * m[1], v.z * m[2], v.w * m[3]);
+    if (res != nullptr) {
+        const float4 q = *reinterpret_cast<const float4 *>(res + r * ldr + c);
+        o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+    }
+    *reinterpret_cast<float4 *>(y + r * ldy + c) = o;
+}
+
+// word_embedding(ids) -> dropout(seed_w) -> + positional encoding -> dropout(seed_x) in one pass (newsEncoders.py:311-315,
+// :828 in training mode; the unfused path took a gather, two dropouts, a repeat and an add over the [tokens, 300] rows):
+//   out[r, c] = m_x(r d + c) * (m_w(r d + c) * E[ids[r], c] + pe[r % T, c])
+__global__ void embed_pe_dropout_kernel(const float *__restrict__ E, int64_t vocab, const int32_t *__restrict__ ids, int64_t rows,
+                                        int T, int d4, const float *__restrict__ pe, float p, uint64_t seed_w, uint64_t seed_x,
+                                        float *__restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * d4) return;
+    const int64_t r = idx / d4;
+    const int c = 4 * (int)(idx - r * d4);
+    const int d = 4 * d4;
+    int64_t id = ids[r];
+    id = (id < 0 || id >= vocab) ? 0 : id;
+    const float4 w = *reinterpret_cast<const float4 *>(E + id * d + c);
+    const float4 q = *reinterpret_cast<const float4 *>(pe + (int64_t)(r % T) * d + c);
+    const uint64_t e0 = (uint64_t)(r * d + c);
+    float4 o;
+    o.x = drop_scale(seed_x, e0, p) * fmaf(drop_scale(seed_w, e0, p), w.x, q.x);
+    o.y = drop_scale(seed_x, e0 + 1, p) * fmaf(drop_scale(seed_w, e0 + 1, p), w.y, q.y);
+    o.z = drop_scale(seed_x, e0 + 2, p) * fmaf(drop_scale(seed_w, e0 + 2, p), w.z, q.z);
+    o.w = drop_scale(seed_x, e0 + 3, p) * fmaf(drop_scale(seed_w, e0 + 3, p), w.w, q.w);
+    *reinterpret_cast<float4 *>(out + r * d + c) = o;
+}
+
 }  // namespace lime
 
 using namespace lime;
@@ -727,5 +779,32 @@ extern "C" int lime_dropout(const float *x, int64_t ldx, float *y, int64_t ldy, 
     }
     dropout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, ldx, y, ldy, rows, cols, p, seed);
     LIME_LAUNCH_CHECK("dropout_kernel");
+    return 0;
+}
+
+extern "C" int lime_dropout_fused(const float *x, int64_t ldx, const float *res, int64_t ldr, float *y, int64_t ldy, int64_t rows,
+                                  int cols, float p, uint64_t seed, uint64_t seed2, int two_masks, void *stream) {
+    LIME_CHECK_ARG(x && y && p >= 0.0f && p < 1.0f, "lime_dropout_fused: bad argument");
+    LIME_CHECK_ARG((cols & 3) == 0 && (ldx & 3) == 0 && (ldy & 3) == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0 &&
+                       (res == nullptr || ((ldr & 3) == 0 && ((uintptr_t)res & 15) == 0)),
+                   "lime_dropout_fused: cols and leading dimensions must be multiples of 4, bases 16-byte aligned");
+    if (rows <= 0 || cols <= 0) return 0;
+    const int64_t total = rows * (cols / 4);
+    dropout_fused4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, ldx, res, ldr, y, ldy, rows, cols / 4, p, seed,
+                                                                                        seed2, two_masks);
+    LIME_LAUNCH_CHECK("dropout_fused4_kernel");
+    return 0;
+}
+
+extern "C" int lime_embed_pe_dropout(const float *E, int64_t vocab, const int32_t *ids, int64_t rows, int T, int d, const float *pe,
+                                     float p, uint64_t seed_w, uint64_t seed_x, float *out, void *stream) {
+    LIME_CHECK_ARG(E && ids && pe && out && vocab > 0 && T > 0 && p >= 0.0f && p < 1.0f, "lime_embed_pe_dropout: bad argument");
+    LIME_CHECK_ARG((d & 3) == 0 && d > 0 && (((uintptr_t)E | (uintptr_t)pe | (uintptr_t)out) & 15) == 0,
+                   "lime_embed_pe_dropout: d must be a multiple of 4, bases 16-byte aligned");
+    if (rows <= 0) return 0;
+    const int64_t total = rows * (d / 4);
+    embed_pe_dropout_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(E, vocab, ids, rows, T, d / 4, pe, p, seed_w,
+                                                                                          seed_x, out);
+    LIME_LAUNCH_CHECK("embed_pe_dropout_kernel");
     return 0;
 }

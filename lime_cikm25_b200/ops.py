@@ -482,6 +482,30 @@ def dropout(x, p, seed, out=None):
     return out
 
 
+_M64 = 2 ** 64 - 1
+
+
+def dropout_fused(x, p, seed, res=None, seed2=None):
+    """x * m(seed) [* m(seed2)] [+ res] in one pass (lime_dropout_fused), the masks of ``dropout``."""
+    lib = _lib.require_device()
+    out = torch.empty_like(x)
+    check(lib.lime_dropout_fused(_ptr(x, torch.float32, "x"), _rowmajor(x, "x"), _ptr(res, torch.float32, "res"),
+                                 _rowmajor(res, "res") if res is not None else 0, _ptr(out, torch.float32, "out"),
+                                 _rowmajor(out, "out"), x.shape[0], x.shape[1], float(p), int(seed) & _M64,
+                                 int(seed2 or 0) & _M64, 0 if seed2 is None else 1, _stream()), "lime_dropout_fused")
+    return out
+
+
+def embed_pe_dropout(E, ids, T, pe, p, seed_w, seed_x):
+    """m_x * (m_w * E[ids] + pe) -> [ids.numel(), d] (lime_embed_pe_dropout)."""
+    lib = _lib.require_device()
+    out = torch.empty((ids.numel(), E.shape[1]), dtype=torch.float32, device=E.device)
+    check(lib.lime_embed_pe_dropout(_ptr(E, torch.float32, "E"), E.shape[0], _ptr(ids, torch.int32, "ids"), ids.numel(), int(T),
+                                    E.shape[1], _ptr(pe, torch.float32, "pe"), float(p), int(seed_w) & _M64, int(seed_x) & _M64,
+                                    _ptr(out, torch.float32, "out"), _stream()), "lime_embed_pe_dropout")
+    return out
+
+
 # ---- training kernels of the user encoder (csrc/train_user.cu) -------------------------------------
 def _f32(t, name):
     return _ptr(t, torch.float32, name)

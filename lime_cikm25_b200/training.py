@@ -31,7 +31,10 @@ def _branch(base, ids, T, transformer, pos_encoder, heads, p, seed):
     l = transformer.layers[0]
     d = base.word_embedding.weight.shape[1]
     pe = pos_encoder.pe.reshape(-1, d)
-    if p > 0:
+    if p > 0 and d % 4 == 0 and base.word_embedding.weight.is_contiguous():
+        # dropout(word embeddings, seed) + pe, dropout(., seed + 1): one kernel with the two masks of the unfused form below
+        x0 = A.EmbedPEDropout.apply(base.word_embedding.weight, ids.reshape(-1).contiguous(), T, pe.contiguous(), p, seed, seed + 1)
+    elif p > 0:
         w = A.dropout(A.Gather.apply(base.word_embedding.weight, ids.reshape(-1).contiguous()), p, seed)
         x0 = A.dropout(w + pe[:T].repeat(n, 1), p, seed + 1)
     else:
@@ -39,13 +42,13 @@ def _branch(base, ids, T, transformer, pos_encoder, heads, p, seed):
     qkv = A.linear(x0, l.self_attn.in_proj_weight, l.self_attn.in_proj_bias)
     ctx = A.MHA.apply(qkv, n, T, d, heads, p, seed + 2)
     if p > 0:
-        y = A.dropout(A.linear(ctx, l.self_attn.out_proj.weight, l.self_attn.out_proj.bias), p, seed + 3) + x0
+        y = A.dropout_add(A.linear(ctx, l.self_attn.out_proj.weight, l.self_attn.out_proj.bias), x0, p, seed + 3)
     else:
         y = A.linear(ctx, l.self_attn.out_proj.weight, l.self_attn.out_proj.bias, residual=x0)
     x1 = A.LayerNorm.apply(y, l.norm1.weight, l.norm1.bias, l.norm1.eps)
     hf = A.dropout(A.linear(x1, l.linear1.weight, l.linear1.bias, act=RELU), p, seed + 4)
     if p > 0:
-        y2 = A.dropout(A.linear(hf, l.linear2.weight, l.linear2.bias), p, seed + 5) + x1
+        y2 = A.dropout_add(A.linear(hf, l.linear2.weight, l.linear2.bias), x1, p, seed + 5)
     else:
         y2 = A.linear(hf, l.linear2.weight, l.linear2.bias, residual=x1)
     return A.LayerNormMeanPool.apply(y2, l.norm2.weight, l.norm2.bias, n, T, l.norm2.eps)

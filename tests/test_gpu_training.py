@@ -176,6 +176,32 @@ def test_training_step_gradients(lib, bs, B):
     print("training step: %d parameters, worst gradient error %.2e" % (checked, worst))
 
 
+def test_fused_dropout_sites_equal_the_unfused_ones(lib):
+    """lime_embed_pe_dropout and lime_dropout_fused apply the masks of the separate dropout kernel (same seeds, same element
+    index), forward and backward."""
+    from lime_cikm25_b200 import autograd as A
+    V, d, T, n, p = 300, 300, 32, 6, 0.3
+    E = randn(V, d, seed=1).requires_grad_()
+    pe = randn(64, d, seed=2)
+    ids = torch.randint(0, V, (n * T,), generator=gen(3)).to(torch.int32).to(DEV)
+    g = randn(n * T, d, seed=4)
+    a = A.EmbedPEDropout.apply(E, ids, T, pe, p, 77, 78)
+    a.backward(g)
+    ga, E.grad = E.grad.clone(), None
+    b = A.dropout(A.dropout(A.Gather.apply(E, ids), p, 77) + pe[:T].repeat(n, 1), p, 78)
+    b.backward(g)
+    assert torch.allclose(a, b, rtol=1e-6, atol=1e-6) and torch.allclose(ga, E.grad, rtol=1e-4, atol=1e-5)
+    assert 0.4 < float((a == 0).float().mean()) / (1 - (1 - p) ** 1) < 1.1      # second mask zeroes ~p of the elements
+    x, r = randn(n * T, d, seed=5).requires_grad_(), randn(n * T, d, seed=6).requires_grad_()
+    y = A.dropout_add(x, r, p, 99)
+    y.backward(g)
+    gx, gr = x.grad.clone(), r.grad.clone()
+    x.grad = r.grad = None
+    y2 = A.dropout(x, p, 99) + r
+    y2.backward(g)
+    assert torch.equal(y, y2) and torch.equal(gx, x.grad) and torch.equal(gr, r.grad)
+
+
 def test_trainer_step_is_the_reference_update(lib):
     """Trainer.step (flat gradient buffer, clip on the buffer, fused Adam) = the reference's step (trainer.py:131-148):
     zero_grad, backward, nn.utils.clip_grad_norm_, plain torch.optim.Adam -- same parameters after two steps."""
