@@ -15,9 +15,10 @@ model = model.cuda().eval()
 ref = None
 with torch.no_grad():
     model.scoring.fold()
-    for mode in (False, "x3", "x3", True, True):
+    for mode in (False, "x3-ffma-mha", "x3", "x3", True, True):
         model.news_encoder.engine.bf16 = mode is True
-        model.news_encoder.engine.x3 = mode == "x3"
+        model.news_encoder.engine.x3 = str(mode).startswith("x3")
+        model.news_encoder.engine.x3_mha = mode != "x3-ffma-mha"
         torch.cuda.synchronize(); t0 = time.perf_counter()
         cache = util.build_news_cache(model, news, "cuda", **({"chunk": chunk} if chunk else {}))
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
