@@ -625,6 +625,150 @@ mha_fwd_tc_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d,
     }
 }
 
+// fp32x3 mode of lime_mha (Stage A, fp32 q | k | v rows and fp32 ctx as mha_kernel<T>): the same fragment layout as
+// mha_fwd_tc_kernel, every operand an fp16 hi / lo pair (x = hi + lo, 22 significant bits; activations of a LayerNormed
+// transformer sit well inside the fp16 range) and every product three MMAs: hi*hi + lo*hi + hi*lo, fp32 accumulation --
+// the dropped lo*lo term is 2^-22 of the product.  q is scaled by 1/sqrt(hd) in fp32 BEFORE the split, like mha_kernel.
+// The softmax weights p in [0, 1] are split the same way for O = P V.  Replaces the FFMA mha_kernel<T> in that mode
+// (22 % of its cache build).  Shared memory: six [T][40] fp16 tiles (61,440 B at T = 128: dynamic).
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+template <int T>
+__global__ void __launch_bounds__(T)
+mha_x3_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int nhead, int hd, float scale, float p_drop,
+              uint64_t seed, int64_t news0) {
+    constexpr int P = 40;
+    constexpr int NT = T / 8;
+    typedef __half Tile[T][P];
+    extern __shared__ __align__(16) unsigned char mhax_smem[];
+    Tile *tl = reinterpret_cast<Tile *>(mhax_smem);             // Qhi Qlo Khi Klo Vhi Vlo
+    const int64_t news = blockIdx.y;
+    const int head = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t2 = 2 * (lane & 3);
+    const int64_t ld = 3 * (int64_t)d;
+    const float *base = qkv + news * T * ld;
+    for (int idx = tid; idx < T * 32; idx += T) {
+        const int r = idx >> 5, e = idx & 31;
+        const bool ok = e < hd;
+        const float x[3] = {ok ? base[r * ld + head * hd + e] * scale : 0.0f, ok ? base[r * ld + d + head * hd + e] : 0.0f,
+                            ok ? base[r * ld + 2 * d + head * hd + e] : 0.0f};
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const __half h = __float2half_rn(x[m]);
+            tl[2 * m][r][e] = h;
+            tl[2 * m + 1][r][e] = __float2half_rn(x[m] - __half2float(h));
+        }
+    }
+    __syncthreads();
+    const uint64_t drop_nh = ((uint64_t)(news0 + news) * nhead + head) * T;
+    constexpr float kLog2e = 1.4426950408889634f;
+#pragma unroll 1
+    for (int mb = 0; mb < 2; ++mb) {
+        const int r0 = 32 * warp + 16 * mb;
+        uint32_t qh[2][4], ql[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            ldsm_x4(qh[ks], &tl[0][r0 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * ks + 8 * (lane >> 4)]);
+            ldsm_x4(ql[ks], &tl[1][r0 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * ks + 8 * (lane >> 4)]);
+        }
+        float sacc[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.0f;
+            uint32_t kh[4], kl[4];
+            ldsm_x4(kh, &tl[2][8 * j + (lane & 7)][8 * (lane >> 3)]);
+            ldsm_x4(kl, &tl[3][8 * j + (lane & 7)][8 * (lane >> 3)]);
+            mma_f16_16816(sacc[j], ql[0], kh[0], kh[1]);                   // the small terms first
+            mma_f16_16816(sacc[j], ql[1], kh[2], kh[3]);
+            mma_f16_16816(sacc[j], qh[0], kl[0], kl[1]);
+            mma_f16_16816(sacc[j], qh[1], kl[2], kl[3]);
+            mma_f16_16816(sacc[j], qh[0], kh[0], kh[1]);
+            mma_f16_16816(sacc[j], qh[1], kh[2], kh[3]);
+        }
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            m0 = fmaxf(m0, fmaxf(sacc[j][0], sacc[j][1]));
+            m1 = fmaxf(m1, fmaxf(sacc[j][2], sacc[j][3]));
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float l0 = 0.0f, l1 = 0.0f;
+        const int ra = r0 + g, rb = ra + 8;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            sacc[j][0] = exp2f((sacc[j][0] - m0) * kLog2e);
+            sacc[j][1] = exp2f((sacc[j][1] - m0) * kLog2e);
+            sacc[j][2] = exp2f((sacc[j][2] - m1) * kLog2e);
+            sacc[j][3] = exp2f((sacc[j][3] - m1) * kLog2e);
+            l0 += sacc[j][0] + sacc[j][1];
+            l1 += sacc[j][2] + sacc[j][3];
+            if (p_drop > 0.0f) {                             // the sums are taken BEFORE the mask: O = (softmax * M) V
+                const int c = 8 * j + t2;
+                sacc[j][0] *= drop_scale(seed, (drop_nh + ra) * T + c, p_drop);
+                sacc[j][1] *= drop_scale(seed, (drop_nh + ra) * T + c + 1, p_drop);
+                sacc[j][2] *= drop_scale(seed, (drop_nh + rb) * T + c, p_drop);
+                sacc[j][3] *= drop_scale(seed, (drop_nh + rb) * T + c + 1, p_drop);
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        float oacc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.0f;
+#pragma unroll
+        for (int kk = 0; kk < T / 16; ++kk) {
+            uint32_t ph[4], pl[4];
+            split2_f16(sacc[2 * kk][0], sacc[2 * kk][1], ph[0], pl[0]);
+            split2_f16(sacc[2 * kk][2], sacc[2 * kk][3], ph[1], pl[1]);
+            split2_f16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1], ph[2], pl[2]);
+            split2_f16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3], ph[3], pl[3]);
+#pragma unroll
+            for (int jp = 0; jp < 2; ++jp) {
+                uint32_t vh[4], vl[4];
+                ldsm_x4_trans(vh, &tl[4][16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
+                ldsm_x4_trans(vl, &tl[5][16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
+                mma_f16_16816(oacc[2 * jp], pl, vh[0], vh[1]);
+                mma_f16_16816(oacc[2 * jp + 1], pl, vh[2], vh[3]);
+                mma_f16_16816(oacc[2 * jp], ph, vl[0], vl[1]);
+                mma_f16_16816(oacc[2 * jp + 1], ph, vl[2], vl[3]);
+                mma_f16_16816(oacc[2 * jp], ph, vh[0], vh[1]);
+                mma_f16_16816(oacc[2 * jp + 1], ph, vh[2], vh[3]);
+            }
+        }
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        float *o0 = ctx + (news * T + ra) * (int64_t)d + head * hd, *o1 = o0 + 8 * (int64_t)d;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = 8 * j + t2;
+            if (c < hd) {
+                o0[c] = oacc[j][0] * i0;
+                o1[c] = oacc[j][2] * i1;
+            }
+            if (c + 1 < hd) {
+                o0[c + 1] = oacc[j][1] * i0;
+                o1[c + 1] = oacc[j][3] * i1;
+            }
+        }
+    }
+}
+
 // ---- LayerNorm (two-pass, like ATen) ------------------------------------------------------------
 constexpr int kLnMaxPerLane = 16;   // d <= 512
 
@@ -978,6 +1122,27 @@ extern "C" int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int
         mha_kernel<128, float, float><<<grid, 128, 0, as_stream(stream)>>>(qkv, ctx, 3 * (int64_t)d, d, d, nhead, hd, scale, p_drop, seed, news0);
     }
     LIME_LAUNCH_CHECK("mha_kernel");
+    return 0;
+}
+
+// fp32x3 mode of lime_mha: same arguments, fp16 hi / lo operand pairs on the tensor cores (mma.sync m16n8k16, 3 MMAs per product)
+extern "C" int lime_mha_x3(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, float p_drop, uint64_t seed,
+                           int64_t news0, void *stream) {
+    LIME_CHECK_ARG(qkv && ctx, "lime_mha_x3: null argument");
+    LIME_CHECK_ARG((T == 32 || T == 128) && nhead > 0 && d % nhead == 0 && d / nhead <= 32, "lime_mha_x3: unsupported shape T=%d d=%d heads=%d", T, d, nhead);
+    LIME_CHECK_ARG(n_news <= 65535, "lime_mha_x3: at most 65535 news per call (got %lld)", (long long)n_news);
+    if (n_news <= 0) return 0;
+    const int hd = d / nhead;
+    const float scale = 1.0f / sqrtf((float)hd);
+    dim3 grid(nhead, (unsigned)n_news);
+    const int smem = 6 * T * 40 * (int)sizeof(__half);
+    if (T == 32) {
+        mha_x3_kernel<32><<<grid, 32, smem, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale, p_drop, seed, news0);
+    } else {
+        LIME_CUDA(cudaFuncSetAttribute(mha_x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mha_x3_kernel<128><<<grid, 128, smem, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale, p_drop, seed, news0);
+    }
+    LIME_LAUNCH_CHECK("mha_x3_kernel");
     return 0;
 }
 

@@ -77,6 +77,7 @@ class NewsEncoderEngine:
         self._fp = None
         self.bf16 = False        # "bf16 mode": bf16 activations, the 4 transformer GEMMs by TMA + tcgen05 (lime_linear_bf16_tma)
         self.x3 = False          # "fp32x3 mode" (opt-in; default = the fp32 FFMA kernels, the strict-parity mode): fp32 activations, every transformer GEMM as 3 bf16 tensor-core passes on hi / lo pairs
+        self.x3_mha = True       # fp32x3 mode: attention core on the tensor cores too (lime_mha_x3, fp16 hi / lo pairs); False = the FFMA core
 
     # -- weights -----------------------------------------------------------------------------------
     def _params(self):
@@ -194,7 +195,7 @@ class NewsEncoderEngine:
         qkv = ops.linear_x3(xh, xl, W["in_w_hi"], W["in_w_lo"], W["in_b"], alpha=al)
         del xh, xl
         ctx = torch.empty(rows, 300, dtype=torch.float32, device=dev)
-        ops.mha(qkv, ctx, n, T, 300, self.cfg.head_num)
+        ops.mha(qkv, ctx, n, T, 300, self.cfg.head_num, x3=self.x3_mha)
         del qkv
         ch, cl = ops.split16(ctx, scale=sa)
         y = ops.linear_x3(ch, cl, W["out_w_hi"], W["out_w_lo"], W["out_b"], residual=x0, alpha=al)

@@ -200,10 +200,11 @@ def embed_pe(E, ids, T, pe, out):
     return out
 
 
-def mha(qkv, ctx, n_news, T, d, nhead, p_drop=0.0, seed=0, bf16=False):
-    """attention core; bf16: lime_mha_fwd_bf16 (tensor cores, q k v and P rounded to bf16), the training step's bf16 mode"""
+def mha(qkv, ctx, n_news, T, d, nhead, p_drop=0.0, seed=0, bf16=False, x3=False):
+    """attention core; bf16: lime_mha_fwd_bf16 (tensor cores, q k v and P rounded to bf16), the training step's bf16 mode;
+    x3: lime_mha_x3 (tensor cores on fp16 hi / lo pairs, fp32-level accuracy), Stage A's fp32x3 mode"""
     lib = _lib.require_device()
-    fn = lib.lime_mha_fwd_bf16 if bf16 else lib.lime_mha
+    fn = lib.lime_mha_x3 if x3 else lib.lime_mha_fwd_bf16 if bf16 else lib.lime_mha
     for lo in range(0, n_news, 65535):
         hi = min(n_news, lo + 65535)
         check(fn(qkv[lo * T:].data_ptr(), ctx[lo * T:].data_ptr(), hi - lo, T, d, nhead, float(p_drop),

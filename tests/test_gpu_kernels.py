@@ -196,6 +196,15 @@ def test_embed_pe_and_mha(lib, T):
     q, k, v = qkv.double().view(n, T, 3, heads, d // heads).permute(2, 0, 3, 1, 4)
     att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d // heads), dim=-1)
     close(ctx.view(n, T, d), (att @ v).transpose(1, 2).reshape(n, T, d), 1e-5)
+    # fp32x3 mode of the same core: fp16 hi / lo pairs on the tensor cores, same fp32-level bar against fp64
+    ctx3 = torch.full((n * T, d), float("nan"), device=DEV)
+    ops.mha(qkv, ctx3, n, T, d, heads, x3=True)
+    close(ctx3.view(n, T, d), (att @ v).transpose(1, 2).reshape(n, T, d), 1e-5)
+    big = qkv * 2.0                                          # sharper softmax (logits up to +-15), larger operands
+    ops.mha(big, ctx3, n, T, d, heads, x3=True)
+    q, k, v = big.double().view(n, T, 3, heads, d // heads).permute(2, 0, 3, 1, 4)
+    att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d // heads), dim=-1)
+    close(ctx3.view(n, T, d), (att @ v).transpose(1, 2).reshape(n, T, d), 1e-5)
 
 
 def test_layernorm_and_meanpool(lib):
