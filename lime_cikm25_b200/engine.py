@@ -78,6 +78,7 @@ class NewsEncoderEngine:
         self.bf16 = False        # "bf16 mode": bf16 activations, the 4 transformer GEMMs by TMA + tcgen05 (lime_linear_bf16_tma)
         self.x3 = False          # "fp32x3 mode" (opt-in; default = the fp32 FFMA kernels, the strict-parity mode): fp32 activations, every transformer GEMM as 3 bf16 tensor-core passes on hi / lo pairs
         self.x3_mha = True       # fp32x3 mode: attention core on the tensor cores too (lime_mha_x3, fp16 hi / lo pairs); False = the FFMA core
+        self.x3_small = True     # tensor-core modes: intent layers, intent-attention affine and the content projection as fp32x3 passes (False = FFMA lime_linear)
 
     # -- weights -----------------------------------------------------------------------------------
     def _params(self):
@@ -101,6 +102,11 @@ class NewsEncoderEngine:
             W[i * 400:(i + 1) * 400, :350].copy_(lin.weight.detach())
             b[i * 400:(i + 1) * 400].copy_(lin.bias.detach())
         P["intent_w"], P["intent_b"] = W, b
+        # tensor-core modes: the intent layers, their attention's first affine and the content half of LIME.project as
+        # fp32x3 passes too (fp16 pairs 2^10 w = hi + lo, K padded to a multiple of 64)
+        P["intent_w_hi"], P["intent_w_lo"] = ops.split16(W, scale=ops.X3_W_SCALE)
+        for name, att in (("title", base.title_intent_attention), ("body", base.body_intent_attention)):
+            P[name + "_a1_hi"], P[name + "_a1_lo"] = ops.split16(att.affine1.weight.detach(), scale=ops.X3_W_SCALE)
 
         def tr(t):
             l = t.layers[0]
@@ -136,6 +142,7 @@ class NewsEncoderEngine:
         P["body_pe"] = base.body_pos_encoder.pe.detach().reshape(-1, 300).contiguous()
         pw = m.project.weight.detach()                    # [400, 1800] = [W_c | W_f]
         P["Wc"], P["Wf"], P["proj_b"] = pw[:, :900], pw[:, 900:], m.project.bias.detach()
+        P["Wc_hi"], P["Wc_lo"] = ops.split16(P["Wc"], scale=ops.X3_W_SCALE)
         self._prep, self._fp = P, fp
         return P
 
@@ -228,9 +235,17 @@ class NewsEncoderEngine:
                           category, subCategory, feat[:, 300:], TOPIC_LD)
         k = len(base.intent_layers)
         pooled = []
-        for feat, att in ((feat_t, base.title_intent_attention), (feat_b, base.body_intent_attention)):
-            e = ops.linear(feat, P["intent_w"], P["intent_b"], act=ops.ACT_RELU)          # [n, k*400]
-            pre = ops.linear(e.view(n * k, 400), att.affine1.weight.detach(), att.affine1.bias.detach())
+        tc_mode = (self.bf16 or self.x3) and self.x3_small
+        sa, al = ops.X3_ACT_SCALE, 1.0 / (ops.X3_ACT_SCALE * ops.X3_W_SCALE)
+        for feat, att, name in ((feat_t, base.title_intent_attention, "title"), (feat_b, base.body_intent_attention, "body")):
+            if tc_mode:
+                fh, fl = ops.split16(feat, scale=sa)
+                e = ops.linear_x3(fh, fl, P["intent_w_hi"], P["intent_w_lo"], P["intent_b"], act=ops.ACT_RELU, alpha=al)
+                eh, el = ops.split16(e.view(n * k, 400), scale=sa)
+                pre = ops.linear_x3(eh, el, P[name + "_a1_hi"], P[name + "_a1_lo"], att.affine1.bias.detach(), alpha=al)
+            else:
+                e = ops.linear(feat, P["intent_w"], P["intent_b"], act=ops.ACT_RELU)          # [n, k*400]
+                pre = ops.linear(e.view(n * k, 400), att.affine1.weight.detach(), att.affine1.bias.detach())
             out = torch.empty(n, 400, **f32)
             ops.intent_pool(pre, e, att.affine2.weight.detach().reshape(-1), out, n, k, 400)
             pooled.append(out)
@@ -425,10 +440,15 @@ class ScoringEngine:
             ct, sb = category[lo:hi].contiguous(), subCategory[lo:hi].contiguous()
             content = self.news.encode_content(tt, bt, ct, sb)
             h, c = hist[lo:hi], cand[lo:hi]
-            ops.linear(content, Wc, out=h[:, :D])                                   # vc
-            tc_mode = self.news.bf16 or self.news.x3        # tensor-core modes: the two folds as fp32x3 passes (2^-16 per product)
+            tc_mode = self.news.bf16 or self.news.x3        # tensor-core modes: the two folds as fp32x3 passes (2^-22 per product)
+            al = 1.0 / (ops.X3_ACT_SCALE * ops.X3_W_SCALE)
+            if tc_mode and self.news.x3_small:
+                P = self.news.prepare()
+                ch_, cl_ = ops.split16(content, scale=ops.X3_ACT_SCALE)
+                ops.linear_x3(ch_, cl_, P["Wc_hi"], P["Wc_lo"], out=h[:, :D], alpha=al)   # vc
+            else:
+                ops.linear(content, Wc, out=h[:, :D])                               # vc
             if tc_mode:
-                al = 1.0 / (ops.X3_ACT_SCALE * ops.X3_W_SCALE)
                 vh, vl = ops.split16(h[:, :D], scale=ops.X3_ACT_SCALE)
                 ops.linear_x3(vh, vl, F["Gg_hi"], F["Gg_lo"], out=h[:, HIST_GW:HIST_GW + D], alpha=al)
             else:

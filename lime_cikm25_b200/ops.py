@@ -119,6 +119,7 @@ def cast_bf16(x, kp=None):
     return hi
 
 
+X3_MAX_K = 512
 X3_ACT_SCALE, X3_W_SCALE = 16.0, 1024.0      # fp16 pairs of the fp32x3 mode: activations * 2^4, weights * 2^10 (hi < 65504, lo out of the subnormals)
 
 
@@ -144,6 +145,14 @@ def linear_x3(xh, xl, wh, wl, bias=None, residual=None, act=ACT_NONE, out=None, 
     accumulating passes add BEFORE the activation)."""
     assert act == ACT_NONE or residual is None
     n = wh.shape[0] if n is None else n
+    kp = xh.shape[1]
+    if kp > X3_MAX_K:                  # contractions longer than one lime_linear_bf16_tma pass: accumulate 512-column slices in place
+        assert act == ACT_NONE
+        for k0 in range(0, kp, X3_MAX_K):
+            k1 = min(kp, k0 + X3_MAX_K)
+            out = linear_x3(xh[:, k0:k1], xl[:, k0:k1], wh[:, k0:k1], wl[:, k0:k1], bias if k0 == 0 else None,
+                            residual=residual if k0 == 0 else out, out=out, n=n, alpha=alpha)
+        return out
     out = linear_tma(xh, wh, None, residual=residual, out=out, n=n, out_bf16=False, alpha=alpha)
     linear_tma(xl, wh, None, residual=out, out=out, n=n, out_bf16=False, alpha=alpha)
     linear_tma(xh, wl, bias, residual=out, act=act | ACT_RES_FIRST, out=out, n=n, out_bf16=False, alpha=alpha)

@@ -15,10 +15,11 @@ model = model.cuda().eval()
 ref = None
 with torch.no_grad():
     model.scoring.fold()
-    for mode in (False, "x3-ffma-mha", "x3", "x3", True, True):
+    for mode in (False, "x3-ffma-small", "x3", "x3", "bf16-ffma-small", True, True):
         model.news_encoder.engine.bf16 = mode is True
         model.news_encoder.engine.x3 = str(mode).startswith("x3")
-        model.news_encoder.engine.x3_mha = mode != "x3-ffma-mha"
+        model.news_encoder.engine.bf16 = mode is True or str(mode).startswith("bf16")
+        model.news_encoder.engine.x3_small = not str(mode).endswith("ffma-small")
         torch.cuda.synchronize(); t0 = time.perf_counter()
         cache = util.build_news_cache(model, news, "cuda", **({"chunk": chunk} if chunk else {}))
         torch.cuda.synchronize(); dt = time.perf_counter() - t0

@@ -117,7 +117,7 @@ def test_linear_bf16_tma(lib, m, n, k, act):
     assert float(got16[:, n:].float().abs().sum()) == 0.0
 
 
-@pytest.mark.parametrize("m,n,k", [(300, 900, 300), (1000, 300, 512), (77, 512, 300), (5, 7, 52)])
+@pytest.mark.parametrize("m,n,k", [(300, 900, 300), (1000, 300, 512), (77, 512, 300), (5, 7, 52), (333, 400, 900)])
 @pytest.mark.parametrize("fp16", [True, False])
 def test_linear_x3_fp32_accurate(lib, m, n, k, fp16):
     """Three accumulating tensor-core passes on hi / lo operand pairs reproduce the fp32 layer: fp16 pairs (pre-scaled by powers
@@ -132,7 +132,8 @@ def test_linear_x3_fp32_accurate(lib, m, n, k, fp16):
     z = a.double() @ w.double().t() + b.double()
     tol = 6e-6 if fp16 else 5e-5          # (fp16 pairs: the remaining error is the tensor core's own fp32 accumulation)
     close(ops.linear_x3(ah, al, wh, wl, b, residual=r, alpha=1.0 / (sa * sw)), z + r.double(), tol)
-    close(ops.linear_x3(ah, al, wh, wl, b, act=ops.ACT_RELU, alpha=1.0 / (sa * sw)), torch.relu(z), tol)
+    if k <= ops.X3_MAX_K:                 # longer contractions accumulate 512-column slices in place: no activation there
+        close(ops.linear_x3(ah, al, wh, wl, b, act=ops.ACT_RELU, alpha=1.0 / (sa * sw)), torch.relu(z), tol)
 
 
 def test_stage_a_bf16_glue(lib):
