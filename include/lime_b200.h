@@ -100,6 +100,14 @@ int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, int64_t ldw,
 /* act | LIME_ACT_RES_FIRST: the residual joins the sum BEFORE the activation, C = act(A . W^T + bias + residual): the
  * accumulating passes of the three-pass bf16x3 layer (residual = C, in place). */
 #define LIME_ACT_RES_FIRST 16
+/* The fp32x3 dense layer in ONE launch (fp32x3 encoder mode of newsEncoders.py:244-247's GEMMs): A = Ahi + Alo and W = Whi + Wlo
+ * are 16-bit pairs from lime_split_bf16_pairs (same lda / ldw for both images, k padded to a multiple of 64, both W images
+ * resident: 2 k bn 2 B <= 160 KB), C = act(alpha (Alo Whi^T + Ahi Wlo^T + Ahi Whi^T) + bias) + residual in fp32; the three
+ * products accumulate in one TMEM tile, small ones first (the tensor core truncates addends at the accumulator's exponent),
+ * so C is written once (the three-pass form re-reads and re-writes it twice). */
+int lime_linear_x3_tma(const void *Ahi, const void *Alo, int64_t lda, const void *Whi, const void *Wlo, int64_t ldw,
+                       const float *bias, const float *residual, int64_t ldr, float *C, int64_t ldc, int64_t m, int32_t n,
+                       int32_t k, int32_t act, float alpha, int32_t ab_is_fp16, void *stream);
 /* fp32 rows -> 16-bit pair hi = r16(scale x), lo = r16(scale x - hi), each [rows, ld16] with columns d..ld16-1 zero; fp16 pairs
  * (as_fp16 != 0: scale x = hi + lo to 2^-22, scale a power of two that keeps hi below 65504) or bf16 pairs (2^-17).
  * With the same split of W, x . W^T ~ xh . Wh^T + xl . Wh^T + xh . Wl^T reproduces the fp32 product on the tensor cores

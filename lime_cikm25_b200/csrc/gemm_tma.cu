@@ -82,6 +82,7 @@ static_assert(GB_COUNT * 8 + 8 <= 256, "barrier area");
 
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap,
+                const __grid_constant__ CUtensorMap amap2, const __grid_constant__ CUtensorMap wmap2, int x3,
                 const __grid_constant__ CUtensorMap cmap, const __grid_constant__ CUtensorMap rmap, int tma_epilogue, int ncov,
                 const float *__restrict__ bias, const float *__restrict__ residual, int64_t ldr, void *__restrict__ Cout,
                 int64_t ldc, int c_bf16, int64_t m, int n, int nkb, int bn, int n_tiles, int act, float alpha, int ab_fp16) {
@@ -102,6 +103,11 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     const int col0 = nt * bn;
     const int64_t m_tiles = (m + GT_M - 1) / GT_M;
     const int64_t mt0 = blockIdx.x / (unsigned)n_tiles, mt_step = gridDim.x / (unsigned)n_tiles;
+    // fp32x3 mode (x3 != 0): A = amap (hi) + amap2 (lo), W = wmap (hi) + wmap2 (lo); ONE accumulator takes the three products
+    // lo.hi + hi.lo + hi.hi as 3 nkb K blocks (K block i: segment i / nkb), both W images resident (slots 0..nkb-1 hi, nkb.. lo).
+    // The small products come FIRST: the tensor core aligns every addend to the accumulator's exponent and truncates, so small
+    // terms added onto the finished hi.hi sum would each lose their low bits (measured: 8.6e-6 instead of 3e-6 of the row scale)
+    const int nsteps = x3 ? 3 * nkb : nkb;
 
     if (tid == 0) {
         tc::mbar_init(bars + GB_WFULL, 1);
@@ -126,16 +132,19 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     if (warp == GT_EPI_WARPS) {
         // ---------------- TMA producer ----------------
         if (lane == 0) {
-            mbar_expect_tx(bars + GB_WFULL, (uint32_t)(nkb * bn * 128));
+            mbar_expect_tx(bars + GB_WFULL, (uint32_t)((x3 ? 2 : 1) * nkb * bn * 128));
             for (int kb = 0; kb < nkb; ++kb) tma_load_2d(tc::smem_u32(w_s) + (uint32_t)(kb * bn * 128), &wmap, 64 * kb, col0, bars + GB_WFULL);
+            if (x3)
+                for (int kb = 0; kb < nkb; ++kb) tma_load_2d(tc::smem_u32(w_s) + (uint32_t)((nkb + kb) * bn * 128), &wmap2, 64 * kb, col0, bars + GB_WFULL);
             uint32_t it = 0;
             for (int64_t mt = mt0; mt < m_tiles; mt += mt_step) {
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                for (int i = 0; i < nsteps; ++i, ++it) {
+                    const int seg = i / nkb, kb = i - seg * nkb;
                     const int s = (int)(it % GT_STAGES);
                     const uint32_t ph = (it / GT_STAGES) & 1u;
                     tc::mbar_wait(bars + GB_AEMPTY + s, ph ^ 1u);
                     mbar_expect_tx(bars + GB_AFULL + s, GT_A_BYTES);
-                    tma_load_2d(tc::smem_u32(a_s) + (uint32_t)(s * GT_A_BYTES), &amap, 64 * kb, (int)(mt * GT_M), bars + GB_AFULL + s);
+                    tma_load_2d(tc::smem_u32(a_s) + (uint32_t)(s * GT_A_BYTES), seg == 0 ? &amap2 : &amap, 64 * kb, (int)(mt * GT_M), bars + GB_AFULL + s);
                 }
             }
         }
@@ -150,15 +159,16 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                 const uint32_t acc = tile & 1u;
                 tc::mbar_wait(bars + GB_ACCEMPTY + acc, ((tile >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
                 tc::fence_after_sync();
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                for (int i = 0; i < nsteps; ++i, ++it) {
+                    const int seg = i / nkb, kb = i - seg * nkb;
                     const int s = (int)(it % GT_STAGES);
                     tc::mbar_wait(bars + GB_AFULL + s, (it / GT_STAGES) & 1u);
                     tc::fence_after_sync();
                     const uint64_t da = tc::smem_desc_sw128(tc::smem_u32(a_s) + (uint32_t)(s * GT_A_BYTES));
-                    const uint64_t db = tc::smem_desc_sw128(tc::smem_u32(w_s) + (uint32_t)(kb * bn * 128));
+                    const uint64_t db = tc::smem_desc_sw128(tc::smem_u32(w_s) + (uint32_t)((kb + (seg == 1 ? nkb : 0)) * bn * 128));
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        tc::mma_bf16(tmem + acc * 256u, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (kb | ks) != 0);
+                        tc::mma_bf16(tmem + acc * 256u, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (i | ks) != 0);
                     tc::mma_commit(bars + GB_AEMPTY + s);
                 }
                 tc::mma_commit(bars + GB_ACCFULL + acc);
@@ -506,11 +516,14 @@ int tensor_map_bf16_2d(CUtensorMap *out, const void *ptr, uint64_t cols, uint64_
 }  // namespace
 }  // namespace lime
 
-extern "C" int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, int64_t ldw, const float *bias,
-                                    const float *residual, int64_t ldr, void *C, int64_t ldc, int32_t c_is_bf16,
-                                    int64_t m, int32_t n, int32_t k, int32_t act, float alpha, int32_t ab_is_fp16, void *stream) {
+// A2 / W2 != NULL: the fp32x3 form (lime_linear_x3_tma), lo images of A and W beside the hi images
+static int linear_tma_launch(const void *A, const void *A2, int64_t lda, const void *W, const void *W2, int64_t ldw, const float *bias,
+                             const float *residual, int64_t ldr, void *C, int64_t ldc, int32_t c_is_bf16,
+                             int64_t m, int32_t n, int32_t k, int32_t act, float alpha, int32_t ab_is_fp16, void *stream) {
     using namespace lime;
-    LIME_CHECK_ARG(A && W && C, "lime_linear_bf16_tma: null argument");
+    const int x3 = A2 != nullptr;
+    LIME_CHECK_ARG(A && W && C && (A2 != nullptr) == (W2 != nullptr), "lime_linear_bf16_tma: null argument");
+    LIME_CHECK_ARG(!x3 || ((((uintptr_t)A2 | (uintptr_t)W2) & 15) == 0 && !c_is_bf16), "lime_linear_x3_tma: lo operands must be 16-byte aligned, output fp32");
     LIME_CHECK_ARG(k >= 64 && k % 64 == 0 && k <= 512, "lime_linear_bf16_tma: k=%d must be a multiple of 64 in [64, 512] (pad with zeros)", k);
     LIME_CHECK_ARG(n >= 1 && lda >= k && ldw >= k && lda % 8 == 0 && ldw % 8 == 0 && ldc >= n,
                    "lime_linear_bf16_tma: bad leading dimensions (lda %lld ldw %lld ldc %lld, n %d k %d)", (long long)lda,
@@ -527,16 +540,22 @@ extern "C" int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, i
     const int ncov = tma_epi && c_is_bf16 ? (int)ldc : n;          // stored width: a bf16 output includes its zero padding columns
     LIME_CHECK_ARG(ncov - n < 64, "lime_linear_bf16_tma: ldc %lld leaves more than 63 padding columns after n %d", (long long)ldc, n);
     // N tile: the widest multiple of 32 (<= 256) whose W slice fits the resident area, then balanced over the tiles
-    int bn_max = GT_W_MAX / (nkb * 128);
+    int bn_max = GT_W_MAX / ((x3 ? 2 : 1) * nkb * 128);
     bn_max = bn_max > 256 ? 256 : (bn_max / 32) * 32;
     const int gran = tma_epi && c_is_bf16 ? 64 : 32;              // bf16 boxes are 64 columns wide
     bn_max = bn_max / gran * gran;
     const int n_tiles = (ncov + bn_max - 1) / bn_max;
     int bn = (((ncov + n_tiles - 1) / n_tiles) + gran - 1) / gran * gran;
     LIME_CHECK_ARG(bn <= bn_max && n_tiles <= 64, "lime_linear_bf16_tma: n=%d does not tile", n);
-    CUtensorMap amap, wmap, cmap, rmap;
+    CUtensorMap amap, wmap, amap2, wmap2, cmap, rmap;
     if (int rc = tensor_map_bf16_2d(&amap, A, (uint64_t)k, (uint64_t)m, (uint64_t)lda, GT_M)) return rc;
     if (int rc = tensor_map_bf16_2d(&wmap, W, (uint64_t)k, (uint64_t)n, (uint64_t)ldw, (uint32_t)bn)) return rc;
+    amap2 = amap;
+    wmap2 = wmap;
+    if (x3) {
+        if (int rc = tensor_map_bf16_2d(&amap2, A2, (uint64_t)k, (uint64_t)m, (uint64_t)lda, GT_M)) return rc;
+        if (int rc = tensor_map_bf16_2d(&wmap2, W2, (uint64_t)k, (uint64_t)n, (uint64_t)ldw, (uint32_t)bn)) return rc;
+    }
     cmap = amap;
     rmap = amap;
     if (tma_epi) {
@@ -553,10 +572,26 @@ extern "C" int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, i
     int groups = num_sms() / n_tiles;
     if (groups < 1) groups = 1;
     if (groups > m_tiles) groups = (int)m_tiles;
-    gemm_tma_kernel<<<groups * n_tiles, GT_THREADS, GT_SMEM, as_stream(stream)>>>(amap, wmap, cmap, rmap, tma_epi ? 1 : 0, ncov, bias, residual, ldr,
+    gemm_tma_kernel<<<groups * n_tiles, GT_THREADS, GT_SMEM, as_stream(stream)>>>(amap, wmap, amap2, wmap2, x3, cmap, rmap, tma_epi ? 1 : 0, ncov, bias, residual, ldr,
                                                                                     C, ldc, c_is_bf16, m, n, nkb, bn, n_tiles, act, alpha, ab_is_fp16);
     LIME_LAUNCH_CHECK("gemm_tma_kernel");
     return 0;
+}
+
+extern "C" int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, int64_t ldw, const float *bias,
+                                    const float *residual, int64_t ldr, void *C, int64_t ldc, int32_t c_is_bf16,
+                                    int64_t m, int32_t n, int32_t k, int32_t act, float alpha, int32_t ab_is_fp16, void *stream) {
+    return linear_tma_launch(A, nullptr, lda, W, nullptr, ldw, bias, residual, ldr, C, ldc, c_is_bf16, m, n, k, act, alpha, ab_is_fp16, stream);
+}
+
+// fp32x3 dense layer in ONE launch: C = act(alpha (Alo Whi^T + Ahi Wlo^T + Ahi Whi^T) + bias [+ residual]) -- the three products
+// of the hi / lo operand pairs accumulate in the same TMEM tile (3 k / 64 K blocks), so the fp32 output is written once instead
+// of being re-read and re-written by two more accumulating passes.
+extern "C" int lime_linear_x3_tma(const void *Ahi, const void *Alo, int64_t lda, const void *Whi, const void *Wlo, int64_t ldw,
+                                  const float *bias, const float *residual, int64_t ldr, float *C, int64_t ldc,
+                                  int64_t m, int32_t n, int32_t k, int32_t act, float alpha, int32_t ab_is_fp16, void *stream) {
+    LIME_CHECK_ARG(Alo && Wlo, "lime_linear_x3_tma: null argument");
+    return linear_tma_launch(Ahi, Alo, lda, Whi, Wlo, ldw, bias, residual, ldr, C, ldc, 0, m, n, k, act, alpha, ab_is_fp16, stream);
 }
 
 // dW = dZ^T . X on bf16 images (see gemm_tn_tma_kernel): C[m, n] (+)= alpha * sum_{r < k} A[r, i] * B[r, j]

@@ -120,6 +120,7 @@ def cast_bf16(x, kp=None):
 
 
 X3_MAX_K = 512
+X3_FUSED = True       # linear_x3 as ONE lime_linear_x3_tma launch (False: three accumulating lime_linear_bf16_tma passes)
 X3_ACT_SCALE, X3_W_SCALE = 16.0, 1024.0      # fp16 pairs of the fp32x3 mode: activations * 2^4, weights * 2^10 (hi < 65504, lo out of the subnormals)
 
 
@@ -152,6 +153,22 @@ def linear_x3(xh, xl, wh, wl, bias=None, residual=None, act=ACT_NONE, out=None, 
             k1 = min(kp, k0 + X3_MAX_K)
             out = linear_x3(xh[:, k0:k1], xl[:, k0:k1], wh[:, k0:k1], wl[:, k0:k1], bias if k0 == 0 else None,
                             residual=residual if k0 == 0 else out, out=out, n=n, alpha=alpha)
+        return out
+    if X3_FUSED:                       # one launch: the three products accumulate in the same TMEM tile (lime_linear_x3_tma)
+        lib = _lib.require_device()
+        m = xh.shape[0]
+        if out is None:
+            out = torch.empty((m, n), dtype=torch.float32, device=xh.device)
+        if not (xh.dtype == xl.dtype == wh.dtype == wl.dtype) or xh.dtype not in (torch.bfloat16, torch.float16):
+            raise TypeError("operand pairs must all be bfloat16 or all float16")
+        lda, ldw = _rowmajor(xh, "xh"), _rowmajor(wh, "wh")
+        if _rowmajor(xl, "xl") != lda or _rowmajor(wl, "wl") != ldw or xl.shape != xh.shape or wl.shape != wh.shape:
+            raise ValueError("hi / lo images must share shape and row pitch")
+        ldr = _rowmajor(residual, "residual") if residual is not None else 0
+        check(lib.lime_linear_x3_tma(xh.data_ptr(), xl.data_ptr(), lda, wh.data_ptr(), wl.data_ptr(), ldw,
+                                     _ptr(bias, torch.float32, "bias"), _ptr(residual, torch.float32, "residual"), ldr,
+                                     _ptr(out, torch.float32, "out"), _rowmajor(out, "out"), m, n, kp, act, float(alpha),
+                                     1 if xh.dtype == torch.float16 else 0, _stream()), "lime_linear_x3_tma")
         return out
     out = linear_tma(xh, wh, None, residual=residual, out=out, n=n, out_bf16=False, alpha=alpha)
     linear_tma(xl, wh, None, residual=out, out=out, n=n, out_bf16=False, alpha=alpha)
