@@ -14,17 +14,23 @@ sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
 model = model.cuda().eval()
 news = synth.make_news_table(40, vocabulary_size=300, seed=1)
 imp = synth.make_impressions(3, news.news_num, cand_fixed=4, near_zero_frac=0.8, seed=2)
-want = O.score_pairs_reference_style(sd, news, imp, cfg, 8).numpy().astype(np.float64)
+want32 = O.score_pairs_reference_style(sd, news, imp, cfg, 8).numpy().astype(np.float64)
+want = O.score_pairs_reference_style(sd, news, imp, cfg, 8, dtype=torch.float64).double().numpy() if True else want32
+print("fp32 oracle vs fp64 oracle: mean %+.2e max %.2e" % ((want32 - want).mean(), np.abs(want32 - want).max()))
+from lime_cikm25_b200 import ops
 rows = {}
 with torch.no_grad():
-    for mode in ("ffma", "x3", "x3-ffma-mha"):
-        e = model.news_encoder.engine
-        e.x3 = mode.startswith("x3"); e.x3_mha = mode == "x3"
-        cache = util.build_news_cache(model, news)
-        got = util.score_impressions(model, cache, engine.DeviceImpressions(imp, "cuda"), 8).cpu().numpy().astype(np.float64)
-        d = got - want
-        print("%-12s score err: mean %+.2e  max|.| %.2e   (rms want %.2f)" % (mode, d.mean(), np.abs(d).max(), np.sqrt((want ** 2).mean())))
-        rows[mode] = (cache.hist_rows.double().cpu(), cache.cand_rows.double().cpu())
+    for mode in ("ffma", "x3"):
+        for smode in (ops.SCORE_AUTO, ops.SCORE_EXACT):
+            ops.score_configure(smode)
+            e = model.news_encoder.engine
+            e.x3 = mode.startswith("x3")
+            cache = util.build_news_cache(model, news)
+            got = util.score_impressions(model, cache, engine.DeviceImpressions(imp, "cuda"), 8).cpu().numpy().astype(np.float64)
+            d = got - want
+            print("%-5s scoring=%s  err vs fp64 oracle: mean %+.2e  max|.| %.2e   (rms want %.2f)" % (mode, "exact" if smode else "tc", d.mean(), np.abs(d).max(), np.sqrt((want ** 2).mean())))
+            rows[mode] = (cache.hist_rows.double().cpu(), cache.cand_rows.double().cpu())
+    ops.score_configure(ops.SCORE_AUTO)
     F = model.scoring.fold()
     G, Gg = F["G"].double().cpu(), F["Gg"].double().cpu()
     for mode in ("ffma", "x3"):
