@@ -659,16 +659,25 @@ mha_x3_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int
     const int g = lane >> 2, t2 = 2 * (lane & 3);
     const int64_t ld = 3 * (int64_t)d;
     const float *base = qkv + news * T * ld;
-    for (int idx = tid; idx < T * 32; idx += T) {
-        const int r = idx >> 5, e = idx & 31;
-        const bool ok = e < hd;
-        const float x[3] = {ok ? base[r * ld + head * hd + e] * scale : 0.0f, ok ? base[r * ld + d + head * hd + e] : 0.0f,
-                            ok ? base[r * ld + 2 * d + head * hd + e] : 0.0f};
+    // a head slice of a row is hd contiguous floats; with hd even and d * 4 a multiple of 8 every pair is an aligned float2
+    const bool vec2 = (hd & 1) == 0 && (d & 1) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 7) == 0;
+    for (int idx = tid; idx < T * 16; idx += T) {
+        const int r = idx >> 4, e = 2 * (idx & 15);
+        float2 x[3];
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
-            const __half h = __float2half_rn(x[m]);
-            tl[2 * m][r][e] = h;
-            tl[2 * m + 1][r][e] = __float2half_rn(x[m] - __half2float(h));
+            const float *src = base + r * ld + m * d + head * hd + e;
+            if (vec2 && e + 1 < hd) x[m] = __ldg(reinterpret_cast<const float2 *>(src));
+            else x[m] = make_float2(e < hd ? __ldg(src) : 0.0f, e + 1 < hd ? __ldg(src + 1) : 0.0f);
+        }
+        x[0].x *= scale;
+        x[0].y *= scale;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            uint32_t hi, lo;
+            split2_f16(x[m].x, x[m].y, hi, lo);
+            *reinterpret_cast<uint32_t *>(&tl[2 * m][r][e]) = hi;
+            *reinterpret_cast<uint32_t *>(&tl[2 * m + 1][r][e]) = lo;
         }
     }
     __syncthreads();
@@ -684,18 +693,23 @@ mha_x3_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int
             ldsm_x4(ql[ks], &tl[1][r0 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * ks + 8 * (lane >> 4)]);
         }
         float sacc[NT][4];
+        uint32_t kh[2][4], kl[2][4];                                       // the key fragments one tile ahead of their MMAs
+        ldsm_x4(kh[0], &tl[2][lane & 7][8 * (lane >> 3)]);
+        ldsm_x4(kl[0], &tl[3][lane & 7][8 * (lane >> 3)]);
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.0f;
-            uint32_t kh[4], kl[4];
-            ldsm_x4(kh, &tl[2][8 * j + (lane & 7)][8 * (lane >> 3)]);
-            ldsm_x4(kl, &tl[3][8 * j + (lane & 7)][8 * (lane >> 3)]);
-            mma_f16_16816(sacc[j], ql[0], kh[0], kh[1]);                   // the small terms first
-            mma_f16_16816(sacc[j], ql[1], kh[2], kh[3]);
-            mma_f16_16816(sacc[j], qh[0], kl[0], kl[1]);
-            mma_f16_16816(sacc[j], qh[1], kl[2], kl[3]);
-            mma_f16_16816(sacc[j], qh[0], kh[0], kh[1]);
-            mma_f16_16816(sacc[j], qh[1], kh[2], kh[3]);
+            if (j + 1 < NT) {
+                ldsm_x4(kh[(j + 1) & 1], &tl[2][8 * (j + 1) + (lane & 7)][8 * (lane >> 3)]);
+                ldsm_x4(kl[(j + 1) & 1], &tl[3][8 * (j + 1) + (lane & 7)][8 * (lane >> 3)]);
+            }
+            const uint32_t(&a)[4] = kh[j & 1], (&b)[4] = kl[j & 1];
+            mma_f16_16816(sacc[j], ql[0], a[0], a[1]);                     // the small terms first
+            mma_f16_16816(sacc[j], ql[1], a[2], a[3]);
+            mma_f16_16816(sacc[j], qh[0], b[0], b[1]);
+            mma_f16_16816(sacc[j], qh[1], b[2], b[3]);
+            mma_f16_16816(sacc[j], qh[0], a[0], a[1]);
+            mma_f16_16816(sacc[j], qh[1], a[2], a[3]);
         }
         float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
@@ -732,6 +746,9 @@ mha_x3_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int
         float oacc[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.0f;
+        uint32_t vh[2][4], vl[2][4];                                       // the value fragments one step (kk, jp) ahead
+        ldsm_x4_trans(vh[0], &tl[4][(lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]);
+        ldsm_x4_trans(vl[0], &tl[5][(lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]);
 #pragma unroll
         for (int kk = 0; kk < T / 16; ++kk) {
             uint32_t ph[4], pl[4];
@@ -741,15 +758,19 @@ mha_x3_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int
             split2_f16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3], ph[3], pl[3]);
 #pragma unroll
             for (int jp = 0; jp < 2; ++jp) {
-                uint32_t vh[4], vl[4];
-                ldsm_x4_trans(vh, &tl[4][16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
-                ldsm_x4_trans(vl, &tl[5][16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * jp + 8 * (lane >> 4)]);
-                mma_f16_16816(oacc[2 * jp], pl, vh[0], vh[1]);
-                mma_f16_16816(oacc[2 * jp + 1], pl, vh[2], vh[3]);
-                mma_f16_16816(oacc[2 * jp], ph, vl[0], vl[1]);
-                mma_f16_16816(oacc[2 * jp + 1], ph, vl[2], vl[3]);
-                mma_f16_16816(oacc[2 * jp], ph, vh[0], vh[1]);
-                mma_f16_16816(oacc[2 * jp + 1], ph, vh[2], vh[3]);
+                const int st = 2 * kk + jp;                                // step; the next one is (kk, 1) or (kk + 1, 0)
+                if (st + 1 < T / 8) {
+                    const int nk = (st + 1) >> 1, nj = (st + 1) & 1;
+                    ldsm_x4_trans(vh[(st + 1) & 1], &tl[4][16 * nk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * nj + 8 * (lane >> 4)]);
+                    ldsm_x4_trans(vl[(st + 1) & 1], &tl[5][16 * nk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * nj + 8 * (lane >> 4)]);
+                }
+                const uint32_t(&a)[4] = vh[st & 1], (&b)[4] = vl[st & 1];
+                mma_f16_16816(oacc[2 * jp], pl, a[0], a[1]);
+                mma_f16_16816(oacc[2 * jp + 1], pl, a[2], a[3]);
+                mma_f16_16816(oacc[2 * jp], ph, b[0], b[1]);
+                mma_f16_16816(oacc[2 * jp + 1], ph, b[2], b[3]);
+                mma_f16_16816(oacc[2 * jp], ph, a[0], a[1]);
+                mma_f16_16816(oacc[2 * jp + 1], ph, a[2], a[3]);
             }
         }
         const float i0 = 1.0f / l0, i1 = 1.0f / l1;
@@ -757,6 +778,11 @@ mha_x3_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = 8 * j + t2;
+            if (c + 1 < hd && vec2 && (reinterpret_cast<uintptr_t>(ctx) & 7) == 0) {          // one 8-byte store per row
+                *reinterpret_cast<float2 *>(o0 + c) = make_float2(oacc[j][0] * i0, oacc[j][1] * i0);
+                *reinterpret_cast<float2 *>(o1 + c) = make_float2(oacc[j][2] * i1, oacc[j][3] * i1);
+                continue;
+            }
             if (c < hd) {
                 o0[c] = oacc[j][0] * i0;
                 o1[c] = oacc[j][2] * i1;
