@@ -372,9 +372,12 @@ int lime_mha_fwd_bf16(const float *qkv, float *ctx, int64_t n_news, int T, int d
                       int64_t news0, void *stream);
 /* fp32x3 mode of lime_mha (Stage A, same arguments and layouts): q, k, v and the softmax weights as fp16 hi / lo pairs
  * (22 significant bits), each product three mma.sync m16n8k16 passes with fp32 accumulation -- fp32-level accuracy
- * on the tensor cores; replaces the FFMA core of newsEncoders.py:244-247's nn.MultiheadAttention in that mode. */
-int lime_mha_x3(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, float p_drop, uint64_t seed,
-                int64_t news0, void *stream);
+ * on the tensor cores; replaces the FFMA core of newsEncoders.py:244-247's nn.MultiheadAttention in that mode.
+ * ctx_hi / ctx_lo != NULL: the context is written as the fp16 pair out_scale * ctx = hi + lo, each [rows, ld16] with columns
+ * d..ld16-1 zero (the A operand of the out_proj lime_linear_x3_tma: no fp32 copy, no lime_split_bf16_pairs pass); ctx is
+ * then not written and may be NULL. */
+int lime_mha_x3(const float *qkv, float *ctx, void *ctx_hi, void *ctx_lo, int32_t ld16, float out_scale, int64_t n_news, int T,
+                int d, int nhead, float p_drop, uint64_t seed, int64_t news0, void *stream);
 /* bf16 mode of lime_mha_bwd: q, k, v, dO rounded to bf16, every product of the backward on the tensor cores (mma.sync
  * m16n8k16, fp32 accumulation), softmax statistics in fp32; same arguments and dropout mask. */
 int lime_mha_bwd_bf16(const float *qkv, const float *dctx, float *dqkv, int64_t n_news, int T, int d, int nhead,

@@ -97,7 +97,7 @@ PROTOTYPES = {
     "lime_scatter_add_rows_sorted": (C.c_int, [P, I64, P, P, I64, C.c_int, P, I64, I64, P]),
     "lime_mha_bwd": (C.c_int, [P, P, P, I64, C.c_int, C.c_int, C.c_int, F32, C.c_uint64, I64, P]),
     "lime_mha_fwd_bf16": (C.c_int, [P, P, I64, C.c_int, C.c_int, C.c_int, F32, C.c_uint64, I64, P]),
-    "lime_mha_x3": (C.c_int, [P, P, I64, C.c_int, C.c_int, C.c_int, F32, C.c_uint64, I64, P]),
+    "lime_mha_x3": (C.c_int, [P, P, P, P, I32, F32, I64, C.c_int, C.c_int, C.c_int, F32, C.c_uint64, I64, P]),
     "lime_mha_bwd_bf16": (C.c_int, [P, P, P, I64, C.c_int, C.c_int, C.c_int, F32, C.c_uint64, I64, P]),
     "lime_intent_pool_bwd": (C.c_int, [P, P, P, P, I64, P, P, P, I64, C.c_int, C.c_int, P]),
     "lime_content_fuse_bwd": (C.c_int, [P, P, P, I64, I64, C.c_int, P, P, P]),

@@ -646,8 +646,8 @@ __device__ __forceinline__ void split2_f16(float a, float b, uint32_t &hi, uint3
 
 template <int T>
 __global__ void __launch_bounds__(T)
-mha_x3_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int nhead, int hd, float scale, float p_drop,
-              uint64_t seed, int64_t news0) {
+mha_x3_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, __half *__restrict__ ctx_hi, __half *__restrict__ ctx_lo,
+              int ld16, float out_scale, int d, int nhead, int hd, float scale, float p_drop, uint64_t seed, int64_t news0) {
     constexpr int P = 40;
     constexpr int NT = T / 8;
     typedef __half Tile[T][P];
@@ -774,6 +774,43 @@ mha_x3_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d, int
             }
         }
         const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        if (ctx_hi != nullptr) {
+            // the context leaves as the next GEMM's operand pair: out_scale * ctx = hi + lo (fp16), no fp32 copy, no split pass
+            const int64_t p0 = (news * T + ra) * (int64_t)ld16 + head * hd, p1 = p0 + 8 * (int64_t)ld16;
+            const float s0 = i0 * out_scale, s1 = i1 * out_scale;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 8 * j + t2;
+                if (c + 1 < hd && ((ld16 | hd) & 1) == 0) {
+                    uint32_t hi, lo;
+                    split2_f16(oacc[j][0] * s0, oacc[j][1] * s0, hi, lo);
+                    *reinterpret_cast<uint32_t *>(ctx_hi + p0 + c) = hi;
+                    *reinterpret_cast<uint32_t *>(ctx_lo + p0 + c) = lo;
+                    split2_f16(oacc[j][2] * s1, oacc[j][3] * s1, hi, lo);
+                    *reinterpret_cast<uint32_t *>(ctx_hi + p1 + c) = hi;
+                    *reinterpret_cast<uint32_t *>(ctx_lo + p1 + c) = lo;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (c + e < hd) {
+                            const float xa = oacc[j][e] * s0, xb = oacc[j][2 + e] * s1;
+                            const __half ha = __float2half_rn(xa), hb = __float2half_rn(xb);
+                            ctx_hi[p0 + c + e] = ha;
+                            ctx_lo[p0 + c + e] = __float2half_rn(xa - __half2float(ha));
+                            ctx_hi[p1 + c + e] = hb;
+                            ctx_lo[p1 + c + e] = __float2half_rn(xb - __half2float(hb));
+                        }
+                    }
+                }
+            }
+            if (head == nhead - 1) {                             // zero K padding of the operand (columns d .. ld16 - 1)
+                for (int c = d + (lane & 3); c < ld16; c += 4) {
+                    const int64_t q0 = (news * T + ra) * (int64_t)ld16 + c, q1 = q0 + 8 * (int64_t)ld16;
+                    ctx_hi[q0] = ctx_lo[q0] = ctx_hi[q1] = ctx_lo[q1] = __float2half_rn(0.0f);
+                }
+            }
+            continue;
+        }
         float *o0 = ctx + (news * T + ra) * (int64_t)d + head * hd, *o1 = o0 + 8 * (int64_t)d;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -1152,9 +1189,11 @@ extern "C" int lime_mha(const float *qkv, float *ctx, int64_t n_news, int T, int
 }
 
 // fp32x3 mode of lime_mha: same arguments, fp16 hi / lo operand pairs on the tensor cores (mma.sync m16n8k16, 3 MMAs per product)
-extern "C" int lime_mha_x3(const float *qkv, float *ctx, int64_t n_news, int T, int d, int nhead, float p_drop, uint64_t seed,
-                           int64_t news0, void *stream) {
-    LIME_CHECK_ARG(qkv && ctx, "lime_mha_x3: null argument");
+extern "C" int lime_mha_x3(const float *qkv, float *ctx, void *ctx_hi, void *ctx_lo, int32_t ld16, float out_scale, int64_t n_news, int T,
+                           int d, int nhead, float p_drop, uint64_t seed, int64_t news0, void *stream) {
+    LIME_CHECK_ARG(qkv && (ctx || (ctx_hi && ctx_lo)), "lime_mha_x3: null argument");
+    LIME_CHECK_ARG(!ctx_hi || (ctx_lo && ld16 >= d && ((((uintptr_t)ctx_hi | (uintptr_t)ctx_lo) & 3) == 0)), "lime_mha_x3: pair output needs both images, ld16 >= d, 4-byte alignment");
+    __half *ch = reinterpret_cast<__half *>(ctx_hi), *cl = reinterpret_cast<__half *>(ctx_lo);
     LIME_CHECK_ARG((T == 32 || T == 128) && nhead > 0 && d % nhead == 0 && d / nhead <= 32, "lime_mha_x3: unsupported shape T=%d d=%d heads=%d", T, d, nhead);
     LIME_CHECK_ARG(n_news <= 65535, "lime_mha_x3: at most 65535 news per call (got %lld)", (long long)n_news);
     if (n_news <= 0) return 0;
@@ -1163,10 +1202,10 @@ extern "C" int lime_mha_x3(const float *qkv, float *ctx, int64_t n_news, int T, 
     dim3 grid(nhead, (unsigned)n_news);
     const int smem = 6 * T * 40 * (int)sizeof(__half);
     if (T == 32) {
-        mha_x3_kernel<32><<<grid, 32, smem, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale, p_drop, seed, news0);
+        mha_x3_kernel<32><<<grid, 32, smem, as_stream(stream)>>>(qkv, ctx, ch, cl, ld16, out_scale, d, nhead, hd, scale, p_drop, seed, news0);
     } else {
         LIME_CUDA(cudaFuncSetAttribute(mha_x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        mha_x3_kernel<128><<<grid, 128, smem, as_stream(stream)>>>(qkv, ctx, d, nhead, hd, scale, p_drop, seed, news0);
+        mha_x3_kernel<128><<<grid, 128, smem, as_stream(stream)>>>(qkv, ctx, ch, cl, ld16, out_scale, d, nhead, hd, scale, p_drop, seed, news0);
     }
     LIME_LAUNCH_CHECK("mha_x3_kernel");
     return 0;

@@ -201,10 +201,13 @@ class NewsEncoderEngine:
         xh, xl = ops.split16(x0, scale=sa)
         qkv = ops.linear_x3(xh, xl, W["in_w_hi"], W["in_w_lo"], W["in_b"], alpha=al)
         del xh, xl
-        ctx = torch.empty(rows, 300, dtype=torch.float32, device=dev)
-        ops.mha(qkv, ctx, n, T, 300, self.cfg.head_num, x3=self.x3_mha)
+        ctx = torch.empty(rows, 300, dtype=torch.float32, device=dev)       # (re-used below as the LayerNorm output)
+        if self.x3_mha:
+            ch, cl = ops.mha_x3_pairs(qkv, n, T, 300, self.cfg.head_num, sa)   # the context leaves as out_proj's operand pair
+        else:
+            ops.mha(qkv, ctx, n, T, 300, self.cfg.head_num)
+            ch, cl = ops.split16(ctx, scale=sa)
         del qkv
-        ch, cl = ops.split16(ctx, scale=sa)
         y = ops.linear_x3(ch, cl, W["out_w_hi"], W["out_w_lo"], W["out_b"], residual=x0, alpha=al)
         del ch, cl
         x1 = ops.layernorm(y, W["n1_w"], W["n1_b"], out=ctx, eps=W["eps1"])       # reuse ctx

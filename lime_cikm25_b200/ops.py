@@ -230,12 +230,30 @@ def mha(qkv, ctx, n_news, T, d, nhead, p_drop=0.0, seed=0, bf16=False, x3=False)
     """attention core; bf16: lime_mha_fwd_bf16 (tensor cores, q k v and P rounded to bf16), the training step's bf16 mode;
     x3: lime_mha_x3 (tensor cores on fp16 hi / lo pairs, fp32-level accuracy), Stage A's fp32x3 mode"""
     lib = _lib.require_device()
-    fn = lib.lime_mha_x3 if x3 else lib.lime_mha_fwd_bf16 if bf16 else lib.lime_mha
+    fn = lib.lime_mha_fwd_bf16 if bf16 else lib.lime_mha
     for lo in range(0, n_news, 65535):
         hi = min(n_news, lo + 65535)
-        check(fn(qkv[lo * T:].data_ptr(), ctx[lo * T:].data_ptr(), hi - lo, T, d, nhead, float(p_drop),
-                           int(seed) & (2 ** 64 - 1), lo, _stream()), "lime_mha")
+        if x3:
+            check(lib.lime_mha_x3(qkv[lo * T:].data_ptr(), ctx[lo * T:].data_ptr(), None, None, 0, 1.0, hi - lo, T, d, nhead,
+                                  float(p_drop), int(seed) & (2 ** 64 - 1), lo, _stream()), "lime_mha_x3")
+        else:
+            check(fn(qkv[lo * T:].data_ptr(), ctx[lo * T:].data_ptr(), hi - lo, T, d, nhead, float(p_drop),
+                     int(seed) & (2 ** 64 - 1), lo, _stream()), "lime_mha")
     return ctx
+
+
+def mha_x3_pairs(qkv, n_news, T, d, nhead, scale, kp=None):
+    """lime_mha_x3 with the context written as the fp16 operand pair scale * ctx = hi + lo, each [n_news * T, kp] (kp = d padded to
+    a multiple of 64, padding columns zero): the A operand of the out_proj linear_x3, no fp32 context and no split pass."""
+    lib = _lib.require_device()
+    kp = kp or (d + 63) // 64 * 64
+    hi16 = torch.empty(n_news * T, kp, dtype=torch.float16, device=qkv.device)
+    lo16 = torch.empty(n_news * T, kp, dtype=torch.float16, device=qkv.device)
+    for lo in range(0, n_news, 65535):
+        hi = min(n_news, lo + 65535)
+        check(lib.lime_mha_x3(_ptr(qkv, torch.float32, "qkv") + lo * T * qkv.stride(0) * 4, None, hi16[lo * T:].data_ptr(),
+                              lo16[lo * T:].data_ptr(), kp, float(scale), hi - lo, T, d, nhead, 0.0, 0, lo, _stream()), "lime_mha_x3")
+    return hi16, lo16
 
 
 def layernorm(x, gamma, beta, out, eps=1e-5):

@@ -201,6 +201,9 @@ def test_embed_pe_and_mha(lib, T):
     ctx3 = torch.full((n * T, d), float("nan"), device=DEV)
     ops.mha(qkv, ctx3, n, T, d, heads, x3=True)
     close(ctx3.view(n, T, d), (att @ v).transpose(1, 2).reshape(n, T, d), 1e-5)
+    ph, pl = ops.mha_x3_pairs(qkv, n, T, d, heads, 16.0)      # the same context as the next layer's fp16 operand pair
+    assert ph.shape == (n * T, 320) and float(ph[:, d:].float().abs().sum()) == 0 and float(pl[:, d:].float().abs().sum()) == 0
+    close((ph[:, :d].double() + pl[:, :d].double()).view(n, T, d) / 16.0, (att @ v).transpose(1, 2).reshape(n, T, d), 1e-5)
     big = qkv * 2.0                                          # sharper softmax (logits up to +-15), larger operands
     ops.mha(big, ctx3, n, T, d, heads, x3=True)
     q, k, v = big.double().view(n, T, 3, heads, d // heads).permute(2, 0, 3, 1, 4)
