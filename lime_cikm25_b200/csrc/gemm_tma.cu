@@ -103,11 +103,14 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     const int col0 = nt * bn;
     const int64_t m_tiles = (m + GT_M - 1) / GT_M;
     const int64_t mt0 = blockIdx.x / (unsigned)n_tiles, mt_step = gridDim.x / (unsigned)n_tiles;
-    // fp32x3 mode (x3 != 0): A = amap (hi) + amap2 (lo), W = wmap (hi) + wmap2 (lo); ONE accumulator takes the three products
-    // lo.hi + hi.lo + hi.hi as 3 nkb K blocks (K block i: segment i / nkb), both W images resident (slots 0..nkb-1 hi, nkb.. lo).
-    // The small products come FIRST: the tensor core aligns every addend to the accumulator's exponent and truncates, so small
-    // terms added onto the finished hi.hi sum would each lose their low bits (measured: 8.6e-6 instead of 3e-6 of the row scale)
-    const int nsteps = x3 ? 3 * nkb : nkb;
+    // fp32x3 mode (x3 != 0): A = amap (hi) + amap2 (lo), W = wmap (hi) + wmap2 (lo), both W images resident (slots 0..nkb-1 hi,
+    // nkb.. lo).  Per 64-wide K block the ring carries A_lo then A_hi (2 nkb steps per tile): A_lo feeds small += A_lo.W_hi,
+    // A_hi feeds small += A_hi.W_lo AND big += A_hi.W_hi -- every A image crosses the L2 -> shared-memory path once (with
+    // bn <= 128 the 8 CTAs of an M tile already read it at the L2's per-SM rate).  TWO accumulators per tile (bn <= 128: big at
+    // column 0, small at column 128 of the tile's 256-column half), summed by the epilogue: the tensor core aligns every addend to
+    // the accumulator's exponent and truncates, so small products added onto a running hi.hi sum lose their low bits
+    // (measured with one accumulator, hi.hi first: 8.6e-6 instead of 3e-6 of the row scale).
+    const int nsteps = x3 ? 2 * nkb : nkb;
 
     if (tid == 0) {
         tc::mbar_init(bars + GB_WFULL, 1);
@@ -139,12 +142,13 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
             uint32_t it = 0;
             for (int64_t mt = mt0; mt < m_tiles; mt += mt_step) {
                 for (int i = 0; i < nsteps; ++i, ++it) {
-                    const int seg = i / nkb, kb = i - seg * nkb;
+                    const int kb = x3 ? i >> 1 : i;
+                    const bool lo_img = x3 && (i & 1) == 0;
                     const int s = (int)(it % GT_STAGES);
                     const uint32_t ph = (it / GT_STAGES) & 1u;
                     tc::mbar_wait(bars + GB_AEMPTY + s, ph ^ 1u);
                     mbar_expect_tx(bars + GB_AFULL + s, GT_A_BYTES);
-                    tma_load_2d(tc::smem_u32(a_s) + (uint32_t)(s * GT_A_BYTES), seg == 0 ? &amap2 : &amap, 64 * kb, (int)(mt * GT_M), bars + GB_AFULL + s);
+                    tma_load_2d(tc::smem_u32(a_s) + (uint32_t)(s * GT_A_BYTES), lo_img ? &amap2 : &amap, 64 * kb, (int)(mt * GT_M), bars + GB_AFULL + s);
                 }
             }
         }
@@ -160,12 +164,29 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                 tc::mbar_wait(bars + GB_ACCEMPTY + acc, ((tile >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
                 tc::fence_after_sync();
                 for (int i = 0; i < nsteps; ++i, ++it) {
-                    const int seg = i / nkb, kb = i - seg * nkb;
+                    const int kb = x3 ? i >> 1 : i;
+                    const bool lo_img = x3 && (i & 1) == 0;
                     const int s = (int)(it % GT_STAGES);
                     tc::mbar_wait(bars + GB_AFULL + s, (it / GT_STAGES) & 1u);
                     tc::fence_after_sync();
                     const uint64_t da = tc::smem_desc_sw128(tc::smem_u32(a_s) + (uint32_t)(s * GT_A_BYTES));
-                    const uint64_t db = tc::smem_desc_sw128(tc::smem_u32(w_s) + (uint32_t)((kb + (seg == 1 ? nkb : 0)) * bn * 128));
+                    const uint64_t db = tc::smem_desc_sw128(tc::smem_u32(w_s) + (uint32_t)(kb * bn * 128));
+                    if (x3) {
+                        const uint64_t dbl = tc::smem_desc_sw128(tc::smem_u32(w_s) + (uint32_t)((nkb + kb) * bn * 128));
+                        if (lo_img) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                tc::mma_bf16(tmem + acc * 256u + 128u, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (kb | ks) != 0);
+                        } else {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                tc::mma_bf16(tmem + acc * 256u + 128u, da + (uint64_t)(2 * ks), dbl + (uint64_t)(2 * ks), idesc, true);
+                                tc::mma_bf16(tmem + acc * 256u, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (kb | ks) != 0);
+                            }
+                        }
+                        tc::mma_commit(bars + GB_AEMPTY + s);
+                        continue;
+                    }
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
                         tc::mma_bf16(tmem + acc * 256u, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (i | ks) != 0);
@@ -233,6 +254,12 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                     } else {
                         uint32_t v[32];
                         tmem_ld32(tlane + (uint32_t)c0, v);
+                        if (x3) {                                  // big + small accumulator
+                            uint32_t v2[32];
+                            tmem_ld32(tlane + 128u + (uint32_t)c0, v2);
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(v2[e]));
+                        }
                         if (residual != nullptr) {
                             tc::mbar_wait(rbar, res_it & 1u);
                             ++res_it;
@@ -280,6 +307,12 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
             for (int c0 = 32 * half; c0 < ncols; c0 += 8 * GT_EPI_WARPS) {
                 uint32_t v[32];
                 tmem_ld32(tlane + (uint32_t)c0, v);
+                if (x3) {                                          // big + small accumulator
+                    uint32_t v2[32];
+                    tmem_ld32(tlane + 128u + (uint32_t)c0, v2);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(v2[e]));
+                }
 #ifdef LIME_GT_NOSTORE           // timing diagnostic only (wrong results): the epilogue drains TMEM and stores nothing
                 if (v[0] == 0x7fc12345u && r < m) reinterpret_cast<float *>(Cout)[0] = 1.0f;
                 continue;
@@ -541,7 +574,7 @@ static int linear_tma_launch(const void *A, const void *A2, int64_t lda, const v
     LIME_CHECK_ARG(ncov - n < 64, "lime_linear_bf16_tma: ldc %lld leaves more than 63 padding columns after n %d", (long long)ldc, n);
     // N tile: the widest multiple of 32 (<= 256) whose W slice fits the resident area, then balanced over the tiles
     int bn_max = GT_W_MAX / ((x3 ? 2 : 1) * nkb * 128);
-    bn_max = bn_max > 256 ? 256 : (bn_max / 32) * 32;
+    bn_max = bn_max > (x3 ? 128 : 256) ? (x3 ? 128 : 256) : (bn_max / 32) * 32;      // x3: two accumulators share a 256-column half of TMEM
     const int gran = tma_epi && c_is_bf16 ? 64 : 32;              // bf16 boxes are 64 columns wide
     bn_max = bn_max / gran * gran;
     const int n_tiles = (ncov + bn_max - 1) / bn_max;
@@ -584,9 +617,9 @@ extern "C" int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, i
     return linear_tma_launch(A, nullptr, lda, W, nullptr, ldw, bias, residual, ldr, C, ldc, c_is_bf16, m, n, k, act, alpha, ab_is_fp16, stream);
 }
 
-// fp32x3 dense layer in ONE launch: C = act(alpha (Alo Whi^T + Ahi Wlo^T + Ahi Whi^T) + bias [+ residual]) -- the three products
-// of the hi / lo operand pairs accumulate in the same TMEM tile (3 k / 64 K blocks), so the fp32 output is written once instead
-// of being re-read and re-written by two more accumulating passes.
+// fp32x3 dense layer in ONE launch: C = act(alpha ((Alo Whi^T + Ahi Wlo^T) + Ahi Whi^T) + bias [+ residual]) -- the small products and
+// the hi.hi product accumulate in two TMEM tiles that the epilogue sums, so the fp32 output is written once instead of being
+// re-read and re-written by two more accumulating passes, and every A image is staged once per K block.
 extern "C" int lime_linear_x3_tma(const void *Ahi, const void *Alo, int64_t lda, const void *Whi, const void *Wlo, int64_t ldw,
                                   const float *bias, const float *residual, int64_t ldr, float *C, int64_t ldc,
                                   int64_t m, int32_t n, int32_t k, int32_t act, float alpha, int32_t ab_is_fp16, void *stream) {
