@@ -64,7 +64,7 @@ def _parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bf16-encoder", action="store_true", help="run the 4 transformer GEMMs on tcgen05 (bf16 mode)")
     ap.add_argument("--encoder", default=None, choices=["fp32", "fp32x3", "bf16"],
-                    help="Stage A mode of the scored cache: fp32 (FFMA, default), fp32x3 (3 bf16 tensor-core passes on hi/lo pairs), bf16")
+                    help="Stage A mode of the scored cache: fp32 (FFMA, default), fp32x3 (tensor cores on fp16 hi/lo pairs, fp32-level accuracy), bf16")
     ap.add_argument("--train-steps", type=int, default=4, help="timed training steps of the secondary train_step report (0 = skip)")
     ap.add_argument("--train-batch", type=int, default=32, help="samples per rank per training step (BASELINE.json configs[2])")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -346,12 +346,13 @@ def run_b200(args):
             if mode == enc_mode:
                 continue
             set_mode(mode)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            other = util.build_news_cache(model, news, dev)
-            torch.cuda.synchronize()
-            other_modes[mode] = time.perf_counter() - t0
-            del other
+            for rep in range(2):          # the second build is the reported one: the first pays one-time setup (allocator growth, tensor-map encoder)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                other = util.build_news_cache(model, news, dev)
+                torch.cuda.synchronize()
+                other_modes[mode] = time.perf_counter() - t0
+                del other
         set_mode(enc_mode)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -504,9 +505,10 @@ def run_b200(args):
                         "encoder": enc_mode,
                         "other_modes": {mode: {"seconds": sec, "news_per_sec": news.news_num / sec, "tflops": news.news_num * 241.3e6 / sec / 1e12}
                                         for mode, sec in other_modes.items()},
-                        "modes": "fp32 = FFMA kernels (reference-accurate default, 1e-4 vs the reference's vectors); fp32x3 = every transformer "
-                                 "GEMM as 3 bf16 tcgen05 passes on hi/lo pairs (2e-4); bf16 = bf16 activations, TMA + tcgen05 GEMMs, "
-                                 "tensor-core attention (metrics within 1e-3)"},
+                        "modes": "fp32 = FFMA kernels (reference-accurate default, 1e-4 vs the reference's vectors); fp32x3 = every dense layer "
+                                 "one tcgen05 launch on fp16 hi/lo pairs (lo.hi + hi.lo and hi.hi in two TMEM accumulators), attention on mma.sync "
+                                 "hi/lo pairs (vectors 3e-6 from the fp32 mode); bf16 = bf16 activations, TMA + tcgen05 GEMMs, tensor-core attention "
+                                 "(metrics within 1e-3); other_modes: second of two builds"},
         "metrics": {"auc": result[0] / result[4], "mrr": result[1] / result[4],
                     "ndcg5": result[2] / result[4], "ndcg10": result[3] / result[4]},
     }
