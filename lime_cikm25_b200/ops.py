@@ -121,6 +121,8 @@ def cast_bf16(x, kp=None):
 
 X3_MAX_K = 512
 X3_FUSED = True       # linear_x3 as ONE lime_linear_x3_tma launch (False: three accumulating lime_linear_bf16_tma passes)
+X3_FUSED_MAX_K = 320  # ... per 320-column slice of the contraction: both W images of a 128-column N tile stay resident (k = 512 in one
+                      # launch means 64-column tiles, 5 CTAs pulling every A tile through the L2 path)
 X3_ACT_SCALE, X3_W_SCALE = 16.0, 1024.0      # fp16 pairs of the fp32x3 mode: activations * 2^4, weights * 2^10 (hi < 65504, lo out of the subnormals)
 
 
@@ -147,10 +149,11 @@ def linear_x3(xh, xl, wh, wl, bias=None, residual=None, act=ACT_NONE, out=None, 
     assert act == ACT_NONE or residual is None
     n = wh.shape[0] if n is None else n
     kp = xh.shape[1]
-    if kp > X3_MAX_K:                  # contractions longer than one lime_linear_bf16_tma pass: accumulate 512-column slices in place
+    max_k = X3_FUSED_MAX_K if X3_FUSED and act == ACT_NONE else X3_MAX_K      # (a layer with an activation is one launch up to k = 512)
+    if kp > max_k:                     # longer contractions accumulate column slices in place (no activation then)
         assert act == ACT_NONE
-        for k0 in range(0, kp, X3_MAX_K):
-            k1 = min(kp, k0 + X3_MAX_K)
+        for k0 in range(0, kp, max_k):
+            k1 = min(kp, k0 + max_k)
             out = linear_x3(xh[:, k0:k1], xl[:, k0:k1], wh[:, k0:k1], wl[:, k0:k1], bias if k0 == 0 else None,
                             residual=residual if k0 == 0 else out, out=out, n=n, alpha=alpha)
         return out

@@ -132,7 +132,7 @@ def test_linear_x3_fp32_accurate(lib, m, n, k, fp16):
     z = a.double() @ w.double().t() + b.double()
     tol = 6e-6 if fp16 else 5e-5          # (fp16 pairs: the remaining error is the tensor core's own fp32 accumulation)
     close(ops.linear_x3(ah, al, wh, wl, b, residual=r, alpha=1.0 / (sa * sw)), z + r.double(), tol)
-    if k <= ops.X3_MAX_K:                 # longer contractions accumulate 512-column slices in place: no activation there
+    if k <= ops.X3_MAX_K:                 # longer contractions accumulate column slices in place: no activation there
         close(ops.linear_x3(ah, al, wh, wl, b, act=ops.ACT_RELU, alpha=1.0 / (sa * sw)), torch.relu(z), tol)
 
 
