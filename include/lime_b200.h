@@ -151,6 +151,13 @@ int lime_layernorm(const float *x, int64_t ldx, const float *gamma, const float 
 /* lime_layernorm with a second, bf16 image of every row: y16 [rows, ld16] (columns d..ld16-1 zero) */
 int lime_layernorm_bf16(const float *x, int64_t ldx, const float *gamma, const float *beta, float *y, int64_t ldy,
                         void *y16, int32_t ld16, int64_t rows, int d, float eps, void *stream);
+/* fp32x3-mode twins of lime_embed_pe_bf16 / lime_layernorm_bf16: beside the fp32 row, the fp16 operand PAIR scale * x = hi + lo
+ * (each [rows, ld16], columns d..ld16-1 zero) of the next lime_linear_x3_tma -- the producer writes it, no lime_split_bf16_pairs
+ * pass re-reads the row. */
+int lime_embed_pe_pairs(const float *E, int64_t vocab, const int32_t *ids, int64_t rows, int T, int d, const float *pe,
+                        float *out, void *hi16, void *lo16, int32_t ld16, float scale, void *stream);
+int lime_layernorm_pairs(const float *x, int64_t ldx, const float *gamma, const float *beta, float *y, int64_t ldy,
+                         void *hi16, void *lo16, int32_t ld16, float scale, int64_t rows, int d, float eps, void *stream);
 /* LayerNorm of every token followed by the unmasked mean over the T tokens of a news (:317,:321):
  * x [n_news*T, d] -> out[n, :d] (row stride ldo). */
 int lime_layernorm_meanpool(const float *x, const float *gamma, const float *beta, float *out,

@@ -57,6 +57,8 @@ PROTOTYPES = {
     "lime_cast_bf16_colsum": (C.c_int, [P, I64, I64, I32, P, I32, P, P]),
     "lime_embed_pe_bf16": (C.c_int, [P, I64, P, I64, C.c_int, C.c_int, P, P, P, I32, P]),
     "lime_mha_bf16": (C.c_int, [P, I64, P, I64, I64, C.c_int, C.c_int, C.c_int, P]),
+    "lime_embed_pe_pairs": (C.c_int, [P, I64, P, I64, C.c_int, C.c_int, P, P, P, P, I32, F32, P]),
+    "lime_layernorm_pairs": (C.c_int, [P, I64, P, P, P, I64, P, P, I32, F32, I64, C.c_int, F32, P]),
     "lime_layernorm_bf16": (C.c_int, [P, I64, P, P, P, I64, P, I32, I64, C.c_int, F32, P]),
     "lime_embed_pe": (C.c_int, [P, I64, P, I64, C.c_int, C.c_int, P, P, P]),
     "lime_mha": (C.c_int, [P, P, I64, C.c_int, C.c_int, C.c_int, F32, C.c_uint64, I64, P]),

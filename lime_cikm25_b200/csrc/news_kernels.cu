@@ -56,6 +56,39 @@ embed_pe_bf16_kernel(const float *__restrict__ E, int64_t vocab, const int32_t *
     *reinterpret_cast<uint2 *>(out16 + r * ld16 + 4 * q) = pk;
 }
 
+// the same with the fp16 operand PAIR of the fp32x3 mode beside the fp32 row: scale * x = hi + lo, each [rows, ld16], columns d.. zero
+__global__ void __launch_bounds__(256)
+embed_pe_pairs_kernel(const float *__restrict__ E, int64_t vocab, const int32_t *__restrict__ ids, int64_t rows, int T, int d4,
+                      const float *__restrict__ pe, float *__restrict__ out, __half *__restrict__ hi16, __half *__restrict__ lo16, int ld16,
+                      float scale) {
+    const int q4 = ld16 / 4;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * q4) return;
+    const int64_t r = idx / q4;
+    const int q = (int)(idx - r * q4);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < d4) {
+        int64_t id = ids[r];
+        id = (id < 0 || id >= vocab) ? 0 : id;
+        const float4 e = reinterpret_cast<const float4 *>(E)[id * d4 + q];
+        const float4 p = reinterpret_cast<const float4 *>(pe)[(r % T) * d4 + q];
+        o = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+        reinterpret_cast<float4 *>(out)[r * d4 + q] = o;
+    }
+    const float v[4] = {o.x * scale, o.y * scale, o.z * scale, o.w * scale};
+    uint32_t h[2], l[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+        h[e] = *reinterpret_cast<const uint32_t *>(&hh);
+        l[e] = *reinterpret_cast<const uint32_t *>(&ll);
+    }
+    *reinterpret_cast<uint2 *>(hi16 + r * ld16 + 4 * q) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2 *>(lo16 + r * ld16 + 4 * q) = make_uint2(l[0], l[1]);
+}
+
 // ---- multi-head self-attention core, no mask (nn.MultiheadAttention inside the encoder layer) ---
 // 128 threads: one query row per thread, G = 128/T heads of one news per block.  K and V of the
 // block's heads sit in shared memory (rows padded to 32 floats); every thread walks the same key j
@@ -895,6 +928,29 @@ layernorm_bf16_kernel(const float *__restrict__ x, int64_t ldx, const float *__r
     }
 }
 
+// ... and with the fp16 operand pair of the fp32x3 mode: scale * y = hi + lo, each [rows, ld16], columns d.. zero
+__global__ void __launch_bounds__(256)
+layernorm_pairs_kernel(const float *__restrict__ x, int64_t ldx, const float *__restrict__ gamma, const float *__restrict__ beta,
+                       float *__restrict__ y, int64_t ldy, __half *__restrict__ hi16, __half *__restrict__ lo16, int ld16, float scale,
+                       int64_t rows, int d, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    float o[kLnMaxPerLane];
+    ln_row(x + r * ldx, d, lane, eps, gamma, beta, o);
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        if (c < d) y[r * ldy + c] = o[i];
+        if (c < ld16) {
+            const float xs = c < d ? o[i] * scale : 0.0f;
+            const __half h = __float2half_rn(xs);
+            hi16[r * ld16 + c] = h;
+            lo16[r * ld16 + c] = __float2half_rn(xs - __half2float(h));
+        }
+    }
+}
+
 // LayerNorm of every token + unmasked mean over the T tokens (newsEncoders.py:317,321)
 __global__ void __launch_bounds__(256)
 layernorm_meanpool_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
@@ -1087,6 +1143,18 @@ extern "C" int lime_embed_pe_bf16(const float *E, int64_t vocab, const int32_t *
     return 0;
 }
 
+extern "C" int lime_embed_pe_pairs(const float *E, int64_t vocab, const int32_t *ids, int64_t rows, int T, int d, const float *pe,
+                                   float *out, void *hi16, void *lo16, int32_t ld16, float scale, void *stream) {
+    LIME_CHECK_ARG(E && ids && pe && out && hi16 && lo16, "lime_embed_pe_pairs: null argument");
+    LIME_CHECK_ARG((d & 3) == 0 && T > 0 && vocab > 0 && ld16 >= d && (ld16 & 7) == 0, "lime_embed_pe_pairs: d=%d ld16=%d", d, ld16);
+    if (rows <= 0) return 0;
+    const int64_t total = rows * (ld16 / 4);
+    embed_pe_pairs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+        E, vocab, ids, rows, T, d / 4, pe, out, reinterpret_cast<__half *>(hi16), reinterpret_cast<__half *>(lo16), ld16, scale);
+    LIME_LAUNCH_CHECK("embed_pe_pairs_kernel");
+    return 0;
+}
+
 // fp32 rows -> two 16-bit images hi = r16(s x), lo = r16(s x - hi) of [rows, ld16] (columns d.. zero): the operands of the
 // three-pass dense layer (x . w ~ xh . wh + xl . wh + xh . wl) of the fp32-accurate tensor-core mode.  fp16 pairs carry
 // 11 + 11 bits (2^-22 relative; s = a power of two that keeps the lo halves of typical values out of the subnormals), bf16
@@ -1254,6 +1322,17 @@ extern "C" int lime_layernorm_bf16(const float *x, int64_t ldx, const float *gam
     layernorm_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(x, ldx, gamma, beta, y, ldy,
                                                                                    reinterpret_cast<__nv_bfloat16 *>(y16), ld16, rows, d, eps);
     LIME_LAUNCH_CHECK("layernorm_bf16_kernel");
+    return 0;
+}
+
+extern "C" int lime_layernorm_pairs(const float *x, int64_t ldx, const float *gamma, const float *beta, float *y, int64_t ldy,
+                                    void *hi16, void *lo16, int32_t ld16, float scale, int64_t rows, int d, float eps, void *stream) {
+    LIME_CHECK_ARG(x && gamma && beta && y && hi16 && lo16, "lime_layernorm_pairs: null argument");
+    LIME_CHECK_ARG(d > 0 && d <= 32 * kLnMaxPerLane && ld16 >= d && ld16 <= 32 * kLnMaxPerLane, "lime_layernorm_pairs: d=%d ld16=%d unsupported (<= 512)", d, ld16);
+    if (rows <= 0) return 0;
+    layernorm_pairs_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(
+        x, ldx, gamma, beta, y, ldy, reinterpret_cast<__half *>(hi16), reinterpret_cast<__half *>(lo16), ld16, scale, rows, d, eps);
+    LIME_LAUNCH_CHECK("layernorm_pairs_kernel");
     return 0;
 }
 

@@ -196,9 +196,8 @@ class NewsEncoderEngine:
         dev = ids.device
         E = base.word_embedding.weight.detach()
         x0 = torch.empty(rows, 300, dtype=torch.float32, device=dev)
-        ops.embed_pe(E, ids, T, pe, x0)
         sa, al = ops.X3_ACT_SCALE, 1.0 / (ops.X3_ACT_SCALE * ops.X3_W_SCALE)
-        xh, xl = ops.split16(x0, scale=sa)
+        xh, xl = ops.embed_pe_pairs(E, ids.reshape(-1), T, pe, x0, sa)        # fp32 residual stream + the in_proj operand pair
         qkv = ops.linear_x3(xh, xl, W["in_w_hi"], W["in_w_lo"], W["in_b"], alpha=al)
         del xh, xl
         ctx = torch.empty(rows, 300, dtype=torch.float32, device=dev)       # (re-used below as the LayerNorm output)
@@ -210,8 +209,8 @@ class NewsEncoderEngine:
         del qkv
         y = ops.linear_x3(ch, cl, W["out_w_hi"], W["out_w_lo"], W["out_b"], residual=x0, alpha=al)
         del ch, cl
-        x1 = ops.layernorm(y, W["n1_w"], W["n1_b"], out=ctx, eps=W["eps1"])       # reuse ctx
-        xh, xl = ops.split16(x1, scale=sa)
+        x1 = ctx                                                                 # reuse ctx
+        xh, xl = ops.layernorm_pairs(y, W["n1_w"], W["n1_b"], x1, sa, eps=W["eps1"])   # fp32 residual stream + the FFN-1 operand pair
         hf = ops.linear_x3(xh, xl, W["l1_w_hi"], W["l1_w_lo"], W["l1_b"], act=ops.ACT_RELU, alpha=al)
         del xh, xl
         hh, hl = ops.split16(hf, scale=sa)

@@ -205,6 +205,32 @@ def layernorm_bf16(x, gamma, beta, out, out16, eps=1e-5):
     return out, out16
 
 
+def _pair_buffers(rows, d, device, kp=None):
+    kp = kp or (d + 63) // 64 * 64
+    return (torch.empty(rows, kp, dtype=torch.float16, device=device), torch.empty(rows, kp, dtype=torch.float16, device=device))
+
+
+def embed_pe_pairs(E, ids, T, pe, out, scale):
+    """embed_pe + the fp16 operand pair scale * out = hi + lo ([rows, kp], padding columns zero) of the fp32x3 mode."""
+    lib = _lib.require_device()
+    hi, lo = _pair_buffers(ids.numel(), E.shape[1], out.device)
+    check(lib.lime_embed_pe_pairs(_ptr(E, torch.float32, "E"), E.shape[0], _ptr(ids, torch.int32, "ids"), ids.numel(), T,
+                                  E.shape[1], _ptr(pe, torch.float32, "pe"), _ptr(out, torch.float32, "out"),
+                                  hi.data_ptr(), lo.data_ptr(), hi.shape[1], float(scale), _stream()), "lime_embed_pe_pairs")
+    return hi, lo
+
+
+def layernorm_pairs(x, gamma, beta, out, scale, eps=1e-5):
+    """layernorm + the fp16 operand pair scale * out = hi + lo ([rows, kp], padding columns zero) of the fp32x3 mode."""
+    lib = _lib.require_device()
+    hi, lo = _pair_buffers(x.shape[0], x.shape[1], x.device)
+    check(lib.lime_layernorm_pairs(_ptr(x, torch.float32, "x"), _rowmajor(x, "x"), _ptr(gamma, torch.float32, "gamma"),
+                                   _ptr(beta, torch.float32, "beta"), _ptr(out, torch.float32, "out"), _rowmajor(out, "out"),
+                                   hi.data_ptr(), lo.data_ptr(), hi.shape[1], float(scale), x.shape[0], x.shape[1], eps,
+                                   _stream()), "lime_layernorm_pairs")
+    return hi, lo
+
+
 def gemm_strided(a, b, alpha=1.0, out=None):
     """out = alpha * a @ b for arbitrary-stride 2-D views (weight folding only)."""
     lib = _lib.require_device()

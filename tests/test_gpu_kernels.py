@@ -211,6 +211,26 @@ def test_embed_pe_and_mha(lib, T):
     close(ctx3.view(n, T, d), (att @ v).transpose(1, 2).reshape(n, T, d), 1e-5)
 
 
+def test_pair_producers_match_split16(lib):
+    """fp32x3 mode: embed_pe_pairs / layernorm_pairs write the same fp32 rows as their plain twins and the same fp16 operand pair
+    (bit for bit) as lime_split_bf16_pairs of those rows."""
+    n, T, d, V = 5, 32, 300, 70
+    E = randn(V, d, seed=21, scale=0.3)
+    ids = torch.randint(0, V, (n, T), generator=gen(22)).to(torch.int32).to(DEV)
+    pe = O.positional_encoding(T, d, torch.float32).to(DEV)
+    x, x2 = torch.empty(n * T, d, device=DEV), torch.empty(n * T, d, device=DEV)
+    ops.embed_pe(E, ids, T, pe, x)
+    hi, lo = ops.embed_pe_pairs(E, ids.reshape(-1), T, pe, x2, ops.X3_ACT_SCALE)
+    wh, wl = ops.split16(x, scale=ops.X3_ACT_SCALE)
+    assert torch.equal(x, x2) and torch.equal(hi, wh) and torch.equal(lo, wl) and hi.shape == (n * T, 320)
+    g, b = randn(d, seed=23) * 0.1 + 1, randn(d, seed=24) * 0.1
+    y, y2 = torch.empty_like(x), torch.empty_like(x)
+    ops.layernorm(x, g, b, y)
+    hi, lo = ops.layernorm_pairs(x, g, b, y2, ops.X3_ACT_SCALE)
+    wh, wl = ops.split16(y, scale=ops.X3_ACT_SCALE)
+    assert torch.equal(y, y2) and torch.equal(hi, wh) and torch.equal(lo, wl)
+
+
 def test_layernorm_and_meanpool(lib):
     rows, d, T = 7 * 32, 300, 32
     x, g, b = randn(rows, d, seed=12) + 0.3, randn(d, seed=13) * 0.1 + 1, randn(d, seed=14) * 0.1
