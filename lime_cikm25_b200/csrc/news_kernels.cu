@@ -663,7 +663,8 @@ mha_fwd_tc_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d,
 // transformer sit well inside the fp16 range) and every product three MMAs: hi*hi + lo*hi + hi*lo, fp32 accumulation --
 // the dropped lo*lo term is 2^-22 of the product.  q is scaled by 1/sqrt(hd) in fp32 BEFORE the split, like mha_kernel.
 // The softmax weights p in [0, 1] are split the same way for O = P V.  Replaces the FFMA mha_kernel<T> in that mode
-// (22 % of its cache build).  Shared memory: six [T][40] fp16 tiles (61,440 B at T = 128: dynamic).
+// (22 % of its cache build).  Shared memory: four [T][40] fp16 tiles (K, V hi / lo: 40,960 B at T = 128) and 128 registers, so
+// that FOUR CTAs of 4 warps share an SM (the kernel is latency bound: ldmatrix -> mma chains at 12 warps per SM before).
 __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -678,14 +679,14 @@ __device__ __forceinline__ void split2_f16(float a, float b, uint32_t &hi, uint3
 }
 
 template <int T>
-__global__ void __launch_bounds__(T)
+__global__ void __launch_bounds__(T, T == 128 ? 4 : 1)
 mha_x3_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, __half *__restrict__ ctx_hi, __half *__restrict__ ctx_lo,
               int ld16, float out_scale, int d, int nhead, int hd, float scale, float p_drop, uint64_t seed, int64_t news0) {
     constexpr int P = 40;
     constexpr int NT = T / 8;
     typedef __half Tile[T][P];
     extern __shared__ __align__(16) unsigned char mhax_smem[];
-    Tile *tl = reinterpret_cast<Tile *>(mhax_smem);             // Qhi Qlo Khi Klo Vhi Vlo
+    Tile *tl = reinterpret_cast<Tile *>(mhax_smem);             // Khi Klo Vhi Vlo (the query fragments come straight from global memory)
     const int64_t news = blockIdx.y;
     const int head = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -694,23 +695,33 @@ mha_x3_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, __half *__
     const float *base = qkv + news * T * ld;
     // a head slice of a row is hd contiguous floats; with hd even and d * 4 a multiple of 8 every pair is an aligned float2
     const bool vec2 = (hd & 1) == 0 && (d & 1) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 7) == 0;
-    for (int idx = tid; idx < T * 16; idx += T) {
-        const int r = idx >> 4, e = 2 * (idx & 15);
-        float2 x[3];
+    // T * 16 column pairs per matrix, 16 per thread: the loads of 8 pairs (K and V: 16 x 8 bytes in flight per thread) are issued
+    // before the first split / store -- the kernel is bound by the latency of this prologue (ncu: 57 % of the stall samples on its loads)
 #pragma unroll
-        for (int m = 0; m < 3; ++m) {
-            const float *src = base + r * ld + m * d + head * hd + e;
-            if (vec2 && e + 1 < hd) x[m] = __ldg(reinterpret_cast<const float2 *>(src));
-            else x[m] = make_float2(e < hd ? __ldg(src) : 0.0f, e + 1 < hd ? __ldg(src + 1) : 0.0f);
+    for (int b = 0; b < 2; ++b) {
+        float2 x[8][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + (8 * b + i) * T;
+            const int r = idx >> 4, e = 2 * (idx & 15);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const float *src = base + r * ld + (m + 1) * d + head * hd + e;
+                if (vec2 && e + 1 < hd) x[i][m] = __ldg(reinterpret_cast<const float2 *>(src));
+                else x[i][m] = make_float2(e < hd ? __ldg(src) : 0.0f, e + 1 < hd ? __ldg(src + 1) : 0.0f);
+            }
         }
-        x[0].x *= scale;
-        x[0].y *= scale;
 #pragma unroll
-        for (int m = 0; m < 3; ++m) {
-            uint32_t hi, lo;
-            split2_f16(x[m].x, x[m].y, hi, lo);
-            *reinterpret_cast<uint32_t *>(&tl[2 * m][r][e]) = hi;
-            *reinterpret_cast<uint32_t *>(&tl[2 * m + 1][r][e]) = lo;
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + (8 * b + i) * T;
+            const int r = idx >> 4, e = 2 * (idx & 15);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                uint32_t hi, lo;
+                split2_f16(x[i][m].x, x[i][m].y, hi, lo);
+                *reinterpret_cast<uint32_t *>(&tl[2 * m][r][e]) = hi;
+                *reinterpret_cast<uint32_t *>(&tl[2 * m + 1][r][e]) = lo;
+            }
         }
     }
     __syncthreads();
@@ -719,22 +730,30 @@ mha_x3_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, __half *__
 #pragma unroll 1
     for (int mb = 0; mb < 2; ++mb) {
         const int r0 = 32 * warp + 16 * mb;
+        // A fragments of m16n8k16: a0 = (row g, cols t2..), a1 = (row g + 8, same), a2 / a3 = the same rows, cols + 8
         uint32_t qh[2][4], ql[2][4];
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-            ldsm_x4(qh[ks], &tl[0][r0 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * ks + 8 * (lane >> 4)]);
-            ldsm_x4(ql[ks], &tl[1][r0 + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * ks + 8 * (lane >> 4)]);
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const int row = r0 + g + 8 * (f & 1), col = 16 * ks + t2 + 8 * (f >> 1);
+                const float *src = base + row * ld + head * hd + col;
+                float2 q;
+                if (vec2 && col + 1 < hd) q = __ldg(reinterpret_cast<const float2 *>(src));
+                else q = make_float2(col < hd ? __ldg(src) : 0.0f, col + 1 < hd ? __ldg(src + 1) : 0.0f);
+                split2_f16(q.x * scale, q.y * scale, qh[ks][f], ql[ks][f]);
+            }
         }
         float sacc[NT][4];
         uint32_t kh[2][4], kl[2][4];                                       // the key fragments one tile ahead of their MMAs
-        ldsm_x4(kh[0], &tl[2][lane & 7][8 * (lane >> 3)]);
-        ldsm_x4(kl[0], &tl[3][lane & 7][8 * (lane >> 3)]);
+        ldsm_x4(kh[0], &tl[0][lane & 7][8 * (lane >> 3)]);
+        ldsm_x4(kl[0], &tl[1][lane & 7][8 * (lane >> 3)]);
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.0f;
             if (j + 1 < NT) {
-                ldsm_x4(kh[(j + 1) & 1], &tl[2][8 * (j + 1) + (lane & 7)][8 * (lane >> 3)]);
-                ldsm_x4(kl[(j + 1) & 1], &tl[3][8 * (j + 1) + (lane & 7)][8 * (lane >> 3)]);
+                ldsm_x4(kh[(j + 1) & 1], &tl[0][8 * (j + 1) + (lane & 7)][8 * (lane >> 3)]);
+                ldsm_x4(kl[(j + 1) & 1], &tl[1][8 * (j + 1) + (lane & 7)][8 * (lane >> 3)]);
             }
             const uint32_t(&a)[4] = kh[j & 1], (&b)[4] = kl[j & 1];
             mma_f16_16816(sacc[j], ql[0], a[0], a[1]);                     // the small terms first
@@ -780,8 +799,8 @@ mha_x3_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, __half *__
 #pragma unroll
         for (int j = 0; j < 4; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.0f;
         uint32_t vh[2][4], vl[2][4];                                       // the value fragments one step (kk, jp) ahead
-        ldsm_x4_trans(vh[0], &tl[4][(lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]);
-        ldsm_x4_trans(vl[0], &tl[5][(lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]);
+        ldsm_x4_trans(vh[0], &tl[2][(lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]);
+        ldsm_x4_trans(vl[0], &tl[3][(lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]);
 #pragma unroll
         for (int kk = 0; kk < T / 16; ++kk) {
             uint32_t ph[4], pl[4];
@@ -794,8 +813,8 @@ mha_x3_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, __half *__
                 const int st = 2 * kk + jp;                                // step; the next one is (kk, 1) or (kk + 1, 0)
                 if (st + 1 < T / 8) {
                     const int nk = (st + 1) >> 1, nj = (st + 1) & 1;
-                    ldsm_x4_trans(vh[(st + 1) & 1], &tl[4][16 * nk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * nj + 8 * (lane >> 4)]);
-                    ldsm_x4_trans(vl[(st + 1) & 1], &tl[5][16 * nk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * nj + 8 * (lane >> 4)]);
+                    ldsm_x4_trans(vh[(st + 1) & 1], &tl[2][16 * nk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * nj + 8 * (lane >> 4)]);
+                    ldsm_x4_trans(vl[(st + 1) & 1], &tl[3][16 * nk + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * nj + 8 * (lane >> 4)]);
                 }
                 const uint32_t(&a)[4] = vh[st & 1], (&b)[4] = vl[st & 1];
                 mma_f16_16816(oacc[2 * jp], pl, a[0], a[1]);
@@ -1268,7 +1287,7 @@ extern "C" int lime_mha_x3(const float *qkv, float *ctx, void *ctx_hi, void *ctx
     const int hd = d / nhead;
     const float scale = 1.0f / sqrtf((float)hd);
     dim3 grid(nhead, (unsigned)n_news);
-    const int smem = 6 * T * 40 * (int)sizeof(__half);
+    const int smem = 4 * T * 40 * (int)sizeof(__half);
     if (T == 32) {
         mha_x3_kernel<32><<<grid, 32, smem, as_stream(stream)>>>(qkv, ctx, ch, cl, ld16, out_scale, d, nhead, hd, scale, p_drop, seed, news0);
     } else {
