@@ -370,13 +370,33 @@ mha_bwd_tc_kernel(const float *__restrict__ qkv, const float *__restrict__ dctx,
     const int g = lane >> 2, t2 = 2 * (lane & 3);
     const int64_t ld = 3 * (int64_t)d;
     const float *base = qkv + news * T * ld;
-    for (int idx = tid; idx < T * 32; idx += T) {
-        const int r = idx >> 5, e = idx & 31;
-        const bool ok = e < hd;
-        Qs[r][e] = __float2bfloat16_rn(ok ? base[r * ld + head * hd + e] : 0.0f);
-        Ks[r][e] = __float2bfloat16_rn(ok ? base[r * ld + d + head * hd + e] : 0.0f);
-        Vs[r][e] = __float2bfloat16_rn(ok ? base[r * ld + 2 * d + head * hd + e] : 0.0f);
-        Os[r][e] = __float2bfloat16_rn(ok ? dctx[(news * T + r) * (int64_t)d + head * hd + e] : 0.0f);
+    // T * 16 column pairs per matrix, 16 per thread, loaded 8 at a time (32 x 8 bytes in flight per thread) before the first
+    // conversion: the prologue's load latency is what bounds these one-(news, head)-per-CTA kernels (ncu on mha_x3_kernel)
+    const bool vec2 = (hd & 1) == 0 && (d & 1) == 0 && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dctx)) & 7) == 0;
+    const float *dbase = dctx + news * T * (int64_t)d;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        float2 x[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + (8 * b + i) * T;
+            const int r = idx >> 4, e = 2 * (idx & 15);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const float *src = m < 3 ? base + r * ld + m * d + head * hd + e : dbase + r * (int64_t)d + head * hd + e;
+                if (vec2 && e + 1 < hd) x[i][m] = __ldg(reinterpret_cast<const float2 *>(src));
+                else x[i][m] = make_float2(e < hd ? __ldg(src) : 0.0f, e + 1 < hd ? __ldg(src + 1) : 0.0f);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + (8 * b + i) * T;
+            const int r = idx >> 4, e = 2 * (idx & 15);
+            *reinterpret_cast<uint32_t *>(&Qs[r][e]) = pack2_bf16(x[i][0].x, x[i][0].y);
+            *reinterpret_cast<uint32_t *>(&Ks[r][e]) = pack2_bf16(x[i][1].x, x[i][1].y);
+            *reinterpret_cast<uint32_t *>(&Vs[r][e]) = pack2_bf16(x[i][2].x, x[i][2].y);
+            *reinterpret_cast<uint32_t *>(&Os[r][e]) = pack2_bf16(x[i][3].x, x[i][3].y);
+        }
     }
     __syncthreads();
     const uint64_t drop_nh = ((uint64_t)(news0 + news) * nhead + head) * T;
@@ -566,12 +586,30 @@ mha_fwd_tc_kernel(const float *__restrict__ qkv, float *__restrict__ ctx, int d,
     const int g = lane >> 2, t2 = 2 * (lane & 3);
     const int64_t ld = 3 * (int64_t)d;
     const float *base = qkv + news * T * ld;
-    for (int idx = tid; idx < T * 32; idx += T) {
-        const int r = idx >> 5, e = idx & 31;
-        const bool ok = e < hd;
-        Qs[r][e] = __float2bfloat16_rn(ok ? base[r * ld + head * hd + e] : 0.0f);
-        Ks[r][e] = __float2bfloat16_rn(ok ? base[r * ld + d + head * hd + e] : 0.0f);
-        Vs[r][e] = __float2bfloat16_rn(ok ? base[r * ld + 2 * d + head * hd + e] : 0.0f);
+    // T * 16 column pairs per matrix, 16 per thread, loaded 8 at a time before the first conversion (see mha_bwd_tc_kernel)
+    const bool vec2 = (hd & 1) == 0 && (d & 1) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 7) == 0;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        float2 x[8][3];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + (8 * b + i) * T;
+            const int r = idx >> 4, e = 2 * (idx & 15);
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const float *src = base + r * ld + m * d + head * hd + e;
+                if (vec2 && e + 1 < hd) x[i][m] = __ldg(reinterpret_cast<const float2 *>(src));
+                else x[i][m] = make_float2(e < hd ? __ldg(src) : 0.0f, e + 1 < hd ? __ldg(src + 1) : 0.0f);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + (8 * b + i) * T;
+            const int r = idx >> 4, e = 2 * (idx & 15);
+            *reinterpret_cast<uint32_t *>(&Qs[r][e]) = pack2_bf16(x[i][0].x, x[i][0].y);
+            *reinterpret_cast<uint32_t *>(&Ks[r][e]) = pack2_bf16(x[i][1].x, x[i][1].y);
+            *reinterpret_cast<uint32_t *>(&Vs[r][e]) = pack2_bf16(x[i][2].x, x[i][2].y);
+        }
     }
     __syncthreads();
     const uint64_t drop_nh = ((uint64_t)(news0 + news) * nhead + head) * T;
