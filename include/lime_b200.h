@@ -108,6 +108,12 @@ int lime_linear_bf16_tma(const void *A, int64_t lda, const void *W, int64_t ldw,
 int lime_linear_x3_tma(const void *Ahi, const void *Alo, int64_t lda, const void *Whi, const void *Wlo, int64_t ldw,
                        const float *bias, const float *residual, int64_t ldr, float *C, int64_t ldc, int64_t m, int32_t n,
                        int32_t k, int32_t act, float alpha, int32_t ab_is_fp16, void *stream);
+/* The same layer with the result leaving as the NEXT fp32x3 layer's operand pair: out_scale * act(alpha (...) + bias) = hi + lo
+ * (fp16, each [m, ld16], ld16 a multiple of 8, columns n..ld16-1 zero) -- the FFN hidden layer of newsEncoders.py:244-247 never
+ * exists as an fp32 matrix and no lime_split_bf16_pairs pass re-reads it.  No residual. */
+int lime_linear_x3_pairs_tma(const void *Ahi, const void *Alo, int64_t lda, const void *Whi, const void *Wlo, int64_t ldw,
+                             const float *bias, void *Chi, void *Clo, int64_t ld16, float out_scale, int64_t m, int32_t n,
+                             int32_t k, int32_t act, float alpha, int32_t ab_is_fp16, void *stream);
 /* fp32 rows -> 16-bit pair hi = r16(scale x), lo = r16(scale x - hi), each [rows, ld16] with columns d..ld16-1 zero; fp16 pairs
  * (as_fp16 != 0: scale x = hi + lo to 2^-22, scale a power of two that keeps hi below 65504) or bf16 pairs (2^-17).
  * With the same split of W, x . W^T ~ xh . Wh^T + xl . Wh^T + xh . Wl^T reproduces the fp32 product on the tensor cores

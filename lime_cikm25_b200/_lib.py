@@ -52,6 +52,7 @@ PROTOTYPES = {
     "lime_linear_bf16": (C.c_int, _LINEAR),
     "lime_gemm_strided": (C.c_int, [P, I64, I64, P, I64, I64, P, I64, C.c_int, C.c_int, C.c_int, F32, P]),
     "lime_linear_x3_tma": (C.c_int, [P, P, I64, P, P, I64, P, P, I64, P, I64, I64, I32, I32, I32, F32, I32, P]),
+    "lime_linear_x3_pairs_tma": (C.c_int, [P, P, I64, P, P, I64, P, P, P, I64, F32, I64, I32, I32, I32, F32, I32, P]),
     "lime_linear_bf16_tma": (C.c_int, [P, I64, P, I64, P, P, I64, P, I64, I32, I64, I32, I32, I32, F32, I32, P]),
     "lime_split_bf16_pairs": (C.c_int, [P, I64, I64, I32, P, P, I32, F32, I32, P]),
     "lime_cast_bf16_colsum": (C.c_int, [P, I64, I64, I32, P, I32, P, P]),

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <mutex>
 
@@ -83,7 +84,8 @@ static_assert(GB_COUNT * 8 + 8 <= 256, "barrier area");
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap,
                 const __grid_constant__ CUtensorMap amap2, const __grid_constant__ CUtensorMap wmap2, int x3,
-                const __grid_constant__ CUtensorMap cmap, const __grid_constant__ CUtensorMap rmap, int tma_epilogue, int ncov,
+                const __grid_constant__ CUtensorMap cmap, const __grid_constant__ CUtensorMap cmap2, float out_scale,
+                const __grid_constant__ CUtensorMap rmap, int tma_epilogue, int ncov,
                 const float *__restrict__ bias, const float *__restrict__ residual, int64_t ldr, void *__restrict__ Cout,
                 int64_t ldc, int c_bf16, int64_t m, int n, int nkb, int bn, int n_tiles, int act, float alpha, int ab_fp16) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -234,7 +236,52 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                         waited = true;
                     }
                     // 128-byte rows, SWIZZLE_128B: 16-byte unit u of row r at position u ^ (r & 7)
-                    if (c_bf16) {
+                    const CUtensorMap *smap = &cmap;
+                    if (c_bf16 == 2) {
+                        // fp16 PAIR output (the next fp32x3 layer's operand): out_scale * y = hi + lo, hi through cmap, lo through cmap2.
+                        // One staging tile: the hi image is handed to the TMA unit, then the tile is refilled with the lo image
+                        // (TMEM is simply read again).
+#pragma unroll 1
+                        for (int img = 0; img < 2; ++img) {
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                uint32_t v[32];
+                                tmem_ld32(tlane + (uint32_t)(c0 + 32 * hh), v);
+                                if (x3) {
+                                    uint32_t v2[32];
+                                    tmem_ld32(tlane + 128u + (uint32_t)(c0 + 32 * hh), v2);
+#pragma unroll
+                                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(v2[e]));
+                                }
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    uint32_t o[4];
+#pragma unroll
+                                    for (int e2 = 0; e2 < 4; ++e2) {
+                                        const int c = 8 * u + 2 * e2;
+                                        const float ya = act_apply(act, fmaf(alpha, __uint_as_float(v[c]), bias_s[c0 + 32 * hh + c])) * out_scale;
+                                        const float yb = act_apply(act, fmaf(alpha, __uint_as_float(v[c + 1]), bias_s[c0 + 32 * hh + c + 1])) * out_scale;
+                                        const __half2 h2 = __floats2half2_rn(ya, yb);
+                                        const float2 hf = __half22float2(h2);
+                                        const __half2 l2 = __floats2half2_rn(ya - hf.x, yb - hf.y);
+                                        o[e2] = img == 0 ? *reinterpret_cast<const uint32_t *>(&h2) : *reinterpret_cast<const uint32_t *>(&l2);
+                                    }
+                                    *reinterpret_cast<uint4 *>(buf + lane * 128 + 16 * ((4 * hh + u) ^ (lane & 7))) = make_uint4(o[0], o[1], o[2], o[3]);
+                                }
+                            }
+                            if (img == 0) {
+                                tc::fence_proxy_async_smem();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    tma_store_2d(&cmap, col0 + c0, row0, tc::smem_u32(buf));
+                                    bulk_commit();
+                                    bulk_wait_read<0>();           // the tile is refilled with the lo image
+                                }
+                                __syncwarp();
+                            }
+                        }
+                        smap = &cmap2;
+                    } else if (c_bf16) {
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {           // bn is a multiple of 64 here: both halves are columns of this tile
                             uint32_t v[32];
@@ -281,7 +328,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                     tc::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&cmap, col0 + c0, row0, tc::smem_u32(buf));
+                        tma_store_2d(smap, col0 + c0, row0, tc::smem_u32(buf));
                         bulk_commit();
                     }
                 }
@@ -550,13 +597,16 @@ int tensor_map_bf16_2d(CUtensorMap *out, const void *ptr, uint64_t cols, uint64_
 }  // namespace lime
 
 // A2 / W2 != NULL: the fp32x3 form (lime_linear_x3_tma), lo images of A and W beside the hi images
+// c_is_bf16 == 2: fp16 pair output (C = hi image, C2 = lo image, out_scale), the x3 form only
 static int linear_tma_launch(const void *A, const void *A2, int64_t lda, const void *W, const void *W2, int64_t ldw, const float *bias,
                              const float *residual, int64_t ldr, void *C, int64_t ldc, int32_t c_is_bf16,
-                             int64_t m, int32_t n, int32_t k, int32_t act, float alpha, int32_t ab_is_fp16, void *stream) {
+                             int64_t m, int32_t n, int32_t k, int32_t act, float alpha, int32_t ab_is_fp16, void *stream,
+                             void *C2 = nullptr, float out_scale = 1.0f) {
     using namespace lime;
     const int x3 = A2 != nullptr;
     LIME_CHECK_ARG(A && W && C && (A2 != nullptr) == (W2 != nullptr), "lime_linear_bf16_tma: null argument");
-    LIME_CHECK_ARG(!x3 || ((((uintptr_t)A2 | (uintptr_t)W2) & 15) == 0 && !c_is_bf16), "lime_linear_x3_tma: lo operands must be 16-byte aligned, output fp32");
+    LIME_CHECK_ARG(!x3 || ((((uintptr_t)A2 | (uintptr_t)W2) & 15) == 0 && c_is_bf16 != 1), "lime_linear_x3_tma: lo operands must be 16-byte aligned, output fp32");
+    LIME_CHECK_ARG(c_is_bf16 != 2 || (x3 && C2 != nullptr && residual == nullptr && ((uintptr_t)C2 & 15) == 0), "lime_linear_x3_pairs_tma: needs the x3 form, both images 16-byte aligned, no residual");
     LIME_CHECK_ARG(k >= 64 && k % 64 == 0 && k <= 512, "lime_linear_bf16_tma: k=%d must be a multiple of 64 in [64, 512] (pad with zeros)", k);
     LIME_CHECK_ARG(n >= 1 && lda >= k && ldw >= k && lda % 8 == 0 && ldw % 8 == 0 && ldc >= n,
                    "lime_linear_bf16_tma: bad leading dimensions (lda %lld ldw %lld ldc %lld, n %d k %d)", (long long)lda,
@@ -580,7 +630,8 @@ static int linear_tma_launch(const void *A, const void *A2, int64_t lda, const v
     const int n_tiles = (ncov + bn_max - 1) / bn_max;
     int bn = (((ncov + n_tiles - 1) / n_tiles) + gran - 1) / gran * gran;
     LIME_CHECK_ARG(bn <= bn_max && n_tiles <= 64, "lime_linear_bf16_tma: n=%d does not tile", n);
-    CUtensorMap amap, wmap, amap2, wmap2, cmap, rmap;
+    LIME_CHECK_ARG(c_is_bf16 != 2 || tma_epi, "lime_linear_x3_pairs_tma: the pair output needs 16-byte aligned rows (ld16 a multiple of 8)");
+    CUtensorMap amap, wmap, amap2, wmap2, cmap, cmap2, rmap;
     if (int rc = tensor_map_bf16_2d(&amap, A, (uint64_t)k, (uint64_t)m, (uint64_t)lda, GT_M)) return rc;
     if (int rc = tensor_map_bf16_2d(&wmap, W, (uint64_t)k, (uint64_t)n, (uint64_t)ldw, (uint32_t)bn)) return rc;
     amap2 = amap;
@@ -590,11 +641,17 @@ static int linear_tma_launch(const void *A, const void *A2, int64_t lda, const v
         if (int rc = tensor_map_bf16_2d(&wmap2, W2, (uint64_t)k, (uint64_t)n, (uint64_t)ldw, (uint32_t)bn)) return rc;
     }
     cmap = amap;
+    cmap2 = amap;
     rmap = amap;
     if (tma_epi) {
         if (int rc = tensor_map_2d(&cmap, c_is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, esz, C, (uint64_t)ncov,
                                    (uint64_t)m, (uint64_t)ldc, c_is_bf16 ? 64 : 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))
             return rc;
+        cmap2 = cmap;
+        if (c_is_bf16 == 2)
+            if (int rc = tensor_map_2d(&cmap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C2, (uint64_t)ncov, (uint64_t)m, (uint64_t)ldc, 64, 32,
+                                       CU_TENSOR_MAP_SWIZZLE_128B))
+                return rc;
         if (residual != nullptr)
             if (int rc = tensor_map_2d(&rmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, residual, (uint64_t)n, (uint64_t)m, (uint64_t)ldr, 32, 32,
                                        CU_TENSOR_MAP_SWIZZLE_128B))
@@ -605,7 +662,7 @@ static int linear_tma_launch(const void *A, const void *A2, int64_t lda, const v
     int groups = num_sms() / n_tiles;
     if (groups < 1) groups = 1;
     if (groups > m_tiles) groups = (int)m_tiles;
-    gemm_tma_kernel<<<groups * n_tiles, GT_THREADS, GT_SMEM, as_stream(stream)>>>(amap, wmap, amap2, wmap2, x3, cmap, rmap, tma_epi ? 1 : 0, ncov, bias, residual, ldr,
+    gemm_tma_kernel<<<groups * n_tiles, GT_THREADS, GT_SMEM, as_stream(stream)>>>(amap, wmap, amap2, wmap2, x3, cmap, cmap2, out_scale, rmap, tma_epi ? 1 : 0, ncov, bias, residual, ldr,
                                                                                     C, ldc, c_is_bf16, m, n, nkb, bn, n_tiles, act, alpha, ab_is_fp16);
     LIME_LAUNCH_CHECK("gemm_tma_kernel");
     return 0;
@@ -625,6 +682,15 @@ extern "C" int lime_linear_x3_tma(const void *Ahi, const void *Alo, int64_t lda,
                                   int64_t m, int32_t n, int32_t k, int32_t act, float alpha, int32_t ab_is_fp16, void *stream) {
     LIME_CHECK_ARG(Alo && Wlo, "lime_linear_x3_tma: null argument");
     return linear_tma_launch(Ahi, Alo, lda, Whi, Wlo, ldw, bias, residual, ldr, C, ldc, 0, m, n, k, act, alpha, ab_is_fp16, stream);
+}
+
+// ... with the result leaving as the NEXT x3 layer's operand pair: out_scale * act(alpha (...) + bias) = hi + lo (fp16, each [m, ld16],
+// columns n..ld16-1 zero) instead of an fp32 matrix that a lime_split_bf16_pairs pass would re-read (the FFN hidden layer).
+extern "C" int lime_linear_x3_pairs_tma(const void *Ahi, const void *Alo, int64_t lda, const void *Whi, const void *Wlo, int64_t ldw,
+                                        const float *bias, void *Chi, void *Clo, int64_t ld16, float out_scale,
+                                        int64_t m, int32_t n, int32_t k, int32_t act, float alpha, int32_t ab_is_fp16, void *stream) {
+    LIME_CHECK_ARG(Alo && Wlo && Chi && Clo, "lime_linear_x3_pairs_tma: null argument");
+    return linear_tma_launch(Ahi, Alo, lda, Whi, Wlo, ldw, bias, nullptr, 0, Chi, ld16, 2, m, n, k, act, alpha, ab_is_fp16, stream, Clo, out_scale);
 }
 
 // dW = dZ^T . X on bf16 images (see gemm_tn_tma_kernel): C[m, n] (+)= alpha * sum_{r < k} A[r, i] * B[r, j]

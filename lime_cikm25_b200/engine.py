@@ -211,10 +211,14 @@ class NewsEncoderEngine:
         del ch, cl
         x1 = ctx                                                                 # reuse ctx
         xh, xl = ops.layernorm_pairs(y, W["n1_w"], W["n1_b"], x1, sa, eps=W["eps1"])   # fp32 residual stream + the FFN-1 operand pair
-        hf = ops.linear_x3(xh, xl, W["l1_w_hi"], W["l1_w_lo"], W["l1_b"], act=ops.ACT_RELU, alpha=al)
-        del xh, xl
-        hh, hl = ops.split16(hf, scale=sa)
-        del hf
+        if ops.X3_FUSED:            # the FFN hidden layer leaves its GEMM as FFN-2's operand pair
+            hh, hl = ops.linear_x3_pairs(xh, xl, W["l1_w_hi"], W["l1_w_lo"], W["l1_b"], act=ops.ACT_RELU, alpha=al, out_scale=sa)
+            del xh, xl
+        else:
+            hf = ops.linear_x3(xh, xl, W["l1_w_hi"], W["l1_w_lo"], W["l1_b"], act=ops.ACT_RELU, alpha=al)
+            del xh, xl
+            hh, hl = ops.split16(hf, scale=sa)
+            del hf
         y2 = ops.linear_x3(hh, hl, W["l2_w_hi"], W["l2_w_lo"], W["l2_b"], residual=x1, out=y, alpha=al)
         ops.layernorm_meanpool(y2, W["n2_w"], W["n2_b"], feat, n, T, eps=W["eps2"])
 

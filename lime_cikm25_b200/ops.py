@@ -179,6 +179,26 @@ def linear_x3(xh, xl, wh, wl, bias=None, residual=None, act=ACT_NONE, out=None, 
     return out
 
 
+def linear_x3_pairs(xh, xl, wh, wl, bias=None, act=ACT_NONE, n=None, alpha=1.0, out_scale=1.0):
+    """linear_x3 whose result leaves as the next x3 layer's fp16 operand pair: out_scale * act(alpha x . w^T + bias) = hi + lo, each
+    [m, kp] (kp = n padded to a multiple of 64, padding columns zero) -- lime_linear_x3_pairs_tma, one launch, k <= 512."""
+    lib = _lib.require_device()
+    m, kp_in = xh.shape
+    n = wh.shape[0] if n is None else n
+    kp = (n + 63) // 64 * 64
+    hi = torch.empty(m, kp, dtype=torch.float16, device=xh.device)
+    lo = torch.empty(m, kp, dtype=torch.float16, device=xh.device)
+    if not (xh.dtype == xl.dtype == wh.dtype == wl.dtype == torch.float16):
+        raise TypeError("operand pairs must be float16")
+    lda, ldw = _rowmajor(xh, "xh"), _rowmajor(wh, "wh")
+    if _rowmajor(xl, "xl") != lda or _rowmajor(wl, "wl") != ldw or xl.shape != xh.shape or wl.shape != wh.shape:
+        raise ValueError("hi / lo images must share shape and row pitch")
+    check(lib.lime_linear_x3_pairs_tma(xh.data_ptr(), xl.data_ptr(), lda, wh.data_ptr(), wl.data_ptr(), ldw,
+                                       _ptr(bias, torch.float32, "bias"), hi.data_ptr(), lo.data_ptr(), kp, float(out_scale),
+                                       m, n, kp_in, act, float(alpha), 1, _stream()), "lime_linear_x3_pairs_tma")
+    return hi, lo
+
+
 def embed_pe_bf16(E, ids, T, pe, out, out16):
     lib = _lib.require_device()
     check(lib.lime_embed_pe_bf16(_ptr(E, torch.float32, "E"), E.shape[0], _ptr(ids, torch.int32, "ids"), ids.numel(), T,

@@ -211,6 +211,24 @@ def test_embed_pe_and_mha(lib, T):
     close(ctx3.view(n, T, d), (att @ v).transpose(1, 2).reshape(n, T, d), 1e-5)
 
 
+@pytest.mark.parametrize("m,n,k", [(1000, 512, 300), (333, 200, 320), (128, 64, 512)])
+def test_linear_x3_pairs_match_split16(lib, m, n, k):
+    """lime_linear_x3_pairs_tma: the operand pair written by the GEMM's epilogue is, bit for bit, lime_split_bf16_pairs of the fp32
+    result of lime_linear_x3_tma (same accumulators, same scale-then-split arithmetic); padding columns zero."""
+    a, w, b = randn(m, k, seed=31), randn(n, k, seed=32, scale=k ** -0.5), randn(n, seed=33)
+    sa, sw = ops.X3_ACT_SCALE, ops.X3_W_SCALE
+    ah, al = ops.split16(a, scale=sa)
+    wh, wl = ops.split16(w, scale=sw)
+    for act in (ops.ACT_RELU, ops.ACT_NONE):
+        if act == ops.ACT_NONE and k > ops.X3_FUSED_MAX_K:
+            continue          # linear_x3 accumulates such a contraction in 320-column slices (another summation order)
+        z = ops.linear_x3(ah, al, wh, wl, b, act=act, alpha=1.0 / (sa * sw))
+        want_hi, want_lo = ops.split16(z, scale=sa)
+        hi, lo = ops.linear_x3_pairs(ah, al, wh, wl, b, act=act, alpha=1.0 / (sa * sw), out_scale=sa)
+        assert hi.shape == want_hi.shape and torch.equal(hi, want_hi) and torch.equal(lo, want_lo)
+        assert float(hi[:, n:].float().abs().sum()) == 0 and float(lo[:, n:].float().abs().sum()) == 0
+
+
 def test_pair_producers_match_split16(lib):
     """fp32x3 mode: embed_pe_pairs / layernorm_pairs write the same fp32 rows as their plain twins and the same fp16 operand pair
     (bit for bit) as lime_split_bf16_pairs of those rows."""
