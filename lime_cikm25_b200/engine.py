@@ -76,7 +76,7 @@ class NewsEncoderEngine:
         self._prep = None
         self._fp = None
         self.bf16 = False        # "bf16 mode": bf16 activations, the 4 transformer GEMMs by TMA + tcgen05 (lime_linear_bf16_tma)
-        self.x3 = False          # "fp32x3 mode" (opt-in; default = the fp32 FFMA kernels, the strict-parity mode): fp32 activations, every transformer GEMM as 3 bf16 tensor-core passes on hi / lo pairs
+        self.x3 = False          # "fp32x3 mode" (opt-in; default = the fp32 FFMA kernels, the strict-parity mode): fp32 residual stream, every dense layer on the tensor cores over fp16 hi / lo pairs
         self.x3_mha = True       # fp32x3 mode: attention core on the tensor cores too (lime_mha_x3, fp16 hi / lo pairs); False = the FFMA core
         self.x3_small = True     # tensor-core modes: intent layers, intent-attention affine and the content projection as fp32x3 passes (False = FFMA lime_linear)
 
@@ -188,8 +188,9 @@ class NewsEncoderEngine:
         ops.layernorm_meanpool(y2, W["n2_w"], W["n2_b"], feat, n, T, eps=W["eps2"])
 
     def _branch_x3(self, ids, T, W, pe, feat):
-        """The same branch in the fp32x3 mode: every transformer GEMM as three accumulating bf16 tensor-core passes on hi / lo
-        operand pairs (ops.linear_x3, ~2^-16 relative per product: fp32-level accuracy), activations fp32 throughout."""
+        """The same branch in the fp32x3 mode: every dense layer on the tensor cores over fp16 hi / lo operand pairs (ops.linear_x3,
+        2^-21 relative per product: fp32-level accuracy), attention on mma.sync hi / lo pairs; the residual stream stays fp32 and
+        every producer (embedding, attention, LayerNorm, FFN-1) writes the next layer's operand pair itself."""
         base = self.m.base_news_encoder
         n = ids.shape[0]
         rows = n * T

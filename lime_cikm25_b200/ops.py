@@ -143,9 +143,10 @@ def cast_bf16_colsum(x, kp=None):
 
 def linear_x3(xh, xl, wh, wl, bias=None, residual=None, act=ACT_NONE, out=None, n=None, alpha=1.0):
     """fp32-accurate dense layer on the tensor cores: out = act(alpha x . w^T + bias) + residual with x = xh + xl, w = wh + wl as
-    16-bit pairs (fp16: 2^-21 per product; alpha undoes their power-of-two scaling), three accumulating lime_linear_bf16_tma
-    passes (xh.wh [+ residual], + xl.wh, + xh.wl + bias then act).  With an activation the residual must be None (the
-    accumulating passes add BEFORE the activation)."""
+    16-bit pairs (fp16: 2^-21 per product; alpha undoes their power-of-two scaling).  X3_FUSED (default): ONE
+    lime_linear_x3_tma launch per <= 320-column slice of the contraction (small products and hi.hi in two TMEM accumulators; a
+    layer with an activation is one launch up to k = 512); otherwise three accumulating lime_linear_bf16_tma passes (xh.wh
+    [+ residual], + xl.wh, + xh.wl + bias then act).  With an activation the residual must be None."""
     assert act == ACT_NONE or residual is None
     n = wh.shape[0] if n is None else n
     kp = xh.shape[1]
